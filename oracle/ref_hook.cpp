@@ -1,0 +1,228 @@
+/* oracle/ref_hook.cpp -- TEST INFRASTRUCTURE ONLY (never linked into the product).
+ *
+ * In-process hook around the UNMODIFIED reference objects (compiled from /root/reference/src
+ * by oracle/Makefile, pindel.cpp with -Dmain=pindel_reference_main).  It lets tests and the
+ * CPU-baseline leg of bench.py call the reference's own seam functions on batches of reads:
+ *
+ *     GetCloseEnd(chrSeq, read)              src/pindel.h:523   (src/pindel.cpp:2531)
+ *     CleanUniquePoints(read.UP_Close)       src/pindel.cpp:2904 (as reader.cpp:272 / :1541 do)
+ *     SearchFarEnds(chrSeq, reads, chr)      src/pindel.h:741   (src/pindel.cpp:1115)
+ *
+ * and read back every UniquePoint they produce.  Nothing here restates the algorithm; it only
+ * marshals plain C arrays into SPLIT_READ objects and back.
+ */
+#include "pindel.h"
+#include "control_state.h"
+#include "bddata.h"
+#include "reader.h"
+#include "searcher.h"
+#include "user_defined_settings.h"
+#include "logstream.h"
+
+#include <chrono>
+#include <cstdint>
+#include <cstring>
+#include <omp.h>
+#include <string>
+#include <vector>
+
+extern void init(int argc, char *argv[], ControlState &currentState);
+extern void CleanUniquePoints(SortedUniquePoints &Input_UP);
+extern std::vector<unsigned int> g_maxMismatch;
+extern BDData g_bdData;
+extern UserDefinedSettings *userSettings;
+
+namespace {
+ControlState *g_state = NULL;
+std::vector<std::string> g_argv_store;
+
+int chrIdOf(const Chromosome *c)
+{
+   for (unsigned i = 0;; i++) {
+      const Chromosome *k = g_genome.getChr(i);
+      if (k == NULL) return -1;
+      if (k == c) return (int)i;
+   }
+}
+
+void pushUP(std::vector<int32_t> &out, const UniquePoint &up)
+{
+   out.push_back(up.LengthStr);
+   out.push_back((int32_t)up.AbsLoc);
+   out.push_back(up.Direction == FORWARD ? 0 : 1);
+   out.push_back(up.Strand == SENSE ? 0 : 1);
+   out.push_back(up.Mismatches);
+   out.push_back(chrIdOf(up.chromosome_p));
+}
+} // namespace
+
+extern "C" {
+
+/* argv: pindel command line WITHOUT argv[0]; must carry -f <fasta> -p <pindel text file> -o <prefix>. */
+int pgref_init(int argc, const char **argv)
+{
+   if (g_state != NULL) return -1; // the reference keeps process-global state; one init per process
+   userSettings = UserDefinedSettings::Instance();
+   g_state = new ControlState();
+   g_argv_store.clear();
+   g_argv_store.push_back("pindel_ref_hook");
+   for (int i = 0; i < argc; i++) g_argv_store.push_back(argv[i]);
+   std::vector<char *> av;
+   for (size_t i = 0; i < g_argv_store.size(); i++) av.push_back(const_cast<char *>(g_argv_store[i].c_str()));
+   init((int)av.size(), &av[0], *g_state);
+   return 0;
+}
+
+int pgref_n_chr(void)
+{
+   int n = 0;
+   while (g_genome.getChr((unsigned)n) != NULL) n++;
+   return n;
+}
+const char *pgref_chr_name(int i) { return g_genome.getChr((unsigned)i)->getName().c_str(); }
+const char *pgref_chr_seq(int i) { return g_genome.getChr((unsigned)i)->getSeq().c_str(); }
+uint32_t pgref_chr_len(int i) { return g_genome.getChr((unsigned)i)->getCompSize(); }
+void pgref_max_mismatch(uint32_t *out, int n)
+{
+   for (int i = 0; i < n; i++) out[i] = (i < (int)g_maxMismatch.size()) ? g_maxMismatch[i] : 0;
+}
+int pgref_setting_int(const char *which)
+{
+   std::string w(which);
+   if (w == "ADDITIONAL_MISMATCH") return userSettings->ADDITIONAL_MISMATCH;
+   if (w == "Min_Perfect_Match_Around_BP") return userSettings->Min_Perfect_Match_Around_BP;
+   if (w == "MaxRangeIndex") return userSettings->MaxRangeIndex;
+   if (w == "minClose") return userSettings->minClose;
+   if (w == "numThreads") return userSettings->numThreads;
+   return -1;
+}
+double pgref_setting_double(const char *which)
+{
+   std::string w(which);
+   if (w == "MaximumAllowedMismatchRate") return userSettings->MaximumAllowedMismatchRate;
+   if (w == "Seq_Error_Rate") return userSettings->Seq_Error_Rate;
+   if (w == "sensitivity") return userSettings->sensitivity;
+   return -1.0;
+}
+
+/* Mirrors main()'s per-window g_bdData.loadRegion(currentWindow.makePindelCoordinateCopy())
+ * (src/pindel.cpp:1831,1853); start/end are biological (unpadded) coordinates. */
+int pgref_set_window(int chr, uint32_t start, uint32_t end)
+{
+   const Chromosome *c = g_genome.getChr((unsigned)chr);
+   if (c == NULL) return -1;
+   SearchWindow w(c, start, end);
+   g_bdData.loadRegion(w.makePindelCoordinateCopy());
+   return 0;
+}
+
+/* BAM-mode main() calls g_bdData.UpdateBD(currentState) before loadRegion (src/pindel.cpp:1841-1845); it is what
+ * moves the external (-b) BreakDancer events into the active event list.  With no discordant pairs loaded this
+ * activates exactly the -b events, which lets tests exercise the multi-region cluster pass of SearchFarEnd. */
+void pgref_update_bd(void) { g_bdData.UpdateBD(*g_state); }
+
+void pgref_free(void *p) { free(p); }
+
+/* Runs the reference on n reads (all anchored on chromosome chr, as in one Pindel window).
+ * mode bit0: close end (always), bit1: far end.  threads = OpenMP threads.
+ * Output: malloc'ed int32 stream, per read
+ *   [flip, L_after, n_close_raw, n_close_clean, n_far, n_cluster_regions,
+ *    close_raw UPs.., close_clean UPs.., far UPs.. (6 ints each: len, absLoc, dir, strand, mm, chr),
+ *    cluster regions.. (3 ints each: chr, start, end)]
+ * seconds[0] = wall time of the GetCloseEnd loop, seconds[1] = wall time of SearchFarEnds. */
+int64_t pgref_search(int n, const char *seq_blob, const uint32_t *seq_off, const char *matched_d,
+                     const uint32_t *rel_pos, const int16_t *insert_size, int chr, int mode, int threads,
+                     int32_t **out_stream, double *seconds)
+{
+   const Chromosome *c = g_genome.getChr((unsigned)chr);
+   if (c == NULL) return -1;
+   const std::string &chrSeq = c->getSeq();
+   omp_set_num_threads(threads > 0 ? threads : 1);
+
+   std::vector<SPLIT_READ> reads((size_t)n);
+   std::vector<std::string> original((size_t)n);
+   for (int i = 0; i < n; i++) {
+      SPLIT_READ &r = reads[i];
+      r.Name = "@r";
+      r.FragName = c->getName();
+      original[i].assign(seq_blob + seq_off[i], seq_off[i + 1] - seq_off[i]);
+      r.setUnmatchedSeq(original[i]);
+      r.MatchedD = matched_d[i];
+      r.MatchedRelPos = rel_pos[i];
+      r.MS = 60;
+      r.InsertSize = insert_size[i];
+      r.Tag = "S";
+   }
+   std::vector<SortedUniquePoints> rawClose((size_t)n);
+
+   std::chrono::steady_clock::time_point t0 = std::chrono::steady_clock::now();
+   #pragma omp parallel for schedule(dynamic, 64)
+   for (int i = 0; i < n; i++) {
+      GetCloseEnd(chrSeq, reads[i]);
+   }
+   std::chrono::steady_clock::time_point t1 = std::chrono::steady_clock::now();
+   for (int i = 0; i < n; i++) {
+      rawClose[i] = reads[i].UP_Close;
+      if (reads[i].UP_Close.size()) {
+         reads[i].Used = false;
+         reads[i].UniqueRead = true;
+         CleanUniquePoints(reads[i].UP_Close);
+      }
+   }
+   // the reference only forwards reads with a close end to SearchFarEnds (reader.cpp:262-288)
+   std::vector<SPLIT_READ> kept;
+   std::vector<int> keptIndex;
+   for (int i = 0; i < n; i++) {
+      if (reads[i].UP_Close.size()) {
+         kept.push_back(reads[i]);
+         keptIndex.push_back(i);
+      }
+   }
+   std::chrono::steady_clock::time_point t2 = std::chrono::steady_clock::now(), t3 = t2;
+   if (mode & 2) {
+      std::ostream *savedLog = logStream;
+      t2 = std::chrono::steady_clock::now();
+      SearchFarEnds(chrSeq, kept, *c);
+      t3 = std::chrono::steady_clock::now();
+      logStream = savedLog;
+   }
+   if (seconds) {
+      seconds[0] = std::chrono::duration<double>(t1 - t0).count();
+      seconds[1] = std::chrono::duration<double>(t3 - t2).count();
+   }
+
+   std::vector<int32_t> out;
+   out.reserve((size_t)n * 64);
+   size_t k = 0;
+   for (int i = 0; i < n; i++) {
+      const SPLIT_READ *r = &reads[i];
+      bool isKept = (k < keptIndex.size() && keptIndex[k] == i);
+      if (isKept) r = &kept[k];
+      out.push_back(r->getUnmatchedSeq() == original[i] ? 0 : 1);
+      out.push_back(r->getReadLength());
+      out.push_back((int32_t)rawClose[i].size());
+      out.push_back((int32_t)r->UP_Close.size());
+      out.push_back((int32_t)r->UP_Far.size());
+      size_t nRegionsSlot = out.size();
+      out.push_back(0);
+      for (unsigned j = 0; j < rawClose[i].size(); j++) pushUP(out, rawClose[i][j]);
+      for (unsigned j = 0; j < r->UP_Close.size(); j++) pushUP(out, r->UP_Close[j]);
+      for (unsigned j = 0; j < r->UP_Far.size(); j++) pushUP(out, r->UP_Far[j]);
+      if (isKept) {
+         const SearchWindowCluster &cl = g_bdData.getCorrespondingSearchWindowCluster(*r);
+         out[nRegionsSlot] = (int32_t)cl.size();
+         for (unsigned j = 0; j < cl.size(); j++) {
+            out.push_back(chrIdOf(cl[j].getChromosome()));
+            out.push_back((int32_t)cl[j].getStart());
+            out.push_back((int32_t)cl[j].getEnd());
+         }
+         k++;
+      }
+   }
+   int32_t *buf = (int32_t *)malloc(out.size() * sizeof(int32_t) + 4);
+   memcpy(buf, out.data(), out.size() * sizeof(int32_t));
+   *out_stream = buf;
+   return (int64_t)out.size();
+}
+
+} // extern "C"

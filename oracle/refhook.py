@@ -1,0 +1,154 @@
+"""oracle/refhook.py -- TEST INFRASTRUCTURE ONLY.
+
+ctypes wrapper around oracle/_ref/libpindel_ref.so: the UNMODIFIED reference objects (compiled
+from /root/reference/src by oracle/Makefile) plus oracle/ref_hook.cpp.  It runs the reference's
+own GetCloseEnd / CleanUniquePoints / SearchFarEnds (src/pindel.h:523,741) on a batch and returns
+every UniquePoint.  The reference keeps process-global state, so use one process per configuration
+(`run_in_subprocess`).  Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline /
+--impl reference legs may import this module.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import tempfile
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB = os.path.join(HERE, "_ref", "libpindel_ref.so")
+
+
+def available() -> bool:
+    return os.path.exists(LIB)
+
+
+def write_fasta(path: str, contigs) -> None:
+    """contigs: list of (name, uint8 ASCII array).  60 columns per line."""
+    with open(path, "wb") as f:
+        for name, seq in contigs:
+            f.write(b">" + name.encode() + b"\n")
+            n = seq.size
+            full = (n // 60) * 60
+            if full:
+                body = np.empty((full // 60, 61), dtype=np.uint8)
+                body[:, :60] = seq[:full].reshape(-1, 60)
+                body[:, 60] = 10
+                f.write(body.tobytes())
+            if n > full:
+                f.write(seq[full:].tobytes() + b"\n")
+
+
+class RefHook:
+    """One initialised reference instance (one per process)."""
+
+    def __init__(self, fasta: str, extra_args=(), workdir: str | None = None):
+        self.lib = C.CDLL(LIB)
+        L = self.lib
+        L.pgref_chr_name.restype = C.c_char_p
+        L.pgref_chr_seq.restype = C.c_void_p
+        L.pgref_chr_len.restype = C.c_uint32
+        L.pgref_setting_double.restype = C.c_double
+        L.pgref_search.restype = C.c_int64
+        self.workdir = workdir or tempfile.mkdtemp(prefix="pgref_")
+        dummy = os.path.join(self.workdir, "empty_reads.txt")
+        open(dummy, "w").close()
+        args = ["-f", fasta, "-p", dummy, "-o", os.path.join(self.workdir, "out")] + [str(a) for a in extra_args]
+        arr = (C.c_char_p * len(args))(*[a.encode() for a in args])
+        # the reference prints progress on stdout; keep the test output clean
+        devnull = os.open(os.devnull, os.O_WRONLY)
+        saved = os.dup(1)
+        os.dup2(devnull, 1)
+        try:
+            rc = L.pgref_init(len(args), arr)
+        finally:
+            os.dup2(saved, 1)
+            os.close(saved)
+            os.close(devnull)
+        if rc != 0:
+            raise RuntimeError("pgref_init failed")
+        self.n_chr = L.pgref_n_chr()
+
+    def chr_name(self, i: int) -> str:
+        return self.lib.pgref_chr_name(i).decode()
+
+    def chr_seq(self, i: int) -> np.ndarray:
+        """The padded in-memory chromosome string (src/pindel.cpp:305-309) as a uint8 array (copy)."""
+        n = self.lib.pgref_chr_len(i)
+        ptr = self.lib.pgref_chr_seq(i)
+        return np.ctypeslib.as_array(C.cast(ptr, C.POINTER(C.c_uint8)), shape=(n,)).copy()
+
+    def max_mismatch(self) -> np.ndarray:
+        out = np.zeros(500, dtype=np.uint32)
+        self.lib.pgref_max_mismatch(out.ctypes.data_as(C.c_void_p), 500)
+        return out
+
+    def setting_int(self, name: str) -> int:
+        return self.lib.pgref_setting_int(name.encode())
+
+    def setting_double(self, name: str) -> float:
+        return self.lib.pgref_setting_double(name.encode())
+
+    def update_bd(self) -> None:
+        """Activate the -b BreakDancer events (BDData::UpdateBD, src/bddata.cpp:646)."""
+        devnull = os.open(os.devnull, os.O_WRONLY)
+        saved = os.dup(1)
+        os.dup2(devnull, 1)
+        try:
+            self.lib.pgref_update_bd()
+        finally:
+            os.dup2(saved, 1)
+            os.close(saved)
+            os.close(devnull)
+
+    def set_window(self, chr_id: int, start: int, end: int) -> None:
+        if self.lib.pgref_set_window(chr_id, C.c_uint32(start), C.c_uint32(end)) != 0:
+            raise RuntimeError("pgref_set_window failed")
+
+    def search(self, seq_blob, seq_off, matched_d, rel_pos, insert_size, chr_id=0, far=True, threads=1):
+        """Returns (stream int32 array, (close_seconds, far_seconds)).  See parse_stream()."""
+        n = len(seq_off) - 1
+        seq_blob = np.ascontiguousarray(seq_blob, dtype=np.uint8)
+        seq_off = np.ascontiguousarray(seq_off, dtype=np.uint32)
+        matched_d = np.ascontiguousarray(matched_d, dtype=np.uint8)
+        rel_pos = np.ascontiguousarray(rel_pos, dtype=np.uint32)
+        insert_size = np.ascontiguousarray(insert_size, dtype=np.int16)
+        out = C.POINTER(C.c_int32)()
+        secs = (C.c_double * 2)()
+        devnull = os.open(os.devnull, os.O_WRONLY)
+        saved = os.dup(1)
+        os.dup2(devnull, 1)
+        try:
+            ln = self.lib.pgref_search(n, seq_blob.ctypes.data_as(C.c_void_p), seq_off.ctypes.data_as(C.c_void_p),
+                                       matched_d.ctypes.data_as(C.c_void_p), rel_pos.ctypes.data_as(C.c_void_p),
+                                       insert_size.ctypes.data_as(C.c_void_p), chr_id, 3 if far else 1, threads,
+                                       C.byref(out), secs)
+        finally:
+            os.dup2(saved, 1)
+            os.close(saved)
+            os.close(devnull)
+        if ln < 0:
+            raise RuntimeError("pgref_search failed")
+        stream = np.ctypeslib.as_array(out, shape=(ln,)).copy()
+        self.lib.pgref_free(out)
+        return stream, (secs[0], secs[1])
+
+
+def parse_stream(stream: np.ndarray, n: int):
+    """-> list of dicts {flip, L, close_raw, close, far, regions}; UPs as int arrays [k,6]
+    (len, absLoc, dir 0=FORWARD/1=BACKWARD, strand 0=SENSE/1=ANTISENSE, mm, chr)."""
+    out = []
+    p = 0
+    s = stream
+    for _ in range(n):
+        flip, L, ncr, ncc, nf, nreg = (int(x) for x in s[p:p + 6])
+        p += 6
+        cr = s[p:p + 6 * ncr].reshape(ncr, 6).astype(np.int64); p += 6 * ncr
+        cc = s[p:p + 6 * ncc].reshape(ncc, 6).astype(np.int64); p += 6 * ncc
+        fa = s[p:p + 6 * nf].reshape(nf, 6).astype(np.int64); p += 6 * nf
+        rg = s[p:p + 3 * nreg].reshape(nreg, 3).astype(np.int64); p += 3 * nreg
+        for a in (cr, cc, fa):
+            a[:, 1] &= 0xFFFFFFFF  # AbsLoc is unsigned in the reference
+        out.append(dict(flip=flip, L=L, close_raw=cr, close=cc, far=fa, regions=rg))
+    assert p == s.size
+    return out

@@ -1,0 +1,153 @@
+"""Synthetic references and anchored split-read batches (SURVEY.md section 8(d) read model).
+
+Everything here is deterministic given the seed (numpy PCG64), vectorised, and free of any
+dependency on /root/reference, so the same inputs can be regenerated on the GPU box, fed to
+the CUDA path, to the C oracle and (where it was built) to the reference hook library.
+
+Read model: a split read spans one planted breakpoint at an offset k in [20, L-20]; the anchor
+mate sits at the expected insert distance on either strand; `matched_rel_pos` follows the
+reference's build_record_SR convention (src/reader.cpp:857-866: leftmost position for '+'
+anchors, position + aligned length for '-' anchors); 1 % substitution errors, 0.1 % N,
+10 % non-split decoys that map end to end (they must be rejected by CheckMismatches,
+src/searcher.cpp:331-388).
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass
+
+import numpy as np
+
+SPACER = 100000  # g_SpacerBeforeAfter, src/pindel.h:122
+_ACGT = np.frombuffer(b"ACGT", dtype=np.uint8)
+_COMP = np.zeros(256, dtype=np.uint8)
+for _a, _b in zip(b"ACGTN", b"TGCAN"):
+    _COMP[_a] = _b
+_CODE = np.zeros(256, dtype=np.uint8)
+_CODE[ord("C")], _CODE[ord("G")], _CODE[ord("T")] = 1, 2, 3
+
+
+def make_reference(n_bases: int, seed: int, n_runs=()) -> np.ndarray:
+    """Uniform i.i.d. ACGT reference as a uint8 ASCII array (biological coordinates, unpadded).
+
+    n_runs: iterable of (start, length) stretches overwritten with 'N'."""
+    rng = np.random.Generator(np.random.PCG64(seed))
+    ref = _ACGT[rng.integers(0, 4, size=n_bases, dtype=np.uint8)]
+    for s, ln in n_runs:
+        ref[s:s + ln] = ord("N")
+    return ref
+
+
+def pad_reference(ref: np.ndarray) -> np.ndarray:
+    """The reference's in-memory chromosome: SPACER 'N' on both sides (src/pindel.cpp:305-309)."""
+    out = np.full(ref.size + 2 * SPACER, ord("N"), dtype=np.uint8)
+    out[SPACER:SPACER + ref.size] = ref
+    return out
+
+
+@dataclass
+class ReadBatch:
+    """SoA batch of anchored unmapped read-ends (the inputs of GetCloseEnd, src/pindel.h:523)."""
+    seq: np.ndarray            # uint8 [n, L] ASCII (UnmatchedSeq)
+    matched_d: np.ndarray      # uint8 [n]  '+' or '-'      (SPLIT_READ::MatchedD)
+    matched_rel_pos: np.ndarray  # uint32 [n]                (SPLIT_READ::MatchedRelPos)
+    insert_size: np.ndarray    # int16 [n]                   (SPLIT_READ::InsertSize)
+    kind: np.ndarray           # uint8 [n] 0=D 1=SI 2=INV 3=TD 4=decoy (generator's truth, not an input)
+
+    @property
+    def n(self) -> int:
+        return int(self.seq.shape[0])
+
+    @property
+    def read_len(self) -> int:
+        return int(self.seq.shape[1])
+
+    def slice(self, lo: int, hi: int) -> "ReadBatch":
+        return ReadBatch(self.seq[lo:hi], self.matched_d[lo:hi], self.matched_rel_pos[lo:hi],
+                         self.insert_size[lo:hi], self.kind[lo:hi])
+
+    def blob(self):
+        """(seq_blob bytes-like uint8 [n*L], seq_off uint32 [n+1]) as the C-ABI takes them."""
+        n, L = self.seq.shape
+        off = (np.arange(n + 1, dtype=np.uint64) * L).astype(np.uint32)
+        return np.ascontiguousarray(self.seq).reshape(-1), off
+
+    def to_pindel_text(self, chr_name: str, tag: str = "S") -> str:
+        """Pindel text records (src/pindel_read_reader.cpp:50-66)."""
+        lines = []
+        for i in range(self.n):
+            lines.append("@r%d" % i)
+            lines.append(self.seq[i].tobytes().decode())
+            lines.append("%s\t%s\t%d\t60\t%d\t%s" % (chr(self.matched_d[i]), chr_name,
+                                                     int(self.matched_rel_pos[i]), int(self.insert_size[i]), tag))
+        return "\n".join(lines) + "\n"
+
+
+def make_reads(ref: np.ndarray, n: int, read_len: int, seed: int, insert_size: int = 500,
+               mix=(0.60, 0.25, 0.05, 0.10), decoy_frac: float = 0.10, max_del: int = 1000,
+               sub_rate: float = 0.01, n_rate: float = 0.001, chunk: int = 1 << 18,
+               lo: int | None = None, hi: int | None = None) -> ReadBatch:
+    """n anchored split reads over `ref` (unpadded ASCII array); events planted in [lo, hi).
+
+    mix = fractions of (deletion, short insertion 1-50 bp, inversion >= 50 bp, tandem dup)
+    among the non-decoy reads; deletion sizes are log-uniform in [1, max_del]."""
+    L = read_len
+    G = ref.size
+    margin = 4 * insert_size + 3 * L + max_del + 4096
+    lo = margin if lo is None else max(lo, margin)
+    hi = G - margin if hi is None else min(hi, G - margin)
+    if hi <= lo:
+        raise ValueError("reference too small for the requested read model")
+    rng = np.random.Generator(np.random.PCG64(seed))
+    seqs = np.empty((n, L), dtype=np.uint8)
+    md = np.empty(n, dtype=np.uint8)
+    mpos = np.empty(n, dtype=np.uint32)
+    kinds = np.empty(n, dtype=np.uint8)
+    cum = np.cumsum(np.asarray(mix, dtype=np.float64))
+    cum /= cum[-1]
+    ar = np.arange(L, dtype=np.int64)[None, :]
+    for c0 in range(0, n, chunk):
+        m = min(chunk, n - c0)
+        u = rng.random(m)
+        kind = np.searchsorted(cum, rng.random(m), side="right").astype(np.uint8)
+        kind[u < decoy_frac] = 4
+        k = rng.integers(20, L - 20 + 1, size=m)              # bases before the breakpoint
+        a = rng.integers(lo, hi, size=m)                       # breakpoint: first segment is ref[a-k, a)
+        dsz = np.exp(rng.random(m) * np.log(max_del)).astype(np.int64)  # log-uniform 1..max_del
+        isz = rng.integers(1, 51, size=m)                      # short insertion length
+        vsz = rng.integers(50, max_del + 1, size=m)            # inversion / tandem-dup span
+        # Model geometry ('+' anchor: close end = first segment, read forward).  For '-' anchors the
+        # same model is laid out on the reverse-complement strand (coordinate x -> G-1-x), which
+        # yields a read whose close end is its last segment with the anchor to the right.
+        first = ar < k[:, None]
+        b = np.where(kind == 0, a + dsz, a)                    # deletion: skip dsz bases
+        b = np.where(kind == 3, a - vsz, b)                    # tandem dup: jump back to the segment start
+        b = np.where(kind == 2, a + vsz, b)                    # inversion: second part read backwards from a+vsz
+        j2 = ar - k[:, None]                                   # offset inside the second segment
+        ins = (kind == 1)
+        j2 = np.where(ins[:, None], j2 - isz[:, None], j2)     # insertion: second segment starts after isz bases
+        idx2 = np.where((kind == 2)[:, None], b[:, None] - 1 - j2, b[:, None] + j2)
+        idxm = np.where(first, a[:, None] - k[:, None] + ar, idx2)
+        inserted = ins[:, None] & (~first) & (j2 < 0)
+        idxm = np.clip(idxm, 0, G - 1)
+        plus = rng.random(m) < 0.5
+        t = np.where(plus[:, None], ref[idxm], _COMP[ref[G - 1 - idxm]])
+        inv2 = (kind == 2)[:, None] & (~first)
+        t = np.where(inv2, _COMP[t], t)
+        rnd_ins = _ACGT[rng.integers(0, 4, size=(m, L), dtype=np.uint8)]
+        t = np.where(inserted, rnd_ins, t)
+        # sequencing errors: substitutions to a different base, then sprinkled N
+        err = rng.random((m, L)) < sub_rate
+        shift = rng.integers(1, 4, size=(m, L), dtype=np.uint8)
+        sub = _ACGT[(_CODE[t] + shift) & 3]
+        t = np.where(err & (t != ord("N")), sub, t)
+        t = np.where(rng.random((m, L)) < n_rate, np.uint8(ord("N")), t)
+        slack = rng.integers(1, max(2, insert_size - L), size=m)
+        g_first = a - k                                        # model coordinate of the read's first base
+        pos_plus = g_first - slack                             # window [A, A+IS) must contain g_first
+        pos_minus = (G - 1 - g_first) + slack                  # window [A-IS, A) must contain the mirrored base
+        s_rc = _COMP[t[:, ::-1]]                               # UnmatchedSeq = RC(model read) on either strand
+        seqs[c0:c0 + m] = s_rc
+        md[c0:c0 + m] = np.where(plus, ord("+"), ord("-"))
+        mpos[c0:c0 + m] = np.where(plus, pos_plus, pos_minus).astype(np.uint32)
+        kinds[c0:c0 + m] = kind
+    return ReadBatch(seqs, md, mpos, np.full(n, insert_size, dtype=np.int16), kinds)
