@@ -1,0 +1,166 @@
+/* include/pindel_pg.h -- C ABI of the B200 pattern-growth split-read search (libpindel_pg.so).
+ *
+ * The reference (genome/pindel) has no plugin or FFI layer; the seam this library replaces is the pair
+ * of C++ functions that the reference calls inside its OpenMP loops (citations under /root/reference/):
+ *
+ *   void GetCloseEnd(const std::string& CurrentChrSeq, SPLIT_READ& read)          src/pindel.h:523
+ *        callers: ReadBuffer::flush  src/read_buffer.cpp:39-50 (BAM input, <= 50 000 reads per flush)
+ *                 ReadInRead         src/reader.cpp:248-256, 300-306 (Pindel-text input, 1000 per batch)
+ *   void SearchFarEnds(const std::string& chrSeq, std::vector<SPLIT_READ>& reads,
+ *                      const Chromosome& chr)                                      src/pindel.h:741
+ *        caller:  main               src/pindel.cpp:1888
+ *
+ * pg_close_end() is the batched GetCloseEnd, pg_far_end() the batched SearchFarEnds, pg_search() runs
+ * both back to back on the device.  Plain pointers and sizes only; the caller owns every host buffer,
+ * the library owns device memory and the packed reference.  There is no CPU fallback behind this ABI:
+ * every entry point fails with PG_ERR_CUDA when no usable device exists.
+ *
+ * Coordinates are the reference's: positions index the padded in-memory chromosome string
+ * (100 000 'N' before and after the sequence, src/pindel.cpp:305-309).
+ */
+#ifndef PINDEL_PG_H
+#define PINDEL_PG_H
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PG_OK 0
+#define PG_ERR_ARG 1        /* bad argument */
+#define PG_ERR_CUDA 2       /* CUDA runtime error (including "no device") */
+#define PG_ERR_STATE 3      /* call order (e.g. search before pg_set_reference) */
+#define PG_ERR_RUNS_CAP 4   /* caller's run buffer too small: results->n_runs holds the required size; call pg_download again */
+#define PG_ERR_UNSUPPORTED 5 /* a read is longer, or needs more mismatch levels, than the library supports */
+
+typedef struct pg_ctx pg_ctx;
+
+/* Pindel's command-line options that reach the search path (src/fn_parameters.cpp:17-351). */
+typedef struct pg_settings {
+   double seq_error_rate;        /* -e  Seq_Error_Rate              (default 0.01) */
+   double sensitivity;           /* -E  sensitivity                 (default 0.95) */
+   double max_mismatch_rate;     /* -u  MaximumAllowedMismatchRate  (default 0.02) */
+   int32_t additional_mismatch;  /* -a  ADDITIONAL_MISMATCH         (default 1, minimum 1: src/pindel.cpp:927-930) */
+   int32_t min_close;            /* -H  minClose / g_MinClose       (default 8) */
+   int32_t min_perfect_match;    /* -m  Min_Perfect_Match_Around_BP (default 3) */
+   int32_t max_range_index;      /* -x  MaxRangeIndex               (default 2, maximum 9: src/pindel.cpp:919-924) */
+   int32_t device;               /* CUDA device ordinal */
+   int32_t reserved;
+} pg_settings;
+
+/* One run of consecutive UniquePoints (src/pindel.h:137-158) found from the same seed with the same number of
+ * mismatches: LengthStr = len0 .. len0+count-1, AbsLoc = abs_loc0 +/- (LengthStr - len0) (+ FORWARD, - BACKWARD). */
+typedef struct pg_run {
+   uint32_t abs_loc0;
+   uint16_t len0;
+   uint16_t count;
+   uint8_t mm;          /* UniquePoint::Mismatches */
+   uint8_t dirstrand;   /* bit0: Direction 0 FORWARD '+' / 1 BACKWARD '-';  bit1: Strand 0 SENSE '+' / 1 ANTISENSE '-' */
+   int16_t chr;         /* index into the chromosomes given to pg_set_reference (UniquePoint::chromosome_p) */
+} pg_run;
+
+/* Expanded UniquePoint. */
+typedef struct pg_up {
+   uint32_t abs_loc;
+   int16_t len;
+   int16_t mm;
+   uint8_t dir;         /* 0 FORWARD, 1 BACKWARD */
+   uint8_t strand;      /* 0 SENSE, 1 ANTISENSE */
+   int16_t chr;
+} pg_up;
+
+#define PG_READ_FLIPPED 1u      /* UnmatchedSeq must be reverse-complemented on the host (GetCloseEnd mutates the read, src/pindel.cpp:2545) */
+#define PG_READ_UNSUPPORTED 2u  /* read not searched (see PG_ERR_UNSUPPORTED) */
+#define PG_READ_OVERFLOW 4u     /* internal: never visible after a successful call */
+
+typedef struct pg_read_out {
+   uint32_t run_off;        /* this read's runs: runs[run_off .. run_off + n_close_runs) = UP_Close (before CleanUniquePoints), */
+   uint16_t n_close_runs;   /*                   then n_far_runs runs = UP_Far */
+   uint16_t n_far_runs;
+   uint16_t len_after;      /* ReadLength after the search (setUnmatchedSeq strips trailing non-alphanumerics, src/pindel.cpp:142-169) */
+   uint16_t flags;          /* PG_READ_* */
+} pg_read_out;
+
+/* SearchWindow [start, end) on chromosome chr: one region of a BreakDancer search cluster
+ * (g_bdData.getCorrespondingSearchWindowCluster, src/bddata.cpp:949-967). */
+typedef struct pg_region {
+   int32_t chr;
+   uint32_t start, end;
+} pg_region;
+
+/* What SearchFarEnd needs to know about a read's close end when pg_far_end is called on its own. */
+typedef struct pg_close_info {
+   uint32_t last_abs_loc;   /* UP_Close.back().AbsLoc (getLastAbsLocCloseEnd, src/pindel.cpp:474-477) */
+   uint16_t max_len;        /* UP_Close.MaxLen(); 0 = no close end, the read is skipped */
+   uint16_t pad;
+} pg_close_info;
+
+/* A batch of anchored unmapped read-ends in SoA form (fields of SPLIT_READ, src/pindel.h:265-383). */
+typedef struct pg_reads {
+   int32_t n;
+   const char *seq_blob;            /* UnmatchedSeq of every read, concatenated (ASCII) */
+   const uint32_t *seq_off;         /* [n+1] offsets into seq_blob */
+   const char *matched_d;           /* [n] MatchedD '+' / '-'            (pg_far_end: may be NULL) */
+   const uint32_t *matched_rel_pos; /* [n] MatchedRelPos                 (pg_far_end: may be NULL) */
+   const int16_t *insert_size;      /* [n] InsertSize                    (pg_far_end: may be NULL) */
+   const int32_t *chr_id;           /* [n] chromosome of the anchor (FragName); NULL = all on chromosome 0 */
+   const pg_close_info *close_info; /* [n] pg_far_end only */
+   const pg_region *regions;        /* BreakDancer clusters of all reads, concatenated; NULL = none */
+   const uint32_t *region_off;      /* [n+1] offsets into regions; NULL = none */
+} pg_reads;
+
+typedef struct pg_results {
+   pg_read_out *out;        /* [n], caller-allocated */
+   pg_run *runs;            /* [runs_cap], caller-allocated */
+   uint32_t runs_cap;
+   uint32_t n_runs;         /* out: runs written (or required, with PG_ERR_RUNS_CAP) */
+} pg_results;
+
+void pg_default_settings(pg_settings *s);
+pg_ctx *pg_create(const pg_settings *s);          /* NULL on failure: see pg_create_error() */
+const char *pg_create_error(void);
+void pg_destroy(pg_ctx *ctx);
+const char *pg_last_error(pg_ctx *ctx);
+
+/* Use an existing CUDA stream (a cudaStream_t) for every copy and launch; NULL = the library's own stream. */
+int pg_set_stream(pg_ctx *ctx, void *cuda_stream);
+
+/* Chromosome strings exactly as the reference holds them in memory (Genome::loadChromosome, src/pindel.cpp:270-312):
+ * upper-case, non-ACGT as 'N', padded with 100 000 'N' on both sides.  The library packs them to 2 bits per base
+ * (+ a 1-bit N plane) on the device; the host strings are not referenced after the call returns. */
+int pg_set_reference(pg_ctx *ctx, int32_t n_chr, const char *const *seq, const uint32_t *len);
+
+/* g_maxMismatch as derived from -e/-E (createProbTable, src/pindel.cpp:781-819); out has 500 entries. */
+int pg_max_mismatch_table(pg_ctx *ctx, uint32_t *out);
+
+/* The reference seam, batched (host buffers in, host buffers out; copies are inside the call). */
+int pg_close_end(pg_ctx *ctx, const pg_reads *in, pg_results *res);   /* GetCloseEnd   for every read */
+int pg_far_end(pg_ctx *ctx, const pg_reads *in, pg_results *res);     /* SearchFarEnd  for every read with a close end */
+int pg_search(pg_ctx *ctx, const pg_reads *in, pg_results *res);      /* both, without BreakDancer clusters unless given up front */
+
+/* The same, split into its asynchronous steps (for callers that keep batches resident or overlap batches):
+ * pg_upload copies a batch to the device, pg_launch runs mode (1 close, 2 far, 3 both) on the resident batch,
+ * pg_download waits and copies the results back.  pg_launch may be repeated on the same resident batch. */
+int pg_upload(pg_ctx *ctx, const pg_reads *in);
+int pg_launch(pg_ctx *ctx, int32_t mode);
+int pg_download(pg_ctx *ctx, pg_results *res);
+int pg_sync(pg_ctx *ctx);
+
+/* Bookkeeping the benchmarks report. */
+uint64_t pg_kernel_launches(pg_ctx *ctx);      /* search-kernel launches since pg_create */
+uint32_t pg_last_run_count(pg_ctx *ctx);       /* runs produced by the last completed launch (valid after pg_sync/pg_download) */
+
+/* Pinned host memory for batch buffers (optional; any host pointer is accepted by the calls above). */
+void *pg_host_alloc(size_t bytes);
+void pg_host_free(void *p);
+
+/* Host helpers: expand runs to UniquePoints (returns the count; out may be NULL to just count), and
+ * CleanUniquePoints (src/pindel.cpp:2904-2941) in place (returns the new count). */
+uint32_t pg_expand_runs(const pg_run *runs, uint32_t n_runs, pg_up *out);
+uint32_t pg_clean_unique_points(pg_up *ups, uint32_t n);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,226 @@
+"""Host-side mirror of the reference's search seam on top of libpindel_pg.so (ctypes over the C ABI).
+
+Names follow the reference: `get_close_end` is the batched GetCloseEnd (src/pindel.h:523), `search_far_ends`
+the batched SearchFarEnds (src/pindel.h:741), `search` runs both on the device.  This module contains no
+search logic: if the CUDA library is missing or no device is present it raises -- there is no CPU path.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+from . import runs as R
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "libpindel_pg.so")
+
+PG_OK, PG_ERR_ARG, PG_ERR_CUDA, PG_ERR_STATE, PG_ERR_RUNS_CAP, PG_ERR_UNSUPPORTED = range(6)
+
+
+class Settings(C.Structure):
+    _fields_ = [("seq_error_rate", C.c_double), ("sensitivity", C.c_double), ("max_mismatch_rate", C.c_double),
+                ("additional_mismatch", C.c_int32), ("min_close", C.c_int32), ("min_perfect_match", C.c_int32),
+                ("max_range_index", C.c_int32), ("device", C.c_int32), ("reserved", C.c_int32)]
+
+
+class _Reads(C.Structure):
+    _fields_ = [("n", C.c_int32), ("seq_blob", C.c_void_p), ("seq_off", C.c_void_p), ("matched_d", C.c_void_p),
+                ("matched_rel_pos", C.c_void_p), ("insert_size", C.c_void_p), ("chr_id", C.c_void_p),
+                ("close_info", C.c_void_p), ("regions", C.c_void_p), ("region_off", C.c_void_p)]
+
+
+class _Results(C.Structure):
+    _fields_ = [("out", C.c_void_p), ("runs", C.c_void_p), ("runs_cap", C.c_uint32), ("n_runs", C.c_uint32)]
+
+
+class PgError(RuntimeError):
+    pass
+
+
+_lib = None
+
+
+def load_library() -> C.CDLL:
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise PgError("libpindel_pg.so is not built (run `python -m pindel_b200.build`); there is no CPU fallback")
+        lib = C.CDLL(LIB_PATH)
+        lib.pg_create.restype = C.c_void_p
+        lib.pg_create.argtypes = [C.POINTER(Settings)]
+        lib.pg_create_error.restype = C.c_char_p
+        lib.pg_last_error.restype = C.c_char_p
+        lib.pg_last_error.argtypes = [C.c_void_p]
+        lib.pg_destroy.argtypes = [C.c_void_p]
+        lib.pg_kernel_launches.restype = C.c_uint64
+        lib.pg_kernel_launches.argtypes = [C.c_void_p]
+        lib.pg_last_run_count.restype = C.c_uint32
+        lib.pg_last_run_count.argtypes = [C.c_void_p]
+        lib.pg_host_alloc.restype = C.c_void_p
+        lib.pg_host_alloc.argtypes = [C.c_size_t]
+        lib.pg_host_free.argtypes = [C.c_void_p]
+        for f in ("pg_set_stream", "pg_max_mismatch_table"):
+            getattr(lib, f).argtypes = [C.c_void_p, C.c_void_p]
+        lib.pg_set_reference.argtypes = [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p]
+        for f in ("pg_close_end", "pg_far_end", "pg_search"):
+            getattr(lib, f).argtypes = [C.c_void_p, C.POINTER(_Reads), C.POINTER(_Results)]
+        lib.pg_upload.argtypes = [C.c_void_p, C.POINTER(_Reads)]
+        lib.pg_launch.argtypes = [C.c_void_p, C.c_int32]
+        lib.pg_download.argtypes = [C.c_void_p, C.POINTER(_Results)]
+        lib.pg_sync.argtypes = [C.c_void_p]
+        _lib = lib
+    return _lib
+
+
+def pinned_empty(n: int, dtype) -> np.ndarray:
+    """numpy array backed by pinned host memory (pg_host_alloc); freed when the array is collected."""
+    lib = load_library()
+    dt = np.dtype(dtype)
+    nbytes = max(1, n * dt.itemsize)
+    p = lib.pg_host_alloc(nbytes)
+    if not p:
+        raise PgError("pg_host_alloc failed")
+    buf = (C.c_uint8 * nbytes).from_address(p)
+    arr = np.frombuffer(buf, dtype=dt, count=n)
+    _PINNED[id(buf)] = (buf, p)
+    import weakref
+    weakref.finalize(arr, _free_pinned, id(buf))
+    return arr
+
+
+_PINNED = {}
+
+
+def _free_pinned(key):
+    ent = _PINNED.pop(key, None)
+    if ent and _lib is not None:
+        _lib.pg_host_free(ent[1])
+
+
+class PatternGrowth:
+    """One search context on one GPU (pg_ctx)."""
+
+    def __init__(self, device: int = 0, **settings):
+        self.lib = load_library()
+        s = Settings()
+        self.lib.pg_default_settings(C.byref(s))
+        s.device = device
+        for k, v in settings.items():
+            if not hasattr(s, k):
+                raise TypeError("unknown setting %r" % k)
+            setattr(s, k, v)
+        self.settings = s
+        self.ctx = self.lib.pg_create(C.byref(s))
+        if not self.ctx:
+            raise PgError("pg_create: " + self.lib.pg_create_error().decode())
+        self._keep = []
+        self._n = 0
+
+    def close(self):
+        if getattr(self, "ctx", None):
+            self.lib.pg_destroy(self.ctx)
+            self.ctx = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, rc, what):
+        if rc != PG_OK:
+            raise PgError("%s failed (%d): %s" % (what, rc, self.lib.pg_last_error(self.ctx).decode()))
+
+    def set_stream(self, cuda_stream_handle: int):
+        self._check(self.lib.pg_set_stream(self.ctx, C.c_void_p(cuda_stream_handle)), "pg_set_stream")
+
+    def max_mismatch_table(self) -> np.ndarray:
+        out = np.zeros(500, dtype=np.uint32)
+        self._check(self.lib.pg_max_mismatch_table(self.ctx, out.ctypes.data_as(C.c_void_p)), "pg_max_mismatch_table")
+        return out
+
+    def set_reference(self, chr_seqs):
+        """chr_seqs: list of padded chromosome strings as uint8 ASCII arrays (or bytes)."""
+        arrs = [np.frombuffer(c, dtype=np.uint8) if isinstance(c, (bytes, bytearray)) else
+                np.ascontiguousarray(c, dtype=np.uint8) for c in chr_seqs]
+        ptrs = (C.c_void_p * len(arrs))(*[a.ctypes.data for a in arrs])
+        lens = np.array([a.size for a in arrs], dtype=np.uint32)
+        self._check(self.lib.pg_set_reference(self.ctx, len(arrs), ptrs, lens.ctypes.data_as(C.c_void_p)), "pg_set_reference")
+        self.n_chr = len(arrs)
+
+    # ---- batches -------------------------------------------------------------------------------
+    def _reads(self, seq_blob, seq_off, matched_d=None, matched_rel_pos=None, insert_size=None, chr_id=None,
+               close_info=None, regions=None, region_off=None):
+        def arr(a, dt):
+            return None if a is None else np.ascontiguousarray(a, dtype=dt)
+        keep = dict(seq_blob=arr(seq_blob, np.uint8), seq_off=arr(seq_off, np.uint32), matched_d=arr(matched_d, np.uint8),
+                    matched_rel_pos=arr(matched_rel_pos, np.uint32), insert_size=arr(insert_size, np.int16),
+                    chr_id=arr(chr_id, np.int32), close_info=arr(close_info, R.CLOSEINFO_DT),
+                    regions=arr(regions, R.REGION_DT), region_off=arr(region_off, np.uint32))
+        r = _Reads()
+        r.n = len(keep["seq_off"]) - 1
+        for k, v in keep.items():
+            setattr(r, k, None if v is None else v.ctypes.data)
+        return r, keep
+
+    def upload(self, **batch):
+        r, keep = self._reads(**batch)
+        self._keep = keep
+        self._n = r.n
+        self._check(self.lib.pg_upload(self.ctx, C.byref(r)), "pg_upload")
+
+    def launch(self, mode: int = 3):
+        self._check(self.lib.pg_launch(self.ctx, mode), "pg_launch")
+
+    def sync(self):
+        self._check(self.lib.pg_sync(self.ctx), "pg_sync")
+
+    def download(self, out=None, runs=None):
+        n = self._n
+        out = np.zeros(n, dtype=R.OUT_DT) if out is None else out
+        runs = np.zeros(max(1024, 24 * n), dtype=R.RUN_DT) if runs is None else runs
+        res = _Results(out.ctypes.data, runs.ctypes.data, runs.size, 0)
+        rc = self.lib.pg_download(self.ctx, C.byref(res))
+        if rc == PG_ERR_RUNS_CAP:
+            runs = np.zeros(res.n_runs, dtype=R.RUN_DT)
+            res = _Results(out.ctypes.data, runs.ctypes.data, runs.size, 0)
+            rc = self.lib.pg_download(self.ctx, C.byref(res))
+        self._check(rc, "pg_download")
+        return out, runs[:res.n_runs]
+
+    def _call(self, fn, what, **batch):
+        r, keep = self._reads(**batch)
+        n = r.n
+        self._n = n
+        out = np.zeros(n, dtype=R.OUT_DT)
+        runs = np.zeros(max(1024, 24 * n), dtype=R.RUN_DT)
+        res = _Results(out.ctypes.data, runs.ctypes.data, runs.size, 0)
+        rc = fn(self.ctx, C.byref(r), C.byref(res))
+        if rc == PG_ERR_RUNS_CAP:
+            runs = np.zeros(res.n_runs, dtype=R.RUN_DT)
+            res = _Results(out.ctypes.data, runs.ctypes.data, runs.size, 0)
+            rc = self.lib.pg_download(self.ctx, C.byref(res))
+        self._check(rc, what)
+        return out, runs[:res.n_runs]
+
+    def get_close_end(self, **batch):
+        """Batched GetCloseEnd (src/pindel.cpp:2531-2605): -> (out[n], runs); UP_Close before CleanUniquePoints."""
+        return self._call(self.lib.pg_close_end, "pg_close_end", **batch)
+
+    def search_far_ends(self, **batch):
+        """Batched SearchFarEnds (src/pindel.cpp:1115-1138); needs close_info, the post-flip sequences, optional clusters."""
+        return self._call(self.lib.pg_far_end, "pg_far_end", **batch)
+
+    def search(self, **batch):
+        """GetCloseEnd + SearchFarEnd per read, fused on the device."""
+        return self._call(self.lib.pg_search, "pg_search", **batch)
+
+    @property
+    def kernel_launches(self) -> int:
+        return int(self.lib.pg_kernel_launches(self.ctx))
+
+    @property
+    def last_run_count(self) -> int:
+        return int(self.lib.pg_last_run_count(self.ctx))

@@ -1,0 +1,722 @@
+// pindel_b200/csrc/pg_warp.cuh
+//
+// The warp program of the B200 pattern-growth search: ONE warp owns ONE anchored read and runs
+// the reference's whole per-read path on it --
+//   GetCloseEnd        src/pindel.cpp:2531-2605  (GetCloseEndInner :2250-2396,
+//                      CheckLeft_Close / CheckRight_Close src/searcher.cpp:153-197 / 247-286,
+//                      ExtendMatchClose :65-97, CategorizePositions :48-63)
+//   SearchFarEnd       src/pindel.cpp:1001-1074  (SearchFarEndAtPos src/farend_searcher.cpp:46-103,
+//                      CheckBoth src/pindel.cpp:2823-2902, ExtendMatch :2673-2725)
+//   CheckMismatches    src/searcher.cpp:331-388
+// -- re-formulated for SIMT instead of translated:
+//
+//  * The reference grows per-mismatch-level position vectors one read base at a time.  Those
+//    vectors are only ever consumed through their sizes and, when a size is 1, their single
+//    element.  For a seed p let D_t(p) be the read index of its (t+1)-th mismatch (L if none):
+//    p sits in a level <= t exactly for lengths len <= D_t(p).  So the number of candidates in
+//    levels <= t at length len is #{p : D_t(p) >= len}, and everything CheckLeft/Right_Close and
+//    CheckBoth test -- "first non-empty level", "exactly one candidate", "no competitor within
+//    ADDITIONAL_MISMATCH levels" -- is decided by the LARGEST and SECOND-LARGEST D_t over all
+//    seeds (plus which seed owns the largest), for each of the T = MAX+ADD+1 levels.
+//  * One lane per reference position: the 2-bit (bit-plane) packed window is staged in shared
+//    memory; a lane funnel-shifts its 32-base stretch out of two broadcast words, XORs it with
+//    the read's bit-planes, and pulls its first T mismatch offsets out of the mismatch mask with
+//    ffs -- no per-base loop, no dynamic memory, no recursion.  Lane-local top-2 keys are merged
+//    with redux.sync; seeds that match too well to be decided inside 32 bases (the true locus)
+//    are queued and finished cooperatively (lane c = 32-base chunk c, then lane t = level t).
+//  * A final lane-per-length pass replays the reference's control flow (in-range abort,
+//    uniqueness, minimum length, CheckMismatches) and emits run-length coded UniquePoints.
+//
+// The file is written against a tiny SIMT vocabulary (pg_lane, pg_ballot, pg_shfl, pg_redux_*,
+// pg_syncwarp ...) so that the very same code also compiles for the CPU lane emulator in
+// tests/emul/ (test infrastructure only: the shipped library contains the CUDA build alone).
+#pragma once
+#include <stdint.h>
+
+#ifndef PG_EMULATE
+#define PG_DEV __device__ __forceinline__
+#define PG_DEVNI __device__ __noinline__
+PG_DEV int pg_lane() { return (int)(threadIdx.x & 31); }
+PG_DEV uint32_t pg_ballot(bool p) { return __ballot_sync(0xffffffffu, p); }
+PG_DEV bool pg_any(bool p) { return __any_sync(0xffffffffu, p); }
+PG_DEV uint32_t pg_shfl(uint32_t v, int src) { return __shfl_sync(0xffffffffu, v, src); }
+PG_DEV uint32_t pg_redux_max(uint32_t v) { return __reduce_max_sync(0xffffffffu, v); }
+PG_DEV uint32_t pg_redux_add(uint32_t v) { return __reduce_add_sync(0xffffffffu, v); }
+PG_DEV uint32_t pg_redux_or(uint32_t v) { return __reduce_or_sync(0xffffffffu, v); }
+PG_DEV void pg_syncwarp() { __syncwarp(); }
+PG_DEV int pg_popc(uint32_t v) { return __popc(v); }
+PG_DEV int pg_ffs(uint32_t v) { return __ffs((int)v); }
+PG_DEV int pg_clz(uint32_t v) { return __clz((int)v); }
+PG_DEV uint32_t pg_brev(uint32_t v) { return __brev(v); }
+PG_DEV uint32_t pg_fsr(uint32_t lo, uint32_t hi, uint32_t s) { return __funnelshift_r(lo, hi, s); }
+PG_DEV uint32_t pg_fsrc(uint32_t lo, uint32_t hi, uint32_t s) { return __funnelshift_rc(lo, hi, s); }
+PG_DEV uint32_t pg_atomic_add(uint32_t *p, uint32_t v) { return atomicAdd(p, v); }
+PG_DEV uint32_t pg_umax(uint32_t a, uint32_t b) { return max(a, b); }
+PG_DEV uint32_t pg_umin(uint32_t a, uint32_t b) { return min(a, b); }
+PG_DEV uint32_t pg_ldg32(const uint32_t *p) { return __ldg(p); }
+PG_DEV uint2 pg_ldg64(const uint2 *p) { return __ldg(p); }
+PG_DEV uint8_t pg_ldg8(const uint8_t *p) { return __ldg(p); }
+#endif
+
+#include "pg_warp_types.h"
+
+// ------------------------------------------------------------------------------------------------
+// Per-warp shared memory
+// ------------------------------------------------------------------------------------------------
+template <int LW, int TL>
+struct PgWarpSmem {
+   // tile of the packed reference window (filled by TMA on the device)
+   alignas(16) uint2 tile[PG_TILE_WORDS];
+   alignas(16) uint32_t tile_n[PG_TILE_WORDS];
+   alignas(8) uint64_t mbar;
+   // read bit-planes: [0] forward order, [1] reversed order; planes lo, hi, N, X(other)
+   uint32_t q[2][4][LW];
+   // cooperative full-length mismatch masks: N-rule (M) and strict equality (S)
+   uint32_t M[TL][LW];
+   uint32_t S[TL][LW];
+   uint32_t mw[LW];
+   // per-level results of the current job
+   uint32_t A[TL + 1], B[TL + 1], P[TL + 1], META[TL + 1], H[TL + 1], ALIAS[TL + 1];
+   uint32_t queue[PG_QCAP];
+};
+
+struct PgLevel {      // warp-level top-2 for level == lane
+   uint32_t A, B, pos, meta;
+};
+
+PG_DEV void pg_level_merge(PgLevel &w, uint32_t D, uint32_t pos, uint32_t meta)
+{
+   if (D > w.A) { w.B = w.A; w.A = D; w.pos = pos; w.meta = meta; }
+   else if (D > w.B) { w.B = D; }
+}
+
+PG_DEV void pg_key_update(uint32_t &a, uint32_t &b, uint32_t key)
+{
+   uint32_t nb = pg_umax(b, pg_umin(a, key));
+   a = pg_umax(a, key);
+   b = nb;
+}
+
+// 32 reference bases starting at absolute position pos, straight from the packed chromosome.
+PG_DEV void pg_fetch32_global(const PgChrom &c, int64_t pos, uint32_t &lo, uint32_t &hi, uint32_t &nn)
+{
+   int64_t w = pos >> 5;             // may be negative inside the guard band
+   uint32_t sh = (uint32_t)(pos & 31);
+   uint2 a = pg_ldg64(c.planes + w), b = pg_ldg64(c.planes + w + 1);
+   lo = pg_fsr(a.x, b.x, sh);
+   hi = pg_fsr(a.y, b.y, sh);
+   nn = pg_fsr(pg_ldg32(c.nplane + w), pg_ldg32(c.nplane + w + 1), sh);
+}
+
+// Describes which read characters a search consumes: chars[j] = plane[arr] (bit j) ^ inv.
+struct PgChars {
+   int arr;          // 0 forward planes, 1 reversed planes
+   uint32_t inv;     // 0 or ~0: complement
+};
+
+template <int LW, int TL>
+PG_DEV uint32_t pg_valid_mask(int L, int c)
+{
+   int rem = L - 32 * c;
+   return rem >= 32 ? 0xffffffffu : (rem <= 0 ? 0u : ((1u << rem) - 1u));
+}
+
+// Mismatch words of chunk c for a seed: x = reference stretch in growth order.
+template <int LW, int TL>
+PG_DEV void pg_mism_words(const PgWarpSmem<LW, TL> *ws, PgChars ch, int c, int L, uint32_t xlo, uint32_t xhi, uint32_t xn,
+                          uint32_t &M, uint32_t &S)
+{
+   uint32_t qlo = ws->q[ch.arr][0][c] ^ ch.inv, qhi = ws->q[ch.arr][1][c] ^ ch.inv;
+   uint32_t qn = ws->q[ch.arr][2][c], qx = ws->q[ch.arr][3][c];
+   uint32_t diff = (xlo ^ qlo) | (xhi ^ qhi);
+   uint32_t v = pg_valid_mask<LW, TL>(L, c);
+   M = (((diff & ~qn) | qx | xn)) & v;                       // Matches(), src/searcher.cpp:36-44
+   S = ((((diff | xn) & ~qn) | (~xn & qn) | qx)) & v;        // plain char equality (BP_On_Read != BP_On_Ref)
+}
+
+// Reference stretch of chunk c (read indices 32c..32c+31) for a seed at pos growing in direction d.
+PG_DEV void pg_seed_stretch(const PgChrom &chrom, uint32_t pos, int d, int c, uint32_t &lo, uint32_t &hi, uint32_t &nn)
+{
+   if (d > 0) {
+      pg_fetch32_global(chrom, (int64_t)pos + 32 * c, lo, hi, nn);
+   } else {
+      pg_fetch32_global(chrom, (int64_t)pos - 32 * c - 31, lo, hi, nn);
+      lo = pg_brev(lo); hi = pg_brev(hi); nn = pg_brev(nn);
+   }
+}
+
+// Cooperative: lanes c < nchunks compute the full-length masks of one seed into ws->mw (N-rule) or
+// ws->M[slot]/ws->S[slot]; returns the total N-rule mismatch count when want_slot >= 0.
+template <int LW, int TL>
+PG_DEV uint32_t pg_full_masks(PgWarpSmem<LW, TL> *ws, const PgChrom &chrom, PgChars ch, uint32_t pos, int d, int L,
+                              int slot)
+{
+   int lane = pg_lane();
+   int nch = (L + 31) >> 5;
+   uint32_t M = 0, S = 0;
+   if (lane < nch) {
+      uint32_t lo, hi, nn;
+      pg_seed_stretch(chrom, pos, d, lane, lo, hi, nn);
+      pg_mism_words<LW, TL>(ws, ch, lane, L, lo, hi, nn, M, S);
+      if (slot >= 0) { ws->M[slot][lane] = M; ws->S[slot][lane] = S; }
+      else ws->mw[lane] = M;
+   }
+   uint32_t h = pg_redux_add((uint32_t)pg_popc(M));
+   pg_syncwarp();
+   return h;
+}
+
+// ------------------------------------------------------------------------------------------------
+// One search = one (or, for BreakDancer clusters, several) windows scanned with one character set.
+// ------------------------------------------------------------------------------------------------
+struct PgSearch {
+   bool far;          // both strands (SearchFarEndAtPos) or one (GetCloseEndInner)
+   PgChars chp;       // characters for the '+1' growth (close: the only set; far: plus strand)
+   int d;             // close: growth direction; far: unused
+   int bp_start;
+   int L, MAX, T;
+};
+
+template <int LW, int TL>
+struct PgWarpCtx {
+   PgWarpSmem<LW, TL> *ws;
+   const PgParams *prm;
+   const PgChrom *chroms;
+   PgLevel lvl;               // level == lane
+   uint32_t qn;               // queued slow seeds (uniform)
+   uint32_t any_seed;         // uniform
+};
+
+// device-specific: stage words [w0, w0+nw) of a chromosome into ws->tile / ws->tile_n
+template <int LW, int TL>
+PG_DEV void pg_tile_load(PgWarpSmem<LW, TL> *ws, const PgChrom &c, int64_t w0, int nw, uint32_t &phase);
+
+template <int LW, int TL>
+PG_DEV void pg_flush_queue(PgWarpCtx<LW, TL> &cx, const PgSearch &se, const PgChrom &chrom, int chr_id, uint32_t c0lo, uint32_t c0hi)
+{
+   PgWarpSmem<LW, TL> *ws = cx.ws;
+   int lane = pg_lane();
+   pg_syncwarp();
+   for (uint32_t i = 0; i < cx.qn; i++) {
+      uint32_t pos = ws->queue[i];
+      int d = se.d;
+      PgChars ch = se.chp;
+      uint32_t minus = 0;
+      if (se.far) {
+         // plus seed iff ref[pos] == read[0] (farend_searcher.cpp:76), else it was queued as a minus seed
+         uint2 wv = pg_ldg64(chrom.planes + (pos >> 5));
+         uint32_t rlo = (wv.x >> (pos & 31)) & 1u, rhi = (wv.y >> (pos & 31)) & 1u;
+         minus = (rlo != c0lo || rhi != c0hi) ? 1u : 0u;
+         d = minus ? -1 : 1;
+         ch.inv = minus ? ~se.chp.inv : se.chp.inv;
+      }
+      pg_full_masks<LW, TL>(ws, chrom, ch, pos, d, se.L, -1);
+      if (lane < se.T) {
+         // D_lane = read index of the (lane+1)-th mismatch at index >= 1, or L
+         int rank = lane;
+         uint32_t D = (uint32_t)se.L;
+         int nch = (se.L + 31) >> 5;
+         for (int c = 0; c < nch; c++) {
+            uint32_t w = ws->mw[c];
+            if (c == 0) w &= ~1u;
+            int pc = pg_popc(w);
+            if (rank < pc) {
+               for (int k = 0; k < rank; k++) w &= w - 1;
+               D = (uint32_t)(32 * c + pg_ffs(w) - 1);
+               break;
+            }
+            rank -= pc;
+         }
+         pg_level_merge(cx.lvl, D, pos, ((uint32_t)chr_id << 1) | minus);
+      }
+      pg_syncwarp();
+   }
+   cx.qn = 0;
+}
+
+// Scan window [s, e) of one chromosome (tile by tile) and fold its seeds into cx.lvl.
+template <int LW, int TL>
+PG_DEV void pg_scan_window(PgWarpCtx<LW, TL> &cx, const PgSearch &se, int chr_id, uint32_t s, uint32_t e, uint32_t &phase)
+{
+   PgWarpSmem<LW, TL> *ws = cx.ws;
+   const PgChrom chrom = cx.chroms[chr_id];
+   int lane = pg_lane();
+   if (e > chrom.len) e = chrom.len;
+   if (s >= e) return;
+   // first character of each strand's character set
+   uint32_t q0lo = ws->q[se.chp.arr][0][0], q0hi = ws->q[se.chp.arr][1][0];
+   uint32_t q0n = ws->q[se.chp.arr][2][0], q0x = ws->q[se.chp.arr][3][0];
+   if ((q0n | q0x) & 1u) return;            // first char N (or non-ACGTN): no seeds (pindel.cpp:2281, farend_searcher.cpp:54)
+   uint32_t c0lo = (q0lo ^ se.chp.inv) & 1u, c0hi = (q0hi ^ se.chp.inv) & 1u;
+   bool read_special = false;
+   {
+      uint32_t sp = 0;
+      if (lane < LW) sp = ws->q[se.chp.arr][2][lane] | ws->q[se.chp.arr][3][lane];
+      read_special = pg_any(sp != 0);
+   }
+   uint32_t valid0 = pg_valid_mask<LW, TL>(se.L, 0);
+   for (uint32_t ts = s; ts < e; ts += PG_TILE_POS) {
+      uint32_t te = (e - ts > PG_TILE_POS) ? ts + PG_TILE_POS : e;
+      int64_t w0 = (((int64_t)(ts >> 5)) - 1) & ~(int64_t)3;
+      int64_t w1 = (int64_t)((te - 1) >> 5) + 2;          // exclusive
+      int nw = (int)(((w1 - w0) + 3) & ~(int64_t)3);
+      pg_tile_load<LW, TL>(ws, chrom, w0, nw, phase);
+      // does the tile hold any reference N?
+      uint32_t nacc = 0;
+      for (int i = lane; i < nw; i += 32) nacc |= ws->tile_n[i];
+      bool special = read_special || pg_any(nacc != 0);
+      uint32_t origin = ts & ~31u;
+      uint32_t ka_[TL], kb_[TL];     // lane-local top-2 keys of this tile, one pair per level
+#pragma unroll
+      for (int t = 0; t < TL; t++) { ka_[t] = 0; kb_[t] = 0; }
+      for (uint32_t base = origin; base < te; base += 32) {
+         uint32_t p = base + (uint32_t)lane;
+         bool active = (p >= ts) && (p < te);
+         int wi = (int)((int64_t)(base >> 5) - w0);
+         uint2 W0 = ws->tile[wi], W1 = ws->tile[wi + 1], Wp = ws->tile[wi - 1];
+         uint32_t xlo, xhi, xn = 0, inv = se.chp.inv;
+         bool fwd = true;
+         if (se.far) {
+            uint32_t rlo = (W0.x >> lane) & 1u, rhi = (W0.y >> lane) & 1u;
+            fwd = (rlo == c0lo) && (rhi == c0hi);
+            if (!fwd) inv = ~inv;
+         } else {
+            fwd = se.d > 0;
+         }
+         if (fwd) {
+            xlo = pg_fsr(W0.x, W1.x, (uint32_t)lane);
+            xhi = pg_fsr(W0.y, W1.y, (uint32_t)lane);
+         } else {
+            xlo = pg_brev(pg_fsrc(Wp.x, W0.x, (uint32_t)lane + 1u));
+            xhi = pg_brev(pg_fsrc(Wp.y, W0.y, (uint32_t)lane + 1u));
+         }
+         uint32_t mism = (xlo ^ q0lo ^ inv) | (xhi ^ q0hi ^ inv);
+         if (special) {
+            uint32_t N0 = ws->tile_n[wi], N1 = ws->tile_n[wi + 1], Np = ws->tile_n[wi - 1];
+            xn = fwd ? pg_fsr(N0, N1, (uint32_t)lane) : pg_brev(pg_fsrc(Np, N0, (uint32_t)lane + 1u));
+            mism = (mism & ~q0n) | q0x | xn;
+         }
+         mism &= valid0;
+         bool seed = active && !(mism & 1u);
+         uint32_t m0 = mism & ~1u;
+         int cnt = pg_popc(m0);
+         bool hot = seed && cnt >= se.T;
+         bool slow = seed && !hot;
+         if (hot) {
+            uint32_t idx = p - origin;
+#pragma unroll
+            for (int t = 0; t < TL; t++) {
+               if (t < se.T) {
+                  uint32_t D = (uint32_t)(pg_ffs(m0) - 1);
+                  m0 &= m0 - 1;
+                  pg_key_update(ka_[t], kb_[t], (D << PG_IDX_BITS) | idx);
+               }
+            }
+         }
+         uint32_t seedmask = pg_ballot(seed);
+         uint32_t slowmask = pg_ballot(slow);
+         cx.any_seed |= seedmask;
+         if (slowmask) {
+            if (slow) ws->queue[cx.qn + (uint32_t)pg_popc(slowmask & ((1u << lane) - 1u))] = p;
+            cx.qn += (uint32_t)pg_popc(slowmask);
+         }
+         bool last_iter = base + 32u >= te;
+         if (cx.qn > PG_QCAP - 32 || (last_iter && cx.qn)) pg_flush_queue<LW, TL>(cx, se, chrom, chr_id, c0lo, c0hi);
+      }
+      // fold the tile's lane-local top-2 into the warp-level state of lane t
+#pragma unroll
+      for (int t = 0; t < TL; t++) {
+         if (t < se.T) {
+            uint32_t ka = pg_redux_max(ka_[t]);
+            uint32_t mine = (ka_[t] == ka) ? kb_[t] : ka_[t];
+            uint32_t kb = pg_redux_max(mine);
+            if (lane == t && ka != 0) {
+               uint32_t pos = origin + (ka & PG_IDX_MASK);
+               uint32_t minus = 0;
+               if (se.far) {
+                  int wi = (int)((int64_t)(pos >> 5) - w0);
+                  uint2 wv = ws->tile[wi];
+                  uint32_t rlo = (wv.x >> (pos & 31)) & 1u, rhi = (wv.y >> (pos & 31)) & 1u;
+                  minus = (rlo != c0lo || rhi != c0hi) ? 1u : 0u;
+               }
+               pg_level_merge(cx.lvl, ka >> PG_IDX_BITS, pos, ((uint32_t)chr_id << 1) | minus);
+               if (kb != 0) pg_level_merge(cx.lvl, kb >> PG_IDX_BITS, 0xffffffffu, 0);
+            }
+         }
+      }
+      pg_syncwarp();
+   }
+}
+
+// Result of one search, runs written to `dst`.
+struct PgResult {
+   uint32_t n_runs;
+   uint32_t n_ups;
+   uint32_t max_len;       // LengthStr of the last UniquePoint (SortedUniquePoints::MaxLen)
+   uint32_t last_abs_loc;  // AbsLoc of the last UniquePoint
+   uint32_t seeds;         // any seed at all (NumberOfHits > 0)
+};
+
+// The lane-per-length replay of CheckLeft/Right_Close / CheckBoth + CheckMismatches.
+template <int LW, int TL>
+PG_DEV PgResult pg_walk_emit(PgWarpCtx<LW, TL> &cx, const PgSearch &se, PgRun *dst, uint32_t dst_cap)
+{
+   PgWarpSmem<LW, TL> *ws = cx.ws;
+   const PgParams *prm = cx.prm;
+   int lane = pg_lane();
+   PgResult res;
+   res.n_runs = 0; res.n_ups = 0; res.max_len = 0; res.last_abs_loc = 0; res.seeds = cx.any_seed ? 1u : 0u;
+   if (lane <= TL) { ws->A[lane] = 0; ws->B[lane] = 0; }
+   pg_syncwarp();
+   if (lane < se.T) {
+      ws->A[lane] = cx.lvl.A; ws->B[lane] = cx.lvl.B; ws->P[lane] = cx.lvl.pos; ws->META[lane] = cx.lvl.meta;
+   }
+   pg_syncwarp();
+   // full-length masks of the seeds that can own a UniquePoint (one per level <= MAX)
+   for (int t = 0; t <= se.MAX; t++) {
+      uint32_t At = ws->A[t];
+      bool need = At >= (uint32_t)(se.bp_start + t);
+      bool alias = need && t > 0 && ws->A[t - 1] >= (uint32_t)(se.bp_start + t - 1) && ws->P[t] == ws->P[t - 1] &&
+                   ws->META[t] == ws->META[t - 1];
+      if (!need) { if (lane == 0) ws->ALIAS[t] = (uint32_t)t; pg_syncwarp(); continue; }
+      if (alias) { if (lane == 0) { ws->ALIAS[t] = ws->ALIAS[t - 1]; ws->H[t] = ws->H[t - 1]; } pg_syncwarp(); continue; }
+      uint32_t meta = ws->META[t];
+      int d = se.far ? ((meta & 1u) ? -1 : 1) : se.d;
+      PgChars ch = se.chp;
+      if (se.far && (meta & 1u)) ch.inv = ~ch.inv;
+      uint32_t h = pg_full_masks<LW, TL>(ws, cx.chroms[meta >> 1], ch, ws->P[t], d, se.L, t);
+      if (lane == 0) { ws->ALIAS[t] = (uint32_t)t; ws->H[t] = h; }
+      pg_syncwarp();
+   }
+   const int L = se.L, MAX = se.MAX, ADD = prm->add_mm, MP = prm->min_perfect;
+   const uint32_t thr = prm->thr[L];
+   bool dead = false;          // uniform: an earlier length aborted the growth
+   // open run carried across rounds (uniform)
+   uint32_t run_len0 = 0, run_cnt = 0, run_m = 0;
+   int prev_valid = 0; uint32_t prev_m = 0;
+   for (int r0 = se.bp_start; r0 <= L - 1 && !dead; r0 += 32) {
+      int len = r0 + lane;
+      bool inrange = len <= L - 1;
+      int m = 0;
+      for (int t = 0; t <= MAX; t++) m += (ws->A[t] < (uint32_t)len) ? 1 : 0;
+      bool abort_here = inrange && ((uint32_t)m > (uint32_t)prm->g[len]);       // searcher.cpp:167-169, pindel.cpp:2836-2838
+      uint32_t abmask = pg_ballot(abort_here);
+      uint32_t live = abmask ? ((1u << (pg_ffs(abmask) - 1)) - 1u) : 0xffffffffu;
+      if (abmask) dead = true;
+      bool cand = inrange && ((live >> lane) & 1u) && m <= MAX;
+      bool valid = false;
+      if (cand) {
+         // level m holds exactly one candidate, it is long enough, and nothing competes within ADD levels
+         cand = ws->B[m] < (uint32_t)len && len >= se.bp_start + m && ws->B[m + ADD] < (uint32_t)len &&
+                (!se.far || ADD > 0);
+      }
+      if (cand) {
+         uint32_t meta = ws->META[m];
+         int d = se.far ? ((meta & 1u) ? -1 : 1) : se.d;
+         int slot = (int)ws->ALIAS[m];
+         bool ok = (d > 0) ? (len > MP) : (len >= MP);                           // searcher.cpp:346 / :360 substr clipping
+         for (int j = 0; ok && j < MP; j++) {
+            int bit = len - MP + j;
+            ok = !((ws->S[slot][bit >> 5] >> (bit & 31)) & 1u);
+         }
+         valid = ok && ws->H[m] >= thr;                                          // searcher.cpp:383
+      }
+      uint32_t vmask = pg_ballot(valid);
+      // run boundaries: a run continues while consecutive lengths are valid with the same level
+      uint32_t pm = pg_shfl((uint32_t)m, (lane + 31) & 31);
+      int pv = (int)((vmask >> ((lane + 31) & 31)) & 1u);
+      if (lane == 0) { pm = prev_m; pv = prev_valid; }
+      bool starts = valid && !(pv && pm == (uint32_t)m);
+      uint32_t smask = pg_ballot(starts);
+      // uniform replay over the bits of vmask / smask
+      uint32_t rem = vmask;
+      while (rem) {
+         int bpos = pg_ffs(rem) - 1;
+         uint32_t mm = pg_shfl((uint32_t)m, bpos);
+         if ((smask >> bpos) & 1u) {
+            if (run_cnt) {       // close the open run
+               if (lane == 0 && res.n_runs < dst_cap) {
+                  uint32_t meta = ws->META[run_m];
+                  int d = se.far ? ((meta & 1u) ? -1 : 1) : se.d;
+                  PgRun rr;
+                  rr.abs_loc0 = ws->P[run_m] + (uint32_t)(d * (int)(run_len0 - 1));
+                  rr.len0 = (uint16_t)run_len0; rr.count = (uint16_t)run_cnt; rr.mm = (uint8_t)run_m;
+                  rr.dirstrand = se.far ? ((meta & 1u) ? 3u : 0u) : (se.d > 0 ? 2u : 1u);
+                  rr.chr = (int16_t)(meta >> 1);
+                  dst[res.n_runs] = rr;
+               }
+               res.n_runs++;
+            }
+            run_len0 = (uint32_t)(r0 + bpos); run_cnt = 0; run_m = mm;
+         }
+         // extend over the consecutive valid non-start bits following bpos
+         uint32_t after = (bpos == 31) ? 0u : (~0u << (bpos + 1));
+         uint32_t stop = (~vmask | smask) & after;          // first bit after bpos that is invalid or starts a new run
+         int endb = stop ? (pg_ffs(stop) - 1) : 32;
+         run_cnt += (uint32_t)(endb - bpos);
+         res.n_ups += (uint32_t)(endb - bpos);
+         res.max_len = (uint32_t)(r0 + endb - 1);
+         rem &= (endb >= 32) ? 0u : (~0u << endb);
+      }
+      prev_valid = (int)((vmask >> 31) & 1u);
+      prev_m = pg_shfl((uint32_t)m, 31);
+      if (!prev_valid && run_cnt) {
+         // a gap ends the run only logically; keep it open until the next start closes it (no merging across gaps:
+         // the next valid length is flagged as a start because pv == 0)
+      }
+   }
+   if (run_cnt) {
+      if (lane == 0 && res.n_runs < dst_cap) {
+         uint32_t meta = ws->META[run_m];
+         int d = se.far ? ((meta & 1u) ? -1 : 1) : se.d;
+         PgRun rr;
+         rr.abs_loc0 = ws->P[run_m] + (uint32_t)(d * (int)(run_len0 - 1));
+         rr.len0 = (uint16_t)run_len0; rr.count = (uint16_t)run_cnt; rr.mm = (uint8_t)run_m;
+         rr.dirstrand = se.far ? ((meta & 1u) ? 3u : 0u) : (se.d > 0 ? 2u : 1u);
+         rr.chr = (int16_t)(meta >> 1);
+         dst[res.n_runs] = rr;
+      }
+      res.n_runs++;
+   }
+   if (res.n_ups) {
+      uint32_t meta = ws->META[run_m];
+      int d = se.far ? ((meta & 1u) ? -1 : 1) : se.d;
+      res.last_abs_loc = ws->P[run_m] + (uint32_t)(d * (int)(res.max_len - 1));
+   }
+   pg_syncwarp();
+   return res;
+}
+
+template <int LW, int TL>
+PG_DEV void pg_search_begin(PgWarpCtx<LW, TL> &cx)
+{
+   cx.lvl.A = 0; cx.lvl.B = 0; cx.lvl.pos = 0; cx.lvl.meta = 0;
+   cx.qn = 0; cx.any_seed = 0;
+}
+
+// Pack the read (ASCII) into bit-planes; returns the stripped length (setUnmatchedSeq, pindel.cpp:142-169).
+template <int LW, int TL>
+PG_DEV int pg_pack_read(PgWarpSmem<LW, TL> *ws, const uint8_t *seq, int len)
+{
+   int lane = pg_lane();
+   // strip trailing non-alphanumerics
+   int L = 0;
+   for (int c0 = 0; c0 < len; c0 += 32) {
+      int i = c0 + lane;
+      uint8_t ch = (i < len) ? pg_ldg8(seq + i) : (uint8_t)0;
+      bool alnum = (ch >= '0' && ch <= '9') || (ch >= 'A' && ch <= 'Z') || (ch >= 'a' && ch <= 'z');
+      uint32_t mk = pg_ballot(alnum);
+      if (mk) L = c0 + 32 - pg_clz(mk);
+   }
+   for (int c = 0; c < LW; c++) {
+      for (int rev = 0; rev < 2; rev++) {
+         int i = 32 * c + lane;
+         int src = rev ? (L - 1 - i) : i;
+         uint8_t ch = (i < L) ? pg_ldg8(seq + src) : (uint8_t)'A';
+         uint32_t code = (ch == 'C') ? 1u : (ch == 'G') ? 2u : (ch == 'T') ? 3u : 0u;
+         bool isn = (ch == 'N');
+         bool isx = !(ch == 'A' || ch == 'C' || ch == 'G' || ch == 'T' || ch == 'N');
+         uint32_t lo = pg_ballot((code & 1u) != 0), hi = pg_ballot((code & 2u) != 0);
+         uint32_t nn = pg_ballot(isn), xx = pg_ballot(isx);
+         if (lane == 0) { ws->q[rev][0][c] = lo; ws->q[rev][1][c] = hi; ws->q[rev][2][c] = nn; ws->q[rev][3][c] = xx; }
+      }
+   }
+   pg_syncwarp();
+   return L;
+}
+
+// setUnmatchedSeq(ReverseComplement(seq)) (pindel.cpp:2545): materialise RC(read) as the new forward read.
+// Leading non-ACGTN characters become trailing NULs after the flip and are stripped; returns the new length.
+template <int LW, int TL>
+PG_DEV int pg_flip_read(PgWarpSmem<LW, TL> *ws, int L)
+{
+   int lane = pg_lane();
+   // k = number of leading 'other' characters of the current read
+   int k = 0;
+   {
+      bool done = false;
+      for (int c = 0; c < LW && !done; c++) {
+         uint32_t x = ws->q[0][3][c] & pg_valid_mask<LW, TL>(L, c);
+         uint32_t nx = ~x & pg_valid_mask<LW, TL>(L, c);
+         if (nx) { k += pg_ffs(nx) - 1; done = true; }
+         else { int rem = L - 32 * c; k += rem >= 32 ? 32 : (rem > 0 ? rem : 0); if (rem <= 32) done = true; }
+      }
+   }
+   int Ln = L - k;
+   // new forward  F'[j] = comp(R[L-1-j]) = ~V[j]  (j < Ln);  new reversed V'[j] = comp(R[k+j]) = ~(F >> k)[j]
+   uint32_t nf[4] = {0, 0, 0, 0}, nv[4] = {0, 0, 0, 0};
+   if (lane < LW) {
+      uint32_t vm = pg_valid_mask<LW, TL>(Ln, lane);
+      int ws_ = lane + (k >> 5);
+      uint32_t sh = (uint32_t)(k & 31);
+      for (int pl = 0; pl < 4; pl++) {
+         uint32_t v = ws->q[1][pl][lane];
+         uint32_t f0 = (ws_ < LW) ? ws->q[0][pl][ws_] : 0u, f1 = (ws_ + 1 < LW) ? ws->q[0][pl][ws_ + 1] : 0u;
+         uint32_t fs = pg_fsr(f0, f1, sh);
+         if (pl < 2) { v = ~v; fs = ~fs; }
+         nf[pl] = v & vm; nv[pl] = fs & vm;
+      }
+      // a base that is N or other carries code bits 0 in both planes before complement -> keep them 0
+      nf[0] &= ~(nf[2] | nf[3]); nf[1] &= ~(nf[2] | nf[3]);
+      nv[0] &= ~(nv[2] | nv[3]); nv[1] &= ~(nv[2] | nv[3]);
+   }
+   pg_syncwarp();
+   if (lane < LW) {
+      for (int pl = 0; pl < 4; pl++) { ws->q[0][pl][lane] = nf[pl]; ws->q[1][pl][lane] = nv[pl]; }
+   }
+   pg_syncwarp();
+   return Ln;
+}
+
+// The whole per-read program: GetCloseEnd (pindel.cpp:2531-2605) then SearchFarEnd (pindel.cpp:1001-1074), written
+// as one loop over "searches" so that the scan and the replay are instantiated exactly once.
+template <int LW, int TL>
+PG_DEV void pg_process_read(PgWarpCtx<LW, TL> &cx, const PgBatch &bt, int ri, PgRun *scratch, uint32_t &phase)
+{
+   PgWarpSmem<LW, TL> *ws = cx.ws;
+   const PgParams *prm = cx.prm;
+   int lane = pg_lane();
+   const uint32_t cap = bt.scratch_cap;
+   PgRun *closeBuf = scratch, *farBest = scratch + cap, *farNew = scratch + 2 * cap;
+   uint32_t o0 = bt.seq_off[ri], o1 = bt.seq_off[ri + 1];
+   int rawlen = (int)(o1 - o0);
+   PgReadOut ro;
+   ro.run_off = 0; ro.n_close_runs = 0; ro.n_far_runs = 0; ro.len_after = 0; ro.flags = 0;
+   if (rawlen > 32 * LW || rawlen >= PG_TABLE) {
+      ro.flags = PG_F_TOOLONG; ro.len_after = (uint16_t)rawlen;
+      if (lane == 0) bt.out[ri] = ro;
+      return;
+   }
+   int L = pg_pack_read<LW, TL>(ws, bt.seq_blob + o0, rawlen);
+   if ((int)prm->g[L] + prm->add_mm + 1 > TL) {      // more mismatch levels than this build tracks
+      ro.flags = PG_F_TOOLONG; ro.len_after = (uint16_t)L;
+      if (lane == 0) bt.out[ri] = ro;
+      return;
+   }
+   const int chr_id = bt.chr_id ? bt.chr_id[ri] : 0;
+   const uint8_t md = (bt.mode & 1) ? bt.matched_d[ri] : (uint8_t)0;
+   const uint32_t rp = (bt.mode & 1) ? bt.matched_rel_pos[ri] : 0u;
+   const int isz = (bt.mode & 1) ? bt.insert_size[ri] : 0;
+   const int n_regions = (bt.regions && bt.region_off) ? (int)(bt.region_off[ri + 1] - bt.region_off[ri]) : 0;
+   const PgRegion *cluster = n_regions ? bt.regions + bt.region_off[ri] : (const PgRegion *)0;
+   uint32_t flips = 0;
+   PgResult cres, best;
+   cres.n_runs = 0; cres.n_ups = 0; cres.max_len = 0; cres.last_abs_loc = 0; cres.seeds = 0;
+   best = cres;
+   enum { ST_CLOSE = 0, ST_FAR_CLUSTER = 1, ST_FAR_WINDOW = 2, ST_DONE = 3 };
+   int st = ST_DONE;
+   int range_index = 0;        // GetCloseEnd: RangeIndex 0..1
+   bool second_try = false;    // GetCloseEnd: the attempt after setUnmatchedSeq(ReverseComplement())
+   int k = 1;                  // SearchFarEnd: rangeIndex 1..MaxRangeIndex+1
+   uint32_t span = 64;         // START_SEARCH_SPAN
+   if (bt.mode & 1) {
+      st = ST_CLOSE;
+   } else if ((bt.mode & 2) && bt.close_info) {
+      cres.n_ups = bt.close_info[ri].max_len ? 1u : 0u;
+      cres.max_len = bt.close_info[ri].max_len;
+      cres.last_abs_loc = bt.close_info[ri].last_abs_loc;
+      if (cres.n_ups && L > 0) st = n_regions ? ST_FAR_CLUSTER : ST_FAR_WINDOW;
+   }
+   while (st != ST_DONE) {
+      // ---- describe the search ----
+      PgSearch se;
+      se.L = L; se.MAX = prm->g[L]; se.T = se.MAX + prm->add_mm + 1;
+      PgRegion one;
+      const PgRegion *regs = &one;
+      int nreg = 1;
+      PgRun *dst = farNew;
+      bool skip = false;
+      if (st == ST_CLOSE) {
+         // GetCloseEndInner, pindel.cpp:2250-2396
+         se.far = false; se.bp_start = prm->min_close; dst = closeBuf;
+         int64_t start, end;
+         if (md == '+') {
+            // CurrentReadSeq = ReverseComplement(read): chars[j] = comp(R[L-1-j]); seeded on its first char, grows right
+            se.chp.arr = 1; se.chp.inv = ~0u; se.d = 1;
+            start = (int64_t)rp + PG_SPACER - (int64_t)range_index * isz;
+            end = start + (int64_t)(2 * range_index + 1) * isz;
+         } else {
+            // CurrentReadSeq = read, seeded on its last char, grows left: chars[j] = R[L-1-j]
+            se.chp.arr = 1; se.chp.inv = 0u; se.d = -1;
+            end = (int64_t)rp + PG_SPACER + (int64_t)range_index * isz;
+            start = end - (int64_t)(2 * range_index + 1) * isz;
+         }
+         if (start < 0) start = 0;
+         if (end > 0xffffffffll) end = 0xffffffffll;
+         one.chr = chr_id; one.start = (uint32_t)start; one.end = (uint32_t)(end > start ? end : start);
+         skip = !(md == '+' || md == '-') || L <= 0;
+      } else {
+         // SearchFarEndAtPos, farend_searcher.cpp:46-103
+         se.far = true; se.bp_start = PG_FAR_BP_START; se.chp.arr = 0; se.chp.inv = 0u; se.d = 1;
+         skip = (ws->q[0][2][0] & 1u) != 0;          // read[0] == 'N' -> returns at once (:54-56)
+         if (st == ST_FAR_CLUSTER) { regs = cluster; nreg = n_regions; }
+         else {
+            uint32_t center = cres.last_abs_loc, size = cx.chroms[chr_id].len;
+            one.chr = chr_id;
+            one.start = (center > span + PG_SPACER) ? center - span : PG_SPACER;               // pindel.cpp:1033-1042
+            one.end = (center + span + PG_SPACER < size) ? center + span : size - PG_SPACER;
+         }
+      }
+      // ---- run it ----
+      pg_search_begin<LW, TL>(cx);
+      if (!skip) {
+         for (int r = 0; r < nreg; r++) {
+            PgRegion rg = regs[r];
+            uint32_t s = rg.start, e = rg.end;
+            if (se.far) {
+               int64_t ss = (int32_t)rg.start, ee = (int32_t)rg.end;    // int Start/End, farend_searcher.cpp:65-69
+               if (ss < 0) ss = ee - 1;
+               if (ss < 0) ss = 0;
+               if (ee < ss) ee = ss;
+               s = (uint32_t)ss; e = (uint32_t)ee;
+            }
+            if (e > s) pg_scan_window<LW, TL>(cx, se, rg.chr, s, e, phase);
+         }
+      }
+      PgResult res = pg_walk_emit<LW, TL>(cx, se, dst, cap);
+      // ---- decide what comes next ----
+      if (st == ST_CLOSE) {
+         cres = res;
+         if (res.n_ups) {
+            st = ((bt.mode & 2) && L > 0) ? (n_regions ? ST_FAR_CLUSTER : ST_FAR_WINDOW) : ST_DONE;
+         } else if (!second_try) {
+            L = pg_flip_read<LW, TL>(ws, L);         // Temp_One_Read.setUnmatchedSeq(ReverseComplement(..)), pindel.cpp:2545
+            flips++;
+            second_try = true;
+         } else {
+            second_try = false;
+            if (++range_index >= 2) st = ST_DONE;    // MaxRange = 2
+         }
+      } else {
+         if (res.seeds && res.max_len >= best.max_len) {          // NewUPFarIsBetter, farend_searcher.cpp:30-44
+            best = res;
+            PgRun *t = farBest; farBest = farNew; farNew = t;
+         }
+         bool good = best.max_len + cres.max_len >= (uint32_t)L; // goodFarEndFound, pindel.cpp:480-483
+         if (st == ST_FAR_CLUSTER) {
+            st = good ? ST_DONE : ST_FAR_WINDOW;
+         } else {
+            span *= 4;
+            if (good || ++k > prm->max_range_index + 1) st = ST_DONE;
+         }
+      }
+   }
+   // publish: one allocation in the run pool for close + far runs
+   uint32_t ncl = (bt.mode & 1) ? cres.n_runs : 0u;
+   uint32_t total = ncl + best.n_runs;
+   uint32_t off = 0;
+   if (lane == 0 && total) off = pg_atomic_add(bt.counters + 1, total);
+   off = pg_shfl(off, 0);
+   ro.len_after = (uint16_t)L;
+   ro.flags = (uint16_t)((flips & 1u) ? PG_F_FLIPPED : 0u);
+   if (total && (off + total > bt.run_pool_cap || ncl > cap || best.n_runs > cap)) {
+      ro.flags |= PG_F_OVERFLOW;
+      if (lane == 0) bt.counters[2] = 1;
+   } else {
+      ro.run_off = off; ro.n_close_runs = (uint16_t)ncl; ro.n_far_runs = (uint16_t)best.n_runs;
+      pg_syncwarp();
+      for (uint32_t i = (uint32_t)lane; i < total; i += 32) bt.run_pool[off + i] = (i < ncl) ? closeBuf[i] : farBest[i - ncl];
+   }
+   if (lane == 0) bt.out[ri] = ro;
+   pg_syncwarp();
+}

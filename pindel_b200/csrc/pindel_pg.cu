@@ -1,0 +1,546 @@
+// pindel_b200/csrc/pindel_pg.cu -- kernels + C ABI of libpindel_pg.so (sm_100a only).
+//
+//   pg_pack_kernel    : ASCII chromosome -> {lo,hi} bit-planes + N plane (2 bits/base + 1 bit/base)
+//   pg_search_kernel  : persistent grid, one warp per read (pg_warp.cuh); the reference window of every search is
+//                       staged into shared memory with TMA bulk copies (cp.async.bulk + mbarrier), results go to a
+//                       run pool through one atomic allocation per read
+//   extern "C" pg_*   : the ABI declared in include/pindel_pg.h
+//
+// There is no host implementation of the search in this library: without a CUDA device every call fails.
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include <string>
+#include <vector>
+
+#include "pg_warp.cuh"
+#include "pg_params.h"
+#include "../../include/pindel_pg.h"
+
+static_assert(sizeof(pg_run) == sizeof(PgRun) && sizeof(pg_run) == 12, "run layout");
+static_assert(sizeof(pg_read_out) == sizeof(PgReadOut) && sizeof(pg_read_out) == 12, "read_out layout");
+static_assert(sizeof(pg_region) == sizeof(PgRegion) && sizeof(pg_region) == 12, "region layout");
+static_assert(sizeof(pg_close_info) == sizeof(PgCloseInfo) && sizeof(pg_close_info) == 8, "close_info layout");
+static_assert(PG_READ_FLIPPED == PG_F_FLIPPED && PG_READ_UNSUPPORTED == PG_F_TOOLONG && PG_READ_OVERFLOW == PG_F_OVERFLOW, "flags");
+
+#define PG_BLOCK_THREADS 256
+#define PG_WARPS_PER_BLOCK (PG_BLOCK_THREADS / 32)
+
+// ------------------------------------------------------------------------------------------------
+// TMA tile staging: two bulk copies (bit-planes, N plane) completing on the warp's mbarrier
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t pg_smem_addr(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+template <int LW, int TL>
+__device__ __forceinline__ void pg_tile_load(PgWarpSmem<LW, TL> *ws, const PgChrom &c, int64_t w0, int nw, uint32_t &phase)
+{
+   __syncwarp();                                      // every lane is done with the previous tile
+   uint32_t bar = pg_smem_addr(&ws->mbar);
+   if (pg_lane() == 0) {
+      uint32_t bytes_p = (uint32_t)nw * 8u, bytes_n = (uint32_t)nw * 4u;
+      asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes_p + bytes_n) : "memory");
+      asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                      pg_smem_addr(ws->tile)),
+                   "l"(c.planes + w0), "r"(bytes_p), "r"(bar)
+                   : "memory");
+      asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                      pg_smem_addr(ws->tile_n)),
+                   "l"(c.nplane + w0), "r"(bytes_n), "r"(bar)
+                   : "memory");
+   }
+   uint32_t done = 0;
+   while (!done) {
+      asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                   : "=r"(done)
+                   : "r"(bar), "r"(phase)
+                   : "memory");
+   }
+   phase ^= 1u;
+}
+
+template <int LW, int TL>
+__global__ void __launch_bounds__(PG_BLOCK_THREADS) pg_search_kernel(PgBatch bt, const PgParams *__restrict__ prm_g,
+                                                                     const PgChrom *__restrict__ chroms)
+{
+   extern __shared__ __align__(128) unsigned char pg_dyn_smem[];
+   __shared__ PgParams s_prm;
+   {
+      const uint32_t *src = reinterpret_cast<const uint32_t *>(prm_g);
+      uint32_t *dst = reinterpret_cast<uint32_t *>(&s_prm);
+      for (int i = threadIdx.x; i < (int)(sizeof(PgParams) / 4); i += blockDim.x) dst[i] = src[i];
+   }
+   const int warp = threadIdx.x >> 5;
+   PgWarpSmem<LW, TL> *ws = reinterpret_cast<PgWarpSmem<LW, TL> *>(pg_dyn_smem) + warp;
+   if (pg_lane() == 0) {
+      asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(pg_smem_addr(&ws->mbar)) : "memory");
+      asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+   }
+   __syncthreads();
+   PgWarpCtx<LW, TL> cx;
+   cx.ws = ws; cx.prm = &s_prm; cx.chroms = chroms;
+   uint32_t phase = 0;
+   const uint32_t gwarp = blockIdx.x * PG_WARPS_PER_BLOCK + warp;
+   PgRun *scratch = bt.scratch + (size_t)gwarp * 3u * bt.scratch_cap;
+   for (;;) {
+      uint32_t ri = 0;
+      if (pg_lane() == 0) ri = atomicAdd(bt.counters, 1u);
+      ri = __shfl_sync(0xffffffffu, ri, 0);
+      if ((int)ri >= bt.n_reads) break;
+      pg_process_read<LW, TL>(cx, bt, (int)ri, scratch, phase);
+   }
+}
+
+// One warp per 32 bases: coalesced byte loads, three ballots, one 8-byte + one 4-byte store.
+__global__ void pg_pack_kernel(const uint8_t *__restrict__ ascii, uint32_t n_bases, uint32_t first_word, uint2 *planes,
+                               uint32_t *nplane)
+{
+   uint32_t gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+   uint32_t lane = threadIdx.x & 31;
+   uint32_t nw = (n_bases + 31u) >> 5;
+   if (gw >= nw) return;
+   uint32_t i = gw * 32u + lane;
+   uint8_t c = (i < n_bases) ? ascii[i] : (uint8_t)'N';
+   uint32_t code = (c == 'C') ? 1u : (c == 'G') ? 2u : (c == 'T') ? 3u : 0u;
+   bool isn = !(c == 'A' || c == 'C' || c == 'G' || c == 'T');
+   uint32_t lo = __ballot_sync(0xffffffffu, code & 1u), hi = __ballot_sync(0xffffffffu, code & 2u);
+   uint32_t nn = __ballot_sync(0xffffffffu, isn);
+   if (lane == 0) {
+      planes[first_word + gw] = make_uint2(lo, hi);
+      nplane[first_word + gw] = nn;
+   }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Context
+// ------------------------------------------------------------------------------------------------
+struct DevBuf {
+   void *p = nullptr;
+   size_t cap = 0;
+};
+
+struct pg_ctx {
+   pg_settings st;
+   int device = 0;
+   int n_sm = 0;
+   cudaStream_t own_stream = nullptr, stream = nullptr;
+   std::string err;
+   PgParams prm_h;
+   uint32_t table[PG_TABLE];
+   PgParams *prm_d = nullptr;
+   // reference
+   std::vector<void *> chrom_allocs;
+   std::vector<PgChrom> chroms_h;
+   PgChrom *chroms_d = nullptr;
+   // resident batch
+   int n = 0;
+   bool have_anchor = false, have_chr = false, have_close = false, have_regions = false;
+   uint32_t max_read_len = 0;
+   DevBuf seq_blob, seq_off, md, pos, isz, chr, closeinfo, regions, region_off, out, pool, counters, scratch;
+   uint32_t pool_cap = 0;
+   uint32_t *counters_h = nullptr;     // pinned
+   int last_mode = 0;
+   bool launched = false;
+   uint64_t launches = 0;
+   uint32_t last_runs = 0;
+};
+
+static thread_local std::string g_create_error;
+
+static int fail(pg_ctx *c, int code, const std::string &msg)
+{
+   if (c) c->err = msg;
+   return code;
+}
+#define CU(call)                                                                                                      \
+   do {                                                                                                               \
+      cudaError_t e_ = (call);                                                                                        \
+      if (e_ != cudaSuccess) return fail(ctx, PG_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e_));       \
+   } while (0)
+
+static int ensure(pg_ctx *ctx, DevBuf &b, size_t bytes)
+{
+   if (bytes <= b.cap) return PG_OK;
+   if (b.p) CU(cudaFree(b.p));
+   b.p = nullptr; b.cap = 0;
+   size_t want = bytes + bytes / 4 + 256;
+   CU(cudaMalloc(&b.p, want));
+   b.cap = want;
+   return PG_OK;
+}
+
+template <int LW, int TL>
+static int launch_variant(pg_ctx *ctx, const PgBatch &bt_in)
+{
+   PgBatch bt = bt_in;
+   size_t smem = sizeof(PgWarpSmem<LW, TL>) * PG_WARPS_PER_BLOCK;
+   CU(cudaFuncSetAttribute(pg_search_kernel<LW, TL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+   int per_sm = 0;
+   CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, pg_search_kernel<LW, TL>, PG_BLOCK_THREADS, smem));
+   if (per_sm < 1) per_sm = 1;
+   int grid = ctx->n_sm * per_sm;                       // a whole number of waves: one resident CTA set per SM
+   long need_blocks = ((long)bt.n_reads + PG_WARPS_PER_BLOCK - 1) / PG_WARPS_PER_BLOCK;
+   if (need_blocks < grid) grid = (int)(need_blocks > 0 ? need_blocks : 1);
+   bt.scratch_cap = 32u * LW;
+   int rc = ensure(ctx, ctx->scratch, sizeof(PgRun) * 3u * bt.scratch_cap * (size_t)grid * PG_WARPS_PER_BLOCK);
+   if (rc != PG_OK) return rc;
+   bt.scratch = (PgRun *)ctx->scratch.p;
+   pg_search_kernel<LW, TL><<<grid, PG_BLOCK_THREADS, smem, ctx->stream>>>(bt, ctx->prm_d, ctx->chroms_d);
+   CU(cudaGetLastError());
+   ctx->launches++;
+   return PG_OK;
+}
+
+extern "C" {
+
+void pg_default_settings(pg_settings *s)
+{
+   memset(s, 0, sizeof(*s));
+   s->seq_error_rate = 0.01;
+   s->sensitivity = 0.95;
+   s->max_mismatch_rate = 0.02;
+   s->additional_mismatch = 1;
+   s->min_close = 8;
+   s->min_perfect_match = 3;
+   s->max_range_index = 2;
+   s->device = 0;
+}
+
+const char *pg_create_error(void) { return g_create_error.c_str(); }
+const char *pg_last_error(pg_ctx *ctx) { return ctx ? ctx->err.c_str() : "null context"; }
+
+pg_ctx *pg_create(const pg_settings *s)
+{
+   g_create_error.clear();
+   if (!s) { g_create_error = "null settings"; return nullptr; }
+   if (s->additional_mismatch < 0 || s->min_close < 1 || s->min_perfect_match < 0 || s->max_range_index < 0 ||
+       s->max_range_index > 9) {
+      g_create_error = "settings out of range";
+      return nullptr;
+   }
+   int ndev = 0;
+   cudaError_t e = cudaGetDeviceCount(&ndev);
+   if (e != cudaSuccess || ndev == 0) {
+      g_create_error = std::string("no CUDA device: ") + (e != cudaSuccess ? cudaGetErrorString(e) : "device count is 0") +
+                       " (libpindel_pg has no CPU path)";
+      return nullptr;
+   }
+   if (s->device < 0 || s->device >= ndev) { g_create_error = "device ordinal out of range"; return nullptr; }
+   pg_ctx *ctx = new pg_ctx();
+   ctx->st = *s;
+   ctx->device = s->device;
+   pg_prob_table(0.001 + s->seq_error_rate, s->sensitivity, ctx->table);      // src/pindel.cpp:856
+   if (pg_fill_params(&ctx->prm_h, s->additional_mismatch, s->min_close, s->min_perfect_match, s->max_range_index,
+                      s->max_mismatch_rate, ctx->table) != 0) {
+      g_create_error = "mismatch table does not fit";
+      delete ctx;
+      return nullptr;
+   }
+   bool ok = cudaSetDevice(ctx->device) == cudaSuccess &&
+             cudaDeviceGetAttribute(&ctx->n_sm, cudaDevAttrMultiProcessorCount, ctx->device) == cudaSuccess &&
+             cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking) == cudaSuccess &&
+             cudaMalloc(&ctx->prm_d, sizeof(PgParams)) == cudaSuccess &&
+             cudaMemcpy(ctx->prm_d, &ctx->prm_h, sizeof(PgParams), cudaMemcpyHostToDevice) == cudaSuccess &&
+             cudaHostAlloc((void **)&ctx->counters_h, 16, cudaHostAllocDefault) == cudaSuccess;
+   if (!ok) {
+      g_create_error = std::string("CUDA initialisation failed: ") + cudaGetErrorString(cudaGetLastError());
+      delete ctx;
+      return nullptr;
+   }
+   ctx->stream = ctx->own_stream;
+   return ctx;
+}
+
+void pg_destroy(pg_ctx *ctx)
+{
+   if (!ctx) return;
+   cudaSetDevice(ctx->device);
+   cudaDeviceSynchronize();
+   for (void *p : ctx->chrom_allocs) cudaFree(p);
+   DevBuf *bufs[] = {&ctx->seq_blob, &ctx->seq_off, &ctx->md, &ctx->pos, &ctx->isz, &ctx->chr, &ctx->closeinfo,
+                     &ctx->regions, &ctx->region_off, &ctx->out, &ctx->pool, &ctx->counters, &ctx->scratch};
+   for (DevBuf *b : bufs) if (b->p) cudaFree(b->p);
+   if (ctx->chroms_d) cudaFree(ctx->chroms_d);
+   if (ctx->prm_d) cudaFree(ctx->prm_d);
+   if (ctx->counters_h) cudaFreeHost(ctx->counters_h);
+   if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
+   delete ctx;
+}
+
+int pg_set_stream(pg_ctx *ctx, void *cuda_stream)
+{
+   if (!ctx) return PG_ERR_ARG;
+   CU(cudaSetDevice(ctx->device));
+   CU(cudaStreamSynchronize(ctx->stream));
+   ctx->stream = cuda_stream ? (cudaStream_t)cuda_stream : ctx->own_stream;
+   return PG_OK;
+}
+
+int pg_max_mismatch_table(pg_ctx *ctx, uint32_t *out)
+{
+   if (!ctx || !out) return PG_ERR_ARG;
+   memcpy(out, ctx->table, sizeof(uint32_t) * PG_TABLE);
+   return PG_OK;
+}
+
+int pg_set_reference(pg_ctx *ctx, int32_t n_chr, const char *const *seq, const uint32_t *len)
+{
+   if (!ctx || n_chr <= 0 || n_chr > 32767 || !seq || !len) return fail(ctx, PG_ERR_ARG, "pg_set_reference: bad arguments");
+   CU(cudaSetDevice(ctx->device));
+   CU(cudaStreamSynchronize(ctx->stream));
+   for (void *p : ctx->chrom_allocs) cudaFree(p);
+   ctx->chrom_allocs.clear();
+   ctx->chroms_h.clear();
+   if (ctx->chroms_d) { cudaFree(ctx->chroms_d); ctx->chroms_d = nullptr; }
+   const size_t CHUNK = (size_t)64 << 20;        // bases per staging chunk (multiple of 32)
+   uint8_t *stage = nullptr;
+   size_t maxlen = 0;
+   for (int i = 0; i < n_chr; i++) if (len[i] > maxlen) maxlen = len[i];
+   CU(cudaMalloc((void **)&stage, maxlen < CHUNK ? (maxlen ? maxlen : 1) : CHUNK));
+   for (int i = 0; i < n_chr; i++) {
+      uint32_t nwords = (len[i] + 31u) / 32u;
+      size_t total = (size_t)nwords + 2u * PG_PADW;
+      uint2 *planes = nullptr;
+      uint32_t *nplane = nullptr;
+      CU(cudaMalloc((void **)&planes, total * sizeof(uint2)));
+      ctx->chrom_allocs.push_back(planes);
+      CU(cudaMalloc((void **)&nplane, total * sizeof(uint32_t)));
+      ctx->chrom_allocs.push_back(nplane);
+      CU(cudaMemsetAsync(planes, 0, total * sizeof(uint2), ctx->stream));
+      CU(cudaMemsetAsync(nplane, 0xff, total * sizeof(uint32_t), ctx->stream));   // guard band reads as N
+      for (size_t b0 = 0; b0 < len[i]; b0 += CHUNK) {
+         size_t nb = len[i] - b0 < CHUNK ? len[i] - b0 : CHUNK;
+         CU(cudaMemcpyAsync(stage, seq[i] + b0, nb, cudaMemcpyHostToDevice, ctx->stream));
+         uint32_t nw = (uint32_t)((nb + 31) / 32);
+         uint32_t threads = 256, blocks = (nw * 32u + threads - 1) / threads;
+         pg_pack_kernel<<<blocks, threads, 0, ctx->stream>>>(stage, (uint32_t)nb, (uint32_t)(PG_PADW + b0 / 32), planes, nplane);
+         CU(cudaGetLastError());
+         CU(cudaStreamSynchronize(ctx->stream));   // staging buffer and (possibly pageable) source are reused
+      }
+      PgChrom c;
+      c.planes = planes + PG_PADW;
+      c.nplane = nplane + PG_PADW;
+      c.len = len[i];
+      c.nwords = nwords;
+      ctx->chroms_h.push_back(c);
+   }
+   CU(cudaFree(stage));
+   CU(cudaMalloc((void **)&ctx->chroms_d, sizeof(PgChrom) * (size_t)n_chr));
+   CU(cudaMemcpy(ctx->chroms_d, ctx->chroms_h.data(), sizeof(PgChrom) * (size_t)n_chr, cudaMemcpyHostToDevice));
+   return PG_OK;
+}
+
+int pg_upload(pg_ctx *ctx, const pg_reads *in)
+{
+   if (!ctx || !in || in->n < 0 || (in->n > 0 && (!in->seq_blob || !in->seq_off)))
+      return fail(ctx, PG_ERR_ARG, "pg_upload: bad arguments");
+   CU(cudaSetDevice(ctx->device));
+   const int n = in->n;
+   ctx->launched = false;
+   ctx->n = n;
+   ctx->have_anchor = in->matched_d && in->matched_rel_pos && in->insert_size;
+   ctx->have_chr = in->chr_id != nullptr;
+   ctx->have_close = in->close_info != nullptr;
+   ctx->have_regions = in->regions && in->region_off;
+   if (n == 0) return PG_OK;
+   // longest read and chromosome ids are validated here, on the host
+   uint32_t maxlen = 0;
+   for (int i = 0; i < n; i++) {
+      if (in->seq_off[i + 1] < in->seq_off[i]) return fail(ctx, PG_ERR_ARG, "pg_upload: seq_off must be non-decreasing");
+      uint32_t l = in->seq_off[i + 1] - in->seq_off[i];
+      if (l > maxlen) maxlen = l;
+   }
+   ctx->max_read_len = maxlen;
+   if (maxlen >= PG_TABLE)
+      return fail(ctx, PG_ERR_UNSUPPORTED, "read longer than 499 bases (the reference's g_maxMismatch table has 500 entries)");
+   if (ctx->have_chr) {
+      for (int i = 0; i < n; i++)
+         if (in->chr_id[i] < 0 || (size_t)in->chr_id[i] >= ctx->chroms_h.size())
+            return fail(ctx, PG_ERR_ARG, "pg_upload: chr_id out of range");
+   }
+   size_t blob = in->seq_off[n];
+   int rc;
+#define UP(buf, src, bytes)                                                                              \
+   if ((rc = ensure(ctx, buf, (bytes))) != PG_OK) return rc;                                             \
+   CU(cudaMemcpyAsync(buf.p, (src), (bytes), cudaMemcpyHostToDevice, ctx->stream))
+   UP(ctx->seq_blob, in->seq_blob, blob ? blob : 1);
+   UP(ctx->seq_off, in->seq_off, sizeof(uint32_t) * ((size_t)n + 1));
+   if (ctx->have_anchor) {
+      UP(ctx->md, in->matched_d, (size_t)n);
+      UP(ctx->pos, in->matched_rel_pos, sizeof(uint32_t) * (size_t)n);
+      UP(ctx->isz, in->insert_size, sizeof(int16_t) * (size_t)n);
+   }
+   if (ctx->have_chr) { UP(ctx->chr, in->chr_id, sizeof(int32_t) * (size_t)n); }
+   if (ctx->have_close) { UP(ctx->closeinfo, in->close_info, sizeof(pg_close_info) * (size_t)n); }
+   if (ctx->have_regions) {
+      size_t nr = in->region_off[n];
+      for (size_t i = 0; i < nr; i++)
+         if (in->regions[i].chr < 0 || (size_t)in->regions[i].chr >= ctx->chroms_h.size())
+            return fail(ctx, PG_ERR_ARG, "pg_upload: region chromosome out of range");
+      UP(ctx->regions, in->regions, sizeof(pg_region) * (nr ? nr : 1));
+      UP(ctx->region_off, in->region_off, sizeof(uint32_t) * ((size_t)n + 1));
+   }
+#undef UP
+   return PG_OK;
+}
+
+int pg_launch(pg_ctx *ctx, int32_t mode)
+{
+   if (!ctx || mode < 1 || mode > 3) return fail(ctx, PG_ERR_ARG, "pg_launch: mode must be 1, 2 or 3");
+   if (ctx->chroms_h.empty()) return fail(ctx, PG_ERR_STATE, "pg_launch: no reference (call pg_set_reference)");
+   if ((mode & 1) && !ctx->have_anchor) return fail(ctx, PG_ERR_ARG, "close-end search needs matched_d, matched_rel_pos and insert_size");
+   if (mode == 2 && !ctx->have_close) return fail(ctx, PG_ERR_ARG, "far-end-only search needs close_info");
+   CU(cudaSetDevice(ctx->device));
+   ctx->last_mode = mode;
+   ctx->launched = true;
+   if (ctx->n == 0) return PG_OK;
+   const int n = ctx->n;
+   int rc;
+   if ((rc = ensure(ctx, ctx->out, sizeof(PgReadOut) * (size_t)n)) != PG_OK) return rc;
+   if ((rc = ensure(ctx, ctx->counters, 16)) != PG_OK) return rc;
+   if (ctx->pool_cap == 0 || ctx->pool.p == nullptr) {
+      size_t want = (size_t)n * 24u + 4096u;
+      if (want > 0xfffffff0u) want = 0xfffffff0u;
+      if ((rc = ensure(ctx, ctx->pool, sizeof(PgRun) * want)) != PG_OK) return rc;
+      ctx->pool_cap = (uint32_t)(ctx->pool.cap / sizeof(PgRun));
+   }
+   CU(cudaMemsetAsync(ctx->counters.p, 0, 16, ctx->stream));
+   PgBatch bt;
+   memset(&bt, 0, sizeof(bt));
+   bt.n_reads = n;
+   bt.mode = mode;
+   bt.seq_blob = (const uint8_t *)ctx->seq_blob.p;
+   bt.seq_off = (const uint32_t *)ctx->seq_off.p;
+   bt.matched_d = ctx->have_anchor ? (const uint8_t *)ctx->md.p : nullptr;
+   bt.matched_rel_pos = ctx->have_anchor ? (const uint32_t *)ctx->pos.p : nullptr;
+   bt.insert_size = ctx->have_anchor ? (const int16_t *)ctx->isz.p : nullptr;
+   bt.chr_id = ctx->have_chr ? (const int32_t *)ctx->chr.p : nullptr;
+   bt.close_info = (mode == 2 && ctx->have_close) ? (const PgCloseInfo *)ctx->closeinfo.p : nullptr;
+   bt.regions = ctx->have_regions ? (const PgRegion *)ctx->regions.p : nullptr;
+   bt.region_off = ctx->have_regions ? (const uint32_t *)ctx->region_off.p : nullptr;
+   bt.out = (PgReadOut *)ctx->out.p;
+   bt.run_pool = (PgRun *)ctx->pool.p;
+   bt.run_pool_cap = ctx->pool_cap;
+   bt.counters = (uint32_t *)ctx->counters.p;
+   // variant: words per read plane (LW) and mismatch levels tracked (TL)
+   int need_t = 0;
+   for (uint32_t l = 0; l <= ctx->max_read_len && l < 512; l++) {
+      int t = (int)ctx->prm_h.g[l] + ctx->prm_h.add_mm + 1;
+      if (t > need_t) need_t = t;
+   }
+   if (need_t > 32) return fail(ctx, PG_ERR_UNSUPPORTED, "more than 32 mismatch levels (g_maxMismatch + -a + 1)");
+   if (ctx->max_read_len <= 256 && need_t <= 8) return launch_variant<8, 8>(ctx, bt);
+   if (ctx->max_read_len <= 256 && need_t <= 16) return launch_variant<8, 16>(ctx, bt);
+   if (need_t <= 16) return launch_variant<16, 16>(ctx, bt);
+   return launch_variant<16, 32>(ctx, bt);
+}
+
+int pg_sync(pg_ctx *ctx)
+{
+   if (!ctx) return PG_ERR_ARG;
+   CU(cudaSetDevice(ctx->device));
+   CU(cudaStreamSynchronize(ctx->stream));
+   return PG_OK;
+}
+
+// Waits for the launch; if the run pool was too small, grows it to the exact size and runs again.
+static int finish_launch(pg_ctx *ctx)
+{
+   if (!ctx->launched) return fail(ctx, PG_ERR_STATE, "no launch to wait for");
+   if (ctx->n == 0) { ctx->last_runs = 0; return PG_OK; }
+   for (int attempt = 0; attempt < 3; attempt++) {
+      CU(cudaMemcpyAsync(ctx->counters_h, ctx->counters.p, 16, cudaMemcpyDeviceToHost, ctx->stream));
+      CU(cudaStreamSynchronize(ctx->stream));
+      if (ctx->counters_h[2] == 0) { ctx->last_runs = ctx->counters_h[1]; return PG_OK; }
+      uint32_t need = ctx->counters_h[1];
+      CU(cudaFree(ctx->pool.p));
+      ctx->pool.p = nullptr; ctx->pool.cap = 0; ctx->pool_cap = 0;
+      int rc = ensure(ctx, ctx->pool, sizeof(PgRun) * ((size_t)need + 1024u));
+      if (rc != PG_OK) return rc;
+      ctx->pool_cap = (uint32_t)(ctx->pool.cap / sizeof(PgRun));
+      rc = pg_launch(ctx, ctx->last_mode);
+      if (rc != PG_OK) return rc;
+   }
+   return fail(ctx, PG_ERR_CUDA, "run pool kept overflowing");
+}
+
+int pg_download(pg_ctx *ctx, pg_results *res)
+{
+   if (!ctx || !res) return PG_ERR_ARG;
+   CU(cudaSetDevice(ctx->device));
+   int rc = finish_launch(ctx);
+   if (rc != PG_OK) return rc;
+   res->n_runs = ctx->last_runs;
+   if (ctx->n == 0) return PG_OK;
+   if (!res->out) return fail(ctx, PG_ERR_ARG, "pg_download: out is NULL");
+   if (res->n_runs > res->runs_cap || (res->n_runs && !res->runs))
+      return fail(ctx, PG_ERR_RUNS_CAP, "run buffer too small");
+   CU(cudaMemcpyAsync(res->out, ctx->out.p, sizeof(PgReadOut) * (size_t)ctx->n, cudaMemcpyDeviceToHost, ctx->stream));
+   if (res->n_runs)
+      CU(cudaMemcpyAsync(res->runs, ctx->pool.p, sizeof(PgRun) * (size_t)res->n_runs, cudaMemcpyDeviceToHost, ctx->stream));
+   CU(cudaStreamSynchronize(ctx->stream));
+   return PG_OK;
+}
+
+static int run_all(pg_ctx *ctx, const pg_reads *in, pg_results *res, int mode)
+{
+   int rc = pg_upload(ctx, in);
+   if (rc != PG_OK) return rc;
+   rc = pg_launch(ctx, mode);
+   if (rc != PG_OK) return rc;
+   return pg_download(ctx, res);
+}
+
+int pg_close_end(pg_ctx *ctx, const pg_reads *in, pg_results *res) { return run_all(ctx, in, res, 1); }
+int pg_far_end(pg_ctx *ctx, const pg_reads *in, pg_results *res) { return run_all(ctx, in, res, 2); }
+int pg_search(pg_ctx *ctx, const pg_reads *in, pg_results *res) { return run_all(ctx, in, res, 3); }
+
+uint64_t pg_kernel_launches(pg_ctx *ctx) { return ctx ? ctx->launches : 0; }
+uint32_t pg_last_run_count(pg_ctx *ctx) { return ctx ? ctx->last_runs : 0; }
+
+void *pg_host_alloc(size_t bytes)
+{
+   void *p = nullptr;
+   if (cudaHostAlloc(&p, bytes ? bytes : 1, cudaHostAllocDefault) != cudaSuccess) return nullptr;
+   return p;
+}
+void pg_host_free(void *p) { if (p) cudaFreeHost(p); }
+
+uint32_t pg_expand_runs(const pg_run *runs, uint32_t n_runs, pg_up *out)
+{
+   uint32_t k = 0;
+   for (uint32_t r = 0; r < n_runs; r++) {
+      const pg_run &q = runs[r];
+      for (uint32_t j = 0; j < q.count; j++, k++) {
+         if (!out) continue;
+         pg_up u;
+         u.len = (int16_t)(q.len0 + j);
+         u.abs_loc = (q.dirstrand & 1u) ? q.abs_loc0 - j : q.abs_loc0 + j;
+         u.mm = q.mm;
+         u.dir = q.dirstrand & 1u;
+         u.strand = (q.dirstrand >> 1) & 1u;
+         u.chr = q.chr;
+         out[k] = u;
+      }
+   }
+   return k;
+}
+
+// CleanUniquePoints, src/pindel.cpp:2904-2941: keep the points that share chromosome, direction, strand and
+// terminal (AbsLoc -/+ LengthStr) with the LAST point.
+uint32_t pg_clean_unique_points(pg_up *ups, uint32_t n)
+{
+   if (!ups || n == 0) return 0;
+   pg_up last = ups[n - 1];
+   uint32_t terminal = last.dir == 0 ? last.abs_loc - (uint32_t)last.len : last.abs_loc + (uint32_t)last.len;
+   uint32_t w = 0;
+   for (uint32_t i = 0; i < n; i++) {
+      if (ups[i].chr != last.chr || ups[i].dir != last.dir || ups[i].strand != last.strand) continue;
+      uint32_t t = last.dir == 0 ? ups[i].abs_loc - (uint32_t)ups[i].len : ups[i].abs_loc + (uint32_t)ups[i].len;
+      if (t == terminal) ups[w++] = ups[i];
+   }
+   return w;
+}
+
+} // extern "C"

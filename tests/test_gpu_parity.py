@@ -1,0 +1,84 @@
+"""GPU parity tests proper: the CUDA path, called through the C ABI (pindel_b200.api -> libpindel_pg.so), against
+the oracle on the same seeded inputs.  Bit-exact: positions, lengths, directions, strands, mismatch counts,
+flip state, read length after the search."""
+import numpy as np
+import pytest
+
+from pindel_b200 import api, runs as R, synth
+from tests import helpers as H
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def ref2m():
+    ref = synth.make_reference(2_000_000, 20260925, n_runs=[(700_000, 5000), (1_200_000, 37), (1_500_003, 1)])
+    return ref, synth.pad_reference(ref)
+
+
+def run_gpu(pg, batch, **kw):
+    out, runs = pg.search(**H.batch_kwargs(batch), **kw)
+    return R.per_read(out, runs), out, runs
+
+
+@pytest.mark.parametrize("L,n,seed", [(100, 20000, 11), (150, 20000, 12), (75, 10000, 13), (250, 4000, 14)])
+def test_fused_search_matches_oracle(ref2m, L, n, seed):
+    ref, padded = ref2m
+    batch = synth.make_reads(ref, n, L, seed=seed)
+    pg = api.PatternGrowth()
+    pg.set_reference([padded])
+    got, out, runs = run_gpu(pg, batch)
+    exp = H.oracle_results([padded], batch)
+    H.compare(exp, got, "fused L=%d" % L)
+    assert pg.kernel_launches >= 1
+    assert (out["flags"] & (R.F_TOOLONG | R.F_OVERFLOW)).sum() == 0
+    pg.close()
+
+
+def test_close_then_far_equals_fused(ref2m):
+    ref, padded = ref2m
+    batch = synth.make_reads(ref, 8000, 100, seed=21)
+    pg = api.PatternGrowth()
+    pg.set_reference([padded])
+    fused, _, _ = run_gpu(pg, batch)
+    kw = H.batch_kwargs(batch)
+    out_c, runs_c = pg.get_close_end(**kw)
+    close = R.per_read(out_c, runs_c)
+    # host side of the seam: flip the sequences that GetCloseEnd flipped, derive close_info
+    seqs = batch.seq.copy()
+    comp = np.zeros(256, dtype=np.uint8)
+    for a, b in zip(b"ACGTN", b"TGCAN"):
+        comp[a] = b
+    ci = np.zeros(batch.n, dtype=R.CLOSEINFO_DT)
+    for i, r in enumerate(close):
+        if r["flip"]:
+            seqs[i] = comp[seqs[i][::-1]]
+        if len(r["close"]):
+            ci["last_abs_loc"][i] = r["close"][-1][1]
+            ci["max_len"][i] = r["close"][-1][0]
+    out_f, runs_f = pg.search_far_ends(seq_blob=seqs.reshape(-1), seq_off=kw["seq_off"], close_info=ci)
+    far = R.per_read(out_f, runs_f)
+    for i in range(batch.n):
+        assert np.array_equal(close[i]["close_raw"], fused[i]["close_raw"]), i
+        assert np.array_equal(far[i]["far"], fused[i]["far"]), i
+    pg.close()
+
+
+@pytest.mark.parametrize("settings", [dict(max_range_index=4, max_mismatch_rate=0.05),
+                                      dict(additional_mismatch=2, min_perfect_match=5, min_close=10, seq_error_rate=0.03)])
+def test_non_default_settings(ref2m, settings):
+    ref, padded = ref2m
+    batch = synth.make_reads(ref, 6000, 100, seed=31, max_del=20000)
+    pg = api.PatternGrowth(**settings)
+    pg.set_reference([padded])
+    got, out, _ = run_gpu(pg, batch)
+    exp = H.oracle_results([padded], batch, **settings)
+    H.compare(exp, got, str(settings))
+    pg.close()
+
+
+def test_table_matches_oracle():
+    from oracle import pgoracle
+    pg = api.PatternGrowth()
+    assert np.array_equal(pg.max_mismatch_table(), pgoracle.prob_table())
+    pg.close()
