@@ -151,6 +151,14 @@ int pg_sync(pg_ctx *ctx);
 uint64_t pg_kernel_launches(pg_ctx *ctx);      /* search-kernel launches since pg_create */
 uint32_t pg_last_run_count(pg_ctx *ctx);       /* runs produced by the last completed launch (valid after pg_sync/pg_download) */
 
+/* Statistics of the last completed launch (waits for it): reference positions scanned (sum of the window sizes of every
+ * search executed, the W terms of the algorithmic-bytes formula in DESIGN.md) and UniquePoints produced. */
+int pg_last_stats(pg_ctx *ctx, uint64_t *window_bases, uint64_t *unique_points);
+
+/* Device pointers of the last completed launch's results (pg_read_out[n], pg_run[n_runs]), valid until the next
+ * pg_launch/pg_upload; for callers that hand the records to a collective (NCCL gather) without a host round trip. */
+int pg_device_results(pg_ctx *ctx, void **out_dev, void **runs_dev, uint32_t *n_runs);
+
 /* Pinned host memory for batch buffers (optional; any host pointer is accepted by the calls above). */
 void *pg_host_alloc(size_t bytes);
 void pg_host_free(void *p);

@@ -124,7 +124,7 @@ void pgref_update_bd(void) { g_bdData.UpdateBD(*g_state); }
 void pgref_free(void *p) { free(p); }
 
 /* Runs the reference on n reads (all anchored on chromosome chr, as in one Pindel window).
- * mode bit0: close end (always), bit1: far end.  threads = OpenMP threads.
+ * mode bit0: close end (always), bit1: far end, bit2: timing only (no output stream).  threads = OpenMP threads.
  * Output: malloc'ed int32 stream, per read
  *   [flip, L_after, n_close_raw, n_close_clean, n_far, n_cluster_regions,
  *    close_raw UPs.., close_clean UPs.., far UPs.. (6 ints each: len, absLoc, dir, strand, mm, chr),
@@ -192,6 +192,11 @@ int64_t pgref_search(int n, const char *seq_blob, const uint32_t *seq_off, const
    }
 
    std::vector<int32_t> out;
+   if (mode & 4) { // timing only: no result stream
+      int32_t *buf0 = (int32_t *)malloc(4);
+      *out_stream = buf0;
+      return 0;
+   }
    out.reserve((size_t)n * 64);
    size_t k = 0;
    for (int i = 0; i < n; i++) {

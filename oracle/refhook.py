@@ -105,7 +105,7 @@ class RefHook:
         if self.lib.pgref_set_window(chr_id, C.c_uint32(start), C.c_uint32(end)) != 0:
             raise RuntimeError("pgref_set_window failed")
 
-    def search(self, seq_blob, seq_off, matched_d, rel_pos, insert_size, chr_id=0, far=True, threads=1):
+    def search(self, seq_blob, seq_off, matched_d, rel_pos, insert_size, chr_id=0, far=True, threads=1, timing_only=False):
         """Returns (stream int32 array, (close_seconds, far_seconds)).  See parse_stream()."""
         n = len(seq_off) - 1
         seq_blob = np.ascontiguousarray(seq_blob, dtype=np.uint8)
@@ -121,7 +121,7 @@ class RefHook:
         try:
             ln = self.lib.pgref_search(n, seq_blob.ctypes.data_as(C.c_void_p), seq_off.ctypes.data_as(C.c_void_p),
                                        matched_d.ctypes.data_as(C.c_void_p), rel_pos.ctypes.data_as(C.c_void_p),
-                                       insert_size.ctypes.data_as(C.c_void_p), chr_id, 3 if far else 1, threads,
+                                       insert_size.ctypes.data_as(C.c_void_p), chr_id, (3 if far else 1) | (4 if timing_only else 0), threads,
                                        C.byref(out), secs)
         finally:
             os.dup2(saved, 1)

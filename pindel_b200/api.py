@@ -14,7 +14,7 @@ import numpy as np
 from . import runs as R
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libpindel_pg.so")
+LIB_PATH = os.environ.get("PG_LIB", os.path.join(HERE, "libpindel_pg.so"))
 
 PG_OK, PG_ERR_ARG, PG_ERR_CUDA, PG_ERR_STATE, PG_ERR_RUNS_CAP, PG_ERR_UNSUPPORTED = range(6)
 
@@ -70,6 +70,8 @@ def load_library() -> C.CDLL:
         lib.pg_launch.argtypes = [C.c_void_p, C.c_int32]
         lib.pg_download.argtypes = [C.c_void_p, C.POINTER(_Results)]
         lib.pg_sync.argtypes = [C.c_void_p]
+        lib.pg_last_stats.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+        lib.pg_device_results.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
         _lib = lib
     return _lib
 
@@ -216,6 +218,18 @@ class PatternGrowth:
     def search(self, **batch):
         """GetCloseEnd + SearchFarEnd per read, fused on the device."""
         return self._call(self.lib.pg_search, "pg_search", **batch)
+
+    def last_stats(self):
+        """(reference positions scanned, UniquePoints produced) by the last launch; waits for it."""
+        wb, up = C.c_uint64(0), C.c_uint64(0)
+        self._check(self.lib.pg_last_stats(self.ctx, C.byref(wb), C.byref(up)), "pg_last_stats")
+        return int(wb.value), int(up.value)
+
+    def device_results(self):
+        """(out device pointer, runs device pointer, n_runs) of the last launch; waits for it."""
+        o, r, k = C.c_void_p(0), C.c_void_p(0), C.c_uint32(0)
+        self._check(self.lib.pg_device_results(self.ctx, C.byref(o), C.byref(r), C.byref(k)), "pg_device_results")
+        return int(o.value or 0), int(r.value or 0), int(k.value)
 
     @property
     def kernel_launches(self) -> int:

@@ -51,6 +51,7 @@ PG_DEV uint32_t pg_brev(uint32_t v) { return __brev(v); }
 PG_DEV uint32_t pg_fsr(uint32_t lo, uint32_t hi, uint32_t s) { return __funnelshift_r(lo, hi, s); }
 PG_DEV uint32_t pg_fsrc(uint32_t lo, uint32_t hi, uint32_t s) { return __funnelshift_rc(lo, hi, s); }
 PG_DEV uint32_t pg_atomic_add(uint32_t *p, uint32_t v) { return atomicAdd(p, v); }
+PG_DEV void pg_atomic_add64(unsigned long long *p, unsigned long long v) { atomicAdd(p, v); }
 PG_DEV uint32_t pg_umax(uint32_t a, uint32_t b) { return max(a, b); }
 PG_DEV uint32_t pg_umin(uint32_t a, uint32_t b) { return min(a, b); }
 PG_DEV uint32_t pg_ldg32(const uint32_t *p) { return __ldg(p); }
@@ -300,17 +301,18 @@ PG_DEV void pg_scan_window(PgWarpCtx<LW, TL> &cx, const PgSearch &se, int chr_id
          bool seed = active && !(mism & 1u);
          uint32_t m0 = mism & ~1u;
          int cnt = pg_popc(m0);
-         bool hot = seed && cnt >= se.T;
+         // "hot" seeds are decided inside their first 32 bases: all TL tracked levels get their mismatch index from
+         // this one word (levels >= T carry values nobody reads).  Everything else is finished cooperatively.
+         bool hot = seed && cnt >= TL;
          bool slow = seed && !hot;
          if (hot) {
             uint32_t idx = p - origin;
+            uint32_t mrev = pg_brev(m0);          // mismatch at read index j <-> bit 31-j: clz walks the indices upwards
 #pragma unroll
             for (int t = 0; t < TL; t++) {
-               if (t < se.T) {
-                  uint32_t D = (uint32_t)(pg_ffs(m0) - 1);
-                  m0 &= m0 - 1;
-                  pg_key_update(ka_[t], kb_[t], (D << PG_IDX_BITS) | idx);
-               }
+               uint32_t D = (uint32_t)pg_clz(mrev);
+               mrev &= ~(0x80000000u >> D);
+               pg_key_update(ka_[t], kb_[t], D * (1u << PG_IDX_BITS) + idx);
             }
          }
          uint32_t seedmask = pg_ballot(seed);
@@ -326,22 +328,20 @@ PG_DEV void pg_scan_window(PgWarpCtx<LW, TL> &cx, const PgSearch &se, int chr_id
       // fold the tile's lane-local top-2 into the warp-level state of lane t
 #pragma unroll
       for (int t = 0; t < TL; t++) {
-         if (t < se.T) {
-            uint32_t ka = pg_redux_max(ka_[t]);
-            uint32_t mine = (ka_[t] == ka) ? kb_[t] : ka_[t];
-            uint32_t kb = pg_redux_max(mine);
-            if (lane == t && ka != 0) {
-               uint32_t pos = origin + (ka & PG_IDX_MASK);
-               uint32_t minus = 0;
-               if (se.far) {
-                  int wi = (int)((int64_t)(pos >> 5) - w0);
-                  uint2 wv = ws->tile[wi];
-                  uint32_t rlo = (wv.x >> (pos & 31)) & 1u, rhi = (wv.y >> (pos & 31)) & 1u;
-                  minus = (rlo != c0lo || rhi != c0hi) ? 1u : 0u;
-               }
-               pg_level_merge(cx.lvl, ka >> PG_IDX_BITS, pos, ((uint32_t)chr_id << 1) | minus);
-               if (kb != 0) pg_level_merge(cx.lvl, kb >> PG_IDX_BITS, 0xffffffffu, 0);
+         uint32_t ka = pg_redux_max(ka_[t]);
+         uint32_t mine = (ka_[t] == ka) ? kb_[t] : ka_[t];
+         uint32_t kb = pg_redux_max(mine);
+         if (lane == t && ka != 0) {
+            uint32_t pos = origin + (ka & PG_IDX_MASK);
+            uint32_t minus = 0;
+            if (se.far) {
+               int wi = (int)((int64_t)(pos >> 5) - w0);
+               uint2 wv = ws->tile[wi];
+               uint32_t rlo = (wv.x >> (pos & 31)) & 1u, rhi = (wv.y >> (pos & 31)) & 1u;
+               minus = (rlo != c0lo || rhi != c0hi) ? 1u : 0u;
             }
+            pg_level_merge(cx.lvl, ka >> PG_IDX_BITS, pos, ((uint32_t)chr_id << 1) | minus);
+            if (kb != 0) pg_level_merge(cx.lvl, kb >> PG_IDX_BITS, 0xffffffffu, 0);
          }
       }
       pg_syncwarp();
@@ -607,6 +607,7 @@ PG_DEV void pg_process_read(PgWarpCtx<LW, TL> &cx, const PgBatch &bt, int ri, Pg
    int st = ST_DONE;
    int range_index = 0;        // GetCloseEnd: RangeIndex 0..1
    bool second_try = false;    // GetCloseEnd: the attempt after setUnmatchedSeq(ReverseComplement())
+   unsigned long long window_bases = 0;   // reference positions scanned for this read (bench statistics)
    int k = 1;                  // SearchFarEnd: rangeIndex 1..MaxRangeIndex+1
    uint32_t span = 64;         // START_SEARCH_SPAN
    if (bt.mode & 1) {
@@ -670,7 +671,10 @@ PG_DEV void pg_process_read(PgWarpCtx<LW, TL> &cx, const PgBatch &bt, int ri, Pg
                if (ee < ss) ee = ss;
                s = (uint32_t)ss; e = (uint32_t)ee;
             }
-            if (e > s) pg_scan_window<LW, TL>(cx, se, rg.chr, s, e, phase);
+            if (e > s) {
+               pg_scan_window<LW, TL>(cx, se, rg.chr, s, e, phase);
+               window_bases += (unsigned long long)(e - s);
+            }
          }
       }
       PgResult res = pg_walk_emit<LW, TL>(cx, se, dst, cap);
@@ -717,6 +721,11 @@ PG_DEV void pg_process_read(PgWarpCtx<LW, TL> &cx, const PgBatch &bt, int ri, Pg
       pg_syncwarp();
       for (uint32_t i = (uint32_t)lane; i < total; i += 32) bt.run_pool[off + i] = (i < ncl) ? closeBuf[i] : farBest[i - ncl];
    }
-   if (lane == 0) bt.out[ri] = ro;
+   if (lane == 0) {
+      bt.out[ri] = ro;
+      // statistics for the roofline arithmetic: counters[4..5] = window bases, [6..7] = UniquePoints (64-bit each)
+      pg_atomic_add64((unsigned long long *)(bt.counters + 4), window_bases);
+      pg_atomic_add64((unsigned long long *)(bt.counters + 6), (unsigned long long)(((bt.mode & 1) ? cres.n_ups : 0u) + best.n_ups));
+   }
    pg_syncwarp();
 }

@@ -88,7 +88,7 @@ struct PgBatch {
    PgReadOut *out;                  // [n]
    PgRun *run_pool;
    uint32_t run_pool_cap;
-   uint32_t *counters;              // [0] next read, [1] runs allocated, [2] overflow flag
+   uint32_t *counters;              // [8]: [0] next read, [1] runs allocated, [2] overflow flag, [4..5] window bases, [6..7] UniquePoints
    PgRun *scratch;                  // [n_warps * 3 * scratch_cap]
    uint32_t scratch_cap;
 };

@@ -26,6 +26,9 @@ static_assert(sizeof(pg_close_info) == sizeof(PgCloseInfo) && sizeof(pg_close_in
 static_assert(PG_READ_FLIPPED == PG_F_FLIPPED && PG_READ_UNSUPPORTED == PG_F_TOOLONG && PG_READ_OVERFLOW == PG_F_OVERFLOW, "flags");
 
 #define PG_BLOCK_THREADS 256
+#ifndef PG_MINB
+#define PG_MINB 3          // resident CTAs per SM the register allocator is asked to make room for (TL <= 8 variants)
+#endif
 #define PG_WARPS_PER_BLOCK (PG_BLOCK_THREADS / 32)
 
 // ------------------------------------------------------------------------------------------------
@@ -61,7 +64,7 @@ __device__ __forceinline__ void pg_tile_load(PgWarpSmem<LW, TL> *ws, const PgChr
 }
 
 template <int LW, int TL>
-__global__ void __launch_bounds__(PG_BLOCK_THREADS) pg_search_kernel(PgBatch bt, const PgParams *__restrict__ prm_g,
+__global__ void __launch_bounds__(PG_BLOCK_THREADS, (TL <= 8) ? PG_MINB : 1) pg_search_kernel(PgBatch bt, const PgParams *__restrict__ prm_g,
                                                                      const PgChrom *__restrict__ chroms)
 {
    extern __shared__ __align__(128) unsigned char pg_dyn_smem[];
@@ -144,6 +147,7 @@ struct pg_ctx {
    bool launched = false;
    uint64_t launches = 0;
    uint32_t last_runs = 0;
+   uint64_t last_window_bases = 0, last_ups = 0;
 };
 
 static thread_local std::string g_create_error;
@@ -242,7 +246,7 @@ pg_ctx *pg_create(const pg_settings *s)
              cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking) == cudaSuccess &&
              cudaMalloc(&ctx->prm_d, sizeof(PgParams)) == cudaSuccess &&
              cudaMemcpy(ctx->prm_d, &ctx->prm_h, sizeof(PgParams), cudaMemcpyHostToDevice) == cudaSuccess &&
-             cudaHostAlloc((void **)&ctx->counters_h, 16, cudaHostAllocDefault) == cudaSuccess;
+             cudaHostAlloc((void **)&ctx->counters_h, 32, cudaHostAllocDefault) == cudaSuccess;
    if (!ok) {
       g_create_error = std::string("CUDA initialisation failed: ") + cudaGetErrorString(cudaGetLastError());
       delete ctx;
@@ -398,14 +402,14 @@ int pg_launch(pg_ctx *ctx, int32_t mode)
    const int n = ctx->n;
    int rc;
    if ((rc = ensure(ctx, ctx->out, sizeof(PgReadOut) * (size_t)n)) != PG_OK) return rc;
-   if ((rc = ensure(ctx, ctx->counters, 16)) != PG_OK) return rc;
+   if ((rc = ensure(ctx, ctx->counters, 32)) != PG_OK) return rc;
    if (ctx->pool_cap == 0 || ctx->pool.p == nullptr) {
       size_t want = (size_t)n * 24u + 4096u;
       if (want > 0xfffffff0u) want = 0xfffffff0u;
       if ((rc = ensure(ctx, ctx->pool, sizeof(PgRun) * want)) != PG_OK) return rc;
       ctx->pool_cap = (uint32_t)(ctx->pool.cap / sizeof(PgRun));
    }
-   CU(cudaMemsetAsync(ctx->counters.p, 0, 16, ctx->stream));
+   CU(cudaMemsetAsync(ctx->counters.p, 0, 32, ctx->stream));
    PgBatch bt;
    memset(&bt, 0, sizeof(bt));
    bt.n_reads = n;
@@ -430,8 +434,17 @@ int pg_launch(pg_ctx *ctx, int32_t mode)
       if (t > need_t) need_t = t;
    }
    if (need_t > 32) return fail(ctx, PG_ERR_UNSUPPORTED, "more than 32 mismatch levels (g_maxMismatch + -a + 1)");
-   if (ctx->max_read_len <= 256 && need_t <= 8) return launch_variant<8, 8>(ctx, bt);
-   if (ctx->max_read_len <= 256 && need_t <= 16) return launch_variant<8, 16>(ctx, bt);
+   // TL = mismatch levels tracked per seed: the smallest compiled value that covers the batch (exact for the
+   // common single-read-length batch, so the per-level loops carry no dead levels)
+   if (ctx->max_read_len <= 256) {
+      if (need_t <= 5) return launch_variant<8, 5>(ctx, bt);
+      if (need_t <= 6) return launch_variant<8, 6>(ctx, bt);
+      if (need_t <= 7) return launch_variant<8, 7>(ctx, bt);
+      if (need_t <= 8) return launch_variant<8, 8>(ctx, bt);
+      if (need_t <= 12) return launch_variant<8, 12>(ctx, bt);
+      if (need_t <= 16) return launch_variant<8, 16>(ctx, bt);
+   }
+   if (need_t <= 8) return launch_variant<16, 8>(ctx, bt);
    if (need_t <= 16) return launch_variant<16, 16>(ctx, bt);
    return launch_variant<16, 32>(ctx, bt);
 }
@@ -450,9 +463,14 @@ static int finish_launch(pg_ctx *ctx)
    if (!ctx->launched) return fail(ctx, PG_ERR_STATE, "no launch to wait for");
    if (ctx->n == 0) { ctx->last_runs = 0; return PG_OK; }
    for (int attempt = 0; attempt < 3; attempt++) {
-      CU(cudaMemcpyAsync(ctx->counters_h, ctx->counters.p, 16, cudaMemcpyDeviceToHost, ctx->stream));
+      CU(cudaMemcpyAsync(ctx->counters_h, ctx->counters.p, 32, cudaMemcpyDeviceToHost, ctx->stream));
       CU(cudaStreamSynchronize(ctx->stream));
-      if (ctx->counters_h[2] == 0) { ctx->last_runs = ctx->counters_h[1]; return PG_OK; }
+      if (ctx->counters_h[2] == 0) {
+         ctx->last_runs = ctx->counters_h[1];
+         memcpy(&ctx->last_window_bases, ctx->counters_h + 4, 8);
+         memcpy(&ctx->last_ups, ctx->counters_h + 6, 8);
+         return PG_OK;
+      }
       uint32_t need = ctx->counters_h[1];
       CU(cudaFree(ctx->pool.p));
       ctx->pool.p = nullptr; ctx->pool.cap = 0; ctx->pool_cap = 0;
@@ -498,6 +516,29 @@ int pg_search(pg_ctx *ctx, const pg_reads *in, pg_results *res) { return run_all
 
 uint64_t pg_kernel_launches(pg_ctx *ctx) { return ctx ? ctx->launches : 0; }
 uint32_t pg_last_run_count(pg_ctx *ctx) { return ctx ? ctx->last_runs : 0; }
+
+int pg_last_stats(pg_ctx *ctx, uint64_t *window_bases, uint64_t *unique_points)
+{
+   if (!ctx) return PG_ERR_ARG;
+   CU(cudaSetDevice(ctx->device));
+   int rc = finish_launch(ctx);
+   if (rc != PG_OK) return rc;
+   if (window_bases) *window_bases = ctx->last_window_bases;
+   if (unique_points) *unique_points = ctx->last_ups;
+   return PG_OK;
+}
+
+int pg_device_results(pg_ctx *ctx, void **out_dev, void **runs_dev, uint32_t *n_runs)
+{
+   if (!ctx) return PG_ERR_ARG;
+   CU(cudaSetDevice(ctx->device));
+   int rc = finish_launch(ctx);
+   if (rc != PG_OK) return rc;
+   if (out_dev) *out_dev = ctx->out.p;
+   if (runs_dev) *runs_dev = ctx->pool.p;
+   if (n_runs) *n_runs = ctx->last_runs;
+   return PG_OK;
+}
 
 void *pg_host_alloc(size_t bytes)
 {

@@ -151,3 +151,77 @@ def make_reads(ref: np.ndarray, n: int, read_len: int, seed: int, insert_size: i
         mpos[c0:c0 + m] = np.where(plus, pos_plus, pos_minus).astype(np.uint32)
         kinds[c0:c0 + m] = kind
     return ReadBatch(seqs, md, mpos, np.full(n, insert_size, dtype=np.int16), kinds)
+
+
+def make_reads_torch(ref_t, n: int, read_len: int, seed: int, insert_size: int = 500, mix=(0.60, 0.25, 0.05, 0.10),
+                     decoy_frac: float = 0.10, max_del: int = 1000, sub_rate: float = 0.01, n_rate: float = 0.001,
+                     chunk: int = 1 << 20, lo=None, hi=None):
+    """Same read model as make_reads(), generated with torch ops on ref_t's device (bench-sized batches:
+    10 M x 150 bp in seconds on a GPU).  ref_t: uint8 ASCII tensor (unpadded).  Returns torch tensors
+    (seq [n, L] uint8, matched_d [n] uint8, matched_rel_pos [n] int64, insert_size [n] int16, kind [n] uint8).
+    The random stream differs from the numpy generator; the distribution is the same."""
+    import torch
+    dev = ref_t.device
+    L, G = read_len, ref_t.numel()
+    margin = 4 * insert_size + 3 * L + max_del + 4096
+    lo = margin if lo is None else max(lo, margin)
+    hi = G - margin if hi is None else min(hi, G - margin)
+    if hi <= lo:
+        raise ValueError("reference too small for the requested read model")
+    gen = torch.Generator(device=dev)
+    gen.manual_seed(seed)
+    comp = torch.zeros(256, dtype=torch.uint8, device=dev)
+    for a_, b_ in zip(b"ACGTN", b"TGCAN"):
+        comp[a_] = b_
+    code = torch.zeros(256, dtype=torch.int64, device=dev)
+    code[ord("C")], code[ord("G")], code[ord("T")] = 1, 2, 3
+    acgt = torch.tensor(list(b"ACGT"), dtype=torch.uint8, device=dev)
+    cum = torch.cumsum(torch.tensor(mix, dtype=torch.float64, device=dev), 0)
+    cum = cum / cum[-1]
+    ar = torch.arange(L, device=dev, dtype=torch.int64)[None, :]
+    seqs = torch.empty((n, L), dtype=torch.uint8, device=dev)
+    md = torch.empty(n, dtype=torch.uint8, device=dev)
+    mpos = torch.empty(n, dtype=torch.int64, device=dev)
+    kinds = torch.empty(n, dtype=torch.uint8, device=dev)
+
+    def rnd(*shape):
+        return torch.rand(*shape, generator=gen, device=dev, dtype=torch.float64)
+
+    def rint(lo_, hi_, *shape):
+        return torch.randint(lo_, hi_, shape, generator=gen, device=dev, dtype=torch.int64)
+
+    for c0 in range(0, n, chunk):
+        m = min(chunk, n - c0)
+        kind = torch.searchsorted(cum, rnd(m), right=True).clamp_(max=3)
+        kind = torch.where(rnd(m) < decoy_frac, torch.full_like(kind, 4), kind)
+        k = rint(20, L - 20 + 1, m)
+        a = rint(lo, hi, m)
+        dsz = torch.exp(rnd(m) * float(np.log(max_del))).to(torch.int64)
+        isz = rint(1, 51, m)
+        vsz = rint(50, max_del + 1, m)
+        first = ar < k[:, None]
+        b = torch.where(kind == 0, a + dsz, a)
+        b = torch.where(kind == 3, a - vsz, b)
+        b = torch.where(kind == 2, a + vsz, b)
+        j2 = ar - k[:, None]
+        ins = kind == 1
+        j2 = torch.where(ins[:, None], j2 - isz[:, None], j2)
+        idx2 = torch.where((kind == 2)[:, None], b[:, None] - 1 - j2, b[:, None] + j2)
+        idxm = torch.where(first, a[:, None] - k[:, None] + ar, idx2).clamp_(0, G - 1)
+        inserted = ins[:, None] & (~first) & (j2 < 0)
+        plus = rnd(m) < 0.5
+        t = torch.where(plus[:, None], ref_t[idxm], comp[ref_t[G - 1 - idxm].long()])
+        inv2 = (kind == 2)[:, None] & (~first)
+        t = torch.where(inv2, comp[t.long()], t)
+        t = torch.where(inserted, acgt[rint(0, 4, m, L)], t)
+        err = torch.rand(m, L, generator=gen, device=dev) < sub_rate
+        sub = acgt[(code[t.long()] + rint(1, 4, m, L)) & 3]
+        t = torch.where(err & (t != ord("N")), sub, t)
+        t = torch.where(torch.rand(m, L, generator=gen, device=dev) < n_rate, torch.full_like(t, ord("N")), t)
+        slack = rint(1, max(2, insert_size - L), m)
+        g_first = a - k
+        seqs[c0:c0 + m] = comp[t.flip(1).long()]
+        md[c0:c0 + m] = torch.where(plus, torch.full_like(k, ord("+")), torch.full_like(k, ord("-"))).to(torch.uint8)
+        mpos[c0:c0 + m] = torch.where(plus, g_first - slack, (G - 1 - g_first) + slack)
+        kinds[c0:c0 + m] = kind.to(torch.uint8)
+    return seqs, md, mpos, torch.full((n,), insert_size, dtype=torch.int16, device=dev), kinds

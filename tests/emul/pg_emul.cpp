@@ -108,6 +108,7 @@ PG_DEV uint32_t pg_brev(uint32_t v)
 PG_DEV uint32_t pg_fsr(uint32_t lo, uint32_t hi, uint32_t s) { uint64_t v = ((uint64_t)hi << 32) | lo; return (uint32_t)(v >> (s & 31)); }
 PG_DEV uint32_t pg_fsrc(uint32_t lo, uint32_t hi, uint32_t s) { uint64_t v = ((uint64_t)hi << 32) | lo; if (s > 32) s = 32; return (uint32_t)(v >> s); }
 PG_DEV uint32_t pg_atomic_add(uint32_t *p, uint32_t v) { uint32_t o = *p; *p = o + v; return o; }
+PG_DEV void pg_atomic_add64(unsigned long long *p, unsigned long long v) { *p += v; }
 PG_DEV uint32_t pg_umax(uint32_t a, uint32_t b) { return a > b ? a : b; }
 PG_DEV uint32_t pg_umin(uint32_t a, uint32_t b) { return a < b ? a : b; }
 PG_DEV uint32_t pg_ldg32(const uint32_t *p) { return *p; }
@@ -183,7 +184,7 @@ int pgemu_search(int n_chr, const char *const *chr_seq, const uint32_t *chr_len,
       chroms[i].len = packed[i].len;
       chroms[i].nwords = packed[i].nwords;
    }
-   uint32_t counters[4] = {0, 0, 0, 0};
+   alignas(8) uint32_t counters[8] = {0, 0, 0, 0, 0, 0, 0, 0};
    std::vector<PgRun> scratch(3 * 512);
    PgBatch bt;
    bt.n_reads = n_reads; bt.mode = mode; bt.seq_blob = seq_blob; bt.seq_off = seq_off;
@@ -197,8 +198,14 @@ int pgemu_search(int n_chr, const char *const *chr_seq, const uint32_t *chr_len,
    for (int i = 0; i < n_reads; i++) if (seq_off[i + 1] - seq_off[i] > maxlen) maxlen = seq_off[i + 1] - seq_off[i];
    int need_t = 0;
    for (uint32_t l = 0; l <= maxlen && l < 512; l++) if ((int)prm->g[l] + prm->add_mm + 1 > need_t) need_t = (int)prm->g[l] + prm->add_mm + 1;
-   if (maxlen <= 256 && need_t <= 8) run_variant<8, 8>(bt, prm, chroms.data());
+   if (maxlen <= 256 && need_t <= 5) run_variant<8, 5>(bt, prm, chroms.data());
+   else if (maxlen <= 256 && need_t <= 6) run_variant<8, 6>(bt, prm, chroms.data());
+   else if (maxlen <= 256 && need_t <= 7) run_variant<8, 7>(bt, prm, chroms.data());
+   else if (maxlen <= 256 && need_t <= 8) run_variant<8, 8>(bt, prm, chroms.data());
+   else if (maxlen <= 256 && need_t <= 12) run_variant<8, 12>(bt, prm, chroms.data());
    else if (maxlen <= 256 && need_t <= 16) run_variant<8, 16>(bt, prm, chroms.data());
+   else if (need_t <= 8) run_variant<16, 8>(bt, prm, chroms.data());
+   else if (need_t <= 16) run_variant<16, 16>(bt, prm, chroms.data());
    else run_variant<16, 32>(bt, prm, chroms.data());
    if (n_runs_used) *n_runs_used = counters[1];
    return (int)counters[2];
