@@ -130,15 +130,6 @@ def workload_name(a, n_total):
 
 
 # ---------------------------------------------------------------------------------------------------------------
-def shard_windows(ref_bases, rank, world):
-    """10 Mbp anchor windows dealt round-robin to the ranks; world 1 -> the whole reference."""
-    if world == 1:
-        return [(0, ref_bases)]
-    wins = [(s, min(s + SHARD, ref_bases)) for s in range(0, ref_bases, SHARD)]
-    mine = [w for i, w in enumerate(wins) if i % world == rank]
-    return mine or [wins[rank % len(wins)]]
-
-
 def make_batch_torch(ref_t, n, L, seed, windows):
     """Reads of this rank: the generator is run once per assigned window with a proportional share of n."""
     import torch
@@ -218,7 +209,7 @@ def main():
 
     import torch
     import torch.distributed as dist
-    from pindel_b200 import api, runs as R, synth
+    from pindel_b200 import api, runs as R, shard, synth
 
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device -- the search path has no CPU fallback (use --impl reference for the CPU reference)")
@@ -234,7 +225,7 @@ def main():
     ref_np = synth.make_reference(a.ref_bases, REF_SEED)
     padded = synth.pad_reference(ref_np)
     ref_t = torch.from_numpy(ref_np).to(dev)
-    seq_t, md_t, pos_t, isz_t, kind_t = make_batch_torch(ref_t, n, L, 777 + rank, shard_windows(a.ref_bases, rank, world))
+    seq_t, md_t, pos_t, isz_t, kind_t = make_batch_torch(ref_t, n, L, 777 + rank, shard.shard_windows(a.ref_bases, rank, world))
     del ref_t
     log("workload generated in %.1fs" % (time.time() - t0))
 
@@ -265,24 +256,13 @@ def main():
     runs_h = api.pinned_empty(max(1024, 8 * n), R.RUN_DT)
 
     def gather_records():
-        """The single NCCL collective of the path: breakpoint records (per-read headers + runs) to rank 0."""
+        """The single collective of the path: breakpoint records (per-read headers + runs) to rank 0 over NCCL."""
         if world == 1:
             return
         optr, rptr, nruns = pg.device_results()
-        cnt = torch.tensor([nruns], device=dev, dtype=torch.int64)
-        dist.all_reduce(cnt, op=dist.ReduceOp.MAX)
-        cap = int(cnt.item())
         out_d = torch.as_tensor(DevArr(optr, n * R.OUT_DT.itemsize), device=dev)
-        runs_d = torch.zeros(cap * R.RUN_DT.itemsize, dtype=torch.uint8, device=dev)
-        runs_d[:nruns * R.RUN_DT.itemsize] = torch.as_tensor(DevArr(rptr, max(1, nruns * R.RUN_DT.itemsize)), device=dev)[:nruns * R.RUN_DT.itemsize]
-        if rank == 0:
-            og = [torch.empty_like(out_d) for _ in range(world)]
-            rg = [torch.empty_like(runs_d) for _ in range(world)]
-            dist.gather(out_d, og, dst=0)
-            dist.gather(runs_d, rg, dst=0)
-        else:
-            dist.gather(out_d, None, dst=0)
-            dist.gather(runs_d, None, dst=0)
+        runs_d = torch.as_tensor(DevArr(rptr, max(1, nruns * R.RUN_DT.itemsize)), device=dev)[:nruns * R.RUN_DT.itemsize]
+        shard.gather_records(out_d, runs_d, dst=0)
 
     def step_resident():
         pg.launch(3)

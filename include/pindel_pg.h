@@ -73,6 +73,9 @@ typedef struct pg_up {
 #define PG_READ_FLIPPED 1u      /* UnmatchedSeq must be reverse-complemented on the host (GetCloseEnd mutates the read, src/pindel.cpp:2545) */
 #define PG_READ_UNSUPPORTED 2u  /* read not searched (see PG_ERR_UNSUPPORTED) */
 #define PG_READ_OVERFLOW 4u     /* internal: never visible after a successful call */
+#define PG_READ_NFLIPS(flags) (((flags) >> 8) & 3u)  /* times GetCloseEnd ran setUnmatchedSeq(ReverseComplement(seq)) on this read
+                                                        (0..2); replay them on the host copy of the read, in order: a flip maps
+                                                        non-ACGTN bases to NUL and strips the ones that end up trailing */
 
 typedef struct pg_read_out {
    uint32_t run_off;        /* this read's runs: runs[run_off .. run_off + n_close_runs) = UP_Close (before CleanUniquePoints), */

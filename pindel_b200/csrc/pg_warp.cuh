@@ -712,7 +712,7 @@ PG_DEV void pg_process_read(PgWarpCtx<LW, TL> &cx, const PgBatch &bt, int ri, Pg
    if (lane == 0 && total) off = pg_atomic_add(bt.counters + 1, total);
    off = pg_shfl(off, 0);
    ro.len_after = (uint16_t)L;
-   ro.flags = (uint16_t)((flips & 1u) ? PG_F_FLIPPED : 0u);
+   ro.flags = (uint16_t)(((flips & 1u) ? PG_F_FLIPPED : 0u) | ((flips & 3u) << PG_F_NFLIPS_SHIFT));
    if (total && (off + total > bt.run_pool_cap || ncl > cap || best.n_runs > cap)) {
       ro.flags |= PG_F_OVERFLOW;
       if (lane == 0) bt.counters[2] = 1;

@@ -24,6 +24,7 @@ struct uint2 { uint32_t x, y; };
 #define PG_F_FLIPPED 1u     // UnmatchedSeq was reverse-complemented an odd number of times
 #define PG_F_TOOLONG 2u     // read longer than the compiled limit -> not searched
 #define PG_F_OVERFLOW 4u    // run pool exhausted -> results of this read dropped
+#define PG_F_NFLIPS_SHIFT 8 // bits 8..9: how many times GetCloseEnd called setUnmatchedSeq(ReverseComplement(..)) (0..2)
 
 struct PgChrom {
    const uint2 *planes;     // [nwords] {lo, hi} bit-planes, 32 bases per element; base i -> bit (i & 31) of element i >> 5

@@ -57,13 +57,48 @@ def clean_unique_points(ups: np.ndarray) -> np.ndarray:
     return ups[keep]
 
 
-def per_read(out: np.ndarray, runs: np.ndarray):
-    """-> list of dicts {flip, L, close_raw, close, far, flags} (same keys as oracle.refhook.parse_stream)."""
+_RC = bytes.maketrans(b"ACGTN", b"TGCAN")
+_KEEP = set(b"ACGTN")
+
+
+def set_unmatched_seq(seq: bytes) -> bytes:
+    """SPLIT_READ::setUnmatchedSeq (src/pindel.cpp:142-169): trailing non-alphanumerics are stripped."""
+    n = len(seq)
+    while n > 0 and not chr(seq[n - 1]).isalnum():
+        n -= 1
+    return seq[:n]
+
+
+def reverse_complement(seq: bytes) -> bytes:
+    """ReverseComplement (src/pindel.cpp:2037-2048, Convert2RC4N): anything but A/C/G/T/N becomes NUL."""
+    return bytes((c if c in _KEEP else 0) for c in seq[::-1]).translate(_RC)
+
+
+def final_sequence(seq: bytes, nflips: int) -> bytes:
+    """The read's UnmatchedSeq after GetCloseEnd: the host replays the flips the device reports (PG_READ_NFLIPS)."""
+    s = set_unmatched_seq(seq)
+    for _ in range(nflips):
+        s = set_unmatched_seq(reverse_complement(s))
+    return s
+
+
+def per_read(out: np.ndarray, runs: np.ndarray, seq_blob=None, seq_off=None):
+    """-> list of dicts {flip, L, close_raw, close, far, flags, nflips} (same keys as oracle.refhook.parse_stream).
+    With the input sequences given, `flip` means what it means in the oracle streams: the final UnmatchedSeq differs
+    from the input; without them it is the parity of the flips."""
     res = []
-    for o in out:
+    for i, o in enumerate(out):
         off, nc, nf = int(o["run_off"]), int(o["n_close_runs"]), int(o["n_far_runs"])
         cr = expand_runs(runs[off:off + nc])
         fa = expand_runs(runs[off + nc:off + nc + nf])
-        res.append(dict(flip=int(o["flags"]) & F_FLIPPED, L=int(o["len_after"]), close_raw=cr,
-                        close=clean_unique_points(cr), far=fa, flags=int(o["flags"])))
+        flags = int(o["flags"])
+        nflips = (flags >> 8) & 3
+        flip = flags & F_FLIPPED
+        if seq_blob is not None:
+            orig = bytes(seq_blob[int(seq_off[i]):int(seq_off[i + 1])])
+            fin = final_sequence(orig, nflips)
+            assert len(fin) == int(o["len_after"]) or (flags & F_TOOLONG), (i, len(fin), int(o["len_after"]))
+            flip = int(fin != orig)
+        res.append(dict(flip=flip, L=int(o["len_after"]), close_raw=cr, close=clean_unique_points(cr), far=fa,
+                        flags=flags, nflips=nflips))
     return res

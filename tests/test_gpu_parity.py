@@ -17,8 +17,9 @@ def ref2m():
 
 
 def run_gpu(pg, batch, **kw):
-    out, runs = pg.search(**H.batch_kwargs(batch), **kw)
-    return R.per_read(out, runs), out, runs
+    bk = H.batch_kwargs(batch)
+    out, runs = pg.search(**bk, **kw)
+    return R.per_read(out, runs, bk["seq_blob"], bk["seq_off"]), out, runs
 
 
 @pytest.mark.parametrize("L,n,seed", [(100, 20000, 11), (150, 20000, 12), (75, 10000, 13), (250, 4000, 14)])
