@@ -40,6 +40,7 @@ PG_DEV int pg_lane() { return (int)(threadIdx.x & 31); }
 PG_DEV uint32_t pg_ballot(bool p) { return __ballot_sync(0xffffffffu, p); }
 PG_DEV bool pg_any(bool p) { return __any_sync(0xffffffffu, p); }
 PG_DEV uint32_t pg_shfl(uint32_t v, int src) { return __shfl_sync(0xffffffffu, v, src); }
+PG_DEV uint32_t pg_shfl_up(uint32_t v, int d) { return __shfl_up_sync(0xffffffffu, v, d); }
 PG_DEV uint32_t pg_redux_max(uint32_t v) { return __reduce_max_sync(0xffffffffu, v); }
 PG_DEV uint32_t pg_redux_add(uint32_t v) { return __reduce_add_sync(0xffffffffu, v); }
 PG_DEV uint32_t pg_redux_or(uint32_t v) { return __reduce_or_sync(0xffffffffu, v); }
@@ -79,6 +80,7 @@ struct PgWarpSmem {
    // per-level results of the current job
    uint32_t A[TL + 1], B[TL + 1], P[TL + 1], META[TL + 1], H[TL + 1], ALIAS[TL + 1];
    uint32_t queue[PG_QCAP];
+   uint16_t seedq[PG_CHUNK_POS];     // seeds of the current chunk: offset from the tile origin | strand << 15
 };
 
 struct PgLevel {      // warp-level top-2 for level == lane
@@ -236,94 +238,132 @@ PG_DEV void pg_flush_queue(PgWarpCtx<LW, TL> &cx, const PgSearch &se, const PgCh
 }
 
 // Scan window [s, e) of one chromosome (tile by tile) and fold its seeds into cx.lvl.
+//
+// Two phases per chunk of PG_CHUNK_POS positions, so that the expensive part runs on full warps:
+//   (1) seed list: lane j owns word j of the chunk; which of its 32 positions are seeds is a pure word operation
+//       (reference base == first read character, for the far end also == its complement), so a lane finds all of
+//       its seeds without looking at the read; a warp prefix sum packs them, in position order, into ws->seedq;
+//   (2) seeds are dealt 32 at a time to the lanes: funnel-shift the 32-base stretch out of the staged tile, XOR with
+//       the read's bit-planes, pull the first TL mismatch indices out of the mask, update the lane-local top-2 keys.
 template <int LW, int TL>
 PG_DEV void pg_scan_window(PgWarpCtx<LW, TL> &cx, const PgSearch &se, int chr_id, uint32_t s, uint32_t e, uint32_t &phase)
 {
    PgWarpSmem<LW, TL> *ws = cx.ws;
    const PgChrom chrom = cx.chroms[chr_id];
-   int lane = pg_lane();
+   const int lane = pg_lane();
    if (e > chrom.len) e = chrom.len;
    if (s >= e) return;
    // first character of each strand's character set
-   uint32_t q0lo = ws->q[se.chp.arr][0][0], q0hi = ws->q[se.chp.arr][1][0];
-   uint32_t q0n = ws->q[se.chp.arr][2][0], q0x = ws->q[se.chp.arr][3][0];
+   const uint32_t q0lo = ws->q[se.chp.arr][0][0], q0hi = ws->q[se.chp.arr][1][0];
+   const uint32_t q0n = ws->q[se.chp.arr][2][0], q0x = ws->q[se.chp.arr][3][0];
    if ((q0n | q0x) & 1u) return;            // first char N (or non-ACGTN): no seeds (pindel.cpp:2281, farend_searcher.cpp:54)
-   uint32_t c0lo = (q0lo ^ se.chp.inv) & 1u, c0hi = (q0hi ^ se.chp.inv) & 1u;
+   const uint32_t c0lo = (q0lo ^ se.chp.inv) & 1u, c0hi = (q0hi ^ se.chp.inv) & 1u;
+   const uint32_t c0lom = c0lo ? ~0u : 0u, c0him = c0hi ? ~0u : 0u;
    bool read_special = false;
    {
       uint32_t sp = 0;
       if (lane < LW) sp = ws->q[se.chp.arr][2][lane] | ws->q[se.chp.arr][3][lane];
       read_special = pg_any(sp != 0);
    }
-   uint32_t valid0 = pg_valid_mask<LW, TL>(se.L, 0);
+   const uint32_t valid0 = pg_valid_mask<LW, TL>(se.L, 0) & ~1u;
+   const bool far = se.far;
+   const bool single_fwd = se.d > 0;
    for (uint32_t ts = s; ts < e; ts += PG_TILE_POS) {
-      uint32_t te = (e - ts > PG_TILE_POS) ? ts + PG_TILE_POS : e;
-      int64_t w0 = (((int64_t)(ts >> 5)) - 1) & ~(int64_t)3;
-      int64_t w1 = (int64_t)((te - 1) >> 5) + 2;          // exclusive
-      int nw = (int)(((w1 - w0) + 3) & ~(int64_t)3);
+      const uint32_t te = (e - ts > PG_TILE_POS) ? ts + PG_TILE_POS : e;
+      const int64_t w0 = (((int64_t)(ts >> 5)) - 1) & ~(int64_t)3;
+      const int64_t w1 = (int64_t)((te - 1) >> 5) + 2;          // exclusive
+      const int nw = (int)(((w1 - w0) + 3) & ~(int64_t)3);
       pg_tile_load<LW, TL>(ws, chrom, w0, nw, phase);
       // does the tile hold any reference N?
       uint32_t nacc = 0;
       for (int i = lane; i < nw; i += 32) nacc |= ws->tile_n[i];
-      bool special = read_special || pg_any(nacc != 0);
-      uint32_t origin = ts & ~31u;
+      const bool special = read_special || pg_any(nacc != 0);
+      const uint32_t origin = (uint32_t)(w0 << 5);              // absolute position of tile word 0, bit 0 (w0 >= -4)
       uint32_t ka_[TL], kb_[TL];     // lane-local top-2 keys of this tile, one pair per level
 #pragma unroll
       for (int t = 0; t < TL; t++) { ka_[t] = 0; kb_[t] = 0; }
-      for (uint32_t base = origin; base < te; base += 32) {
-         uint32_t p = base + (uint32_t)lane;
-         bool active = (p >= ts) && (p < te);
-         int wi = (int)((int64_t)(base >> 5) - w0);
-         uint2 W0 = ws->tile[wi], W1 = ws->tile[wi + 1], Wp = ws->tile[wi - 1];
-         uint32_t xlo, xhi, xn = 0, inv = se.chp.inv;
-         bool fwd = true;
-         if (se.far) {
-            uint32_t rlo = (W0.x >> lane) & 1u, rhi = (W0.y >> lane) & 1u;
-            fwd = (rlo == c0lo) && (rhi == c0hi);
-            if (!fwd) inv = ~inv;
-         } else {
-            fwd = se.d > 0;
-         }
-         if (fwd) {
-            xlo = pg_fsr(W0.x, W1.x, (uint32_t)lane);
-            xhi = pg_fsr(W0.y, W1.y, (uint32_t)lane);
-         } else {
-            xlo = pg_brev(pg_fsrc(Wp.x, W0.x, (uint32_t)lane + 1u));
-            xhi = pg_brev(pg_fsrc(Wp.y, W0.y, (uint32_t)lane + 1u));
-         }
-         uint32_t mism = (xlo ^ q0lo ^ inv) | (xhi ^ q0hi ^ inv);
-         if (special) {
-            uint32_t N0 = ws->tile_n[wi], N1 = ws->tile_n[wi + 1], Np = ws->tile_n[wi - 1];
-            xn = fwd ? pg_fsr(N0, N1, (uint32_t)lane) : pg_brev(pg_fsrc(Np, N0, (uint32_t)lane + 1u));
-            mism = (mism & ~q0n) | q0x | xn;
-         }
-         mism &= valid0;
-         bool seed = active && !(mism & 1u);
-         uint32_t m0 = mism & ~1u;
-         int cnt = pg_popc(m0);
-         // "hot" seeds are decided inside their first 32 bases: all TL tracked levels get their mismatch index from
-         // this one word (levels >= T carry values nobody reads).  Everything else is finished cooperatively.
-         bool hot = seed && cnt >= TL;
-         bool slow = seed && !hot;
-         if (hot) {
-            uint32_t idx = p - origin;
-            uint32_t mrev = pg_brev(m0);          // mismatch at read index j <-> bit 31-j: clz walks the indices upwards
-#pragma unroll
-            for (int t = 0; t < TL; t++) {
-               uint32_t D = (uint32_t)pg_clz(mrev);
-               mrev &= ~(0x80000000u >> D);
-               pg_key_update(ka_[t], kb_[t], D * (1u << PG_IDX_BITS) + idx);
+      for (uint32_t cs = ts & ~31u; cs < te; cs += PG_CHUNK_POS) {
+         // ---- (1) seed list of this chunk ----
+         uint32_t plus = 0, minus = 0;
+         {
+            uint32_t wpos = cs + 32u * (uint32_t)lane;            // first position of this lane's word
+            if (wpos < te) {
+               int wi = (int)((int64_t)(wpos >> 5) - w0);
+               uint2 W = ws->tile[wi];
+               uint32_t notn = ~ws->tile_n[wi];
+               uint32_t inr = ~0u;                                 // positions of the word inside [ts, te)
+               if (wpos < ts) inr &= ~0u << (ts - wpos);
+               if (te - wpos < 32u) inr &= (1u << (te - wpos)) - 1u;
+               uint32_t dl = W.x ^ c0lom, dh = W.y ^ c0him;       // 0 bits where the base equals read[0]
+               plus = ~(dl | dh) & notn & inr;
+               if (far) minus = (dl & dh) & notn & inr;          // both planes differ: the complement of read[0]
+               else if (!single_fwd) { minus = plus; plus = 0; } // close end growing left: every seed is a "minus" seed
             }
          }
-         uint32_t seedmask = pg_ballot(seed);
-         uint32_t slowmask = pg_ballot(slow);
-         cx.any_seed |= seedmask;
-         if (slowmask) {
-            if (slow) ws->queue[cx.qn + (uint32_t)pg_popc(slowmask & ((1u << lane) - 1u))] = p;
-            cx.qn += (uint32_t)pg_popc(slowmask);
+         uint32_t cnt = (uint32_t)(pg_popc(plus) + pg_popc(minus));
+         uint32_t incl = cnt;                                     // inclusive prefix sum over the lanes
+#pragma unroll
+         for (int d = 1; d < 32; d <<= 1) {
+            uint32_t v = pg_shfl_up(incl, d);
+            if (lane >= d) incl += v;
          }
-         bool last_iter = base + 32u >= te;
-         if (cx.qn > PG_QCAP - 32 || (last_iter && cx.qn)) pg_flush_queue<LW, TL>(cx, se, chrom, chr_id, c0lo, c0hi);
+         const uint32_t nseeds = pg_shfl(incl, 31);
+         if (nseeds == 0) continue;
+         cx.any_seed = 1;
+         {
+            uint32_t o = incl - cnt;
+            uint32_t both = plus | minus;
+            uint32_t rel = cs + 32u * (uint32_t)lane - origin;
+            while (both) {
+               uint32_t bit = (uint32_t)pg_ffs(both) - 1u;
+               both &= both - 1u;
+               ws->seedq[o++] = (uint16_t)((rel + bit) | (((minus >> bit) & 1u) << 15));
+            }
+         }
+         pg_syncwarp();
+         // ---- (2) 32 seeds per pass ----
+         for (uint32_t q0 = 0; q0 < nseeds; q0 += 32) {
+            uint32_t qi = q0 + (uint32_t)lane;
+            bool have = qi < nseeds;
+            uint32_t ent = have ? (uint32_t)ws->seedq[qi] : 0u;
+            uint32_t off = ent & 0x7fffu;
+            bool bwd = (ent >> 15) != 0;
+            uint32_t shift = off & 31u;
+            int wi = (int)(off >> 5);
+            uint32_t inv = se.chp.inv;
+            if (bwd) { wi -= 1; shift += 1u; if (far) inv = ~inv; }
+            uint2 A = ws->tile[wi], B = ws->tile[wi + 1];
+            uint32_t xlo = pg_fsrc(A.x, B.x, shift), xhi = pg_fsrc(A.y, B.y, shift);
+            if (bwd) { xlo = pg_brev(xlo); xhi = pg_brev(xhi); }
+            uint32_t mism = (xlo ^ q0lo ^ inv) | (xhi ^ q0hi ^ inv);
+            if (special) {
+               uint32_t xn = pg_fsrc(ws->tile_n[wi], ws->tile_n[wi + 1], shift);
+               if (bwd) xn = pg_brev(xn);
+               mism = (mism & ~q0n) | q0x | xn;
+            }
+            uint32_t m0 = mism & valid0;
+            // "hot" seeds are decided inside their first 32 bases: all TL tracked levels get their mismatch index
+            // from this one word (levels >= T carry values nobody reads); the rest are finished cooperatively
+            bool hot = have && pg_popc(m0) >= TL;
+            bool slow = have && !hot;
+            if (hot) {
+               uint32_t mrev = pg_brev(m0);          // mismatch at read index j <-> bit 31-j: clz walks the indices upwards
+#pragma unroll
+               for (int t = 0; t < TL; t++) {
+                  uint32_t D = (uint32_t)pg_clz(mrev);
+                  mrev &= ~(0x80000000u >> D);
+                  pg_key_update(ka_[t], kb_[t], D * (1u << PG_IDX_BITS) + off);
+               }
+            }
+            uint32_t slowmask = pg_ballot(slow);
+            if (slowmask) {
+               if (slow) ws->queue[cx.qn + (uint32_t)pg_popc(slowmask & ((1u << lane) - 1u))] = origin + off;
+               cx.qn += (uint32_t)pg_popc(slowmask);
+            }
+            bool last_pass = q0 + 32u >= nseeds;
+            if (cx.qn > PG_QCAP - 32 || (last_pass && cx.qn)) pg_flush_queue<LW, TL>(cx, se, chrom, chr_id, c0lo, c0hi);
+         }
+         pg_syncwarp();
       }
       // fold the tile's lane-local top-2 into the warp-level state of lane t
 #pragma unroll
@@ -332,12 +372,12 @@ PG_DEV void pg_scan_window(PgWarpCtx<LW, TL> &cx, const PgSearch &se, int chr_id
          uint32_t mine = (ka_[t] == ka) ? kb_[t] : ka_[t];
          uint32_t kb = pg_redux_max(mine);
          if (lane == t && ka != 0) {
-            uint32_t pos = origin + (ka & PG_IDX_MASK);
+            uint32_t off = ka & PG_IDX_MASK;
+            uint32_t pos = origin + off;
             uint32_t minus = 0;
-            if (se.far) {
-               int wi = (int)((int64_t)(pos >> 5) - w0);
-               uint2 wv = ws->tile[wi];
-               uint32_t rlo = (wv.x >> (pos & 31)) & 1u, rhi = (wv.y >> (pos & 31)) & 1u;
+            if (far) {
+               uint2 wv = ws->tile[off >> 5];
+               uint32_t rlo = (wv.x >> (off & 31)) & 1u, rhi = (wv.y >> (off & 31)) & 1u;
                minus = (rlo != c0lo || rhi != c0hi) ? 1u : 0u;
             }
             pg_level_merge(cx.lvl, ka >> PG_IDX_BITS, pos, ((uint32_t)chr_id << 1) | minus);
@@ -394,7 +434,11 @@ PG_DEV PgResult pg_walk_emit(PgWarpCtx<LW, TL> &cx, const PgSearch &se, PgRun *d
    // open run carried across rounds (uniform)
    uint32_t run_len0 = 0, run_cnt = 0, run_m = 0;
    int prev_valid = 0; uint32_t prev_m = 0;
-   for (int r0 = se.bp_start; r0 <= L - 1 && !dead; r0 += 32) {
+   // no length beyond the longest-lived candidate of levels <= MAX can pass the in-range test (m would be MAX+1 > g[len])
+   int len_hi = 0;
+   for (int t = 0; t <= MAX; t++) len_hi = ((int)ws->A[t] > len_hi) ? (int)ws->A[t] : len_hi;
+   if (len_hi > L - 1) len_hi = L - 1;
+   for (int r0 = se.bp_start; r0 <= len_hi && !dead; r0 += 32) {
       int len = r0 + lane;
       bool inrange = len <= L - 1;
       int m = 0;
@@ -610,6 +654,8 @@ PG_DEV void pg_process_read(PgWarpCtx<LW, TL> &cx, const PgBatch &bt, int ri, Pg
    unsigned long long window_bases = 0;   // reference positions scanned for this read (bench statistics)
    int k = 1;                  // SearchFarEnd: rangeIndex 1..MaxRangeIndex+1
    uint32_t span = 64;         // START_SEARCH_SPAN
+   bool have_prev_window = false;
+   uint32_t prev_ws = 0, prev_we = 0;
    if (bt.mode & 1) {
       st = ST_CLOSE;
    } else if ((bt.mode & 2) && bt.close_info) {
@@ -622,11 +668,14 @@ PG_DEV void pg_process_read(PgWarpCtx<LW, TL> &cx, const PgBatch &bt, int ri, Pg
       // ---- describe the search ----
       PgSearch se;
       se.L = L; se.MAX = prm->g[L]; se.T = se.MAX + prm->add_mm + 1;
-      PgRegion one;
-      const PgRegion *regs = &one;
+      PgRegion two[2];
+      PgRegion &one = two[0];
+      const PgRegion *regs = two;
       int nreg = 1;
       PgRun *dst = farNew;
       bool skip = false;
+      bool keep_state = false;     // far windows are nested: window k only scans the two rings around window k-1
+      unsigned long long alg_bases = 0;
       if (st == ST_CLOSE) {
          // GetCloseEndInner, pindel.cpp:2250-2396
          se.far = false; se.bp_start = prm->min_close; dst = closeBuf;
@@ -653,13 +702,23 @@ PG_DEV void pg_process_read(PgWarpCtx<LW, TL> &cx, const PgBatch &bt, int ri, Pg
          if (st == ST_FAR_CLUSTER) { regs = cluster; nreg = n_regions; }
          else {
             uint32_t center = cres.last_abs_loc, size = cx.chroms[chr_id].len;
-            one.chr = chr_id;
-            one.start = (center > span + PG_SPACER) ? center - span : PG_SPACER;               // pindel.cpp:1033-1042
-            one.end = (center + span + PG_SPACER < size) ? center + span : size - PG_SPACER;
+            uint32_t wsx = (center > span + PG_SPACER) ? center - span : PG_SPACER;            // pindel.cpp:1033-1042
+            uint32_t wex = (center + span + PG_SPACER < size) ? center + span : size - PG_SPACER;
+            alg_bases = wex > wsx ? (unsigned long long)(wex - wsx) : 0ull;
+            one.chr = chr_id; one.start = wsx; one.end = wex;
+            if (have_prev_window && !skip && wsx <= prev_ws && wex >= prev_we && prev_we >= prev_ws) {
+               // the reference searches the whole window again (pindel.cpp:1027-1029); the top-2 state of window k-1
+               // is still exact for its positions, so only [wsx, prev_ws) and [prev_we, wex) are new
+               keep_state = true;
+               two[0].chr = chr_id; two[0].start = wsx; two[0].end = prev_ws;
+               two[1].chr = chr_id; two[1].start = prev_we; two[1].end = wex;
+               nreg = 2;
+            }
+            have_prev_window = !skip; prev_ws = wsx; prev_we = wex;
          }
       }
       // ---- run it ----
-      pg_search_begin<LW, TL>(cx);
+      if (!keep_state) pg_search_begin<LW, TL>(cx);
       if (!skip) {
          for (int r = 0; r < nreg; r++) {
             PgRegion rg = regs[r];
@@ -673,9 +732,10 @@ PG_DEV void pg_process_read(PgWarpCtx<LW, TL> &cx, const PgBatch &bt, int ri, Pg
             }
             if (e > s) {
                pg_scan_window<LW, TL>(cx, se, rg.chr, s, e, phase);
-               window_bases += (unsigned long long)(e - s);
+               if (st != ST_FAR_WINDOW) window_bases += (unsigned long long)(e - s);
             }
          }
+         window_bases += alg_bases;      // far windows are accounted at the size the reference scans, rings or not
       }
       PgResult res = pg_walk_emit<LW, TL>(cx, se, dst, cap);
       // ---- decide what comes next ----

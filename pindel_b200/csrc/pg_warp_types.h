@@ -14,6 +14,7 @@ struct uint2 { uint32_t x, y; };
 #define PG_PADW 64          // guard words on both sides of every packed chromosome
 #define PG_TILE_POS 2048    // reference positions per shared-memory tile
 #define PG_TILE_WORDS 76    // 64 + 1 before + 1 after + alignment slack (multiple of 4)
+#define PG_CHUNK_POS 1024   // positions per seed-list chunk (one 32-base word per lane)
 #define PG_QCAP 64          // deferred ("slow") seed queue per warp
 #define PG_IDX_BITS 20
 #define PG_IDX_MASK 0xFFFFFu

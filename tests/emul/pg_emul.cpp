@@ -16,7 +16,7 @@
 #define PG_DEV static inline
 struct uint2 { uint32_t x, y; };
 
-enum { OP_NONE, OP_BALLOT, OP_ANY, OP_SHFL, OP_MAX, OP_ADD, OP_OR, OP_SYNC };
+enum { OP_NONE, OP_BALLOT, OP_ANY, OP_SHFL, OP_SHFL_UP, OP_MAX, OP_ADD, OP_OR, OP_SYNC };
 struct Emu {
    ucontext_t sched;
    ucontext_t lane_ctx[32];
@@ -76,6 +76,7 @@ static void emu_run_warp(void (*body)(void *), void *arg)
       case OP_BALLOT: for (int i = 0; i < 32; i++) if (emu.in[i]) r |= 1u << i; for (int i = 0; i < 32; i++) emu.out[i] = r; break;
       case OP_ANY: for (int i = 0; i < 32; i++) if (emu.in[i]) r = 1; for (int i = 0; i < 32; i++) emu.out[i] = r; break;
       case OP_SHFL: for (int i = 0; i < 32; i++) emu.out[i] = emu.in[emu.aux[i] & 31]; break;
+      case OP_SHFL_UP: for (int i = 0; i < 32; i++) emu.out[i] = (i - emu.aux[i] >= 0) ? emu.in[i - emu.aux[i]] : emu.in[i]; break;
       case OP_MAX: for (int i = 0; i < 32; i++) if (emu.in[i] > r) r = emu.in[i]; for (int i = 0; i < 32; i++) emu.out[i] = r; break;
       case OP_ADD: for (int i = 0; i < 32; i++) r += emu.in[i]; for (int i = 0; i < 32; i++) emu.out[i] = r; break;
       case OP_OR: for (int i = 0; i < 32; i++) r |= emu.in[i]; for (int i = 0; i < 32; i++) emu.out[i] = r; break;
@@ -90,6 +91,7 @@ PG_DEV int pg_lane() { return E->cur; }
 PG_DEV uint32_t pg_ballot(bool p) { return emu_collective(OP_BALLOT, p ? 1u : 0u, 0); }
 PG_DEV bool pg_any(bool p) { return emu_collective(OP_ANY, p ? 1u : 0u, 0) != 0; }
 PG_DEV uint32_t pg_shfl(uint32_t v, int src) { return emu_collective(OP_SHFL, v, src); }
+PG_DEV uint32_t pg_shfl_up(uint32_t v, int d) { return emu_collective(OP_SHFL_UP, v, d); }
 PG_DEV uint32_t pg_redux_max(uint32_t v) { return emu_collective(OP_MAX, v, 0); }
 PG_DEV uint32_t pg_redux_add(uint32_t v) { return emu_collective(OP_ADD, v, 0); }
 PG_DEV uint32_t pg_redux_or(uint32_t v) { return emu_collective(OP_OR, v, 0); }

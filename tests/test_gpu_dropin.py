@@ -1,0 +1,36 @@
+"""Drop-in check at the file level: the UNMODIFIED reference host program (command line, Pindel-text input, window loop,
+SV drivers, reporter) with its two search seam functions served by libpindel_pg.so (oracle/ref_gpu_bridge.cpp, bound by
+the dynamic linker -- no reference source is patched) must write byte-identical _D/_SI/_INV/_TD (and _LI/_BP/
+_CloseEndMapped) files to the ones the pure reference binary wrote for the same inputs (tests/golden/colo_slice.*).
+Needs oracle/_ref/pindel_gpu_demo, which is built in the container where /root/reference exists and travels to the
+GPU box with the snapshot."""
+import gzip
+import os
+import subprocess
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+DEMO = os.path.join(ROOT, "oracle", "_ref", "pindel_gpu_demo")
+GOLD = os.path.join(ROOT, "tests", "golden")
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.skipif(not os.path.exists(DEMO), reason="oracle/_ref/pindel_gpu_demo not built (needs /root/reference at build time)")
+def test_reference_host_with_gpu_search_writes_identical_files(tmp_path):
+    fa = tmp_path / "colo_slice.fa"
+    fa.write_bytes(gzip.open(os.path.join(GOLD, "colo_slice.fa.gz")).read())
+    (tmp_path / "colo_slice.fa.fai").write_text("20s\t500000\t5\t60\t61\n")
+    rd = tmp_path / "reads.txt"
+    rd.write_bytes(gzip.open(os.path.join(GOLD, "colo_slice_reads.txt.gz")).read())
+    # the freshly built product library, not a stale copy next to the demo
+    env = dict(os.environ, LD_LIBRARY_PATH=os.path.join(ROOT, "pindel_b200") + ":" + os.environ.get("LD_LIBRARY_PATH", ""))
+    p = subprocess.run([DEMO, "-f", str(fa), "-p", str(rd), "-o", str(tmp_path / "colo_slice.out"), "-k", "-s", "-l", "-T", "1"],
+                       capture_output=True, text=True, timeout=1200, env=env)
+    assert p.returncode == 0, p.stdout[-2000:] + p.stderr[-2000:]
+    assert "served by libpindel_pg" in p.stderr and " 0 GetCloseEnd calls" not in p.stderr
+    for suf in ("D", "SI", "INV", "TD", "LI", "BP", "CloseEndMapped"):
+        got = (tmp_path / ("colo_slice.out_" + suf)).read_bytes()
+        exp = gzip.open(os.path.join(GOLD, "colo_slice.out_%s.gz" % suf)).read()
+        assert got == exp, "_%s differs from the reference's file (%d vs %d bytes)" % (suf, len(got), len(exp))
