@@ -333,7 +333,7 @@ def main():
     achieved = alg_bytes / (ms_step / 1e3) / 1e9
     traffic = committed_traffic()
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": (traffic or {}).get("dram_bytes_per_launch"),
+                "traffic": (traffic["dram_bytes_per_read"] * n) if traffic and "dram_bytes_per_read" in traffic else None,
                 "peak_source": peak_src, "algorithmic_bytes_per_launch": int(alg_bytes),
                 "bytes_per_read": alg_bytes / n, "window_bases_per_read": window_bases / n, "unique_points_per_read": n_ups / n,
                 "note": "launch duration = CUDA-event time of the timed region / steps (includes the NCCL gather when gpus > 1); "

@@ -35,7 +35,7 @@
 
 #ifndef PG_EMULATE
 #define PG_DEV __device__ __forceinline__
-#define PG_DEVNI __device__ __noinline__
+#define PG_COLD __device__ __noinline__   // rarely executed helpers: one out-of-line copy keeps the kernel's code small
 PG_DEV int pg_lane() { return (int)(threadIdx.x & 31); }
 PG_DEV uint32_t pg_ballot(bool p) { return __ballot_sync(0xffffffffu, p); }
 PG_DEV bool pg_any(bool p) { return __any_sync(0xffffffffu, p); }
@@ -151,9 +151,12 @@ PG_DEV void pg_seed_stretch(const PgChrom &chrom, uint32_t pos, int d, int c, ui
 // Cooperative: lanes c < nchunks compute the full-length masks of one seed into ws->mw (N-rule) or
 // ws->M[slot]/ws->S[slot]; returns the total N-rule mismatch count when want_slot >= 0.
 template <int LW, int TL>
-PG_DEV uint32_t pg_full_masks(PgWarpSmem<LW, TL> *ws, const PgChrom &chrom, PgChars ch, uint32_t pos, int d, int L,
-                              int slot)
+PG_COLD uint32_t pg_full_masks(PgWarpSmem<LW, TL> *ws, const PgChrom *chrom_p, int ch_arr, uint32_t ch_inv, uint32_t pos, int d,
+                               int L, int slot)
 {
+   const PgChrom chrom = *chrom_p;
+   PgChars ch;
+   ch.arr = ch_arr; ch.inv = ch_inv;
    int lane = pg_lane();
    int nch = (L + 31) >> 5;
    uint32_t M = 0, S = 0;
@@ -195,7 +198,7 @@ template <int LW, int TL>
 PG_DEV void pg_tile_load(PgWarpSmem<LW, TL> *ws, const PgChrom &c, int64_t w0, int nw, uint32_t &phase);
 
 template <int LW, int TL>
-PG_DEV void pg_flush_queue(PgWarpCtx<LW, TL> &cx, const PgSearch &se, const PgChrom &chrom, int chr_id, uint32_t c0lo, uint32_t c0hi)
+PG_DEV void pg_flush_queue(PgWarpCtx<LW, TL> &cx, const PgSearch &se, const PgChrom *chrom_p, int chr_id, uint32_t c0lo, uint32_t c0hi)
 {
    PgWarpSmem<LW, TL> *ws = cx.ws;
    int lane = pg_lane();
@@ -207,23 +210,25 @@ PG_DEV void pg_flush_queue(PgWarpCtx<LW, TL> &cx, const PgSearch &se, const PgCh
       uint32_t minus = 0;
       if (se.far) {
          // plus seed iff ref[pos] == read[0] (farend_searcher.cpp:76), else it was queued as a minus seed
-         uint2 wv = pg_ldg64(chrom.planes + (pos >> 5));
+         uint2 wv = pg_ldg64(chrom_p->planes + (pos >> 5));
          uint32_t rlo = (wv.x >> (pos & 31)) & 1u, rhi = (wv.y >> (pos & 31)) & 1u;
          minus = (rlo != c0lo || rhi != c0hi) ? 1u : 0u;
          d = minus ? -1 : 1;
          ch.inv = minus ? ~se.chp.inv : se.chp.inv;
       }
-      pg_full_masks<LW, TL>(ws, chrom, ch, pos, d, se.L, -1);
+      pg_full_masks<LW, TL>(ws, chrom_p, ch.arr, ch.inv, pos, d, se.L, -1);
       if (lane < se.T) {
          // D_lane = read index of the (lane+1)-th mismatch at index >= 1, or L
          int rank = lane;
          uint32_t D = (uint32_t)se.L;
          int nch = (se.L + 31) >> 5;
+#pragma unroll 1
          for (int c = 0; c < nch; c++) {
             uint32_t w = ws->mw[c];
             if (c == 0) w &= ~1u;
             int pc = pg_popc(w);
             if (rank < pc) {
+#pragma unroll 1
                for (int k = 0; k < rank; k++) w &= w - 1;
                D = (uint32_t)(32 * c + pg_ffs(w) - 1);
                break;
@@ -276,6 +281,7 @@ PG_DEV void pg_scan_window(PgWarpCtx<LW, TL> &cx, const PgSearch &se, int chr_id
       pg_tile_load<LW, TL>(ws, chrom, w0, nw, phase);
       // does the tile hold any reference N?
       uint32_t nacc = 0;
+#pragma unroll 1
       for (int i = lane; i < nw; i += 32) nacc |= ws->tile_n[i];
       const bool special = read_special || pg_any(nacc != 0);
       const uint32_t origin = (uint32_t)(w0 << 5);              // absolute position of tile word 0, bit 0 (w0 >= -4)
@@ -361,28 +367,30 @@ PG_DEV void pg_scan_window(PgWarpCtx<LW, TL> &cx, const PgSearch &se, int chr_id
                cx.qn += (uint32_t)pg_popc(slowmask);
             }
             bool last_pass = q0 + 32u >= nseeds;
-            if (cx.qn > PG_QCAP - 32 || (last_pass && cx.qn)) pg_flush_queue<LW, TL>(cx, se, chrom, chr_id, c0lo, c0hi);
+            if (cx.qn > PG_QCAP - 32 || (last_pass && cx.qn)) pg_flush_queue<LW, TL>(cx, se, cx.chroms + chr_id, chr_id, c0lo, c0hi);
          }
          pg_syncwarp();
       }
-      // fold the tile's lane-local top-2 into the warp-level state of lane t
+      // fold the tile's lane-local top-2 into the warp-level state of lane t (two redux.max per level; the merge
+      // itself is written once, outside the unrolled loop, to keep the code small)
+      uint32_t my_ka = 0, my_kb = 0;
 #pragma unroll
       for (int t = 0; t < TL; t++) {
          uint32_t ka = pg_redux_max(ka_[t]);
          uint32_t mine = (ka_[t] == ka) ? kb_[t] : ka_[t];
          uint32_t kb = pg_redux_max(mine);
-         if (lane == t && ka != 0) {
-            uint32_t off = ka & PG_IDX_MASK;
-            uint32_t pos = origin + off;
-            uint32_t minus = 0;
-            if (far) {
-               uint2 wv = ws->tile[off >> 5];
-               uint32_t rlo = (wv.x >> (off & 31)) & 1u, rhi = (wv.y >> (off & 31)) & 1u;
-               minus = (rlo != c0lo || rhi != c0hi) ? 1u : 0u;
-            }
-            pg_level_merge(cx.lvl, ka >> PG_IDX_BITS, pos, ((uint32_t)chr_id << 1) | minus);
-            if (kb != 0) pg_level_merge(cx.lvl, kb >> PG_IDX_BITS, 0xffffffffu, 0);
+         if (lane == t) { my_ka = ka; my_kb = kb; }
+      }
+      if (my_ka != 0) {
+         uint32_t off = my_ka & PG_IDX_MASK;
+         uint32_t minus = 0;
+         if (far) {
+            uint2 wv = ws->tile[off >> 5];
+            uint32_t rlo = (wv.x >> (off & 31)) & 1u, rhi = (wv.y >> (off & 31)) & 1u;
+            minus = (rlo != c0lo || rhi != c0hi) ? 1u : 0u;
          }
+         pg_level_merge(cx.lvl, my_ka >> PG_IDX_BITS, origin + off, ((uint32_t)chr_id << 1) | minus);
+         if (my_kb != 0) pg_level_merge(cx.lvl, my_kb >> PG_IDX_BITS, 0xffffffffu, 0);
       }
       pg_syncwarp();
    }
@@ -413,6 +421,7 @@ PG_DEV PgResult pg_walk_emit(PgWarpCtx<LW, TL> &cx, const PgSearch &se, PgRun *d
    }
    pg_syncwarp();
    // full-length masks of the seeds that can own a UniquePoint (one per level <= MAX)
+#pragma unroll 1
    for (int t = 0; t <= se.MAX; t++) {
       uint32_t At = ws->A[t];
       bool need = At >= (uint32_t)(se.bp_start + t);
@@ -424,7 +433,7 @@ PG_DEV PgResult pg_walk_emit(PgWarpCtx<LW, TL> &cx, const PgSearch &se, PgRun *d
       int d = se.far ? ((meta & 1u) ? -1 : 1) : se.d;
       PgChars ch = se.chp;
       if (se.far && (meta & 1u)) ch.inv = ~ch.inv;
-      uint32_t h = pg_full_masks<LW, TL>(ws, cx.chroms[meta >> 1], ch, ws->P[t], d, se.L, t);
+      uint32_t h = pg_full_masks<LW, TL>(ws, cx.chroms + (meta >> 1), ch.arr, ch.inv, ws->P[t], d, se.L, t);
       if (lane == 0) { ws->ALIAS[t] = (uint32_t)t; ws->H[t] = h; }
       pg_syncwarp();
    }
@@ -436,12 +445,14 @@ PG_DEV PgResult pg_walk_emit(PgWarpCtx<LW, TL> &cx, const PgSearch &se, PgRun *d
    int prev_valid = 0; uint32_t prev_m = 0;
    // no length beyond the longest-lived candidate of levels <= MAX can pass the in-range test (m would be MAX+1 > g[len])
    int len_hi = 0;
+#pragma unroll 1
    for (int t = 0; t <= MAX; t++) len_hi = ((int)ws->A[t] > len_hi) ? (int)ws->A[t] : len_hi;
    if (len_hi > L - 1) len_hi = L - 1;
    for (int r0 = se.bp_start; r0 <= len_hi && !dead; r0 += 32) {
       int len = r0 + lane;
       bool inrange = len <= L - 1;
       int m = 0;
+#pragma unroll 1
       for (int t = 0; t <= MAX; t++) m += (ws->A[t] < (uint32_t)len) ? 1 : 0;
       bool abort_here = inrange && ((uint32_t)m > (uint32_t)prm->g[len]);       // searcher.cpp:167-169, pindel.cpp:2836-2838
       uint32_t abmask = pg_ballot(abort_here);
@@ -459,6 +470,7 @@ PG_DEV PgResult pg_walk_emit(PgWarpCtx<LW, TL> &cx, const PgSearch &se, PgRun *d
          int d = se.far ? ((meta & 1u) ? -1 : 1) : se.d;
          int slot = (int)ws->ALIAS[m];
          bool ok = (d > 0) ? (len > MP) : (len >= MP);                           // searcher.cpp:346 / :360 substr clipping
+#pragma unroll 1
          for (int j = 0; ok && j < MP; j++) {
             int bit = len - MP + j;
             ok = !((ws->S[slot][bit >> 5] >> (bit & 31)) & 1u);
@@ -540,7 +552,7 @@ PG_DEV void pg_search_begin(PgWarpCtx<LW, TL> &cx)
 
 // Pack the read (ASCII) into bit-planes; returns the stripped length (setUnmatchedSeq, pindel.cpp:142-169).
 template <int LW, int TL>
-PG_DEV int pg_pack_read(PgWarpSmem<LW, TL> *ws, const uint8_t *seq, int len)
+PG_COLD int pg_pack_read(PgWarpSmem<LW, TL> *ws, const uint8_t *seq, int len)
 {
    int lane = pg_lane();
    // strip trailing non-alphanumerics
@@ -572,7 +584,7 @@ PG_DEV int pg_pack_read(PgWarpSmem<LW, TL> *ws, const uint8_t *seq, int len)
 // setUnmatchedSeq(ReverseComplement(seq)) (pindel.cpp:2545): materialise RC(read) as the new forward read.
 // Leading non-ACGTN characters become trailing NULs after the flip and are stripped; returns the new length.
 template <int LW, int TL>
-PG_DEV int pg_flip_read(PgWarpSmem<LW, TL> *ws, int L)
+PG_COLD int pg_flip_read(PgWarpSmem<LW, TL> *ws, int L)
 {
    int lane = pg_lane();
    // k = number of leading 'other' characters of the current read

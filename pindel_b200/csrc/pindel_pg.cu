@@ -75,7 +75,11 @@ __global__ void __launch_bounds__(PG_BLOCK_THREADS, (TL <= 8) ? PG_MINB : 1) pg_
       for (int i = threadIdx.x; i < (int)(sizeof(PgParams) / 4); i += blockDim.x) dst[i] = src[i];
    }
    const int warp = threadIdx.x >> 5;
-   PgWarpSmem<LW, TL> *ws = reinterpret_cast<PgWarpSmem<LW, TL> *>(pg_dyn_smem) + warp;
+   // the byte offset of this warp's slice is made opaque so that it lives in one register instead of being
+   // re-derived from %tid at every use (the compiler otherwise rematerialises it all over the hot loop)
+   uint32_t ws_off = (uint32_t)warp * (uint32_t)sizeof(PgWarpSmem<LW, TL>);
+   asm volatile("" : "+r"(ws_off));
+   PgWarpSmem<LW, TL> *ws = reinterpret_cast<PgWarpSmem<LW, TL> *>(pg_dyn_smem + ws_off);
    if (pg_lane() == 0) {
       asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(pg_smem_addr(&ws->mbar)) : "memory");
       asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
