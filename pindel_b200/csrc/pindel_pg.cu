@@ -27,7 +27,7 @@ static_assert(PG_READ_FLIPPED == PG_F_FLIPPED && PG_READ_UNSUPPORTED == PG_F_TOO
 
 #define PG_BLOCK_THREADS 256
 #ifndef PG_MINB
-#define PG_MINB 3          // resident CTAs per SM the register allocator is asked to make room for (TL <= 8 variants)
+#define PG_MINB 4          // resident CTAs per SM the register allocator is asked to make room for (TL <= 8 variants)
 #endif
 #define PG_WARPS_PER_BLOCK (PG_BLOCK_THREADS / 32)
 
