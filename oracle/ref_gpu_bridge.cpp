@@ -12,12 +12,16 @@
  * dynamic linker binds every call the reference makes to these two names (reader.cpp:254,304, read_buffer.cpp:47,
  * pindel.cpp:1888) to the definitions below.  No reference source is patched or copied.
  *
- * GetCloseEnd is called once per read from inside the reference's own loops, so this shim issues one-read batches
- * (slow, but it keeps the caller untouched); SearchFarEnds is a true batch call.  A maintainer would batch the
- * close-end loop as INTEGRATION.md shows.
+ * GetCloseEnd is called once per read from inside the reference's own text-input loop (reader.cpp:248-256,300-306), so
+ * for Pindel-text input this shim issues one-read batches (slow, but the caller stays untouched).  For BAM input the
+ * reference funnels reads through ReadBuffer::flush (read_buffer.cpp:36-101), a public member function, so the bridge
+ * supplies that too -- as the batched binding INTEGRATION.md describes: one pg_close_end call per flush of up to
+ * 50 000 reads.  SearchFarEnds is a true batch call in both modes.
  */
 #include "pindel.h"
 #include "bddata.h"
+#include "read_buffer.h"
+#include "reader.h"
 #include "logstream.h"
 #include "user_defined_settings.h"
 
@@ -115,6 +119,72 @@ void GetCloseEnd(const std::string &CurrentChrSeq, SPLIT_READ &read)
    read.UP_Close.clear();
    appendRuns(read.UP_Close, &runs[out.run_off], out.n_close_runs);
    if (!read.UP_Close.empty()) read.Used = false;                  /* src/pindel.cpp:2294, :2321 */
+}
+
+/* ReadBuffer::flush, batched (replaces read_buffer.cpp:36-101 by symbol; same observable behaviour: reads with a close
+ * end are post-processed by updateReadAfterCloseEndMapping and appended to m_filteredReads in buffer order -- the
+ * order the reference produces with one thread). */
+void ReadBuffer::flush()
+{
+   {
+      std::lock_guard<std::mutex> lock(g_mutex);
+      ensureContext();
+      const int n = m_currentsize;
+      std::string blob;
+      std::vector<uint32_t> off(n + 1, 0), pos(n);
+      std::vector<char> md(n);
+      std::vector<int16_t> isz(n);
+      std::vector<int32_t> chr(n);
+      std::vector<int> idx;                  /* reads that take part (MapperSplit == false) */
+      for (int i = 0; i < n; i++) {
+         if (m_rawreads[i].MapperSplit) continue;
+         const SPLIT_READ &r = m_rawreads[i];
+         int k = (int)idx.size();
+         blob += r.getUnmatchedSeq();
+         off[k + 1] = (uint32_t)blob.size();
+         md[k] = r.MatchedD; pos[k] = r.MatchedRelPos; isz[k] = r.InsertSize; chr[k] = g_genome.getChrID(r.FragName);
+         if (r.InsertSize > g_maxInsertSize) g_maxInsertSize = r.InsertSize;
+         idx.push_back(i);
+      }
+      const int m = (int)idx.size();
+      if (m > 0) {
+         pg_reads in;
+         memset(&in, 0, sizeof(in));
+         in.n = m; in.seq_blob = blob.c_str(); in.seq_off = &off[0]; in.matched_d = &md[0]; in.matched_rel_pos = &pos[0];
+         in.insert_size = &isz[0]; in.chr_id = &chr[0];
+         std::vector<pg_read_out> out(m);
+         std::vector<pg_run> runs((size_t)m * 16 + 1024);
+         pg_results res;
+         res.out = &out[0]; res.runs = &runs[0]; res.runs_cap = (uint32_t)runs.size(); res.n_runs = 0;
+         int rc = pg_close_end(g_ctx, &in, &res);
+         if (rc == PG_ERR_RUNS_CAP) {
+            runs.resize(res.n_runs);
+            res.runs = &runs[0]; res.runs_cap = (uint32_t)runs.size();
+            rc = pg_download(g_ctx, &res);
+         }
+         if (rc != PG_OK) die("pg_close_end (ReadBuffer::flush)");
+         for (int k = 0; k < m; k++) {
+            SPLIT_READ &read = m_rawreads[idx[k]];
+            if (out[k].flags & PG_READ_UNSUPPORTED) die("read not supported by the library");
+            for (unsigned f = 0; f < PG_READ_NFLIPS(out[k].flags); f++)
+               read.setUnmatchedSeq(ReverseComplement(read.getUnmatchedSeq()));
+            read.UP_Close.clear();
+            appendRuns(read.UP_Close, &runs[out[k].run_off], out[k].n_close_runs);
+            if (!read.UP_Close.empty()) read.Used = false;
+         }
+         g_close_calls += (unsigned long)m;
+      }
+   }
+   for (int i = 0; i < m_currentsize; i++) {
+      if (m_rawreads[i].hasCloseEnd()) {
+         updateReadAfterCloseEndMapping(m_rawreads[i]);
+         m_rawreads[i].SampleName2Number.insert(std::pair<std::string, unsigned>(m_rawreads[i].Tag, 1));
+         m_filteredReads.push_back(m_rawreads[i]);
+      }
+   }
+   m_rawreads.clear();
+   m_currentsize = 0;
+   std::cout << "The number of one end mapped read: " << m_filteredReads.size() << std::endl;
 }
 
 void SearchFarEnds(const std::string &chromosomeSeq, std::vector<SPLIT_READ> &reads, const Chromosome &currentChromosome)

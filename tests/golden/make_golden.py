@@ -9,6 +9,8 @@ What it writes (all small; the inputs are either regenerable from a seed or stor
                         the untouched GetCloseEnd / CleanUniquePoints / SearchFarEnds) on seeded synthetic batches
   edge_cases.npz        hand-made reads (N / IUPAC / lower case / trailing junk / short / near chromosome ends) + the
                         reference's answers
+  sim_prefix.*          a prefix of test/SmallTest/sim1chrVs2.bam (re-blocked as BGZF) + its reference: the BAM-input
+                        scenario, with the _D/_SI/_INV/_TD/... files written by the reference binary
   colo_slice.*          a 500 kbp slice of test/SmallTest/hs_ref_chr20.fa (with the start of the centromere N run)
                         and the reads of test/SmallTest/COLO-829_20-p_ok-1.txt anchored in it: inputs, the reference's
                         per-read streams, and the _D/_SI/_INV/_TD files written by the reference binary
@@ -169,13 +171,79 @@ def worker_colo():
     print("colo_slice: %d reads" % len(seqs))
 
 
+def bgzf_write(path, payload: bytes):
+    """Valid BGZF: gzip members of <= 65280 input bytes with the BC extra field, then the empty EOF block."""
+    import struct
+    import zlib
+    with open(path, "wb") as f:
+        def block(chunk):
+            co = zlib.compressobj(9, zlib.DEFLATED, -15)
+            comp = co.compress(chunk) + co.flush()
+            bsize = 12 + 6 + len(comp) + 8
+            f.write(struct.pack("<BBBBIBBHBBHH", 31, 139, 8, 4, 0, 0, 255, 6, 66, 67, 2, bsize - 1))
+            f.write(comp)
+            f.write(struct.pack("<II", zlib.crc32(chunk) & 0xFFFFFFFF, len(chunk)))
+        for k in range(0, len(payload), 65280):
+            block(payload[k:k + 65280])
+        block(b"")
+
+
+BAM_CUT = (100_000, 135_000)   # keep the alignments that start in this range (inversion + tandem duplication + RP clusters)
+
+
+def worker_bam():
+    """BAM-input scenario (devtools/run_regressiontests.sh:7) on a prefix of test/SmallTest/sim1chrVs2.bam: exercises
+    the reference's BAM reader (through oracle/shim/minihts.cpp), ReadBuffer::flush, discordant-pair discovery and the
+    BreakDancer-like clusters that feed multi-region far-end searches."""
+    import struct
+    src = "/root/reference/test/SmallTest/"
+    raw = gzip.open(src + "sim1chrVs2.bam").read()
+    assert raw[:4] == b"BAM\1"
+    p = 4
+    l_text = struct.unpack_from("<i", raw, p)[0]; p += 4 + l_text
+    n_ref = struct.unpack_from("<i", raw, p)[0]; p += 4
+    for _ in range(n_ref):
+        l = struct.unpack_from("<i", raw, p)[0]; p += 4 + l + 4
+    out = bytearray(raw[:p])
+    kept = 0
+    while p + 4 <= len(raw):
+        bs = struct.unpack_from("<i", raw, p)[0]
+        pos = struct.unpack_from("<i", raw, p + 8)[0]
+        if BAM_CUT[0] <= pos < BAM_CUT[1]:
+            out += raw[p:p + 4 + bs]; kept += 1
+        p += 4 + bs
+    bgzf_write(os.path.join(HERE, "sim_prefix.bam"), bytes(out))
+    fa = open(src + "sim1chrVs2.fa", "rb").read()
+    with gzip.open(os.path.join(HERE, "sim_prefix.fa.gz"), "wb", compresslevel=9) as g:
+        g.write(fa)
+    fai = open(src + "sim1chrVs2.fa.fai").read()
+    open(os.path.join(HERE, "sim_prefix.fa.fai"), "w").write(fai)
+    tmp = tempfile.mkdtemp()
+    open(os.path.join(tmp, "sim_prefix.fa"), "wb").write(fa)
+    open(os.path.join(tmp, "sim_prefix.fa.fai"), "w").write(fai)
+    import shutil
+    shutil.copy(os.path.join(HERE, "sim_prefix.bam"), os.path.join(tmp, "sim_prefix.bam"))
+    # the reference insists on an index file next to the BAM (src/pindel.cpp:690-697); the test reader ignores its content
+    open(os.path.join(tmp, "sim_prefix.bam.bai"), "wb").write(b"BAI\x01\x00\x00\x00\x00")
+    open(os.path.join(tmp, "conf.txt"), "w").write("%s\t500\tSIM1CHRVS2\n" % os.path.join(tmp, "sim_prefix.bam"))
+    subprocess.check_call([os.path.join(ROOT, "oracle", "_ref", "pindel_ref"), "-f", os.path.join(tmp, "sim_prefix.fa"), "-i",
+                           os.path.join(tmp, "conf.txt"), "-o", os.path.join(tmp, "sim_prefix.out"), "-k", "-s", "-l", "-T", "1"],
+                          stdout=subprocess.DEVNULL)
+    for suf in ("D", "SI", "INV", "TD", "LI", "BP", "RP", "CloseEndMapped"):
+        data = open(os.path.join(tmp, "sim_prefix.out_" + suf), "rb").read()
+        with gzip.open(os.path.join(HERE, "sim_prefix.out_%s.gz" % suf), "wb", compresslevel=9) as g:
+            g.write(data)
+    print("sim_prefix: %d alignments kept" % kept)
+
+
 if __name__ == "__main__":
     if len(sys.argv) > 1:
         kind, _, name = sys.argv[1].partition(":")
-        {"synth": lambda: worker_synth(name), "edge": worker_edge, "colo": worker_colo}[kind]()
+        {"synth": lambda: worker_synth(name), "edge": worker_edge, "colo": worker_colo, "bam": worker_bam}[kind]()
     else:
         for nm in SYNTH:
             subprocess.check_call([sys.executable, __file__, "synth:" + nm])
         subprocess.check_call([sys.executable, __file__, "edge"])
         subprocess.check_call([sys.executable, __file__, "colo"])
+        subprocess.check_call([sys.executable, __file__, "bam"])
         subprocess.check_call(["ls", "-la", HERE])

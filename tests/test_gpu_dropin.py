@@ -34,3 +34,26 @@ def test_reference_host_with_gpu_search_writes_identical_files(tmp_path):
         got = (tmp_path / ("colo_slice.out_" + suf)).read_bytes()
         exp = gzip.open(os.path.join(GOLD, "colo_slice.out_%s.gz" % suf)).read()
         assert got == exp, "_%s differs from the reference's file (%d vs %d bytes)" % (suf, len(got), len(exp))
+
+
+@pytest.mark.skipif(not os.path.exists(DEMO), reason="oracle/_ref/pindel_gpu_demo not built (needs /root/reference at build time)")
+def test_reference_host_bam_input_with_gpu_search(tmp_path):
+    """BAM-config input (-i): the reference's BAM reader, ReadBuffer::flush (here: the batched binding), discordant-pair
+    discovery and BreakDancer-like clusters feeding multi-region far-end searches; golden files written by the pure
+    reference binary for the same inputs (tests/golden/sim_prefix.*)."""
+    import shutil
+    fa = tmp_path / "sim_prefix.fa"
+    fa.write_bytes(gzip.open(os.path.join(GOLD, "sim_prefix.fa.gz")).read())
+    shutil.copy(os.path.join(GOLD, "sim_prefix.fa.fai"), tmp_path / "sim_prefix.fa.fai")
+    shutil.copy(os.path.join(GOLD, "sim_prefix.bam"), tmp_path / "sim_prefix.bam")
+    (tmp_path / "sim_prefix.bam.bai").write_bytes(b"BAI\x01\x00\x00\x00\x00")
+    (tmp_path / "conf.txt").write_text("%s\t500\tSIM1CHRVS2\n" % (tmp_path / "sim_prefix.bam"))
+    env = dict(os.environ, LD_LIBRARY_PATH=os.path.join(ROOT, "pindel_b200") + ":" + os.environ.get("LD_LIBRARY_PATH", ""))
+    p = subprocess.run([DEMO, "-f", str(fa), "-i", str(tmp_path / "conf.txt"), "-o", str(tmp_path / "sim_prefix.out"), "-k", "-s", "-l", "-T", "1"],
+                       capture_output=True, text=True, timeout=1200, env=env)
+    assert p.returncode == 0, p.stdout[-2000:] + p.stderr[-2000:]
+    assert "served by libpindel_pg" in p.stderr and " 0 GetCloseEnd calls" not in p.stderr
+    for suf in ("D", "SI", "INV", "TD", "LI", "BP", "RP", "CloseEndMapped"):
+        got = (tmp_path / ("sim_prefix.out_" + suf)).read_bytes()
+        exp = gzip.open(os.path.join(GOLD, "sim_prefix.out_%s.gz" % suf)).read()
+        assert got == exp, "_%s differs from the reference's file (%d vs %d bytes)" % (suf, len(got), len(exp))
