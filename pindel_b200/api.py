@@ -192,18 +192,18 @@ class PatternGrowth:
         self._check(rc, "pg_download")
         return out, runs[:res.n_runs]
 
-    def _call(self, fn, what, **batch):
+    def _call(self, fn, what, out=None, runs=None, **batch):
         r, keep = self._reads(**batch)
         n = r.n
         self._n = n
-        out = np.zeros(n, dtype=R.OUT_DT)
-        runs = np.zeros(max(1024, 24 * n), dtype=R.RUN_DT)
+        out = np.zeros(n, dtype=R.OUT_DT) if out is None else out
+        runs = np.empty(max(1024, 8 * n), dtype=R.RUN_DT) if runs is None else runs
         res = _Results(out.ctypes.data, runs.ctypes.data, runs.size, 0)
         rc = fn(self.ctx, C.byref(r), C.byref(res))
-        if rc == PG_ERR_RUNS_CAP:
-            runs = np.zeros(res.n_runs, dtype=R.RUN_DT)
+        if rc == PG_ERR_RUNS_CAP:        # the required size came back in n_runs: repeat the call with room for it
+            runs = np.empty(res.n_runs, dtype=R.RUN_DT)
             res = _Results(out.ctypes.data, runs.ctypes.data, runs.size, 0)
-            rc = self.lib.pg_download(self.ctx, C.byref(res))
+            rc = fn(self.ctx, C.byref(r), C.byref(res))
         self._check(rc, what)
         return out, runs[:res.n_runs]
 

@@ -35,6 +35,7 @@
 
 #ifndef PG_EMULATE
 #define PG_DEV __device__ __forceinline__
+#define PG_PIN(x) asm volatile("" : "+r"(x))
 #define PG_COLD __device__ __noinline__   // rarely executed helpers: one out-of-line copy keeps the kernel's code small
 PG_DEV int pg_lane() { return (int)(threadIdx.x & 31); }
 PG_DEV uint32_t pg_ballot(bool p) { return __ballot_sync(0xffffffffu, p); }
@@ -270,7 +271,8 @@ PG_DEV void pg_scan_window(PgWarpCtx<LW, TL> &cx, const PgSearch &se, int chr_id
       if (lane < LW) sp = ws->q[se.chp.arr][2][lane] | ws->q[se.chp.arr][3][lane];
       read_special = pg_any(sp != 0);
    }
-   const uint32_t valid0 = pg_valid_mask<LW, TL>(se.L, 0) & ~1u;
+   uint32_t valid0 = pg_valid_mask<LW, TL>(se.L, 0) & ~1u;
+   PG_PIN(valid0);                              // keep it in a register: it is otherwise re-derived from L in every pass
    const bool far = se.far;
    const bool single_fwd = se.d > 0;
    for (uint32_t ts = s; ts < e; ts += PG_TILE_POS) {
@@ -334,16 +336,17 @@ PG_DEV void pg_scan_window(PgWarpCtx<LW, TL> &cx, const PgSearch &se, int chr_id
             uint32_t ent = have ? (uint32_t)ws->seedq[qi] : 0u;
             uint32_t off = ent & 0x7fffu;
             bool bwd = (ent >> 15) != 0;
-            uint32_t shift = off & 31u;
-            int wi = (int)(off >> 5);
-            uint32_t inv = se.chp.inv;
-            if (bwd) { wi -= 1; shift += 1u; if (far) inv = ~inv; }
+            // the 32 reference bases the seed grows over: [off, off+32) rightwards, [off-31, off] (then reversed) leftwards
+            uint32_t first = bwd ? off - 31u : off;
+            uint32_t shift = first & 31u;
+            int wi = (int)(first >> 5);
+            uint32_t inv = (bwd && far) ? ~se.chp.inv : se.chp.inv;
             uint2 A = ws->tile[wi], B = ws->tile[wi + 1];
-            uint32_t xlo = pg_fsrc(A.x, B.x, shift), xhi = pg_fsrc(A.y, B.y, shift);
+            uint32_t xlo = pg_fsr(A.x, B.x, shift), xhi = pg_fsr(A.y, B.y, shift);
             if (bwd) { xlo = pg_brev(xlo); xhi = pg_brev(xhi); }
             uint32_t mism = (xlo ^ q0lo ^ inv) | (xhi ^ q0hi ^ inv);
             if (special) {
-               uint32_t xn = pg_fsrc(ws->tile_n[wi], ws->tile_n[wi + 1], shift);
+               uint32_t xn = pg_fsr(ws->tile_n[wi], ws->tile_n[wi + 1], shift);
                if (bwd) xn = pg_brev(xn);
                mism = (mism & ~q0n) | q0x | xn;
             }

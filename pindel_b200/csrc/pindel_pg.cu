@@ -25,6 +25,7 @@ static_assert(sizeof(pg_region) == sizeof(PgRegion) && sizeof(pg_region) == 12, 
 static_assert(sizeof(pg_close_info) == sizeof(PgCloseInfo) && sizeof(pg_close_info) == 8, "close_info layout");
 static_assert(PG_READ_FLIPPED == PG_F_FLIPPED && PG_READ_UNSUPPORTED == PG_F_TOOLONG && PG_READ_OVERFLOW == PG_F_OVERFLOW, "flags");
 
+#define PG_PIPE_CHUNK_DEFAULT (1 << 20)   // reads per chunk of the pipelined path; PG_PIPE_CHUNK in the environment overrides it (tests)
 #define PG_BLOCK_THREADS 256
 #ifndef PG_MINB
 #define PG_MINB 4          // resident CTAs per SM the register allocator is asked to make room for (TL <= 8 variants)
@@ -152,7 +153,12 @@ struct pg_ctx {
    uint64_t launches = 0;
    uint32_t last_runs = 0;
    uint64_t last_window_bases = 0, last_ups = 0;
+   struct PipeState *pipe = nullptr;    // streams, events and the two chunk slots of the pipelined path (lazy)
+   int pipe_chunk = PG_PIPE_CHUNK_DEFAULT;
 };
+
+struct PipeState;
+static void pipe_destroy(PipeState *ps);
 
 static thread_local std::string g_create_error;
 
@@ -179,7 +185,7 @@ static int ensure(pg_ctx *ctx, DevBuf &b, size_t bytes)
 }
 
 template <int LW, int TL>
-static int launch_variant(pg_ctx *ctx, const PgBatch &bt_in)
+static int launch_variant(pg_ctx *ctx, const PgBatch &bt_in, cudaStream_t stream, DevBuf &scratch)
 {
    PgBatch bt = bt_in;
    size_t smem = sizeof(PgWarpSmem<LW, TL>) * PG_WARPS_PER_BLOCK;
@@ -191,13 +197,37 @@ static int launch_variant(pg_ctx *ctx, const PgBatch &bt_in)
    long need_blocks = ((long)bt.n_reads + PG_WARPS_PER_BLOCK - 1) / PG_WARPS_PER_BLOCK;
    if (need_blocks < grid) grid = (int)(need_blocks > 0 ? need_blocks : 1);
    bt.scratch_cap = 32u * LW;
-   int rc = ensure(ctx, ctx->scratch, sizeof(PgRun) * 3u * bt.scratch_cap * (size_t)grid * PG_WARPS_PER_BLOCK);
+   int rc = ensure(ctx, scratch, sizeof(PgRun) * 3u * bt.scratch_cap * (size_t)grid * PG_WARPS_PER_BLOCK);
    if (rc != PG_OK) return rc;
-   bt.scratch = (PgRun *)ctx->scratch.p;
-   pg_search_kernel<LW, TL><<<grid, PG_BLOCK_THREADS, smem, ctx->stream>>>(bt, ctx->prm_d, ctx->chroms_d);
+   bt.scratch = (PgRun *)scratch.p;
+   pg_search_kernel<LW, TL><<<grid, PG_BLOCK_THREADS, smem, stream>>>(bt, ctx->prm_d, ctx->chroms_d);
    CU(cudaGetLastError());
    ctx->launches++;
    return PG_OK;
+}
+
+// Picks the kernel variant: LW = 32-base words per read plane, TL = mismatch levels tracked per seed -- the smallest
+// compiled value that covers the batch (exact for the common single-read-length batch, so the per-level loops carry no
+// dead levels).
+static int dispatch_variant(pg_ctx *ctx, const PgBatch &bt, uint32_t max_read_len, cudaStream_t stream, DevBuf &scratch)
+{
+   int need_t = 0;
+   for (uint32_t l = 0; l <= max_read_len && l < 512; l++) {
+      int t = (int)ctx->prm_h.g[l] + ctx->prm_h.add_mm + 1;
+      if (t > need_t) need_t = t;
+   }
+   if (need_t > 32) return fail(ctx, PG_ERR_UNSUPPORTED, "more than 32 mismatch levels (g_maxMismatch + -a + 1)");
+   if (max_read_len <= 256) {
+      if (need_t <= 5) return launch_variant<8, 5>(ctx, bt, stream, scratch);
+      if (need_t <= 6) return launch_variant<8, 6>(ctx, bt, stream, scratch);
+      if (need_t <= 7) return launch_variant<8, 7>(ctx, bt, stream, scratch);
+      if (need_t <= 8) return launch_variant<8, 8>(ctx, bt, stream, scratch);
+      if (need_t <= 12) return launch_variant<8, 12>(ctx, bt, stream, scratch);
+      if (need_t <= 16) return launch_variant<8, 16>(ctx, bt, stream, scratch);
+   }
+   if (need_t <= 8) return launch_variant<16, 8>(ctx, bt, stream, scratch);
+   if (need_t <= 16) return launch_variant<16, 16>(ctx, bt, stream, scratch);
+   return launch_variant<16, 32>(ctx, bt, stream, scratch);
 }
 
 extern "C" {
@@ -257,6 +287,7 @@ pg_ctx *pg_create(const pg_settings *s)
       return nullptr;
    }
    ctx->stream = ctx->own_stream;
+   if (const char *e = getenv("PG_PIPE_CHUNK")) { int v = atoi(e); if (v >= 256) ctx->pipe_chunk = v; }
    return ctx;
 }
 
@@ -269,6 +300,7 @@ void pg_destroy(pg_ctx *ctx)
    DevBuf *bufs[] = {&ctx->seq_blob, &ctx->seq_off, &ctx->md, &ctx->pos, &ctx->isz, &ctx->chr, &ctx->closeinfo,
                      &ctx->regions, &ctx->region_off, &ctx->out, &ctx->pool, &ctx->counters, &ctx->scratch};
    for (DevBuf *b : bufs) if (b->p) cudaFree(b->p);
+   pipe_destroy(ctx->pipe);
    if (ctx->chroms_d) cudaFree(ctx->chroms_d);
    if (ctx->prm_d) cudaFree(ctx->prm_d);
    if (ctx->counters_h) cudaFreeHost(ctx->counters_h);
@@ -431,26 +463,7 @@ int pg_launch(pg_ctx *ctx, int32_t mode)
    bt.run_pool = (PgRun *)ctx->pool.p;
    bt.run_pool_cap = ctx->pool_cap;
    bt.counters = (uint32_t *)ctx->counters.p;
-   // variant: words per read plane (LW) and mismatch levels tracked (TL)
-   int need_t = 0;
-   for (uint32_t l = 0; l <= ctx->max_read_len && l < 512; l++) {
-      int t = (int)ctx->prm_h.g[l] + ctx->prm_h.add_mm + 1;
-      if (t > need_t) need_t = t;
-   }
-   if (need_t > 32) return fail(ctx, PG_ERR_UNSUPPORTED, "more than 32 mismatch levels (g_maxMismatch + -a + 1)");
-   // TL = mismatch levels tracked per seed: the smallest compiled value that covers the batch (exact for the
-   // common single-read-length batch, so the per-level loops carry no dead levels)
-   if (ctx->max_read_len <= 256) {
-      if (need_t <= 5) return launch_variant<8, 5>(ctx, bt);
-      if (need_t <= 6) return launch_variant<8, 6>(ctx, bt);
-      if (need_t <= 7) return launch_variant<8, 7>(ctx, bt);
-      if (need_t <= 8) return launch_variant<8, 8>(ctx, bt);
-      if (need_t <= 12) return launch_variant<8, 12>(ctx, bt);
-      if (need_t <= 16) return launch_variant<8, 16>(ctx, bt);
-   }
-   if (need_t <= 8) return launch_variant<16, 8>(ctx, bt);
-   if (need_t <= 16) return launch_variant<16, 16>(ctx, bt);
-   return launch_variant<16, 32>(ctx, bt);
+   return dispatch_variant(ctx, bt, ctx->max_read_len, ctx->stream, ctx->scratch);
 }
 
 int pg_sync(pg_ctx *ctx)
@@ -505,8 +518,223 @@ int pg_download(pg_ctx *ctx, pg_results *res)
    return PG_OK;
 }
 
+
+} // extern "C"
+
+// ------------------------------------------------------------------------------------------------
+// Large batches: chunks of ctx->pipe_chunk reads flow through two device slots on three streams, so that the H2D copy
+// of chunk c+1 and the D2H copy of chunk c-1 overlap the search kernel of chunk c.
+// ------------------------------------------------------------------------------------------------
+
+struct PipeSlot {
+   DevBuf seq_blob, seq_off, md, pos, isz, chr, closeinfo, regions, region_off, out, pool, counters, scratch;
+   uint32_t pool_cap = 0;
+   uint32_t *counters_h = nullptr;
+   cudaEvent_t in_done = nullptr, k_done = nullptr, cnt_done = nullptr, out_done = nullptr;
+   int c0 = 0, c1 = 0;
+   uint32_t n_runs = 0;
+   bool busy = false;
+};
+
+struct PipeState {
+   PipeSlot slot[2];
+   cudaStream_t s_in = nullptr, s_k = nullptr, s_out = nullptr;
+   bool ready = false;
+};
+
+static void pipe_destroy(PipeState *ps)
+{
+   if (!ps) return;
+   for (int i = 0; i < 2; i++) {
+      PipeSlot &sl = ps->slot[i];
+      DevBuf *bufs[] = {&sl.seq_blob, &sl.seq_off, &sl.md, &sl.pos, &sl.isz, &sl.chr, &sl.closeinfo, &sl.regions, &sl.region_off,
+                        &sl.out, &sl.pool, &sl.counters, &sl.scratch};
+      for (DevBuf *b : bufs) if (b->p) cudaFree(b->p);
+      if (sl.counters_h) cudaFreeHost(sl.counters_h);
+      cudaEvent_t evs[] = {sl.in_done, sl.k_done, sl.cnt_done, sl.out_done};
+      for (cudaEvent_t e : evs) if (e) cudaEventDestroy(e);
+   }
+   if (ps->s_in) cudaStreamDestroy(ps->s_in);
+   if (ps->s_k) cudaStreamDestroy(ps->s_k);
+   if (ps->s_out) cudaStreamDestroy(ps->s_out);
+   delete ps;
+}
+
+static int pipe_init(pg_ctx *ctx, PipeState *&ps)
+{
+   if (ps && ps->ready) return PG_OK;
+   if (!ps) ps = new PipeState();
+   CU(cudaStreamCreateWithFlags(&ps->s_in, cudaStreamNonBlocking));
+   CU(cudaStreamCreateWithFlags(&ps->s_k, cudaStreamNonBlocking));
+   CU(cudaStreamCreateWithFlags(&ps->s_out, cudaStreamNonBlocking));
+   for (int i = 0; i < 2; i++) {
+      PipeSlot &sl = ps->slot[i];
+      CU(cudaHostAlloc((void **)&sl.counters_h, 32, cudaHostAllocDefault));
+      CU(cudaEventCreateWithFlags(&sl.in_done, cudaEventDisableTiming));
+      CU(cudaEventCreateWithFlags(&sl.k_done, cudaEventDisableTiming));
+      CU(cudaEventCreateWithFlags(&sl.cnt_done, cudaEventDisableTiming));
+      CU(cudaEventCreateWithFlags(&sl.out_done, cudaEventDisableTiming));
+   }
+   ps->ready = true;
+   return PG_OK;
+}
+
+static int pipe_launch_kernel(pg_ctx *ctx, PipeState *ps, PipeSlot &sl, const pg_reads *in, int mode, uint32_t max_read_len)
+{
+   const int m = sl.c1 - sl.c0;
+   const bool have_anchor = in->matched_d && in->matched_rel_pos && in->insert_size;
+   const bool have_regions = in->regions && in->region_off;
+   CU(cudaMemsetAsync(sl.counters.p, 0, 32, ps->s_k));
+   PgBatch bt;
+   memset(&bt, 0, sizeof(bt));
+   bt.n_reads = m;
+   bt.mode = mode;
+   // offsets stay absolute (as the caller gave them); the blob / region pointers are shifted instead
+   bt.seq_blob = (const uint8_t *)sl.seq_blob.p - in->seq_off[sl.c0];
+   bt.seq_off = (const uint32_t *)sl.seq_off.p;
+   bt.matched_d = have_anchor ? (const uint8_t *)sl.md.p : nullptr;
+   bt.matched_rel_pos = have_anchor ? (const uint32_t *)sl.pos.p : nullptr;
+   bt.insert_size = have_anchor ? (const int16_t *)sl.isz.p : nullptr;
+   bt.chr_id = in->chr_id ? (const int32_t *)sl.chr.p : nullptr;
+   bt.close_info = (mode == 2 && in->close_info) ? (const PgCloseInfo *)sl.closeinfo.p : nullptr;
+   bt.regions = have_regions ? (const PgRegion *)sl.regions.p - in->region_off[sl.c0] : nullptr;
+   bt.region_off = have_regions ? (const uint32_t *)sl.region_off.p : nullptr;
+   bt.out = (PgReadOut *)sl.out.p;
+   bt.run_pool = (PgRun *)sl.pool.p;
+   bt.run_pool_cap = sl.pool_cap;
+   bt.counters = (uint32_t *)sl.counters.p;
+   int rc = dispatch_variant(ctx, bt, max_read_len, ps->s_k, sl.scratch);
+   if (rc != PG_OK) return rc;
+   CU(cudaEventRecord(sl.k_done, ps->s_k));
+   CU(cudaMemcpyAsync(sl.counters_h, sl.counters.p, 32, cudaMemcpyDeviceToHost, ps->s_k));
+   CU(cudaEventRecord(sl.cnt_done, ps->s_k));
+   return PG_OK;
+}
+
+static int run_pipelined(pg_ctx *ctx, PipeState *&ps, const pg_reads *in, pg_results *res, int mode)
+{
+   const int n = in->n;
+   const bool have_anchor = in->matched_d && in->matched_rel_pos && in->insert_size;
+   const bool have_regions = in->regions && in->region_off;
+   if ((mode & 1) && !have_anchor) return fail(ctx, PG_ERR_ARG, "close-end search needs matched_d, matched_rel_pos and insert_size");
+   if (mode == 2 && !in->close_info) return fail(ctx, PG_ERR_ARG, "far-end-only search needs close_info");
+   if (ctx->chroms_h.empty()) return fail(ctx, PG_ERR_STATE, "no reference (call pg_set_reference)");
+   if (!res || !res->out) return fail(ctx, PG_ERR_ARG, "results buffers missing");
+   uint32_t maxlen = 0;
+   for (int i = 0; i < n; i++) {
+      if (in->seq_off[i + 1] < in->seq_off[i]) return fail(ctx, PG_ERR_ARG, "seq_off must be non-decreasing");
+      uint32_t l = in->seq_off[i + 1] - in->seq_off[i];
+      if (l > maxlen) maxlen = l;
+      if (in->chr_id && (in->chr_id[i] < 0 || (size_t)in->chr_id[i] >= ctx->chroms_h.size()))
+         return fail(ctx, PG_ERR_ARG, "chr_id out of range");
+   }
+   if (maxlen >= PG_TABLE)
+      return fail(ctx, PG_ERR_UNSUPPORTED, "read longer than 499 bases (the reference's g_maxMismatch table has 500 entries)");
+   if (have_regions)
+      for (size_t i = 0, nr = in->region_off[n]; i < nr; i++)
+         if (in->regions[i].chr < 0 || (size_t)in->regions[i].chr >= ctx->chroms_h.size())
+            return fail(ctx, PG_ERR_ARG, "region chromosome out of range");
+   int rc = pipe_init(ctx, ps);
+   if (rc != PG_OK) return rc;
+   CU(cudaStreamSynchronize(ctx->stream));         // everything queued by the caller on its stream comes first
+   ctx->launched = false;                           // no resident batch after a pipelined call
+   ctx->n = 0;
+   const int nchunks = (n + ctx->pipe_chunk - 1) / ctx->pipe_chunk;
+   uint64_t total_runs = 0, wb = 0, ups = 0;
+   bool cap_exceeded = false;
+   auto drain = [&](PipeSlot &sl) -> int {        // kernel of this slot is done: copy its results out
+      CU(cudaEventSynchronize(sl.cnt_done));
+      if (sl.counters_h[2] != 0) {                // run pool too small for this chunk: grow exactly, run the chunk again
+         uint32_t need = sl.counters_h[1];
+         CU(cudaFree(sl.pool.p));
+         sl.pool.p = nullptr; sl.pool.cap = 0;
+         int r = ensure(ctx, sl.pool, sizeof(PgRun) * ((size_t)need + 1024u));
+         if (r != PG_OK) return r;
+         sl.pool_cap = (uint32_t)(sl.pool.cap / sizeof(PgRun));
+         r = pipe_launch_kernel(ctx, ps, sl, in, mode, maxlen);
+         if (r != PG_OK) return r;
+         CU(cudaEventSynchronize(sl.cnt_done));
+         if (sl.counters_h[2] != 0) return fail(ctx, PG_ERR_CUDA, "run pool kept overflowing");
+      }
+      sl.n_runs = sl.counters_h[1];
+      uint64_t a, b;
+      memcpy(&a, sl.counters_h + 4, 8); memcpy(&b, sl.counters_h + 6, 8);
+      wb += a; ups += b;
+      const int m = sl.c1 - sl.c0;
+      CU(cudaStreamWaitEvent(ps->s_out, sl.k_done, 0));
+      CU(cudaMemcpyAsync(res->out + sl.c0, sl.out.p, sizeof(PgReadOut) * (size_t)m, cudaMemcpyDeviceToHost, ps->s_out));
+      if (total_runs + sl.n_runs <= res->runs_cap && res->runs) {
+         if (sl.n_runs)
+            CU(cudaMemcpyAsync(res->runs + total_runs, sl.pool.p, sizeof(PgRun) * (size_t)sl.n_runs, cudaMemcpyDeviceToHost, ps->s_out));
+      } else {
+         cap_exceeded = true;
+      }
+      CU(cudaEventRecord(sl.out_done, ps->s_out));
+      CU(cudaEventSynchronize(sl.out_done));       // (the next chunk's kernel is already running behind this wait)
+      const uint32_t base = (uint32_t)total_runs;  // run offsets of this chunk become offsets into the caller's buffer
+      if (base)
+         for (int i = sl.c0; i < sl.c1; i++) res->out[i].run_off += base;
+      total_runs += sl.n_runs;
+      sl.busy = false;
+      return PG_OK;
+   };
+   for (int c = 0; c < nchunks; c++) {
+      PipeSlot &sl = ps->slot[c & 1];
+      if (sl.busy) { rc = drain(sl); if (rc != PG_OK) return rc; }
+      sl.c0 = c * ctx->pipe_chunk;
+      sl.c1 = (sl.c0 + ctx->pipe_chunk < n) ? sl.c0 + ctx->pipe_chunk : n;
+      const int m = sl.c1 - sl.c0;
+#define UPS(buf, src, bytes)                                                                              \
+   if ((rc = ensure(ctx, buf, (bytes))) != PG_OK) return rc;                                              \
+   CU(cudaMemcpyAsync(buf.p, (src), (bytes), cudaMemcpyHostToDevice, ps->s_in))
+      size_t b0 = in->seq_off[sl.c0], b1 = in->seq_off[sl.c1];
+      UPS(sl.seq_blob, in->seq_blob + b0, (b1 - b0) ? (b1 - b0) : 1);
+      UPS(sl.seq_off, in->seq_off + sl.c0, sizeof(uint32_t) * ((size_t)m + 1));
+      if (have_anchor) {
+         UPS(sl.md, in->matched_d + sl.c0, (size_t)m);
+         UPS(sl.pos, in->matched_rel_pos + sl.c0, sizeof(uint32_t) * (size_t)m);
+         UPS(sl.isz, in->insert_size + sl.c0, sizeof(int16_t) * (size_t)m);
+      }
+      if (in->chr_id) { UPS(sl.chr, in->chr_id + sl.c0, sizeof(int32_t) * (size_t)m); }
+      if (mode == 2 && in->close_info) { UPS(sl.closeinfo, in->close_info + sl.c0, sizeof(pg_close_info) * (size_t)m); }
+      if (have_regions) {
+         size_t r0 = in->region_off[sl.c0], r1 = in->region_off[sl.c1];
+         UPS(sl.regions, in->regions + r0, sizeof(pg_region) * ((r1 - r0) ? (r1 - r0) : 1));
+         UPS(sl.region_off, in->region_off + sl.c0, sizeof(uint32_t) * ((size_t)m + 1));
+      }
+#undef UPS
+      CU(cudaEventRecord(sl.in_done, ps->s_in));
+      if ((rc = ensure(ctx, sl.out, sizeof(PgReadOut) * (size_t)m)) != PG_OK) return rc;
+      if ((rc = ensure(ctx, sl.counters, 32)) != PG_OK) return rc;
+      if (sl.pool_cap == 0) {
+         if ((rc = ensure(ctx, sl.pool, sizeof(PgRun) * ((size_t)ctx->pipe_chunk * 12u + 4096u))) != PG_OK) return rc;
+         sl.pool_cap = (uint32_t)(sl.pool.cap / sizeof(PgRun));
+      }
+      CU(cudaStreamWaitEvent(ps->s_k, sl.in_done, 0));
+      rc = pipe_launch_kernel(ctx, ps, sl, in, mode, maxlen);
+      if (rc != PG_OK) return rc;
+      sl.busy = true;
+   }
+   for (int k = 0; k < 2; k++) {                  // drain in chunk order
+      PipeSlot &sl = ps->slot[(nchunks + k) & 1];
+      if (sl.busy) { rc = drain(sl); if (rc != PG_OK) return rc; }
+   }
+   ctx->last_runs = (uint32_t)total_runs;
+   ctx->last_window_bases = wb;
+   ctx->last_ups = ups;
+   res->n_runs = (uint32_t)total_runs;
+   if (cap_exceeded) return fail(ctx, PG_ERR_RUNS_CAP, "run buffer too small (results->n_runs holds the required size; repeat the call)");
+   return PG_OK;
+}
+
+extern "C" {
+
 static int run_all(pg_ctx *ctx, const pg_reads *in, pg_results *res, int mode)
 {
+   if (ctx && in && in->n >= 2 * ctx->pipe_chunk && in->seq_blob && in->seq_off) {
+      CU(cudaSetDevice(ctx->device));
+      return run_pipelined(ctx, ctx->pipe, in, res, mode);
+   }
    int rc = pg_upload(ctx, in);
    if (rc != PG_OK) return rc;
    rc = pg_launch(ctx, mode);

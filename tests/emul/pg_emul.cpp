@@ -15,6 +15,7 @@
 #define PG_EMULATE 1
 #define PG_DEV static inline
 #define PG_COLD static
+#define PG_PIN(x) ((void)(x))
 struct uint2 { uint32_t x, y; };
 
 enum { OP_NONE, OP_BALLOT, OP_ANY, OP_SHFL, OP_SHFL_UP, OP_MAX, OP_ADD, OP_OR, OP_SYNC };

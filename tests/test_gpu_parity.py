@@ -83,3 +83,29 @@ def test_table_matches_oracle():
     pg = api.PatternGrowth()
     assert np.array_equal(pg.max_mismatch_table(), pgoracle.prob_table())
     pg.close()
+
+
+def test_pipelined_large_batch_path_equals_single_launch(ref2m, monkeypatch):
+    """Batches of >= 2 chunks go through the chunked, copy/compute-overlapped path of pg_search; with a small chunk size
+    (PG_PIPE_CHUNK) the same code runs on a test-sized batch and must return exactly what a single launch returns."""
+    ref, padded = ref2m
+    batch = synth.make_reads(ref, 7003, 100, seed=41)
+    kw = H.batch_kwargs(batch)
+    pg1 = api.PatternGrowth()
+    pg1.set_reference([padded])
+    a = R.per_read(*pg1.search(**kw), kw["seq_blob"], kw["seq_off"])
+    launches_single = pg1.kernel_launches
+    pg1.close()
+    monkeypatch.setenv("PG_PIPE_CHUNK", "1000")
+    pg2 = api.PatternGrowth()
+    pg2.set_reference([padded])
+    out, runs = pg2.search(**kw)
+    b = R.per_read(out, runs, kw["seq_blob"], kw["seq_off"])
+    assert pg2.kernel_launches >= 8 and launches_single == 1
+    H.compare(a, b, "pipelined vs single launch")
+    # a run buffer that is too small is reported with the required size, then the repeated call succeeds
+    small = np.empty(10, dtype=R.RUN_DT)
+    out2, runs2 = pg2.search(runs=small, **kw)
+    H.compare(a, R.per_read(out2, runs2, kw["seq_blob"], kw["seq_off"]), "pipelined after RUNS_CAP retry")
+    wb, ups = pg2.last_stats() if False else (0, 0)
+    pg2.close()
