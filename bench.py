@@ -103,7 +103,7 @@ class ClockSampler:
         sm_sorted = sorted(sm)
         load = sm_sorted[len(sm_sorted) // 2:] if sm_sorted else []
         return {"sm_mhz": float(np.median(load)) if load else None, "sm_max_mhz": max(mx) if mx else None,
-                "samples": len(sm), "reasons": sorted(reasons)}
+                "sm_mhz_min": min(sm) if sm else None, "samples": len(sm), "reasons": sorted(reasons)}
 
 
 def measured_hbm_peak():

@@ -447,17 +447,14 @@ PG_DEV PgResult pg_walk_emit(PgWarpCtx<LW, TL> &cx, const PgSearch &se, PgRun *d
    uint32_t run_len0 = 0, run_cnt = 0, run_m = 0;
    int prev_valid = 0; uint32_t prev_m = 0;
    // A_t is non-decreasing in t: no length beyond A_MAX can pass the in-range test (m would be MAX+1 > g[len])
-   uint32_t Areg[TL];
-#pragma unroll
-   for (int t = 0; t < TL; t++) Areg[t] = (t <= MAX) ? ws->A[t] : 0xffffffffu;
    int len_hi = (int)ws->A[MAX];
    if (len_hi > L - 1) len_hi = L - 1;
    for (int r0 = se.bp_start; r0 <= len_hi && !dead; r0 += 32) {
       int len = r0 + lane;
       bool inrange = len <= L - 1;
       int m = 0;
-#pragma unroll
-      for (int t = 0; t < TL; t++) m += (Areg[t] < (uint32_t)len) ? 1 : 0;      // levels > MAX hold ~0: never counted
+#pragma unroll 1
+      for (int t = 0; t <= MAX; t++) m += (ws->A[t] < (uint32_t)len) ? 1 : 0;
       bool abort_here = inrange && ((uint32_t)m > (uint32_t)prm->g[len]);       // searcher.cpp:167-169, pindel.cpp:2836-2838
       uint32_t abmask = pg_ballot(abort_here);
       uint32_t live = abmask ? ((1u << (pg_ffs(abmask) - 1)) - 1u) : 0xffffffffu;

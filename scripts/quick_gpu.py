@@ -21,5 +21,12 @@ pg.upload(**kw)
 for it in range(3):
     t = time.time(); pg.launch(3); pg.sync(); dt = time.time() - t
     print("kernel only %.4fs  %.3f Mreads/s" % (dt, n / dt / 1e6))
+if len(sys.argv) > 4:      # back-to-back launches, like bench.py's timed region
+    k = int(sys.argv[4])
+    t = time.time()
+    for it in range(k):
+        pg.launch(3)
+    pg.sync(); dt = (time.time() - t) / k
+    print("kernel x%d back to back %.4fs  %.3f Mreads/s" % (k, dt, n / dt / 1e6))
 res = R.per_read(out[:2000], runs)
 print("close found", sum(1 for r in res if len(r["close"])), "far found", sum(1 for r in res if len(r["far"])), "of 2000")
