@@ -344,6 +344,8 @@ def main():
                         "the path is not HBM-bound at Pindel's default -x: the packed reference is L2-resident (see DESIGN.md)"}
     if traffic:
         roofline["traffic_source"] = traffic.get("source")
+        if "compute" in traffic:
+            roofline["compute"] = traffic["compute"]      # ncu issue/pipe utilisation of the same kernel (committed digest)
 
     result = {
         "metric": "anchored split-reads/sec through pattern-growth search", "value": value, "unit": "reads/s",
