@@ -1,0 +1,249 @@
+// include/pindel_pg.hpp -- header-only C++ host mirror of the reference's search seam on top of the C ABI
+// (include/pindel_pg.h).  Names, argument meaning and side effects follow the reference (citations under
+// /root/reference/): a maintainer who knows
+//
+//     void GetCloseEnd(const std::string& CurrentChrSeq, SPLIT_READ& read)                    src/pindel.h:523
+//     void SearchFarEnds(const std::string&, std::vector<SPLIT_READ>&, const Chromosome&)     src/pindel.h:741
+//     struct UniquePoint / class SortedUniquePoints / struct SPLIT_READ                       src/pindel.h:137-197,265-383
+//     std::string ReverseComplement(const std::string&)                                       src/pindel.cpp:2037-2048
+//     void CleanUniquePoints(SortedUniquePoints&)                                             src/pindel.cpp:2904-2941
+//
+// finds the same things here, batched: Searcher::GetCloseEnd(reads) and Searcher::SearchFarEnds(reads, clusters) take the
+// whole vector.  No search logic lives in this header; without a CUDA device the Searcher constructor throws.
+#ifndef PINDEL_PG_HPP
+#define PINDEL_PG_HPP
+#include <cctype>
+#include <cstring>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+#include "pindel_pg.h"
+
+namespace pindel_pg {
+
+const char SENSE = '+', ANTISENSE = '-', FORWARD = '+', BACKWARD = '-';        // src/pindel.h:110-113
+const unsigned g_SpacerBeforeAfter = 100000;                                     // src/pindel.h:122
+
+struct UniquePoint {                     // src/pindel.h:137-158; the chromosome is an index into the reference list
+   int chromosome_id;
+   short LengthStr;
+   unsigned int AbsLoc;
+   char Direction;
+   char Strand;
+   short Mismatches;
+};
+
+class SortedUniquePoints {               // src/pindel.h:160-197
+public:
+   void push_back(const UniquePoint &up) { m_positions.push_back(up); }
+   unsigned int size() const { return (unsigned int)m_positions.size(); }
+   bool empty() const { return m_positions.empty(); }
+   void clear() { m_positions.clear(); }
+   unsigned int MaxLen() const { return m_positions.empty() ? 0u : (unsigned int)m_positions.back().LengthStr; }   // src/pindel.cpp:490-498
+   const UniquePoint &operator[](unsigned int i) const { return m_positions[i]; }
+   UniquePoint &operator[](unsigned int i) { return m_positions[i]; }
+   void swap(SortedUniquePoints &o) { m_positions.swap(o.m_positions); }
+private:
+   std::vector<UniquePoint> m_positions;
+};
+
+inline std::string ReverseComplement(const std::string &in)     // src/pindel.cpp:2037-2048 with Convert2RC4N (:966-970)
+{
+   std::string out(in.size(), '\0');
+   for (size_t j = 0; j < in.size(); j++) {
+      char c = in[in.size() - 1 - j], r;
+      switch (c) { case 'A': r = 'T'; break; case 'C': r = 'G'; break; case 'G': r = 'C'; break; case 'T': r = 'A'; break;
+                   case 'N': r = 'N'; break; default: r = '\0'; }
+      out[j] = r;
+   }
+   return out;
+}
+
+inline void CleanUniquePoints(SortedUniquePoints &ups)          // src/pindel.cpp:2904-2941
+{
+   if (ups.empty()) return;
+   SortedUniquePoints kept;
+   const UniquePoint last = ups[ups.size() - 1];
+   const unsigned terminal = last.Direction == FORWARD ? last.AbsLoc - last.LengthStr : last.AbsLoc + last.LengthStr;
+   for (unsigned i = 0; i < ups.size(); i++) {
+      const UniquePoint &u = ups[i];
+      if (u.chromosome_id != last.chromosome_id || u.Direction != last.Direction || u.Strand != last.Strand) continue;
+      unsigned t = last.Direction == FORWARD ? u.AbsLoc - u.LengthStr : u.AbsLoc + u.LengthStr;
+      if (t == terminal) kept.push_back(u);
+   }
+   ups.swap(kept);
+}
+
+struct SPLIT_READ {                      // the fields of src/pindel.h:265-383 that the search path reads or writes
+   std::string Name;
+   int chromosome_id = 0;                // FragName, as an index
+   char MatchedD = 0;
+   unsigned int MatchedRelPos = 0;
+   short InsertSize = 0;
+   bool Used = false;
+   bool MapperSplit = false;
+   SortedUniquePoints UP_Close, UP_Far;
+
+   void setUnmatchedSeq(const std::string &s)                    // src/pindel.cpp:142-169: trailing non-alphanumerics are stripped
+   {
+      UnmatchedSeq = s;
+      while (!UnmatchedSeq.empty() && !std::isalnum((unsigned char)UnmatchedSeq[UnmatchedSeq.size() - 1])) UnmatchedSeq.resize(UnmatchedSeq.size() - 1);
+   }
+   const std::string &getUnmatchedSeq() const { return UnmatchedSeq; }
+   short getReadLength() const { return (short)UnmatchedSeq.size(); }
+   bool hasCloseEnd() const { return !UP_Close.empty(); }
+   unsigned int getLastAbsLocCloseEnd() const { return UP_Close[UP_Close.size() - 1].AbsLoc; }        // src/pindel.cpp:474-477
+   bool goodFarEndFound() const { return UP_Far.MaxLen() + UP_Close.MaxLen() >= UnmatchedSeq.size(); } // src/pindel.cpp:480-483
+private:
+   std::string UnmatchedSeq;
+};
+
+struct SearchWindow { int chromosome_id; unsigned int start, end; };   // src/pindel.h:665-716, [start, end) padded coordinates
+typedef std::vector<SearchWindow> SearchWindowCluster;
+
+class Searcher {
+public:
+   explicit Searcher(const pg_settings &s) : ctx_(pg_create(&s))
+   {
+      if (!ctx_) throw std::runtime_error(std::string("pg_create: ") + pg_create_error());
+   }
+   Searcher() : ctx_(NULL)
+   {
+      pg_settings s;
+      pg_default_settings(&s);
+      ctx_ = pg_create(&s);
+      if (!ctx_) throw std::runtime_error(std::string("pg_create: ") + pg_create_error());
+   }
+   ~Searcher() { pg_destroy(ctx_); }
+
+   // the padded in-memory chromosome strings (Genome::loadAll, src/pindel.cpp:237-312), in chromosome_id order
+   void setReference(const std::vector<std::string> &chromosomes)
+   {
+      std::vector<const char *> p;
+      std::vector<uint32_t> l;
+      for (size_t i = 0; i < chromosomes.size(); i++) { p.push_back(chromosomes[i].data()); l.push_back((uint32_t)chromosomes[i].size()); }
+      check(pg_set_reference(ctx_, (int32_t)p.size(), p.data(), l.data()), "pg_set_reference");
+   }
+
+   std::vector<unsigned int> maxMismatchTable()                  // g_maxMismatch, src/pindel.cpp:794-819
+   {
+      std::vector<uint32_t> t(500);
+      check(pg_max_mismatch_table(ctx_, t.data()), "pg_max_mismatch_table");
+      return std::vector<unsigned int>(t.begin(), t.end());
+   }
+
+   // GetCloseEnd for every read (src/pindel.cpp:2531-2605): may reverse-complement the read, fills UP_Close (not cleaned).
+   void GetCloseEnd(std::vector<SPLIT_READ> &reads)
+   {
+      Batch b(reads, NULL, false);
+      run(pg_close_end, b, "pg_close_end");
+      for (size_t i = 0; i < reads.size(); i++) {
+         SPLIT_READ &r = reads[i];
+         for (unsigned f = 0; f < PG_READ_NFLIPS(b.out[i].flags); f++) r.setUnmatchedSeq(ReverseComplement(r.getUnmatchedSeq()));
+         r.UP_Close.clear();
+         append(r.UP_Close, b.runs.data() + b.out[i].run_off, b.out[i].n_close_runs);
+         if (!r.UP_Close.empty()) r.Used = false;               // src/pindel.cpp:2294, :2321
+      }
+   }
+
+   // SearchFarEnds (src/pindel.cpp:1115-1138) for reads whose UP_Close is set (already cleaned, as in the reference);
+   // clusters[i] = g_bdData.getCorrespondingSearchWindowCluster(reads[i]) or empty.
+   void SearchFarEnds(std::vector<SPLIT_READ> &reads, const std::vector<SearchWindowCluster> *clusters = NULL)
+   {
+      Batch b(reads, clusters, true);
+      run(pg_far_end, b, "pg_far_end");
+      for (size_t i = 0; i < reads.size(); i++) {
+         if (reads[i].MapperSplit || reads[i].UP_Close.empty()) continue;
+         reads[i].UP_Far.clear();
+         append(reads[i].UP_Far, b.runs.data() + b.out[i].run_off + b.out[i].n_close_runs, b.out[i].n_far_runs);
+      }
+   }
+
+   uint64_t kernelLaunches() const { return pg_kernel_launches(ctx_); }
+
+private:
+   struct Batch {
+      std::string blob;
+      std::vector<uint32_t> off, pos, region_off;
+      std::vector<char> md;
+      std::vector<int16_t> isz;
+      std::vector<int32_t> chr;
+      std::vector<pg_close_info> ci;
+      std::vector<pg_region> regions;
+      std::vector<pg_read_out> out;
+      std::vector<pg_run> runs;
+      pg_reads in;
+      Batch(const std::vector<SPLIT_READ> &reads, const std::vector<SearchWindowCluster> *clusters, bool far)
+      {
+         const size_t n = reads.size();
+         off.assign(n + 1, 0); pos.resize(n); md.resize(n); isz.resize(n); chr.resize(n); ci.resize(n); region_off.assign(n + 1, 0);
+         for (size_t i = 0; i < n; i++) {
+            const SPLIT_READ &r = reads[i];
+            blob += r.getUnmatchedSeq();
+            off[i + 1] = (uint32_t)blob.size();
+            pos[i] = r.MatchedRelPos; md[i] = r.MatchedD; isz[i] = r.InsertSize; chr[i] = r.chromosome_id;
+            ci[i].pad = 0; ci[i].max_len = 0; ci[i].last_abs_loc = 0;
+            if (far && !r.MapperSplit && !r.UP_Close.empty()) {
+               ci[i].max_len = (uint16_t)r.UP_Close.MaxLen();
+               ci[i].last_abs_loc = r.getLastAbsLocCloseEnd();
+               if (clusters)
+                  for (size_t k = 0; k < (*clusters)[i].size(); k++) {
+                     pg_region g;
+                     g.chr = (*clusters)[i][k].chromosome_id; g.start = (*clusters)[i][k].start; g.end = (*clusters)[i][k].end;
+                     regions.push_back(g);
+                  }
+            }
+            region_off[i + 1] = (uint32_t)regions.size();
+         }
+         std::memset(&in, 0, sizeof(in));
+         in.n = (int32_t)n; in.seq_blob = blob.data(); in.seq_off = off.data(); in.chr_id = n ? chr.data() : NULL;
+         if (!far) { in.matched_d = md.data(); in.matched_rel_pos = pos.data(); in.insert_size = isz.data(); }
+         else { in.close_info = ci.data(); if (!regions.empty()) { in.regions = regions.data(); in.region_off = region_off.data(); } }
+         out.resize(n ? n : 1);
+         runs.resize(n * 8 + 1024);
+      }
+   };
+
+   void run(int (*fn)(pg_ctx *, const pg_reads *, pg_results *), Batch &b, const char *what)
+   {
+      pg_results res;
+      res.out = b.out.data(); res.runs = b.runs.data(); res.runs_cap = (uint32_t)b.runs.size(); res.n_runs = 0;
+      int rc = fn(ctx_, &b.in, &res);
+      if (rc == PG_ERR_RUNS_CAP) {
+         b.runs.resize(res.n_runs);
+         res.runs = b.runs.data(); res.runs_cap = (uint32_t)b.runs.size();
+         rc = fn(ctx_, &b.in, &res);
+      }
+      check(rc, what);
+      for (int i = 0; i < b.in.n; i++)
+         if (b.out[i].flags & PG_READ_UNSUPPORTED) throw std::runtime_error(std::string(what) + ": read not supported by the library");
+   }
+
+   static void append(SortedUniquePoints &dst, const pg_run *runs, unsigned n)
+   {
+      for (unsigned r = 0; r < n; r++)
+         for (unsigned j = 0; j < runs[r].count; j++) {
+            UniquePoint u;
+            u.chromosome_id = runs[r].chr;
+            u.LengthStr = (short)(runs[r].len0 + j);
+            u.AbsLoc = (runs[r].dirstrand & 1u) ? runs[r].abs_loc0 - j : runs[r].abs_loc0 + j;
+            u.Direction = (runs[r].dirstrand & 1u) ? BACKWARD : FORWARD;
+            u.Strand = (runs[r].dirstrand & 2u) ? ANTISENSE : SENSE;
+            u.Mismatches = (short)runs[r].mm;
+            dst.push_back(u);
+         }
+   }
+
+   void check(int rc, const char *what)
+   {
+      if (rc != PG_OK) throw std::runtime_error(std::string(what) + ": " + pg_last_error(ctx_));
+   }
+
+   pg_ctx *ctx_;
+   Searcher(const Searcher &);
+   Searcher &operator=(const Searcher &);
+};
+
+} // namespace pindel_pg
+#endif
