@@ -290,19 +290,25 @@ PG_DEV void pg_scan_window(PgWarpCtx<LW, TL> &cx, const PgSearch &se, int chr_id
       uint32_t ka_[TL], kb_[TL];     // lane-local top-2 keys of this tile, one pair per level
 #pragma unroll
       for (int t = 0; t < TL; t++) { ka_[t] = 0; kb_[t] = 0; }
-      for (uint32_t cs = ts & ~31u; cs < te; cs += PG_CHUNK_POS) {
+      // positions per lane in the seed-list phase: 32 (one word) for long tiles, 16 or 8 for the short windows that
+      // dominate (close windows, inner far windows), so that all 32 lanes share the list building
+      const uint32_t tlen = te - (ts & ~31u);
+      const uint32_t gran = tlen <= 256u ? 8u : (tlen <= 512u ? 16u : 32u);
+      const uint32_t gmask = gran == 32u ? ~0u : ((1u << gran) - 1u);
+      for (uint32_t cs = ts & ~31u; cs < te; cs += 32u * gran) {
          // ---- (1) seed list of this chunk ----
          uint32_t plus = 0, minus = 0;
+         const uint32_t p0 = cs + gran * (uint32_t)lane;         // first position owned by this lane
          {
-            uint32_t wpos = cs + 32u * (uint32_t)lane;            // first position of this lane's word
-            if (wpos < te) {
-               int wi = (int)((int64_t)(wpos >> 5) - w0);
+            if (p0 < te) {
+               int wi = (int)((int64_t)(p0 >> 5) - w0);
+               uint32_t sub = p0 & 31u;
                uint2 W = ws->tile[wi];
-               uint32_t notn = ~ws->tile_n[wi];
-               uint32_t inr = ~0u;                                 // positions of the word inside [ts, te)
-               if (wpos < ts) inr &= ~0u << (ts - wpos);
-               if (te - wpos < 32u) inr &= (1u << (te - wpos)) - 1u;
-               uint32_t dl = W.x ^ c0lom, dh = W.y ^ c0him;       // 0 bits where the base equals read[0]
+               uint32_t notn = ~ws->tile_n[wi] >> sub;
+               uint32_t inr = gmask;                              // owned positions inside [ts, te)
+               if (p0 < ts) inr &= (ts - p0 >= 32u) ? 0u : (~0u << (ts - p0));
+               if (te - p0 < gran) inr &= (1u << (te - p0)) - 1u;
+               uint32_t dl = (W.x ^ c0lom) >> sub, dh = (W.y ^ c0him) >> sub;   // 0 bits where the base equals read[0]
                plus = ~(dl | dh) & notn & inr;
                if (far) minus = (dl & dh) & notn & inr;          // both planes differ: the complement of read[0]
                else if (!single_fwd) { minus = plus; plus = 0; } // close end growing left: every seed is a "minus" seed
@@ -321,7 +327,7 @@ PG_DEV void pg_scan_window(PgWarpCtx<LW, TL> &cx, const PgSearch &se, int chr_id
          {
             uint32_t o = incl - cnt;
             uint32_t both = plus | minus;
-            uint32_t rel = cs + 32u * (uint32_t)lane - origin;
+            uint32_t rel = p0 - origin;
             while (both) {
                uint32_t bit = (uint32_t)pg_ffs(both) - 1u;
                both &= both - 1u;
