@@ -81,7 +81,6 @@ struct PgWarpSmem {
    // per-level results of the current job
    uint32_t A[TL + 1], B[TL + 1], P[TL + 1], META[TL + 1], H[TL + 1], ALIAS[TL + 1];
    uint32_t queue[PG_QCAP];
-   uint32_t save[4][32];             // parked warp-level state of GetCloseEnd's first attempt (level == lane)
    uint16_t seedq[PG_CHUNK_POS];     // seeds of the current chunk: offset from the tile origin | strand << 15
 };
 
@@ -684,9 +683,6 @@ PG_DEV void pg_process_read(PgWarpCtx<LW, TL> &cx, const PgBatch &bt, int ri, Pg
    uint32_t span = 64;         // START_SEARCH_SPAN
    bool have_prev_window = false;
    uint32_t prev_ws = 0, prev_we = 0;
-   bool r0_valid = false;      // GetCloseEnd: window and read lengths of the RangeIndex 0 attempts
-   uint32_t r0_s = 0, r0_e = 0, r0_seeds_a = 0;
-   int r0_len_a = -1, r0_len_b = -2;
    if (bt.mode & 1) {
       st = ST_CLOSE;
    } else if ((bt.mode & 2) && bt.close_info) {
@@ -726,27 +722,6 @@ PG_DEV void pg_process_read(PgWarpCtx<LW, TL> &cx, const PgBatch &bt, int ri, Pg
          if (end > 0xffffffffll) end = 0xffffffffll;
          one.chr = chr_id; one.start = (uint32_t)start; one.end = (uint32_t)(end > start ? end : start);
          skip = !(md == '+' || md == '-') || L <= 0;
-         alg_bases = (unsigned long long)(one.end - one.start);
-         // RangeIndex 1 searches [anchor -/+ IS, ...) which contains the RangeIndex 0 window.  Its first attempt uses the
-         // orientation of the attempt just made (state still in cx.lvl); its second attempt uses the orientation of the very
-         // first attempt (state parked in shared memory).  Either way only the two rings around the old window are new --
-         // provided the read is still the same string (a flip can strip IUPAC characters, pindel.cpp:142-169).
-         if (range_index == 1 && !skip && r0_valid && one.start <= r0_s && one.end >= r0_e && r0_e >= r0_s) {
-            bool usable = false;
-            if (!second_try) usable = (L == r0_len_b);
-            else if (L == r0_len_a) {
-               usable = true;
-               if (lane < TL) { cx.lvl.A = ws->save[0][lane]; cx.lvl.B = ws->save[1][lane]; cx.lvl.pos = ws->save[2][lane]; cx.lvl.meta = ws->save[3][lane]; }
-               cx.any_seed = r0_seeds_a;
-            }
-            if (usable) {
-               keep_state = true;
-               two[0].chr = chr_id; two[0].start = one.start; two[0].end = r0_s;
-               two[1].chr = chr_id; two[1].start = r0_e; two[1].end = (uint32_t)(end > start ? end : start);
-               nreg = 2;
-            }
-         }
-         if (range_index == 0) { r0_valid = !skip; r0_s = one.start; r0_e = one.end; }
       } else {
          // SearchFarEndAtPos, farend_searcher.cpp:46-103
          se.far = true; se.bp_start = PG_FAR_BP_START; se.chp.arr = 0; se.chp.inv = 0u; se.d = 1;
@@ -784,10 +759,10 @@ PG_DEV void pg_process_read(PgWarpCtx<LW, TL> &cx, const PgBatch &bt, int ri, Pg
             }
             if (e > s) {
                pg_scan_window<LW, TL>(cx, se, rg.chr, s, e, phase);
-               if (st == ST_FAR_CLUSTER) window_bases += (unsigned long long)(e - s);
+               if (st != ST_FAR_WINDOW) window_bases += (unsigned long long)(e - s);
             }
          }
-         window_bases += alg_bases;      // nested windows are accounted at the size the reference scans, rings or not
+         window_bases += alg_bases;      // far windows are accounted at the size the reference scans, rings or not
       }
       PgResult res = pg_walk_emit<LW, TL>(cx, se, dst, cap);
       // ---- decide what comes next ----
@@ -796,15 +771,10 @@ PG_DEV void pg_process_read(PgWarpCtx<LW, TL> &cx, const PgBatch &bt, int ri, Pg
          if (res.n_ups) {
             st = ((bt.mode & 2) && L > 0) ? (n_regions ? ST_FAR_CLUSTER : ST_FAR_WINDOW) : ST_DONE;
          } else if (!second_try) {
-            if (range_index == 0) {                  // park the first orientation's state for RangeIndex 1's second attempt
-               if (lane < TL) { ws->save[0][lane] = cx.lvl.A; ws->save[1][lane] = cx.lvl.B; ws->save[2][lane] = cx.lvl.pos; ws->save[3][lane] = cx.lvl.meta; }
-               r0_len_a = L; r0_seeds_a = cx.any_seed;
-            }
             L = pg_flip_read<LW, TL>(ws, L);         // Temp_One_Read.setUnmatchedSeq(ReverseComplement(..)), pindel.cpp:2545
             flips++;
             second_try = true;
          } else {
-            if (range_index == 0) r0_len_b = L;
             second_try = false;
             if (++range_index >= 2) st = ST_DONE;    // MaxRange = 2
          }
