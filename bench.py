@@ -195,8 +195,27 @@ def cpu_baseline_reference(ref_np, seq_np, md_np, pos_np, isz_np, target_seconds
 
 
 # ---------------------------------------------------------------------------------------------------------------
+_REAL_STDOUT = None
+
+
+def claim_stdout():
+    """Only the result line may reach stdout: libraries print there too (NCCL's version banner, the reference's progress
+    messages), so fd 1 is pointed at stderr for the whole run and the JSON line is written to the saved descriptor."""
+    global _REAL_STDOUT
+    if _REAL_STDOUT is None:
+        sys.stdout.flush()
+        _REAL_STDOUT = os.dup(1)
+        os.dup2(2, 1)
+
+
+def emit(result):
+    sys.stdout.flush()
+    os.write(_REAL_STDOUT if _REAL_STDOUT is not None else 1, (json.dumps(result) + "\n").encode())
+
+
 def main():
     a = parse_args()
+    claim_stdout()
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -269,14 +288,14 @@ def main():
         gather_records()
 
     def step_e2e():
-        if world == 1:
-            # the call a user makes: host buffers in, host buffers out (large batches are chunked and the copies
-            # overlap the kernel inside the library)
-            return pg.search(out=out_h, runs=runs_h, **batch)
-        pg.upload(**batch)
-        pg.launch(3)
-        gather_records()
-        return pg.download(out=out_h, runs=runs_h)
+        # the call a user makes: host buffers in, host buffers out (large batches are chunked and the copies overlap
+        # the kernel inside the library); with several GPUs the records then go to rank 0 in one NCCL gather
+        out_e, runs_e = pg.search(out=out_h, runs=runs_h, **batch)
+        if world > 1:
+            out_d = torch.from_numpy(out_e.view(np.uint8)).to(dev, non_blocking=True)
+            runs_d = torch.from_numpy(runs_e.view(np.uint8)).to(dev, non_blocking=True)
+            shard.gather_records(out_d, runs_d, dst=0)
+        return out_e, runs_e
 
     def barrier():
         if world > 1:
@@ -369,7 +388,7 @@ def main():
         except Exception as e:  # the baseline is reported, never required for the GPU numbers
             result["cpu_baseline"] = {"value": None, "unit": "reads/s", "cores": os.cpu_count(), "kind": "unavailable", "sample": repr(e)}
     if rank == 0:
-        print(json.dumps(result), flush=True)
+        emit(result)
     pg.close()
     if world > 1:
         dist.barrier()
@@ -429,7 +448,7 @@ def reference_arm(a, rank, world, log):
         "cpu_baseline": {"value": value, "unit": "reads/s", "cores": cores, "kind": kind, "sample": sample},
         "e2e": {"value": value, "unit": "reads/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
-    print(json.dumps(result), flush=True)
+    emit(result)
 
 
 if __name__ == "__main__":
