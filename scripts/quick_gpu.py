@@ -10,7 +10,8 @@ mbp = int(sys.argv[3]) if len(sys.argv) > 3 else 10
 ref = synth.make_reference(mbp * 1_000_000, 20260926)
 padded = synth.pad_reference(ref)
 t = time.time(); batch = synth.make_reads(ref, n, L, seed=5); print("gen %.2fs" % (time.time() - t))
-pg = api.PatternGrowth()
+import os
+pg = api.PatternGrowth(max_range_index=int(os.environ.get('PG_X', '2')))
 t = time.time(); pg.set_reference([padded]); print("set_reference %.3fs" % (time.time() - t))
 blob, off = batch.blob()
 kw = dict(seq_blob=blob, seq_off=off, matched_d=batch.matched_d, matched_rel_pos=batch.matched_rel_pos, insert_size=batch.insert_size)
