@@ -16,3 +16,13 @@ def pytest_configure(config):
 def oracle_lib():
     from oracle import pgoracle
     return pgoracle.load()
+
+
+@pytest.fixture(scope="session", autouse=True)
+def native_artefacts():
+    """The suite needs the in-tree native builds (the product library for the ABI tests, the oracle port, the emulator);
+    build whatever is missing or stale once per session -- the same thing __graft_entry__.build() does."""
+    from pindel_b200 import build as B
+    B.build_cuda()
+    B.build_oracle()
+    yield
