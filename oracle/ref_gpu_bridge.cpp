@@ -12,16 +12,17 @@
  * dynamic linker binds every call the reference makes to these two names (reader.cpp:254,304, read_buffer.cpp:47,
  * pindel.cpp:1888) to the definitions below.  No reference source is patched or copied.
  *
- * GetCloseEnd is called once per read from inside the reference's own text-input loop (reader.cpp:248-256,300-306), so
- * for Pindel-text input this shim issues one-read batches (slow, but the caller stays untouched).  For BAM input the
- * reference funnels reads through ReadBuffer::flush (read_buffer.cpp:36-101), a public member function, so the bridge
- * supplies that too -- as the batched binding INTEGRATION.md describes: one pg_close_end call per flush of up to
- * 50 000 reads.  SearchFarEnds is a true batch call in both modes.
+ * Besides the two seam functions the bridge supplies the two places where the reference *batches* reads before calling
+ * GetCloseEnd -- ReadBuffer::flush for BAM input (read_buffer.cpp:36-101) and ReadInRead for Pindel-text input
+ * (reader.cpp:196-361), both reachable by symbol -- as the batched binding INTEGRATION.md describes: one pg_close_end
+ * call per batch.  The per-read GetCloseEnd below remains for any other caller; SearchFarEnds is a batch call anyway.
+ * Set PG_BRIDGE_UNBATCHED=1 to make the text path go through the per-read shim instead (the reference's own ReadInRead).
  */
 #include "pindel.h"
 #include "bddata.h"
 #include "read_buffer.h"
 #include "reader.h"
+#include "pindel_read_reader.h"
 #include "logstream.h"
 #include "user_defined_settings.h"
 
@@ -91,6 +92,121 @@ void appendRuns(SortedUniquePoints &dst, const pg_run *runs, unsigned n)
 }
 } // namespace
 
+/* pg_close_end over reads[idx[0..m)], results applied the way GetCloseEnd leaves a SPLIT_READ. */
+static void closeEndBatch(std::vector<SPLIT_READ> &reads, const std::vector<int> &idx)
+{
+   const int m = (int)idx.size();
+   if (m == 0) return;
+   std::string blob;
+   std::vector<uint32_t> off(m + 1, 0), pos(m);
+   std::vector<char> md(m);
+   std::vector<int16_t> isz(m);
+   std::vector<int32_t> chr(m);
+   for (int k = 0; k < m; k++) {
+      const SPLIT_READ &r = reads[idx[k]];
+      blob += r.getUnmatchedSeq();
+      off[k + 1] = (uint32_t)blob.size();
+      md[k] = r.MatchedD; pos[k] = r.MatchedRelPos; isz[k] = r.InsertSize; chr[k] = g_genome.getChrID(r.FragName);
+      if (r.InsertSize > g_maxInsertSize) g_maxInsertSize = r.InsertSize;     /* side effect of GetCloseEndInner, src/pindel.cpp:2257 */
+   }
+   pg_reads in;
+   memset(&in, 0, sizeof(in));
+   in.n = m; in.seq_blob = blob.c_str(); in.seq_off = &off[0]; in.matched_d = &md[0]; in.matched_rel_pos = &pos[0];
+   in.insert_size = &isz[0]; in.chr_id = &chr[0];
+   std::vector<pg_read_out> out(m);
+   std::vector<pg_run> runs((size_t)m * 16 + 1024);
+   pg_results res;
+   res.out = &out[0]; res.runs = &runs[0]; res.runs_cap = (uint32_t)runs.size(); res.n_runs = 0;
+   int rc = pg_close_end(g_ctx, &in, &res);
+   if (rc == PG_ERR_RUNS_CAP) {
+      runs.resize(res.n_runs);
+      res.runs = &runs[0]; res.runs_cap = (uint32_t)runs.size();
+      rc = pg_close_end(g_ctx, &in, &res);
+   }
+   if (rc != PG_OK) die("pg_close_end (batch)");
+   for (int k = 0; k < m; k++) {
+      SPLIT_READ &read = reads[idx[k]];
+      if (out[k].flags & PG_READ_UNSUPPORTED) die("read not supported by the library");
+      for (unsigned f = 0; f < PG_READ_NFLIPS(out[k].flags); f++)
+         read.setUnmatchedSeq(ReverseComplement(read.getUnmatchedSeq()));
+      read.UP_Close.clear();
+      appendRuns(read.UP_Close, &runs[out[k].run_off], out[k].n_close_runs);
+      if (!read.UP_Close.empty()) read.Used = false;
+   }
+   g_close_calls += (unsigned long)m;
+}
+
+/* ReadInRead, batched (replaces reader.cpp:196-361 by symbol): scan the Pindel-text file, keep the reads anchored in
+ * the window, search their close ends in ONE batch instead of 1000-read OpenMP batches, then post-process them in file
+ * order exactly as the reference does (reader.cpp:258-293 / 307-338). */
+extern unsigned int g_NumReadInWindow, g_NumReadScanned, g_InWinPlus, g_InWinMinus, g_CloseMappedPlus, g_CloseMappedMinus;
+short ReadInRead(PindelReadReader &inf_ReadSeq, const std::string &FragName, const std::string &CurrentChr,
+                 std::vector<SPLIT_READ> &Reads, const SearchWindow &currentWindow)
+{
+   *logStream << "Scanning and processing reads anchored in " << FragName << std::endl;
+   std::vector<SPLIT_READ> BufferReads;
+   SPLIT_READ Temp_One_Read;
+   inf_ReadSeq.Reset();
+   while (inf_ReadSeq.HasNext()) {
+      Temp_One_Read = inf_ReadSeq.NextRead();
+      if (Temp_One_Read.Name[0] != FirstCharReadName) {
+         *logStream << "Something wrong with the read name: " << Temp_One_Read.Name << std::endl;
+         Reads.clear();
+         return EXIT_FAILURE;
+      }
+      g_NumReadScanned++;
+      if (Temp_One_Read.MatchedD != Minus && Temp_One_Read.MatchedD != Plus) {
+         *logStream << Temp_One_Read.Name << std::endl << Temp_One_Read.getUnmatchedSeq() << std::endl << Temp_One_Read.MatchedD << " ..." << std::endl << "+/-" << std::endl;
+         return EXIT_FAILURE;
+      }
+      if (Temp_One_Read.MatchedRelPos > g_maxPos) g_maxPos = Temp_One_Read.MatchedRelPos;
+      if (Temp_One_Read.FragName == FragName && Temp_One_Read.MatchedRelPos >= currentWindow.getStart() &&
+          Temp_One_Read.MatchedRelPos < currentWindow.getEnd()) {
+         g_NumReadInWindow++;
+         if (Temp_One_Read.MatchedD == Plus) g_InWinPlus++; else g_InWinMinus++;
+         if (Temp_One_Read.MatchedRelPos > currentWindow.getChromosome()->getBiolSize())
+            Temp_One_Read.MatchedRelPos = currentWindow.getChromosome()->getBiolSize();
+         BufferReads.push_back(Temp_One_Read);
+      }
+   }
+   if (std::getenv("PG_BRIDGE_UNBATCHED")) {
+      for (size_t i = 0; i < BufferReads.size(); i++) GetCloseEnd(CurrentChr, BufferReads[i]);   /* one-read batches */
+   } else {
+      std::lock_guard<std::mutex> lock(g_mutex);
+      ensureContext();
+      std::vector<int> idx(BufferReads.size());
+      for (size_t i = 0; i < idx.size(); i++) idx[i] = (int)i;
+      closeEndBatch(BufferReads, idx);
+   }
+   int UPCLOSE_COUNTER = 0;
+   for (size_t i = 0; i < BufferReads.size(); i++) {
+      SPLIT_READ &currentRead = BufferReads[i];
+      if (currentRead.UP_Close.size()) {
+         UPCLOSE_COUNTER++;
+         if (g_reportLength < currentRead.getReadLength()) g_reportLength = currentRead.getReadLength();
+         currentRead.Used = false;
+         currentRead.UniqueRead = true;
+         CleanUniquePoints(currentRead.UP_Close);
+         currentRead.CloseEndLength = currentRead.UP_Close[currentRead.UP_Close.size() - 1].LengthStr;
+         if (currentRead.MatchedD == Plus)
+            currentRead.LeftMostPos = currentRead.UP_Close[currentRead.UP_Close.size() - 1].AbsLoc + 1 - currentRead.CloseEndLength;
+         else
+            currentRead.LeftMostPos = currentRead.UP_Close[currentRead.UP_Close.size() - 1].AbsLoc + currentRead.CloseEndLength - currentRead.getReadLength();
+         currentRead.SampleName2Number.insert(std::pair<std::string, unsigned>(currentRead.Tag, 1));
+         Reads.push_back(currentRead);
+         if (currentRead.MatchedD == Plus) g_CloseMappedPlus++; else g_CloseMappedMinus++;
+         g_sampleNames.insert(currentRead.Tag);
+      }
+   }
+   *logStream << "last one: " << BufferReads.size() << " and UPCLOSE= " << UPCLOSE_COUNTER << std::endl;
+   if (FirstChr) FirstChr = false;
+   *logStream << "Number of problematic reads in current window:            \t" << g_NumReadInWindow << ", + " << g_InWinPlus << " - " << g_InWinMinus << std::endl;
+   *logStream << "Number of split-reads where the close end could be mapped:\t" << Reads.size() << ", + " << g_CloseMappedPlus << " - " << g_CloseMappedMinus << std::endl;
+   if (Reads.size() == 0) return 0;
+   *logStream << " finished!" << std::endl;
+   return 0;
+}
+
 void GetCloseEnd(const std::string &CurrentChrSeq, SPLIT_READ &read)
 {
    (void)CurrentChrSeq;
@@ -129,51 +245,9 @@ void ReadBuffer::flush()
    {
       std::lock_guard<std::mutex> lock(g_mutex);
       ensureContext();
-      const int n = m_currentsize;
-      std::string blob;
-      std::vector<uint32_t> off(n + 1, 0), pos(n);
-      std::vector<char> md(n);
-      std::vector<int16_t> isz(n);
-      std::vector<int32_t> chr(n);
-      std::vector<int> idx;                  /* reads that take part (MapperSplit == false) */
-      for (int i = 0; i < n; i++) {
-         if (m_rawreads[i].MapperSplit) continue;
-         const SPLIT_READ &r = m_rawreads[i];
-         int k = (int)idx.size();
-         blob += r.getUnmatchedSeq();
-         off[k + 1] = (uint32_t)blob.size();
-         md[k] = r.MatchedD; pos[k] = r.MatchedRelPos; isz[k] = r.InsertSize; chr[k] = g_genome.getChrID(r.FragName);
-         if (r.InsertSize > g_maxInsertSize) g_maxInsertSize = r.InsertSize;
-         idx.push_back(i);
-      }
-      const int m = (int)idx.size();
-      if (m > 0) {
-         pg_reads in;
-         memset(&in, 0, sizeof(in));
-         in.n = m; in.seq_blob = blob.c_str(); in.seq_off = &off[0]; in.matched_d = &md[0]; in.matched_rel_pos = &pos[0];
-         in.insert_size = &isz[0]; in.chr_id = &chr[0];
-         std::vector<pg_read_out> out(m);
-         std::vector<pg_run> runs((size_t)m * 16 + 1024);
-         pg_results res;
-         res.out = &out[0]; res.runs = &runs[0]; res.runs_cap = (uint32_t)runs.size(); res.n_runs = 0;
-         int rc = pg_close_end(g_ctx, &in, &res);
-         if (rc == PG_ERR_RUNS_CAP) {
-            runs.resize(res.n_runs);
-            res.runs = &runs[0]; res.runs_cap = (uint32_t)runs.size();
-            rc = pg_download(g_ctx, &res);
-         }
-         if (rc != PG_OK) die("pg_close_end (ReadBuffer::flush)");
-         for (int k = 0; k < m; k++) {
-            SPLIT_READ &read = m_rawreads[idx[k]];
-            if (out[k].flags & PG_READ_UNSUPPORTED) die("read not supported by the library");
-            for (unsigned f = 0; f < PG_READ_NFLIPS(out[k].flags); f++)
-               read.setUnmatchedSeq(ReverseComplement(read.getUnmatchedSeq()));
-            read.UP_Close.clear();
-            appendRuns(read.UP_Close, &runs[out[k].run_off], out[k].n_close_runs);
-            if (!read.UP_Close.empty()) read.Used = false;
-         }
-         g_close_calls += (unsigned long)m;
-      }
+      std::vector<int> idx;                  /* reads that take part (MapperSplit == false, read_buffer.cpp:46) */
+      for (int i = 0; i < m_currentsize; i++) if (!m_rawreads[i].MapperSplit) idx.push_back(i);
+      closeEndBatch(m_rawreads, idx);
    }
    for (int i = 0; i < m_currentsize; i++) {
       if (m_rawreads[i].hasCloseEnd()) {

@@ -34,6 +34,15 @@ def test_reference_host_with_gpu_search_writes_identical_files(tmp_path):
         got = (tmp_path / ("colo_slice.out_" + suf)).read_bytes()
         exp = gzip.open(os.path.join(GOLD, "colo_slice.out_%s.gz" % suf)).read()
         assert got == exp, "_%s differs from the reference's file (%d vs %d bytes)" % (suf, len(got), len(exp))
+    # the same through the per-read GetCloseEnd shim (one-read batches): the seam function itself, unbatched
+    env2 = dict(env, PG_BRIDGE_UNBATCHED="1")
+    p2 = subprocess.run([DEMO, "-f", str(fa), "-p", str(rd), "-o", str(tmp_path / "unbatched.out"), "-k", "-s", "-l", "-T", "1"],
+                        capture_output=True, text=True, timeout=1200, env=env2)
+    assert p2.returncode == 0, p2.stdout[-2000:] + p2.stderr[-2000:]
+    for suf in ("D", "SI", "INV", "TD"):
+        got = (tmp_path / ("unbatched.out_" + suf)).read_bytes()
+        exp = gzip.open(os.path.join(GOLD, "colo_slice.out_%s.gz" % suf)).read()
+        assert got == exp, "unbatched _%s differs" % suf
 
 
 @pytest.mark.skipif(not os.path.exists(DEMO), reason="oracle/_ref/pindel_gpu_demo not built (needs /root/reference at build time)")
