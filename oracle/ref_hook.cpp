@@ -10,6 +10,12 @@
  *
  * and read back every UniquePoint they produce.  Nothing here restates the algorithm; it only
  * marshals plain C arrays into SPLIT_READ objects and back.
+ *
+ * pgref_classify does the same for the seven SV drivers SearchSVs runs (src/pindel.cpp:1140-1164).  What a driver hands
+ * to the reporter (its Vars[box] lists) is captured instead of reported: SearchDeletions / SearchShortInsertions through
+ * their virtual outputResults, the five free-function drivers through the SortOutput* definitions below, which take
+ * precedence over reporter.o's inside this one library (oracle/Makefile links it with --allow-multiple-definition,
+ * ref_hook.o first).  libpindel_refcore.so and pindel_ref keep the reference's reporter.
  */
 #include "pindel.h"
 #include "control_state.h"
@@ -18,6 +24,15 @@
 #include "searcher.h"
 #include "user_defined_settings.h"
 #include "logstream.h"
+#include "reporter.h"
+#include "search_variant.h"
+#include "searchdeletions.h"
+#include "searchshortinsertions.h"
+#include "search_deletions_nt.h"
+#include "search_tandem_duplications.h"
+#include "search_tandem_duplications_nt.h"
+#include "search_inversions.h"
+#include "search_inversions_nt.h"
 
 #include <chrono>
 #include <cstdint>
@@ -54,7 +69,86 @@ void pushUP(std::vector<int32_t> &out, const UniquePoint &up)
    out.push_back(up.Mismatches);
    out.push_back(chrIdOf(up.chromosome_p));
 }
+
+// ---- capture of the drivers' box lists ----
+std::vector<int32_t> *g_varsSink = NULL;
+int g_varsCount = 0;
+void captureVars(std::vector<unsigned> Vars[], unsigned NumBoxes)
+{
+   if (g_varsSink == NULL) return;
+   for (unsigned b = 0; b < NumBoxes; b++) {
+      for (size_t k = 0; k < Vars[b].size(); k++) {
+         g_varsSink->push_back((int32_t)b);
+         g_varsSink->push_back((int32_t)Vars[b][k]);
+         g_varsCount++;
+      }
+   }
+}
+class CaptureDeletions : public SearchDeletions
+{
+protected:
+   void outputResults(BDData &, ControlState &, std::vector<unsigned> Vars[], const unsigned NumBoxes, const SearchWindow &)
+   {
+      captureVars(Vars, NumBoxes);
+   }
+};
+class CaptureShortInsertions : public SearchShortInsertions
+{
+protected:
+   void outputResults(BDData &, ControlState &, std::vector<unsigned> Vars[], const unsigned NumBoxes, const SearchWindow &)
+   {
+      captureVars(Vars, NumBoxes);
+   }
+};
+
+uint32_t fnv1a(const std::string &s)
+{
+   uint32_t h = 2166136261u;
+   for (size_t i = 0; i < s.size(); i++) h = (h ^ (uint8_t)s[i]) * 16777619u;
+   return h;
+}
+void putState(std::vector<int32_t> &out, const SPLIT_READ &r)
+{
+   uint32_t head = 0, tail = 0;
+   const std::string &s = r.NT_str;
+   for (size_t i = 0; i < 4 && i < s.size(); i++) head |= (uint32_t)(uint8_t)s[i] << (8 * i);
+   for (size_t i = 0; i < 4 && i < s.size(); i++) tail |= (uint32_t)(uint8_t)s[s.size() - 1 - i] << (8 * i);
+   out.push_back(r.Left);
+   out.push_back(r.Right);
+   out.push_back(r.BP);
+   out.push_back((int32_t)r.BPLeft);
+   out.push_back((int32_t)r.BPRight);
+   out.push_back((int32_t)r.IndelSize);
+   out.push_back(r.NT_size);
+   out.push_back(r.Used ? 1 : 0);
+   out.push_back((int32_t)s.size());
+   out.push_back((int32_t)fnv1a(s));
+   out.push_back((int32_t)head);
+   out.push_back((int32_t)tail);
+}
 } // namespace
+
+// Definitions that shadow reporter.o's inside libpindel_ref.so only (see the header comment).
+void SortOutputDI(ControlState &, const unsigned &NumBoxes, const std::string &, std::vector<SPLIT_READ> &, std::vector<unsigned> DI[],
+                  std::ofstream &, std::ofstream &)
+{
+   captureVars(DI, NumBoxes);
+}
+void SortAndOutputTandemDuplications(ControlState &, const unsigned &NumBoxes, const std::string &, std::vector<SPLIT_READ> &,
+                                     std::vector<unsigned> TDs[], std::ofstream &, const bool)
+{
+   captureVars(TDs, NumBoxes);
+}
+void SortOutputInv(ControlState &, const unsigned &NumBoxes, const std::string &, std::vector<SPLIT_READ> &, std::vector<unsigned> Inv[],
+                   std::ofstream &)
+{
+   captureVars(Inv, NumBoxes);
+}
+void SortOutputInv_NT(ControlState &, const unsigned &NumBoxes, const std::string &, std::vector<SPLIT_READ> &,
+                      std::vector<unsigned> Inv[], std::ofstream &)
+{
+   captureVars(Inv, NumBoxes);
+}
 
 extern "C" {
 
@@ -94,6 +188,8 @@ int pgref_setting_int(const char *which)
    if (w == "MaxRangeIndex") return userSettings->MaxRangeIndex;
    if (w == "minClose") return userSettings->minClose;
    if (w == "numThreads") return userSettings->numThreads;
+   if (w == "MIN_IndelSize_Inversion") return userSettings->MIN_IndelSize_Inversion;
+   if (w == "Min_Num_Matched_Bases") return userSettings->Min_Num_Matched_Bases;
    return -1;
 }
 double pgref_setting_double(const char *which)
@@ -224,6 +320,81 @@ int64_t pgref_search(int n, const char *seq_blob, const uint32_t *seq_off, const
          k++;
       }
    }
+   int32_t *buf = (int32_t *)malloc(out.size() * sizeof(int32_t) + 4);
+   memcpy(buf, out.data(), out.size() * sizeof(int32_t));
+   *out_stream = buf;
+   return (int64_t)out.size();
+}
+
+/* Runs the reference's SV drivers (the ones in driver_mask, bit = position in SearchSVs' order: D, DI, TD, TD_NT, INV,
+ * INV_NT, SI; src/pindel.cpp:1140-1164) over n reads of one window on chromosome chr.
+ * up: [k,5] int32 rows (len, absLoc, dir 0/1, strand 0/1, mm); a read's first n_close[i] rows are UP_Close, the rest UP_Far.
+ * region_mode 1: userSettings' region becomes [region_start, region_end] (stays so for the rest of the process).
+ * Output stream: see svo_classify in oracle/sv_oracle.c (same format).  seconds[d] = wall time of driver d. */
+int64_t pgref_classify(int n, const char *seq_blob, const uint32_t *seq_off, const char *matched_d, const int16_t *insert_size,
+                       const uint8_t *rflags, const int32_t *up, const uint32_t *up_off, const uint32_t *n_close, int chr,
+                       uint32_t win_start, uint32_t win_end, uint32_t num_boxes, uint32_t box_size, uint32_t driver_mask,
+                       int region_mode, uint32_t region_start, uint32_t region_end, int32_t **out_stream, double *seconds)
+{
+   const Chromosome *c = g_genome.getChr((unsigned)chr);
+   if (c == NULL) return -1;
+   ControlState cs;
+   cs.Reads_SR.resize((size_t)n);
+   for (int i = 0; i < n; i++) {
+      SPLIT_READ &r = cs.Reads_SR[i];
+      r.Name = "@" + std::to_string(i);
+      r.FragName = c->getName();
+      r.setUnmatchedSeq(std::string(seq_blob + seq_off[i], seq_off[i + 1] - seq_off[i]));
+      r.MatchedD = matched_d[i];
+      r.MS = 60;
+      r.InsertSize = insert_size[i];
+      r.Tag = "S";
+      r.Used = (rflags[i] & 1) != 0;
+      const uint32_t a = up_off[i], b = up_off[i + 1];
+      for (uint32_t k = a; k < b; k++) {
+         UniquePoint p(c, (short)up[5 * k], (unsigned)up[5 * k + 1], up[5 * k + 2] ? BACKWARD : FORWARD,
+                       up[5 * k + 3] ? ANTISENSE : SENSE, (short)up[5 * k + 4]);
+         if (k - a < n_close[i]) r.UP_Close.push_back(p);
+         else r.UP_Far.push_back(p);
+      }
+      r.FarFragName = (rflags[i] & 2) ? std::string("@other") : (r.UP_Far.empty() ? std::string("") : r.FragName);
+   }
+   if (region_mode == 1) const_cast<SearchRegion *>(userSettings->getRegion())->SetRegion(c->getName(), region_start, region_end);
+   BoxSize = box_size;
+   SearchWindow window(c, win_start, win_end);
+   std::vector<int32_t> out;
+   std::ostream *savedLog = logStream;
+   for (int d = 0; d < 7; d++) {
+      if (seconds) seconds[d] = 0.0;
+      if (!((driver_mask >> d) & 1)) continue;
+      std::vector<int32_t> vars;
+      g_varsSink = &vars;
+      g_varsCount = 0;
+      const size_t futureBefore = cs.FutureReads_SR.size();
+      std::chrono::steady_clock::time_point t0 = std::chrono::steady_clock::now();
+      switch (d) {
+      case 0: { CaptureDeletions s; s.Search(g_bdData, cs, num_boxes, window); break; }
+      case 1: searchIndels(cs, num_boxes, window); break;
+      case 2: searchTandemDuplications(cs, num_boxes, window); break;
+      case 3: searchTandemDuplicationsNT(cs, num_boxes, window); break;
+      case 4: searchInversions(cs, num_boxes, window); break;
+      case 5: searchInversionsNT(cs, num_boxes, window); break;
+      case 6: { CaptureShortInsertions s; s.Search(g_bdData, cs, num_boxes, window); break; }
+      }
+      if (seconds) seconds[d] = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+      g_varsSink = NULL;
+      out.push_back(d);
+      out.push_back(g_varsCount);
+      out.push_back((int32_t)(cs.FutureReads_SR.size() - futureBefore));
+      out.insert(out.end(), vars.begin(), vars.end());
+      for (size_t k = futureBefore; k < cs.FutureReads_SR.size(); k++) { // a saved read is a copy; its Name carries the index
+         const SPLIT_READ &f = cs.FutureReads_SR[k];
+         out.push_back((int32_t)atoi(f.Name.c_str() + 1));
+         putState(out, f);
+      }
+      for (int i = 0; i < n; i++) putState(out, cs.Reads_SR[i]);
+   }
+   logStream = savedLog;
    int32_t *buf = (int32_t *)malloc(out.size() * sizeof(int32_t) + 4);
    memcpy(buf, out.data(), out.size() * sizeof(int32_t));
    *out_stream = buf;

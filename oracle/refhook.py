@@ -50,6 +50,7 @@ class RefHook:
         L.pgref_chr_len.restype = C.c_uint32
         L.pgref_setting_double.restype = C.c_double
         L.pgref_search.restype = C.c_int64
+        L.pgref_classify.restype = C.c_int64
         self.workdir = workdir or tempfile.mkdtemp(prefix="pgref_")
         dummy = os.path.join(self.workdir, "empty_reads.txt")
         open(dummy, "w").close()
@@ -132,6 +133,42 @@ class RefHook:
         stream = np.ctypeslib.as_array(out, shape=(ln,)).copy()
         self.lib.pgref_free(out)
         return stream, (secs[0], secs[1])
+
+
+    def classify(self, seq_blob, seq_off, matched_d, insert_size, rflags, up_rows, up_off, n_close, window, num_boxes, box_size,
+                 chr_id=0, driver_mask=0x7F, region=None):
+        """The reference's SV drivers on one window.  up_rows int32 [k,5] (len, absLoc, dir, strand, mm); window = (start, end).
+        Returns (dump stream int32, seconds[7]); parse with oracle.svoracle.parse_dump."""
+        n = len(matched_d)
+        seq_blob = np.ascontiguousarray(seq_blob, dtype=np.uint8)
+        seq_off = np.ascontiguousarray(seq_off, dtype=np.uint32)
+        matched_d = np.ascontiguousarray(matched_d, dtype=np.uint8)
+        insert_size = np.ascontiguousarray(insert_size, dtype=np.int16)
+        rflags = np.ascontiguousarray(rflags, dtype=np.uint8)
+        up_rows = np.ascontiguousarray(up_rows, dtype=np.int32).reshape(-1, 5)
+        up_off = np.ascontiguousarray(up_off, dtype=np.uint32)
+        n_close = np.ascontiguousarray(n_close, dtype=np.uint32)
+        out = C.POINTER(C.c_int32)()
+        secs = (C.c_double * 7)()
+        devnull = os.open(os.devnull, os.O_WRONLY)
+        saved = os.dup(1)
+        os.dup2(devnull, 1)
+        try:
+            vp = lambda a: a.ctypes.data_as(C.c_void_p)
+            ln = self.lib.pgref_classify(n, vp(seq_blob), vp(seq_off), vp(matched_d), vp(insert_size), vp(rflags), vp(up_rows),
+                                         vp(up_off), vp(n_close), chr_id, C.c_uint32(window[0]), C.c_uint32(window[1]),
+                                         C.c_uint32(num_boxes), C.c_uint32(box_size), C.c_uint32(driver_mask),
+                                         0 if region is None else 1, C.c_uint32(0 if region is None else region[0]),
+                                         C.c_uint32(0 if region is None else region[1]), C.byref(out), secs)
+        finally:
+            os.dup2(saved, 1)
+            os.close(saved)
+            os.close(devnull)
+        if ln < 0:
+            raise RuntimeError("pgref_classify failed")
+        stream = np.ctypeslib.as_array(out, shape=(max(int(ln), 1),))[:ln].copy()
+        self.lib.pgref_free(out)
+        return stream, [secs[i] for i in range(7)]
 
 
 def parse_stream(stream: np.ndarray, n: int):
