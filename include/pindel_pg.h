@@ -166,6 +166,95 @@ int pg_device_results(pg_ctx *ctx, void **out_dev, void **runs_dev, uint32_t *n_
 void *pg_host_alloc(size_t bytes);
 void pg_host_free(void *p);
 
+/* ------------------------------------------------------------------------------------------------------------------
+ * SV classification: the seven per-read drivers SearchSVs runs after the far-end search
+ * (src/pindel.cpp:1140-1164) -- SearchDeletions / SearchShortInsertions ::Search (src/search_variant.cpp:49),
+ * searchIndels (src/search_deletions_nt.cpp:26), searchTandemDuplications(NT) (src/search_tandem_duplications.cpp:28,
+ * src/search_tandem_duplications_nt.cpp:27), searchInversions(NT) (src/search_inversions.cpp:29,
+ * src/search_inversions_nt.cpp:27).  One call classifies every read of a window with all selected drivers; what each
+ * driver did to a read comes back as records the host replays driver by driver (Vars[box].push_back, FutureReads_SR,
+ * the SPLIT_READ fields), then calls the reference's SortOutput* as before.
+ * ------------------------------------------------------------------------------------------------------------------ */
+#define PG_SV_D 0
+#define PG_SV_DI 1
+#define PG_SV_TD 2
+#define PG_SV_TD_NT 3
+#define PG_SV_INV 4
+#define PG_SV_INV_NT 5
+#define PG_SV_SI 6
+#define PG_SV_ALL_DRIVERS 0x7Fu
+
+#define PG_SV_NONE 0     /* fields assigned, read not taken */
+#define PG_SV_BOX 1      /* Vars[box].push_back(ReadIndex); Used = true */
+#define PG_SV_FUTURE 2   /* saveReadForNextCycle (src/pindel.cpp:587-592) */
+#define PG_SV_BREAK 3    /* breakpoint beyond the chromosome string: Used = true (src/search_variant.cpp:133-136) */
+
+#define PG_SVF_CORE 1u   /* record carries Left, Right, BP, IndelSize, BPLeft, BPRight */
+#define PG_SVF_NTSTR 2u  /* ... NT_str */
+#define PG_SVF_NTSIZE 4u /* ... NT_size */
+#define PG_SVF_KILLED 8u /* LeftMostTD / LeftMostINV set Used = true before the outcome (src/search_tandem_duplications.cpp:196-202) */
+
+#define PG_NT_EMPTY 0    /* NT_str = "" */
+#define PG_NT_SEQ 1      /* NT_str = rotl(UnmatchedSeq.substr(nt_start, nt_len), nt_rot) */
+#define PG_NT_RC 2       /* NT_str = rotl(ReverseComplement(UnmatchedSeq).substr(nt_start, nt_len), nt_rot) */
+
+#define PG_SVR_USED 1u       /* pg_sv_reads.rflags: SPLIT_READ::Used */
+#define PG_SVR_OTHERCHR 2u   /*                     FragName != FarFragName */
+
+typedef struct pg_sv_record {
+   uint32_t read;        /* ReadIndex in the batch */
+   uint8_t driver;       /* PG_SV_D .. PG_SV_SI */
+   uint8_t outcome;      /* PG_SV_NONE / BOX / FUTURE / BREAK */
+   uint8_t fields;       /* PG_SVF_* */
+   uint8_t seq;          /* order among the records of (driver, read) */
+   int32_t left, right;  /* SPLIT_READ::Left, Right   (src/pindel.h:350-351) */
+   uint32_t bp_left, bp_right, indel_size;
+   int16_t bp;
+   uint16_t nt_size;
+   uint16_t nt_start, nt_len, nt_rot;
+   uint8_t nt_src;       /* PG_NT_* */
+   uint8_t pad;
+   uint32_t box;         /* TempBoxIndex (PG_SV_BOX) */
+} pg_sv_record;
+
+typedef struct pg_sv_window {
+   uint32_t driver_mask;          /* bit d = run driver d; Analyze_TD / Analyze_INV clear theirs (src/pindel.cpp:1151-1158) */
+   int32_t chr;                   /* chromosome of the window (pg_set_reference order) */
+   uint32_t window_end;           /* SearchWindow::getEnd() */
+   uint32_t num_boxes, box_size;  /* NumBoxes, BoxSize (src/pindel.cpp:1806-1810) */
+   uint32_t region_start_defined, region_start, region_end_defined, region_end;   /* userSettings->getRegion() */
+   int32_t min_inversion_size;    /* -v  MIN_IndelSize_Inversion (default 30) */
+   int32_t min_matched_bases;     /* -M  Min_Num_Matched_Bases   (default 30) */
+   int32_t reserved;
+} pg_sv_window;
+
+/* A window's reads after the far-end search: final UnmatchedSeq, anchor strand, insert size, flags, and the UP_Close
+ * (after CleanUniquePoints; raw lists are accepted, the filter is idempotent) and UP_Far lists as runs. */
+typedef struct pg_sv_reads {
+   int32_t n_reads;
+   const uint8_t *seq_blob;
+   const uint32_t *seq_off;       /* [n+1] */
+   const uint8_t *matched_d;
+   const int16_t *insert_size;
+   const uint8_t *rflags;         /* PG_SVR_* */
+   const uint32_t *run_off;       /* [n+1] first run of each read: its UP_Close runs, then its UP_Far runs */
+   const uint16_t *n_close_runs;  /* [n] */
+   const pg_run *runs;
+} pg_sv_reads;
+
+typedef struct pg_sv_results {
+   pg_sv_record *records;         /* caller-allocated, sorted by (driver, read, seq) on return */
+   uint32_t records_cap;
+   uint32_t n_records;            /* on return; if > records_cap the call returned PG_ERR_RUNS_CAP and nothing was copied */
+} pg_sv_results;
+
+int pg_classify(pg_ctx *ctx, const pg_sv_reads *in, const pg_sv_window *win, pg_sv_results *res);
+uint64_t pg_classify_launches(pg_ctx *ctx);   /* classification-kernel launches since pg_create */
+
+/* Host helper: run-length encode UniquePoints (the inverse of pg_expand_runs) for callers that hold expanded lists.
+ * Returns the number of runs (out may be NULL to just count). */
+uint32_t pg_compress_ups(const pg_up *ups, uint32_t n, pg_run *out);
+
 /* Host helpers: expand runs to UniquePoints (returns the count; out may be NULL to just count), and
  * CleanUniquePoints (src/pindel.cpp:2904-2941) in place (returns the new count). */
 uint32_t pg_expand_runs(const pg_run *runs, uint32_t n_runs, pg_up *out);

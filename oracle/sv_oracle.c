@@ -161,7 +161,7 @@ static void left_most_inv(const char *chr, uint32_t chr_len, Read *r)
       r->used = 1;
       return;
    }
-   while (chr[pos] == rc_char(chr[end])) {
+   while (pos + 1 < chr_len && end > 0 && chr[pos] == rc_char(chr[end])) { /* (bounds added; never reached on padded input) */
       ++pos;
       --end;
    }

@@ -35,6 +35,23 @@ class _Results(C.Structure):
     _fields_ = [("out", C.c_void_p), ("runs", C.c_void_p), ("runs_cap", C.c_uint32), ("n_runs", C.c_uint32)]
 
 
+class _SvReads(C.Structure):
+    _fields_ = [("n_reads", C.c_int32), ("seq_blob", C.c_void_p), ("seq_off", C.c_void_p), ("matched_d", C.c_void_p),
+                ("insert_size", C.c_void_p), ("rflags", C.c_void_p), ("run_off", C.c_void_p), ("n_close_runs", C.c_void_p),
+                ("runs", C.c_void_p)]
+
+
+class _SvWindow(C.Structure):
+    _fields_ = [("driver_mask", C.c_uint32), ("chr", C.c_int32), ("window_end", C.c_uint32), ("num_boxes", C.c_uint32),
+                ("box_size", C.c_uint32), ("region_start_defined", C.c_uint32), ("region_start", C.c_uint32),
+                ("region_end_defined", C.c_uint32), ("region_end", C.c_uint32), ("min_inversion_size", C.c_int32),
+                ("min_matched_bases", C.c_int32), ("reserved", C.c_int32)]
+
+
+class _SvResults(C.Structure):
+    _fields_ = [("records", C.c_void_p), ("records_cap", C.c_uint32), ("n_records", C.c_uint32)]
+
+
 class PgError(RuntimeError):
     pass
 
@@ -71,6 +88,11 @@ def load_library() -> C.CDLL:
         lib.pg_download.argtypes = [C.c_void_p, C.POINTER(_Results)]
         lib.pg_sync.argtypes = [C.c_void_p]
         lib.pg_last_stats.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+        lib.pg_classify.argtypes = [C.c_void_p, C.POINTER(_SvReads), C.POINTER(_SvWindow), C.POINTER(_SvResults)]
+        lib.pg_classify_launches.restype = C.c_uint64
+        lib.pg_classify_launches.argtypes = [C.c_void_p]
+        lib.pg_compress_ups.restype = C.c_uint32
+        lib.pg_compress_ups.argtypes = [C.c_void_p, C.c_uint32, C.c_void_p]
         lib.pg_device_results.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
         _lib = lib
     return _lib
@@ -230,6 +252,35 @@ class PatternGrowth:
         o, r, k = C.c_void_p(0), C.c_void_p(0), C.c_uint32(0)
         self._check(self.lib.pg_device_results(self.ctx, C.byref(o), C.byref(r), C.byref(k)), "pg_device_results")
         return int(o.value or 0), int(r.value or 0), int(k.value)
+
+    def classify(self, batch: dict, win: dict, records=None) -> np.ndarray:
+        """The seven SV drivers of SearchSVs (src/pindel.cpp:1140-1164) on one window: batch = the arrays of pg_sv_reads
+        (pindel_b200.sv.batch_from_lists), win = pindel_b200.sv.window(...).  -> records (sv.RECORD_DT) sorted by
+        (driver, read, seq); replay them with pindel_b200.sv.replay."""
+        from . import sv
+        n = len(batch["matched_d"])
+        arrs = {k: np.ascontiguousarray(batch[k], dtype=dt) for k, dt in
+                (("seq_blob", np.uint8), ("seq_off", np.uint32), ("matched_d", np.uint8), ("insert_size", np.int16),
+                 ("rflags", np.uint8), ("run_off", np.uint32), ("n_close_runs", np.uint16), ("runs", R.RUN_DT))}
+        r = _SvReads(n, *[arrs[k].ctypes.data for k in ("seq_blob", "seq_off", "matched_d", "insert_size", "rflags", "run_off",
+                                                        "n_close_runs", "runs")])
+        reg = win.get("region")
+        w = _SvWindow(win["driver_mask"], win.get("chr", 0), win["window_end"], win["num_boxes"], win["box_size"],
+                      0 if reg is None else 1, 0 if reg is None else reg[0], 0 if reg is None else 1, 0 if reg is None else reg[1],
+                      win["min_inversion_size"], win["min_matched_bases"], 0)
+        rec = np.empty(max(1024, 2 * n), dtype=sv.RECORD_DT) if records is None else records
+        res = _SvResults(rec.ctypes.data, rec.size, 0)
+        rc = self.lib.pg_classify(self.ctx, C.byref(r), C.byref(w), C.byref(res))
+        if rc == PG_ERR_RUNS_CAP:
+            rec = np.empty(res.n_records, dtype=sv.RECORD_DT)
+            res = _SvResults(rec.ctypes.data, rec.size, 0)
+            rc = self.lib.pg_classify(self.ctx, C.byref(r), C.byref(w), C.byref(res))
+        self._check(rc, "pg_classify")
+        return rec[:res.n_records]
+
+    @property
+    def classify_launches(self) -> int:
+        return int(self.lib.pg_classify_launches(self.ctx))
 
     @property
     def kernel_launches(self) -> int:

@@ -1,9 +1,10 @@
 """Build every native artefact in-tree (nvcc cross-compiles sm_100a without a GPU).
 
   pindel_b200/libpindel_pg.so   the product: CUDA kernels + C ABI (include/pindel_pg.h)
-  oracle/libpg_oracle.so        test infrastructure: C restatement of the reference algorithm
+  oracle/libpg_oracle.so        test infrastructure: C restatement of the reference algorithm (libsv_oracle.so: the SV drivers)
   oracle/_ref/*                 test infrastructure: the reference itself, when /root/reference is present
   tests/emul/libpg_emul.so      test infrastructure: CPU lane emulator of the warp program
+  tests/emul/libsv_emul.so      test infrastructure: the SV-classification program compiled for the host
 """
 from __future__ import annotations
 
@@ -43,8 +44,9 @@ def build_oracle():
 
 def build_emulator():
     sys.path.insert(0, ROOT)
-    from tests.emul import emul
+    from tests.emul import emul, sv_emul
     emul.build()
+    sv_emul.build()
 
 
 def build_all(force=False):

@@ -1,0 +1,602 @@
+// pindel_b200/csrc/pg_sv.cuh -- the SV-classification program: what Pindel's seven per-read drivers decide for one read
+// (SURVEY.md section 8(f), row N1), written once and compiled twice: as the body of pg_sv_kernel (pindel_pg.cu, one
+// thread per read) and, for the CPU-side unit tests, as plain C++ (tests/emul).
+//
+// The reference walks expanded UniquePoint vectors; here the lists stay run-length coded (PgRun, the search kernel's own
+// output, so the two stages chain on the device without expansion).  Every driver is an instance of one pair
+// enumerator: close entries in list order (or reversed), far *runs* in list order (or reversed) -- an arm's test pins
+// either the far length (D, TD, INV: LengthStr sum == ReadLength) or the far position (SI: adjacent breakpoints), so a
+// far run holds at most one candidate -- then the arm's field assignments, the breakpoint slide over the packed
+// reference (GetRealStart4Deletion/Insertion, LeftMostTD, LeftMostINV), and the bin / region / box tail.
+//
+// A driver "fire" is reported as a PgSvRecord; the host replays records per driver (pg_sv_types.h).
+//
+// Reference: src/search_variant.cpp:49-266, src/searchdeletions.cpp:33-61, src/searchshortinsertions.cpp:33-61,
+// src/search_deletions_nt.cpp:26-140, src/search_tandem_duplications.cpp:28-222, src/search_tandem_duplications_nt.cpp:27-131,
+// src/search_inversions.cpp:29-318, src/search_inversions_nt.cpp:27-200, src/pindel.cpp:561-592,2094-2163.
+#pragma once
+#include "pg_sv_types.h"
+
+#ifdef __CUDACC__
+#define PGSV_HD __host__ __device__ __forceinline__
+#define PGSV_FN __host__ __device__
+#else
+#define PGSV_HD inline
+#define PGSV_FN inline
+#endif
+
+struct PgSvUP {
+   int32_t len;     // LengthStr
+   uint32_t loc;    // AbsLoc
+   int32_t mm;      // Mismatches
+   int32_t dir;     // 0 FORWARD, 1 BACKWARD
+   int32_t strand;  // 0 SENSE, 1 ANTISENSE
+};
+
+PGSV_HD PgSvUP pg_sv_up(const PgRun &r, int j)
+{
+   PgSvUP u;
+   u.len = (int32_t)r.len0 + j;
+   u.dir = r.dirstrand & 1;
+   u.strand = (r.dirstrand >> 1) & 1;
+   u.loc = u.dir ? r.abs_loc0 - (uint32_t)j : r.abs_loc0 + (uint32_t)j;
+   u.mm = r.mm;
+   return u;
+}
+
+// CleanUniquePoints (src/pindel.cpp:2904-2941) keeps the points that extend the last one: same chromosome, direction,
+// strand and the same AbsLoc -/+ LengthStr.  That value is constant inside a run, so whole runs stay or go.
+PGSV_HD uint32_t pg_sv_term(const PgRun &r) { return (r.dirstrand & 1) ? r.abs_loc0 + r.len0 : r.abs_loc0 - r.len0; }
+PGSV_HD bool pg_sv_close_kept(const PgRun &r, const PgRun &last)
+{
+   return r.chr == last.chr && r.dirstrand == last.dirstrand && pg_sv_term(r) == pg_sv_term(last);
+}
+
+// reference base at padded position pos: 0..3 = A C G T, 4 = N (anything else)
+PGSV_HD int pg_sv_ref(const PgChrom &c, uint32_t pos)
+{
+   if (pos >= c.len) return 4; // (the reference would read past its string; callers never get here with real UniquePoints)
+   const uint32_t w = pos >> 5, b = pos & 31;
+   if ((c.nplane[w] >> b) & 1) return 4;
+   const uint2 p = c.planes[w];
+   return (int)(((p.x >> b) & 1) | (((p.y >> b) & 1) << 1));
+}
+
+PGSV_HD int pg_sv_code(uint8_t ch) { return ch == 'A' ? 0 : ch == 'C' ? 1 : ch == 'G' ? 2 : ch == 'T' ? 3 : ch == 'N' ? 4 : 5; }
+
+struct PgSvRead {
+   const uint8_t *seq;
+   int32_t rl;              // ReadLength
+   int32_t max_e;           // MAX_SNP_ERROR = g_maxMismatch[ReadLength]   (src/pindel.cpp:166)
+   uint8_t matched_d;
+   int32_t insert_size;
+   const PgRun *cr;         // close runs
+   int32_t ncr;
+   const PgRun *fr;         // far runs
+   int32_t nfr;
+   uint32_t index;
+   // SPLIT_READ fields the drivers assign (src/pindel.h:349-360)
+   int32_t left, right;
+   uint32_t bp_left, bp_right, indel;
+   int32_t bp;              // short BP
+   uint32_t nt_size;
+   uint32_t nt_start, nt_len, nt_rot;
+   uint32_t nt_src;
+   bool used;
+   uint32_t dirty;          // PG_SVF_* assigned since the last record
+   uint32_t seq_no;
+};
+
+struct PgSvEnv {
+   const PgSvParams *P;
+   PgChrom chrom;
+   PgSvRecord *records;
+   uint32_t records_cap;
+   uint32_t *counters;
+};
+
+PGSV_HD uint32_t pg_sv_alloc(uint32_t *ctr)
+{
+#if defined(__CUDA_ARCH__)
+   return atomicAdd(ctr, 1u);
+#else
+   return (*ctr)++;
+#endif
+}
+
+PGSV_FN void pg_sv_emit(const PgSvEnv &ev, PgSvRead &r, int driver, int outcome, uint32_t box)
+{
+   const uint32_t slot = pg_sv_alloc(&ev.counters[0]);
+   if (slot < ev.records_cap) {
+      PgSvRecord rec;
+      rec.read = r.index;
+      rec.driver = (uint8_t)driver;
+      rec.outcome = (uint8_t)outcome;
+      rec.fields = (uint8_t)r.dirty;
+      rec.seq = (uint8_t)r.seq_no;
+      rec.left = r.left;
+      rec.right = r.right;
+      rec.bp_left = r.bp_left;
+      rec.bp_right = r.bp_right;
+      rec.indel_size = r.indel;
+      rec.bp = (int16_t)r.bp;
+      rec.nt_size = (uint16_t)r.nt_size;
+      rec.nt_start = (uint16_t)r.nt_start;
+      rec.nt_len = (uint16_t)r.nt_len;
+      rec.nt_rot = (uint16_t)r.nt_rot;
+      rec.nt_src = (uint8_t)r.nt_src;
+      rec.pad = 0;
+      rec.box = box;
+      ev.records[slot] = rec;
+   } else {
+      ev.counters[1] = 1u;
+   }
+   r.seq_no++;
+   r.dirty = 0;
+}
+
+// character i of the current NT_str
+PGSV_HD uint8_t pg_sv_nt_char(const PgSvRead &r, uint32_t i)
+{
+   uint32_t k = i + r.nt_rot;
+   if (k >= r.nt_len) k -= r.nt_len;
+   k += r.nt_start;
+   if (r.nt_src == PG_NT_SEQ) return r.seq[k];
+   const uint8_t ch = r.seq[(uint32_t)r.rl - 1 - k]; // ReverseComplement, Convert2RC4N (src/pindel.cpp:2037-2048)
+   return ch == 'A' ? 'T' : ch == 'C' ? 'G' : ch == 'G' ? 'C' : ch == 'T' ? 'A' : ch == 'N' ? 'N' : 0;
+}
+
+PGSV_HD void pg_sv_set_nt(PgSvRead &r, uint32_t src, uint32_t start, uint32_t want) // std::string::substr(start, want)
+{
+   const uint32_t avail = (uint32_t)r.rl > start ? (uint32_t)r.rl - start : 0u;
+   r.nt_len = want > avail ? avail : want;
+   r.nt_src = r.nt_len ? src : PG_NT_EMPTY;
+   r.nt_start = start;
+   r.nt_rot = 0;
+   r.dirty |= PG_SVF_NTSTR;
+}
+
+// GetRealStart4Deletion (src/pindel.cpp:2094-2116); only RealStart is used by the caller
+PGSV_FN uint32_t pg_sv_slide_deletion(const PgChrom &c, uint32_t real_start, uint32_t real_end)
+{
+   uint32_t pos = real_start + PG_SPACER, end = real_end + PG_SPACER - 1;
+   for (;;) {
+      const int a = pg_sv_ref(c, pos);
+      if (a == 4 || a != pg_sv_ref(c, end)) break;
+      --pos;
+      --end;
+   }
+   return pos - PG_SPACER;
+}
+
+// GetRealStart4Insertion (src/pindel.cpp:2131-2163): rotating the inserted string is a rotation offset here
+PGSV_FN uint32_t pg_sv_slide_insertion(const PgChrom &c, PgSvRead &r, uint32_t real_end)
+{
+   uint32_t after = real_end + PG_SPACER;
+   for (;;) {
+      const int a = pg_sv_ref(c, after);
+      if (a == 4 || a != pg_sv_code(pg_sv_nt_char(r, 0))) break;
+      r.nt_rot = r.nt_rot + 1 == r.nt_len ? 0 : r.nt_rot + 1; // rotateForward
+      after++;
+   }
+   uint32_t before = after - 1;
+   for (;;) {
+      const int a = pg_sv_ref(c, before);
+      if (a == 4 || a != pg_sv_code(pg_sv_nt_char(r, r.nt_len - 1))) break;
+      r.nt_rot = r.nt_rot == 0 ? r.nt_len - 1 : r.nt_rot - 1; // rotateBack
+      before--;
+   }
+   return before - PG_SPACER;
+}
+
+// LeftMostTD (src/search_tandem_duplications.cpp:186-222); returns true when the read was "killed"
+PGSV_FN bool pg_sv_left_most_td(const PgChrom &c, PgSvRead &r)
+{
+   uint32_t pos = r.bp_left + PG_SPACER, end = r.bp_right + PG_SPACER - 1;
+   const uint32_t pos0 = pos;
+   if (pos >= c.len || end >= c.len) {
+      r.bp_left = 1;
+      r.bp_right = 1;
+      r.bp = 1;
+      r.used = true;
+      return true;
+   }
+   while (pos > 0 && pg_sv_ref(c, pos) == pg_sv_ref(c, end)) { // no 'N' test here: N == N keeps sliding
+      --pos;
+      --end;
+   }
+   int32_t diff = (int32_t)(pos0 - pos);
+   if (diff > 0) {
+      if (diff >= r.bp) diff = r.bp - 1;
+      r.bp_left -= (uint32_t)diff;
+      r.bp_right -= (uint32_t)diff;
+      r.bp = (int16_t)(r.bp - diff);
+   }
+   return false;
+}
+
+// LeftMostINV (src/search_inversions.cpp:283-318)
+PGSV_FN bool pg_sv_left_most_inv(const PgChrom &c, PgSvRead &r)
+{
+   uint32_t pos = r.bp_left + PG_SPACER + 1, end = r.bp_right + PG_SPACER - 1;
+   const uint32_t pos0 = pos;
+   if (c.len <= pos + PG_SPACER) {
+      r.bp_left = 1;
+      r.bp_right = 1;
+      r.bp = 1;
+      r.used = true;
+      return true;
+   }
+   while (pos + 1 < c.len && end > 0) { // TheInput[PosIndex] == Convert2RC4N[TheInput[End]]: complement of A/C/G/T, N pairs with N
+      const int a = pg_sv_ref(c, pos), b = pg_sv_ref(c, end);
+      if (!(a == 4 ? b == 4 : (b != 4 && a == 3 - b))) break;
+      ++pos;
+      --end;
+   }
+   int32_t diff = (int16_t)(pos - pos0);
+   if (diff > 0 && r.matched_d != '+') { // the '+' branch clamps DIFF and drops it
+      if (diff + r.bp >= r.rl) diff = (int16_t)(r.rl - r.bp - 1);
+      r.bp_left += (uint32_t)diff;
+      r.bp_right -= (uint32_t)diff;
+      r.bp = (int16_t)(r.bp + diff);
+   }
+   return false;
+}
+
+// readTransgressesBinBoundaries / saveReadForNextCycle / readInSpecifiedRegion / the box test (src/pindel.cpp:561-592,
+// e.g. src/search_variant.cpp:147-166)
+PGSV_FN void pg_sv_tail(const PgSvEnv &ev, PgSvRead &r, int driver, bool check_bin)
+{
+   const PgSvParams &P = *ev.P;
+   if (check_bin && r.bp_right > P.window_end - (uint32_t)(2 * r.insert_size)) {
+      pg_sv_emit(ev, r, driver, PG_SV_FUTURE, 0);
+      r.used = true;
+      return;
+   }
+   if (P.region_start_defined && r.bp_left + 1 < P.region_start) return;
+   if (P.region_end_defined && r.bp_left + 1 > P.region_end) return;
+   const uint32_t box = r.bp_left / P.box_size;
+   if (box < P.num_boxes) {
+      pg_sv_emit(ev, r, driver, PG_SV_BOX, box);
+      r.used = true;
+   }
+}
+
+// arms of the pair drivers
+#define PG_ARM_D_PLUS 0
+#define PG_ARM_D_MINUS 1
+#define PG_ARM_SI_PLUS 2
+#define PG_ARM_SI_MINUS 3
+#define PG_ARM_TD_PLUS 4
+#define PG_ARM_TD_MINUS 5
+#define PG_ARM_INV0 6   // '+' anchor, far end downstream    (src/search_inversions.cpp:54-105)
+#define PG_ARM_INV1 7   // '+' anchor inside the inverted block (:107-160)
+#define PG_ARM_INV2 8   // '-' anchor                         (:166-214)
+#define PG_ARM_INV3 9   // '-' anchor inside                  (:216-268)
+
+// One passing pair: assign the fields, slide the breakpoint, decide.  Returns false when the far loop must stop (D/SI's
+// "breakpoint beyond the chromosome" exit, src/search_variant.cpp:133-136).
+PGSV_FN bool pg_sv_fire(const PgSvEnv &ev, PgSvRead &r, int driver, int arm, const PgSvUP &c, const PgSvUP &f)
+{
+   const uint32_t SP = PG_SPACER, rl = (uint32_t)r.rl, cl = (uint32_t)c.len, fl = (uint32_t)f.len;
+   r.dirty |= PG_SVF_CORE;
+   switch (arm) {
+   case PG_ARM_D_PLUS:
+   case PG_ARM_SI_PLUS:
+      r.left = (int32_t)(c.loc - cl + 1);
+      r.right = (int32_t)(f.loc + fl - 1);
+      r.bp = c.len - 1;
+      r.bp_left = c.loc - SP;
+      r.bp_right = f.loc - SP;
+      break;
+   case PG_ARM_D_MINUS:
+   case PG_ARM_SI_MINUS:
+      r.left = (int32_t)(f.loc - fl + 1);
+      r.right = (int32_t)(c.loc + cl - 1);
+      r.bp = f.len - 1;
+      r.bp_left = f.loc - SP;
+      r.bp_right = c.loc - SP;
+      break;
+   case PG_ARM_TD_PLUS:
+      r.right = (int32_t)(c.loc - cl + 1);
+      r.left = (int32_t)(f.loc + fl - 1);
+      r.bp = c.len - 1;
+      r.indel = c.loc - f.loc + 1;
+      r.bp_right = c.loc - SP;
+      r.bp_left = f.loc - SP;
+      break;
+   case PG_ARM_TD_MINUS:
+      r.right = (int32_t)(f.loc - fl + 1);
+      r.left = (int32_t)(c.loc + cl - 1);
+      r.bp = f.len - 1;
+      r.indel = f.loc - c.loc + 1;
+      r.bp_right = f.loc - SP;
+      r.bp_left = c.loc - SP;
+      break;
+   case PG_ARM_INV0:
+      r.left = (int32_t)((c.loc + 1) - cl);
+      r.right = (int32_t)(f.loc - fl + rl);
+      r.bp = c.len - 1;
+      r.indel = f.loc - c.loc;
+      r.bp_left = c.loc + 1 - SP;
+      r.bp_right = f.loc - SP;
+      break;
+   case PG_ARM_INV1:
+      r.right = (int32_t)(c.loc - cl + rl);
+      r.left = (int32_t)(f.loc - fl + 1);
+      r.bp = f.len - 1;
+      r.indel = c.loc - f.loc;
+      r.bp_right = c.loc - SP;
+      r.bp_left = (f.loc + 1) - SP;
+      break;
+   case PG_ARM_INV2:
+      r.left = (int32_t)(f.loc + fl - rl);
+      r.right = (int32_t)(c.loc + cl - 1);
+      r.bp = f.len - 1;
+      r.indel = c.loc - f.loc;
+      r.bp_left = f.loc - SP;
+      r.bp_right = c.loc - 1 - SP;
+      break;
+   default: // PG_ARM_INV3
+      r.right = (int32_t)(f.loc + fl - 1);
+      r.left = (int32_t)(c.loc + cl - rl);
+      r.bp = c.len - 1;
+      r.indel = f.loc - c.loc;
+      r.bp_left = c.loc - SP;
+      r.bp_right = f.loc - 1 - SP;
+      break;
+   }
+   if (arm <= PG_ARM_SI_MINUS) {
+      const bool plus = (arm == PG_ARM_D_PLUS || arm == PG_ARM_SI_PLUS);
+      if (arm <= PG_ARM_D_MINUS) { // SearchDeletions::calculateIndelSize, getInsertedStr = ""
+         r.indel = (uint32_t)((r.right - r.left) - (r.rl - 1));
+         pg_sv_set_nt(r, PG_NT_EMPTY, 0, 0);
+      } else { // SearchShortInsertions
+         r.indel = (uint32_t)((r.rl - 1) - (r.right - r.left));
+         pg_sv_set_nt(r, plus ? PG_NT_RC : PG_NT_SEQ, (uint32_t)(r.bp + 1), r.indel);
+      }
+      uint32_t real_left = r.bp_left;
+      if (ev.chrom.len < real_left || ev.chrom.len < r.bp_right) {
+         r.used = true;
+         pg_sv_emit(ev, r, driver, PG_SV_BREAK, 0);
+         return false;
+      }
+      real_left = r.nt_len ? pg_sv_slide_insertion(ev.chrom, r, r.bp_right) : pg_sv_slide_deletion(ev.chrom, real_left, r.bp_right);
+      int32_t diff = (int16_t)(r.bp_left - real_left);
+      if ((r.bp - 1) < diff) diff = r.bp - 1;
+      if (diff > 0) {
+         r.bp = (int16_t)(r.bp - diff);
+         r.bp_left -= (uint32_t)diff;
+         r.bp_right -= (uint32_t)diff;
+      }
+      pg_sv_tail(ev, r, driver, true);
+      return true;
+   }
+   if (arm <= PG_ARM_TD_MINUS) {
+      if (r.bp_left == 0) return true; // src/search_tandem_duplications.cpp:88-90
+      if (pg_sv_left_most_td(ev.chrom, r)) r.dirty |= PG_SVF_KILLED;
+      pg_sv_tail(ev, r, driver, true);
+      return true;
+   }
+   pg_sv_set_nt(r, PG_NT_EMPTY, 0, 0);
+   r.nt_size = 0;
+   r.dirty |= PG_SVF_NTSIZE;
+   if (pg_sv_left_most_inv(ev.chrom, r)) r.dirty |= PG_SVF_KILLED;
+   pg_sv_tail(ev, r, driver, arm <= PG_ARM_INV1); // the '-' arms have no bin test (src/search_inversions.cpp:199,251)
+   return true;
+}
+
+// the test of one arm on a (close point, far point) pair
+PGSV_HD bool pg_sv_pair_ok(const PgSvParams &P, const PgSvRead &r, int arm, const PgSvUP &c, const PgSvUP &f)
+{
+   const uint32_t mi = (uint32_t)P.min_inv;
+   const bool sum_eq = f.len + c.len == r.rl;
+   switch (arm) {
+   case PG_ARM_D_PLUS: return sum_eq && f.loc > c.loc + 1;
+   case PG_ARM_D_MINUS: return sum_eq && c.loc > f.loc + 1;
+   case PG_ARM_SI_PLUS: return f.loc == c.loc + 1 && c.len + f.len < r.rl;
+   case PG_ARM_SI_MINUS: return c.loc == f.loc + 1 && c.len + f.len < r.rl;
+   case PG_ARM_TD_PLUS: return sum_eq && f.loc + (uint32_t)f.len < c.loc && f.loc + (uint32_t)c.len < c.loc;
+   case PG_ARM_TD_MINUS: return sum_eq && c.loc + (uint32_t)c.len < f.loc && c.loc + (uint32_t)f.len < f.loc;
+   case PG_ARM_INV0: return sum_eq && f.loc > c.loc + mi;
+   case PG_ARM_INV1: return sum_eq && f.loc + mi < c.loc;
+   case PG_ARM_INV2: return sum_eq && c.loc > f.loc + mi;
+   default: return sum_eq && c.loc + mi < f.loc;
+   }
+}
+
+// The pair enumerator shared by D, SI, TD and INV: mismatch budget e outermost, then close points, then far points.
+PGSV_FN void pg_sv_pairs(const PgSvEnv &ev, PgSvRead &r, int driver, int arm, bool close_desc, bool far_desc, int far_dir)
+{
+   const PgRun &last_close = r.cr[r.ncr - 1];
+   for (int e = 0; e <= r.max_e && !r.used; e++) {
+      for (int ci = 0; ci < r.ncr && !r.used; ci++) {
+         const PgRun &crun = r.cr[close_desc ? r.ncr - 1 - ci : ci];
+         if ((int)crun.mm > e || !pg_sv_close_kept(crun, last_close)) continue;
+         for (int cj = 0; cj < (int)crun.count && !r.used; cj++) {
+            const PgSvUP c = pg_sv_up(crun, close_desc ? (int)crun.count - 1 - cj : cj);
+            for (int fi = 0; fi < r.nfr && !r.used; fi++) {
+               const PgRun &frun = r.fr[far_desc ? r.nfr - 1 - fi : fi];
+               if ((int)frun.mm > e || (int)frun.mm + c.mm > e || (frun.dirstrand & 1) != far_dir) continue;
+               int32_t j; // the only member of this far run the arm can accept
+               if (arm == PG_ARM_SI_PLUS || arm == PG_ARM_SI_MINUS) {
+                  const uint32_t want = arm == PG_ARM_SI_PLUS ? c.loc + 1 : c.loc - 1;
+                  j = (int32_t)(far_dir ? frun.abs_loc0 - want : want - frun.abs_loc0);
+               } else {
+                  j = r.rl - c.len - (int32_t)frun.len0;
+               }
+               if (j < 0 || j >= (int32_t)frun.count) continue;
+               const PgSvUP f = pg_sv_up(frun, j);
+               if (!pg_sv_pair_ok(*ev.P, r, arm, c, f)) continue;
+               if (!pg_sv_fire(ev, r, driver, arm, c, f)) break;
+            }
+         }
+      }
+   }
+}
+
+PGSV_HD PgSvUP pg_sv_first(const PgRun *runs) { return pg_sv_up(runs[0], 0); }
+PGSV_HD PgSvUP pg_sv_last(const PgRun *runs, int n) { return pg_sv_up(runs[n - 1], (int)runs[n - 1].count - 1); }
+// UP_Close[0] after CleanUniquePoints: the first run that survives the filter
+PGSV_HD PgSvUP pg_sv_first_close(const PgSvRead &r)
+{
+   int k = 0;
+   while (!pg_sv_close_kept(r.cr[k], r.cr[r.ncr - 1])) k++;
+   return pg_sv_up(r.cr[k], 0);
+}
+
+// the shared shape of DI, TD_NT and INV_NT: one test on (last close point, last far point)
+PGSV_FN void pg_sv_nt_driver(const PgSvEnv &ev, PgSvRead &r, int driver)
+{
+   const PgSvParams &P = *ev.P;
+   const PgSvUP c = pg_sv_last(r.cr, r.ncr), f = pg_sv_last(r.fr, r.nfr);
+   const uint32_t SP = PG_SPACER, rl = (uint32_t)r.rl, cl = (uint32_t)c.len, fl = (uint32_t)f.len, mi = (uint32_t)P.min_inv;
+   const int32_t sum = f.len + c.len;
+   const bool plus = r.matched_d == '+';
+   if (!plus && r.matched_d != '-') return;
+   if (driver == PG_SV_TD_NT && sum >= r.rl) return;
+   if (f.mm + c.mm > (int32_t)(int16_t)P.nt_thr[sum < 1032 ? sum : 1031]) return;
+   if (driver == PG_SV_INV_NT) {
+      const PgSvUP c0 = pg_sv_first_close(r), f0 = pg_sv_first(r.fr);
+      if (!(c0.strand != f0.strand && c0.dir == f0.dir)) return;
+      if (f.dir != (plus ? 0 : 1)) return;
+   } else if (f.dir != (plus ? 1 : 0)) return;
+   const uint32_t nts = (uint32_t)(uint16_t)(r.rl - f.len - c.len);
+   if (driver == PG_SV_DI) { // src/search_deletions_nt.cpp:55-124
+      if (!(sum < r.rl && sum >= P.min_matched && (plus ? f.loc > c.loc + 1 : c.loc > f.loc + 1))) return;
+      r.dirty |= PG_SVF_CORE | PG_SVF_NTSIZE;
+      if (plus) {
+         r.left = (int32_t)(c.loc - cl + 1);
+         r.right = (int32_t)(f.loc + fl - 1);
+         r.bp = c.len - 1;
+      } else {
+         r.left = (int32_t)(f.loc - fl + 1);
+         r.right = (int32_t)(c.loc + cl - 1);
+         r.bp = f.len - 1;
+      }
+      r.nt_size = nts;
+      pg_sv_set_nt(r, plus ? PG_NT_RC : PG_NT_SEQ, (uint32_t)(r.bp + 1), nts);
+      r.indel = (uint32_t)((r.right - r.left) + (int32_t)nts - (r.rl - 1));
+      r.bp_left = (plus ? c.loc : f.loc) - SP;
+      r.bp_right = (plus ? f.loc : c.loc) - SP;
+      pg_sv_tail(ev, r, driver, true);
+      return;
+   }
+   if (driver == PG_SV_TD_NT) { // src/search_tandem_duplications_nt.cpp:56-117
+      if (!(sum > P.min_matched)) return;
+      if (plus ? !(f.loc + fl < c.loc && f.loc + cl < c.loc) : !(c.loc + cl < f.loc && c.loc + fl < f.loc)) return;
+      r.dirty |= PG_SVF_CORE | PG_SVF_NTSIZE;
+      if (plus) {
+         r.right = (int32_t)(c.loc - cl + 1);
+         r.left = (int32_t)(f.loc + fl - 1);
+         r.bp = c.len - 1;
+         r.indel = c.loc - f.loc + 1;
+      } else {
+         r.right = (int32_t)(f.loc - fl + 1);
+         r.left = (int32_t)(c.loc + cl - 1);
+         r.bp = f.len - 1;
+         r.indel = f.loc - c.loc + 1;
+      }
+      r.nt_size = nts;
+      pg_sv_set_nt(r, plus ? PG_NT_RC : PG_NT_SEQ, (uint32_t)(r.bp + 1), nts);
+      r.bp_right = (plus ? c.loc : f.loc) - SP;
+      r.bp_left = (plus ? f.loc : c.loc) - SP;
+      pg_sv_tail(ev, r, driver, true);
+      return;
+   }
+   // INV_NT, src/search_inversions_nt.cpp:56-186: the two tests of a strand run one after the other, whatever the first did
+   if (!(sum < r.rl && sum >= P.min_matched)) return;
+   for (int k = 0; k < 2; k++) {
+      const int arm = plus ? (k == 0 ? PG_ARM_INV0 : PG_ARM_INV1) : (k == 0 ? PG_ARM_INV2 : PG_ARM_INV3);
+      bool ok;
+      switch (arm) {
+      case PG_ARM_INV0: ok = f.loc > c.loc + mi; break;
+      case PG_ARM_INV1: ok = f.loc + mi < c.loc; break;
+      case PG_ARM_INV2: ok = c.loc > f.loc + mi; break;
+      default: ok = c.loc + mi < f.loc; break;
+      }
+      if (!ok) continue;
+      r.dirty |= PG_SVF_CORE | PG_SVF_NTSIZE;
+      r.nt_size = nts;
+      switch (arm) {
+      case PG_ARM_INV0:
+         r.left = (int32_t)((c.loc + 1) - cl);
+         r.right = (int32_t)(f.loc - fl + rl);
+         r.bp = c.len - 1;
+         r.indel = f.loc - c.loc;
+         pg_sv_set_nt(r, PG_NT_RC, (uint32_t)(r.bp + 1), nts);
+         r.bp_left = c.loc + 1 - SP;
+         r.bp_right = f.loc - SP;
+         break;
+      case PG_ARM_INV1:
+         r.right = (int32_t)(c.loc - cl + rl);
+         r.left = (int32_t)(f.loc - fl + 1);
+         r.bp = f.len - 1;
+         r.indel = c.loc - f.loc;
+         pg_sv_set_nt(r, PG_NT_SEQ, (uint32_t)(r.bp + 1), nts);
+         r.bp_right = c.loc - SP;
+         r.bp_left = (f.loc + 1) - SP;
+         break;
+      case PG_ARM_INV2:
+         r.left = (int32_t)(f.loc + fl - rl);
+         r.right = (int32_t)(c.loc + cl - 1);
+         r.bp = f.len - 1;
+         r.indel = c.loc - f.loc;
+         pg_sv_set_nt(r, PG_NT_SEQ, (uint32_t)(r.bp + 1), nts);
+         r.bp_left = f.loc - SP;
+         r.bp_right = c.loc - 1 - SP;
+         break;
+      default:
+         r.right = (int32_t)(f.loc + fl - 1);
+         r.left = (int32_t)(c.loc + cl - rl);
+         r.bp = c.len - 1;
+         r.indel = f.loc - c.loc;
+         pg_sv_set_nt(r, PG_NT_RC, (uint32_t)(r.bp + 1), nts);
+         r.bp_left = c.loc - SP;
+         r.bp_right = f.loc - 1 - SP;
+         break;
+      }
+      pg_sv_tail(ev, r, driver, true);
+   }
+}
+
+// All selected drivers on one read, in SearchSVs' order (src/pindel.cpp:1140-1164).
+PGSV_FN void pg_sv_classify_read(const PgSvEnv &ev, PgSvRead &r, bool other_chr)
+{
+   const PgSvParams &P = *ev.P;
+   if (other_chr || r.nfr == 0 || r.ncr == 0) return; // every driver skips such reads
+   const bool plus = r.matched_d == '+', minus = r.matched_d == '-';
+   for (int d = 0; d < PG_SV_NDRIVERS; d++) {
+      if (!((P.driver_mask >> d) & 1u) || r.used) continue;
+      r.seq_no = 0;
+      switch (d) {
+      case PG_SV_D:
+         if (plus) pg_sv_pairs(ev, r, d, PG_ARM_D_PLUS, false, true, 1);
+         else if (minus) pg_sv_pairs(ev, r, d, PG_ARM_D_MINUS, true, true, 0);
+         break;
+      case PG_SV_SI:
+         if (plus) pg_sv_pairs(ev, r, d, PG_ARM_SI_PLUS, false, true, 1);
+         else if (minus) pg_sv_pairs(ev, r, d, PG_ARM_SI_MINUS, true, true, 0);
+         break;
+      case PG_SV_TD:
+         if (plus) pg_sv_pairs(ev, r, d, PG_ARM_TD_PLUS, false, true, 1);
+         else if (minus) pg_sv_pairs(ev, r, d, PG_ARM_TD_MINUS, true, false, 0);
+         break;
+      case PG_SV_INV: {
+         const PgSvUP c0 = pg_sv_first_close(r), cl = pg_sv_last(r.cr, r.ncr), f0 = pg_sv_first(r.fr), fl = pg_sv_last(r.fr, r.nfr);
+         if (!(c0.strand != f0.strand && c0.dir == f0.dir)) break;
+         const uint32_t mi = (uint32_t)P.min_inv;
+         if (plus) {
+            if (f0.loc > cl.loc + mi) pg_sv_pairs(ev, r, d, PG_ARM_INV0, true, false, 0);
+            else if (fl.loc + mi < c0.loc) pg_sv_pairs(ev, r, d, PG_ARM_INV1, false, true, 0);
+         } else if (minus) {
+            if (cl.loc > f0.loc + mi) pg_sv_pairs(ev, r, d, PG_ARM_INV2, true, false, 1);
+            else if (c0.loc + mi < fl.loc) pg_sv_pairs(ev, r, d, PG_ARM_INV3, false, true, 1);
+         }
+         break;
+      }
+      default: pg_sv_nt_driver(ev, r, d); break;
+      }
+      if (r.dirty) pg_sv_emit(ev, r, d, PG_SV_NONE, 0); // fields assigned, read not taken: the host still gets the values
+   }
+}

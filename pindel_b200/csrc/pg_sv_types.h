@@ -66,7 +66,7 @@ struct PgSvParams {
    uint32_t region_end_defined, region_end;
    int32_t min_inv;         // MIN_IndelSize_Inversion     (src/user_defined_settings.h:68)
    int32_t min_matched;     // Min_Num_Matched_Bases       (-M)
-   uint16_t nt_thr[1024];   // nt_thr[k] = (short)(1 + Seq_Error_Rate * k), k = far length + close length, host-computed in double
+   uint16_t nt_thr[1032];   // nt_thr[k] = (short)(1 + Seq_Error_Rate * k), k = far length + close length, host-computed in double
                             //             (src/search_deletions_nt.cpp:50-51)
 };
 

@@ -12,10 +12,12 @@
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
+#include <algorithm>
 #include <string>
 #include <vector>
 
 #include "pg_warp.cuh"
+#include "pg_sv.cuh"
 #include "pg_params.h"
 #include "../../include/pindel_pg.h"
 
@@ -121,6 +123,46 @@ __global__ void pg_pack_kernel(const uint8_t *__restrict__ ascii, uint32_t n_bas
 }
 
 // ------------------------------------------------------------------------------------------------
+// SV classification: one thread per read runs the seven drivers (pg_sv.cuh).  The work per read is a few hundred
+// integer operations over its own run lists, so the stage is bound by launch + record traffic, not by issue slots.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) pg_sv_kernel(PgSvBatch b, const PgSvParams *__restrict__ P, const PgParams *__restrict__ prm,
+                                                    const PgChrom *__restrict__ chroms)
+{
+   const int i = blockIdx.x * blockDim.x + threadIdx.x;
+   if (i >= b.n_reads) return;
+   PgSvEnv ev;
+   ev.P = P;
+   ev.chrom = chroms[P->chr];
+   ev.records = b.records;
+   ev.records_cap = b.records_cap;
+   ev.counters = b.counters;
+   PgSvRead r;
+   const uint32_t s0 = b.seq_off[i], s1 = b.seq_off[i + 1];
+   r.seq = b.seq_blob + s0;
+   r.rl = (int32_t)(s1 - s0);
+   r.max_e = prm->g[r.rl < 512 ? r.rl : 511];
+   r.matched_d = b.matched_d[i];
+   r.insert_size = b.insert_size[i];
+   const uint32_t r0 = b.run_off[i], r1 = b.run_off[i + 1];
+   r.cr = b.runs + r0;
+   r.ncr = b.n_close_runs[i];
+   r.fr = r.cr + r.ncr;
+   r.nfr = (int32_t)(r1 - r0) - r.ncr;
+   r.index = (uint32_t)i;
+   r.left = r.right = 0;
+   r.bp_left = r.bp_right = r.indel = 0;
+   r.bp = 0;
+   r.nt_size = r.nt_start = r.nt_len = r.nt_rot = 0;
+   r.nt_src = PG_NT_EMPTY;
+   const uint8_t fl = b.rflags[i];
+   r.used = (fl & PG_SVR_USED) != 0;
+   r.dirty = 0;
+   r.seq_no = 0;
+   pg_sv_classify_read(ev, r, (fl & PG_SVR_OTHERCHR) != 0);
+}
+
+// ------------------------------------------------------------------------------------------------
 // Context
 // ------------------------------------------------------------------------------------------------
 struct DevBuf {
@@ -153,6 +195,9 @@ struct pg_ctx {
    uint64_t launches = 0;
    uint32_t last_runs = 0;
    uint64_t last_window_bases = 0, last_ups = 0;
+   // SV classification (pg_classify)
+   DevBuf sv_seq, sv_off, sv_md, sv_isz, sv_flags, sv_runoff, sv_nclose, sv_runs, sv_records, sv_params, sv_counters;
+   uint64_t sv_launches = 0;
    struct PipeState *pipe = nullptr;    // streams, events and the two chunk slots of the pipelined path (lazy)
    int pipe_chunk = PG_PIPE_CHUNK_DEFAULT;
 };
@@ -300,6 +345,9 @@ void pg_destroy(pg_ctx *ctx)
    DevBuf *bufs[] = {&ctx->seq_blob, &ctx->seq_off, &ctx->md, &ctx->pos, &ctx->isz, &ctx->chr, &ctx->closeinfo,
                      &ctx->regions, &ctx->region_off, &ctx->out, &ctx->pool, &ctx->counters, &ctx->scratch};
    for (DevBuf *b : bufs) if (b->p) cudaFree(b->p);
+   DevBuf *svbufs[] = {&ctx->sv_seq, &ctx->sv_off, &ctx->sv_md, &ctx->sv_isz, &ctx->sv_flags, &ctx->sv_runoff, &ctx->sv_nclose,
+                       &ctx->sv_runs, &ctx->sv_records, &ctx->sv_params, &ctx->sv_counters};
+   for (DevBuf *b : svbufs) if (b->p) cudaFree(b->p);
    pipe_destroy(ctx->pipe);
    if (ctx->chroms_d) cudaFree(ctx->chroms_d);
    if (ctx->prm_d) cudaFree(ctx->prm_d);
@@ -814,6 +862,139 @@ uint32_t pg_clean_unique_points(pg_up *ups, uint32_t n)
       if (t == terminal) ups[w++] = ups[i];
    }
    return w;
+}
+
+// ---- SV classification ------------------------------------------------------------------------------------------
+static_assert(sizeof(pg_sv_record) == sizeof(PgSvRecord) && sizeof(pg_sv_record) == 44, "sv record layout");
+
+int pg_classify(pg_ctx *ctx, const pg_sv_reads *in, const pg_sv_window *win, pg_sv_results *res)
+{
+   if (!ctx || !in || !win || !res) return fail(ctx, PG_ERR_ARG, "pg_classify: null argument");
+   if (ctx->chroms_h.empty()) return fail(ctx, PG_ERR_STATE, "pg_classify: pg_set_reference has not been called");
+   if (win->chr < 0 || win->chr >= (int32_t)ctx->chroms_h.size()) return fail(ctx, PG_ERR_ARG, "pg_classify: chromosome out of range");
+   if (win->box_size == 0) return fail(ctx, PG_ERR_ARG, "pg_classify: box_size is 0");
+   res->n_records = 0;
+   const int n = in->n_reads;
+   if (n < 0) return fail(ctx, PG_ERR_ARG, "pg_classify: negative read count");
+   if (n == 0) return PG_OK;
+   if (!in->seq_blob || !in->seq_off || !in->matched_d || !in->insert_size || !in->rflags || !in->run_off || !in->n_close_runs)
+      return fail(ctx, PG_ERR_ARG, "pg_classify: null input array");
+   const uint32_t n_runs = in->run_off[n];
+   if (n_runs && !in->runs) return fail(ctx, PG_ERR_ARG, "pg_classify: null run array");
+   for (int i = 0; i < n; i++) {
+      if (in->run_off[i + 1] < in->run_off[i] || in->n_close_runs[i] > in->run_off[i + 1] - in->run_off[i])
+         return fail(ctx, PG_ERR_ARG, "pg_classify: inconsistent run offsets");
+      if (in->seq_off[i + 1] < in->seq_off[i] || in->seq_off[i + 1] - in->seq_off[i] >= 512)
+         return fail(ctx, PG_ERR_UNSUPPORTED, "pg_classify: read of 512 bases or more");
+   }
+   CU(cudaSetDevice(ctx->device));
+   cudaStream_t st = ctx->stream;
+   PgSvParams P;
+   memset(&P, 0, sizeof P);
+   P.driver_mask = win->driver_mask & PG_SV_ALL;
+   P.chr = win->chr;
+   P.window_end = win->window_end;
+   P.num_boxes = win->num_boxes;
+   P.box_size = win->box_size;
+   P.region_start_defined = win->region_start_defined;
+   P.region_start = win->region_start;
+   P.region_end_defined = win->region_end_defined;
+   P.region_end = win->region_end;
+   P.min_inv = win->min_inversion_size;
+   P.min_matched = win->min_matched_bases;
+   for (int k = 0; k < 1032; k++) P.nt_thr[k] = (uint16_t)(short)(1 + ctx->st.seq_error_rate * k); // src/search_deletions_nt.cpp:50-51
+   int rc;
+   const size_t seq_bytes = in->seq_off[n];
+   if ((rc = ensure(ctx, ctx->sv_seq, seq_bytes + 4)) != PG_OK) return rc;
+   if ((rc = ensure(ctx, ctx->sv_off, sizeof(uint32_t) * (size_t)(n + 1))) != PG_OK) return rc;
+   if ((rc = ensure(ctx, ctx->sv_md, (size_t)n)) != PG_OK) return rc;
+   if ((rc = ensure(ctx, ctx->sv_isz, sizeof(int16_t) * (size_t)n)) != PG_OK) return rc;
+   if ((rc = ensure(ctx, ctx->sv_flags, (size_t)n)) != PG_OK) return rc;
+   if ((rc = ensure(ctx, ctx->sv_runoff, sizeof(uint32_t) * (size_t)(n + 1))) != PG_OK) return rc;
+   if ((rc = ensure(ctx, ctx->sv_nclose, sizeof(uint16_t) * (size_t)n)) != PG_OK) return rc;
+   if ((rc = ensure(ctx, ctx->sv_runs, sizeof(PgRun) * (size_t)(n_runs + 1))) != PG_OK) return rc;
+   if ((rc = ensure(ctx, ctx->sv_params, sizeof(PgSvParams))) != PG_OK) return rc;
+   if ((rc = ensure(ctx, ctx->sv_counters, sizeof(uint32_t) * 4)) != PG_OK) return rc;
+   CU(cudaMemcpyAsync(ctx->sv_seq.p, in->seq_blob, seq_bytes, cudaMemcpyHostToDevice, st));
+   CU(cudaMemcpyAsync(ctx->sv_off.p, in->seq_off, sizeof(uint32_t) * (size_t)(n + 1), cudaMemcpyHostToDevice, st));
+   CU(cudaMemcpyAsync(ctx->sv_md.p, in->matched_d, (size_t)n, cudaMemcpyHostToDevice, st));
+   CU(cudaMemcpyAsync(ctx->sv_isz.p, in->insert_size, sizeof(int16_t) * (size_t)n, cudaMemcpyHostToDevice, st));
+   CU(cudaMemcpyAsync(ctx->sv_flags.p, in->rflags, (size_t)n, cudaMemcpyHostToDevice, st));
+   CU(cudaMemcpyAsync(ctx->sv_runoff.p, in->run_off, sizeof(uint32_t) * (size_t)(n + 1), cudaMemcpyHostToDevice, st));
+   CU(cudaMemcpyAsync(ctx->sv_nclose.p, in->n_close_runs, sizeof(uint16_t) * (size_t)n, cudaMemcpyHostToDevice, st));
+   if (n_runs) CU(cudaMemcpyAsync(ctx->sv_runs.p, in->runs, sizeof(PgRun) * (size_t)n_runs, cudaMemcpyHostToDevice, st));
+   CU(cudaMemcpyAsync(ctx->sv_params.p, &P, sizeof P, cudaMemcpyHostToDevice, st));
+   // records: most reads fire at most once per driver and stop at the first accepted pair; grow and repeat on overflow
+   size_t cap = (size_t)n + (size_t)n / 2 + 1024;
+   uint32_t counters[4];
+   for (int attempt = 0;; attempt++) {
+      if ((rc = ensure(ctx, ctx->sv_records, sizeof(PgSvRecord) * cap)) != PG_OK) return rc;
+      CU(cudaMemsetAsync(ctx->sv_counters.p, 0, sizeof(uint32_t) * 4, st));
+      PgSvBatch b;
+      b.n_reads = n;
+      b.seq_blob = (const uint8_t *)ctx->sv_seq.p;
+      b.seq_off = (const uint32_t *)ctx->sv_off.p;
+      b.matched_d = (const uint8_t *)ctx->sv_md.p;
+      b.insert_size = (const int16_t *)ctx->sv_isz.p;
+      b.rflags = (const uint8_t *)ctx->sv_flags.p;
+      b.run_off = (const uint32_t *)ctx->sv_runoff.p;
+      b.n_close_runs = (const uint16_t *)ctx->sv_nclose.p;
+      b.runs = (const PgRun *)ctx->sv_runs.p;
+      b.records = (PgSvRecord *)ctx->sv_records.p;
+      b.records_cap = (uint32_t)cap;
+      b.counters = (uint32_t *)ctx->sv_counters.p;
+      pg_sv_kernel<<<(n + 127) / 128, 128, 0, st>>>(b, (const PgSvParams *)ctx->sv_params.p, ctx->prm_d, ctx->chroms_d);
+      CU(cudaGetLastError());
+      ctx->sv_launches++;
+      CU(cudaMemcpyAsync(counters, ctx->sv_counters.p, sizeof counters, cudaMemcpyDeviceToHost, st));
+      CU(cudaStreamSynchronize(st));
+      if (counters[0] <= cap) break;
+      if (attempt >= 4) return fail(ctx, PG_ERR_CUDA, "pg_classify: record pool keeps overflowing");
+      cap = (size_t)counters[0] + 1024;
+   }
+   res->n_records = counters[0];
+   if (counters[0] > res->records_cap || (counters[0] && !res->records))
+      return fail(ctx, PG_ERR_RUNS_CAP, "pg_classify: record buffer too small (n_records holds the required size)");
+   if (counters[0]) {
+      CU(cudaMemcpyAsync(res->records, ctx->sv_records.p, sizeof(PgSvRecord) * (size_t)counters[0], cudaMemcpyDeviceToHost, st));
+      CU(cudaStreamSynchronize(st));
+      // pool slots are handed out in completion order; the host replays per driver, reads ascending
+      std::sort(res->records, res->records + counters[0], [](const pg_sv_record &a, const pg_sv_record &b) {
+         if (a.driver != b.driver) return a.driver < b.driver;
+         if (a.read != b.read) return a.read < b.read;
+         return a.seq < b.seq;
+      });
+   }
+   return PG_OK;
+}
+
+uint64_t pg_classify_launches(pg_ctx *ctx) { return ctx ? ctx->sv_launches : 0; }
+
+// Run-length encode an expanded UniquePoint list: consecutive points continue a run when the length grows by one, the
+// position moves by one in the run's direction and chromosome, direction, strand and mismatch count stay.
+uint32_t pg_compress_ups(const pg_up *ups, uint32_t n, pg_run *out)
+{
+   uint32_t k = 0;
+   for (uint32_t i = 0; i < n;) {
+      uint32_t j = i + 1;
+      while (j < n && j - i < 65535u && ups[j].len == ups[j - 1].len + 1 && ups[j].mm == ups[i].mm && ups[j].dir == ups[i].dir &&
+             ups[j].strand == ups[i].strand && ups[j].chr == ups[i].chr &&
+             ups[j].abs_loc == (ups[i].dir ? ups[j - 1].abs_loc - 1u : ups[j - 1].abs_loc + 1u))
+         j++;
+      if (out) {
+         pg_run r;
+         r.abs_loc0 = ups[i].abs_loc;
+         r.len0 = (uint16_t)ups[i].len;
+         r.count = (uint16_t)(j - i);
+         r.mm = (uint8_t)ups[i].mm;
+         r.dirstrand = (uint8_t)((ups[i].dir & 1) | ((ups[i].strand & 1) << 1));
+         r.chr = ups[i].chr;
+         out[k] = r;
+      }
+      k++;
+      i = j;
+   }
+   return k;
 }
 
 } // extern "C"

@@ -70,6 +70,26 @@ def test_host_helpers_expand_and_clean():
     assert np.array_equal(ups["len"][:k], cl[:, 0]) and np.array_equal(ups["abs_loc"][:k], cl[:, 1])
 
 
+def test_host_helper_compress_is_the_inverse_of_expand():
+    lib = api.load_library()
+    from pindel_b200 import sv
+    runs = np.zeros(4, dtype=R.RUN_DT)
+    runs[0] = (1000, 8, 5, 0, 2, 0)
+    runs[1] = (2000, 13, 2, 1, 1, 0)     # BACKWARD
+    runs[2] = (1998, 15, 1, 1, 1, 0)     # continues run 1 in position and length: merges with it
+    runs[3] = (70000, 16, 4, 2, 3, 1)
+    UP = np.dtype([("abs_loc", "<u4"), ("len", "<i2"), ("mm", "<i2"), ("dir", "u1"), ("strand", "u1"), ("chr", "<i2")])
+    n = lib.pg_expand_runs(runs.ctypes.data_as(C.c_void_p), 4, None)
+    ups = np.zeros(n, dtype=UP)
+    lib.pg_expand_runs(runs.ctypes.data_as(C.c_void_p), 4, ups.ctypes.data_as(C.c_void_p))
+    k = lib.pg_compress_ups(ups.ctypes.data_as(C.c_void_p), n, None)
+    assert k == 3
+    back = np.zeros(k, dtype=R.RUN_DT)
+    lib.pg_compress_ups(ups.ctypes.data_as(C.c_void_p), n, back.ctypes.data_as(C.c_void_p))
+    assert np.array_equal(R.expand_runs(back), R.expand_runs(runs))
+    assert np.array_equal(sv.compress_ups(R.expand_runs(runs)), back)      # the numpy mirror agrees with the C helper
+
+
 def test_backward_runs_walk_down():
     runs = np.zeros(1, dtype=R.RUN_DT)
     runs[0] = (5000, 10, 3, 0, 1, 0)     # BACKWARD/SENSE
