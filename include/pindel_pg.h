@@ -250,6 +250,7 @@ typedef struct pg_sv_results {
 
 int pg_classify(pg_ctx *ctx, const pg_sv_reads *in, const pg_sv_window *win, pg_sv_results *res);
 uint64_t pg_classify_launches(pg_ctx *ctx);   /* classification-kernel launches since pg_create */
+double pg_classify_last_kernel_ms(pg_ctx *ctx); /* CUDA-event duration of the last classification kernel */
 
 /* Host helper: run-length encode UniquePoints (the inverse of pg_expand_runs) for callers that hold expanded lists.
  * Returns the number of runs (out may be NULL to just count). */

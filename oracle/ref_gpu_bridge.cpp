@@ -17,6 +17,12 @@
  * (reader.cpp:196-361), both reachable by symbol -- as the batched binding INTEGRATION.md describes: one pg_close_end
  * call per batch.  The per-read GetCloseEnd below remains for any other caller; SearchFarEnds is a batch call anyway.
  * Set PG_BRIDGE_UNBATCHED=1 to make the text path go through the per-read shim instead (the reference's own ReadInRead).
+ *
+ * Row N1 of SURVEY.md section 8(f): the seven SV drivers SearchSVs calls (src/pindel.cpp:1140-1164) are supplied here too --
+ * SearchVariant::Search (D and SI), searchIndels, searchTandemDuplications(NT), searchInversions(NT).  The first driver of
+ * a window sends every read with its UniquePoint lists to pg_classify once (all drivers in one launch); each driver then
+ * replays its own records (SPLIT_READ fields, Vars[box], FutureReads_SR) and calls the reference's reporter
+ * (outputResults / SortOutput*) exactly as before.  PG_BRIDGE_CPU_SV=1 is not offered: there is no CPU path behind the ABI.
  */
 #include "pindel.h"
 #include "bddata.h"
@@ -25,6 +31,15 @@
 #include "pindel_read_reader.h"
 #include "logstream.h"
 #include "user_defined_settings.h"
+#include "control_state.h"
+#include "logdef.h"
+#include "reporter.h"
+#include "search_variant.h"
+#include "search_deletions_nt.h"
+#include "search_tandem_duplications.h"
+#include "search_tandem_duplications_nt.h"
+#include "search_inversions.h"
+#include "search_inversions_nt.h"
 
 #include <cstdio>
 #include <cstdlib>
@@ -42,7 +57,7 @@ extern short g_MinClose;
 namespace {
 pg_ctx *g_ctx = NULL;
 std::mutex g_mutex;
-unsigned long g_close_calls = 0, g_far_reads = 0;
+unsigned long g_close_calls = 0, g_far_reads = 0, g_sv_reads = 0, g_sv_records = 0;
 
 void die(const char *what)
 {
@@ -318,10 +333,267 @@ void SearchFarEnds(const std::string &chromosomeSeq, std::vector<SPLIT_READ> &re
    *logStream << "Far end searching completed for this window." << std::endl;   /* src/pindel.cpp:1137 */
 }
 
+/* ---------------------------------------------------------------------------------------------------------------------
+ * SV drivers (row N1): pg_classify once per window, replay per driver.
+ * ------------------------------------------------------------------------------------------------------------------- */
+namespace {
+struct SvWindowResults {
+   const SPLIT_READ *base = NULL;   /* identity of the window the records belong to */
+   size_t n = 0;
+   unsigned windowStart = 0, windowEnd = 0;
+   const Chromosome *chromosome = NULL;
+   uint32_t mask = 0;
+   std::vector<pg_sv_record> records;
+   size_t first[8] = {0, 0, 0, 0, 0, 0, 0, 0};   /* records of driver d: [first[d], first[d+1]) */
+} g_sv;
+
+int chrIndexOf(const Chromosome *c)
+{
+   for (unsigned i = 0; g_genome.getChr(i) != NULL; i++) if (g_genome.getChr(i) == c) return (int)i;
+   return -1;
+}
+
+void pushUps(std::vector<pg_up> &dst, const SortedUniquePoints &src)
+{
+   for (unsigned k = 0; k < src.size(); k++) {
+      pg_up u;
+      u.abs_loc = src[k].AbsLoc;
+      u.len = src[k].LengthStr;
+      u.mm = src[k].Mismatches;
+      u.dir = src[k].Direction == BACKWARD ? 1 : 0;
+      u.strand = src[k].Strand == ANTISENSE ? 1 : 0;
+      u.chr = (int16_t)chrIndexOf(src[k].chromosome_p);
+      dst.push_back(u);
+   }
+}
+
+void classifyWindow(ControlState &cs, unsigned NumBoxes, const SearchWindow &window, uint32_t mask)
+{
+   std::lock_guard<std::mutex> lock(g_mutex);
+   ensureContext();
+   std::vector<SPLIT_READ> &reads = cs.Reads_SR;
+   const int n = (int)reads.size();
+   std::string blob;
+   std::vector<uint32_t> off(n + 1, 0), runOff(n + 1, 0);
+   std::vector<uint8_t> md(n), flags(n);
+   std::vector<int16_t> isz(n);
+   std::vector<uint16_t> nClose(n);
+   std::vector<pg_run> runs;
+   std::vector<pg_up> ups;
+   for (int i = 0; i < n; i++) {
+      const SPLIT_READ &r = reads[i];
+      blob += r.getUnmatchedSeq();
+      off[i + 1] = (uint32_t)blob.size();
+      md[i] = (uint8_t)r.MatchedD;
+      isz[i] = r.InsertSize;
+      flags[i] = (uint8_t)((r.Used ? PG_SVR_USED : 0u) | (r.FragName != r.FarFragName ? PG_SVR_OTHERCHR : 0u));
+      for (int list = 0; list < 2; list++) {
+         ups.clear();
+         pushUps(ups, list == 0 ? r.UP_Close : r.UP_Far);
+         const uint32_t k = pg_compress_ups(ups.empty() ? NULL : &ups[0], (uint32_t)ups.size(), NULL);
+         const size_t at = runs.size();
+         runs.resize(at + k);
+         if (k) pg_compress_ups(&ups[0], (uint32_t)ups.size(), &runs[at]);
+         if (list == 0) nClose[i] = (uint16_t)k;
+      }
+      runOff[i + 1] = (uint32_t)runs.size();
+   }
+   pg_sv_reads in;
+   memset(&in, 0, sizeof in);
+   in.n_reads = n;
+   in.seq_blob = (const uint8_t *)blob.c_str();
+   in.seq_off = &off[0];
+   in.matched_d = n ? &md[0] : NULL;
+   in.insert_size = n ? &isz[0] : NULL;
+   in.rflags = n ? &flags[0] : NULL;
+   in.run_off = &runOff[0];
+   in.n_close_runs = n ? &nClose[0] : NULL;
+   in.runs = runs.empty() ? NULL : &runs[0];
+   pg_sv_window w;
+   memset(&w, 0, sizeof w);
+   w.driver_mask = mask;
+   w.chr = chrIndexOf(window.getChromosome());
+   w.window_end = window.getEnd();
+   w.num_boxes = NumBoxes;
+   w.box_size = BoxSize;
+   const SearchRegion *region = userSettings->getRegion();
+   w.region_start_defined = region->isStartDefined();
+   w.region_start = region->isStartDefined() ? region->getStart() : 0;
+   w.region_end_defined = region->isEndDefined();
+   w.region_end = region->isEndDefined() ? region->getEnd() : 0;
+   w.min_inversion_size = userSettings->MIN_IndelSize_Inversion;
+   w.min_matched_bases = userSettings->Min_Num_Matched_Bases;
+   g_sv.records.resize((size_t)n * 2 + 1024);
+   pg_sv_results res;
+   res.records = &g_sv.records[0];
+   res.records_cap = (uint32_t)g_sv.records.size();
+   res.n_records = 0;
+   int rc = pg_classify(g_ctx, &in, &w, &res);
+   if (rc == PG_ERR_RUNS_CAP) {
+      g_sv.records.resize(res.n_records);
+      res.records = &g_sv.records[0];
+      res.records_cap = res.n_records;
+      rc = pg_classify(g_ctx, &in, &w, &res);
+   }
+   if (rc != PG_OK) die("pg_classify");
+   g_sv.records.resize(res.n_records);
+   size_t k = 0;
+   for (int d = 0; d <= 7; d++) {
+      while (k < g_sv.records.size() && (int)g_sv.records[k].driver < d) k++;
+      g_sv.first[d] = k;
+   }
+   g_sv.base = n ? &reads[0] : NULL;
+   g_sv.n = (size_t)n;
+   g_sv.windowStart = window.getStart();
+   g_sv.windowEnd = window.getEnd();
+   g_sv.chromosome = window.getChromosome();
+   g_sv.mask = mask;
+   g_sv_reads += (unsigned long)n;
+   g_sv_records += (unsigned long)res.n_records;
+}
+
+uint32_t svMaskFromSettings()
+{
+   uint32_t m = (1u << PG_SV_D) | (1u << PG_SV_DI) | (1u << PG_SV_SI);
+   if (userSettings->Analyze_TD) m |= (1u << PG_SV_TD) | (1u << PG_SV_TD_NT);
+   if (userSettings->Analyze_INV) m |= (1u << PG_SV_INV) | (1u << PG_SV_INV_NT);
+   return m;
+}
+
+/* The records of driver d, applied the way the driver acts on its reads (src/search_variant.cpp:117-175 and the like). */
+void replayDriver(int d, ControlState &cs, unsigned NumBoxes, const SearchWindow &window, std::vector<unsigned> Vars[], int counts[3])
+{
+   std::vector<SPLIT_READ> &reads = cs.Reads_SR;
+   const bool sameWindow = g_sv.base == (reads.empty() ? NULL : &reads[0]) && g_sv.n == reads.size() &&
+                           g_sv.windowStart == window.getStart() && g_sv.windowEnd == window.getEnd() &&
+                           g_sv.chromosome == window.getChromosome() && ((g_sv.mask >> d) & 1u);
+   if (d == PG_SV_D || !sameWindow) classifyWindow(cs, NumBoxes, window, d == PG_SV_D ? svMaskFromSettings() : (1u << d));
+   for (size_t k = g_sv.first[d]; k < g_sv.first[d + 1]; k++) {
+      const pg_sv_record &rec = g_sv.records[k];
+      SPLIT_READ &read = reads[rec.read];
+      if (rec.fields & PG_SVF_CORE) {
+         read.Left = rec.left;
+         read.Right = rec.right;
+         read.BP = rec.bp;
+         read.BPLeft = rec.bp_left;
+         read.BPRight = rec.bp_right;
+         read.IndelSize = rec.indel_size;
+      }
+      if (rec.fields & PG_SVF_NTSTR) {
+         if (rec.nt_src == PG_NT_EMPTY || rec.nt_len == 0) read.NT_str = "";
+         else {
+            const std::string src = rec.nt_src == PG_NT_SEQ ? read.getUnmatchedSeq() : ReverseComplement(read.getUnmatchedSeq());
+            const std::string s = src.substr(rec.nt_start, rec.nt_len);
+            read.NT_str = s.substr(rec.nt_rot) + s.substr(0, rec.nt_rot);
+         }
+      }
+      if (rec.fields & PG_SVF_NTSIZE) read.NT_size = rec.nt_size;
+      if (rec.fields & PG_SVF_KILLED) read.Used = true;
+      switch (rec.outcome) {
+      case PG_SV_FUTURE:
+         cs.FutureReads_SR.push_back(read);     /* saveReadForNextCycle, src/pindel.cpp:587-592 */
+         read.Used = true;
+         break;
+      case PG_SV_BOX:
+         Vars[rec.box].push_back(rec.read);
+         read.Used = true;
+         counts[0]++;
+         counts[read.MatchedD == Plus ? 1 : 2]++;
+         break;
+      case PG_SV_BREAK:
+         read.Used = true;
+         break;
+      default:
+         break;
+      }
+   }
+}
+} // namespace
+
+int SearchVariant::Search(BDData &bdData, ControlState &currentState, const unsigned NumBoxes, const SearchWindow &window)
+{
+   std::vector<unsigned> *Vars = new std::vector<unsigned>[NumBoxes];
+   LOG_INFO(*logStream << "Searching " << typeOfVariant << " ... " << std::endl);
+   int counts[3] = {0, 0, 0};
+   replayDriver(typeOfVariant == "deletions" ? PG_SV_D : PG_SV_SI, currentState, NumBoxes, window, Vars, counts);
+   Count_Var += counts[0];
+   Count_Var_Plus += counts[1];
+   Count_Var_Minus += counts[2];
+   LOG_INFO(*logStream << "Total: " << Count_Var << "\t+" << Count_Var_Plus << "\t-" << Count_Var_Minus << std::endl);
+   outputResults(bdData, currentState, Vars, NumBoxes, window);
+   delete[] Vars;
+   return EXIT_SUCCESS;
+}
+
+int searchIndels(ControlState &currentState, unsigned NumBoxes, const SearchWindow &window)
+{
+   std::vector<unsigned> *DI = new std::vector<unsigned>[NumBoxes];
+   LOG_INFO(*logStream << "Searching deletion-insertions ... " << std::endl);
+   int counts[3] = {0, 0, 0};
+   replayDriver(PG_SV_DI, currentState, NumBoxes, window, DI, counts);
+   std::ofstream DeletionOutf(userSettings->getDOutputFilename().c_str(), std::ios::app);
+   std::ofstream inversionsOutf(userSettings->getINVOutputFilename().c_str(), std::ios::app);
+   SortOutputDI(currentState, NumBoxes, window.getChromosome()->getSeq(), currentState.Reads_SR, DI, DeletionOutf, inversionsOutf);
+   DeletionOutf.close();
+   delete[] DI;
+   return EXIT_SUCCESS;
+}
+
+int searchTandemDuplications(ControlState &currentState, unsigned NumBoxes, const SearchWindow &window)
+{
+   std::vector<unsigned> *TD = new std::vector<unsigned>[NumBoxes];
+   LOG_INFO(*logStream << "Searching tandem duplication events ... " << std::endl);
+   int counts[3] = {0, 0, 0};
+   replayDriver(PG_SV_TD, currentState, NumBoxes, window, TD, counts);
+   std::ofstream TDOutf(userSettings->getTDOutputFilename().c_str(), std::ios::app);
+   SortAndOutputTandemDuplications(currentState, NumBoxes, window.getChromosome()->getSeq(), currentState.Reads_SR, TD, TDOutf, false);
+   delete[] TD;
+   return EXIT_SUCCESS;
+}
+
+int searchTandemDuplicationsNT(ControlState &currentState, unsigned NumBoxes, const SearchWindow &window)
+{
+   std::vector<unsigned> *TD_NT = new std::vector<unsigned>[NumBoxes];
+   LOG_INFO(*logStream << "Searching tandem duplication events with non-template sequence ... " << std::endl);
+   int counts[3] = {0, 0, 0};
+   replayDriver(PG_SV_TD_NT, currentState, NumBoxes, window, TD_NT, counts);
+   std::ofstream TDOutf(userSettings->getTDOutputFilename().c_str(), std::ios::app);
+   SortAndOutputTandemDuplications(currentState, NumBoxes, window.getChromosome()->getSeq(), currentState.Reads_SR, TD_NT, TDOutf, true);
+   TDOutf.close();
+   delete[] TD_NT;
+   return EXIT_SUCCESS;
+}
+
+int searchInversions(ControlState &currentState, unsigned NumBoxes, const SearchWindow &window)
+{
+   std::vector<unsigned> *Inv = new std::vector<unsigned>[NumBoxes];
+   LOG_INFO(*logStream << "Searching inversions ... " << std::endl);
+   int counts[3] = {0, 0, 0};
+   replayDriver(PG_SV_INV, currentState, NumBoxes, window, Inv, counts);
+   std::ofstream InversionOutf(userSettings->getINVOutputFilename().c_str(), std::ios::app);
+   SortOutputInv(currentState, NumBoxes, window.getChromosome()->getSeq(), currentState.Reads_SR, Inv, InversionOutf);
+   delete[] Inv;
+   return EXIT_SUCCESS;
+}
+
+int searchInversionsNT(ControlState &currentState, unsigned NumBoxes, const SearchWindow &window)
+{
+   std::vector<unsigned> *Inv_NT = new std::vector<unsigned>[NumBoxes];
+   LOG_INFO(*logStream << "Searching inversions with non-template sequence ... " << std::endl);
+   int counts[3] = {0, 0, 0};
+   replayDriver(PG_SV_INV_NT, currentState, NumBoxes, window, Inv_NT, counts);
+   std::ofstream InversionOutf(userSettings->getINVOutputFilename().c_str(), std::ios::app);
+   SortOutputInv_NT(currentState, NumBoxes, window.getChromosome()->getSeq(), currentState.Reads_SR, Inv_NT, InversionOutf);
+   delete[] Inv_NT;
+   return EXIT_SUCCESS;
+}
+
 static void reportAtExit()
 {
-   std::fprintf(stderr, "pindel_gpu_demo: %lu GetCloseEnd calls and %lu far-end reads served by libpindel_pg (%llu kernel launches)\n",
-                g_close_calls, g_far_reads, g_ctx ? (unsigned long long)pg_kernel_launches(g_ctx) : 0ull);
+   std::fprintf(stderr, "pindel_gpu_demo: %lu GetCloseEnd calls and %lu far-end reads served by libpindel_pg (%llu kernel launches); "
+                "%lu reads classified by the SV drivers on the device, %lu records (%llu launches)\n",
+                g_close_calls, g_far_reads, g_ctx ? (unsigned long long)pg_kernel_launches(g_ctx) : 0ull, g_sv_reads, g_sv_records,
+                g_ctx ? (unsigned long long)pg_classify_launches(g_ctx) : 0ull);
 }
 
 int main(int argc, char *argv[])

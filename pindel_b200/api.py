@@ -91,6 +91,8 @@ def load_library() -> C.CDLL:
         lib.pg_classify.argtypes = [C.c_void_p, C.POINTER(_SvReads), C.POINTER(_SvWindow), C.POINTER(_SvResults)]
         lib.pg_classify_launches.restype = C.c_uint64
         lib.pg_classify_launches.argtypes = [C.c_void_p]
+        lib.pg_classify_last_kernel_ms.restype = C.c_double
+        lib.pg_classify_last_kernel_ms.argtypes = [C.c_void_p]
         lib.pg_compress_ups.restype = C.c_uint32
         lib.pg_compress_ups.argtypes = [C.c_void_p, C.c_uint32, C.c_void_p]
         lib.pg_device_results.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
@@ -277,6 +279,10 @@ class PatternGrowth:
             rc = self.lib.pg_classify(self.ctx, C.byref(r), C.byref(w), C.byref(res))
         self._check(rc, "pg_classify")
         return rec[:res.n_records]
+
+    @property
+    def classify_last_kernel_ms(self) -> float:
+        return float(self.lib.pg_classify_last_kernel_ms(self.ctx))
 
     @property
     def classify_launches(self) -> int:

@@ -198,6 +198,8 @@ struct pg_ctx {
    // SV classification (pg_classify)
    DevBuf sv_seq, sv_off, sv_md, sv_isz, sv_flags, sv_runoff, sv_nclose, sv_runs, sv_records, sv_params, sv_counters;
    uint64_t sv_launches = 0;
+   cudaEvent_t sv_ev0 = nullptr, sv_ev1 = nullptr;   // around the last pg_sv_kernel launch
+   float sv_last_ms = 0.f;
    struct PipeState *pipe = nullptr;    // streams, events and the two chunk slots of the pipelined path (lazy)
    int pipe_chunk = PG_PIPE_CHUNK_DEFAULT;
 };
@@ -352,6 +354,7 @@ void pg_destroy(pg_ctx *ctx)
    if (ctx->chroms_d) cudaFree(ctx->chroms_d);
    if (ctx->prm_d) cudaFree(ctx->prm_d);
    if (ctx->counters_h) cudaFreeHost(ctx->counters_h);
+   if (ctx->sv_ev0) { cudaEventDestroy(ctx->sv_ev0); cudaEventDestroy(ctx->sv_ev1); }
    if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
    delete ctx;
 }
@@ -943,11 +946,15 @@ int pg_classify(pg_ctx *ctx, const pg_sv_reads *in, const pg_sv_window *win, pg_
       b.records = (PgSvRecord *)ctx->sv_records.p;
       b.records_cap = (uint32_t)cap;
       b.counters = (uint32_t *)ctx->sv_counters.p;
+      if (!ctx->sv_ev0) { CU(cudaEventCreate(&ctx->sv_ev0)); CU(cudaEventCreate(&ctx->sv_ev1)); }
+      CU(cudaEventRecord(ctx->sv_ev0, st));
       pg_sv_kernel<<<(n + 127) / 128, 128, 0, st>>>(b, (const PgSvParams *)ctx->sv_params.p, ctx->prm_d, ctx->chroms_d);
       CU(cudaGetLastError());
+      CU(cudaEventRecord(ctx->sv_ev1, st));
       ctx->sv_launches++;
       CU(cudaMemcpyAsync(counters, ctx->sv_counters.p, sizeof counters, cudaMemcpyDeviceToHost, st));
       CU(cudaStreamSynchronize(st));
+      CU(cudaEventElapsedTime(&ctx->sv_last_ms, ctx->sv_ev0, ctx->sv_ev1));
       if (counters[0] <= cap) break;
       if (attempt >= 4) return fail(ctx, PG_ERR_CUDA, "pg_classify: record pool keeps overflowing");
       cap = (size_t)counters[0] + 1024;
@@ -969,6 +976,7 @@ int pg_classify(pg_ctx *ctx, const pg_sv_reads *in, const pg_sv_window *win, pg_
 }
 
 uint64_t pg_classify_launches(pg_ctx *ctx) { return ctx ? ctx->sv_launches : 0; }
+double pg_classify_last_kernel_ms(pg_ctx *ctx) { return ctx ? (double)ctx->sv_last_ms : 0.0; }
 
 // Run-length encode an expanded UniquePoint list: consecutive points continue a run when the length grows by one, the
 // position moves by one in the run's direction and chromosome, direction, strand and mismatch count stay.

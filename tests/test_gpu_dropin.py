@@ -30,6 +30,7 @@ def test_reference_host_with_gpu_search_writes_identical_files(tmp_path):
                        capture_output=True, text=True, timeout=1200, env=env)
     assert p.returncode == 0, p.stdout[-2000:] + p.stderr[-2000:]
     assert "served by libpindel_pg" in p.stderr and " 0 GetCloseEnd calls" not in p.stderr
+    assert "classified by the SV drivers on the device" in p.stderr and "; 0 reads classified" not in p.stderr
     for suf in ("D", "SI", "INV", "TD", "LI", "BP", "CloseEndMapped"):
         got = (tmp_path / ("colo_slice.out_" + suf)).read_bytes()
         exp = gzip.open(os.path.join(GOLD, "colo_slice.out_%s.gz" % suf)).read()
@@ -62,6 +63,7 @@ def test_reference_host_bam_input_with_gpu_search(tmp_path):
                        capture_output=True, text=True, timeout=1200, env=env)
     assert p.returncode == 0, p.stdout[-2000:] + p.stderr[-2000:]
     assert "served by libpindel_pg" in p.stderr and " 0 GetCloseEnd calls" not in p.stderr
+    assert "classified by the SV drivers on the device" in p.stderr and "; 0 reads classified" not in p.stderr
     for suf in ("D", "SI", "INV", "TD", "LI", "BP", "RP", "CloseEndMapped"):
         got = (tmp_path / ("sim_prefix.out_" + suf)).read_bytes()
         exp = gzip.open(os.path.join(GOLD, "sim_prefix.out_%s.gz" % suf)).read()
