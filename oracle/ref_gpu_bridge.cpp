@@ -35,6 +35,7 @@
 #include "logdef.h"
 #include "reporter.h"
 #include "search_variant.h"
+#include "searchdeletions.h"
 #include "search_deletions_nt.h"
 #include "search_tandem_duplications.h"
 #include "search_tandem_duplications_nt.h"
@@ -515,7 +516,8 @@ int SearchVariant::Search(BDData &bdData, ControlState &currentState, const unsi
    std::vector<unsigned> *Vars = new std::vector<unsigned>[NumBoxes];
    LOG_INFO(*logStream << "Searching " << typeOfVariant << " ... " << std::endl);
    int counts[3] = {0, 0, 0};
-   replayDriver(typeOfVariant == "deletions" ? PG_SV_D : PG_SV_SI, currentState, NumBoxes, window, Vars, counts);
+   /* typeOfVariant cannot tell the two apart: the reference prints the base-class placeholder for both */
+   replayDriver(dynamic_cast<SearchDeletions *>(this) != NULL ? PG_SV_D : PG_SV_SI, currentState, NumBoxes, window, Vars, counts);
    Count_Var += counts[0];
    Count_Var_Plus += counts[1];
    Count_Var_Minus += counts[2];

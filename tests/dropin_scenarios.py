@@ -1,0 +1,55 @@
+"""The two file-level drop-in scenarios (Pindel-text input, BAM-config input), parameterised by the host binary: the
+reference host + bridge on libpindel_pg.so (GPU test) or on the CPU emulators of the device programs (CPU test of the
+bridge's host logic).  Golden files were written by the pure reference binary (tests/golden/)."""
+import gzip
+import os
+import shutil
+import subprocess
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+GOLD = os.path.join(ROOT, "tests", "golden")
+
+
+def _run(demo, args, env):
+    p = subprocess.run([demo] + args, capture_output=True, text=True, timeout=1800, env=env)
+    assert p.returncode == 0, p.stdout[-2000:] + p.stderr[-2000:]
+    assert "served by libpindel_pg" in p.stderr and " 0 GetCloseEnd calls" not in p.stderr
+    # every window is classified by ONE call (all seven drivers in one launch), and the drivers replayed its records
+    assert "classified by the SV drivers on the device" in p.stderr and "; 0 reads classified" not in p.stderr
+    return p
+
+
+def _compare(tmp_path, prefix, gold_prefix, suffixes):
+    for suf in suffixes:
+        got = (tmp_path / ("%s_%s" % (prefix, suf))).read_bytes()
+        exp = gzip.open(os.path.join(GOLD, "%s.out_%s.gz" % (gold_prefix, suf))).read()
+        assert got == exp, "%s_%s differs from the reference's file (%d vs %d bytes)" % (prefix, suf, len(got), len(exp))
+
+
+def colo_slice(demo, tmp_path, env, unbatched_too=True):
+    fa = tmp_path / "colo_slice.fa"
+    fa.write_bytes(gzip.open(os.path.join(GOLD, "colo_slice.fa.gz")).read())
+    (tmp_path / "colo_slice.fa.fai").write_text("20s\t500000\t5\t60\t61\n")
+    rd = tmp_path / "reads.txt"
+    rd.write_bytes(gzip.open(os.path.join(GOLD, "colo_slice_reads.txt.gz")).read())
+    p = _run(demo, ["-f", str(fa), "-p", str(rd), "-o", str(tmp_path / "colo_slice.out"), "-k", "-s", "-l", "-T", "1"], env)
+    _compare(tmp_path, "colo_slice.out", "colo_slice", ("D", "SI", "INV", "TD", "LI", "BP", "CloseEndMapped"))
+    if unbatched_too:   # the same through the per-read GetCloseEnd shim (one-read batches): the seam function itself
+        _run(demo, ["-f", str(fa), "-p", str(rd), "-o", str(tmp_path / "unbatched.out"), "-k", "-s", "-l", "-T", "1"],
+             dict(env, PG_BRIDGE_UNBATCHED="1"))
+        _compare(tmp_path, "unbatched.out", "colo_slice", ("D", "SI", "INV", "TD"))
+    return p
+
+
+def sim_prefix_bam(demo, tmp_path, env):
+    """BAM-config input (-i): the reference's BAM reader, ReadBuffer::flush (here: the batched binding), discordant-pair
+    discovery and BreakDancer-like clusters feeding multi-region far-end searches."""
+    fa = tmp_path / "sim_prefix.fa"
+    fa.write_bytes(gzip.open(os.path.join(GOLD, "sim_prefix.fa.gz")).read())
+    shutil.copy(os.path.join(GOLD, "sim_prefix.fa.fai"), tmp_path / "sim_prefix.fa.fai")
+    shutil.copy(os.path.join(GOLD, "sim_prefix.bam"), tmp_path / "sim_prefix.bam")
+    (tmp_path / "sim_prefix.bam.bai").write_bytes(b"BAI\x01\x00\x00\x00\x00")
+    (tmp_path / "conf.txt").write_text("%s\t500\tSIM1CHRVS2\n" % (tmp_path / "sim_prefix.bam"))
+    p = _run(demo, ["-f", str(fa), "-i", str(tmp_path / "conf.txt"), "-o", str(tmp_path / "sim_prefix.out"), "-k", "-s", "-l", "-T", "1"], env)
+    _compare(tmp_path, "sim_prefix.out", "sim_prefix", ("D", "SI", "INV", "TD", "LI", "BP", "RP", "CloseEndMapped"))
+    return p

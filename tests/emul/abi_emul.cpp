@@ -1,0 +1,154 @@
+// tests/emul/abi_emul.cpp -- TEST INFRASTRUCTURE ONLY.
+//
+// The entry points of include/pindel_pg.h that the drop-in bridge (oracle/ref_gpu_bridge.cpp) binds, served by the CPU
+// emulators of the device programs (pg_emul.cpp: the warp program of pg_warp.cuh on 32 fibers; sv_emul.cpp: pg_sv.cuh as
+// plain C++).  It exists so the *host logic* of the bridge -- marshalling of SPLIT_READs, replay of the classification
+// records, the reporter calls -- can be exercised in the GPU-less container (`pytest -m "not gpu"`), by linking the very
+// same bridge object against this library instead of libpindel_pg.so (oracle/_ref/pindel_emul_demo).  It is not a
+// fallback of the product: libpindel_pg.so contains no host implementation and nothing in pindel_b200/ loads this file.
+#include <stdint.h>
+#include <string.h>
+#include <algorithm>
+#include <string>
+#include <vector>
+
+#include "pg_emul.cpp"
+#include "sv_emul.cpp"
+#include "../../pindel_b200/csrc/pg_host_helpers.h"
+
+struct pg_ctx {
+   pg_settings st;
+   std::string err;
+   std::vector<std::string> chr;
+   std::vector<uint8_t> params;
+   uint32_t table[PG_TABLE];
+   std::vector<pg_read_out> out;
+   std::vector<pg_run> runs;
+   uint64_t launches = 0, sv_launches = 0;
+};
+
+static std::string g_create_error;
+
+static int fail(pg_ctx *c, int code, const char *msg)
+{
+   if (c) c->err = msg;
+   return code;
+}
+
+extern "C" {
+
+void pg_default_settings(pg_settings *s)
+{
+   memset(s, 0, sizeof *s);
+   s->seq_error_rate = 0.01;
+   s->sensitivity = 0.95;
+   s->max_mismatch_rate = 0.02;
+   s->additional_mismatch = 1;
+   s->min_close = 8;
+   s->min_perfect_match = 3;
+   s->max_range_index = 2;
+}
+
+const char *pg_create_error(void) { return g_create_error.c_str(); }
+const char *pg_last_error(pg_ctx *ctx) { return ctx ? ctx->err.c_str() : "null context"; }
+
+pg_ctx *pg_create(const pg_settings *s)
+{
+   pg_ctx *c = new pg_ctx;
+   c->st = *s;
+   c->params.resize(sizeof(PgParams));
+   if (pgemu_make_params(c->params.data(), s->seq_error_rate, s->sensitivity, s->max_mismatch_rate, s->additional_mismatch,
+                         s->min_close, s->min_perfect_match, s->max_range_index) != 0) {
+      g_create_error = "bad settings";
+      delete c;
+      return NULL;
+   }
+   pg_prob_table(0.001 + s->seq_error_rate, s->sensitivity, c->table);
+   return c;
+}
+
+void pg_destroy(pg_ctx *ctx) { delete ctx; }
+
+int pg_max_mismatch_table(pg_ctx *ctx, uint32_t *out)
+{
+   memcpy(out, ctx->table, sizeof(uint32_t) * PG_TABLE);
+   return PG_OK;
+}
+
+int pg_set_reference(pg_ctx *ctx, int32_t n_chr, const char *const *seq, const uint32_t *len)
+{
+   ctx->chr.clear();
+   for (int i = 0; i < n_chr; i++) ctx->chr.push_back(std::string(seq[i], len[i]));
+   return PG_OK;
+}
+
+static int run(pg_ctx *ctx, const pg_reads *in, pg_results *res, int mode)
+{
+   if (ctx->chr.empty()) return fail(ctx, PG_ERR_STATE, "no reference");
+   const int n = in->n;
+   std::vector<const char *> ptr;
+   std::vector<uint32_t> len;
+   for (size_t i = 0; i < ctx->chr.size(); i++) {
+      ptr.push_back(ctx->chr[i].data());
+      len.push_back((uint32_t)ctx->chr[i].size());
+   }
+   ctx->out.assign((size_t)n, pg_read_out());
+   for (uint32_t cap = (uint32_t)n * 16 + 1024;; cap *= 4) {
+      ctx->runs.assign(cap, pg_run());
+      uint32_t used = 0;
+      const int of = pgemu_search((int)ptr.size(), ptr.data(), len.data(), ctx->params.data(), n, mode, (const uint8_t *)in->seq_blob,
+                                  in->seq_off, (const uint8_t *)in->matched_d, in->matched_rel_pos, in->insert_size, in->chr_id,
+                                  in->close_info, in->regions, in->region_off, ctx->out.data(), ctx->runs.data(), cap, &used);
+      if (!of) {
+         ctx->runs.resize(used);
+         break;
+      }
+   }
+   ctx->launches++;
+   return pg_download(ctx, res);
+}
+
+int pg_download(pg_ctx *ctx, pg_results *res)
+{
+   res->n_runs = (uint32_t)ctx->runs.size();
+   if (res->n_runs > res->runs_cap) return fail(ctx, PG_ERR_RUNS_CAP, "run buffer too small");
+   if (!ctx->out.empty()) memcpy(res->out, ctx->out.data(), sizeof(pg_read_out) * ctx->out.size());
+   if (!ctx->runs.empty()) memcpy(res->runs, ctx->runs.data(), sizeof(pg_run) * ctx->runs.size());
+   return PG_OK;
+}
+
+int pg_close_end(pg_ctx *ctx, const pg_reads *in, pg_results *res) { return run(ctx, in, res, 1); }
+int pg_far_end(pg_ctx *ctx, const pg_reads *in, pg_results *res) { return run(ctx, in, res, 2); }
+int pg_search(pg_ctx *ctx, const pg_reads *in, pg_results *res) { return run(ctx, in, res, 3); }
+uint64_t pg_kernel_launches(pg_ctx *ctx) { return ctx ? ctx->launches : 0; }
+
+int pg_classify(pg_ctx *ctx, const pg_sv_reads *in, const pg_sv_window *win, pg_sv_results *res)
+{
+   res->n_records = 0;
+   if (in->n_reads == 0) return PG_OK;
+   const uint32_t w[11] = {win->driver_mask, 0, win->window_end, win->num_boxes, win->box_size, win->region_start_defined,
+                           win->region_start, win->region_end_defined, win->region_end, (uint32_t)win->min_inversion_size,
+                           (uint32_t)win->min_matched_bases};
+   const std::string &c = ctx->chr[(size_t)win->chr];
+   std::vector<PgSvRecord> rec((size_t)in->n_reads * 4 + 1024);
+   const int64_t k = svemu_classify(c.data(), (uint32_t)c.size(), ctx->st.seq_error_rate, ctx->st.sensitivity, w, in->n_reads, in->seq_blob,
+                                    in->seq_off, in->matched_d, in->insert_size, in->rflags, in->run_off, in->n_close_runs,
+                                    (const PgRun *)in->runs, rec.data(), (uint32_t)rec.size());
+   ctx->sv_launches++;
+   res->n_records = (uint32_t)k;
+   if (res->n_records > res->records_cap) return fail(ctx, PG_ERR_RUNS_CAP, "record buffer too small");
+   memcpy(res->records, rec.data(), sizeof(pg_sv_record) * (size_t)k);
+   std::sort(res->records, res->records + k, [](const pg_sv_record &a, const pg_sv_record &b) {
+      if (a.driver != b.driver) return a.driver < b.driver;
+      if (a.read != b.read) return a.read < b.read;
+      return a.seq < b.seq;
+   });
+   return PG_OK;
+}
+
+uint64_t pg_classify_launches(pg_ctx *ctx) { return ctx ? ctx->sv_launches : 0; }
+double pg_classify_last_kernel_ms(pg_ctx *) { return 0.0; }
+uint32_t pg_expand_runs(const pg_run *runs, uint32_t n_runs, pg_up *out) { return pgh_expand_runs(runs, n_runs, out); }
+uint32_t pg_clean_unique_points(pg_up *ups, uint32_t n) { return pgh_clean_unique_points(ups, n); }
+uint32_t pg_compress_ups(const pg_up *ups, uint32_t n, pg_run *out) { return pgh_compress_ups(ups, n, out); }
+}

@@ -1,0 +1,25 @@
+"""CPU test of the drop-in bridge's host logic (oracle/ref_gpu_bridge.cpp): the same bridge object, linked against the
+CPU emulators of the device programs (tests/emul/abi_emul.cpp -> oracle/_ref/pindel_emul_demo) instead of
+libpindel_pg.so, must reproduce the reference's output files.  What this covers without a GPU: marshalling of
+SPLIT_READs into the ABI's SoA batches, the batched ReadBuffer::flush / ReadInRead bindings, replay of the classification
+records per driver (Vars[box], FutureReads_SR, SPLIT_READ fields) and the hand-over to the reference's reporter.  The
+GPU run of the same scenarios is tests/test_gpu_dropin.py."""
+import os
+
+import pytest
+
+from tests import dropin_scenarios as D
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+DEMO = os.path.join(ROOT, "oracle", "_ref", "pindel_emul_demo")
+
+pytestmark = pytest.mark.skipif(not os.path.exists(DEMO), reason="oracle/_ref/pindel_emul_demo not built (needs /root/reference at build time)")
+
+
+def test_text_input_scenario(tmp_path):
+    p = D.colo_slice(DEMO, tmp_path, dict(os.environ), unbatched_too=False)
+    assert "(1 launches)" in p.stderr.splitlines()[-1]
+
+
+def test_bam_input_scenario(tmp_path):
+    D.sim_prefix_bam(DEMO, tmp_path, dict(os.environ))
