@@ -93,6 +93,8 @@ struct PgSvEnv {
    PgSvRecord *records;
    uint32_t records_cap;
    uint32_t *counters;
+   uint8_t *counts;         // optional [PG_SV_NDRIVERS * n_reads], driver-major: records of (driver, read); zeroed by the caller
+   uint32_t n_reads;
 };
 
 PGSV_HD uint32_t pg_sv_alloc(uint32_t *ctr)
@@ -405,33 +407,101 @@ PGSV_HD bool pg_sv_pair_ok(const PgSvParams &P, const PgSvRead &r, int arm, cons
    }
 }
 
-// The pair enumerator shared by D, SI, TD and INV: mismatch budget e outermost, then close points, then far points.
+// The pair enumerator shared by D, SI, TD and INV.  The reference nests four loops -- mismatch budget e, close points,
+// far points, with the arm's test innermost -- and fires every passing pair until one of them takes the read.  Two facts
+// make that cheap on run-length coded lists:
+//   * inside a (close run, far run) pair the arm's test pins the far member: j = K + m * idx is linear in the close
+//     member's index idx (length sum == ReadLength for D/TD/INV, adjacent positions for SI), so the close members that
+//     have a far partner at all form one interval of the close run;
+//   * a fire does not depend on e or on earlier fires, and a pair with c.mm + f.mm = s passes at every e >= s.  Firing
+//     each pair once, at e == s, in the reference's order finds the same taking pair; when nothing takes the read the
+//     fields keep the values of the reference's very last fire, which is the last pair in (close, far) order -- fired
+//     once more at the end if it was not the last one fired.
+struct PgSvSpan {
+   int32_t lo, hi;   // close-run members, in iteration order, that have a partner in the far run (lo > hi: none)
+   int32_t k, m;     // partner of close member idx: j = k + m * idx
+};
+
+PGSV_HD PgSvSpan pg_sv_span(const PgSvRead &r, int arm, const PgRun &crun, const PgRun &frun, bool close_desc, int far_dir)
+{
+   PgSvSpan s;
+   int64_t K;
+   if (arm == PG_ARM_SI_PLUS || arm == PG_ARM_SI_MINUS) {
+      // want = c.loc + 1 (PLUS) or c.loc - 1 (MINUS), c.loc = abs_loc0 +/- idx; j = +/-(want - far abs_loc0), 32-bit wrap
+      const uint32_t want0 = arm == PG_ARM_SI_PLUS ? crun.abs_loc0 + 1u : crun.abs_loc0 - 1u;
+      K = (int64_t)(int32_t)(far_dir ? frun.abs_loc0 - want0 : want0 - frun.abs_loc0);
+      const int cs = (crun.dirstrand & 1) ? -1 : 1;
+      s.m = far_dir ? -cs : cs;
+   } else {
+      K = (int64_t)r.rl - (int64_t)crun.len0 - (int64_t)frun.len0;
+      s.m = -1;
+   }
+   const int64_t fc = frun.count, cc = crun.count;
+   int64_t a = s.m < 0 ? K - fc + 1 : -K, b = s.m < 0 ? K : fc - 1 - K;   // 0 <= K + m * idx <= fc - 1
+   if (a < 0) a = 0;
+   if (b > cc - 1) b = cc - 1;
+   if (K > 0x7FFF0000ll || K < -0x7FFF0000ll) b = a - 1;   // the 32-bit value wraps nowhere near a run member
+   s.k = (int32_t)K;
+   if (close_desc) {
+      s.lo = (int32_t)(cc - 1 - b);
+      s.hi = (int32_t)(cc - 1 - a);
+   } else {
+      s.lo = (int32_t)a;
+      s.hi = (int32_t)b;
+   }
+   return s;
+}
+
 PGSV_FN void pg_sv_pairs(const PgSvEnv &ev, PgSvRead &r, int driver, int arm, bool close_desc, bool far_desc, int far_dir)
 {
    const PgRun &last_close = r.cr[r.ncr - 1];
+   // the pair fired last, and the last pair in (close, far) order among those fired
+   int32_t lf_ci = -1, lf_cj = -1, lf_fi = -1, mx_ci = -1, mx_cj = -1, mx_fi = -1;
    for (int e = 0; e <= r.max_e && !r.used; e++) {
       for (int ci = 0; ci < r.ncr && !r.used; ci++) {
          const PgRun &crun = r.cr[close_desc ? r.ncr - 1 - ci : ci];
          if ((int)crun.mm > e || !pg_sv_close_kept(crun, last_close)) continue;
-         for (int cj = 0; cj < (int)crun.count && !r.used; cj++) {
-            const PgSvUP c = pg_sv_up(crun, close_desc ? (int)crun.count - 1 - cj : cj);
+         const int fmm = e - (int)crun.mm;   // pairs that pass for the first time at this e
+         for (int cur = 0; cur < (int)crun.count && !r.used;) {
+            int next = 0x7FFFFFFF;
+            for (int fi = 0; fi < r.nfr; fi++) {
+               const PgRun &frun = r.fr[far_desc ? r.nfr - 1 - fi : fi];
+               if ((int)frun.mm != fmm || (frun.dirstrand & 1) != far_dir) continue;
+               const PgSvSpan sp = pg_sv_span(r, arm, crun, frun, close_desc, far_dir);
+               if (sp.hi < cur || sp.hi < sp.lo) continue;
+               const int at = sp.lo > cur ? sp.lo : cur;
+               if (at < next) next = at;
+            }
+            if (next == 0x7FFFFFFF) break;
+            const int idx = close_desc ? (int)crun.count - 1 - next : next;
+            const PgSvUP c = pg_sv_up(crun, idx);
             for (int fi = 0; fi < r.nfr && !r.used; fi++) {
                const PgRun &frun = r.fr[far_desc ? r.nfr - 1 - fi : fi];
-               if ((int)frun.mm > e || (int)frun.mm + c.mm > e || (frun.dirstrand & 1) != far_dir) continue;
-               int32_t j; // the only member of this far run the arm can accept
-               if (arm == PG_ARM_SI_PLUS || arm == PG_ARM_SI_MINUS) {
-                  const uint32_t want = arm == PG_ARM_SI_PLUS ? c.loc + 1 : c.loc - 1;
-                  j = (int32_t)(far_dir ? frun.abs_loc0 - want : want - frun.abs_loc0);
-               } else {
-                  j = r.rl - c.len - (int32_t)frun.len0;
-               }
-               if (j < 0 || j >= (int32_t)frun.count) continue;
-               const PgSvUP f = pg_sv_up(frun, j);
+               if ((int)frun.mm != fmm || (frun.dirstrand & 1) != far_dir) continue;
+               const PgSvSpan sp = pg_sv_span(r, arm, crun, frun, close_desc, far_dir);
+               if (next < sp.lo || next > sp.hi) continue;
+               const PgSvUP f = pg_sv_up(frun, sp.k + sp.m * idx);
                if (!pg_sv_pair_ok(*ev.P, r, arm, c, f)) continue;
+               lf_ci = ci;
+               lf_cj = next;
+               lf_fi = fi;
+               if (ci > mx_ci || (ci == mx_ci && (next > mx_cj || (next == mx_cj && fi > mx_fi)))) {
+                  mx_ci = ci;
+                  mx_cj = next;
+                  mx_fi = fi;
+               }
                if (!pg_sv_fire(ev, r, driver, arm, c, f)) break;
             }
+            cur = next + 1;
          }
       }
+   }
+   if (!r.used && mx_ci >= 0 && (mx_ci != lf_ci || mx_cj != lf_cj || mx_fi != lf_fi)) {
+      const PgRun &crun = r.cr[close_desc ? r.ncr - 1 - mx_ci : mx_ci];
+      const PgRun &frun = r.fr[far_desc ? r.nfr - 1 - mx_fi : mx_fi];
+      const int idx = close_desc ? (int)crun.count - 1 - mx_cj : mx_cj;
+      const PgSvSpan sp = pg_sv_span(r, arm, crun, frun, close_desc, far_dir);
+      pg_sv_fire(ev, r, driver, arm, pg_sv_up(crun, idx), pg_sv_up(frun, sp.k + sp.m * idx));
    }
 }
 
@@ -598,5 +668,6 @@ PGSV_FN void pg_sv_classify_read(const PgSvEnv &ev, PgSvRead &r, bool other_chr)
       default: pg_sv_nt_driver(ev, r, d); break;
       }
       if (r.dirty) pg_sv_emit(ev, r, d, PG_SV_NONE, 0); // fields assigned, read not taken: the host still gets the values
+      if (ev.counts && r.seq_no) ev.counts[(size_t)d * ev.n_reads + r.index] = (uint8_t)r.seq_no;
    }
 }

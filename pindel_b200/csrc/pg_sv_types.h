@@ -83,4 +83,5 @@ struct PgSvBatch {
    PgSvRecord *records;
    uint32_t records_cap;
    uint32_t *counters;           // [4]: [0] records allocated, [1] overflow flag, [2] pair tests (statistics)
+   uint8_t *counts;              // [PG_SV_NDRIVERS * n_reads] records per (driver, read), driver-major; zeroed before the launch
 };

@@ -138,6 +138,8 @@ __global__ void __launch_bounds__(128) pg_sv_kernel(PgSvBatch b, const PgSvParam
    ev.records = b.records;
    ev.records_cap = b.records_cap;
    ev.counters = b.counters;
+   ev.counts = b.counts;
+   ev.n_reads = (uint32_t)b.n_reads;
    PgSvRead r;
    const uint32_t s0 = b.seq_off[i], s1 = b.seq_off[i + 1];
    r.seq = b.seq_blob + s0;
@@ -161,6 +163,102 @@ __global__ void __launch_bounds__(128) pg_sv_kernel(PgSvBatch b, const PgSvParam
    r.dirty = 0;
    r.seq_no = 0;
    pg_sv_classify_read(ev, r, (fl & PG_SVR_OTHERCHR) != 0);
+}
+
+// Record order.  pg_sv_kernel hands out pool slots in completion order; the host replays records per driver with reads
+// ascending, i.e. sorted by (driver, read, seq).  That position is an exclusive prefix sum over the per-(driver, read)
+// record counts the kernel leaves in `counts` (driver-major), so the order is restored on the device by a scan and one
+// gather instead of a host sort: pg_scan_reduce / pg_scan_blocks / pg_scan_apply (16 counts per thread, one 16-byte load
+// each), then pg_sv_order_kernel moves every record to offsets[driver * n + read] + seq.
+#define PG_SCAN_THREADS 256
+#define PG_SCAN_PER_BLOCK (PG_SCAN_THREADS * 16)
+
+__device__ __forceinline__ uint32_t pg_sum_bytes(uint32_t w) { return __dp4a(w, 0x01010101u, 0u); }
+
+__global__ void __launch_bounds__(PG_SCAN_THREADS) pg_scan_reduce(const uint4 *__restrict__ counts16, uint32_t n16, uint32_t *__restrict__ block_sums)
+{
+   __shared__ uint32_t warp_sums[PG_SCAN_THREADS / 32];
+   const uint32_t i = blockIdx.x * PG_SCAN_THREADS + threadIdx.x;
+   uint32_t s = 0;
+   if (i < n16) {
+      const uint4 v = counts16[i];
+      s = pg_sum_bytes(v.x) + pg_sum_bytes(v.y) + pg_sum_bytes(v.z) + pg_sum_bytes(v.w);
+   }
+   s = __reduce_add_sync(0xFFFFFFFFu, s);
+   if ((threadIdx.x & 31) == 0) warp_sums[threadIdx.x >> 5] = s;
+   __syncthreads();
+   if (threadIdx.x == 0) {
+      uint32_t t = 0;
+      for (int w = 0; w < PG_SCAN_THREADS / 32; w++) t += warp_sums[w];
+      block_sums[blockIdx.x] = t;
+   }
+}
+
+// exclusive scan of the block sums in place, one block; total -> block_sums[n_blocks]
+__global__ void __launch_bounds__(1024) pg_scan_blocks(uint32_t *block_sums, uint32_t n_blocks)
+{
+   __shared__ uint32_t warp_tot[32];
+   __shared__ uint32_t carry_s;
+   if (threadIdx.x == 0) carry_s = 0;
+   __syncthreads();
+   for (uint32_t base = 0; base < n_blocks; base += 1024) {
+      const uint32_t i = base + threadIdx.x;
+      const uint32_t v = i < n_blocks ? block_sums[i] : 0u;
+      uint32_t x = v;
+      for (int d = 1; d < 32; d <<= 1) {
+         const uint32_t y = __shfl_up_sync(0xFFFFFFFFu, x, d);
+         if ((int)(threadIdx.x & 31) >= d) x += y;
+      }
+      if ((threadIdx.x & 31) == 31) warp_tot[threadIdx.x >> 5] = x;
+      __syncthreads();
+      uint32_t before = carry_s;
+      for (uint32_t w = 0; w < (threadIdx.x >> 5); w++) before += warp_tot[w];
+      if (i < n_blocks) block_sums[i] = before + x - v;
+      __syncthreads();
+      if (threadIdx.x == 1023) carry_s = before + x;
+      __syncthreads();
+   }
+   if (threadIdx.x == 0) block_sums[n_blocks] = carry_s;
+}
+
+__global__ void __launch_bounds__(PG_SCAN_THREADS) pg_scan_apply(const uint4 *__restrict__ counts16, uint32_t n16, const uint32_t *__restrict__ block_sums,
+                                                                 uint32_t *__restrict__ offsets)
+{
+   __shared__ uint32_t warp_tot[PG_SCAN_THREADS / 32];
+   const uint32_t i = blockIdx.x * PG_SCAN_THREADS + threadIdx.x;
+   uint4 v = make_uint4(0, 0, 0, 0);
+   if (i < n16) v = counts16[i];
+   const uint32_t mine = pg_sum_bytes(v.x) + pg_sum_bytes(v.y) + pg_sum_bytes(v.z) + pg_sum_bytes(v.w);
+   uint32_t x = mine;
+   for (int d = 1; d < 32; d <<= 1) {
+      const uint32_t y = __shfl_up_sync(0xFFFFFFFFu, x, d);
+      if ((int)(threadIdx.x & 31) >= d) x += y;
+   }
+   if ((threadIdx.x & 31) == 31) warp_tot[threadIdx.x >> 5] = x;
+   __syncthreads();
+   uint32_t run = block_sums[blockIdx.x] + x - mine;
+   for (uint32_t w = 0; w < (threadIdx.x >> 5); w++) run += warp_tot[w];
+   if (i >= n16) return;
+   const uint32_t words[4] = {v.x, v.y, v.z, v.w};
+   uint4 *dst = reinterpret_cast<uint4 *>(offsets + (size_t)i * 16);
+#pragma unroll
+   for (int k = 0; k < 4; k++) {
+      uint4 o;
+      o.x = run; run += words[k] & 0xFFu;
+      o.y = run; run += (words[k] >> 8) & 0xFFu;
+      o.z = run; run += (words[k] >> 16) & 0xFFu;
+      o.w = run; run += words[k] >> 24;
+      dst[k] = o;
+   }
+}
+
+__global__ void __launch_bounds__(256) pg_sv_order_kernel(const PgSvRecord *__restrict__ pool, uint32_t n_records, const uint32_t *__restrict__ offsets,
+                                                          uint32_t n_reads, PgSvRecord *__restrict__ ordered)
+{
+   const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+   if (t >= n_records) return;
+   const PgSvRecord rec = pool[t];
+   ordered[offsets[(size_t)rec.driver * n_reads + rec.read] + rec.seq] = rec;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -197,7 +295,9 @@ struct pg_ctx {
    uint32_t last_runs = 0;
    uint64_t last_window_bases = 0, last_ups = 0;
    // SV classification (pg_classify)
-   DevBuf sv_seq, sv_off, sv_md, sv_isz, sv_flags, sv_runoff, sv_nclose, sv_runs, sv_records, sv_params, sv_counters;
+   DevBuf sv_seq, sv_off, sv_md, sv_isz, sv_flags, sv_runoff, sv_nclose, sv_runs, sv_records, sv_params, sv_counters, sv_counts, sv_offsets,
+      sv_blocksums, sv_ordered;
+   uint64_t sv_aux_launches = 0;    // scan + order kernels
    uint64_t sv_launches = 0;
    cudaEvent_t sv_ev0 = nullptr, sv_ev1 = nullptr;   // around the last pg_sv_kernel launch
    float sv_last_ms = 0.f;
@@ -349,7 +449,8 @@ void pg_destroy(pg_ctx *ctx)
                      &ctx->regions, &ctx->region_off, &ctx->out, &ctx->pool, &ctx->counters, &ctx->scratch};
    for (DevBuf *b : bufs) if (b->p) cudaFree(b->p);
    DevBuf *svbufs[] = {&ctx->sv_seq, &ctx->sv_off, &ctx->sv_md, &ctx->sv_isz, &ctx->sv_flags, &ctx->sv_runoff, &ctx->sv_nclose,
-                       &ctx->sv_runs, &ctx->sv_records, &ctx->sv_params, &ctx->sv_counters};
+                       &ctx->sv_runs, &ctx->sv_records, &ctx->sv_params, &ctx->sv_counters,
+                       &ctx->sv_counts, &ctx->sv_offsets, &ctx->sv_blocksums, &ctx->sv_ordered};
    for (DevBuf *b : svbufs) if (b->p) cudaFree(b->p);
    pipe_destroy(ctx->pipe);
    if (ctx->chroms_d) cudaFree(ctx->chroms_d);
@@ -835,7 +936,69 @@ void pg_host_free(void *p) { if (p) cudaFreeHost(p); }
 uint32_t pg_expand_runs(const pg_run *runs, uint32_t n_runs, pg_up *out) { return pgh_expand_runs(runs, n_runs, out); }
 uint32_t pg_clean_unique_points(pg_up *ups, uint32_t n) { return pgh_clean_unique_points(ups, n); }
 
-// ---- SV classification ------------------------------------------------------------------------------------------
+// ---- SV classification ----------------------------------------------------------------------------------------
+// The device part of the classification stage on inputs that are already resident: pg_sv_kernel into a record pool
+// (grown and repeated on overflow), the record order restored by scan + gather, one copy back.
+static int sv_classify_device(pg_ctx *ctx, PgSvBatch &b, pg_sv_results *res)
+{
+   cudaStream_t st = ctx->stream;
+   const int n = b.n_reads;
+   int rc;
+   // records: most reads fire at most once per driver and stop at the first accepted pair
+   size_t cap = (size_t)n + (size_t)n / 2 + 1024;
+   const size_t n_counts = (size_t)PG_SV_NDRIVERS * (size_t)n;
+   const uint32_t n16 = (uint32_t)((n_counts + 15) / 16);
+   const uint32_t n_blocks = (n16 + PG_SCAN_THREADS - 1) / PG_SCAN_THREADS;
+   if ((rc = ensure(ctx, ctx->sv_counters, sizeof(uint32_t) * 4)) != PG_OK) return rc;
+   if ((rc = ensure(ctx, ctx->sv_counts, (size_t)n16 * 16)) != PG_OK) return rc;
+   if ((rc = ensure(ctx, ctx->sv_offsets, sizeof(uint32_t) * (size_t)n16 * 16)) != PG_OK) return rc;
+   if ((rc = ensure(ctx, ctx->sv_blocksums, sizeof(uint32_t) * ((size_t)n_blocks + 1))) != PG_OK) return rc;
+   uint32_t counters[4];
+   if (!ctx->sv_ev0) { CU(cudaEventCreate(&ctx->sv_ev0)); CU(cudaEventCreate(&ctx->sv_ev1)); }
+   for (int attempt = 0;; attempt++) {
+      if ((rc = ensure(ctx, ctx->sv_records, sizeof(PgSvRecord) * cap)) != PG_OK) return rc;
+      CU(cudaEventRecord(ctx->sv_ev0, st));
+      CU(cudaMemsetAsync(ctx->sv_counters.p, 0, sizeof(uint32_t) * 4, st));
+      CU(cudaMemsetAsync(ctx->sv_counts.p, 0, (size_t)n16 * 16, st));
+      b.records = (PgSvRecord *)ctx->sv_records.p;
+      b.records_cap = (uint32_t)cap;
+      b.counters = (uint32_t *)ctx->sv_counters.p;
+      b.counts = (uint8_t *)ctx->sv_counts.p;
+      pg_sv_kernel<<<(n + 127) / 128, 128, 0, st>>>(b, (const PgSvParams *)ctx->sv_params.p, ctx->prm_d, ctx->chroms_d);
+      CU(cudaGetLastError());
+      ctx->sv_launches++;
+      pg_scan_reduce<<<n_blocks, PG_SCAN_THREADS, 0, st>>>((const uint4 *)ctx->sv_counts.p, n16, (uint32_t *)ctx->sv_blocksums.p);
+      pg_scan_blocks<<<1, 1024, 0, st>>>((uint32_t *)ctx->sv_blocksums.p, n_blocks);
+      pg_scan_apply<<<n_blocks, PG_SCAN_THREADS, 0, st>>>((const uint4 *)ctx->sv_counts.p, n16, (const uint32_t *)ctx->sv_blocksums.p,
+                                                          (uint32_t *)ctx->sv_offsets.p);
+      CU(cudaGetLastError());
+      CU(cudaMemcpyAsync(counters, ctx->sv_counters.p, sizeof counters, cudaMemcpyDeviceToHost, st));
+      CU(cudaStreamSynchronize(st));
+      if (counters[0] <= cap) break;
+      if (attempt >= 4) return fail(ctx, PG_ERR_CUDA, "pg_classify: record pool keeps overflowing");
+      cap = (size_t)counters[0] + 1024;
+   }
+   res->n_records = counters[0];
+   if (counters[0]) {
+      if ((rc = ensure(ctx, ctx->sv_ordered, sizeof(PgSvRecord) * (size_t)counters[0])) != PG_OK) return rc;
+      pg_sv_order_kernel<<<(counters[0] + 255) / 256, 256, 0, st>>>((const PgSvRecord *)ctx->sv_records.p, counters[0],
+                                                                    (const uint32_t *)ctx->sv_offsets.p, (uint32_t)n,
+                                                                    (PgSvRecord *)ctx->sv_ordered.p);
+      CU(cudaGetLastError());
+      ctx->sv_aux_launches += 4;
+   }
+   CU(cudaEventRecord(ctx->sv_ev1, st));
+   CU(cudaStreamSynchronize(st));
+   CU(cudaEventElapsedTime(&ctx->sv_last_ms, ctx->sv_ev0, ctx->sv_ev1));
+   if (counters[0] > res->records_cap || (counters[0] && !res->records))
+      return fail(ctx, PG_ERR_RUNS_CAP, "pg_classify: record buffer too small (n_records holds the required size)");
+   if (counters[0]) {
+      CU(cudaMemcpyAsync(res->records, ctx->sv_ordered.p, sizeof(PgSvRecord) * (size_t)counters[0], cudaMemcpyDeviceToHost, st));
+      CU(cudaStreamSynchronize(st));
+   }
+   return PG_OK;
+}
+
 static_assert(sizeof(pg_sv_record) == sizeof(PgSvRecord) && sizeof(pg_sv_record) == 44, "sv record layout");
 
 int pg_classify(pg_ctx *ctx, const pg_sv_reads *in, const pg_sv_window *win, pg_sv_results *res)
@@ -885,7 +1048,6 @@ int pg_classify(pg_ctx *ctx, const pg_sv_reads *in, const pg_sv_window *win, pg_
    if ((rc = ensure(ctx, ctx->sv_nclose, sizeof(uint16_t) * (size_t)n)) != PG_OK) return rc;
    if ((rc = ensure(ctx, ctx->sv_runs, sizeof(PgRun) * (size_t)(n_runs + 1))) != PG_OK) return rc;
    if ((rc = ensure(ctx, ctx->sv_params, sizeof(PgSvParams))) != PG_OK) return rc;
-   if ((rc = ensure(ctx, ctx->sv_counters, sizeof(uint32_t) * 4)) != PG_OK) return rc;
    CU(cudaMemcpyAsync(ctx->sv_seq.p, in->seq_blob, seq_bytes, cudaMemcpyHostToDevice, st));
    CU(cudaMemcpyAsync(ctx->sv_off.p, in->seq_off, sizeof(uint32_t) * (size_t)(n + 1), cudaMemcpyHostToDevice, st));
    CU(cudaMemcpyAsync(ctx->sv_md.p, in->matched_d, (size_t)n, cudaMemcpyHostToDevice, st));
@@ -895,52 +1057,18 @@ int pg_classify(pg_ctx *ctx, const pg_sv_reads *in, const pg_sv_window *win, pg_
    CU(cudaMemcpyAsync(ctx->sv_nclose.p, in->n_close_runs, sizeof(uint16_t) * (size_t)n, cudaMemcpyHostToDevice, st));
    if (n_runs) CU(cudaMemcpyAsync(ctx->sv_runs.p, in->runs, sizeof(PgRun) * (size_t)n_runs, cudaMemcpyHostToDevice, st));
    CU(cudaMemcpyAsync(ctx->sv_params.p, &P, sizeof P, cudaMemcpyHostToDevice, st));
-   // records: most reads fire at most once per driver and stop at the first accepted pair; grow and repeat on overflow
-   size_t cap = (size_t)n + (size_t)n / 2 + 1024;
-   uint32_t counters[4];
-   for (int attempt = 0;; attempt++) {
-      if ((rc = ensure(ctx, ctx->sv_records, sizeof(PgSvRecord) * cap)) != PG_OK) return rc;
-      CU(cudaMemsetAsync(ctx->sv_counters.p, 0, sizeof(uint32_t) * 4, st));
-      PgSvBatch b;
-      b.n_reads = n;
-      b.seq_blob = (const uint8_t *)ctx->sv_seq.p;
-      b.seq_off = (const uint32_t *)ctx->sv_off.p;
-      b.matched_d = (const uint8_t *)ctx->sv_md.p;
-      b.insert_size = (const int16_t *)ctx->sv_isz.p;
-      b.rflags = (const uint8_t *)ctx->sv_flags.p;
-      b.run_off = (const uint32_t *)ctx->sv_runoff.p;
-      b.n_close_runs = (const uint16_t *)ctx->sv_nclose.p;
-      b.runs = (const PgRun *)ctx->sv_runs.p;
-      b.records = (PgSvRecord *)ctx->sv_records.p;
-      b.records_cap = (uint32_t)cap;
-      b.counters = (uint32_t *)ctx->sv_counters.p;
-      if (!ctx->sv_ev0) { CU(cudaEventCreate(&ctx->sv_ev0)); CU(cudaEventCreate(&ctx->sv_ev1)); }
-      CU(cudaEventRecord(ctx->sv_ev0, st));
-      pg_sv_kernel<<<(n + 127) / 128, 128, 0, st>>>(b, (const PgSvParams *)ctx->sv_params.p, ctx->prm_d, ctx->chroms_d);
-      CU(cudaGetLastError());
-      CU(cudaEventRecord(ctx->sv_ev1, st));
-      ctx->sv_launches++;
-      CU(cudaMemcpyAsync(counters, ctx->sv_counters.p, sizeof counters, cudaMemcpyDeviceToHost, st));
-      CU(cudaStreamSynchronize(st));
-      CU(cudaEventElapsedTime(&ctx->sv_last_ms, ctx->sv_ev0, ctx->sv_ev1));
-      if (counters[0] <= cap) break;
-      if (attempt >= 4) return fail(ctx, PG_ERR_CUDA, "pg_classify: record pool keeps overflowing");
-      cap = (size_t)counters[0] + 1024;
-   }
-   res->n_records = counters[0];
-   if (counters[0] > res->records_cap || (counters[0] && !res->records))
-      return fail(ctx, PG_ERR_RUNS_CAP, "pg_classify: record buffer too small (n_records holds the required size)");
-   if (counters[0]) {
-      CU(cudaMemcpyAsync(res->records, ctx->sv_records.p, sizeof(PgSvRecord) * (size_t)counters[0], cudaMemcpyDeviceToHost, st));
-      CU(cudaStreamSynchronize(st));
-      // pool slots are handed out in completion order; the host replays per driver, reads ascending
-      std::sort(res->records, res->records + counters[0], [](const pg_sv_record &a, const pg_sv_record &b) {
-         if (a.driver != b.driver) return a.driver < b.driver;
-         if (a.read != b.read) return a.read < b.read;
-         return a.seq < b.seq;
-      });
-   }
-   return PG_OK;
+   PgSvBatch b;
+   memset(&b, 0, sizeof b);
+   b.n_reads = n;
+   b.seq_blob = (const uint8_t *)ctx->sv_seq.p;
+   b.seq_off = (const uint32_t *)ctx->sv_off.p;
+   b.matched_d = (const uint8_t *)ctx->sv_md.p;
+   b.insert_size = (const int16_t *)ctx->sv_isz.p;
+   b.rflags = (const uint8_t *)ctx->sv_flags.p;
+   b.run_off = (const uint32_t *)ctx->sv_runoff.p;
+   b.n_close_runs = (const uint16_t *)ctx->sv_nclose.p;
+   b.runs = (const PgRun *)ctx->sv_runs.p;
+   return sv_classify_device(ctx, b, res);
 }
 
 uint64_t pg_classify_launches(pg_ctx *ctx) { return ctx ? ctx->sv_launches : 0; }

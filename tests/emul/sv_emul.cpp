@@ -49,6 +49,8 @@ int64_t svemu_classify(const char *chr, uint32_t chr_len, double seq_error_rate,
    ev.records = records;
    ev.records_cap = cap;
    ev.counters = counters;
+   ev.counts = NULL;
+   ev.n_reads = (uint32_t)n;
    for (int i = 0; i < n; i++) {
       PgSvRead r;
       memset(&r, 0, sizeof r);
