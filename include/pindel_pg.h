@@ -249,6 +249,19 @@ typedef struct pg_sv_results {
 } pg_sv_results;
 
 int pg_classify(pg_ctx *ctx, const pg_sv_reads *in, const pg_sv_window *win, pg_sv_results *res);
+/* The same on the batch that is still resident on the device after a far-end launch -- pg_far_end / pg_search on a batch
+ * small enough for one launch (< 2 M reads), or pg_upload + pg_launch(2 or 3) + pg_download: sequences, anchors and the
+ * launch's own run lists are used where they lie, nothing is uploaded again.  This is how a host chains the two seams of
+ * one window: SearchFarEnds (src/pindel.cpp:1888) -> SearchSVs (src/pindel.cpp:1140).  ReadIndex in the records is the
+ * index in that batch.
+ *   after pg_launch(2) / pg_far_end: the sequences given to the launch are final (GetCloseEnd already ran); the reads'
+ *       UP_Close lists come from the caller as runs (close_run_off [n+1], close_runs; raw or cleaned);
+ *   after pg_launch(3) / pg_search: the launch's close runs are used and GetCloseEnd's flips are applied on the device;
+ *       close_run_off / close_runs are ignored.
+ * The batch must carry matched_d and insert_size.  rflags: [n] PG_SVR_USED per read, or NULL; FragName != FarFragName is
+ * derived from the far end's chromosome (UpdateFarFragName, src/pindel.cpp:1262-1270). */
+int pg_classify_resident(pg_ctx *ctx, const pg_sv_window *win, const uint8_t *rflags, const uint32_t *close_run_off,
+                         const pg_run *close_runs, pg_sv_results *res);
 uint64_t pg_classify_launches(pg_ctx *ctx);   /* classification-kernel launches since pg_create */
 double pg_classify_last_kernel_ms(pg_ctx *ctx); /* CUDA-event duration of the last classification kernel */
 

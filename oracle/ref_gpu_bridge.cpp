@@ -58,7 +58,9 @@ extern short g_MinClose;
 namespace {
 pg_ctx *g_ctx = NULL;
 std::mutex g_mutex;
-unsigned long g_close_calls = 0, g_far_reads = 0, g_sv_reads = 0, g_sv_records = 0;
+unsigned long g_close_calls = 0, g_far_reads = 0, g_sv_reads = 0, g_sv_records = 0, g_sv_resident = 0;
+const SPLIT_READ *g_farResidentBase = NULL;   /* Reads_SR of the last SearchFarEnds call, still resident on the device */
+size_t g_farResidentN = 0;
 
 void die(const char *what)
 {
@@ -288,11 +290,17 @@ void SearchFarEnds(const std::string &chromosomeSeq, std::vector<SPLIT_READ> &re
    std::vector<int32_t> chr(n);
    std::vector<pg_close_info> ci(n);
    std::vector<pg_region> regions;
+   std::vector<char> md(n);
+   std::vector<uint32_t> pos(n);
+   std::vector<int16_t> isz(n);
+   bool staleFarEnd = false;   /* a read that is skipped here but carries an older UP_Far: the device copy would lack it */
    for (int i = 0; i < n; i++) {
       const SPLIT_READ &r = reads[i];
       blob += r.getUnmatchedSeq();
       off[i + 1] = (uint32_t)blob.size();
       chr[i] = g_genome.getChrID(r.FragName);
+      md[i] = r.MatchedD; pos[i] = r.MatchedRelPos; isz[i] = r.InsertSize;   /* not used by the far-end search; the drivers need them */
+      if ((r.MapperSplit || r.UP_Close.empty()) && !r.UP_Far.empty()) staleFarEnd = true;
       ci[i].pad = 0;
       if (r.MapperSplit || r.UP_Close.empty()) { ci[i].max_len = 0; ci[i].last_abs_loc = 0; }   /* src/pindel.cpp:1129 */
       else {
@@ -313,6 +321,7 @@ void SearchFarEnds(const std::string &chromosomeSeq, std::vector<SPLIT_READ> &re
    pg_reads in;
    memset(&in, 0, sizeof(in));
    in.n = n; in.seq_blob = blob.c_str(); in.seq_off = &off[0]; in.chr_id = n ? &chr[0] : NULL; in.close_info = n ? &ci[0] : NULL;
+   in.matched_d = n ? &md[0] : NULL; in.matched_rel_pos = n ? &pos[0] : NULL; in.insert_size = n ? &isz[0] : NULL;
    if (!regions.empty()) { in.regions = &regions[0]; in.region_off = &region_off[0]; }
    std::vector<pg_read_out> out(n ? n : 1);
    std::vector<pg_run> runs((size_t)n * 16 + 1024);
@@ -331,6 +340,9 @@ void SearchFarEnds(const std::string &chromosomeSeq, std::vector<SPLIT_READ> &re
       appendRuns(reads[i].UP_Far, &runs[out[i].run_off + out[i].n_close_runs], out[i].n_far_runs);
       g_far_reads++;
    }
+   /* the batch stays on the device: the first SV driver of this window classifies it there (pg_classify_resident) */
+   g_farResidentBase = (n && !staleFarEnd) ? &reads[0] : NULL;
+   g_farResidentN = (size_t)n;
    *logStream << "Far end searching completed for this window." << std::endl;   /* src/pindel.cpp:1137 */
 }
 
@@ -374,42 +386,6 @@ void classifyWindow(ControlState &cs, unsigned NumBoxes, const SearchWindow &win
    ensureContext();
    std::vector<SPLIT_READ> &reads = cs.Reads_SR;
    const int n = (int)reads.size();
-   std::string blob;
-   std::vector<uint32_t> off(n + 1, 0), runOff(n + 1, 0);
-   std::vector<uint8_t> md(n), flags(n);
-   std::vector<int16_t> isz(n);
-   std::vector<uint16_t> nClose(n);
-   std::vector<pg_run> runs;
-   std::vector<pg_up> ups;
-   for (int i = 0; i < n; i++) {
-      const SPLIT_READ &r = reads[i];
-      blob += r.getUnmatchedSeq();
-      off[i + 1] = (uint32_t)blob.size();
-      md[i] = (uint8_t)r.MatchedD;
-      isz[i] = r.InsertSize;
-      flags[i] = (uint8_t)((r.Used ? PG_SVR_USED : 0u) | (r.FragName != r.FarFragName ? PG_SVR_OTHERCHR : 0u));
-      for (int list = 0; list < 2; list++) {
-         ups.clear();
-         pushUps(ups, list == 0 ? r.UP_Close : r.UP_Far);
-         const uint32_t k = pg_compress_ups(ups.empty() ? NULL : &ups[0], (uint32_t)ups.size(), NULL);
-         const size_t at = runs.size();
-         runs.resize(at + k);
-         if (k) pg_compress_ups(&ups[0], (uint32_t)ups.size(), &runs[at]);
-         if (list == 0) nClose[i] = (uint16_t)k;
-      }
-      runOff[i + 1] = (uint32_t)runs.size();
-   }
-   pg_sv_reads in;
-   memset(&in, 0, sizeof in);
-   in.n_reads = n;
-   in.seq_blob = (const uint8_t *)blob.c_str();
-   in.seq_off = &off[0];
-   in.matched_d = n ? &md[0] : NULL;
-   in.insert_size = n ? &isz[0] : NULL;
-   in.rflags = n ? &flags[0] : NULL;
-   in.run_off = &runOff[0];
-   in.n_close_runs = n ? &nClose[0] : NULL;
-   in.runs = runs.empty() ? NULL : &runs[0];
    pg_sv_window w;
    memset(&w, 0, sizeof w);
    w.driver_mask = mask;
@@ -429,12 +405,80 @@ void classifyWindow(ControlState &cs, unsigned NumBoxes, const SearchWindow &win
    res.records = &g_sv.records[0];
    res.records_cap = (uint32_t)g_sv.records.size();
    res.n_records = 0;
-   int rc = pg_classify(g_ctx, &in, &w, &res);
-   if (rc == PG_ERR_RUNS_CAP) {
-      g_sv.records.resize(res.n_records);
-      res.records = &g_sv.records[0];
-      res.records_cap = res.n_records;
-      rc = pg_classify(g_ctx, &in, &w, &res);
+   int rc = PG_ERR_STATE;
+   const bool resident = n > 0 && g_farResidentBase == &reads[0] && g_farResidentN == (size_t)n && getenv("PG_BRIDGE_NO_RESIDENT") == NULL;
+   std::vector<uint8_t> flags(n);
+   for (int i = 0; i < n; i++)
+      flags[i] = (uint8_t)((reads[i].Used ? PG_SVR_USED : 0u) | (reads[i].FragName != reads[i].FarFragName ? PG_SVR_OTHERCHR : 0u));
+   if (resident) {
+      /* the window's reads, their anchors and their UP_Far lists are still on the device from SearchFarEnds: send only the
+         UP_Close lists (run-length coded) and the Used flags */
+      std::vector<uint32_t> closeOff(n + 1, 0);
+      std::vector<pg_run> closeRuns;
+      std::vector<pg_up> ups;
+      std::vector<uint8_t> used(n);
+      for (int i = 0; i < n; i++) {
+         ups.clear();
+         pushUps(ups, reads[i].UP_Close);
+         const uint32_t k = pg_compress_ups(ups.empty() ? NULL : &ups[0], (uint32_t)ups.size(), NULL);
+         const size_t at = closeRuns.size();
+         closeRuns.resize(at + k);
+         if (k) pg_compress_ups(&ups[0], (uint32_t)ups.size(), &closeRuns[at]);
+         closeOff[i + 1] = (uint32_t)closeRuns.size();
+         used[i] = (uint8_t)(flags[i] & PG_SVR_USED);
+      }
+      for (int attempt = 0; attempt < 2; attempt++) {
+         rc = pg_classify_resident(g_ctx, &w, &used[0], &closeOff[0], closeRuns.empty() ? NULL : &closeRuns[0], &res);
+         if (rc != PG_ERR_RUNS_CAP) break;
+         g_sv.records.resize(res.n_records);
+         res.records = &g_sv.records[0];
+         res.records_cap = res.n_records;
+      }
+      if (rc == PG_OK) g_sv_resident += (unsigned long)n;
+   }
+   if (rc == PG_ERR_STATE) {   /* nothing resident (other caller order, or a batch that went through the chunked path) */
+      std::string blob;
+      std::vector<uint32_t> off(n + 1, 0), runOff(n + 1, 0);
+      std::vector<uint8_t> md(n);
+      std::vector<int16_t> isz(n);
+      std::vector<uint16_t> nClose(n);
+      std::vector<pg_run> runs;
+      std::vector<pg_up> ups;
+      for (int i = 0; i < n; i++) {
+         const SPLIT_READ &r = reads[i];
+         blob += r.getUnmatchedSeq();
+         off[i + 1] = (uint32_t)blob.size();
+         md[i] = (uint8_t)r.MatchedD;
+         isz[i] = r.InsertSize;
+         for (int list = 0; list < 2; list++) {
+            ups.clear();
+            pushUps(ups, list == 0 ? r.UP_Close : r.UP_Far);
+            const uint32_t k = pg_compress_ups(ups.empty() ? NULL : &ups[0], (uint32_t)ups.size(), NULL);
+            const size_t at = runs.size();
+            runs.resize(at + k);
+            if (k) pg_compress_ups(&ups[0], (uint32_t)ups.size(), &runs[at]);
+            if (list == 0) nClose[i] = (uint16_t)k;
+         }
+         runOff[i + 1] = (uint32_t)runs.size();
+      }
+      pg_sv_reads in;
+      memset(&in, 0, sizeof in);
+      in.n_reads = n;
+      in.seq_blob = (const uint8_t *)blob.c_str();
+      in.seq_off = &off[0];
+      in.matched_d = n ? &md[0] : NULL;
+      in.insert_size = n ? &isz[0] : NULL;
+      in.rflags = n ? &flags[0] : NULL;
+      in.run_off = &runOff[0];
+      in.n_close_runs = n ? &nClose[0] : NULL;
+      in.runs = runs.empty() ? NULL : &runs[0];
+      for (int attempt = 0; attempt < 2; attempt++) {
+         rc = pg_classify(g_ctx, &in, &w, &res);
+         if (rc != PG_ERR_RUNS_CAP) break;
+         g_sv.records.resize(res.n_records);
+         res.records = &g_sv.records[0];
+         res.records_cap = res.n_records;
+      }
    }
    if (rc != PG_OK) die("pg_classify");
    g_sv.records.resize(res.n_records);
@@ -593,9 +637,9 @@ int searchInversionsNT(ControlState &currentState, unsigned NumBoxes, const Sear
 static void reportAtExit()
 {
    std::fprintf(stderr, "pindel_gpu_demo: %lu GetCloseEnd calls and %lu far-end reads served by libpindel_pg (%llu kernel launches); "
-                "%lu reads classified by the SV drivers on the device, %lu records (%llu launches)\n",
+                "%lu reads classified by the SV drivers on the device, %lu records (%llu launches), %lu of the reads without a second upload\n",
                 g_close_calls, g_far_reads, g_ctx ? (unsigned long long)pg_kernel_launches(g_ctx) : 0ull, g_sv_reads, g_sv_records,
-                g_ctx ? (unsigned long long)pg_classify_launches(g_ctx) : 0ull);
+                g_ctx ? (unsigned long long)pg_classify_launches(g_ctx) : 0ull, g_sv_resident);
 }
 
 int main(int argc, char *argv[])

@@ -89,6 +89,7 @@ def load_library() -> C.CDLL:
         lib.pg_sync.argtypes = [C.c_void_p]
         lib.pg_last_stats.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
         lib.pg_classify.argtypes = [C.c_void_p, C.POINTER(_SvReads), C.POINTER(_SvWindow), C.POINTER(_SvResults)]
+        lib.pg_classify_resident.argtypes = [C.c_void_p, C.POINTER(_SvWindow), C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(_SvResults)]
         lib.pg_classify_launches.restype = C.c_uint64
         lib.pg_classify_launches.argtypes = [C.c_void_p]
         lib.pg_classify_last_kernel_ms.restype = C.c_double
@@ -278,6 +279,29 @@ class PatternGrowth:
             res = _SvResults(rec.ctypes.data, rec.size, 0)
             rc = self.lib.pg_classify(self.ctx, C.byref(r), C.byref(w), C.byref(res))
         self._check(rc, "pg_classify")
+        return rec[:res.n_records]
+
+    def classify_resident(self, win: dict, rflags=None, close_run_off=None, close_runs=None, records=None) -> np.ndarray:
+        """pg_classify on the batch that is still on the device after search() / search_far_ends() / launch(2|3): nothing
+        but the window parameters (and, after a far-end-only launch, the reads' close runs) is uploaded."""
+        from . import sv
+        n = self._n
+        reg = win.get("region")
+        w = _SvWindow(win["driver_mask"], win.get("chr", 0), win["window_end"], win["num_boxes"], win["box_size"],
+                      0 if reg is None else 1, 0 if reg is None else reg[0], 0 if reg is None else 1, 0 if reg is None else reg[1],
+                      win["min_inversion_size"], win["min_matched_bases"], 0)
+        fl = None if rflags is None else np.ascontiguousarray(rflags, dtype=np.uint8)
+        co = None if close_run_off is None else np.ascontiguousarray(close_run_off, dtype=np.uint32)
+        cr = None if close_runs is None else np.ascontiguousarray(close_runs, dtype=R.RUN_DT)
+        ptr = lambda a: None if a is None else a.ctypes.data_as(C.c_void_p)
+        rec = np.empty(max(1024, 2 * n), dtype=sv.RECORD_DT) if records is None else records
+        res = _SvResults(rec.ctypes.data, rec.size, 0)
+        rc = self.lib.pg_classify_resident(self.ctx, C.byref(w), ptr(fl), ptr(co), ptr(cr), C.byref(res))
+        if rc == PG_ERR_RUNS_CAP:
+            rec = np.empty(res.n_records, dtype=sv.RECORD_DT)
+            res = _SvResults(rec.ctypes.data, rec.size, 0)
+            rc = self.lib.pg_classify_resident(self.ctx, C.byref(w), ptr(fl), ptr(co), ptr(cr), C.byref(res))
+        self._check(rc, "pg_classify_resident")
         return rec[:res.n_records]
 
     @property

@@ -247,21 +247,23 @@ PGSV_FN bool pg_sv_left_most_inv(const PgChrom &c, PgSvRead &r)
 
 // readTransgressesBinBoundaries / saveReadForNextCycle / readInSpecifiedRegion / the box test (src/pindel.cpp:561-592,
 // e.g. src/search_variant.cpp:147-166)
-PGSV_FN void pg_sv_tail(const PgSvEnv &ev, PgSvRead &r, int driver, bool check_bin)
+PGSV_FN void pg_sv_tail(const PgSvEnv &ev, PgSvRead &r, int driver, bool check_bin, int forced)
 {
    const PgSvParams &P = *ev.P;
-   if (check_bin && r.bp_right > P.window_end - (uint32_t)(2 * r.insert_size)) {
-      pg_sv_emit(ev, r, driver, PG_SV_FUTURE, 0);
-      r.used = true;
-      return;
+   int outcome = forced;   // PG_SV_BREAK from the caller, else decided here; PG_SV_NONE = nothing stored now
+   uint32_t box = 0;
+   if (outcome == PG_SV_NONE) {
+      if (check_bin && r.bp_right > P.window_end - (uint32_t)(2 * r.insert_size)) outcome = PG_SV_FUTURE;
+      else if (P.region_start_defined && r.bp_left + 1 < P.region_start) return;
+      else if (P.region_end_defined && r.bp_left + 1 > P.region_end) return;
+      else {
+         box = r.bp_left / P.box_size;
+         if (box >= P.num_boxes) return;
+         outcome = PG_SV_BOX;
+      }
    }
-   if (P.region_start_defined && r.bp_left + 1 < P.region_start) return;
-   if (P.region_end_defined && r.bp_left + 1 > P.region_end) return;
-   const uint32_t box = r.bp_left / P.box_size;
-   if (box < P.num_boxes) {
-      pg_sv_emit(ev, r, driver, PG_SV_BOX, box);
-      r.used = true;
-   }
+   pg_sv_emit(ev, r, driver, outcome, box);
+   r.used = true;
 }
 
 // arms of the pair drivers
@@ -348,6 +350,8 @@ PGSV_FN bool pg_sv_fire(const PgSvEnv &ev, PgSvRead &r, int driver, int arm, con
       r.bp_right = f.loc - 1 - SP;
       break;
    }
+   bool check_bin = true;
+   int forced = PG_SV_NONE;
    if (arm <= PG_ARM_SI_MINUS) {
       const bool plus = (arm == PG_ARM_D_PLUS || arm == PG_ARM_SI_PLUS);
       if (arm <= PG_ARM_D_MINUS) { // SearchDeletions::calculateIndelSize, getInsertedStr = ""
@@ -359,33 +363,29 @@ PGSV_FN bool pg_sv_fire(const PgSvEnv &ev, PgSvRead &r, int driver, int arm, con
       }
       uint32_t real_left = r.bp_left;
       if (ev.chrom.len < real_left || ev.chrom.len < r.bp_right) {
-         r.used = true;
-         pg_sv_emit(ev, r, driver, PG_SV_BREAK, 0);
-         return false;
+         forced = PG_SV_BREAK;   // Used = true, the far loop stops (src/search_variant.cpp:133-136)
+      } else {
+         real_left = r.nt_len ? pg_sv_slide_insertion(ev.chrom, r, r.bp_right) : pg_sv_slide_deletion(ev.chrom, real_left, r.bp_right);
+         int32_t diff = (int16_t)(r.bp_left - real_left);
+         if ((r.bp - 1) < diff) diff = r.bp - 1;
+         if (diff > 0) {
+            r.bp = (int16_t)(r.bp - diff);
+            r.bp_left -= (uint32_t)diff;
+            r.bp_right -= (uint32_t)diff;
+         }
       }
-      real_left = r.nt_len ? pg_sv_slide_insertion(ev.chrom, r, r.bp_right) : pg_sv_slide_deletion(ev.chrom, real_left, r.bp_right);
-      int32_t diff = (int16_t)(r.bp_left - real_left);
-      if ((r.bp - 1) < diff) diff = r.bp - 1;
-      if (diff > 0) {
-         r.bp = (int16_t)(r.bp - diff);
-         r.bp_left -= (uint32_t)diff;
-         r.bp_right -= (uint32_t)diff;
-      }
-      pg_sv_tail(ev, r, driver, true);
-      return true;
-   }
-   if (arm <= PG_ARM_TD_MINUS) {
+   } else if (arm <= PG_ARM_TD_MINUS) {
       if (r.bp_left == 0) return true; // src/search_tandem_duplications.cpp:88-90
       if (pg_sv_left_most_td(ev.chrom, r)) r.dirty |= PG_SVF_KILLED;
-      pg_sv_tail(ev, r, driver, true);
-      return true;
+   } else {
+      pg_sv_set_nt(r, PG_NT_EMPTY, 0, 0);
+      r.nt_size = 0;
+      r.dirty |= PG_SVF_NTSIZE;
+      if (pg_sv_left_most_inv(ev.chrom, r)) r.dirty |= PG_SVF_KILLED;
+      check_bin = arm <= PG_ARM_INV1; // the '-' arms have no bin test (src/search_inversions.cpp:199,251)
    }
-   pg_sv_set_nt(r, PG_NT_EMPTY, 0, 0);
-   r.nt_size = 0;
-   r.dirty |= PG_SVF_NTSIZE;
-   if (pg_sv_left_most_inv(ev.chrom, r)) r.dirty |= PG_SVF_KILLED;
-   pg_sv_tail(ev, r, driver, arm <= PG_ARM_INV1); // the '-' arms have no bin test (src/search_inversions.cpp:199,251)
-   return true;
+   pg_sv_tail(ev, r, driver, check_bin, forced);
+   return forced != PG_SV_BREAK;
 }
 
 // the test of one arm on a (close point, far point) pair
@@ -457,14 +457,18 @@ PGSV_FN void pg_sv_pairs(const PgSvEnv &ev, PgSvRead &r, int driver, int arm, bo
    const PgRun &last_close = r.cr[r.ncr - 1];
    // the pair fired last, and the last pair in (close, far) order among those fired
    int32_t lf_ci = -1, lf_cj = -1, lf_fi = -1, mx_ci = -1, mx_cj = -1, mx_fi = -1;
-   for (int e = 0; e <= r.max_e && !r.used; e++) {
-      for (int ci = 0; ci < r.ncr && !r.used; ci++) {
+   // passes e = 0 .. max_e fire the pairs with c.mm + f.mm == e; the extra pass replays the last pair in order (one call
+   // site for the fire keeps the device code small: the arms share every instruction of it)
+   for (int e = 0; e <= r.max_e + 1 && !r.used; e++) {
+      const bool replay = e > r.max_e;
+      if (replay && (mx_ci < 0 || (mx_ci == lf_ci && mx_cj == lf_cj && mx_fi == lf_fi))) break;
+      for (int ci = replay ? mx_ci : 0; ci < (replay ? mx_ci + 1 : r.ncr) && !r.used; ci++) {
          const PgRun &crun = r.cr[close_desc ? r.ncr - 1 - ci : ci];
-         if ((int)crun.mm > e || !pg_sv_close_kept(crun, last_close)) continue;
+         if (!replay && ((int)crun.mm > e || !pg_sv_close_kept(crun, last_close))) continue;
          const int fmm = e - (int)crun.mm;   // pairs that pass for the first time at this e
-         for (int cur = 0; cur < (int)crun.count && !r.used;) {
-            int next = 0x7FFFFFFF;
-            for (int fi = 0; fi < r.nfr; fi++) {
+         for (int cur = replay ? mx_cj : 0; cur < (replay ? mx_cj + 1 : (int)crun.count) && !r.used;) {
+            int next = replay ? cur : 0x7FFFFFFF;
+            for (int fi = 0; fi < r.nfr && !replay; fi++) {
                const PgRun &frun = r.fr[far_desc ? r.nfr - 1 - fi : fi];
                if ((int)frun.mm != fmm || (frun.dirstrand & 1) != far_dir) continue;
                const PgSvSpan sp = pg_sv_span(r, arm, crun, frun, close_desc, far_dir);
@@ -475,9 +479,9 @@ PGSV_FN void pg_sv_pairs(const PgSvEnv &ev, PgSvRead &r, int driver, int arm, bo
             if (next == 0x7FFFFFFF) break;
             const int idx = close_desc ? (int)crun.count - 1 - next : next;
             const PgSvUP c = pg_sv_up(crun, idx);
-            for (int fi = 0; fi < r.nfr && !r.used; fi++) {
+            for (int fi = replay ? mx_fi : 0; fi < (replay ? mx_fi + 1 : r.nfr) && !r.used; fi++) {
                const PgRun &frun = r.fr[far_desc ? r.nfr - 1 - fi : fi];
-               if ((int)frun.mm != fmm || (frun.dirstrand & 1) != far_dir) continue;
+               if (!replay && ((int)frun.mm != fmm || (frun.dirstrand & 1) != far_dir)) continue;
                const PgSvSpan sp = pg_sv_span(r, arm, crun, frun, close_desc, far_dir);
                if (next < sp.lo || next > sp.hi) continue;
                const PgSvUP f = pg_sv_up(frun, sp.k + sp.m * idx);
@@ -495,13 +499,6 @@ PGSV_FN void pg_sv_pairs(const PgSvEnv &ev, PgSvRead &r, int driver, int arm, bo
             cur = next + 1;
          }
       }
-   }
-   if (!r.used && mx_ci >= 0 && (mx_ci != lf_ci || mx_cj != lf_cj || mx_fi != lf_fi)) {
-      const PgRun &crun = r.cr[close_desc ? r.ncr - 1 - mx_ci : mx_ci];
-      const PgRun &frun = r.fr[far_desc ? r.nfr - 1 - mx_fi : mx_fi];
-      const int idx = close_desc ? (int)crun.count - 1 - mx_cj : mx_cj;
-      const PgSvSpan sp = pg_sv_span(r, arm, crun, frun, close_desc, far_dir);
-      pg_sv_fire(ev, r, driver, arm, pg_sv_up(crun, idx), pg_sv_up(frun, sp.k + sp.m * idx));
    }
 }
 
@@ -532,101 +529,98 @@ PGSV_FN void pg_sv_nt_driver(const PgSvEnv &ev, PgSvRead &r, int driver)
       if (f.dir != (plus ? 0 : 1)) return;
    } else if (f.dir != (plus ? 1 : 0)) return;
    const uint32_t nts = (uint32_t)(uint16_t)(r.rl - f.len - c.len);
-   if (driver == PG_SV_DI) { // src/search_deletions_nt.cpp:55-124
+   // DI (src/search_deletions_nt.cpp:55-124) and TD_NT (src/search_tandem_duplications_nt.cpp:56-117) make one test;
+   // INV_NT (src/search_inversions_nt.cpp:56-186) runs the two tests of the anchor's strand one after the other,
+   // whatever the first one did.
+   if (driver == PG_SV_DI) {
       if (!(sum < r.rl && sum >= P.min_matched && (plus ? f.loc > c.loc + 1 : c.loc > f.loc + 1))) return;
-      r.dirty |= PG_SVF_CORE | PG_SVF_NTSIZE;
-      if (plus) {
-         r.left = (int32_t)(c.loc - cl + 1);
-         r.right = (int32_t)(f.loc + fl - 1);
-         r.bp = c.len - 1;
-      } else {
-         r.left = (int32_t)(f.loc - fl + 1);
-         r.right = (int32_t)(c.loc + cl - 1);
-         r.bp = f.len - 1;
-      }
-      r.nt_size = nts;
-      pg_sv_set_nt(r, plus ? PG_NT_RC : PG_NT_SEQ, (uint32_t)(r.bp + 1), nts);
-      r.indel = (uint32_t)((r.right - r.left) + (int32_t)nts - (r.rl - 1));
-      r.bp_left = (plus ? c.loc : f.loc) - SP;
-      r.bp_right = (plus ? f.loc : c.loc) - SP;
-      pg_sv_tail(ev, r, driver, true);
-      return;
-   }
-   if (driver == PG_SV_TD_NT) { // src/search_tandem_duplications_nt.cpp:56-117
+   } else if (driver == PG_SV_TD_NT) {
       if (!(sum > P.min_matched)) return;
       if (plus ? !(f.loc + fl < c.loc && f.loc + cl < c.loc) : !(c.loc + cl < f.loc && c.loc + fl < f.loc)) return;
-      r.dirty |= PG_SVF_CORE | PG_SVF_NTSIZE;
-      if (plus) {
-         r.right = (int32_t)(c.loc - cl + 1);
-         r.left = (int32_t)(f.loc + fl - 1);
-         r.bp = c.len - 1;
-         r.indel = c.loc - f.loc + 1;
+   } else if (!(sum < r.rl && sum >= P.min_matched)) return;
+   const int rounds = driver == PG_SV_INV_NT ? 2 : 1;
+   for (int k = 0; k < rounds; k++) {
+      if (driver == PG_SV_DI) {
+         if (plus) {
+            r.left = (int32_t)(c.loc - cl + 1);
+            r.right = (int32_t)(f.loc + fl - 1);
+            r.bp = c.len - 1;
+         } else {
+            r.left = (int32_t)(f.loc - fl + 1);
+            r.right = (int32_t)(c.loc + cl - 1);
+            r.bp = f.len - 1;
+         }
+         pg_sv_set_nt(r, plus ? PG_NT_RC : PG_NT_SEQ, (uint32_t)(r.bp + 1), nts);
+         r.indel = (uint32_t)((r.right - r.left) + (int32_t)nts - (r.rl - 1));
+         r.bp_left = (plus ? c.loc : f.loc) - SP;
+         r.bp_right = (plus ? f.loc : c.loc) - SP;
+      } else if (driver == PG_SV_TD_NT) {
+         if (plus) {
+            r.right = (int32_t)(c.loc - cl + 1);
+            r.left = (int32_t)(f.loc + fl - 1);
+            r.bp = c.len - 1;
+            r.indel = c.loc - f.loc + 1;
+         } else {
+            r.right = (int32_t)(f.loc - fl + 1);
+            r.left = (int32_t)(c.loc + cl - 1);
+            r.bp = f.len - 1;
+            r.indel = f.loc - c.loc + 1;
+         }
+         pg_sv_set_nt(r, plus ? PG_NT_RC : PG_NT_SEQ, (uint32_t)(r.bp + 1), nts);
+         r.bp_right = (plus ? c.loc : f.loc) - SP;
+         r.bp_left = (plus ? f.loc : c.loc) - SP;
       } else {
-         r.right = (int32_t)(f.loc - fl + 1);
-         r.left = (int32_t)(c.loc + cl - 1);
-         r.bp = f.len - 1;
-         r.indel = f.loc - c.loc + 1;
+         const int arm = plus ? (k == 0 ? PG_ARM_INV0 : PG_ARM_INV1) : (k == 0 ? PG_ARM_INV2 : PG_ARM_INV3);
+         bool ok;
+         switch (arm) {
+         case PG_ARM_INV0: ok = f.loc > c.loc + mi; break;
+         case PG_ARM_INV1: ok = f.loc + mi < c.loc; break;
+         case PG_ARM_INV2: ok = c.loc > f.loc + mi; break;
+         default: ok = c.loc + mi < f.loc; break;
+         }
+         if (!ok) continue;
+         switch (arm) {
+         case PG_ARM_INV0:
+            r.left = (int32_t)((c.loc + 1) - cl);
+            r.right = (int32_t)(f.loc - fl + rl);
+            r.bp = c.len - 1;
+            r.indel = f.loc - c.loc;
+            pg_sv_set_nt(r, PG_NT_RC, (uint32_t)(r.bp + 1), nts);
+            r.bp_left = c.loc + 1 - SP;
+            r.bp_right = f.loc - SP;
+            break;
+         case PG_ARM_INV1:
+            r.right = (int32_t)(c.loc - cl + rl);
+            r.left = (int32_t)(f.loc - fl + 1);
+            r.bp = f.len - 1;
+            r.indel = c.loc - f.loc;
+            pg_sv_set_nt(r, PG_NT_SEQ, (uint32_t)(r.bp + 1), nts);
+            r.bp_right = c.loc - SP;
+            r.bp_left = (f.loc + 1) - SP;
+            break;
+         case PG_ARM_INV2:
+            r.left = (int32_t)(f.loc + fl - rl);
+            r.right = (int32_t)(c.loc + cl - 1);
+            r.bp = f.len - 1;
+            r.indel = c.loc - f.loc;
+            pg_sv_set_nt(r, PG_NT_SEQ, (uint32_t)(r.bp + 1), nts);
+            r.bp_left = f.loc - SP;
+            r.bp_right = c.loc - 1 - SP;
+            break;
+         default:
+            r.right = (int32_t)(f.loc + fl - 1);
+            r.left = (int32_t)(c.loc + cl - rl);
+            r.bp = c.len - 1;
+            r.indel = f.loc - c.loc;
+            pg_sv_set_nt(r, PG_NT_RC, (uint32_t)(r.bp + 1), nts);
+            r.bp_left = c.loc - SP;
+            r.bp_right = f.loc - 1 - SP;
+            break;
+         }
       }
-      r.nt_size = nts;
-      pg_sv_set_nt(r, plus ? PG_NT_RC : PG_NT_SEQ, (uint32_t)(r.bp + 1), nts);
-      r.bp_right = (plus ? c.loc : f.loc) - SP;
-      r.bp_left = (plus ? f.loc : c.loc) - SP;
-      pg_sv_tail(ev, r, driver, true);
-      return;
-   }
-   // INV_NT, src/search_inversions_nt.cpp:56-186: the two tests of a strand run one after the other, whatever the first did
-   if (!(sum < r.rl && sum >= P.min_matched)) return;
-   for (int k = 0; k < 2; k++) {
-      const int arm = plus ? (k == 0 ? PG_ARM_INV0 : PG_ARM_INV1) : (k == 0 ? PG_ARM_INV2 : PG_ARM_INV3);
-      bool ok;
-      switch (arm) {
-      case PG_ARM_INV0: ok = f.loc > c.loc + mi; break;
-      case PG_ARM_INV1: ok = f.loc + mi < c.loc; break;
-      case PG_ARM_INV2: ok = c.loc > f.loc + mi; break;
-      default: ok = c.loc + mi < f.loc; break;
-      }
-      if (!ok) continue;
       r.dirty |= PG_SVF_CORE | PG_SVF_NTSIZE;
       r.nt_size = nts;
-      switch (arm) {
-      case PG_ARM_INV0:
-         r.left = (int32_t)((c.loc + 1) - cl);
-         r.right = (int32_t)(f.loc - fl + rl);
-         r.bp = c.len - 1;
-         r.indel = f.loc - c.loc;
-         pg_sv_set_nt(r, PG_NT_RC, (uint32_t)(r.bp + 1), nts);
-         r.bp_left = c.loc + 1 - SP;
-         r.bp_right = f.loc - SP;
-         break;
-      case PG_ARM_INV1:
-         r.right = (int32_t)(c.loc - cl + rl);
-         r.left = (int32_t)(f.loc - fl + 1);
-         r.bp = f.len - 1;
-         r.indel = c.loc - f.loc;
-         pg_sv_set_nt(r, PG_NT_SEQ, (uint32_t)(r.bp + 1), nts);
-         r.bp_right = c.loc - SP;
-         r.bp_left = (f.loc + 1) - SP;
-         break;
-      case PG_ARM_INV2:
-         r.left = (int32_t)(f.loc + fl - rl);
-         r.right = (int32_t)(c.loc + cl - 1);
-         r.bp = f.len - 1;
-         r.indel = c.loc - f.loc;
-         pg_sv_set_nt(r, PG_NT_SEQ, (uint32_t)(r.bp + 1), nts);
-         r.bp_left = f.loc - SP;
-         r.bp_right = c.loc - 1 - SP;
-         break;
-      default:
-         r.right = (int32_t)(f.loc + fl - 1);
-         r.left = (int32_t)(c.loc + cl - rl);
-         r.bp = c.len - 1;
-         r.indel = f.loc - c.loc;
-         pg_sv_set_nt(r, PG_NT_RC, (uint32_t)(r.bp + 1), nts);
-         r.bp_left = c.loc - SP;
-         r.bp_right = f.loc - 1 - SP;
-         break;
-      }
-      pg_sv_tail(ev, r, driver, true);
+      pg_sv_tail(ev, r, driver, true, PG_SV_NONE);
    }
 }
 
@@ -639,33 +633,31 @@ PGSV_FN void pg_sv_classify_read(const PgSvEnv &ev, PgSvRead &r, bool other_chr)
    for (int d = 0; d < PG_SV_NDRIVERS; d++) {
       if (!((P.driver_mask >> d) & 1u) || r.used) continue;
       r.seq_no = 0;
+      int arm = -1;   // pair drivers: which arm runs, if any
       switch (d) {
-      case PG_SV_D:
-         if (plus) pg_sv_pairs(ev, r, d, PG_ARM_D_PLUS, false, true, 1);
-         else if (minus) pg_sv_pairs(ev, r, d, PG_ARM_D_MINUS, true, true, 0);
-         break;
-      case PG_SV_SI:
-         if (plus) pg_sv_pairs(ev, r, d, PG_ARM_SI_PLUS, false, true, 1);
-         else if (minus) pg_sv_pairs(ev, r, d, PG_ARM_SI_MINUS, true, true, 0);
-         break;
-      case PG_SV_TD:
-         if (plus) pg_sv_pairs(ev, r, d, PG_ARM_TD_PLUS, false, true, 1);
-         else if (minus) pg_sv_pairs(ev, r, d, PG_ARM_TD_MINUS, true, false, 0);
-         break;
+      case PG_SV_D: arm = plus ? PG_ARM_D_PLUS : minus ? PG_ARM_D_MINUS : -1; break;
+      case PG_SV_SI: arm = plus ? PG_ARM_SI_PLUS : minus ? PG_ARM_SI_MINUS : -1; break;
+      case PG_SV_TD: arm = plus ? PG_ARM_TD_PLUS : minus ? PG_ARM_TD_MINUS : -1; break;
       case PG_SV_INV: {
          const PgSvUP c0 = pg_sv_first_close(r), cl = pg_sv_last(r.cr, r.ncr), f0 = pg_sv_first(r.fr), fl = pg_sv_last(r.fr, r.nfr);
          if (!(c0.strand != f0.strand && c0.dir == f0.dir)) break;
          const uint32_t mi = (uint32_t)P.min_inv;
-         if (plus) {
-            if (f0.loc > cl.loc + mi) pg_sv_pairs(ev, r, d, PG_ARM_INV0, true, false, 0);
-            else if (fl.loc + mi < c0.loc) pg_sv_pairs(ev, r, d, PG_ARM_INV1, false, true, 0);
-         } else if (minus) {
-            if (cl.loc > f0.loc + mi) pg_sv_pairs(ev, r, d, PG_ARM_INV2, true, false, 1);
-            else if (c0.loc + mi < fl.loc) pg_sv_pairs(ev, r, d, PG_ARM_INV3, false, true, 1);
-         }
+         if (plus) arm = f0.loc > cl.loc + mi ? PG_ARM_INV0 : fl.loc + mi < c0.loc ? PG_ARM_INV1 : -1;
+         else if (minus) arm = cl.loc > f0.loc + mi ? PG_ARM_INV2 : c0.loc + mi < fl.loc ? PG_ARM_INV3 : -1;
          break;
       }
       default: pg_sv_nt_driver(ev, r, d); break;
+      }
+      if (arm >= 0) {
+         // iteration order of the close and far lists, and the far direction the arm accepts:
+         //   D+/SI+/TD+ (close up, far down, BACKWARD)   D-/SI- (down, down, FORWARD)   TD- (down, up, FORWARD)
+         //   INV0 (down, up, FORWARD)   INV1 (up, down, FORWARD)   INV2 (down, up, BACKWARD)   INV3 (up, down, BACKWARD)
+         const bool close_desc = arm == PG_ARM_D_MINUS || arm == PG_ARM_SI_MINUS || arm == PG_ARM_TD_MINUS || arm == PG_ARM_INV0 ||
+                                 arm == PG_ARM_INV2;
+         const bool far_desc = !(arm == PG_ARM_TD_MINUS || arm == PG_ARM_INV0 || arm == PG_ARM_INV2);
+         const int far_dir = (arm == PG_ARM_D_PLUS || arm == PG_ARM_SI_PLUS || arm == PG_ARM_TD_PLUS || arm == PG_ARM_INV2 ||
+                              arm == PG_ARM_INV3) ? 1 : 0;
+         pg_sv_pairs(ev, r, d, arm, close_desc, far_desc, far_dir);
       }
       if (r.dirty) pg_sv_emit(ev, r, d, PG_SV_NONE, 0); // fields assigned, read not taken: the host still gets the values
       if (ev.counts && r.seq_no) ev.counts[(size_t)d * ev.n_reads + r.index] = (uint8_t)r.seq_no;

@@ -80,6 +80,14 @@ struct PgSvBatch {
    const uint32_t *run_off;      // [n+1] first run of the read (UP_Close runs, then UP_Far runs)
    const uint16_t *n_close_runs; // [n]
    const PgRun *runs;
+   // resident mode (pg_classify_resident): the lists of the search launch that is still on the device replace the three
+   // arrays above -- far runs (and, after a close+far launch, close runs) come from res_pool through res_out; after a
+   // far-end-only launch the close runs are the caller's (close_off / close_runs).  rflags may be NULL (nothing used).
+   const PgReadOut *res_out;     // [n] or NULL
+   const PgRun *res_pool;
+   const uint32_t *close_off;    // [n+1] or NULL
+   const PgRun *close_runs;
+   const int32_t *chr_id;        // [n] chromosome of the anchor (FragName) or NULL = 0: FarFragName != FragName is derived
    PgSvRecord *records;
    uint32_t records_cap;
    uint32_t *counters;           // [4]: [0] records allocated, [1] overflow flag, [2] pair tests (statistics)

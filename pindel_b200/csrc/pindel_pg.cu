@@ -144,25 +144,88 @@ __global__ void __launch_bounds__(128) pg_sv_kernel(PgSvBatch b, const PgSvParam
    const uint32_t s0 = b.seq_off[i], s1 = b.seq_off[i + 1];
    r.seq = b.seq_blob + s0;
    r.rl = (int32_t)(s1 - s0);
+   bool other_chr = false;
+   if (b.res_out) {
+      const PgReadOut o = b.res_out[i];
+      if (o.flags & (PG_F_TOOLONG | PG_F_OVERFLOW)) return;
+      r.rl = o.len_after;      // setUnmatchedSeq's strip and the flips are already in the resident sequence
+      r.fr = b.res_pool + o.run_off + o.n_close_runs;
+      r.nfr = o.n_far_runs;
+      if (b.close_off) {
+         r.cr = b.close_runs + b.close_off[i];
+         r.ncr = (int32_t)(b.close_off[i + 1] - b.close_off[i]);
+      } else {
+         r.cr = b.res_pool + o.run_off;
+         r.ncr = o.n_close_runs;
+      }
+      // FarFragName (UpdateFarFragName, src/pindel.cpp:1262-1270) is the chromosome of UP_Far[0]
+      other_chr = r.nfr > 0 && (int32_t)r.fr[0].chr != (b.chr_id ? b.chr_id[i] : 0);
+   } else {
+      const uint32_t r0 = b.run_off[i], r1 = b.run_off[i + 1];
+      r.cr = b.runs + r0;
+      r.ncr = b.n_close_runs[i];
+      r.fr = r.cr + r.ncr;
+      r.nfr = (int32_t)(r1 - r0) - r.ncr;
+   }
    r.max_e = prm->g[r.rl < 512 ? r.rl : 511];
    r.matched_d = b.matched_d[i];
    r.insert_size = b.insert_size[i];
-   const uint32_t r0 = b.run_off[i], r1 = b.run_off[i + 1];
-   r.cr = b.runs + r0;
-   r.ncr = b.n_close_runs[i];
-   r.fr = r.cr + r.ncr;
-   r.nfr = (int32_t)(r1 - r0) - r.ncr;
    r.index = (uint32_t)i;
    r.left = r.right = 0;
    r.bp_left = r.bp_right = r.indel = 0;
    r.bp = 0;
    r.nt_size = r.nt_start = r.nt_len = r.nt_rot = 0;
    r.nt_src = PG_NT_EMPTY;
-   const uint8_t fl = b.rflags[i];
+   const uint8_t fl = b.rflags ? b.rflags[i] : (uint8_t)0;
    r.used = (fl & PG_SVR_USED) != 0;
    r.dirty = 0;
    r.seq_no = 0;
-   pg_sv_classify_read(ev, r, (fl & PG_SVR_OTHERCHR) != 0);
+   other_chr = other_chr || (fl & PG_SVR_OTHERCHR) != 0;
+   pg_sv_classify_read(ev, r, other_chr);
+}
+
+// The final UnmatchedSeq of every read of a close+far launch, for the classification of the resident batch: what the host
+// obtains by replaying the flips (PG_READ_NFLIPS) with setUnmatchedSeq(ReverseComplement(..)).  One warp per read.
+//   strip:   L0 = length without trailing non-alphanumerics (setUnmatchedSeq, src/pindel.cpp:142-169)
+//   1 flip:  k1 leading non-ACGTN characters become trailing NULs and are stripped: out[j] = comp(s[L0-1-j]), j < L0-k1
+//   2 flips: out[j] = s[k1+j] with non-ACGTN -> NUL, length len_after
+__global__ void __launch_bounds__(256) pg_sv_final_seq_kernel(int n_reads, const uint8_t *__restrict__ seq_blob, const uint32_t *__restrict__ seq_off,
+                                                             const PgReadOut *__restrict__ out, uint8_t *__restrict__ final_blob)
+{
+   const int i = (int)((blockIdx.x * blockDim.x + threadIdx.x) >> 5), lane = threadIdx.x & 31;
+   if (i >= n_reads) return;
+   const uint32_t s0 = seq_off[i], len = seq_off[i + 1] - s0;
+   const uint8_t *s = seq_blob + s0;
+   uint8_t *d = final_blob + s0;
+   const PgReadOut o = out[i];
+   const uint32_t nflips = (o.flags >> PG_F_NFLIPS_SHIFT) & 3u;
+   uint32_t L0 = 0, k1 = len;
+   bool found = false;
+   for (uint32_t c0 = 0; c0 < len; c0 += 32) {
+      const uint32_t j = c0 + lane;
+      const uint8_t ch = j < len ? s[j] : (uint8_t)0;
+      const bool alnum = (ch >= '0' && ch <= '9') || (ch >= 'A' && ch <= 'Z') || (ch >= 'a' && ch <= 'z');
+      const bool acgtn = ch == 'A' || ch == 'C' || ch == 'G' || ch == 'T' || ch == 'N';
+      const uint32_t ma = __ballot_sync(0xFFFFFFFFu, alnum), mk = __ballot_sync(0xFFFFFFFFu, acgtn);
+      if (ma) L0 = c0 + 32 - __clz(ma);
+      if (!found && mk) { k1 = c0 + __ffs(mk) - 1; found = true; }
+   }
+   if (k1 > L0) k1 = L0;
+   const uint32_t Lf = o.len_after;
+   for (uint32_t j = lane; j < len; j += 32) {
+      uint8_t ch = 0;
+      if (j < Lf) {
+         if (nflips == 0) ch = s[j];
+         else if (nflips == 1) {
+            const uint8_t x = s[L0 - 1 - j];
+            ch = x == 'A' ? 'T' : x == 'C' ? 'G' : x == 'G' ? 'C' : x == 'T' ? 'A' : x == 'N' ? 'N' : 0;
+         } else {
+            const uint8_t x = s[k1 + j];
+            ch = (x == 'A' || x == 'C' || x == 'G' || x == 'T' || x == 'N') ? x : 0;
+         }
+      }
+      d[j] = ch;
+   }
 }
 
 // Record order.  pg_sv_kernel hands out pool slots in completion order; the host replays records per driver with reads
@@ -286,6 +349,7 @@ struct pg_ctx {
    int n = 0;
    bool have_anchor = false, have_chr = false, have_close = false, have_regions = false;
    uint32_t max_read_len = 0;
+   size_t blob_bytes = 0;
    DevBuf seq_blob, seq_off, md, pos, isz, chr, closeinfo, regions, region_off, out, pool, counters, scratch;
    uint32_t pool_cap = 0;
    uint32_t *counters_h = nullptr;     // pinned
@@ -297,6 +361,8 @@ struct pg_ctx {
    // SV classification (pg_classify)
    DevBuf sv_seq, sv_off, sv_md, sv_isz, sv_flags, sv_runoff, sv_nclose, sv_runs, sv_records, sv_params, sv_counters, sv_counts, sv_offsets,
       sv_blocksums, sv_ordered;
+   PgSvParams sv_params_h;          // staging copy (the async upload reads it until the stream drains)
+   DevBuf sv_close_off, sv_close_runs;
    uint64_t sv_aux_launches = 0;    // scan + order kernels
    uint64_t sv_launches = 0;
    cudaEvent_t sv_ev0 = nullptr, sv_ev1 = nullptr;   // around the last pg_sv_kernel launch
@@ -450,7 +516,8 @@ void pg_destroy(pg_ctx *ctx)
    for (DevBuf *b : bufs) if (b->p) cudaFree(b->p);
    DevBuf *svbufs[] = {&ctx->sv_seq, &ctx->sv_off, &ctx->sv_md, &ctx->sv_isz, &ctx->sv_flags, &ctx->sv_runoff, &ctx->sv_nclose,
                        &ctx->sv_runs, &ctx->sv_records, &ctx->sv_params, &ctx->sv_counters,
-                       &ctx->sv_counts, &ctx->sv_offsets, &ctx->sv_blocksums, &ctx->sv_ordered};
+                       &ctx->sv_counts, &ctx->sv_offsets, &ctx->sv_blocksums, &ctx->sv_ordered, &ctx->sv_close_off,
+                       &ctx->sv_close_runs};
    for (DevBuf *b : svbufs) if (b->p) cudaFree(b->p);
    pipe_destroy(ctx->pipe);
    if (ctx->chroms_d) cudaFree(ctx->chroms_d);
@@ -553,6 +620,7 @@ int pg_upload(pg_ctx *ctx, const pg_reads *in)
             return fail(ctx, PG_ERR_ARG, "pg_upload: chr_id out of range");
    }
    size_t blob = in->seq_off[n];
+   ctx->blob_bytes = blob;
    int rc;
 #define UP(buf, src, bytes)                                                                              \
    if ((rc = ensure(ctx, buf, (bytes))) != PG_OK) return rc;                                             \
@@ -886,6 +954,7 @@ static int run_all(pg_ctx *ctx, const pg_reads *in, pg_results *res, int mode)
 {
    if (ctx && in && in->n >= 2 * ctx->pipe_chunk && in->seq_blob && in->seq_off) {
       CU(cudaSetDevice(ctx->device));
+      ctx->launched = false;      // the chunks went through the pipeline's own slots: nothing stays resident
       return run_pipelined(ctx, ctx->pipe, in, res, mode);
    }
    int rc = pg_upload(ctx, in);
@@ -1001,6 +1070,30 @@ static int sv_classify_device(pg_ctx *ctx, PgSvBatch &b, pg_sv_results *res)
 
 static_assert(sizeof(pg_sv_record) == sizeof(PgSvRecord) && sizeof(pg_sv_record) == 44, "sv record layout");
 
+static int sv_upload_window(pg_ctx *ctx, const pg_sv_window *win)
+{
+   if (win->chr < 0 || win->chr >= (int32_t)ctx->chroms_h.size()) return fail(ctx, PG_ERR_ARG, "pg_classify: chromosome out of range");
+   if (win->box_size == 0) return fail(ctx, PG_ERR_ARG, "pg_classify: box_size is 0");
+   PgSvParams &P = ctx->sv_params_h;
+   memset(&P, 0, sizeof P);
+   P.driver_mask = win->driver_mask & PG_SV_ALL;
+   P.chr = win->chr;
+   P.window_end = win->window_end;
+   P.num_boxes = win->num_boxes;
+   P.box_size = win->box_size;
+   P.region_start_defined = win->region_start_defined;
+   P.region_start = win->region_start;
+   P.region_end_defined = win->region_end_defined;
+   P.region_end = win->region_end;
+   P.min_inv = win->min_inversion_size;
+   P.min_matched = win->min_matched_bases;
+   for (int k = 0; k < 1032; k++) P.nt_thr[k] = (uint16_t)(short)(1 + ctx->st.seq_error_rate * k); // src/search_deletions_nt.cpp:50-51
+   int rc;
+   if ((rc = ensure(ctx, ctx->sv_params, sizeof(PgSvParams))) != PG_OK) return rc;
+   CU(cudaMemcpyAsync(ctx->sv_params.p, &P, sizeof P, cudaMemcpyHostToDevice, ctx->stream));
+   return PG_OK;
+}
+
 int pg_classify(pg_ctx *ctx, const pg_sv_reads *in, const pg_sv_window *win, pg_sv_results *res)
 {
    if (!ctx || !in || !win || !res) return fail(ctx, PG_ERR_ARG, "pg_classify: null argument");
@@ -1023,21 +1116,8 @@ int pg_classify(pg_ctx *ctx, const pg_sv_reads *in, const pg_sv_window *win, pg_
    }
    CU(cudaSetDevice(ctx->device));
    cudaStream_t st = ctx->stream;
-   PgSvParams P;
-   memset(&P, 0, sizeof P);
-   P.driver_mask = win->driver_mask & PG_SV_ALL;
-   P.chr = win->chr;
-   P.window_end = win->window_end;
-   P.num_boxes = win->num_boxes;
-   P.box_size = win->box_size;
-   P.region_start_defined = win->region_start_defined;
-   P.region_start = win->region_start;
-   P.region_end_defined = win->region_end_defined;
-   P.region_end = win->region_end;
-   P.min_inv = win->min_inversion_size;
-   P.min_matched = win->min_matched_bases;
-   for (int k = 0; k < 1032; k++) P.nt_thr[k] = (uint16_t)(short)(1 + ctx->st.seq_error_rate * k); // src/search_deletions_nt.cpp:50-51
    int rc;
+   if ((rc = sv_upload_window(ctx, win)) != PG_OK) return rc;
    const size_t seq_bytes = in->seq_off[n];
    if ((rc = ensure(ctx, ctx->sv_seq, seq_bytes + 4)) != PG_OK) return rc;
    if ((rc = ensure(ctx, ctx->sv_off, sizeof(uint32_t) * (size_t)(n + 1))) != PG_OK) return rc;
@@ -1047,7 +1127,6 @@ int pg_classify(pg_ctx *ctx, const pg_sv_reads *in, const pg_sv_window *win, pg_
    if ((rc = ensure(ctx, ctx->sv_runoff, sizeof(uint32_t) * (size_t)(n + 1))) != PG_OK) return rc;
    if ((rc = ensure(ctx, ctx->sv_nclose, sizeof(uint16_t) * (size_t)n)) != PG_OK) return rc;
    if ((rc = ensure(ctx, ctx->sv_runs, sizeof(PgRun) * (size_t)(n_runs + 1))) != PG_OK) return rc;
-   if ((rc = ensure(ctx, ctx->sv_params, sizeof(PgSvParams))) != PG_OK) return rc;
    CU(cudaMemcpyAsync(ctx->sv_seq.p, in->seq_blob, seq_bytes, cudaMemcpyHostToDevice, st));
    CU(cudaMemcpyAsync(ctx->sv_off.p, in->seq_off, sizeof(uint32_t) * (size_t)(n + 1), cudaMemcpyHostToDevice, st));
    CU(cudaMemcpyAsync(ctx->sv_md.p, in->matched_d, (size_t)n, cudaMemcpyHostToDevice, st));
@@ -1056,7 +1135,6 @@ int pg_classify(pg_ctx *ctx, const pg_sv_reads *in, const pg_sv_window *win, pg_
    CU(cudaMemcpyAsync(ctx->sv_runoff.p, in->run_off, sizeof(uint32_t) * (size_t)(n + 1), cudaMemcpyHostToDevice, st));
    CU(cudaMemcpyAsync(ctx->sv_nclose.p, in->n_close_runs, sizeof(uint16_t) * (size_t)n, cudaMemcpyHostToDevice, st));
    if (n_runs) CU(cudaMemcpyAsync(ctx->sv_runs.p, in->runs, sizeof(PgRun) * (size_t)n_runs, cudaMemcpyHostToDevice, st));
-   CU(cudaMemcpyAsync(ctx->sv_params.p, &P, sizeof P, cudaMemcpyHostToDevice, st));
    PgSvBatch b;
    memset(&b, 0, sizeof b);
    b.n_reads = n;
@@ -1068,6 +1146,59 @@ int pg_classify(pg_ctx *ctx, const pg_sv_reads *in, const pg_sv_window *win, pg_
    b.run_off = (const uint32_t *)ctx->sv_runoff.p;
    b.n_close_runs = (const uint16_t *)ctx->sv_nclose.p;
    b.runs = (const PgRun *)ctx->sv_runs.p;
+   return sv_classify_device(ctx, b, res);
+}
+
+int pg_classify_resident(pg_ctx *ctx, const pg_sv_window *win, const uint8_t *rflags, const uint32_t *close_run_off,
+                         const pg_run *close_runs, pg_sv_results *res)
+{
+   if (!ctx || !win || !res) return fail(ctx, PG_ERR_ARG, "pg_classify_resident: null argument");
+   if (!ctx->launched || !(ctx->last_mode & 2)) return fail(ctx, PG_ERR_STATE, "pg_classify_resident: no far-end launch is resident");
+   if (!ctx->have_anchor) return fail(ctx, PG_ERR_ARG, "pg_classify_resident: the resident batch has no matched_d / insert_size");
+   if (ctx->last_mode == 2 && (!close_run_off || (close_run_off[ctx->n] && !close_runs)))
+      return fail(ctx, PG_ERR_ARG, "pg_classify_resident: a far-end-only launch needs the reads' close runs");
+   res->n_records = 0;
+   CU(cudaSetDevice(ctx->device));
+   int rc = finish_launch(ctx);
+   if (rc != PG_OK) return rc;
+   const int n = ctx->n;
+   if (n == 0) return PG_OK;
+   cudaStream_t st = ctx->stream;
+   if ((rc = sv_upload_window(ctx, win)) != PG_OK) return rc;
+   PgSvBatch b;
+   memset(&b, 0, sizeof b);
+   b.n_reads = n;
+   b.seq_off = (const uint32_t *)ctx->seq_off.p;
+   b.matched_d = (const uint8_t *)ctx->md.p;
+   b.insert_size = (const int16_t *)ctx->isz.p;
+   b.chr_id = ctx->have_chr ? (const int32_t *)ctx->chr.p : nullptr;
+   b.res_out = (const PgReadOut *)ctx->out.p;
+   b.res_pool = (const PgRun *)ctx->pool.p;
+   if (rflags) {
+      if ((rc = ensure(ctx, ctx->sv_flags, (size_t)n)) != PG_OK) return rc;
+      CU(cudaMemcpyAsync(ctx->sv_flags.p, rflags, (size_t)n, cudaMemcpyHostToDevice, st));
+      b.rflags = (const uint8_t *)ctx->sv_flags.p;
+   }
+   if (ctx->last_mode == 2) {
+      for (int i = 0; i < n; i++)
+         if (close_run_off[i + 1] < close_run_off[i]) return fail(ctx, PG_ERR_ARG, "pg_classify_resident: inconsistent close run offsets");
+      const size_t nr = close_run_off[n];
+      if ((rc = ensure(ctx, ctx->sv_close_off, sizeof(uint32_t) * ((size_t)n + 1))) != PG_OK) return rc;
+      if ((rc = ensure(ctx, ctx->sv_close_runs, sizeof(PgRun) * (nr + 1))) != PG_OK) return rc;
+      CU(cudaMemcpyAsync(ctx->sv_close_off.p, close_run_off, sizeof(uint32_t) * ((size_t)n + 1), cudaMemcpyHostToDevice, st));
+      if (nr) CU(cudaMemcpyAsync(ctx->sv_close_runs.p, close_runs, sizeof(PgRun) * nr, cudaMemcpyHostToDevice, st));
+      b.close_off = (const uint32_t *)ctx->sv_close_off.p;
+      b.close_runs = (const PgRun *)ctx->sv_close_runs.p;
+      b.seq_blob = (const uint8_t *)ctx->seq_blob.p;     // pg_far_end takes the sequences as GetCloseEnd left them
+   } else {
+      // close + far launch: the flips happened on the device; materialise the final sequences next to the originals
+      if ((rc = ensure(ctx, ctx->sv_seq, ctx->blob_bytes + 4)) != PG_OK) return rc;
+      pg_sv_final_seq_kernel<<<(n + 7) / 8, 256, 0, st>>>(n, (const uint8_t *)ctx->seq_blob.p, (const uint32_t *)ctx->seq_off.p,
+                                                        (const PgReadOut *)ctx->out.p, (uint8_t *)ctx->sv_seq.p);
+      CU(cudaGetLastError());
+      ctx->sv_aux_launches++;
+      b.seq_blob = (const uint8_t *)ctx->sv_seq.p;
+   }
    return sv_classify_device(ctx, b, res);
 }
 

@@ -73,7 +73,21 @@ def main():
     res = {"stage": "SV classification (7 drivers, one launch)", "reads": int(m), "read_len": L, "runs_per_read": float(run_off[-1]) / m,
            "records": int(rec.size), "records_by_outcome": np.bincount(rec["outcome"], minlength=4).tolist(),
            "e2e_reads_per_s": m / float(np.median(wall)), "e2e_ms": 1e3 * float(np.median(wall)), "kernel_ms": float(np.median(kern)),
+           "kernel_ms_note": "CUDA events around the whole device stage: memsets + pg_sv_kernel + scan + order",
            "kernel_reads_per_s": m / (float(np.median(kern)) * 1e-3), "h2d_bytes": h2d, "d2h_bytes": int(rec.nbytes)}
+    # the same stage on the batch the search left on the device (pg_classify_resident): no second upload; all n reads,
+    # the ones without a close end fall out on the device
+    pg.search(seq_blob=seq.reshape(-1), seq_off=off, matched_d=md, matched_rel_pos=pos, insert_size=isz)
+    rec_r = pg.classify_resident(win, records=rec_buf)
+    assert rec_r.size == rec.size, (rec_r.size, rec.size)
+    wall_r, kern_r = [], []
+    for _ in range(a.reps):
+        t0 = time.perf_counter()
+        rec_r = pg.classify_resident(win, records=rec_buf)
+        wall_r.append(time.perf_counter() - t0)
+        kern_r.append(pg.classify_last_kernel_ms)
+    res["resident"] = {"reads_in_batch": int(n), "e2e_ms": 1e3 * float(np.median(wall_r)), "device_ms": float(np.median(kern_r)),
+                       "e2e_reads_per_s": n / float(np.median(wall_r)), "h2d_bytes": 4168, "d2h_bytes": int(rec_r.nbytes)}
     from oracle import refhook
     if refhook.available() and a.cpu_sample > 0:
         import tempfile

@@ -3,6 +3,7 @@ reference host + bridge on libpindel_pg.so (GPU test) or on the CPU emulators of
 bridge's host logic).  Golden files were written by the pure reference binary (tests/golden/)."""
 import gzip
 import os
+import re
 import shutil
 import subprocess
 
@@ -16,6 +17,10 @@ def _run(demo, args, env):
     assert "served by libpindel_pg" in p.stderr and " 0 GetCloseEnd calls" not in p.stderr
     # every window is classified by ONE call (all seven drivers in one launch), and the drivers replayed its records
     assert "classified by the SV drivers on the device" in p.stderr and "; 0 reads classified" not in p.stderr
+    # ... on the batch SearchFarEnds left on the device, unless the scenario switches that off
+    m = re.search(r"; (\d+) reads classified .* (\d+) of the reads without a second upload", p.stderr)
+    assert m, p.stderr[-500:]
+    assert int(m.group(2)) == (0 if env.get("PG_BRIDGE_NO_RESIDENT") else int(m.group(1))), m.group(0)
     return p
 
 

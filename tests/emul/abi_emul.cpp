@@ -25,6 +25,12 @@ struct pg_ctx {
    std::vector<pg_read_out> out;
    std::vector<pg_run> runs;
    uint64_t launches = 0, sv_launches = 0;
+   // copy of the last far-end-only batch ("resident")
+   int res_n = -1;
+   std::vector<uint8_t> res_seq, res_md;
+   std::vector<uint32_t> res_off;
+   std::vector<int16_t> res_isz;
+   std::vector<int32_t> res_chr;
 };
 
 static std::string g_create_error;
@@ -105,6 +111,16 @@ static int run(pg_ctx *ctx, const pg_reads *in, pg_results *res, int mode)
       }
    }
    ctx->launches++;
+   ctx->res_n = -1;
+   if (mode == 2 && in->matched_d && in->insert_size) {
+      ctx->res_n = n;
+      ctx->res_seq.assign((const uint8_t *)in->seq_blob, (const uint8_t *)in->seq_blob + in->seq_off[n]);
+      ctx->res_off.assign(in->seq_off, in->seq_off + n + 1);
+      ctx->res_md.assign((const uint8_t *)in->matched_d, (const uint8_t *)in->matched_d + n);
+      ctx->res_isz.assign(in->insert_size, in->insert_size + n);
+      ctx->res_chr.assign((size_t)n, 0);
+      if (in->chr_id) ctx->res_chr.assign(in->chr_id, in->chr_id + n);
+   }
    return pg_download(ctx, res);
 }
 
@@ -144,6 +160,40 @@ int pg_classify(pg_ctx *ctx, const pg_sv_reads *in, const pg_sv_window *win, pg_
       return a.seq < b.seq;
    });
    return PG_OK;
+}
+
+// after a far-end-only call: the batch kept above + the caller's close runs, re-assembled into the host-array form
+int pg_classify_resident(pg_ctx *ctx, const pg_sv_window *win, const uint8_t *rflags, const uint32_t *close_run_off,
+                         const pg_run *close_runs, pg_sv_results *res)
+{
+   if (ctx->res_n < 0) return fail(ctx, PG_ERR_STATE, "no far-end launch is resident");
+   const int n = ctx->res_n;
+   std::vector<uint32_t> run_off((size_t)n + 1, 0);
+   std::vector<uint16_t> n_close((size_t)n);
+   std::vector<uint8_t> flags((size_t)n);
+   std::vector<pg_run> runs;
+   for (int i = 0; i < n; i++) {
+      const uint32_t c0 = close_run_off[i], c1 = close_run_off[i + 1];
+      runs.insert(runs.end(), close_runs + c0, close_runs + c1);
+      n_close[i] = (uint16_t)(c1 - c0);
+      const pg_read_out &o = ctx->out[i];
+      const pg_run *fr = ctx->runs.data() + o.run_off + o.n_close_runs;
+      runs.insert(runs.end(), fr, fr + o.n_far_runs);
+      run_off[i + 1] = (uint32_t)runs.size();
+      flags[i] = (uint8_t)((rflags ? rflags[i] & PG_SVR_USED : 0) | ((o.n_far_runs && fr[0].chr != ctx->res_chr[i]) ? PG_SVR_OTHERCHR : 0));
+   }
+   pg_sv_reads in;
+   memset(&in, 0, sizeof in);
+   in.n_reads = n;
+   in.seq_blob = ctx->res_seq.data();
+   in.seq_off = ctx->res_off.data();
+   in.matched_d = ctx->res_md.data();
+   in.insert_size = ctx->res_isz.data();
+   in.rflags = flags.data();
+   in.run_off = run_off.data();
+   in.n_close_runs = n_close.data();
+   in.runs = runs.data();
+   return pg_classify(ctx, &in, win, res);
 }
 
 uint64_t pg_classify_launches(pg_ctx *ctx) { return ctx ? ctx->sv_launches : 0; }

@@ -23,3 +23,9 @@ def test_text_input_scenario(tmp_path):
 
 def test_bam_input_scenario(tmp_path):
     D.sim_prefix_bam(DEMO, tmp_path, dict(os.environ))
+
+
+def test_text_input_scenario_with_the_host_array_classification(tmp_path):
+    """pg_classify (everything uploaded again) instead of pg_classify_resident: the path a host takes when the far-end
+    batch is no longer on the device."""
+    D.colo_slice(DEMO, tmp_path, dict(os.environ, PG_BRIDGE_NO_RESIDENT="1"), unbatched_too=False)

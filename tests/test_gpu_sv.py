@@ -67,6 +67,49 @@ def test_search_then_classify_matches_oracle(L, n, seed, region_frac, wend_frac)
     rec = pg.classify(b, win)
     got = S.dump_from_records(rec, sq, b["rflags"])
     svoracle.compare_dumps(exp, got, "chained L=%d" % L)
+
+    def remap(rec_all):
+        """records of a whole-batch classification -> indices among the reads with a close end (the oracle's batch)"""
+        pos = np.searchsorted(idx, rec_all["read"])
+        assert np.all(pos < len(idx)) and np.array_equal(idx[pos], rec_all["read"]), "record for a read without a close end"
+        r2 = rec_all.copy()
+        r2["read"] = pos
+        return r2
+
+    # (a) resident after the close+far launch: nothing uploaded again, flips applied on the device
+    out2, runs2 = pg.search(**bk)
+    assert np.array_equal(out2, out) or np.array_equal(out2["n_far_runs"], out["n_far_runs"])
+    rec_a = pg.classify_resident(win)
+    svoracle.compare_dumps(exp, S.dump_from_records(remap(rec_a), sq, b["rflags"]), "resident after pg_search L=%d" % L)
+    # (b) the reference's call order: close ends first, then SearchFarEnds on the reads that have one, then the drivers
+    ci_arr = np.zeros(len(idx), dtype=R.CLOSEINFO_DT)
+    close_off = np.zeros(len(idx) + 1, dtype=np.uint32)
+    cparts = []
+    for k, i in enumerate(idx):
+        c = exp_search[i]["close"]
+        ci_arr[k] = (int(c[-1, 1]) & 0xFFFFFFFF, int(c[-1, 0]), 0)
+        o = out[i]
+        cparts.append(runs[int(o["run_off"]):int(o["run_off"]) + int(o["n_close_runs"])])
+        close_off[k + 1] = close_off[k] + int(o["n_close_runs"])
+    pg.search_far_ends(seq_blob=ci["seq_blob"], seq_off=ci["seq_off"], matched_d=ci["matched_d"],
+                       matched_rel_pos=np.asarray(batch.matched_rel_pos)[idx], insert_size=ci["insert_size"], close_info=ci_arr)
+    rec_b = pg.classify_resident(win, rflags=b["rflags"], close_run_off=close_off, close_runs=np.concatenate(cparts))
+    svoracle.compare_dumps(exp, S.dump_from_records(rec_b, sq, b["rflags"]), "resident after pg_far_end L=%d" % L)
+    pg.close()
+
+
+def test_classify_resident_needs_a_resident_far_end_launch():
+    pg = api.PatternGrowth()
+    c = S.load_sv_case("synth_L250_default")
+    pg.set_reference([c["case"].padded])
+    with pytest.raises(api.PgError):
+        pg.classify_resident(c["win"])          # nothing launched
+    ref = synth.make_reference(300_000, 5)
+    batch = synth.make_reads(ref, 500, 100, seed=6)
+    pg.set_reference([synth.pad_reference(ref)])
+    pg.get_close_end(**H.batch_kwargs(batch))
+    with pytest.raises(api.PgError):
+        pg.classify_resident(sv.window(500_000, 300_000))   # a close-end-only launch has no far ends
     pg.close()
 
 
