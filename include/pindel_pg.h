@@ -265,6 +265,39 @@ int pg_classify_resident(pg_ctx *ctx, const pg_sv_window *win, const uint8_t *rf
 uint64_t pg_classify_launches(pg_ctx *ctx);   /* classification-kernel launches since pg_create */
 double pg_classify_last_kernel_ms(pg_ctx *ctx); /* CUDA-event duration of the last classification kernel */
 
+/* ------------------------------------------------------------------------------------------------------------------
+ * Discordant-read-pair clustering: the two quadratic loops of BDData::UpdateBD
+ * (src/bddata.cpp:646-659) that turn the window's discordant pairs into BreakDancer-like events for the far-end search.
+ *   pg_rp_modify    = ModifyRP (src/bddata.cpp:385-431) after its std::sort: the caller sorts (Compare2RP,
+ *                     src/bddata.cpp:239-253 -- std::sort's order among equal keys is the caller's library's business) and
+ *                     passes the rows in that order; InitializeA1B1, the interval-merging double loop in serial row order,
+ *                     the + ReadLength pass and the Visited mark for pairs closer than 500 come back.
+ *   pg_rp_summarize = Summarize (src/bddata.cpp:470-575): identical events are merged into their first row
+ *                     (NumberOfIdentical, Visited; merged_into tells the host whose Tags to append), Report for >= 5.
+ * Rows of one call belong to one chromosome pair (ChrNameA == ChrNameB: Reads_RP_Discovery).
+ * ------------------------------------------------------------------------------------------------------------------ */
+typedef struct pg_rp {            /* RP_READ (src/pindel.h:215-262): what the clustering reads */
+   uint32_t pos_a, pos_b;         /* PosA, PosB (== OriginalPosA, OriginalPosB on entry) */
+   uint32_t insert_size;          /* InsertSize */
+   int16_t read_length;           /* ReadLength */
+   uint8_t da, db;                /* DA, DB: '+' / '-' */
+} pg_rp;
+
+typedef struct pg_rp_cluster {    /* what ModifyRP / Summarize leave in the RP_READ */
+   uint32_t pos_a, pos_a1, pos_b, pos_b1;
+   uint32_t n_identical;          /* NumberOfIdentical */
+   uint32_t merged_into;          /* Summarize: the row that absorbed this one (append this row's Tags there), else its own index */
+   uint8_t visited, report;       /* Visited, Report */
+   uint16_t pad;
+} pg_rp_cluster;
+
+int pg_rp_modify(pg_ctx *ctx, int32_t n, const pg_rp *in, pg_rp_cluster *out);
+int pg_rp_summarize(pg_ctx *ctx, int32_t n, const pg_rp *in, pg_rp_cluster *inout);
+uint64_t pg_rp_launches(pg_ctx *ctx);          /* clustering-kernel launches since pg_create */
+/* how the last pg_rp_modify split its rows: classes run by one warp each, classes run by one CTA each, rows in either */
+void pg_rp_last_classes(pg_ctx *ctx, uint32_t *warp_classes, uint32_t *cta_classes, uint32_t *rows_in_classes);
+double pg_rp_last_kernel_ms(pg_ctx *ctx);      /* CUDA-event duration of the last call's kernels */
+
 /* Host helper: run-length encode UniquePoints (the inverse of pg_expand_runs) for callers that hold expanded lists.
  * Returns the number of runs (out may be NULL to just count). */
 uint32_t pg_compress_ups(const pg_up *ups, uint32_t n, pg_run *out);

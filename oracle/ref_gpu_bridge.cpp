@@ -43,6 +43,7 @@
 #include "search_inversions_nt.h"
 
 #include <cstdio>
+#include <algorithm>
 #include <cstdlib>
 #include <mutex>
 #include <string>
@@ -58,7 +59,7 @@ extern short g_MinClose;
 namespace {
 pg_ctx *g_ctx = NULL;
 std::mutex g_mutex;
-unsigned long g_close_calls = 0, g_far_reads = 0, g_sv_reads = 0, g_sv_records = 0, g_sv_resident = 0;
+unsigned long g_close_calls = 0, g_far_reads = 0, g_sv_reads = 0, g_sv_records = 0, g_sv_resident = 0, g_rp_rows = 0;
 const SPLIT_READ *g_farResidentBase = NULL;   /* Reads_SR of the last SearchFarEnds call, still resident on the device */
 size_t g_farResidentN = 0;
 
@@ -344,6 +345,72 @@ void SearchFarEnds(const std::string &chromosomeSeq, std::vector<SPLIT_READ> &re
    g_farResidentBase = (n && !staleFarEnd) ? &reads[0] : NULL;
    g_farResidentN = (size_t)n;
    *logStream << "Far end searching completed for this window." << std::endl;   /* src/pindel.cpp:1137 */
+}
+
+/* ---------------------------------------------------------------------------------------------------------------------
+ * Row N2: the two quadratic loops of BDData::UpdateBD (src/bddata.cpp:646-659).  ModifyRP and Summarize are free functions
+ * of bddata.cpp, so the same interposition serves them: the sort stays here, with the reference's own comparator (the
+ * order std::sort leaves among equal keys is then the reference's), the loops run on the device.
+ * ------------------------------------------------------------------------------------------------------------------- */
+bool Compare2RP(const RP_READ &first, const RP_READ &second);   /* src/bddata.cpp:239-253 */
+namespace {
+void marshalRP(const std::vector<RP_READ> &v, std::vector<pg_rp> &in)
+{
+   in.resize(v.size());
+   for (size_t i = 0; i < v.size(); i++) {
+      in[i].pos_a = v[i].PosA; in[i].pos_b = v[i].PosB; in[i].insert_size = v[i].InsertSize;
+      in[i].read_length = v[i].ReadLength; in[i].da = (uint8_t)v[i].DA; in[i].db = (uint8_t)v[i].DB;
+   }
+}
+} // namespace
+
+void ModifyRP(std::vector<RP_READ> &Reads_RP)
+{
+   std::cout << "Reads_RP.size(): " << Reads_RP.size() << std::endl;
+   if (Reads_RP.size() == 0) return;
+   std::cout << "sorting read-pair" << std::endl;
+   sort(Reads_RP.begin(), Reads_RP.end(), Compare2RP);
+   std::cout << "sorting read-pair finished." << std::endl;
+   std::lock_guard<std::mutex> lock(g_mutex);
+   ensureContext();
+   std::vector<pg_rp> in;
+   marshalRP(Reads_RP, in);
+   std::vector<pg_rp_cluster> out(in.size());
+   if (pg_rp_modify(g_ctx, (int32_t)in.size(), &in[0], &out[0]) != PG_OK) die("pg_rp_modify");
+   for (size_t i = 0; i < Reads_RP.size(); i++) {
+      RP_READ &r = Reads_RP[i];
+      r.PosA = out[i].pos_a; r.PosA1 = out[i].pos_a1; r.PosB = out[i].pos_b; r.PosB1 = out[i].pos_b1;
+      if (out[i].visited) r.Visited = true;
+   }
+   g_rp_rows += (unsigned long)Reads_RP.size();
+}
+
+void Summarize(std::vector<RP_READ> &Reads_RP)
+{
+   if (Reads_RP.empty()) return;
+   std::lock_guard<std::mutex> lock(g_mutex);
+   ensureContext();
+   std::vector<pg_rp> in;
+   marshalRP(Reads_RP, in);
+   std::vector<pg_rp_cluster> st(in.size());
+   for (size_t i = 0; i < Reads_RP.size(); i++) {
+      const RP_READ &r = Reads_RP[i];
+      st[i].pos_a = r.PosA; st[i].pos_a1 = r.PosA1; st[i].pos_b = r.PosB; st[i].pos_b1 = r.PosB1;
+      st[i].n_identical = r.NumberOfIdentical; st[i].merged_into = (uint32_t)i;
+      st[i].visited = r.Visited ? 1 : 0; st[i].report = r.Report ? 1 : 0; st[i].pad = 0;
+   }
+   if (pg_rp_summarize(g_ctx, (int32_t)in.size(), &in[0], &st[0]) != PG_OK) die("pg_rp_summarize");
+   for (size_t i = 0; i < Reads_RP.size(); i++) {
+      RP_READ &r = Reads_RP[i];
+      r.NumberOfIdentical = st[i].n_identical;
+      r.Visited = st[i].visited != 0;
+      r.Report = st[i].report != 0;
+      if (st[i].merged_into != (uint32_t)i && r.Tags.size()) {      /* src/bddata.cpp:500-505: the absorbing row collects the Tags, in row order */
+         RP_READ &first = Reads_RP[st[i].merged_into];
+         first.Tags.insert(first.Tags.end(), r.Tags.begin(), r.Tags.end());
+         r.Tags.clear();
+      }
+   }
 }
 
 /* ---------------------------------------------------------------------------------------------------------------------
@@ -637,9 +704,10 @@ int searchInversionsNT(ControlState &currentState, unsigned NumBoxes, const Sear
 static void reportAtExit()
 {
    std::fprintf(stderr, "pindel_gpu_demo: %lu GetCloseEnd calls and %lu far-end reads served by libpindel_pg (%llu kernel launches); "
-                "%lu reads classified by the SV drivers on the device, %lu records (%llu launches), %lu of the reads without a second upload\n",
+                "%lu reads classified by the SV drivers on the device, %lu records (%llu launches), %lu of the reads without a second upload; %lu read pairs clustered on the device (%llu launches)\n",
                 g_close_calls, g_far_reads, g_ctx ? (unsigned long long)pg_kernel_launches(g_ctx) : 0ull, g_sv_reads, g_sv_records,
-                g_ctx ? (unsigned long long)pg_classify_launches(g_ctx) : 0ull, g_sv_resident);
+                g_ctx ? (unsigned long long)pg_classify_launches(g_ctx) : 0ull, g_sv_resident, g_rp_rows,
+                g_ctx ? (unsigned long long)pg_rp_launches(g_ctx) : 0ull);
 }
 
 int main(int argc, char *argv[])

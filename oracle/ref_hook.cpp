@@ -34,6 +34,7 @@
 #include "search_inversions.h"
 #include "search_inversions_nt.h"
 
+#include <algorithm>
 #include <chrono>
 #include <cstdint>
 #include <cstring>
@@ -402,3 +403,64 @@ int64_t pgref_classify(int n, const char *seq_blob, const uint32_t *seq_off, con
 }
 
 } // extern "C"
+
+/* Row N2 of SURVEY.md section 8(f): the reference's own discordant-pair clustering, exactly as BDData::UpdateBD chains it
+ * (src/bddata.cpp:654-659): sort by (PosA, PosB), ModifyRP (sort by original position descending, InitializeA1B1, the
+ * O(n^2) interval-merging loop, + ReadLength), Summarize (identical-interval groups, Report for >= 5).  One thread: the
+ * reference's OpenMP loop updates rows other threads are reading (src/bddata.cpp:401-417), so only the serial order is defined.
+ * out: n rows of 14 int32 in the order ModifyRP's sort leaves: input index, OriginalPosA, OriginalPosB, DA, DB, ReadLength,
+ * InsertSize, PosA, PosA1, PosB, PosB1, Visited, Report, NumberOfIdentical; then tags: for every row the number of Tags it
+ * holds followed by the input indices they came from (Summarize moves Tags into the row that absorbs another). */
+bool SortByFirstAndThenSecondCoordinate(const RP_READ &read1, const RP_READ &read2);
+void ModifyRP(std::vector<RP_READ> &Reads_RP);
+void Summarize(std::vector<RP_READ> &Reads_RP);
+
+extern "C" int64_t pgref_rp_cluster(int n, const uint32_t *pos_a, const uint32_t *pos_b, const char *da, const char *db,
+                                    const int16_t *read_length, const uint32_t *insert_size, int32_t **out_stream, double *seconds)
+{
+   std::vector<RP_READ> v((size_t)n);
+   for (int i = 0; i < n; i++) {
+      RP_READ &r = v[i];
+      r.ReadName = "r" + std::to_string(i);
+      r.ChrNameA = "c";
+      r.ChrNameB = "c";
+      r.DA = da[i];
+      r.DB = db[i];
+      r.PosA = r.OriginalPosA = pos_a[i];
+      r.PosB = r.OriginalPosB = pos_b[i];
+      r.ReadLength = read_length[i];
+      r.InsertSize = insert_size[i];
+      r.Experimental_InsertSize = (unsigned)i;   /* not read by the functions under test: carries the input index */
+      r.Tag = std::to_string(i);
+      r.Tags.push_back(r.Tag);
+   }
+   const int saved = omp_get_max_threads();
+   omp_set_num_threads(1);
+   auto t0 = std::chrono::steady_clock::now();
+   std::sort(v.begin(), v.end(), SortByFirstAndThenSecondCoordinate);
+   ModifyRP(v);
+   auto t1 = std::chrono::steady_clock::now();
+   Summarize(v);
+   auto t2 = std::chrono::steady_clock::now();
+   omp_set_num_threads(saved);
+   if (seconds) {
+      seconds[0] = std::chrono::duration<double>(t1 - t0).count();
+      seconds[1] = std::chrono::duration<double>(t2 - t1).count();
+   }
+   std::vector<int32_t> out;
+   for (int i = 0; i < n; i++) {
+      const RP_READ &r = v[i];
+      const int32_t row[14] = {(int32_t)r.Experimental_InsertSize, (int32_t)r.OriginalPosA, (int32_t)r.OriginalPosB, r.DA, r.DB, r.ReadLength,
+                               (int32_t)r.InsertSize, (int32_t)r.PosA, (int32_t)r.PosA1, (int32_t)r.PosB, (int32_t)r.PosB1, r.Visited ? 1 : 0,
+                               r.Report ? 1 : 0, (int32_t)r.NumberOfIdentical};
+      out.insert(out.end(), row, row + 14);
+   }
+   for (int i = 0; i < n; i++) {
+      out.push_back((int32_t)v[i].Tags.size());
+      for (size_t k = 0; k < v[i].Tags.size(); k++) out.push_back((int32_t)std::stoi(v[i].Tags[k]));
+   }
+   int32_t *buf = (int32_t *)malloc(out.size() * sizeof(int32_t) + 4);
+   memcpy(buf, out.data(), out.size() * sizeof(int32_t));
+   *out_stream = buf;
+   return (int64_t)out.size();
+}

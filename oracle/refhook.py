@@ -189,3 +189,35 @@ def parse_stream(stream: np.ndarray, n: int):
         out.append(dict(flip=flip, L=L, close_raw=cr, close=cc, far=fa, regions=rg))
     assert p == s.size
     return out
+
+
+def rp_cluster(rows):
+    """The reference's own sort + ModifyRP + Summarize (oracle/ref_hook.cpp pgref_rp_cluster; needs no initialised
+    instance).  rows: structured array with pos_a, pos_b, da, db, read_length, insert_size (oracle.rporacle.RP_DT).
+    -> (table [n, 14] int64: input index, OriginalPosA, OriginalPosB, DA, DB, ReadLength, InsertSize, PosA, PosA1, PosB, PosB1,
+    Visited, Report, NumberOfIdentical -- in the order ModifyRP's sort leaves; tags: list of input-index lists; seconds)."""
+    lib = C.CDLL(LIB)
+    lib.pgref_rp_cluster.restype = C.c_int64
+    n = len(rows)
+    cols = [np.ascontiguousarray(rows[k]) for k in ("pos_a", "pos_b", "da", "db", "read_length", "insert_size")]
+    out = C.POINTER(C.c_int32)()
+    secs = (C.c_double * 2)()
+    devnull = os.open(os.devnull, os.O_WRONLY)
+    saved = os.dup(1)
+    os.dup2(devnull, 1)
+    try:
+        k = lib.pgref_rp_cluster(n, *[c.ctypes.data_as(C.c_void_p) for c in cols], C.byref(out), secs)
+    finally:
+        os.dup2(saved, 1)
+        os.close(saved)
+        os.close(devnull)
+    stream = np.ctypeslib.as_array(out, shape=(max(int(k), 1),))[:k].copy()
+    lib.pgref_free(out)
+    table = stream[:14 * n].reshape(n, 14).astype(np.int64)
+    table[:, [1, 2, 6, 7, 8, 9, 10, 13]] &= 0xFFFFFFFF
+    tags, p = [], 14 * n
+    for _ in range(n):
+        c = int(stream[p])
+        tags.append(stream[p + 1:p + 1 + c].tolist())
+        p += 1 + c
+    return table, tags, (secs[0], secs[1])

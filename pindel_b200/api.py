@@ -90,6 +90,14 @@ def load_library() -> C.CDLL:
         lib.pg_last_stats.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
         lib.pg_classify.argtypes = [C.c_void_p, C.POINTER(_SvReads), C.POINTER(_SvWindow), C.POINTER(_SvResults)]
         lib.pg_classify_resident.argtypes = [C.c_void_p, C.POINTER(_SvWindow), C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(_SvResults)]
+        lib.pg_rp_modify.argtypes = [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p]
+        lib.pg_rp_summarize.argtypes = [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p]
+        lib.pg_rp_last_classes.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+        lib.pg_rp_last_classes.restype = None
+        lib.pg_rp_launches.restype = C.c_uint64
+        lib.pg_rp_launches.argtypes = [C.c_void_p]
+        lib.pg_rp_last_kernel_ms.restype = C.c_double
+        lib.pg_rp_last_kernel_ms.argtypes = [C.c_void_p]
         lib.pg_classify_launches.restype = C.c_uint64
         lib.pg_classify_launches.argtypes = [C.c_void_p]
         lib.pg_classify_last_kernel_ms.restype = C.c_double
@@ -303,6 +311,39 @@ class PatternGrowth:
             rc = self.lib.pg_classify_resident(self.ctx, C.byref(w), ptr(fl), ptr(co), ptr(cr), C.byref(res))
         self._check(rc, "pg_classify_resident")
         return rec[:res.n_records]
+
+    def rp_modify(self, rows: np.ndarray) -> np.ndarray:
+        """ModifyRP after its sort (src/bddata.cpp:396-430) on the device: rows = pindel_b200.rp.RP_DT in the order the
+        caller's Compare2RP sort leaves -> pindel_b200.rp.CLUSTER_DT."""
+        from . import rp
+        rows = np.ascontiguousarray(rows, dtype=rp.RP_DT)
+        out = np.zeros(rows.size, dtype=rp.CLUSTER_DT)
+        self._check(self.lib.pg_rp_modify(self.ctx, int(rows.size), rows.ctypes.data_as(C.c_void_p), out.ctypes.data_as(C.c_void_p)),
+                    "pg_rp_modify")
+        return out
+
+    def rp_summarize(self, rows: np.ndarray, state: np.ndarray) -> np.ndarray:
+        """Summarize (src/bddata.cpp:470-575) on the device; returns the updated copy of `state`."""
+        from . import rp
+        rows = np.ascontiguousarray(rows, dtype=rp.RP_DT)
+        out = np.ascontiguousarray(state, dtype=rp.CLUSTER_DT).copy()
+        self._check(self.lib.pg_rp_summarize(self.ctx, int(rows.size), rows.ctypes.data_as(C.c_void_p), out.ctypes.data_as(C.c_void_p)),
+                    "pg_rp_summarize")
+        return out
+
+    def rp_last_classes(self):
+        """(classes run by one warp, classes run by one CTA, rows in either) of the last rp_modify."""
+        a, b, c = C.c_uint32(0), C.c_uint32(0), C.c_uint32(0)
+        self.lib.pg_rp_last_classes(self.ctx, C.byref(a), C.byref(b), C.byref(c))
+        return int(a.value), int(b.value), int(c.value)
+
+    @property
+    def rp_last_kernel_ms(self) -> float:
+        return float(self.lib.pg_rp_last_kernel_ms(self.ctx))
+
+    @property
+    def rp_launches(self) -> int:
+        return int(self.lib.pg_rp_launches(self.ctx))
 
     @property
     def classify_last_kernel_ms(self) -> float:

@@ -4,7 +4,7 @@
   oracle/libpg_oracle.so        test infrastructure: C restatement of the reference algorithm (libsv_oracle.so: the SV drivers)
   oracle/_ref/*                 test infrastructure: the reference itself, when /root/reference is present
   tests/emul/libpg_emul.so      test infrastructure: CPU lane emulator of the warp program
-  tests/emul/libsv_emul.so      test infrastructure: the SV-classification program compiled for the host
+  tests/emul/libsv_emul.so      test infrastructure: the SV-classification program compiled for the host (librp_emul.so: read-pair clustering)
 """
 from __future__ import annotations
 
@@ -44,9 +44,10 @@ def build_oracle():
 
 def build_emulator():
     sys.path.insert(0, ROOT)
-    from tests.emul import emul, sv_emul
+    from tests.emul import emul, rp_emul, sv_emul
     emul.build()
     sv_emul.build()
+    rp_emul.build()
 
 
 def build_all(force=False):

@@ -1,0 +1,75 @@
+// pindel_b200/csrc/pg_rp_host.h -- host part of pg_rp_modify: the O(n log n) split of a window's discordant pairs into
+// classes that cannot influence each other (the device then runs every class as an independent recurrence).  Kept apart
+// from pindel_pg.cu so that the CPU suite exercises the same function (tests/emul/rp_emul.cpp).
+#pragma once
+#include <stdint.h>
+#include <algorithm>
+#include <vector>
+#include "pg_rp.cuh"
+
+// Classes of rows that can interact (see pg_rp.cuh): equal strands, and connected through overlapping initial A intervals
+// or overlapping initial B intervals.  Rows whose A or B interval is wider than 1000 never pass RecipicalOverlap, neither
+// as first nor as second: they stay alone.  -> rows grouped by class (ascending inside a class), classes of one row left out;
+// classes of more than warp_max rows go to the second list.
+static inline void pg_rp_classes(int n, const PgRp *in, uint32_t warp_max, std::vector<uint32_t> &rows_small, std::vector<uint32_t> &off_small,
+                                 std::vector<uint32_t> &rows_big, std::vector<uint32_t> &off_big)
+{
+   std::vector<PgRpIv> iv((size_t)n);
+   std::vector<uint32_t> parent((size_t)n), live;
+   live.reserve((size_t)n);
+   for (int i = 0; i < n; i++) {
+      iv[i] = pg_rp_init(in[i]);
+      parent[i] = (uint32_t)i;
+      if (!(pg_rp_iabs((int)(iv[i].a - iv[i].a1)) > 1000 || pg_rp_iabs((int)(iv[i].b - iv[i].b1)) > 1000)) live.push_back((uint32_t)i);
+   }
+   auto find = [&](uint32_t x) {
+      while (parent[x] != x) { parent[x] = parent[parent[x]]; x = parent[x]; }
+      return x;
+   };
+   auto unite = [&](uint32_t x, uint32_t y) {
+      x = find(x); y = find(y);
+      if (x != y) parent[x > y ? x : y] = x > y ? y : x;
+   };
+   for (int side = 0; side < 2; side++) {
+      // sweep over (strands, interval start): a row joins the running component while its start lies before the component's end
+      std::sort(live.begin(), live.end(), [&](uint32_t x, uint32_t y) {
+         const uint32_t kx = (uint32_t)in[x].da << 8 | in[x].db, ky = (uint32_t)in[y].da << 8 | in[y].db;
+         if (kx != ky) return kx < ky;
+         const uint32_t sx = side ? iv[x].b : iv[x].a, sy = side ? iv[y].b : iv[y].a;
+         return sx != sy ? sx < sy : x < y;
+      });
+      uint32_t run_key = 0xFFFFFFFFu, run_end = 0, run_row = 0;
+      for (uint32_t x : live) {
+         const uint32_t k = (uint32_t)in[x].da << 8 | in[x].db, s0 = side ? iv[x].b : iv[x].a, s1 = side ? iv[x].b1 : iv[x].a1;
+         if (k == run_key && s0 < run_end) {
+            unite(x, run_row);
+            if (s1 > run_end) run_end = s1;
+         } else {
+            run_key = k;
+            run_end = s1;
+            run_row = x;
+         }
+      }
+   }
+   // class lists: counting sort by root keeps the rows of a class ascending
+   std::vector<uint32_t> count((size_t)n, 0), start((size_t)n, 0);
+   for (uint32_t x : live) count[find(x)]++;
+   rows_small.clear(); rows_big.clear();
+   off_small.assign(1, 0); off_big.assign(1, 0);
+   std::vector<uint32_t> slot((size_t)n, 0xFFFFFFFFu);
+   for (int i = 0; i < n; i++) {      // roots in ascending order; a root is the smallest row of its class
+      if (count[i] < 2) continue;
+      std::vector<uint32_t> &rows = count[i] > warp_max ? rows_big : rows_small;
+      std::vector<uint32_t> &off = count[i] > warp_max ? off_big : off_small;
+      slot[i] = (uint32_t)rows.size();
+      rows.resize(rows.size() + count[i]);
+      off.push_back((uint32_t)rows.size());
+   }
+   std::sort(live.begin(), live.end());
+   for (uint32_t x : live) {
+      const uint32_t r = find(x);
+      if (count[r] < 2) continue;
+      (count[r] > warp_max ? rows_big : rows_small)[slot[r]++] = x;
+   }
+}
+

@@ -18,6 +18,8 @@
 
 #include "pg_warp.cuh"
 #include "pg_sv.cuh"
+#include "pg_rp.cuh"
+#include "pg_rp_host.h"
 #include "pg_params.h"
 #include "../../include/pindel_pg.h"
 #include "pg_host_helpers.h"
@@ -363,7 +365,12 @@ struct pg_ctx {
       sv_blocksums, sv_ordered;
    PgSvParams sv_params_h;          // staging copy (the async upload reads it until the stream drains)
    DevBuf sv_close_off, sv_close_runs;
-   uint64_t sv_aux_launches = 0;    // scan + order kernels
+   uint64_t sv_aux_launches = 0;
+   // read-pair clustering (pg_rp_modify / pg_rp_summarize)
+   DevBuf rp_in, rp_out, rp_rows, rp_off, rp_scratch, rp_merged, rp_nid, rp_counters;
+   uint64_t rp_launches = 0;
+   uint32_t rp_classes_small = 0, rp_classes_big = 0, rp_rows_in_classes = 0;   // of the last pg_rp_modify
+   float rp_last_ms = 0.f;    // scan + order kernels
    uint64_t sv_launches = 0;
    cudaEvent_t sv_ev0 = nullptr, sv_ev1 = nullptr;   // around the last pg_sv_kernel launch
    float sv_last_ms = 0.f;
@@ -517,7 +524,8 @@ void pg_destroy(pg_ctx *ctx)
    DevBuf *svbufs[] = {&ctx->sv_seq, &ctx->sv_off, &ctx->sv_md, &ctx->sv_isz, &ctx->sv_flags, &ctx->sv_runoff, &ctx->sv_nclose,
                        &ctx->sv_runs, &ctx->sv_records, &ctx->sv_params, &ctx->sv_counters,
                        &ctx->sv_counts, &ctx->sv_offsets, &ctx->sv_blocksums, &ctx->sv_ordered, &ctx->sv_close_off,
-                       &ctx->sv_close_runs};
+                       &ctx->sv_close_runs, &ctx->rp_in, &ctx->rp_out, &ctx->rp_rows, &ctx->rp_off, &ctx->rp_scratch, &ctx->rp_merged,
+                       &ctx->rp_nid, &ctx->rp_counters};
    for (DevBuf *b : svbufs) if (b->p) cudaFree(b->p);
    pipe_destroy(ctx->pipe);
    if (ctx->chroms_d) cudaFree(ctx->chroms_d);
@@ -1204,6 +1212,108 @@ int pg_classify_resident(pg_ctx *ctx, const pg_sv_window *win, const uint8_t *rf
 
 uint64_t pg_classify_launches(pg_ctx *ctx) { return ctx ? ctx->sv_launches : 0; }
 double pg_classify_last_kernel_ms(pg_ctx *ctx) { return ctx ? (double)ctx->sv_last_ms : 0.0; }
+
+// ---- read-pair clustering (row N2) --------------------------------------------------------------------------------
+static_assert(sizeof(pg_rp) == sizeof(PgRp) && sizeof(pg_rp) == 16, "rp layout");
+static_assert(sizeof(pg_rp_cluster) == sizeof(PgRpCluster) && sizeof(pg_rp_cluster) == 28, "rp cluster layout");
+#define PG_RP_SMEM_ROWS 12800u   // 200 KB of intervals per CTA
+
+int pg_rp_modify(pg_ctx *ctx, int32_t n, const pg_rp *in, pg_rp_cluster *out)
+{
+   if (!ctx || n < 0 || (n > 0 && (!in || !out))) return fail(ctx, PG_ERR_ARG, "pg_rp_modify: bad arguments");
+   if (n == 0) return PG_OK;
+   CU(cudaSetDevice(ctx->device));
+   cudaStream_t st = ctx->stream;
+   std::vector<uint32_t> rows_small, off_small, rows_big, off_big;
+   pg_rp_classes(n, reinterpret_cast<const PgRp *>(in), 1024u, rows_small, off_small, rows_big, off_big);
+   const uint32_t n_small = (uint32_t)off_small.size() - 1, n_big = (uint32_t)off_big.size() - 1;
+   const size_t rs = rows_small.size(), rb = rows_big.size();
+   // device layout: [small class rows | big class rows], [small offsets | big offsets]
+   int rc;
+   if ((rc = ensure(ctx, ctx->rp_in, sizeof(PgRp) * (size_t)n)) != PG_OK) return rc;
+   if ((rc = ensure(ctx, ctx->rp_out, sizeof(PgRpCluster) * (size_t)n)) != PG_OK) return rc;
+   if ((rc = ensure(ctx, ctx->rp_rows, sizeof(uint32_t) * (rs + rb + 1))) != PG_OK) return rc;
+   if ((rc = ensure(ctx, ctx->rp_off, sizeof(uint32_t) * ((size_t)n_small + n_big + 2))) != PG_OK) return rc;
+   if ((rc = ensure(ctx, ctx->rp_scratch, sizeof(uint4) * (rs + rb + 1))) != PG_OK) return rc;
+   CU(cudaMemcpyAsync(ctx->rp_in.p, in, sizeof(PgRp) * (size_t)n, cudaMemcpyHostToDevice, st));
+   uint32_t *rows_d = (uint32_t *)ctx->rp_rows.p, *off_d = (uint32_t *)ctx->rp_off.p;
+   if (rs) CU(cudaMemcpyAsync(rows_d, rows_small.data(), sizeof(uint32_t) * rs, cudaMemcpyHostToDevice, st));
+   if (rb) CU(cudaMemcpyAsync(rows_d + rs, rows_big.data(), sizeof(uint32_t) * rb, cudaMemcpyHostToDevice, st));
+   CU(cudaMemcpyAsync(off_d, off_small.data(), sizeof(uint32_t) * ((size_t)n_small + 1), cudaMemcpyHostToDevice, st));
+   CU(cudaMemcpyAsync(off_d + n_small + 1, off_big.data(), sizeof(uint32_t) * ((size_t)n_big + 1), cudaMemcpyHostToDevice, st));
+   if (!ctx->sv_ev0) { CU(cudaEventCreate(&ctx->sv_ev0)); CU(cudaEventCreate(&ctx->sv_ev1)); }
+   CU(cudaEventRecord(ctx->sv_ev0, st));
+   pg_rp_single_kernel<<<(n + 255) / 256, 256, 0, st>>>(n, (const PgRp *)ctx->rp_in.p, (PgRpCluster *)ctx->rp_out.p);
+   ctx->rp_launches++;
+   if (n_small) {
+      pg_rp_modify_warp_kernel<<<(n_small + 7) / 8, 256, 0, st>>>((const PgRp *)ctx->rp_in.p, rows_d, off_d, n_small, (uint4 *)ctx->rp_scratch.p,
+                                                                 (PgRpCluster *)ctx->rp_out.p);
+      ctx->rp_launches++;
+   }
+   if (n_big) {
+      uint32_t biggest = 0;
+      for (uint32_t g = 0; g < n_big; g++) biggest = off_big[g + 1] - off_big[g] > biggest ? off_big[g + 1] - off_big[g] : biggest;
+      const uint32_t smem_rows = biggest < PG_RP_SMEM_ROWS ? biggest : PG_RP_SMEM_ROWS;
+      CU(cudaFuncSetAttribute(pg_rp_modify_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(uint4) * PG_RP_SMEM_ROWS)));
+      pg_rp_modify_kernel<<<n_big, PG_RP_THREADS, sizeof(uint4) * (size_t)smem_rows, st>>>((const PgRp *)ctx->rp_in.p, rows_d + rs, off_d + n_small + 1,
+                                                                                         (uint4 *)ctx->rp_scratch.p + rs, smem_rows,
+                                                                                         (PgRpCluster *)ctx->rp_out.p);
+      ctx->rp_launches++;
+   }
+   CU(cudaGetLastError());
+   CU(cudaEventRecord(ctx->sv_ev1, st));
+   ctx->rp_classes_small = n_small;
+   ctx->rp_classes_big = n_big;
+   ctx->rp_rows_in_classes = (uint32_t)(rs + rb);
+   CU(cudaMemcpyAsync(out, ctx->rp_out.p, sizeof(PgRpCluster) * (size_t)n, cudaMemcpyDeviceToHost, st));
+   CU(cudaStreamSynchronize(st));
+   CU(cudaEventElapsedTime(&ctx->rp_last_ms, ctx->sv_ev0, ctx->sv_ev1));
+   return PG_OK;
+}
+
+int pg_rp_summarize(pg_ctx *ctx, int32_t n, const pg_rp *in, pg_rp_cluster *inout)
+{
+   if (!ctx || n < 0 || (n > 0 && (!in || !inout))) return fail(ctx, PG_ERR_ARG, "pg_rp_summarize: bad arguments");
+   if (n < 5) {   // src/bddata.cpp:474-478
+      for (int i = 0; i < n; i++) inout[i].report = 0;
+      return PG_OK;
+   }
+   CU(cudaSetDevice(ctx->device));
+   cudaStream_t st = ctx->stream;
+   int rc;
+   if ((rc = ensure(ctx, ctx->rp_in, sizeof(PgRp) * (size_t)n)) != PG_OK) return rc;
+   if ((rc = ensure(ctx, ctx->rp_out, sizeof(PgRpCluster) * (size_t)n)) != PG_OK) return rc;
+   if ((rc = ensure(ctx, ctx->rp_merged, sizeof(uint32_t) * (size_t)n)) != PG_OK) return rc;
+   if ((rc = ensure(ctx, ctx->rp_nid, sizeof(uint32_t) * (size_t)n)) != PG_OK) return rc;
+   if ((rc = ensure(ctx, ctx->rp_counters, sizeof(uint32_t) * 2)) != PG_OK) return rc;
+   CU(cudaMemcpyAsync(ctx->rp_in.p, in, sizeof(PgRp) * (size_t)n, cudaMemcpyHostToDevice, st));
+   CU(cudaMemcpyAsync(ctx->rp_out.p, inout, sizeof(PgRpCluster) * (size_t)n, cudaMemcpyHostToDevice, st));
+   CU(cudaMemsetAsync(ctx->rp_nid.p, 0, sizeof(uint32_t) * (size_t)n, st));
+   CU(cudaMemsetAsync(ctx->rp_counters.p, 0, sizeof(uint32_t) * 2, st));
+   if (!ctx->sv_ev0) { CU(cudaEventCreate(&ctx->sv_ev0)); CU(cudaEventCreate(&ctx->sv_ev1)); }
+   CU(cudaEventRecord(ctx->sv_ev0, st));
+   pg_rp_group_kernel<<<(n + 7) / 8, 256, 0, st>>>(n, (const PgRp *)ctx->rp_in.p, (const PgRpCluster *)ctx->rp_out.p,
+                                                   (uint32_t *)ctx->rp_merged.p, (uint32_t *)ctx->rp_nid.p, (uint32_t *)ctx->rp_counters.p);
+   pg_rp_report_kernel<<<(n + 255) / 256, 256, 0, st>>>(n, (PgRpCluster *)ctx->rp_out.p, (const uint32_t *)ctx->rp_merged.p,
+                                                       (const uint32_t *)ctx->rp_nid.p, (const uint32_t *)ctx->rp_counters.p);
+   CU(cudaGetLastError());
+   CU(cudaEventRecord(ctx->sv_ev1, st));
+   ctx->rp_launches += 2;
+   CU(cudaMemcpyAsync(inout, ctx->rp_out.p, sizeof(PgRpCluster) * (size_t)n, cudaMemcpyDeviceToHost, st));
+   CU(cudaStreamSynchronize(st));
+   CU(cudaEventElapsedTime(&ctx->rp_last_ms, ctx->sv_ev0, ctx->sv_ev1));
+   return PG_OK;
+}
+
+uint64_t pg_rp_launches(pg_ctx *ctx) { return ctx ? ctx->rp_launches : 0; }
+void pg_rp_last_classes(pg_ctx *ctx, uint32_t *warp_classes, uint32_t *cta_classes, uint32_t *rows_in_classes)
+{
+   if (!ctx) return;
+   if (warp_classes) *warp_classes = ctx->rp_classes_small;
+   if (cta_classes) *cta_classes = ctx->rp_classes_big;
+   if (rows_in_classes) *rows_in_classes = ctx->rp_rows_in_classes;
+}
+double pg_rp_last_kernel_ms(pg_ctx *ctx) { return ctx ? (double)ctx->rp_last_ms : 0.0; }
 
 uint32_t pg_compress_ups(const pg_up *ups, uint32_t n, pg_run *out) { return pgh_compress_ups(ups, n, out); }
 

@@ -225,3 +225,38 @@ def make_reads_torch(ref_t, n: int, read_len: int, seed: int, insert_size: int =
         mpos[c0:c0 + m] = torch.where(plus, g_first - slack, (G - 1 - g_first) + slack)
         kinds[c0:c0 + m] = kind.to(torch.uint8)
     return seqs, md, mpos, torch.full((n,), insert_size, dtype=torch.int16, device=dev), kinds
+
+
+def make_discordant_pairs(n_events: int, seed: int, span: int = 60_000_000, background: int = 0, max_support: int = 40,
+                          libraries=((100, 250), (150, 500)), both_mates: float = 0.8) -> np.ndarray:
+    """Synthetic input of the read-pair clustering (row N2): what build_record_RP_Discovery (src/reader.cpp:982-1097)
+    leaves in Reads_RP_Discovery for one chromosome -- PosA < PosB, strands, read length and insert size of the library.
+    Events: two breakpoints with `support` pairs scattered within one insert size of them (most pairs twice: the BAM holds
+    both mates and both records normalise to the same row); `background` isolated pairs.  -> structured array
+    (oracle.rporacle.RP_DT layout), in BAM order (sorted by the position of the record that produced the row)."""
+    rng = np.random.default_rng(seed)
+    rows = []
+    for _ in range(n_events):
+        rl, isz = libraries[int(rng.integers(0, len(libraries)))]
+        a = int(rng.integers(10_000, max(20_000, span - 2_000_000)))
+        kind = rng.random()
+        dist = int(rng.integers(50, 400)) if kind < 0.1 else int(rng.integers(800, 5000)) if kind < 0.7 else int(rng.integers(5000, 1_500_000))
+        b = a + dist
+        da, db = (b"+-", b"-+", b"++", b"--")[int(rng.integers(0, 4))]
+        for _ in range(int(rng.integers(1, max_support + 1))):
+            pa = a + int(rng.integers(-isz, isz))
+            pb = b + int(rng.integers(-isz, isz))
+            if pa >= pb:
+                continue
+            for _ in range(2 if rng.random() < both_mates else 1):
+                rows.append((pa, pb, isz, rl, da, db))
+    for _ in range(background):
+        rl, isz = libraries[int(rng.integers(0, len(libraries)))]
+        pa = int(rng.integers(10_000, max(20_000, span - 2_000_000)))
+        pb = pa + int(rng.integers(1, 1_000_000))
+        da, db = (b"+-", b"-+", b"++", b"--")[int(rng.integers(0, 4))]
+        rows.append((pa, pb, isz, rl, da, db))
+    out = np.zeros(len(rows), dtype=[("pos_a", "<u4"), ("pos_b", "<u4"), ("insert_size", "<u4"), ("read_length", "<i2"), ("da", "u1"), ("db", "u1")])
+    for k, r in enumerate(rows):
+        out[k] = r
+    return out[rng.permutation(len(rows))]

@@ -57,4 +57,7 @@ def sim_prefix_bam(demo, tmp_path, env):
     (tmp_path / "conf.txt").write_text("%s\t500\tSIM1CHRVS2\n" % (tmp_path / "sim_prefix.bam"))
     p = _run(demo, ["-f", str(fa), "-i", str(tmp_path / "conf.txt"), "-o", str(tmp_path / "sim_prefix.out"), "-k", "-s", "-l", "-T", "1"], env)
     _compare(tmp_path, "sim_prefix.out", "sim_prefix", ("D", "SI", "INV", "TD", "LI", "BP", "RP", "CloseEndMapped"))
+    # row N2: the discordant pairs of the window went through pg_rp_modify / pg_rp_summarize (ModifyRP / Summarize bound by symbol)
+    m = re.search(r"(\d+) read pairs clustered on the device \((\d+) launches\)", p.stderr)
+    assert m and int(m.group(1)) > 0 and int(m.group(2)) > 0, p.stderr[-500:]
     return p

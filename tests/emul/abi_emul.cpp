@@ -14,6 +14,7 @@
 
 #include "pg_emul.cpp"
 #include "sv_emul.cpp"
+#include "rp_emul.cpp"
 #include "../../pindel_b200/csrc/pg_host_helpers.h"
 
 struct pg_ctx {
@@ -24,7 +25,7 @@ struct pg_ctx {
    uint32_t table[PG_TABLE];
    std::vector<pg_read_out> out;
    std::vector<pg_run> runs;
-   uint64_t launches = 0, sv_launches = 0;
+   uint64_t launches = 0, sv_launches = 0, rp_launches = 0;
    // copy of the last far-end-only batch ("resident")
    int res_n = -1;
    std::vector<uint8_t> res_seq, res_md;
@@ -196,6 +197,19 @@ int pg_classify_resident(pg_ctx *ctx, const pg_sv_window *win, const uint8_t *rf
    return pg_classify(ctx, &in, win, res);
 }
 
+int pg_rp_modify(pg_ctx *ctx, int32_t n, const pg_rp *in, pg_rp_cluster *out)
+{
+   rpemu_modify(n, (const PgRp *)in, (PgRpCluster *)out);
+   ctx->rp_launches++;
+   return PG_OK;
+}
+int pg_rp_summarize(pg_ctx *ctx, int32_t n, const pg_rp *in, pg_rp_cluster *inout)
+{
+   rpemu_summarize(n, (const PgRp *)in, (PgRpCluster *)inout);
+   ctx->rp_launches++;
+   return PG_OK;
+}
+uint64_t pg_rp_launches(pg_ctx *ctx) { return ctx ? ctx->rp_launches : 0; }
 uint64_t pg_classify_launches(pg_ctx *ctx) { return ctx ? ctx->sv_launches : 0; }
 double pg_classify_last_kernel_ms(pg_ctx *) { return 0.0; }
 uint32_t pg_expand_runs(const pg_run *runs, uint32_t n_runs, pg_up *out) { return pgh_expand_runs(runs, n_runs, out); }
