@@ -33,6 +33,7 @@ extern "C" {
 #define PG_ERR_STATE 3      /* call order (e.g. search before pg_set_reference) */
 #define PG_ERR_RUNS_CAP 4   /* caller's run buffer too small: results->n_runs holds the required size; call pg_download again */
 #define PG_ERR_UNSUPPORTED 5 /* a read is longer, or needs more mismatch levels, than the library supports */
+#define PG_ERR_DATA 6        /* corrupt input data (pg_bgzf_inflate: not BGZF, invalid DEFLATE stream, CRC32 mismatch) */
 
 typedef struct pg_ctx pg_ctx;
 
@@ -297,6 +298,21 @@ uint64_t pg_rp_launches(pg_ctx *ctx);          /* clustering-kernel launches sin
 /* how the last pg_rp_modify split its rows: classes run by one warp each, classes run by one CTA each, rows in either */
 void pg_rp_last_classes(pg_ctx *ctx, uint32_t *warp_classes, uint32_t *cta_classes, uint32_t *rows_in_classes);
 double pg_rp_last_kernel_ms(pg_ctx *ctx);      /* CUDA-event duration of the last call's kernels */
+
+/* ------------------------------------------------------------------------------------------------------------------
+ * BGZF inflation (first half): what htslib's bgzf_read_block / inflate_block do behind
+ * sam_itr_next (src/reader.cpp:1099-1151, 1258-1346), for all blocks of a file (or of any run of whole blocks) at once:
+ * the host walks the block headers (BSIZE, ISIZE, CRC32), one device thread inflates one block (RFC 1951) into its place
+ * in the inflated stream and, with check_crc, recomputes the payload's CRC32 as htslib does.
+ *   out == NULL: the inflated stream stays on the device (pg_bgzf_device_data) for a consumer that parses it there;
+ *   out != NULL: it is also copied to the caller's buffer (out_cap bytes; PG_ERR_RUNS_CAP if too small).
+ * *out_len = inflated size.  PG_ERR_DATA: not a BGZF file / corrupt block (text in pg_last_error).
+ * ------------------------------------------------------------------------------------------------------------------ */
+int64_t pg_bgzf_inflated_size(const uint8_t *file, size_t file_len);   /* host only: -1 if the header walk fails */
+int pg_bgzf_inflate(pg_ctx *ctx, const uint8_t *file, size_t file_len, uint8_t *out, size_t out_cap, size_t *out_len, int32_t check_crc);
+int pg_bgzf_device_data(pg_ctx *ctx, void **dev, size_t *len);         /* the last inflated stream; valid until the next call */
+uint64_t pg_bgzf_launches(pg_ctx *ctx);
+double pg_bgzf_last_kernel_ms(pg_ctx *ctx);
 
 /* Host helper: run-length encode UniquePoints (the inverse of pg_expand_runs) for callers that hold expanded lists.
  * Returns the number of runs (out may be NULL to just count). */

@@ -90,6 +90,14 @@ def load_library() -> C.CDLL:
         lib.pg_last_stats.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
         lib.pg_classify.argtypes = [C.c_void_p, C.POINTER(_SvReads), C.POINTER(_SvWindow), C.POINTER(_SvResults)]
         lib.pg_classify_resident.argtypes = [C.c_void_p, C.POINTER(_SvWindow), C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(_SvResults)]
+        lib.pg_bgzf_inflated_size.restype = C.c_int64
+        lib.pg_bgzf_inflated_size.argtypes = [C.c_void_p, C.c_size_t]
+        lib.pg_bgzf_inflate.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t, C.POINTER(C.c_size_t), C.c_int32]
+        lib.pg_bgzf_device_data.argtypes = [C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_size_t)]
+        lib.pg_bgzf_launches.restype = C.c_uint64
+        lib.pg_bgzf_launches.argtypes = [C.c_void_p]
+        lib.pg_bgzf_last_kernel_ms.restype = C.c_double
+        lib.pg_bgzf_last_kernel_ms.argtypes = [C.c_void_p]
         lib.pg_rp_modify.argtypes = [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p]
         lib.pg_rp_summarize.argtypes = [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p]
         lib.pg_rp_last_classes.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
@@ -311,6 +319,36 @@ class PatternGrowth:
             rc = self.lib.pg_classify_resident(self.ctx, C.byref(w), ptr(fl), ptr(co), ptr(cr), C.byref(res))
         self._check(rc, "pg_classify_resident")
         return rec[:res.n_records]
+
+    def bgzf_inflate(self, data, to_host: bool = True, check_crc: bool = True, out=None):
+        """All BGZF blocks of `data` (bytes or uint8 array) inflated on the device.  -> uint8 array (to_host) or the
+        inflated size (the stream then stays on the device: bgzf_device_data())."""
+        buf = np.frombuffer(data, dtype=np.uint8) if isinstance(data, (bytes, bytearray, memoryview)) else np.ascontiguousarray(data, dtype=np.uint8)
+        n = C.c_size_t(0)
+        if not to_host:
+            self._check(self.lib.pg_bgzf_inflate(self.ctx, buf.ctypes.data, buf.size, None, 0, C.byref(n), int(check_crc)), "pg_bgzf_inflate")
+            return int(n.value)
+        if out is None:
+            total = int(self.lib.pg_bgzf_inflated_size(buf.ctypes.data, buf.size))
+            if total < 0:
+                raise PgError("pg_bgzf_inflated_size: not a BGZF file")
+            out = np.empty(total, dtype=np.uint8)
+        self._check(self.lib.pg_bgzf_inflate(self.ctx, buf.ctypes.data, buf.size, out.ctypes.data, out.size, C.byref(n), int(check_crc)),
+                    "pg_bgzf_inflate")
+        return out[:n.value]
+
+    def bgzf_device_data(self):
+        p, n = C.c_void_p(0), C.c_size_t(0)
+        self._check(self.lib.pg_bgzf_device_data(self.ctx, C.byref(p), C.byref(n)), "pg_bgzf_device_data")
+        return int(p.value or 0), int(n.value)
+
+    @property
+    def bgzf_last_kernel_ms(self) -> float:
+        return float(self.lib.pg_bgzf_last_kernel_ms(self.ctx))
+
+    @property
+    def bgzf_launches(self) -> int:
+        return int(self.lib.pg_bgzf_launches(self.ctx))
 
     def rp_modify(self, rows: np.ndarray) -> np.ndarray:
         """ModifyRP after its sort (src/bddata.cpp:396-430) on the device: rows = pindel_b200.rp.RP_DT in the order the

@@ -1,0 +1,316 @@
+// pindel_b200/csrc/pg_bgzf.cuh -- BGZF block inflation on the device (first half: the
+// "BGZF inflate" of BAM ingestion).  A BAM file is a series of BGZF blocks -- gzip members of at most 64 KiB of payload
+// whose compressed size is in the header -- which is what makes the format parallel: every block is an independent
+// DEFLATE stream (RFC 1951).  The reference reaches this through htslib's bgzf_read_block/inflate_block behind
+// sam_itr_next (src/reader.cpp:1099-1151, 1258-1346); here one warp inflates one block.
+//
+// Written from RFC 1951/1952 and the SAM specification (section 4.1, BGZF).  The decoder is a plain table-driven one:
+//   * per block (= per warp) two fast tables in shared memory: literal/length codes up to 9 bits, distance codes up to
+//     6 bits, entry = symbol << 4 | code length; longer codes fall back to the canonical walk over the length counts;
+//   * a 64-bit bit buffer refilled with aligned 32-bit loads;
+//   * every lane of the warp runs the same decode on the same bits (the Huffman chain is serial; uniform execution costs
+//     no extra issue slots and needs no broadcast), and the lanes split what is parallel: the bytes of a match are copied
+//     32 at a time -- one trip to L2 per match instead of one per byte, which is what a thread-per-block decoder pays
+//     (profiles/r1p_bgzf_kernel_thread_per_block.md: 6.5 GB/s, stalled on the store of every copied byte).
+// __host__ __device__ throughout (the host build is the one-lane case), so the CPU suite runs the identical decoder
+// against zlib (tests/emul/bgzf_emul.cpp).
+#pragma once
+#include <stdint.h>
+
+#ifdef __CUDACC__
+#define PGZ_HD __host__ __device__ __forceinline__
+#define PGZ_FN __host__ __device__
+#else
+#define PGZ_HD inline
+#define PGZ_FN inline
+#endif
+
+#define PGZ_LIT_BITS 9
+#define PGZ_DIST_BITS 6
+#define PGZ_LIT_SIZE (1 << PGZ_LIT_BITS)
+#define PGZ_DIST_SIZE (1 << PGZ_DIST_BITS)
+
+#define PGZ_OK 0
+#define PGZ_ERR_HEADER 1      // block type 3, stored LEN/NLEN mismatch, bad code lengths
+#define PGZ_ERR_CODE 2        // a bit pattern that is no code of the current tree
+#define PGZ_ERR_DIST 3        // distance beyond the start of the output
+#define PGZ_ERR_OUTPUT 4      // more output than ISIZE
+#define PGZ_ERR_INPUT 5       // compressed data exhausted
+#define PGZ_ERR_SIZE 6        // stream ended with fewer bytes than ISIZE
+#define PGZ_ERR_CRC 7         // CRC32 of the payload differs from the trailer's
+
+struct PgzBlock {             // one BGZF block, filled by the host's header walk (pg_bgzf_walk)
+   uint64_t comp_off;         // offset of the DEFLATE data in the file (after the 18-byte header for standard blocks)
+   uint64_t out_off;          // offset of this block's payload in the inflated stream
+   uint32_t comp_len;         // DEFLATE bytes (BSIZE + 1 - header - 8)
+   uint32_t isize;            // payload bytes (ISIZE)
+   uint32_t crc;              // CRC32 of the payload (trailer)
+   uint32_t pad;
+};
+
+// CRC-32 (RFC 1952 section 8): reflected polynomial 0xEDB88320
+PGZ_HD uint32_t pgz_crc_entry(uint32_t i)
+{
+   uint32_t c = i;
+   for (int k = 0; k < 8; k++) c = (c & 1u) ? 0xEDB88320u ^ (c >> 1) : c >> 1;
+   return c;
+}
+PGZ_HD uint32_t pgz_crc32(const uint8_t *p, uint32_t n, const uint32_t *table)
+{
+   uint32_t c = 0xFFFFFFFFu;
+   for (uint32_t i = 0; i < n; i++) c = table[(c ^ p[i]) & 0xFFu] ^ (c >> 8);
+   return c ^ 0xFFFFFFFFu;
+}
+
+// canonical Huffman code: count[len], symbols sorted by (len, symbol)
+struct PgzTree {
+   uint16_t count[16];
+   uint16_t symbol[288];
+};
+
+struct PgzScratch {           // working memory of one decoder (shared memory on the device): 2688 bytes
+   uint16_t fast_lit[PGZ_LIT_SIZE];
+   uint16_t fast_dist[PGZ_DIST_SIZE];
+   PgzTree lit, dist;
+   uint8_t lengths[320];
+};
+
+#if defined(__CUDA_ARCH__)
+#define PGZ_SYNC() __syncwarp()
+#else
+#define PGZ_SYNC() ((void)0)
+#endif
+
+struct PgzBits {
+   const uint32_t *words;     // 4-byte aligned view of the input
+   uint32_t next_word;        // index of the next word to load
+   uint32_t n_words;          // words that may be loaded (input padded to a word)
+   uint64_t buf;
+   uint32_t cnt;              // valid bits in buf
+   uint32_t overrun;          // words requested beyond the input (each delivers zeros)
+};
+
+PGZ_HD void pgz_refill(PgzBits &b)
+{
+   if (b.cnt <= 32u) {
+      uint32_t w = 0u;
+      if (b.next_word < b.n_words) w = b.words[b.next_word];
+      else b.overrun++;
+      b.next_word++;
+      b.buf |= (uint64_t)w << b.cnt;
+      b.cnt += 32u;
+   }
+}
+PGZ_HD uint32_t pgz_peek(const PgzBits &b, uint32_t n) { return (uint32_t)b.buf & ((1u << n) - 1u); }
+PGZ_HD void pgz_drop(PgzBits &b, uint32_t n) { b.buf >>= n; b.cnt -= n; }
+PGZ_HD uint32_t pgz_take(PgzBits &b, uint32_t n) { const uint32_t v = pgz_peek(b, n); pgz_drop(b, n); return v; }
+
+// Build the canonical tree of n code lengths and its fast table (bits-wide, indexed by the next input bits, LSB first).
+// Returns 0, or PGZ_ERR_HEADER for an over-subscribed set of lengths (incomplete sets are accepted, like zlib accepts a
+// single distance code; an unassigned pattern then decodes to PGZ_ERR_CODE).
+PGZ_FN int pgz_build(const uint8_t *lengths, int n, PgzTree &t, uint16_t *fast, int bits)
+{
+   for (int l = 0; l < 16; l++) t.count[l] = 0;
+   for (int s = 0; s < n; s++) t.count[lengths[s]]++;
+   uint16_t offs[16];
+   offs[1] = 0;
+   int left = 1;
+   for (int l = 1; l < 16; l++) {
+      left <<= 1;
+      left -= t.count[l];
+      if (left < 0) return PGZ_ERR_HEADER;
+      if (l < 15) offs[l + 1] = (uint16_t)(offs[l] + t.count[l]);
+   }
+   for (int s = 0; s < n; s++)
+      if (lengths[s]) t.symbol[offs[lengths[s]]++] = (uint16_t)s;
+   for (int i = 0; i < (1 << bits); i++) fast[i] = 0;
+   // codes of length l are consecutive, in symbol order, starting at first[l]
+   uint32_t code = 0, index = 0;
+   for (int l = 1; l <= bits; l++) {
+      for (uint32_t k = 0; k < t.count[l]; k++, code++, index++) {
+         uint32_t rev = 0;
+         for (int i = 0; i < l; i++) rev |= ((code >> i) & 1u) << (l - 1 - i);
+         const uint16_t e = (uint16_t)(t.symbol[index] << 4 | l);
+         for (uint32_t i = rev; i < (1u << bits); i += 1u << l) fast[i] = e;
+      }
+      code <<= 1;
+   }
+   return PGZ_OK;
+}
+
+// one symbol: fast table, else the canonical walk (RFC 1951 3.2.2) from the first length the table does not cover
+PGZ_HD int pgz_decode(PgzBits &b, const PgzTree &t, const uint16_t *fast, int bits)
+{
+   const uint16_t e = fast[pgz_peek(b, (uint32_t)bits)];
+   if (e & 15u) {
+      pgz_drop(b, e & 15u);
+      return e >> 4;
+   }
+   int code = 0, first = 0, index = 0;
+   uint64_t v = b.buf;
+   for (int l = 1; l < 16; l++) {
+      code |= (int)(v & 1u);
+      v >>= 1;
+      const int c = t.count[l];
+      if (code - c < first) {
+         pgz_drop(b, (uint32_t)l);
+         return t.symbol[index + (code - first)];
+      }
+      index += c;
+      first += c;
+      first <<= 1;
+      code <<= 1;
+   }
+   return -1;
+}
+
+// Inflate one raw DEFLATE stream of in_len bytes at `in` into out[0, isize).  Called by all `nlanes` lanes of a decoder
+// (32 on the device, 1 on the host) with identical arguments but `lane`; sc is the decoder's scratch.  Returns PGZ_OK or an
+// error (the same in every lane); *produced = bytes written.
+PGZ_FN int pgz_inflate(const uint8_t *in, uint32_t in_len, uint8_t *out, uint32_t isize, PgzScratch *sc, uint32_t lane, uint32_t nlanes,
+                       uint32_t *produced)
+{
+   const uint8_t len_order[19] = {16, 17, 18, 0, 8, 7, 9, 6, 10, 5, 11, 4, 12, 3, 13, 2, 14, 1, 15};
+   const uint16_t len_base[29] = {3, 4, 5, 6, 7, 8, 9, 10, 11, 13, 15, 17, 19, 23, 27, 31, 35, 43, 51, 59, 67, 83, 99, 115, 131, 163, 195, 227, 258};
+   const uint8_t len_extra[29] = {0, 0, 0, 0, 0, 0, 0, 0, 1, 1, 1, 1, 2, 2, 2, 2, 3, 3, 3, 3, 4, 4, 4, 4, 5, 5, 5, 5, 0};
+   const uint16_t dist_base[30] = {1, 2, 3, 4, 5, 7, 9, 13, 17, 25, 33, 49, 65, 97, 129, 193, 257, 385, 513, 769, 1025, 1537, 2049, 3073, 4097, 6145,
+                                   8193, 12289, 16385, 24577};
+   const uint8_t dist_extra[30] = {0, 0, 0, 0, 1, 1, 2, 2, 3, 3, 4, 4, 5, 5, 6, 6, 7, 7, 8, 8, 9, 9, 10, 10, 11, 11, 12, 12, 13, 13};
+   uint8_t *lengths = sc->lengths;
+   PgzBits b;
+   const uint32_t mis = (uint32_t)((uintptr_t)in & 3u);
+   b.words = reinterpret_cast<const uint32_t *>(in - mis);
+   b.n_words = (in_len + mis + 3u) / 4u;
+   b.next_word = 0;
+   b.buf = 0;
+   b.cnt = 0;
+   b.overrun = 0;
+   pgz_refill(b);
+   pgz_drop(b, 8u * mis);
+   uint32_t op = 0;
+   int rc = PGZ_OK;
+   for (int last = 0; !last && rc == PGZ_OK;) {
+      pgz_refill(b);
+      last = (int)pgz_take(b, 1);
+      const uint32_t type = pgz_take(b, 2);
+      if (type == 0) {                       // stored: skip to the byte boundary, LEN, NLEN, bytes
+         pgz_drop(b, b.cnt & 7u);
+         pgz_refill(b);
+         const uint32_t len = pgz_take(b, 16);
+         pgz_refill(b);
+         const uint32_t nlen = pgz_take(b, 16);
+         if ((len ^ 0xFFFFu) != nlen) { rc = PGZ_ERR_HEADER; break; }
+         if (op + len > isize) { rc = PGZ_ERR_OUTPUT; break; }
+         for (uint32_t k = 0; k < len; k++) {
+            pgz_refill(b);
+            const uint8_t v = (uint8_t)pgz_take(b, 8);
+            if (lane == 0) out[op] = v;
+            op++;
+         }
+         continue;
+      }
+      if (type == 3) { rc = PGZ_ERR_HEADER; break; }
+      if (type == 1) {                       // fixed codes (RFC 1951 3.2.6)
+         for (int s = 0; s < 144; s++) lengths[s] = 8;
+         for (int s = 144; s < 256; s++) lengths[s] = 9;
+         for (int s = 256; s < 280; s++) lengths[s] = 7;
+         for (int s = 280; s < 288; s++) lengths[s] = 8;
+         pgz_build(lengths, 288, sc->lit, sc->fast_lit, PGZ_LIT_BITS);
+         for (int s = 0; s < 30; s++) lengths[s] = 5;
+         pgz_build(lengths, 30, sc->dist, sc->fast_dist, PGZ_DIST_BITS);
+      } else {                               // dynamic codes (3.2.7)
+         pgz_refill(b);
+         const int nlen = (int)pgz_take(b, 5) + 257, ndist = (int)pgz_take(b, 5) + 1, ncode = (int)pgz_take(b, 4) + 4;
+         if (nlen > 286 || ndist > 30) { rc = PGZ_ERR_HEADER; break; }
+         uint8_t cl[19];
+         for (int i = 0; i < 19; i++) cl[i] = 0;
+         for (int i = 0; i < ncode; i++) {
+            pgz_refill(b);
+            cl[len_order[i]] = (uint8_t)pgz_take(b, 3);
+         }
+         // the code-length code borrows the literal tree's storage and the distance table's 64 entries
+         if (pgz_build(cl, 19, sc->lit, sc->fast_dist, PGZ_DIST_BITS) != PGZ_OK) { rc = PGZ_ERR_HEADER; break; }
+         int idx = 0;
+         while (idx < nlen + ndist) {
+            pgz_refill(b);
+            const int sym = pgz_decode(b, sc->lit, sc->fast_dist, PGZ_DIST_BITS);
+            if (sym < 0) { rc = PGZ_ERR_CODE; break; }
+            if (sym < 16) {
+               lengths[idx++] = (uint8_t)sym;
+               continue;
+            }
+            int prev = 0, rep;
+            if (sym == 16) {
+               if (idx == 0) { rc = PGZ_ERR_HEADER; break; }
+               prev = lengths[idx - 1];
+               rep = 3 + (int)pgz_take(b, 2);
+            } else if (sym == 17) rep = 3 + (int)pgz_take(b, 3);
+            else rep = 11 + (int)pgz_take(b, 7);
+            if (idx + rep > nlen + ndist) { rc = PGZ_ERR_HEADER; break; }
+            while (rep--) lengths[idx++] = (uint8_t)prev;
+         }
+         if (rc != PGZ_OK) break;
+         if (lengths[256] == 0) { rc = PGZ_ERR_HEADER; break; }   // no end-of-block code
+         if (pgz_build(lengths, nlen, sc->lit, sc->fast_lit, PGZ_LIT_BITS) != PGZ_OK) { rc = PGZ_ERR_HEADER; break; }
+         if (pgz_build(lengths + nlen, ndist, sc->dist, sc->fast_dist, PGZ_DIST_BITS) != PGZ_OK) { rc = PGZ_ERR_HEADER; break; }
+      }
+      for (;;) {                             // the symbols of this block
+         pgz_refill(b);
+         int sym = pgz_decode(b, sc->lit, sc->fast_lit, PGZ_LIT_BITS);
+         if (sym < 0) { rc = PGZ_ERR_CODE; break; }
+         if (sym < 256) {
+            if (op >= isize) { rc = PGZ_ERR_OUTPUT; break; }
+            if (lane == 0) out[op] = (uint8_t)sym;
+            op++;
+            continue;
+         }
+         if (sym == 256) break;
+         sym -= 257;
+         if (sym >= 29) { rc = PGZ_ERR_CODE; break; }
+         const uint32_t len = len_base[sym] + pgz_take(b, len_extra[sym]);
+         pgz_refill(b);
+         const int ds = pgz_decode(b, sc->dist, sc->fast_dist, PGZ_DIST_BITS);
+         if (ds < 0 || ds >= 30) { rc = PGZ_ERR_CODE; break; }
+         const uint32_t d = dist_base[ds] + pgz_take(b, dist_extra[ds]);
+         if (d > op) { rc = PGZ_ERR_DIST; break; }
+         if (op + len > isize) { rc = PGZ_ERR_OUTPUT; break; }
+         // every source byte lies before op (a match that overlaps its own output repeats its first d bytes), so the lanes
+         // copy independently once the earlier stores of the other lanes are visible
+         PGZ_SYNC();
+         const uint8_t *src = out + op - d;
+         for (uint32_t k = lane; k < len; k += nlanes) out[op + k] = src[d >= len ? k : k % d];
+         op += len;
+      }
+      if (b.overrun > 2u) rc = PGZ_ERR_INPUT;   // the bit buffer may look one or two words past the end; decoding from there is an error
+   }
+   PGZ_SYNC();
+   *produced = op;
+   if (rc == PGZ_OK && op != isize) rc = PGZ_ERR_SIZE;
+   return rc;
+}
+
+#ifdef __CUDACC__
+#define PGZ_WARPS 8      // decoders per CTA: 8 x 2688 B of scratch
+
+// status[b] = PGZ_* of block b; one warp per block.  check_crc: also recompute the payload's CRC32 (what htslib's
+// bgzf_read_block does) while the block is still in cache -- lane 0 alone, byte by byte.
+__global__ void __launch_bounds__(32 * PGZ_WARPS) pg_bgzf_inflate_kernel(const uint8_t *__restrict__ file, const PgzBlock *__restrict__ blocks,
+                                                                        uint32_t n_blocks, uint8_t *__restrict__ out, uint32_t *__restrict__ status,
+                                                                        int check_crc)
+{
+   __shared__ PgzScratch scratch[PGZ_WARPS];
+   __shared__ uint32_t crc_table[256];
+   for (uint32_t k = threadIdx.x; k < 256u; k += 32 * PGZ_WARPS) crc_table[k] = pgz_crc_entry(k);
+   __syncthreads();
+   const uint32_t w = threadIdx.x >> 5, lane = threadIdx.x & 31u;
+   const uint32_t i = blockIdx.x * PGZ_WARPS + w;
+   if (i >= n_blocks) return;
+   const PgzBlock bl = blocks[i];
+   uint32_t produced = 0;
+   int rc = pgz_inflate(file + bl.comp_off, bl.comp_len, out + bl.out_off, bl.isize, &scratch[w], lane, 32u, &produced);
+   if (lane == 0) {
+      if (rc == PGZ_OK && check_crc && pgz_crc32(out + bl.out_off, bl.isize, crc_table) != bl.crc) rc = PGZ_ERR_CRC;
+      status[i] = (uint32_t)rc;
+   }
+}
+#endif

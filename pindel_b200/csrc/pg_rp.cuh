@@ -268,22 +268,43 @@ __global__ void pg_rp_single_kernel(int n, const PgRp *__restrict__ in, PgRpClus
 }
 
 // Summarize, first loop (src/bddata.cpp:480-513): every unvisited row joins the first unvisited row with the same
-// intervals and strands.  One warp per row scans the rows before it, 32 at a time, and stops at the first match.
+// intervals and strands.  One warp per row scans the rows before it, 32 at a time, and stops at the first match; what it
+// scans is one 64-bit key per row (a mix of the six compared fields; visited rows get a key nothing matches), so the
+// quadratic part moves 8 bytes per pair, and the fields themselves are only read to confirm a key match.
 // counters: [0] number of "good" rows (unvisited firsts with index <= n - 2), [1] the largest such index.
+PGRP_HD uint64_t pg_rp_mix(uint64_t h, uint64_t v)
+{
+   h ^= v + 0x9E3779B97F4A7C15ull + (h << 6) + (h >> 2);
+   h *= 0xFF51AFD7ED558CCDull;
+   return h ^ (h >> 33);
+}
+
+__global__ void pg_rp_key_kernel(int n, const PgRp *__restrict__ in, const PgRpCluster *__restrict__ st, uint64_t *__restrict__ keys)
+{
+   const int i = blockIdx.x * blockDim.x + threadIdx.x;
+   if (i >= n) return;
+   const PgRpCluster o = st[i];
+   uint64_t h = pg_rp_mix(0x243F6A8885A308D3ull, (uint64_t)o.pos_a << 32 | o.pos_a1);
+   h = pg_rp_mix(h, (uint64_t)o.pos_b << 32 | o.pos_b1);
+   h = pg_rp_mix(h, (uint64_t)in[i].da << 8 | in[i].db);
+   keys[i] = o.visited ? ~(uint64_t)i : (h & 0x7FFFFFFFFFFFFFFFull);   // visited rows: top bit set, all different
+}
+
 __global__ void __launch_bounds__(256) pg_rp_group_kernel(int n, const PgRp *__restrict__ in, const PgRpCluster *__restrict__ st,
-                                                          uint32_t *__restrict__ merged_into, uint32_t *__restrict__ n_identical,
-                                                          uint32_t *__restrict__ counters)
+                                                          const uint64_t *__restrict__ keys, uint32_t *__restrict__ merged_into,
+                                                          uint32_t *__restrict__ n_identical, uint32_t *__restrict__ counters)
 {
    const int i = (int)((blockIdx.x * blockDim.x + threadIdx.x) >> 5), lane = threadIdx.x & 31;
    if (i >= n) return;
    const PgRpCluster me = st[i];
    const PgRp mi = in[i];
+   const uint64_t mykey = keys[i];
    uint32_t rep = (uint32_t)i;
    if (!me.visited) {
       for (int c0 = 0; c0 < i; c0 += 32) {
          const int j = c0 + lane;
-         bool eq = false;
-         if (j < i) {
+         bool eq = j < i && keys[j] == mykey;
+         if (eq) {                                  // rare: confirm on the fields themselves
             const PgRpCluster o = st[j];
             eq = !o.visited && pg_rp_same_event(me, mi, o, in[j]);
          }

@@ -20,6 +20,8 @@
 #include "pg_sv.cuh"
 #include "pg_rp.cuh"
 #include "pg_rp_host.h"
+#include "pg_bgzf.cuh"
+#include "pg_bgzf_host.h"
 #include "pg_params.h"
 #include "../../include/pindel_pg.h"
 #include "pg_host_helpers.h"
@@ -366,8 +368,13 @@ struct pg_ctx {
    PgSvParams sv_params_h;          // staging copy (the async upload reads it until the stream drains)
    DevBuf sv_close_off, sv_close_runs;
    uint64_t sv_aux_launches = 0;
+   // BGZF inflation (pg_bgzf_inflate)
+   DevBuf bz_file, bz_blocks, bz_out, bz_status;
+   size_t bz_out_len = 0;
+   uint64_t bz_launches = 0;
+   float bz_last_ms = 0.f;
    // read-pair clustering (pg_rp_modify / pg_rp_summarize)
-   DevBuf rp_in, rp_out, rp_rows, rp_off, rp_scratch, rp_merged, rp_nid, rp_counters;
+   DevBuf rp_in, rp_out, rp_rows, rp_off, rp_scratch, rp_merged, rp_nid, rp_counters, rp_keys;
    uint64_t rp_launches = 0;
    uint32_t rp_classes_small = 0, rp_classes_big = 0, rp_rows_in_classes = 0;   // of the last pg_rp_modify
    float rp_last_ms = 0.f;    // scan + order kernels
@@ -525,7 +532,7 @@ void pg_destroy(pg_ctx *ctx)
                        &ctx->sv_runs, &ctx->sv_records, &ctx->sv_params, &ctx->sv_counters,
                        &ctx->sv_counts, &ctx->sv_offsets, &ctx->sv_blocksums, &ctx->sv_ordered, &ctx->sv_close_off,
                        &ctx->sv_close_runs, &ctx->rp_in, &ctx->rp_out, &ctx->rp_rows, &ctx->rp_off, &ctx->rp_scratch, &ctx->rp_merged,
-                       &ctx->rp_nid, &ctx->rp_counters};
+                       &ctx->rp_nid, &ctx->rp_counters, &ctx->rp_keys, &ctx->bz_file, &ctx->bz_blocks, &ctx->bz_out, &ctx->bz_status};
    for (DevBuf *b : svbufs) if (b->p) cudaFree(b->p);
    pipe_destroy(ctx->pipe);
    if (ctx->chroms_d) cudaFree(ctx->chroms_d);
@@ -1213,6 +1220,72 @@ int pg_classify_resident(pg_ctx *ctx, const pg_sv_window *win, const uint8_t *rf
 uint64_t pg_classify_launches(pg_ctx *ctx) { return ctx ? ctx->sv_launches : 0; }
 double pg_classify_last_kernel_ms(pg_ctx *ctx) { return ctx ? (double)ctx->sv_last_ms : 0.0; }
 
+// ---- BGZF inflation (row N3, first half) ---------------------------------------------------------------------------
+static_assert(sizeof(PgzBlock) == 32, "bgzf block layout");
+
+int64_t pg_bgzf_inflated_size(const uint8_t *file, size_t file_len)
+{
+   if (!file && file_len) return -1;
+   std::vector<PgzBlock> blocks;
+   if (pg_bgzf_walk(file, file_len, blocks, nullptr) < 0) return -1;
+   return blocks.empty() ? 0 : (int64_t)(blocks.back().out_off + blocks.back().isize);
+}
+
+int pg_bgzf_inflate(pg_ctx *ctx, const uint8_t *file, size_t file_len, uint8_t *out, size_t out_cap, size_t *out_len, int32_t check_crc)
+{
+   if (!ctx || (!file && file_len) || !out_len) return fail(ctx, PG_ERR_ARG, "pg_bgzf_inflate: bad arguments");
+   std::vector<PgzBlock> blocks;
+   size_t bad = 0;
+   if (pg_bgzf_walk(file, file_len, blocks, &bad) < 0)
+      return fail(ctx, PG_ERR_DATA, "pg_bgzf_inflate: not a BGZF block header at offset " + std::to_string(bad));
+   const size_t total = blocks.empty() ? 0 : (size_t)(blocks.back().out_off + blocks.back().isize);
+   *out_len = total;
+   ctx->bz_out_len = 0;
+   if (out && out_cap < total) return fail(ctx, PG_ERR_RUNS_CAP, "pg_bgzf_inflate: output buffer too small (out_len holds the required size)");
+   if (blocks.empty()) return PG_OK;
+   CU(cudaSetDevice(ctx->device));
+   cudaStream_t st = ctx->stream;
+   const uint32_t nb = (uint32_t)blocks.size();
+   int rc;
+   if ((rc = ensure(ctx, ctx->bz_file, file_len + 16)) != PG_OK) return rc;        // the bit reader may look a word past the end
+   if ((rc = ensure(ctx, ctx->bz_blocks, sizeof(PgzBlock) * (size_t)nb)) != PG_OK) return rc;
+   if ((rc = ensure(ctx, ctx->bz_out, total + 16)) != PG_OK) return rc;
+   if ((rc = ensure(ctx, ctx->bz_status, sizeof(uint32_t) * (size_t)nb)) != PG_OK) return rc;
+   CU(cudaMemcpyAsync(ctx->bz_file.p, file, file_len, cudaMemcpyHostToDevice, st));
+   CU(cudaMemsetAsync((uint8_t *)ctx->bz_file.p + file_len, 0, 16, st));
+   CU(cudaMemcpyAsync(ctx->bz_blocks.p, blocks.data(), sizeof(PgzBlock) * (size_t)nb, cudaMemcpyHostToDevice, st));
+   if (!ctx->sv_ev0) { CU(cudaEventCreate(&ctx->sv_ev0)); CU(cudaEventCreate(&ctx->sv_ev1)); }
+   CU(cudaEventRecord(ctx->sv_ev0, st));
+   pg_bgzf_inflate_kernel<<<(nb + PGZ_WARPS - 1) / PGZ_WARPS, 32 * PGZ_WARPS, 0, st>>>((const uint8_t *)ctx->bz_file.p, (const PgzBlock *)ctx->bz_blocks.p,
+                                                                                           nb, (uint8_t *)ctx->bz_out.p, (uint32_t *)ctx->bz_status.p,
+                                                                                           check_crc ? 1 : 0);
+   CU(cudaGetLastError());
+   CU(cudaEventRecord(ctx->sv_ev1, st));
+   ctx->bz_launches++;
+   std::vector<uint32_t> status(nb);
+   CU(cudaMemcpyAsync(status.data(), ctx->bz_status.p, sizeof(uint32_t) * (size_t)nb, cudaMemcpyDeviceToHost, st));
+   if (out && total) CU(cudaMemcpyAsync(out, ctx->bz_out.p, total, cudaMemcpyDeviceToHost, st));
+   CU(cudaStreamSynchronize(st));
+   CU(cudaEventElapsedTime(&ctx->bz_last_ms, ctx->sv_ev0, ctx->sv_ev1));
+   for (uint32_t i = 0; i < nb; i++)
+      if (status[i] != PGZ_OK)
+         return fail(ctx, PG_ERR_DATA, "pg_bgzf_inflate: block " + std::to_string(i) + " (file offset " + std::to_string(blocks[i].comp_off) +
+                                           ") is corrupt: " + (status[i] == PGZ_ERR_CRC ? "CRC32 mismatch" : "invalid DEFLATE stream, code " + std::to_string(status[i])));
+   ctx->bz_out_len = total;
+   return PG_OK;
+}
+
+int pg_bgzf_device_data(pg_ctx *ctx, void **dev, size_t *len)
+{
+   if (!ctx || !dev || !len) return fail(ctx, PG_ERR_ARG, "pg_bgzf_device_data: null argument");
+   *dev = ctx->bz_out_len ? ctx->bz_out.p : nullptr;
+   *len = ctx->bz_out_len;
+   return PG_OK;
+}
+
+uint64_t pg_bgzf_launches(pg_ctx *ctx) { return ctx ? ctx->bz_launches : 0; }
+double pg_bgzf_last_kernel_ms(pg_ctx *ctx) { return ctx ? (double)ctx->bz_last_ms : 0.0; }
+
 // ---- read-pair clustering (row N2) --------------------------------------------------------------------------------
 static_assert(sizeof(pg_rp) == sizeof(PgRp) && sizeof(pg_rp) == 16, "rp layout");
 static_assert(sizeof(pg_rp_cluster) == sizeof(PgRpCluster) && sizeof(pg_rp_cluster) == 28, "rp cluster layout");
@@ -1286,19 +1359,21 @@ int pg_rp_summarize(pg_ctx *ctx, int32_t n, const pg_rp *in, pg_rp_cluster *inou
    if ((rc = ensure(ctx, ctx->rp_merged, sizeof(uint32_t) * (size_t)n)) != PG_OK) return rc;
    if ((rc = ensure(ctx, ctx->rp_nid, sizeof(uint32_t) * (size_t)n)) != PG_OK) return rc;
    if ((rc = ensure(ctx, ctx->rp_counters, sizeof(uint32_t) * 2)) != PG_OK) return rc;
+   if ((rc = ensure(ctx, ctx->rp_keys, sizeof(uint64_t) * (size_t)n)) != PG_OK) return rc;
    CU(cudaMemcpyAsync(ctx->rp_in.p, in, sizeof(PgRp) * (size_t)n, cudaMemcpyHostToDevice, st));
    CU(cudaMemcpyAsync(ctx->rp_out.p, inout, sizeof(PgRpCluster) * (size_t)n, cudaMemcpyHostToDevice, st));
    CU(cudaMemsetAsync(ctx->rp_nid.p, 0, sizeof(uint32_t) * (size_t)n, st));
    CU(cudaMemsetAsync(ctx->rp_counters.p, 0, sizeof(uint32_t) * 2, st));
    if (!ctx->sv_ev0) { CU(cudaEventCreate(&ctx->sv_ev0)); CU(cudaEventCreate(&ctx->sv_ev1)); }
    CU(cudaEventRecord(ctx->sv_ev0, st));
+   pg_rp_key_kernel<<<(n + 255) / 256, 256, 0, st>>>(n, (const PgRp *)ctx->rp_in.p, (const PgRpCluster *)ctx->rp_out.p, (uint64_t *)ctx->rp_keys.p);
    pg_rp_group_kernel<<<(n + 7) / 8, 256, 0, st>>>(n, (const PgRp *)ctx->rp_in.p, (const PgRpCluster *)ctx->rp_out.p,
-                                                   (uint32_t *)ctx->rp_merged.p, (uint32_t *)ctx->rp_nid.p, (uint32_t *)ctx->rp_counters.p);
+                                                   (const uint64_t *)ctx->rp_keys.p, (uint32_t *)ctx->rp_merged.p, (uint32_t *)ctx->rp_nid.p, (uint32_t *)ctx->rp_counters.p);
    pg_rp_report_kernel<<<(n + 255) / 256, 256, 0, st>>>(n, (PgRpCluster *)ctx->rp_out.p, (const uint32_t *)ctx->rp_merged.p,
                                                        (const uint32_t *)ctx->rp_nid.p, (const uint32_t *)ctx->rp_counters.p);
    CU(cudaGetLastError());
    CU(cudaEventRecord(ctx->sv_ev1, st));
-   ctx->rp_launches += 2;
+   ctx->rp_launches += 3;
    CU(cudaMemcpyAsync(inout, ctx->rp_out.p, sizeof(PgRpCluster) * (size_t)n, cudaMemcpyDeviceToHost, st));
    CU(cudaStreamSynchronize(st));
    CU(cudaEventElapsedTime(&ctx->rp_last_ms, ctx->sv_ev0, ctx->sv_ev1));

@@ -260,3 +260,31 @@ def make_discordant_pairs(n_events: int, seed: int, span: int = 60_000_000, back
     for k, r in enumerate(rows):
         out[k] = r
     return out[rng.permutation(len(rows))]
+
+
+def make_bam_like_bytes(n: int, seed: int) -> bytes:
+    """n bytes that compress like BAM records do (for the BGZF inflater's tests and benchmark): per 200-byte record eight
+    little-endian integers (refID, an increasing position, bin/mapq, flag, l_seq, mate fields), a read name with a running
+    number, 50 bytes of 4-bit packed sequence and 100 quality bytes with runs.  Vectorised."""
+    rng = np.random.default_rng(seed)
+    k = n // 200 + 1
+    rec = np.zeros((k, 200), dtype=np.uint8)
+    core = np.zeros((k, 8), dtype="<i4")
+    core[:, 1] = 10_000 + np.cumsum(rng.integers(0, 40, k))
+    core[:, 2] = 0x12340000 | rng.integers(0, 61, k)
+    core[:, 3] = rng.choice(np.array([99, 147, 83, 163, 73, 133], dtype=np.int32), k)
+    core[:, 4] = 100
+    core[:, 6] = core[:, 1] + rng.integers(200, 600, k)
+    core[:, 7] = rng.integers(-600, 600, k)
+    rec[:, :32] = core.view(np.uint8).reshape(k, 32)
+    num = rng.integers(0, 10**9, k)
+    name = np.frombuffer(b"read_000000000\0\0\0\0", dtype=np.uint8).copy()
+    rec[:, 32:50] = name
+    for d in range(9):
+        rec[:, 45 - d] = 48 + (num // 10**d) % 10
+    rec[:, 50:100] = rng.integers(0, 256, (k, 50), dtype=np.uint8)     # 4-bit bases: incompressible beyond the symbol skew
+    q = np.repeat(rng.integers(2, 41, (k, 10), dtype=np.uint8), 10, axis=1)
+    noise = rng.random((k, 100)) < 0.15
+    q[noise] = rng.integers(2, 41, int(noise.sum()), dtype=np.uint8)
+    rec[:, 100:200] = q + 33
+    return rec.tobytes()[:n]
