@@ -701,17 +701,35 @@ int searchInversionsNT(ControlState &currentState, unsigned NumBoxes, const Sear
    return EXIT_SUCCESS;
 }
 
+/* Row N3 (first half): the BAM reader behind the reference's htslib calls (oracle/shim/minihts.cpp) inflates the file
+ * through pg_bgzf_inflate instead of zlib.  PG_BRIDGE_ZLIB=1 keeps zlib (the test compares both). */
+extern "C" int (*minihts_inflate_hook)(const uint8_t *file, size_t len, std::vector<uint8_t> &out);
+static unsigned long g_bgzf_bytes = 0;
+static int deviceInflate(const uint8_t *file, size_t len, std::vector<uint8_t> &out)
+{
+   std::lock_guard<std::mutex> lock(g_mutex);
+   ensureContext();
+   const int64_t total = pg_bgzf_inflated_size(file, len);
+   if (total < 0) { std::fprintf(stderr, "pindel_gpu_demo: not a BGZF file\n"); return 1; }
+   out.resize((size_t)total);
+   size_t got = 0;
+   if (pg_bgzf_inflate(g_ctx, file, len, out.empty() ? NULL : &out[0], out.size(), &got, 1) != PG_OK) die("pg_bgzf_inflate");
+   g_bgzf_bytes += (unsigned long)got;
+   return 0;
+}
+
 static void reportAtExit()
 {
    std::fprintf(stderr, "pindel_gpu_demo: %lu GetCloseEnd calls and %lu far-end reads served by libpindel_pg (%llu kernel launches); "
-                "%lu reads classified by the SV drivers on the device, %lu records (%llu launches), %lu of the reads without a second upload; %lu read pairs clustered on the device (%llu launches)\n",
+                "%lu reads classified by the SV drivers on the device, %lu records (%llu launches), %lu of the reads without a second upload; %lu read pairs clustered on the device (%llu launches); %lu BAM bytes inflated on the device\n",
                 g_close_calls, g_far_reads, g_ctx ? (unsigned long long)pg_kernel_launches(g_ctx) : 0ull, g_sv_reads, g_sv_records,
                 g_ctx ? (unsigned long long)pg_classify_launches(g_ctx) : 0ull, g_sv_resident, g_rp_rows,
-                g_ctx ? (unsigned long long)pg_rp_launches(g_ctx) : 0ull);
+                g_ctx ? (unsigned long long)pg_rp_launches(g_ctx) : 0ull, g_bgzf_bytes);
 }
 
 int main(int argc, char *argv[])
 {
    std::atexit(reportAtExit);        /* the reference's main() leaves through exit() */
+   if (getenv("PG_BRIDGE_ZLIB") == NULL) minihts_inflate_hook = deviceInflate;
    return pindel_reference_main(argc, argv);
 }

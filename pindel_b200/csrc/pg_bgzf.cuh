@@ -62,6 +62,47 @@ PGZ_HD uint32_t pgz_crc32(const uint8_t *p, uint32_t n, const uint32_t *table)
    return c ^ 0xFFFFFFFFu;
 }
 
+// CRC of a concatenation from the CRCs of its parts (the polynomial identity zlib's crc32_combine uses): with the bits of a
+// CRC read as a polynomial over GF(2) modulo P, appending n zero bytes multiplies by x^(8n), so
+// crc(A || B) = crc(A) * x^(8 |B|) mod P  xor  crc(B).  Lets the 32 lanes of a warp checksum 32 slices of a block.
+PGZ_HD uint32_t pgz_multmodp(uint32_t a, uint32_t b)
+{
+   uint32_t m = 1u << 31, p = 0;
+   for (;;) {
+      if (a & m) {
+         p ^= b;
+         if ((a & (m - 1u)) == 0) break;
+      }
+      m >>= 1;
+      b = (b & 1u) ? (b >> 1) ^ 0xEDB88320u : b >> 1;
+   }
+   return p;
+}
+PGZ_HD uint32_t pgz_xpow_bytes(uint32_t n)      // x^(8 n) mod P
+{
+   uint32_t p = 1u << 31, sq = 0x00800000u;    // x^0; x^8 (bit 31 - k holds the coefficient of x^k)
+   while (n) {
+      if (n & 1u) p = pgz_multmodp(sq, p);
+      sq = pgz_multmodp(sq, sq);
+      n >>= 1;
+   }
+   return p;
+}
+// crcs[s] = CRC-32 of slice s, slices of `slice` bytes (the last one shorter, trailing ones possibly empty)
+PGZ_HD uint32_t pgz_crc_combine_slices(const uint32_t *crcs, uint32_t n_slices, uint32_t slice, uint32_t total)
+{
+   if (total == 0) return 0;
+   const uint32_t full = pgz_xpow_bytes(slice);
+   uint32_t acc = crcs[0];
+   for (uint32_t s = 1; s < n_slices; s++) {
+      const uint32_t begin = s * slice;
+      if (begin >= total) break;
+      const uint32_t len = total - begin < slice ? total - begin : slice;
+      acc = pgz_multmodp(len == slice ? full : pgz_xpow_bytes(len), acc) ^ crcs[s];
+   }
+   return acc;
+}
+
 // canonical Huffman code: count[len], symbols sorted by (len, symbol)
 struct PgzTree {
    uint16_t count[16];
@@ -293,7 +334,7 @@ PGZ_FN int pgz_inflate(const uint8_t *in, uint32_t in_len, uint8_t *out, uint32_
 #define PGZ_WARPS 8      // decoders per CTA: 8 x 2688 B of scratch
 
 // status[b] = PGZ_* of block b; one warp per block.  check_crc: also recompute the payload's CRC32 (what htslib's
-// bgzf_read_block does) while the block is still in cache -- lane 0 alone, byte by byte.
+// bgzf_read_block does) while the block is still in cache: every lane checksums one 32nd of the payload, lane 0 combines.
 __global__ void __launch_bounds__(32 * PGZ_WARPS) pg_bgzf_inflate_kernel(const uint8_t *__restrict__ file, const PgzBlock *__restrict__ blocks,
                                                                         uint32_t n_blocks, uint8_t *__restrict__ out, uint32_t *__restrict__ status,
                                                                         int check_crc)
@@ -308,9 +349,14 @@ __global__ void __launch_bounds__(32 * PGZ_WARPS) pg_bgzf_inflate_kernel(const u
    const PgzBlock bl = blocks[i];
    uint32_t produced = 0;
    int rc = pgz_inflate(file + bl.comp_off, bl.comp_len, out + bl.out_off, bl.isize, &scratch[w], lane, 32u, &produced);
-   if (lane == 0) {
-      if (rc == PGZ_OK && check_crc && pgz_crc32(out + bl.out_off, bl.isize, crc_table) != bl.crc) rc = PGZ_ERR_CRC;
-      status[i] = (uint32_t)rc;
+   if (rc == PGZ_OK && check_crc) {
+      const uint32_t slice = (bl.isize + 31u) / 32u, begin = lane * slice;
+      const uint32_t len = begin >= bl.isize ? 0u : (bl.isize - begin < slice ? bl.isize - begin : slice);
+      uint32_t *crcs = reinterpret_cast<uint32_t *>(scratch[w].fast_lit);     // the tables are no longer needed
+      crcs[lane] = pgz_crc32(out + bl.out_off + begin, len, crc_table);
+      __syncwarp();
+      if (lane == 0 && pgz_crc_combine_slices(crcs, 32u, slice, bl.isize) != bl.crc) rc = PGZ_ERR_CRC;
    }
+   if (lane == 0) status[i] = (uint32_t)rc;
 }
 #endif

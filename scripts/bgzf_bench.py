@@ -56,6 +56,17 @@ def main():
                      "kernel_GBps_in_plus_out": (total + buf.size) / (float(np.median(kern)) * 1e-3) / 1e9,
                      "e2e_device_resident_ms": 1e3 * float(np.median(dev)), "e2e_device_resident_GBps_out": total / float(np.median(dev)) / 1e9,
                      "e2e_to_host_ms": 1e3 * float(np.median(host)), "e2e_to_host_GBps_out": total / float(np.median(host)) / 1e9}
+    # the same with the file and the output in pinned host memory (pg_host_alloc): what a reader that owns its buffers gets
+    pbuf = api.pinned_empty(buf.size, np.uint8)
+    pbuf[:] = buf
+    pout = api.pinned_empty(total, np.uint8)
+    dev, host = [], []
+    for _ in range(a.reps):
+        t0 = time.perf_counter(); pg.bgzf_inflate(pbuf, to_host=False); dev.append(time.perf_counter() - t0)
+        t0 = time.perf_counter(); pg.bgzf_inflate(pbuf, out=pout); host.append(time.perf_counter() - t0)
+    assert pout[-unit:].tobytes() == payloads[(n_units - 1) % len(payloads)]
+    res["pinned_crc"] = {"e2e_device_resident_ms": 1e3 * float(np.median(dev)), "e2e_device_resident_GBps_out": total / float(np.median(dev)) / 1e9,
+                         "e2e_to_host_ms": 1e3 * float(np.median(host)), "e2e_to_host_GBps_out": total / float(np.median(host)) / 1e9}
     # zlib on the host cores: the same blocks, inflate + crc32 per block
     blocks = []
     pos = 0

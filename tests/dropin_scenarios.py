@@ -60,4 +60,8 @@ def sim_prefix_bam(demo, tmp_path, env):
     # row N2: the discordant pairs of the window went through pg_rp_modify / pg_rp_summarize (ModifyRP / Summarize bound by symbol)
     m = re.search(r"(\d+) read pairs clustered on the device \((\d+) launches\)", p.stderr)
     assert m and int(m.group(1)) > 0 and int(m.group(2)) > 0, p.stderr[-500:]
+    # row N3 (first half): the BAM file was inflated by pg_bgzf_inflate
+    m = re.search(r"(\d+) BAM bytes inflated on the device", p.stderr)
+    size = len(gzip.decompress((tmp_path / "sim_prefix.bam").read_bytes()))      # the reference opens the file several times
+    assert m and (int(m.group(1)) == 0 if env.get("PG_BRIDGE_ZLIB") else (int(m.group(1)) > 0 and int(m.group(1)) % size == 0)), p.stderr[-300:]
     return p

@@ -15,6 +15,7 @@
 #include "pg_emul.cpp"
 #include "sv_emul.cpp"
 #include "rp_emul.cpp"
+#include "bgzf_emul.cpp"
 #include "../../pindel_b200/csrc/pg_host_helpers.h"
 
 struct pg_ctx {
@@ -210,6 +211,18 @@ int pg_rp_summarize(pg_ctx *ctx, int32_t n, const pg_rp *in, pg_rp_cluster *inou
    return PG_OK;
 }
 uint64_t pg_rp_launches(pg_ctx *ctx) { return ctx ? ctx->rp_launches : 0; }
+int64_t pg_bgzf_inflated_size(const uint8_t *file, size_t file_len) { return bgzfemu_size(file, file_len); }
+int pg_bgzf_inflate(pg_ctx *ctx, const uint8_t *file, size_t file_len, uint8_t *out, size_t out_cap, size_t *out_len, int32_t check_crc)
+{
+   const long total = bgzfemu_size(file, file_len);
+   if (total < 0) return fail(ctx, PG_ERR_DATA, "not a BGZF file");
+   *out_len = (size_t)total;
+   if (out_cap < (size_t)total) return fail(ctx, PG_ERR_RUNS_CAP, "output buffer too small");
+   std::vector<uint32_t> status((size_t)(file_len / 26 + 2));
+   const long nb = bgzfemu_inflate(file, file_len, out, status.data(), (long)status.size(), check_crc);
+   for (long i = 0; i < nb; i++) if (status[(size_t)i]) return fail(ctx, PG_ERR_DATA, "corrupt block");
+   return PG_OK;
+}
 uint64_t pg_classify_launches(pg_ctx *ctx) { return ctx ? ctx->sv_launches : 0; }
 double pg_classify_last_kernel_ms(pg_ctx *) { return 0.0; }
 uint32_t pg_expand_runs(const pg_run *runs, uint32_t n_runs, pg_up *out) { return pgh_expand_runs(runs, n_runs, out); }

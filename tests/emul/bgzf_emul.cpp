@@ -29,7 +29,15 @@ long bgzfemu_inflate(const uint8_t *file, size_t len, uint8_t *out, uint32_t *st
    for (size_t i = 0; i < blocks.size(); i++) {
       uint32_t produced = 0;
       int rc = pgz_inflate(file + blocks[i].comp_off, blocks[i].comp_len, out + blocks[i].out_off, blocks[i].isize, &sc, 0, 1, &produced);
-      if (rc == PGZ_OK && check_crc && pgz_crc32(out + blocks[i].out_off, blocks[i].isize, crc_table) != blocks[i].crc) rc = PGZ_ERR_CRC;
+      if (rc == PGZ_OK && check_crc) {      // the kernel's formulation: 32 slices, combined
+         const uint32_t isize = blocks[i].isize, slice = (isize + 31u) / 32u;
+         uint32_t crcs[32];
+         for (uint32_t l = 0; l < 32; l++) {
+            const uint32_t begin = l * slice, len = begin >= isize ? 0u : (isize - begin < slice ? isize - begin : slice);
+            crcs[l] = pgz_crc32(out + blocks[i].out_off + begin, len, crc_table);
+         }
+         if (pgz_crc_combine_slices(crcs, 32u, slice, isize) != blocks[i].crc) rc = PGZ_ERR_CRC;
+      }
       if ((long)i < max_status) status[i] = (uint32_t)rc;
    }
    return (long)blocks.size();

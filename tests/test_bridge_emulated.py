@@ -25,6 +25,11 @@ def test_bam_input_scenario(tmp_path):
     D.sim_prefix_bam(DEMO, tmp_path, dict(os.environ))
 
 
+def test_bam_input_scenario_with_zlib_inflate(tmp_path):
+    """the reader's own zlib path (PG_BRIDGE_ZLIB=1) instead of pg_bgzf_inflate: both must give the same files"""
+    D.sim_prefix_bam(DEMO, tmp_path, dict(os.environ, PG_BRIDGE_ZLIB="1"))
+
+
 def test_text_input_scenario_with_the_host_array_classification(tmp_path):
     """pg_classify (everything uploaded again) instead of pg_classify_resident: the path a host takes when the far-end
     batch is no longer on the device."""
