@@ -122,6 +122,24 @@ struct PgzScratch {           // working memory of one decoder (shared memory on
 #define PGZ_SYNC() ((void)0)
 #endif
 
+// The fast tables are read once per symbol.  On the device they are addressed through the shared window directly
+// (ld.shared with a 32-bit address computed once per block) instead of through a generic pointer, whose translation the
+// compiler otherwise repeats in front of every lookup (S2R SR_CgaCtaId + address arithmetic on the decode's critical path).
+#if defined(__CUDA_ARCH__)
+typedef uint32_t PgzFastRef;
+PGZ_HD PgzFastRef pgz_fast_ref(const uint16_t *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+PGZ_HD uint32_t pgz_fast_load(PgzFastRef r, uint32_t i)
+{
+   uint16_t v;
+   asm volatile("ld.shared.u16 %0, [%1];" : "=h"(v) : "r"(r + 2u * i) : "memory");
+   return v;
+}
+#else
+typedef const uint16_t *PgzFastRef;
+PGZ_HD PgzFastRef pgz_fast_ref(const uint16_t *p) { return p; }
+PGZ_HD uint32_t pgz_fast_load(PgzFastRef r, uint32_t i) { return r[i]; }
+#endif
+
 struct PgzBits {
    const uint32_t *words;     // 4-byte aligned view of the input
    uint32_t next_word;        // index of the next word to load
@@ -180,9 +198,9 @@ PGZ_FN int pgz_build(const uint8_t *lengths, int n, PgzTree &t, uint16_t *fast, 
 }
 
 // one symbol: fast table, else the canonical walk (RFC 1951 3.2.2) from the first length the table does not cover
-PGZ_HD int pgz_decode(PgzBits &b, const PgzTree &t, const uint16_t *fast, int bits)
+PGZ_HD int pgz_decode(PgzBits &b, const PgzTree &t, PgzFastRef fast, int bits)
 {
-   const uint16_t e = fast[pgz_peek(b, (uint32_t)bits)];
+   const uint32_t e = pgz_fast_load(fast, pgz_peek(b, (uint32_t)bits));
    if (e & 15u) {
       pgz_drop(b, e & 15u);
       return e >> 4;
@@ -212,12 +230,8 @@ PGZ_FN int pgz_inflate(const uint8_t *in, uint32_t in_len, uint8_t *out, uint32_
                        uint32_t *produced)
 {
    const uint8_t len_order[19] = {16, 17, 18, 0, 8, 7, 9, 6, 10, 5, 11, 4, 12, 3, 13, 2, 14, 1, 15};
-   const uint16_t len_base[29] = {3, 4, 5, 6, 7, 8, 9, 10, 11, 13, 15, 17, 19, 23, 27, 31, 35, 43, 51, 59, 67, 83, 99, 115, 131, 163, 195, 227, 258};
-   const uint8_t len_extra[29] = {0, 0, 0, 0, 0, 0, 0, 0, 1, 1, 1, 1, 2, 2, 2, 2, 3, 3, 3, 3, 4, 4, 4, 4, 5, 5, 5, 5, 0};
-   const uint16_t dist_base[30] = {1, 2, 3, 4, 5, 7, 9, 13, 17, 25, 33, 49, 65, 97, 129, 193, 257, 385, 513, 769, 1025, 1537, 2049, 3073, 4097, 6145,
-                                   8193, 12289, 16385, 24577};
-   const uint8_t dist_extra[30] = {0, 0, 0, 0, 1, 1, 2, 2, 3, 3, 4, 4, 5, 5, 6, 6, 7, 7, 8, 8, 9, 9, 10, 10, 11, 11, 12, 12, 13, 13};
    uint8_t *lengths = sc->lengths;
+   const PgzFastRef fast_lit = pgz_fast_ref(sc->fast_lit), fast_dist = pgz_fast_ref(sc->fast_dist);
    PgzBits b;
    const uint32_t mis = (uint32_t)((uintptr_t)in & 3u);
    b.words = reinterpret_cast<const uint32_t *>(in - mis);
@@ -274,7 +288,7 @@ PGZ_FN int pgz_inflate(const uint8_t *in, uint32_t in_len, uint8_t *out, uint32_
          int idx = 0;
          while (idx < nlen + ndist) {
             pgz_refill(b);
-            const int sym = pgz_decode(b, sc->lit, sc->fast_dist, PGZ_DIST_BITS);
+            const int sym = pgz_decode(b, sc->lit, fast_dist, PGZ_DIST_BITS);
             if (sym < 0) { rc = PGZ_ERR_CODE; break; }
             if (sym < 16) {
                lengths[idx++] = (uint8_t)sym;
@@ -297,7 +311,7 @@ PGZ_FN int pgz_inflate(const uint8_t *in, uint32_t in_len, uint8_t *out, uint32_
       }
       for (;;) {                             // the symbols of this block
          pgz_refill(b);
-         int sym = pgz_decode(b, sc->lit, sc->fast_lit, PGZ_LIT_BITS);
+         int sym = pgz_decode(b, sc->lit, fast_lit, PGZ_LIT_BITS);
          if (sym < 0) { rc = PGZ_ERR_CODE; break; }
          if (sym < 256) {
             if (op >= isize) { rc = PGZ_ERR_OUTPUT; break; }
@@ -308,11 +322,15 @@ PGZ_FN int pgz_inflate(const uint8_t *in, uint32_t in_len, uint8_t *out, uint32_
          if (sym == 256) break;
          sym -= 257;
          if (sym >= 29) { rc = PGZ_ERR_CODE; break; }
-         const uint32_t len = len_base[sym] + pgz_take(b, len_extra[sym]);
+         // RFC 1951 3.2.5, the two tables in closed form: length codes 257..264 are 3..10, then four codes per extra bit,
+         // code 285 is 258; distance codes 0..3 are 1..4, then two codes per extra bit
+         const uint32_t lx = sym < 8 || sym == 28 ? 0u : ((uint32_t)sym >> 2) - 1u;
+         const uint32_t len = (sym == 28 ? 258u : sym < 8 ? 3u + (uint32_t)sym : 3u + ((4u + ((uint32_t)sym & 3u)) << lx)) + pgz_take(b, lx);
          pgz_refill(b);
-         const int ds = pgz_decode(b, sc->dist, sc->fast_dist, PGZ_DIST_BITS);
+         const int ds = pgz_decode(b, sc->dist, fast_dist, PGZ_DIST_BITS);
          if (ds < 0 || ds >= 30) { rc = PGZ_ERR_CODE; break; }
-         const uint32_t d = dist_base[ds] + pgz_take(b, dist_extra[ds]);
+         const uint32_t dx = ds < 4 ? 0u : ((uint32_t)ds >> 1) - 1u;
+         const uint32_t d = (ds < 4 ? 1u + (uint32_t)ds : 1u + ((2u + ((uint32_t)ds & 1u)) << dx)) + pgz_take(b, dx);
          if (d > op) { rc = PGZ_ERR_DIST; break; }
          if (op + len > isize) { rc = PGZ_ERR_OUTPUT; break; }
          // every source byte lies before op (a match that overlaps its own output repeats its first d bytes), so the lanes
