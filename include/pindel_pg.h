@@ -266,6 +266,24 @@ int pg_classify_resident(pg_ctx *ctx, const pg_sv_window *win, const uint8_t *rf
 uint64_t pg_classify_launches(pg_ctx *ctx);   /* classification-kernel launches since pg_create */
 double pg_classify_last_kernel_ms(pg_ctx *ctx); /* CUDA-event duration of the last classification kernel */
 
+/* The BAM record index of the inflated stream the last pg_bgzf_inflate left on the device: for every alignment record the
+ * offset of its block_size field, refID, pos, end (pos + reference bases of the CIGAR, as bam_endpos), flag and mapq --
+ * what htslib derives record by record behind sam_itr_next for its region test (src/reader.cpp:1258-1346).  The chain of
+ * block_size fields is walked in 256 KiB segments in parallel from guessed record starts; the guesses are checked against
+ * the walks and a wrong one is walked again, so the table is that of the serial walk.  first_record / n_ref (optional):
+ * offset of the first record and number of references from the BAM header.  PG_ERR_STATE: nothing inflated;
+ * PG_ERR_DATA: not a BAM stream or a truncated record chain; PG_ERR_RUNS_CAP: cap too small (*n_recs = needed). */
+typedef struct pg_bam_rec {
+   uint64_t off;
+   int32_t tid, pos, end;
+   uint16_t flag;
+   uint8_t mapq, pad;
+} pg_bam_rec;
+int pg_bam_index(pg_ctx *ctx, pg_bam_rec *recs, uint64_t cap, uint64_t *n_recs, uint64_t *first_record, int32_t *n_ref);
+uint64_t pg_bam_launches(pg_ctx *ctx);
+double pg_bam_last_ms(pg_ctx *ctx);            /* CUDA-event duration of the last pg_bam_index (kernels + its small copies) */
+void pg_bam_last_segments(pg_ctx *ctx, uint32_t *segments, uint32_t *walked_again);
+
 /* ------------------------------------------------------------------------------------------------------------------
  * Discordant-read-pair clustering: the two quadratic loops of BDData::UpdateBD
  * (src/bddata.cpp:646-659) that turn the window's discordant pairs into BreakDancer-like events for the far-end search.

@@ -718,18 +718,36 @@ static int deviceInflate(const uint8_t *file, size_t len, std::vector<uint8_t> &
    return 0;
 }
 
+/* ... and builds its record table (the walk behind sam_itr_next's region test) with pg_bam_index on the stream that
+ * inflate left on the device. */
+extern "C" int (*minihts_index_hook)(size_t first_record, std::vector<uint8_t> &rows24);
+static unsigned long g_bam_records = 0;
+static int deviceIndex(size_t first_record, std::vector<uint8_t> &rows24)
+{
+   std::lock_guard<std::mutex> lock(g_mutex);
+   uint64_t n = 0, first = 0;
+   int32_t nref = 0;
+   int rc = pg_bam_index(g_ctx, NULL, 0, &n, &first, &nref);
+   if (rc != PG_OK && rc != PG_ERR_RUNS_CAP) die("pg_bam_index");
+   if (first != (uint64_t)first_record) { std::fprintf(stderr, "pindel_gpu_demo: BAM header size differs (%llu vs %zu)\n", (unsigned long long)first, first_record); return 1; }
+   rows24.resize((size_t)n * sizeof(pg_bam_rec));
+   if (n && pg_bam_index(g_ctx, (pg_bam_rec *)&rows24[0], n, &n, NULL, NULL) != PG_OK) die("pg_bam_index");
+   g_bam_records += (unsigned long)n;
+   return 0;
+}
+
 static void reportAtExit()
 {
    std::fprintf(stderr, "pindel_gpu_demo: %lu GetCloseEnd calls and %lu far-end reads served by libpindel_pg (%llu kernel launches); "
-                "%lu reads classified by the SV drivers on the device, %lu records (%llu launches), %lu of the reads without a second upload; %lu read pairs clustered on the device (%llu launches); %lu BAM bytes inflated on the device\n",
+                "%lu reads classified by the SV drivers on the device, %lu records (%llu launches), %lu of the reads without a second upload; %lu read pairs clustered on the device (%llu launches); %lu BAM bytes inflated and %lu records indexed on the device\n",
                 g_close_calls, g_far_reads, g_ctx ? (unsigned long long)pg_kernel_launches(g_ctx) : 0ull, g_sv_reads, g_sv_records,
                 g_ctx ? (unsigned long long)pg_classify_launches(g_ctx) : 0ull, g_sv_resident, g_rp_rows,
-                g_ctx ? (unsigned long long)pg_rp_launches(g_ctx) : 0ull, g_bgzf_bytes);
+                g_ctx ? (unsigned long long)pg_rp_launches(g_ctx) : 0ull, g_bgzf_bytes, g_bam_records);
 }
 
 int main(int argc, char *argv[])
 {
    std::atexit(reportAtExit);        /* the reference's main() leaves through exit() */
-   if (getenv("PG_BRIDGE_ZLIB") == NULL) minihts_inflate_hook = deviceInflate;
+   if (getenv("PG_BRIDGE_ZLIB") == NULL) { minihts_inflate_hook = deviceInflate; minihts_index_hook = deviceIndex; }
    return pindel_reference_main(argc, argv);
 }

@@ -73,6 +73,10 @@ extern "C" {
 
 const char seq_nt16_str[] = "=ACMGRSVTWYHKDBN";
 
+/* optional replacement of the record walk in sam_hdr_read: the table of the stream the inflate hook produced last
+   (24-byte rows: offset u64, refID i32, pos i32, end i32, 4 bytes the reader does not use); 0 = success */
+int (*minihts_index_hook)(size_t first_record, std::vector<uint8_t> &rows24) = NULL;
+
 /* optional replacement of the zlib loop in sam_open: whole BGZF file in, inflated stream out; 0 = success */
 int (*minihts_inflate_hook)(const uint8_t *file, size_t len, std::vector<uint8_t> &out) = NULL;
 
@@ -138,6 +142,19 @@ bam_hdr_t *sam_hdr_read(samFile *fp)
       h->target_len[i] = le32(d + p); p += 4;
    }
    fp->first_record = p;
+   if (!fp->indexed && minihts_index_hook && minihts_inflate_hook) {
+      std::vector<uint8_t> rows;
+      if (minihts_index_hook(p, rows) != 0) die("index hook failed");
+      fp->recs.resize(rows.size() / 24);
+      for (size_t i = 0; i < fp->recs.size(); i++) {
+         const uint8_t *r = rows.data() + 24 * i;
+         uint64_t off;
+         std::memcpy(&off, r, 8);
+         fp->recs[i].off = (size_t)off;
+         fp->recs[i].tid = (int32_t)le32(r + 8); fp->recs[i].pos = (int32_t)le32(r + 12); fp->recs[i].end = (int32_t)le32(r + 16);
+      }
+      fp->indexed = true;
+   }
    if (!fp->indexed) {
       /* record table for region queries */
       size_t q = p, n = fp->data.size();

@@ -98,6 +98,13 @@ def load_library() -> C.CDLL:
         lib.pg_bgzf_launches.argtypes = [C.c_void_p]
         lib.pg_bgzf_last_kernel_ms.restype = C.c_double
         lib.pg_bgzf_last_kernel_ms.argtypes = [C.c_void_p]
+        lib.pg_bam_index.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64), C.POINTER(C.c_int32)]
+        lib.pg_bam_launches.restype = C.c_uint64
+        lib.pg_bam_launches.argtypes = [C.c_void_p]
+        lib.pg_bam_last_ms.restype = C.c_double
+        lib.pg_bam_last_ms.argtypes = [C.c_void_p]
+        lib.pg_bam_last_segments.restype = None
+        lib.pg_bam_last_segments.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
         lib.pg_rp_modify.argtypes = [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p]
         lib.pg_rp_summarize.argtypes = [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p]
         lib.pg_rp_last_classes.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
@@ -349,6 +356,34 @@ class PatternGrowth:
     @property
     def bgzf_launches(self) -> int:
         return int(self.lib.pg_bgzf_launches(self.ctx))
+
+    def bam_index(self, recs=None):
+        """Record table of the inflated stream the last bgzf_inflate left on the device -> (records (pindel_b200.bam.REC_DT),
+        first record offset, n_ref)."""
+        from . import bam
+        n, first, nref = C.c_uint64(0), C.c_uint64(0), C.c_int32(0)
+        if recs is None:
+            rc = self.lib.pg_bam_index(self.ctx, None, 0, C.byref(n), C.byref(first), C.byref(nref))
+            if rc not in (0, PG_ERR_RUNS_CAP):
+                self._check(rc, "pg_bam_index")
+            recs = np.zeros(int(n.value), dtype=bam.REC_DT)
+            if n.value == 0:
+                return recs, int(first.value), int(nref.value)
+        self._check(self.lib.pg_bam_index(self.ctx, recs.ctypes.data, recs.size, C.byref(n), C.byref(first), C.byref(nref)), "pg_bam_index")
+        return recs[:n.value], int(first.value), int(nref.value)
+
+    def bam_last_segments(self):
+        a, b = C.c_uint32(0), C.c_uint32(0)
+        self.lib.pg_bam_last_segments(self.ctx, C.byref(a), C.byref(b))
+        return int(a.value), int(b.value)
+
+    @property
+    def bam_last_ms(self) -> float:
+        return float(self.lib.pg_bam_last_ms(self.ctx))
+
+    @property
+    def bam_launches(self) -> int:
+        return int(self.lib.pg_bam_launches(self.ctx))
 
     def rp_modify(self, rows: np.ndarray) -> np.ndarray:
         """ModifyRP after its sort (src/bddata.cpp:396-430) on the device: rows = pindel_b200.rp.RP_DT in the order the

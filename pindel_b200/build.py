@@ -44,10 +44,12 @@ def build_oracle():
 
 def build_emulator():
     sys.path.insert(0, ROOT)
-    from tests.emul import emul, rp_emul, sv_emul
+    from tests.emul import bam_emul, bgzf_emul, emul, rp_emul, sv_emul
     emul.build()
     sv_emul.build()
     rp_emul.build()
+    bgzf_emul.build()
+    bam_emul.build()
 
 
 def build_all(force=False):

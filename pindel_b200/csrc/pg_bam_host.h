@@ -1,0 +1,35 @@
+// pindel_b200/csrc/pg_bam_host.h -- host part of pg_bam_index: checking the segments' guessed record starts against the
+// segments' walks (see pg_bam.cuh).  Shared by pindel_pg.cu and the CPU-side test harness (tests/emul/bam_emul.cpp).
+#pragma once
+#include <stdint.h>
+#include "pg_bam.cuh"
+
+#define PGB_SEGMENT (256u << 10)   // bytes of inflated stream per segment
+
+// starts[0] is the true first record.  Follows the true chain segment by segment:
+//   a segment the chain jumps over keeps no records (whatever it guessed);
+//   a segment whose guess is the chain's next record is accepted, the chain continues at its landing offset;
+//   otherwise the segment must be walked again from the chain's offset: returns 1 + s and that offset in *forced.
+// Returns 0 when every segment is consistent and the chain ends exactly at n (*total = records), -1 for a corrupt chain.
+static inline long pgb_validate(uint32_t n_seg, uint64_t first, uint64_t n, uint64_t seg, const uint64_t *starts, uint64_t *counts,
+                                const uint64_t *landing, uint64_t *forced, uint64_t *total)
+{
+   uint64_t cur = first, sum = 0;
+   for (uint32_t s = 0; s < n_seg; s++) {
+      const uint64_t b1 = first + (uint64_t)(s + 1) * seg;
+      if (cur >= n || cur >= b1) {
+         counts[s] = 0;
+         continue;
+      }
+      if (starts[s] != cur) {
+         *forced = cur;
+         return 1 + (long)s;
+      }
+      if (landing[s] == PGB_NONE) return -1;
+      sum += counts[s];
+      cur = landing[s];
+   }
+   if (cur != n) return -1;
+   *total = sum;
+   return 0;
+}

@@ -22,6 +22,8 @@
 #include "pg_rp_host.h"
 #include "pg_bgzf.cuh"
 #include "pg_bgzf_host.h"
+#include "pg_bam.cuh"
+#include "pg_bam_host.h"
 #include "pg_params.h"
 #include "../../include/pindel_pg.h"
 #include "pg_host_helpers.h"
@@ -369,7 +371,10 @@ struct pg_ctx {
    DevBuf sv_close_off, sv_close_runs;
    uint64_t sv_aux_launches = 0;
    // BGZF inflation (pg_bgzf_inflate)
-   DevBuf bz_file, bz_blocks, bz_out, bz_status;
+   DevBuf bz_file, bz_blocks, bz_out, bz_status, bm_info, bm_starts, bm_counts, bm_landing, bm_base, bm_recs;
+   uint64_t bm_launches = 0;
+   uint32_t bm_last_segments = 0, bm_last_redone = 0;
+   float bm_last_ms = 0.f;
    size_t bz_out_len = 0;
    uint64_t bz_launches = 0;
    float bz_last_ms = 0.f;
@@ -532,7 +537,8 @@ void pg_destroy(pg_ctx *ctx)
                        &ctx->sv_runs, &ctx->sv_records, &ctx->sv_params, &ctx->sv_counters,
                        &ctx->sv_counts, &ctx->sv_offsets, &ctx->sv_blocksums, &ctx->sv_ordered, &ctx->sv_close_off,
                        &ctx->sv_close_runs, &ctx->rp_in, &ctx->rp_out, &ctx->rp_rows, &ctx->rp_off, &ctx->rp_scratch, &ctx->rp_merged,
-                       &ctx->rp_nid, &ctx->rp_counters, &ctx->rp_keys, &ctx->bz_file, &ctx->bz_blocks, &ctx->bz_out, &ctx->bz_status};
+                       &ctx->rp_nid, &ctx->rp_counters, &ctx->rp_keys, &ctx->bz_file, &ctx->bz_blocks, &ctx->bz_out, &ctx->bz_status,
+                       &ctx->bm_info, &ctx->bm_starts, &ctx->bm_counts, &ctx->bm_landing, &ctx->bm_base, &ctx->bm_recs};
    for (DevBuf *b : svbufs) if (b->p) cudaFree(b->p);
    pipe_destroy(ctx->pipe);
    if (ctx->chroms_d) cudaFree(ctx->chroms_d);
@@ -1285,6 +1291,96 @@ int pg_bgzf_device_data(pg_ctx *ctx, void **dev, size_t *len)
 
 uint64_t pg_bgzf_launches(pg_ctx *ctx) { return ctx ? ctx->bz_launches : 0; }
 double pg_bgzf_last_kernel_ms(pg_ctx *ctx) { return ctx ? (double)ctx->bz_last_ms : 0.0; }
+
+// ---- BAM record index (row N3, between inflate and filter) -----------------------------------------------------------
+static_assert(sizeof(pg_bam_rec) == sizeof(PgBamRec) && sizeof(pg_bam_rec) == 24, "bam rec layout");
+
+int pg_bam_index(pg_ctx *ctx, pg_bam_rec *recs, uint64_t cap, uint64_t *n_recs, uint64_t *first_record, int32_t *n_ref)
+{
+   if (!ctx || !n_recs) return fail(ctx, PG_ERR_ARG, "pg_bam_index: null argument");
+   if (ctx->bz_out_len == 0) return fail(ctx, PG_ERR_STATE, "pg_bam_index: no inflated stream is resident (call pg_bgzf_inflate)");
+   CU(cudaSetDevice(ctx->device));
+   cudaStream_t st = ctx->stream;
+   const uint8_t *d = (const uint8_t *)ctx->bz_out.p;
+   const uint64_t n = ctx->bz_out_len;
+   int rc;
+   if ((rc = ensure(ctx, ctx->bm_info, sizeof(uint64_t) * 2)) != PG_OK) return rc;
+   if (!ctx->sv_ev0) { CU(cudaEventCreate(&ctx->sv_ev0)); CU(cudaEventCreate(&ctx->sv_ev1)); }
+   CU(cudaEventRecord(ctx->sv_ev0, st));
+   pg_bam_header_kernel<<<1, 32, 0, st>>>(d, n, (uint64_t *)ctx->bm_info.p);
+   uint64_t info[2];
+   CU(cudaMemcpyAsync(info, ctx->bm_info.p, sizeof info, cudaMemcpyDeviceToHost, st));
+   CU(cudaStreamSynchronize(st));
+   if (info[0] == PGB_NONE) return fail(ctx, PG_ERR_DATA, "pg_bam_index: the inflated stream is not a BAM file (magic / header)");
+   const uint64_t first = info[0], seg = PGB_SEGMENT;
+   const int32_t nref = (int32_t)info[1];
+   if (first_record) *first_record = first;
+   if (n_ref) *n_ref = nref;
+   const uint32_t n_seg = first >= n ? 1u : (uint32_t)((n - first + seg - 1) / seg);
+   if ((rc = ensure(ctx, ctx->bm_starts, sizeof(uint64_t) * (size_t)n_seg)) != PG_OK) return rc;
+   if ((rc = ensure(ctx, ctx->bm_counts, sizeof(uint64_t) * (size_t)n_seg)) != PG_OK) return rc;
+   if ((rc = ensure(ctx, ctx->bm_landing, sizeof(uint64_t) * (size_t)n_seg)) != PG_OK) return rc;
+   if ((rc = ensure(ctx, ctx->bm_base, sizeof(uint64_t) * (size_t)n_seg)) != PG_OK) return rc;
+   pg_bam_start_kernel<<<(n_seg + 7) / 8, 256, 0, st>>>(d, n, first, seg, n_seg, nref, (uint64_t *)ctx->bm_starts.p);
+   ctx->bm_launches += 2;
+   std::vector<uint64_t> starts(n_seg), counts(n_seg), landing(n_seg), base(n_seg);
+   uint64_t total = 0;
+   uint32_t redone = 0;
+   for (;;) {
+      pg_bam_walk_kernel<<<(n_seg + 127) / 128, 128, 0, st>>>(d, n, first, seg, n_seg, (const uint64_t *)ctx->bm_starts.p, (uint64_t *)ctx->bm_counts.p,
+                                                             (uint64_t *)ctx->bm_landing.p, nullptr, nullptr);
+      CU(cudaGetLastError());
+      ctx->bm_launches++;
+      CU(cudaMemcpyAsync(starts.data(), ctx->bm_starts.p, sizeof(uint64_t) * (size_t)n_seg, cudaMemcpyDeviceToHost, st));
+      CU(cudaMemcpyAsync(counts.data(), ctx->bm_counts.p, sizeof(uint64_t) * (size_t)n_seg, cudaMemcpyDeviceToHost, st));
+      CU(cudaMemcpyAsync(landing.data(), ctx->bm_landing.p, sizeof(uint64_t) * (size_t)n_seg, cudaMemcpyDeviceToHost, st));
+      CU(cudaStreamSynchronize(st));
+      uint64_t forced = 0;
+      const long v = pgb_validate(n_seg, first, n, seg, starts.data(), counts.data(), landing.data(), &forced, &total);
+      if (v < 0) return fail(ctx, PG_ERR_DATA, "pg_bam_index: the record chain does not end at the end of the stream (truncated or corrupt BAM)");
+      if (v == 0) break;
+      // a guess locked on to bytes that only look like records: walk that segment from the chain's true offset
+      CU(cudaMemcpyAsync((uint64_t *)ctx->bm_starts.p + (v - 1), &forced, sizeof(uint64_t), cudaMemcpyHostToDevice, st));
+      CU(cudaStreamSynchronize(st));
+      redone++;
+   }
+   ctx->bm_last_segments = n_seg;
+   ctx->bm_last_redone = redone;
+   *n_recs = total;
+   if (total > cap || (total && !recs)) {
+      CU(cudaEventRecord(ctx->sv_ev1, st));
+      return fail(ctx, PG_ERR_RUNS_CAP, "pg_bam_index: record buffer too small (n_recs holds the required size)");
+   }
+   if (total) {
+      uint64_t b = 0;
+      for (uint32_t s = 0; s < n_seg; s++) { base[s] = b; b += counts[s]; }
+      // segments the chain jumps over must not write: their guess is void
+      for (uint32_t s = 0; s < n_seg; s++) if (counts[s] == 0) starts[s] = PGB_NONE;
+      if ((rc = ensure(ctx, ctx->bm_recs, sizeof(PgBamRec) * (size_t)total)) != PG_OK) return rc;
+      CU(cudaMemcpyAsync(ctx->bm_starts.p, starts.data(), sizeof(uint64_t) * (size_t)n_seg, cudaMemcpyHostToDevice, st));
+      CU(cudaMemcpyAsync(ctx->bm_base.p, base.data(), sizeof(uint64_t) * (size_t)n_seg, cudaMemcpyHostToDevice, st));
+      pg_bam_walk_kernel<<<(n_seg + 127) / 128, 128, 0, st>>>(d, n, first, seg, n_seg, (const uint64_t *)ctx->bm_starts.p, nullptr, nullptr,
+                                                             (const uint64_t *)ctx->bm_base.p, (PgBamRec *)ctx->bm_recs.p);
+      CU(cudaGetLastError());
+      ctx->bm_launches++;
+      CU(cudaEventRecord(ctx->sv_ev1, st));
+      CU(cudaMemcpyAsync(recs, ctx->bm_recs.p, sizeof(PgBamRec) * (size_t)total, cudaMemcpyDeviceToHost, st));
+   } else {
+      CU(cudaEventRecord(ctx->sv_ev1, st));
+   }
+   CU(cudaStreamSynchronize(st));
+   CU(cudaEventElapsedTime(&ctx->bm_last_ms, ctx->sv_ev0, ctx->sv_ev1));
+   return PG_OK;
+}
+
+uint64_t pg_bam_launches(pg_ctx *ctx) { return ctx ? ctx->bm_launches : 0; }
+double pg_bam_last_ms(pg_ctx *ctx) { return ctx ? (double)ctx->bm_last_ms : 0.0; }
+void pg_bam_last_segments(pg_ctx *ctx, uint32_t *segments, uint32_t *walked_again)
+{
+   if (!ctx) return;
+   if (segments) *segments = ctx->bm_last_segments;
+   if (walked_again) *walked_again = ctx->bm_last_redone;
+}
 
 // ---- read-pair clustering (row N2) --------------------------------------------------------------------------------
 static_assert(sizeof(pg_rp) == sizeof(PgRp) && sizeof(pg_rp) == 16, "rp layout");

@@ -16,6 +16,7 @@
 #include "sv_emul.cpp"
 #include "rp_emul.cpp"
 #include "bgzf_emul.cpp"
+#include "bam_emul.cpp"
 #include "../../pindel_b200/csrc/pg_host_helpers.h"
 
 struct pg_ctx {
@@ -33,6 +34,7 @@ struct pg_ctx {
    std::vector<uint32_t> res_off;
    std::vector<int16_t> res_isz;
    std::vector<int32_t> res_chr;
+   std::vector<uint8_t> stream;   // the last inflated stream
 };
 
 static std::string g_create_error;
@@ -221,6 +223,20 @@ int pg_bgzf_inflate(pg_ctx *ctx, const uint8_t *file, size_t file_len, uint8_t *
    std::vector<uint32_t> status((size_t)(file_len / 26 + 2));
    const long nb = bgzfemu_inflate(file, file_len, out, status.data(), (long)status.size(), check_crc);
    for (long i = 0; i < nb; i++) if (status[(size_t)i]) return fail(ctx, PG_ERR_DATA, "corrupt block");
+   ctx->stream.assign(out, out + total);      // "resident" for pg_bam_index
+   return PG_OK;
+}
+int pg_bam_index(pg_ctx *ctx, pg_bam_rec *recs, uint64_t cap, uint64_t *n_recs, uint64_t *first_record, int32_t *n_ref)
+{
+   if (ctx->stream.empty()) return fail(ctx, PG_ERR_STATE, "no inflated stream");
+   uint64_t stats[3] = {0, 0, 0};
+   const long n = bamemu_index(ctx->stream.data(), ctx->stream.size(), 0, NULL, 0, stats);
+   if (n < 0) return fail(ctx, PG_ERR_DATA, "not a BAM stream / corrupt chain");
+   *n_recs = (uint64_t)n;
+   if (first_record) *first_record = stats[2];
+   if (n_ref) { int32_t r = 0; pgb_header(ctx->stream.data(), ctx->stream.size(), &r); *n_ref = r; }
+   if ((uint64_t)n > cap || (n && !recs)) return fail(ctx, PG_ERR_RUNS_CAP, "record buffer too small");
+   bamemu_index(ctx->stream.data(), ctx->stream.size(), 0, (PgBamRec *)recs, cap, stats);
    return PG_OK;
 }
 uint64_t pg_classify_launches(pg_ctx *ctx) { return ctx ? ctx->sv_launches : 0; }

@@ -1,0 +1,60 @@
+// tests/emul/bam_emul.cpp -- TEST INFRASTRUCTURE ONLY: the BAM record index of pindel_b200/csrc/pg_bam.cuh (the functions
+// pg_bam_start_kernel / pg_bam_walk_kernel run) and the host's consistency check (pg_bam_host.h), compiled as plain C++ and
+// driven segment by segment exactly like pg_bam_index drives the kernels.  No GPU.
+#include <stdint.h>
+#include <string.h>
+#include <vector>
+#include "../../pindel_b200/csrc/pg_bam.cuh"
+#include "../../pindel_b200/csrc/pg_bam_host.h"
+
+extern "C" {
+
+int bamemu_rec_size(void) { return (int)sizeof(PgBamRec); }
+
+// seg: segment size (0 = the product's).  Returns the number of records (recs may be NULL to count), -1 not BAM,
+// -2 corrupt chain.  stats[0] = segments, stats[1] = segments that had to be walked again, stats[2] = first record offset.
+long bamemu_index(const uint8_t *d, uint64_t n, uint64_t seg, PgBamRec *recs, uint64_t cap, uint64_t *stats)
+{
+   int32_t n_ref = 0;
+   const uint64_t first = pgb_header(d, n, &n_ref);
+   if (first == PGB_NONE) return -1;
+   if (seg == 0) seg = PGB_SEGMENT;
+   const uint32_t n_seg = first >= n ? 1u : (uint32_t)((n - first + seg - 1) / seg);
+   std::vector<uint64_t> starts(n_seg), counts(n_seg), landing(n_seg), base(n_seg);
+   for (uint32_t s = 0; s < n_seg; s++) {         // pg_bam_start_kernel
+      if (s == 0) { starts[0] = first; continue; }
+      const uint64_t b0 = first + (uint64_t)s * seg, b1 = b0 + seg < n ? b0 + seg : n;
+      starts[s] = PGB_NONE;
+      for (uint64_t c = b0; c < b1; c++)
+         if (pgb_plausible_chain(d, n, c, n_ref)) { starts[s] = c; break; }
+   }
+   uint64_t redone = 0, total = 0;
+   for (;;) {
+      for (uint32_t s = 0; s < n_seg; s++) {      // pg_bam_walk_kernel, pass 0
+         if (starts[s] == PGB_NONE) { counts[s] = 0; landing[s] = PGB_NONE; continue; }
+         const uint64_t b1 = first + (uint64_t)(s + 1) * seg;
+         uint64_t k = 0;
+         landing[s] = pgb_walk(d, n, starts[s], b1 < n ? b1 : n, NULL, &k);
+         counts[s] = landing[s] == PGB_NONE ? 0 : k;
+      }
+      uint64_t forced = 0;
+      const long v = pgb_validate(n_seg, first, n, seg, starts.data(), counts.data(), landing.data(), &forced, &total);
+      if (v < 0) return -2;
+      if (v == 0) break;
+      starts[(size_t)(v - 1)] = forced;
+      redone++;
+   }
+   if (stats) { stats[0] = n_seg; stats[1] = redone; stats[2] = first; }
+   if (!recs) return (long)total;
+   if (cap < total) return -3;
+   uint64_t b = 0;
+   for (uint32_t s = 0; s < n_seg; s++) { base[s] = b; b += counts[s]; }
+   for (uint32_t s = 0; s < n_seg; s++) {         // pass 1
+      if (counts[s] == 0) continue;
+      const uint64_t b1 = first + (uint64_t)(s + 1) * seg;
+      uint64_t k = 0;
+      pgb_walk(d, n, starts[s], b1 < n ? b1 : n, recs + base[s], &k);
+   }
+   return (long)total;
+}
+}

@@ -1,0 +1,39 @@
+"""tests/emul/bam_emul.py -- TEST INFRASTRUCTURE ONLY: ctypes driver of bam_emul.cpp (pg_bam.cuh compiled for the host)."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB = os.path.join(HERE, "libbam_emul.so")
+CSRC = os.path.join(HERE, "..", "..", "pindel_b200", "csrc")
+
+REC_DT = np.dtype([("off", "<u8"), ("tid", "<i4"), ("pos", "<i4"), ("end", "<i4"), ("flag", "<u2"), ("mapq", "u1"), ("pad", "u1")])
+assert REC_DT.itemsize == 24
+
+
+def build(force=False):
+    srcs = [os.path.join(HERE, "bam_emul.cpp"), os.path.join(CSRC, "pg_bam.cuh"), os.path.join(CSRC, "pg_bam_host.h")]
+    if force or not os.path.exists(LIB) or any(os.path.getmtime(s) > os.path.getmtime(LIB) for s in srcs):
+        subprocess.check_call(["/usr/bin/g++", "-O2", "-g", "-fPIC", "-shared", "-Wall", "-x", "c++", "-o", LIB, srcs[0]])
+    lib = C.CDLL(LIB)
+    lib.bamemu_index.restype = C.c_long
+    lib.bamemu_index.argtypes = [C.c_void_p, C.c_uint64, C.c_uint64, C.c_void_p, C.c_uint64, C.c_void_p]
+    assert lib.bamemu_rec_size() == REC_DT.itemsize
+    return lib
+
+
+def index(lib, stream: bytes, seg: int = 0):
+    """-> (records, stats (segments, segments walked again, first record offset))"""
+    buf = np.frombuffer(stream, dtype=np.uint8)
+    stats = np.zeros(3, dtype=np.uint64)
+    n = lib.bamemu_index(buf.ctypes.data, buf.size, seg, None, 0, stats.ctypes.data)
+    if n < 0:
+        raise ValueError("bamemu_index: %d" % n)
+    recs = np.zeros(n, dtype=REC_DT)
+    n2 = lib.bamemu_index(buf.ctypes.data, buf.size, seg, recs.ctypes.data, n, stats.ctypes.data)
+    assert n2 == n
+    return recs, tuple(int(x) for x in stats)
