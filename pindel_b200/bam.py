@@ -28,13 +28,19 @@ def record(tid, pos, name: bytes, flag, mapq, cigar, seq_len, mtid=-1, mpos=-1, 
     return struct.pack("<I", len(body)) + body
 
 
-def serial_index(stream: bytes) -> np.ndarray:
-    """The record table by the plain serial walk (what oracle/shim/minihts.cpp and htslib do)."""
+def first_record_offset(stream: bytes):
+    """-> (offset of the first alignment record, n_ref)"""
     p = 8 + struct.unpack_from("<i", stream, 4)[0]
     n_ref = struct.unpack_from("<i", stream, p)[0]
     p += 4
     for _ in range(n_ref):
         p += 4 + struct.unpack_from("<i", stream, p)[0] + 4
+    return p, n_ref
+
+
+def serial_index(stream: bytes) -> np.ndarray:
+    """The record table by the plain serial walk (what oracle/shim/minihts.cpp and htslib do)."""
+    p, _ = first_record_offset(stream)
     rows = []
     n = len(stream)
     while p + 4 <= n:

@@ -27,7 +27,7 @@ def main():
     from tests.emul import bam_emul
     # one chunk of distinct records, tiled (the index does not care that positions repeat); chunk = whole BGZF blocks
     one = bam.synthetic_stream(60_000, 1)
-    first = int(bam.serial_index(one[:20000])["off"][0])
+    first, _ = bam.first_record_offset(one)
     hdr, chunk = one[:first], one[first:]
     tiles = max(1, (a.mb << 20) // len(chunk))
     comp = bgzf.compress(hdr, eof=False) + bgzf.compress(chunk, eof=False) * tiles + bgzf.EOF_MARKER

@@ -29,7 +29,7 @@ def test_committed_bam_fixture(pg):
     recs, first, n_ref = pg.bam_index()
     assert pg.bam_launches > before
     exp = bam.serial_index(stream)
-    assert same(recs, exp) and n_ref == 2 and first == int(exp["off"][0])
+    assert same(recs, exp) and (first, n_ref) == bam.first_record_offset(stream) and first == int(exp["off"][0])
     assert pg.bam_last_segments()[0] == -(-(len(stream) - first) // (256 << 10))
 
 
