@@ -284,6 +284,23 @@ uint64_t pg_bam_launches(pg_ctx *ctx);
 double pg_bam_last_ms(pg_ctx *ctx);            /* CUDA-event duration of the last pg_bam_index (kernels + its small copies) */
 void pg_bam_last_segments(pg_ctx *ctx, uint32_t *segments, uint32_t *walked_again);
 
+/* Discordant-pair discovery on the indexed stream (first half): what
+ * ReadInBamReads_RP_Discovery (src/reader.cpp:418-480) collects for one BAM file and window -- every record the region
+ * iterator delivers (refID == tid, pos < end, end-of-alignment > beg, up to the first record past the region) through
+ * build_record_RP_Discovery (src/reader.cpp:982-1097).  rows: Reads_RP_Discovery in BAM order (mates ordered by position);
+ * inter_rows: Reads_RP_Discovery_InterChr (pos_a = the read's position, pos_b = its mate's).  src / inter_src: the index
+ * of the record in pg_bam_index's table, for the fields the host adds itself (ReadName, reference names, MQA = mapq, Tag).
+ * n_scanned: records the iterator delivered (g_NumReadScanned's increase).  Needs pg_bgzf_inflate + pg_bam_index first. */
+typedef struct pg_rp_query {
+   int32_t tid;                   /* bam_name2id(header, FragName) */
+   int32_t beg, end;              /* the window: sam_itr_queryi(idx, tid, window.getStart(), window.getEnd()) */
+   int32_t insert_size;           /* the BAM file's insert size (configuration file) */
+   uint32_t min_anchor_quality;   /* userSettings->minimalAnchorQuality (-A, default 0) */
+} pg_rp_query;
+struct pg_rp;
+int pg_bam_rp_discovery(pg_ctx *ctx, const pg_rp_query *q, struct pg_rp *rows, uint32_t *src, uint64_t cap, uint64_t *n_rows,
+                        struct pg_rp *inter_rows, uint32_t *inter_src, uint64_t inter_cap, uint64_t *n_inter, uint64_t *n_scanned);
+
 /* ------------------------------------------------------------------------------------------------------------------
  * Discordant-read-pair clustering: the two quadratic loops of BDData::UpdateBD
  * (src/bddata.cpp:646-659) that turn the window's discordant pairs into BreakDancer-like events for the far-end search.

@@ -43,6 +43,7 @@
 #include "search_inversions_nt.h"
 
 #include <cstdio>
+#include <dlfcn.h>
 #include <algorithm>
 #include <cstdlib>
 #include <mutex>
@@ -704,7 +705,9 @@ int searchInversionsNT(ControlState &currentState, unsigned NumBoxes, const Sear
 /* Row N3 (first half): the BAM reader behind the reference's htslib calls (oracle/shim/minihts.cpp) inflates the file
  * through pg_bgzf_inflate instead of zlib.  PG_BRIDGE_ZLIB=1 keeps zlib (the test compares both). */
 extern "C" int (*minihts_inflate_hook)(const uint8_t *file, size_t len, std::vector<uint8_t> &out);
-static unsigned long g_bgzf_bytes = 0;
+static unsigned long g_bgzf_bytes = 0, g_rpd_rows = 0;
+static const std::vector<uint8_t> *g_lastStream = NULL;
+static std::vector<pg_bam_rec> g_lastTable;
 static int deviceInflate(const uint8_t *file, size_t len, std::vector<uint8_t> &out)
 {
    std::lock_guard<std::mutex> lock(g_mutex);
@@ -715,6 +718,8 @@ static int deviceInflate(const uint8_t *file, size_t len, std::vector<uint8_t> &
    size_t got = 0;
    if (pg_bgzf_inflate(g_ctx, file, len, out.empty() ? NULL : &out[0], out.size(), &got, 1) != PG_OK) die("pg_bgzf_inflate");
    g_bgzf_bytes += (unsigned long)got;
+   g_lastStream = &out;          /* the reader's copy of the stream: valid until its sam_close */
+   g_lastTable.clear();
    return 0;
 }
 
@@ -733,16 +738,84 @@ static int deviceIndex(size_t first_record, std::vector<uint8_t> &rows24)
    rows24.resize((size_t)n * sizeof(pg_bam_rec));
    if (n && pg_bam_index(g_ctx, (pg_bam_rec *)&rows24[0], n, &n, NULL, NULL) != PG_OK) die("pg_bam_index");
    g_bam_records += (unsigned long)n;
+   g_lastTable.assign((const pg_bam_rec *)rows24.data(), (const pg_bam_rec *)rows24.data() + n);
    return 0;
+}
+
+/* Row N2, first half: ReadInBamReads_RP_Discovery (src/reader.cpp:418-480) is a free function of reader.cpp; bound by symbol
+ * like the others.  The file is opened through the reference's own htslib calls (so the stream is inflated and indexed on
+ * the device by the two hooks above), the region iterator + build_record_RP_Discovery run as pg_bam_rp_discovery on the
+ * resident stream, and the rows come back with the index of their record for the fields only the host needs (ReadName,
+ * reference names).  With PG_BRIDGE_ZLIB=1 the reference's own function runs (found with dlsym(RTLD_NEXT)). */
+extern unsigned int g_NumReadScanned;
+typedef bool (*RpDiscoveryFn)(const char *, const std::string &, const std::string *, std::vector<RP_READ> &, std::vector<RP_READ> &, int, std::string,
+                              const SearchWindow &);
+bool ReadInBamReads_RP_Discovery(const char *bam_path, const std::string &FragName, const std::string *CurrentChrSeq, std::vector<RP_READ> &LeftReads,
+                                 std::vector<RP_READ> &LeftReads_InterChr, int InsertSize, std::string Tag, const SearchWindow &currentWindow)
+{
+   if (minihts_index_hook == NULL) {
+      static RpDiscoveryFn original = (RpDiscoveryFn)dlsym(RTLD_NEXT, "_Z27ReadInBamReads_RP_DiscoveryPKcRKNSt7__cxx1112basic_stringIcSt11char_traitsIcESaIcEEEPS7_RSt6vectorI7RP_READSaISB_EESE_iS6_RK12SearchWindow");
+      if (!original) { std::fprintf(stderr, "pindel_gpu_demo: the reference's ReadInBamReads_RP_Discovery was not found\n"); std::exit(EXIT_FAILURE); }
+      return original(bam_path, FragName, CurrentChrSeq, LeftReads, LeftReads_InterChr, InsertSize, Tag, currentWindow);
+   }
+   samFile *fp = sam_open(bam_path, "r");
+   if (!fp) return false;
+   hts_idx_t *idx = sam_index_load(fp, bam_path);
+   bam_hdr_t *header = sam_hdr_read(fp);
+   const int tid = bam_name2id(header, FragName.c_str());
+   {
+      std::lock_guard<std::mutex> lock(g_mutex);
+      pg_rp_query q;
+      q.tid = tid; q.beg = (int32_t)currentWindow.getStart(); q.end = (int32_t)currentWindow.getEnd(); q.insert_size = InsertSize;
+      q.min_anchor_quality = userSettings->minimalAnchorQuality;
+      uint64_t n = 0, ni = 0, scanned = 0;
+      int rc = pg_bam_rp_discovery(g_ctx, &q, NULL, NULL, 0, &n, NULL, NULL, 0, &ni, &scanned);
+      std::vector<pg_rp> rows(n ? n : 1), irows(ni ? ni : 1);
+      std::vector<uint32_t> src(n ? n : 1), isrc(ni ? ni : 1);
+      if (rc == PG_ERR_RUNS_CAP) rc = pg_bam_rp_discovery(g_ctx, &q, &rows[0], &src[0], n, &n, &irows[0], &isrc[0], ni, &ni, &scanned);
+      if (rc != PG_OK) die("pg_bam_rp_discovery");
+      g_NumReadScanned += (unsigned int)scanned;
+      const uint8_t *stream = g_lastStream->data();
+      for (int list = 0; list < 2; list++) {
+         const uint64_t cnt = list ? ni : n;
+         for (uint64_t i = 0; i < cnt; i++) {
+            const pg_rp &r = list ? irows[i] : rows[i];
+            const pg_bam_rec &br = g_lastTable[list ? isrc[i] : src[i]];
+            const uint8_t *rec = stream + br.off + 4;
+            const int32_t mtid = (int32_t)(rec[20] | rec[21] << 8 | rec[22] << 16 | (uint32_t)rec[23] << 24);
+            RP_READ t;
+            t.DA = (char)r.da; t.DB = (char)r.db;
+            t.PosA = t.OriginalPosA = r.pos_a;
+            t.PosB = t.OriginalPosB = r.pos_b;
+            t.Experimental_InsertSize = InsertSize;
+            t.ReadName = (const char *)(rec + 32);
+            t.MQA = t.MQB = br.mapq;
+            t.ChrNameA = header->target_name[br.tid];
+            t.ChrNameB = header->target_name[mtid];
+            t.InsertSize = InsertSize;
+            t.Tag = Tag;
+            t.Tags.clear();
+            t.Tags.push_back(Tag);
+            t.ReadLength = r.read_length;
+            (list ? LeftReads_InterChr : LeftReads).push_back(t);
+         }
+      }
+      g_rpd_rows += (unsigned long)(n + ni);
+   }
+   bam_hdr_destroy(header);
+   hts_idx_destroy(idx);
+   sam_close(fp);
+   (void)CurrentChrSeq;
+   return true;
 }
 
 static void reportAtExit()
 {
    std::fprintf(stderr, "pindel_gpu_demo: %lu GetCloseEnd calls and %lu far-end reads served by libpindel_pg (%llu kernel launches); "
-                "%lu reads classified by the SV drivers on the device, %lu records (%llu launches), %lu of the reads without a second upload; %lu read pairs clustered on the device (%llu launches); %lu BAM bytes inflated and %lu records indexed on the device\n",
+                "%lu reads classified by the SV drivers on the device, %lu records (%llu launches), %lu of the reads without a second upload; %lu read pairs clustered on the device (%llu launches); %lu BAM bytes inflated and %lu records indexed on the device, %lu discordant pairs found there\n",
                 g_close_calls, g_far_reads, g_ctx ? (unsigned long long)pg_kernel_launches(g_ctx) : 0ull, g_sv_reads, g_sv_records,
                 g_ctx ? (unsigned long long)pg_classify_launches(g_ctx) : 0ull, g_sv_resident, g_rp_rows,
-                g_ctx ? (unsigned long long)pg_rp_launches(g_ctx) : 0ull, g_bgzf_bytes, g_bam_records);
+                g_ctx ? (unsigned long long)pg_rp_launches(g_ctx) : 0ull, g_bgzf_bytes, g_bam_records, g_rpd_rows);
 }
 
 int main(int argc, char *argv[])

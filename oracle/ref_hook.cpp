@@ -464,3 +464,38 @@ extern "C" int64_t pgref_rp_cluster(int n, const uint32_t *pos_a, const uint32_t
    *out_stream = buf;
    return (int64_t)out.size();
 }
+
+/* Row N2, first half: the reference's own discordant-pair discovery for one BAM file and window
+ * (ReadInBamReads_RP_Discovery, src/reader.cpp:418-480 -> build_record_RP_Discovery, :982-1097), through the BAM reader of
+ * oracle/shim/minihts.cpp.  Needs pgref_init (the window's chromosome comes from the loaded genome).
+ * out: 9 int32 per row -- list (0 = Reads_RP_Discovery, 1 = ..._InterChr), PosA, PosB, DA, DB, ReadLength, InsertSize, MQA,
+ * FNV-1a of ReadName -- in the order the reference pushed them; then 1 int32: g_NumReadScanned's increase. */
+bool ReadInBamReads_RP_Discovery(const char *bam_path, const std::string &FragName, const std::string *CurrentChrSeq, std::vector<RP_READ> &LeftReads,
+                                 std::vector<RP_READ> &LeftReads_InterChr, int InsertSize, std::string Tag, const SearchWindow &currentWindow);
+extern unsigned int g_NumReadScanned;
+
+extern "C" int64_t pgref_rp_discovery(const char *bam_path, int chr, uint32_t start, uint32_t end, int insert_size, int32_t **out_stream)
+{
+   const Chromosome *c = g_genome.getChr((unsigned)chr);
+   if (c == NULL) return -1;
+   SearchWindow w(c, start, end);
+   std::vector<RP_READ> intra, inter;
+   const unsigned before = g_NumReadScanned;
+   if (!ReadInBamReads_RP_Discovery(bam_path, c->getName(), &c->getSeq(), intra, inter, insert_size, "TAG", w)) return -2;
+   std::vector<int32_t> out;
+   for (int list = 0; list < 2; list++) {
+      const std::vector<RP_READ> &v = list ? inter : intra;
+      for (size_t i = 0; i < v.size(); i++) {
+         uint32_t h = 2166136261u;
+         for (size_t k = 0; k < v[i].ReadName.size(); k++) h = (h ^ (uint8_t)v[i].ReadName[k]) * 16777619u;
+         const int32_t row[9] = {list, (int32_t)v[i].PosA, (int32_t)v[i].PosB, v[i].DA, v[i].DB, v[i].ReadLength, (int32_t)v[i].InsertSize,
+                                 v[i].MQA, (int32_t)h};
+         out.insert(out.end(), row, row + 9);
+      }
+   }
+   out.push_back((int32_t)(g_NumReadScanned - before));
+   int32_t *buf = (int32_t *)malloc(out.size() * sizeof(int32_t) + 4);
+   memcpy(buf, out.data(), out.size() * sizeof(int32_t));
+   *out_stream = buf;
+   return (int64_t)out.size();
+}

@@ -102,6 +102,28 @@ class RefHook:
             os.close(saved)
             os.close(devnull)
 
+    def rp_discovery(self, bam_path: str, chr_id: int, start: int, end: int, insert_size: int):
+        """The reference's ReadInBamReads_RP_Discovery on one BAM file and window -> (rows [k, 9] int64: list, PosA, PosB, DA,
+        DB, ReadLength, InsertSize, MQA, FNV-1a of ReadName; records scanned)."""
+        self.lib.pgref_rp_discovery.restype = C.c_int64
+        out = C.POINTER(C.c_int32)()
+        devnull = os.open(os.devnull, os.O_WRONLY)
+        saved = os.dup(1)
+        os.dup2(devnull, 1)
+        try:
+            k = self.lib.pgref_rp_discovery(bam_path.encode(), chr_id, C.c_uint32(start), C.c_uint32(end), insert_size, C.byref(out))
+        finally:
+            os.dup2(saved, 1)
+            os.close(saved)
+            os.close(devnull)
+        if k < 0:
+            raise RuntimeError("pgref_rp_discovery failed: %d" % k)
+        stream = np.ctypeslib.as_array(out, shape=(int(k),)).copy()
+        self.lib.pgref_free(out)
+        rows = stream[:-1].reshape(-1, 9).astype(np.int64)
+        rows[:, [1, 2, 6, 8]] &= 0xFFFFFFFF
+        return rows, int(stream[-1])
+
     def set_window(self, chr_id: int, start: int, end: int) -> None:
         if self.lib.pgref_set_window(chr_id, C.c_uint32(start), C.c_uint32(end)) != 0:
             raise RuntimeError("pgref_set_window failed")

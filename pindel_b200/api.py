@@ -99,6 +99,8 @@ def load_library() -> C.CDLL:
         lib.pg_bgzf_last_kernel_ms.restype = C.c_double
         lib.pg_bgzf_last_kernel_ms.argtypes = [C.c_void_p]
         lib.pg_bam_index.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64), C.POINTER(C.c_int32)]
+        lib.pg_bam_rp_discovery.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.POINTER(C.c_uint64), C.c_void_p, C.c_void_p,
+                                            C.c_uint64, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]
         lib.pg_bam_launches.restype = C.c_uint64
         lib.pg_bam_launches.argtypes = [C.c_void_p]
         lib.pg_bam_last_ms.restype = C.c_double
@@ -371,6 +373,24 @@ class PatternGrowth:
                 return recs, int(first.value), int(nref.value)
         self._check(self.lib.pg_bam_index(self.ctx, recs.ctypes.data, recs.size, C.byref(n), C.byref(first), C.byref(nref)), "pg_bam_index")
         return recs[:n.value], int(first.value), int(nref.value)
+
+    def bam_rp_discovery(self, tid, beg, end, insert_size, min_anchor_quality=0):
+        """Discordant-pair discovery on the indexed stream (after bgzf_inflate + bam_index).
+        -> (rows (rp.RP_DT), src, inter_rows, inter_src, records delivered by the region iterator)"""
+        from . import rp
+        q = np.array([(tid, beg, end, insert_size, min_anchor_quality)],
+                     dtype=[("tid", "<i4"), ("beg", "<i4"), ("end", "<i4"), ("insert_size", "<i4"), ("min_anchor_quality", "<u4")])
+        n, ni, ns = C.c_uint64(0), C.c_uint64(0), C.c_uint64(0)
+        rc = self.lib.pg_bam_rp_discovery(self.ctx, q.ctypes.data, None, None, 0, C.byref(n), None, None, 0, C.byref(ni), C.byref(ns))
+        if rc not in (0, PG_ERR_RUNS_CAP):
+            self._check(rc, "pg_bam_rp_discovery")
+        rows, src = np.zeros(int(n.value), dtype=rp.RP_DT), np.zeros(int(n.value), dtype=np.uint32)
+        irows, isrc = np.zeros(int(ni.value), dtype=rp.RP_DT), np.zeros(int(ni.value), dtype=np.uint32)
+        if rc == PG_ERR_RUNS_CAP:
+            vp = lambda a: a.ctypes.data_as(C.c_void_p) if a.size else None
+            self._check(self.lib.pg_bam_rp_discovery(self.ctx, q.ctypes.data, vp(rows), vp(src), rows.size, C.byref(n), vp(irows), vp(isrc), irows.size,
+                                                     C.byref(ni), C.byref(ns)), "pg_bam_rp_discovery")
+        return rows, src, irows, isrc, int(ns.value)
 
     def bam_last_segments(self):
         a, b = C.c_uint32(0), C.c_uint32(0)

@@ -58,7 +58,8 @@ def serial_index(stream: bytes) -> np.ndarray:
     return np.array(rows, dtype=REC_DT) if rows else np.zeros(0, dtype=REC_DT)
 
 
-def synthetic_stream(n_records: int, seed: int, refs=(("chr1", 50_000_000), ("chr2", 30_000_000)), adversarial: bool = False) -> bytes:
+def synthetic_stream(n_records: int, seed: int, refs=(("chr1", 50_000_000), ("chr2", 30_000_000)), adversarial: bool = False,
+                     discordant: float = 0.0) -> bytes:
     """A coordinate-sorted BAM stream (inflated).  adversarial: sequence / quality / tag bytes that contain whole fake
     records (valid-looking headers with names), so that a segment boundary falling into them makes the guess lock on."""
     rng = np.random.default_rng(seed)
@@ -86,6 +87,20 @@ def synthetic_stream(n_records: int, seed: int, refs=(("chr1", 50_000_000), ("ch
         aux = b"NMC" + bytes([int(rng.integers(0, 5))]) + b"RGZgrp%d\0" % int(rng.integers(0, 3))
         if adversarial and rng.random() < 0.3:
             aux += b"XZB" + b"C" + struct.pack("<I", 3 * len(fake)) + fake * 3       # B-array tag carrying three fake records
+        mtid, mpos, tlen = tid, pos + int(rng.integers(100, 600)), int(rng.integers(-600, 600))
+        if rng.random() < discordant:          # pairs the discovery keeps: far mate, mate on the other reference, mate before the read
+            k = rng.random()
+            if k < 0.4:
+                tlen = int(rng.integers(2000, 900_000)) * (1 if rng.random() < 0.5 else -1)
+                mpos = max(0, pos + tlen)
+            elif k < 0.7:
+                mtid = 1 - tid
+                mpos = int(rng.integers(0, 1_000_000))
+            else:
+                flag = int(rng.choice([65, 129, 113, 177]))         # both mates on one strand
+                mpos = max(0, pos - int(rng.integers(0, 3000)))
+            if rng.random() < 0.1:
+                flag |= 8                                           # mate unmapped: not a pair for the discovery
         out.append(record(tid if cig else -1 if rng.random() < 0.02 else tid, pos, b"read_%d_%d" % (seed, i), flag, int(rng.integers(0, 61)), cig, rl,
-                          tid, pos + int(rng.integers(100, 600)), int(rng.integers(-600, 600)), aux, rng))
+                          mtid, mpos, tlen, aux, rng))
     return b"".join(out)

@@ -127,6 +127,55 @@ PGB_HD uint64_t pgb_header(const uint8_t *d, uint64_t n, int32_t *n_ref)
    return p;
 }
 
+// ---- discordant-pair discovery on the indexed stream (first half) ----------------------
+// ReadInBamReads_RP_Discovery (src/reader.cpp:418-480): every record the region iterator delivers goes through
+// build_record_RP_Discovery (src/reader.cpp:982-1097), a stateless test that keeps paired, well-mapped reads whose mate is on
+// another reference, too far away, or on the same strand, as one RP_READ row (mates ordered by position when both are on
+// one reference).
+struct PgRpQuery {       // pg_rp_query
+   int32_t tid;          // bam_name2id(header, FragName)
+   int32_t beg, end;     // window.getStart(), window.getEnd(): sam_itr_queryi's region
+   int32_t insert_size;  // the BAM file's insert size from the configuration file
+   uint32_t min_anchor_quality;   // userSettings->minimalAnchorQuality (-A)
+};
+
+struct PgRpRow {         // pg_rp (same layout as PgRp in pg_rp.cuh)
+   uint32_t pos_a, pos_b;
+   uint32_t insert_size;
+   int16_t read_length;
+   uint8_t da, db;
+};
+
+// the iterator ends at the first record that lies past the region (the stream is coordinate-sorted)
+PGB_HD bool pgb_itr_stops(const PgBamRec &r, const PgRpQuery &q) { return r.tid != q.tid ? (r.tid > q.tid || r.tid < 0) : r.pos >= q.end; }
+PGB_HD bool pgb_itr_delivers(const PgBamRec &r, const PgRpQuery &q) { return r.tid == q.tid && r.pos < q.end && r.end > (q.beg < 0 ? 0 : q.beg); }
+
+// 0 = not kept, 1 = Reads_RP_Discovery (both mates on one reference), 2 = Reads_RP_Discovery_InterChr
+PGB_HD int pgb_rp_discovery(const uint8_t *d, const PgBamRec &r, const PgRpQuery &q, PgRpRow &row)
+{
+   const uint8_t *rec = d + r.off + 4;
+   const uint32_t flag = r.flag;
+   if (!(flag & 1u)) return 0;                                   // BAM_FPAIRED
+   if ((uint32_t)r.mapq < q.min_anchor_quality) return 0;
+   if (flag & (4u | 8u)) return 0;                               // BAM_FUNMAP | BAM_FMUNMAP
+   const int32_t mtid = (int32_t)pgb_le32(rec + 20), mpos = (int32_t)pgb_le32(rec + 24), isize = (int32_t)pgb_le32(rec + 28);
+   const bool rev = (flag & 16u) != 0, mrev = (flag & 32u) != 0;
+   const int32_t aisize = isize < 0 ? -isize : isize;
+   if (!(r.tid != mtid || aisize > 3 * q.insert_size + 1000 || rev == mrev)) return 0;
+   row.da = rev ? '-' : '+';
+   row.db = mrev ? '-' : '+';
+   row.pos_a = (uint32_t)r.pos;
+   row.pos_b = (uint32_t)mpos;
+   row.read_length = (int16_t)(int32_t)pgb_le32(rec + 16);       // short ReadLength = l_qseq
+   row.insert_size = (uint32_t)q.insert_size;
+   if (r.tid != mtid) return 2;
+   if (!(row.pos_a < row.pos_b)) {                               // the mate comes first: the row is stored from its side
+      const uint32_t p = row.pos_a; row.pos_a = row.pos_b; row.pos_b = p;
+      const uint8_t s = row.da; row.da = row.db; row.db = s;
+   }
+   return 1;
+}
+
 #ifdef __CUDACC__
 // info: [0] first record offset (PGB_NONE = not a BAM stream), [1] n_ref
 __global__ void pg_bam_header_kernel(const uint8_t *__restrict__ d, uint64_t n, uint64_t *__restrict__ info)
@@ -180,5 +229,48 @@ __global__ void pg_bam_walk_kernel(const uint8_t *__restrict__ d, uint64_t n, ui
    uint64_t k = 0;
    const uint64_t land = pgb_walk(d, n, st, b1 < n ? b1 : n, recs ? recs + base[s] : (PgBamRec *)0, &k);
    if (!recs) { counts[s] = land == PGB_NONE ? 0 : k; landing[s] = land; }
+}
+// counters: [0] index of the first record past the region (initialised to n_recs), [1] records delivered
+__global__ void pg_bam_stop_kernel(const PgBamRec *__restrict__ recs, uint32_t n_recs, PgRpQuery q, uint32_t *__restrict__ counters)
+{
+   const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+   const bool stops = i < n_recs && pgb_itr_stops(recs[i], q);
+   const uint32_t m = __ballot_sync(0xFFFFFFFFu, stops);
+   if (m && (threadIdx.x & 31u) == 0) atomicMin(&counters[0], (i & ~31u) + (uint32_t)__ffs(m) - 1u);
+}
+
+// cls_intra[i] / cls_inter[i] = 1 when record i yields a row of that list (byte arrays, scanned into positions afterwards)
+__global__ void pg_bam_rpd_flag_kernel(const uint8_t *__restrict__ d, const PgBamRec *__restrict__ recs, uint32_t n_recs, PgRpQuery q,
+                                       uint32_t *__restrict__ counters, uint8_t *__restrict__ cls_intra, uint8_t *__restrict__ cls_inter)
+{
+   const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+   bool delivered = false;
+   int cls = 0;
+   if (i < n_recs && i < counters[0]) {
+      const PgBamRec r = recs[i];
+      delivered = pgb_itr_delivers(r, q);
+      PgRpRow row;
+      if (delivered) cls = pgb_rp_discovery(d, r, q, row);
+   }
+   if (i < n_recs) {
+      cls_intra[i] = cls == 1;
+      cls_inter[i] = cls == 2;
+   }
+   const uint32_t m = __ballot_sync(0xFFFFFFFFu, delivered);
+   if (m && (threadIdx.x & 31u) == 0) atomicAdd(&counters[1], (uint32_t)__popc(m));
+}
+
+__global__ void pg_bam_rpd_scatter_kernel(const uint8_t *__restrict__ d, const PgBamRec *__restrict__ recs, uint32_t n_recs, PgRpQuery q,
+                                          const uint8_t *__restrict__ cls_intra, const uint8_t *__restrict__ cls_inter,
+                                          const uint32_t *__restrict__ off_intra, const uint32_t *__restrict__ off_inter,
+                                          PgRpRow *__restrict__ rows, uint32_t *__restrict__ src, PgRpRow *__restrict__ inter_rows,
+                                          uint32_t *__restrict__ inter_src)
+{
+   const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+   if (i >= n_recs || !(cls_intra[i] | cls_inter[i])) return;
+   PgRpRow row;
+   pgb_rp_discovery(d, recs[i], q, row);
+   if (cls_intra[i]) { rows[off_intra[i]] = row; src[off_intra[i]] = i; }
+   else { inter_rows[off_inter[i]] = row; inter_src[off_inter[i]] = i; }
 }
 #endif

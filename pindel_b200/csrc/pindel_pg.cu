@@ -372,7 +372,9 @@ struct pg_ctx {
    uint64_t sv_aux_launches = 0;
    // BGZF inflation (pg_bgzf_inflate)
    DevBuf bz_file, bz_blocks, bz_out, bz_status, bm_info, bm_starts, bm_counts, bm_landing, bm_base, bm_recs;
-   uint64_t bm_launches = 0;
+   uint64_t bm_launches = 0, bm_n_recs = 0;
+   bool bm_valid = false;       // bm_recs holds the table of the resident stream
+   DevBuf bd_cls, bd_off, bd_sums, bd_rows, bd_src, bd_counters;
    uint32_t bm_last_segments = 0, bm_last_redone = 0;
    float bm_last_ms = 0.f;
    size_t bz_out_len = 0;
@@ -538,7 +540,8 @@ void pg_destroy(pg_ctx *ctx)
                        &ctx->sv_counts, &ctx->sv_offsets, &ctx->sv_blocksums, &ctx->sv_ordered, &ctx->sv_close_off,
                        &ctx->sv_close_runs, &ctx->rp_in, &ctx->rp_out, &ctx->rp_rows, &ctx->rp_off, &ctx->rp_scratch, &ctx->rp_merged,
                        &ctx->rp_nid, &ctx->rp_counters, &ctx->rp_keys, &ctx->bz_file, &ctx->bz_blocks, &ctx->bz_out, &ctx->bz_status,
-                       &ctx->bm_info, &ctx->bm_starts, &ctx->bm_counts, &ctx->bm_landing, &ctx->bm_base, &ctx->bm_recs};
+                       &ctx->bm_info, &ctx->bm_starts, &ctx->bm_counts, &ctx->bm_landing, &ctx->bm_base, &ctx->bm_recs,
+                       &ctx->bd_cls, &ctx->bd_off, &ctx->bd_sums, &ctx->bd_rows, &ctx->bd_src, &ctx->bd_counters};
    for (DevBuf *b : svbufs) if (b->p) cudaFree(b->p);
    pipe_destroy(ctx->pipe);
    if (ctx->chroms_d) cudaFree(ctx->chroms_d);
@@ -1247,6 +1250,7 @@ int pg_bgzf_inflate(pg_ctx *ctx, const uint8_t *file, size_t file_len, uint8_t *
    const size_t total = blocks.empty() ? 0 : (size_t)(blocks.back().out_off + blocks.back().isize);
    *out_len = total;
    ctx->bz_out_len = 0;
+   ctx->bm_valid = false;
    if (out && out_cap < total) return fail(ctx, PG_ERR_RUNS_CAP, "pg_bgzf_inflate: output buffer too small (out_len holds the required size)");
    if (blocks.empty()) return PG_OK;
    CU(cudaSetDevice(ctx->device));
@@ -1370,6 +1374,8 @@ int pg_bam_index(pg_ctx *ctx, pg_bam_rec *recs, uint64_t cap, uint64_t *n_recs, 
    }
    CU(cudaStreamSynchronize(st));
    CU(cudaEventElapsedTime(&ctx->bm_last_ms, ctx->sv_ev0, ctx->sv_ev1));
+   ctx->bm_n_recs = total;
+   ctx->bm_valid = true;
    return PG_OK;
 }
 
@@ -1380,6 +1386,89 @@ void pg_bam_last_segments(pg_ctx *ctx, uint32_t *segments, uint32_t *walked_agai
    if (!ctx) return;
    if (segments) *segments = ctx->bm_last_segments;
    if (walked_again) *walked_again = ctx->bm_last_redone;
+}
+
+// ---- discordant-pair discovery on the indexed stream (row N2, first half) ---------------------------------------------
+static_assert(sizeof(pg_rp_query) == sizeof(PgRpQuery) && sizeof(PgRpRow) == sizeof(pg_rp), "rp query / row layout");
+
+int pg_bam_rp_discovery(pg_ctx *ctx, const pg_rp_query *q, pg_rp *rows, uint32_t *src, uint64_t cap, uint64_t *n_rows, pg_rp *inter_rows,
+                        uint32_t *inter_src, uint64_t inter_cap, uint64_t *n_inter, uint64_t *n_scanned)
+{
+   if (!ctx || !q || !n_rows || !n_inter) return fail(ctx, PG_ERR_ARG, "pg_bam_rp_discovery: null argument");
+   if (!ctx->bm_valid || ctx->bz_out_len == 0) return fail(ctx, PG_ERR_STATE, "pg_bam_rp_discovery: no indexed stream is resident (pg_bgzf_inflate + pg_bam_index)");
+   *n_rows = *n_inter = 0;
+   if (n_scanned) *n_scanned = 0;
+   const uint64_t n64 = ctx->bm_n_recs;
+   if (n64 == 0) return PG_OK;
+   if (n64 > 0xFFFFFFF0ull) return fail(ctx, PG_ERR_UNSUPPORTED, "pg_bam_rp_discovery: more than 2^32 records");
+   const uint32_t n = (uint32_t)n64;
+   CU(cudaSetDevice(ctx->device));
+   cudaStream_t st = ctx->stream;
+   PgRpQuery qq;
+   memcpy(&qq, q, sizeof qq);
+   const uint32_t n16 = (n + 15u) / 16u, n_blocks = (n16 + PG_SCAN_THREADS - 1) / PG_SCAN_THREADS;
+   int rc;
+   if ((rc = ensure(ctx, ctx->bd_cls, (size_t)n16 * 16 * 2)) != PG_OK) return rc;
+   if ((rc = ensure(ctx, ctx->bd_off, sizeof(uint32_t) * (size_t)n16 * 16 * 2)) != PG_OK) return rc;
+   if ((rc = ensure(ctx, ctx->bd_sums, sizeof(uint32_t) * ((size_t)n_blocks + 1) * 2)) != PG_OK) return rc;
+   if ((rc = ensure(ctx, ctx->bd_counters, sizeof(uint32_t) * 2)) != PG_OK) return rc;
+   uint8_t *cls_intra = (uint8_t *)ctx->bd_cls.p, *cls_inter = cls_intra + (size_t)n16 * 16;
+   uint32_t *off_intra = (uint32_t *)ctx->bd_off.p, *off_inter = off_intra + (size_t)n16 * 16;
+   uint32_t *sums_intra = (uint32_t *)ctx->bd_sums.p, *sums_inter = sums_intra + n_blocks + 1;
+   const uint32_t init[2] = {n, 0u};
+   CU(cudaMemcpyAsync(ctx->bd_counters.p, init, sizeof init, cudaMemcpyHostToDevice, st));
+   CU(cudaMemsetAsync(ctx->bd_cls.p, 0, (size_t)n16 * 16 * 2, st));
+   const uint8_t *d = (const uint8_t *)ctx->bz_out.p;
+   const PgBamRec *recs = (const PgBamRec *)ctx->bm_recs.p;
+   if (!ctx->sv_ev0) { CU(cudaEventCreate(&ctx->sv_ev0)); CU(cudaEventCreate(&ctx->sv_ev1)); }
+   CU(cudaEventRecord(ctx->sv_ev0, st));
+   const uint32_t grid = (n + 255u) / 256u;
+   pg_bam_stop_kernel<<<grid, 256, 0, st>>>(recs, n, qq, (uint32_t *)ctx->bd_counters.p);
+   pg_bam_rpd_flag_kernel<<<grid, 256, 0, st>>>(d, recs, n, qq, (uint32_t *)ctx->bd_counters.p, cls_intra, cls_inter);
+   for (int list = 0; list < 2; list++) {
+      const uint4 *c16 = (const uint4 *)(list ? cls_inter : cls_intra);
+      uint32_t *sums = list ? sums_inter : sums_intra;
+      pg_scan_reduce<<<n_blocks, PG_SCAN_THREADS, 0, st>>>(c16, n16, sums);
+      pg_scan_blocks<<<1, 1024, 0, st>>>(sums, n_blocks);
+      pg_scan_apply<<<n_blocks, PG_SCAN_THREADS, 0, st>>>(c16, n16, sums, list ? off_inter : off_intra);
+   }
+   CU(cudaGetLastError());
+   ctx->bm_launches += 8;
+   uint32_t counters[2], tot_intra = 0, tot_inter = 0;
+   CU(cudaMemcpyAsync(counters, ctx->bd_counters.p, sizeof counters, cudaMemcpyDeviceToHost, st));
+   CU(cudaMemcpyAsync(&tot_intra, sums_intra + n_blocks, sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+   CU(cudaMemcpyAsync(&tot_inter, sums_inter + n_blocks, sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+   CU(cudaStreamSynchronize(st));
+   *n_rows = tot_intra;
+   *n_inter = tot_inter;
+   if (n_scanned) *n_scanned = counters[1];
+   if (tot_intra > cap || tot_inter > inter_cap || (tot_intra && (!rows || !src)) || (tot_inter && (!inter_rows || !inter_src)))
+      return fail(ctx, PG_ERR_RUNS_CAP, "pg_bam_rp_discovery: row buffers too small (n_rows / n_inter hold the required sizes)");
+   const size_t tot = (size_t)tot_intra + tot_inter;
+   if (tot) {
+      if ((rc = ensure(ctx, ctx->bd_rows, sizeof(PgRpRow) * tot)) != PG_OK) return rc;
+      if ((rc = ensure(ctx, ctx->bd_src, sizeof(uint32_t) * tot)) != PG_OK) return rc;
+      PgRpRow *rows_d = (PgRpRow *)ctx->bd_rows.p;
+      uint32_t *src_d = (uint32_t *)ctx->bd_src.p;
+      pg_bam_rpd_scatter_kernel<<<grid, 256, 0, st>>>(d, recs, n, qq, cls_intra, cls_inter, off_intra, off_inter, rows_d, src_d, rows_d + tot_intra,
+                                                      src_d + tot_intra);
+      CU(cudaGetLastError());
+      ctx->bm_launches++;
+      CU(cudaEventRecord(ctx->sv_ev1, st));
+      if (tot_intra) {
+         CU(cudaMemcpyAsync(rows, rows_d, sizeof(PgRpRow) * (size_t)tot_intra, cudaMemcpyDeviceToHost, st));
+         CU(cudaMemcpyAsync(src, src_d, sizeof(uint32_t) * (size_t)tot_intra, cudaMemcpyDeviceToHost, st));
+      }
+      if (tot_inter) {
+         CU(cudaMemcpyAsync(inter_rows, rows_d + tot_intra, sizeof(PgRpRow) * (size_t)tot_inter, cudaMemcpyDeviceToHost, st));
+         CU(cudaMemcpyAsync(inter_src, src_d + tot_intra, sizeof(uint32_t) * (size_t)tot_inter, cudaMemcpyDeviceToHost, st));
+      }
+   } else {
+      CU(cudaEventRecord(ctx->sv_ev1, st));
+   }
+   CU(cudaStreamSynchronize(st));
+   CU(cudaEventElapsedTime(&ctx->bm_last_ms, ctx->sv_ev0, ctx->sv_ev1));
+   return PG_OK;
 }
 
 // ---- read-pair clustering (row N2) --------------------------------------------------------------------------------

@@ -61,8 +61,10 @@ def sim_prefix_bam(demo, tmp_path, env):
     m = re.search(r"(\d+) read pairs clustered on the device \((\d+) launches\)", p.stderr)
     assert m and int(m.group(1)) > 0 and int(m.group(2)) > 0, p.stderr[-500:]
     # row N3 (first half): the BAM file was inflated by pg_bgzf_inflate
-    m = re.search(r"(\d+) BAM bytes inflated and (\d+) records indexed on the device", p.stderr)
+    m = re.search(r"(\d+) BAM bytes inflated and (\d+) records indexed on the device, (\d+) discordant pairs found there", p.stderr)
     size = len(gzip.decompress((tmp_path / "sim_prefix.bam").read_bytes()))      # the reference opens the file several times
     assert m and (int(m.group(1)) == 0 if env.get("PG_BRIDGE_ZLIB") else (int(m.group(1)) > 0 and int(m.group(1)) % size == 0)), p.stderr[-300:]
     assert (int(m.group(2)) == 0) == bool(env.get("PG_BRIDGE_ZLIB")), p.stderr[-300:]
+    # row N2, first half: the discordant pairs came from pg_bam_rp_discovery (7928 in this fixture, as the reference finds)
+    assert int(m.group(3)) == (0 if env.get("PG_BRIDGE_ZLIB") else 7928), p.stderr[-300:]
     return p

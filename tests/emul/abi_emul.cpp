@@ -35,6 +35,7 @@ struct pg_ctx {
    std::vector<int16_t> res_isz;
    std::vector<int32_t> res_chr;
    std::vector<uint8_t> stream;   // the last inflated stream
+   std::vector<PgBamRec> bam_table;   // its record table (pg_bam_index with a buffer)
 };
 
 static std::string g_create_error;
@@ -237,6 +238,24 @@ int pg_bam_index(pg_ctx *ctx, pg_bam_rec *recs, uint64_t cap, uint64_t *n_recs, 
    if (n_ref) { int32_t r = 0; pgb_header(ctx->stream.data(), ctx->stream.size(), &r); *n_ref = r; }
    if ((uint64_t)n > cap || (n && !recs)) return fail(ctx, PG_ERR_RUNS_CAP, "record buffer too small");
    bamemu_index(ctx->stream.data(), ctx->stream.size(), 0, (PgBamRec *)recs, cap, stats);
+   ctx->bam_table.assign((const PgBamRec *)recs, (const PgBamRec *)recs + n);
+   return PG_OK;
+}
+int pg_bam_rp_discovery(pg_ctx *ctx, const pg_rp_query *q, pg_rp *rows, uint32_t *src, uint64_t cap, uint64_t *n_rows, pg_rp *inter_rows,
+                        uint32_t *inter_src, uint64_t inter_cap, uint64_t *n_inter, uint64_t *n_scanned)
+{
+   if (ctx->stream.empty()) return fail(ctx, PG_ERR_STATE, "no indexed stream");
+   const size_t n = ctx->bam_table.size();
+   std::vector<PgRpRow> a(n + 1), b(n + 1);
+   std::vector<uint32_t> sa(n + 1), sb(n + 1);
+   uint64_t counts[3] = {0, 0, 0};
+   bamemu_rp_discovery(ctx->stream.data(), ctx->bam_table.data(), (uint32_t)n, (const PgRpQuery *)q, a.data(), sa.data(), b.data(), sb.data(), counts);
+   *n_rows = counts[0];
+   *n_inter = counts[1];
+   if (n_scanned) *n_scanned = counts[2];
+   if (counts[0] > cap || counts[1] > inter_cap) return fail(ctx, PG_ERR_RUNS_CAP, "row buffers too small");
+   if (counts[0]) { memcpy(rows, a.data(), sizeof(pg_rp) * counts[0]); memcpy(src, sa.data(), 4 * counts[0]); }
+   if (counts[1]) { memcpy(inter_rows, b.data(), sizeof(pg_rp) * counts[1]); memcpy(inter_src, sb.data(), 4 * counts[1]); }
    return PG_OK;
 }
 uint64_t pg_classify_launches(pg_ctx *ctx) { return ctx ? ctx->sv_launches : 0; }

@@ -57,4 +57,25 @@ long bamemu_index(const uint8_t *d, uint64_t n, uint64_t seg, PgBamRec *recs, ui
    }
    return (long)total;
 }
+
+// pg_bam_rp_discovery in the kernels' formulation: the stop index, the class of every record before it, positions by
+// prefix count, scatter.  rows/src hold the intra rows then (from n_intra on) nothing; inter_* the inter-chromosomal ones.
+// counts[0] = intra rows, [1] = inter rows, [2] = records delivered.
+void bamemu_rp_discovery(const uint8_t *d, const PgBamRec *recs, uint32_t n_recs, const PgRpQuery *q, PgRpRow *rows, uint32_t *src,
+                         PgRpRow *inter_rows, uint32_t *inter_src, uint64_t *counts)
+{
+   uint32_t stop = n_recs;
+   for (uint32_t i = 0; i < n_recs; i++)
+      if (pgb_itr_stops(recs[i], *q)) { stop = i; break; }
+   uint64_t a = 0, b = 0, delivered = 0;
+   for (uint32_t i = 0; i < stop; i++) {
+      if (!pgb_itr_delivers(recs[i], *q)) continue;
+      delivered++;
+      PgRpRow row;
+      const int cls = pgb_rp_discovery(d, recs[i], *q, row);
+      if (cls == 1) { rows[a] = row; src[a++] = i; }
+      else if (cls == 2) { inter_rows[b] = row; inter_src[b++] = i; }
+   }
+   counts[0] = a; counts[1] = b; counts[2] = delivered;
+}
 }

@@ -37,3 +37,22 @@ def index(lib, stream: bytes, seg: int = 0):
     n2 = lib.bamemu_index(buf.ctypes.data, buf.size, seg, recs.ctypes.data, n, stats.ctypes.data)
     assert n2 == n
     return recs, tuple(int(x) for x in stats)
+
+
+RP_DT = np.dtype([("pos_a", "<u4"), ("pos_b", "<u4"), ("insert_size", "<u4"), ("read_length", "<i2"), ("da", "u1"), ("db", "u1")])
+QUERY_DT = np.dtype([("tid", "<i4"), ("beg", "<i4"), ("end", "<i4"), ("insert_size", "<i4"), ("min_anchor_quality", "<u4")])
+
+
+def rp_discovery(lib, stream: bytes, recs: np.ndarray, tid, beg, end, insert_size, min_anchor_quality=0):
+    """-> (rows, src, inter_rows, inter_src, records delivered)"""
+    buf = np.frombuffer(stream, dtype=np.uint8)
+    recs = np.ascontiguousarray(recs, dtype=REC_DT)
+    q = np.array([(tid, beg, end, insert_size, min_anchor_quality)], dtype=QUERY_DT)
+    n = recs.size
+    rows, src = np.zeros(n, dtype=RP_DT), np.zeros(n, dtype=np.uint32)
+    irows, isrc = np.zeros(n, dtype=RP_DT), np.zeros(n, dtype=np.uint32)
+    counts = np.zeros(3, dtype=np.uint64)
+    vp = lambda a: a.ctypes.data_as(C.c_void_p)
+    lib.bamemu_rp_discovery(vp(buf), vp(recs), C.c_uint32(n), vp(q), vp(rows), vp(src), vp(irows), vp(isrc), vp(counts))
+    a, b = int(counts[0]), int(counts[1])
+    return rows[:a], src[:a], irows[:b], isrc[:b], int(counts[2])
