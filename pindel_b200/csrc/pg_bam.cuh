@@ -8,8 +8,8 @@
 // (sizes consistent with l_read_name / n_cigar_op / l_seq, reference ids in range, the read name NUL-terminated) -- and
 // walks from there.  The guesses are then checked against the walks: segment s must land exactly on the guess of the next
 // segment that has one.  Segment 0 starts at the true first record, so a consistent set of walks is the true chain; any
-// mismatch (a guess fooled by data that looks like a record) falls back to one serial walk.  Written from the SAM
-// specification section 4.2; __host__ __device__ so that the CPU suite runs the same code (tests/emul/bam_emul.cpp).
+// mismatch (a guess fooled by data that looks like a record) is repaired by walking that segment again from the chain's own
+// offset (pg_bam_host.h).  Written from the SAM specification section 4.2; __host__ __device__ so that the CPU suite runs the same code (tests/emul/bam_emul.cpp).
 #pragma once
 #include <stdint.h>
 
