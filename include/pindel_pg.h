@@ -349,6 +349,28 @@ int pg_bgzf_device_data(pg_ctx *ctx, void **dev, size_t *len);         /* the la
 uint64_t pg_bgzf_launches(pg_ctx *ctx);
 double pg_bgzf_last_kernel_ms(pg_ctx *ctx);
 
+/* ------------------------------------------------------------------------------------------------------------------
+ * Per-box read ordering and duplicate marking: bubblesortReads + markDuplicates
+ * (src/reporter.cpp:932-972), which the D, SI and TD reporters run on every box with at least NumRead2ReportCutOff reads
+ * (src/reporter.cpp:996-998, 1179-1180, 1425-1427), for all boxes of a driver at once.  The exchange sort's order among
+ * equal keys is part of the output, so it is replayed, not replaced: order[box_off[b] + k] = which member of box b stands
+ * at position k afterwards; nonunique[box_off[b] + k] = 1 when that read's UniqueRead is false afterwards.
+ * keys: one per member, in box order; all reads of a call on one chromosome (smaller() compares FragName first; the caller
+ * keeps boxes with mixed FragNames on the host).  name_id: equal <=> equal Name.
+ * ------------------------------------------------------------------------------------------------------------------ */
+typedef struct pg_sort_key {
+   uint32_t bp_left, bp_right, indel_size;   /* BPLeft, BPRight, IndelSize */
+   int32_t left, right;                      /* Left, Right */
+   uint32_t name_id;
+   uint16_t nt_size;                         /* NT_size */
+   int16_t bp;                               /* BP */
+   uint8_t unique;                           /* UniqueRead on entry */
+   uint8_t pad[3];
+} pg_sort_key;
+int pg_box_sort(pg_ctx *ctx, uint32_t n_boxes, const uint32_t *box_off, const pg_sort_key *keys, uint32_t *order, uint8_t *nonunique);
+uint64_t pg_box_sort_launches(pg_ctx *ctx);
+double pg_box_sort_last_kernel_ms(pg_ctx *ctx);
+
 /* Host helper: run-length encode UniquePoints (the inverse of pg_expand_runs) for callers that hold expanded lists.
  * Returns the number of runs (out may be NULL to just count). */
 uint32_t pg_compress_ups(const pg_up *ups, uint32_t n, pg_run *out);

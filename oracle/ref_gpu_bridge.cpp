@@ -46,6 +46,7 @@
 #include <dlfcn.h>
 #include <algorithm>
 #include <cstdlib>
+#include <map>
 #include <mutex>
 #include <string>
 #include <vector>
@@ -623,6 +624,98 @@ void replayDriver(int d, ControlState &cs, unsigned NumBoxes, const SearchWindow
 }
 } // namespace
 
+/* ---------------------------------------------------------------------------------------------------------------------
+ * Row N4: bubblesortReads + markDuplicates (src/reporter.cpp:932-972) are called per box from inside the reporters, which
+ * stay the reference's; both are free functions, bound by symbol.  The drivers above own the boxes before the reporter
+ * runs, so every box the reporter is going to sort is sorted in ONE pg_box_sort call right after the driver's records have
+ * been replayed; the two functions then only hand the stored result over (checked against the box's content), and run the
+ * reference's own code (dlsym(RTLD_NEXT)) for any box that was not prepared.  PG_BRIDGE_HOST_SORT=1 prepares nothing.
+ * ------------------------------------------------------------------------------------------------------------------- */
+namespace {
+struct PreparedBox {
+   std::vector<unsigned> members, sorted, nonunique;   /* content at preparation time; order afterwards; reads that lose UniqueRead */
+};
+std::map<const std::vector<unsigned> *, PreparedBox> g_prepared;
+unsigned long g_boxes_sorted = 0, g_boxes_host = 0;
+
+void prepareBoxes(const std::vector<SPLIT_READ> &Reads, std::vector<unsigned> Vars[], unsigned NumBoxes)
+{
+   g_prepared.clear();
+   if (getenv("PG_BRIDGE_HOST_SORT")) return;
+   std::lock_guard<std::mutex> lock(g_mutex);
+   ensureContext();
+   std::vector<uint32_t> boxOff(1, 0);
+   std::vector<unsigned> boxes;
+   std::vector<pg_sort_key> keys;
+   std::map<std::string, uint32_t> nameId;
+   for (unsigned b = 0; b < NumBoxes; b++) {
+      const std::vector<unsigned> &v = Vars[b];
+      if (v.size() < userSettings->NumRead2ReportCutOff || v.empty()) continue;
+      bool oneChromosome = true;
+      for (size_t k = 1; k < v.size(); k++) if (Reads[v[k]].FragName != Reads[v[0]].FragName) { oneChromosome = false; break; }
+      if (!oneChromosome) continue;      /* smaller() would go through CompareFragName: left to the reference */
+      for (size_t k = 0; k < v.size(); k++) {
+         const SPLIT_READ &r = Reads[v[k]];
+         pg_sort_key key;
+         memset(&key, 0, sizeof key);
+         key.bp_left = r.BPLeft; key.bp_right = r.BPRight; key.indel_size = r.IndelSize; key.left = r.Left; key.right = r.Right;
+         key.nt_size = r.NT_size; key.bp = r.BP; key.unique = r.UniqueRead ? 1 : 0;
+         std::map<std::string, uint32_t>::iterator it = nameId.find(r.Name);
+         if (it == nameId.end()) it = nameId.insert(std::make_pair(r.Name, (uint32_t)nameId.size())).first;
+         key.name_id = it->second;
+         keys.push_back(key);
+      }
+      boxes.push_back(b);
+      boxOff.push_back((uint32_t)keys.size());
+   }
+   if (boxes.empty()) return;
+   std::vector<uint32_t> order(keys.size());
+   std::vector<uint8_t> non(keys.size());
+   if (pg_box_sort(g_ctx, (uint32_t)boxes.size(), &boxOff[0], &keys[0], &order[0], &non[0]) != PG_OK) die("pg_box_sort");
+   for (size_t i = 0; i < boxes.size(); i++) {
+      const std::vector<unsigned> &v = Vars[boxes[i]];
+      PreparedBox &p = g_prepared[&v];
+      p.members = v;
+      for (uint32_t k = boxOff[i]; k < boxOff[i + 1]; k++) {
+         const unsigned read = v[order[k]];
+         p.sorted.push_back(read);
+         if (non[k]) p.nonunique.push_back(read);
+      }
+   }
+}
+} // namespace
+
+void bubblesortReads(const std::vector<SPLIT_READ> &Reads, std::vector<unsigned> &VariantIndices)
+{
+   std::map<const std::vector<unsigned> *, PreparedBox>::iterator it = g_prepared.find(&VariantIndices);
+   if (it != g_prepared.end() && it->second.members == VariantIndices) {
+      VariantIndices.assign(it->second.sorted.begin(), it->second.sorted.end());
+      it->second.members.clear();          /* handed over: markDuplicates recognises the box by its sorted content */
+      g_boxes_sorted++;
+      return;
+   }
+   typedef void (*Fn)(const std::vector<SPLIT_READ> &, std::vector<unsigned> &);
+   static Fn original = (Fn)dlsym(RTLD_NEXT, "_Z15bubblesortReadsRKSt6vectorI10SPLIT_READSaIS0_EERS_IjSaIjEE");
+   if (!original) { std::fprintf(stderr, "pindel_gpu_demo: the reference's bubblesortReads was not found\n"); std::exit(EXIT_FAILURE); }
+   if (it != g_prepared.end()) g_prepared.erase(it);
+   g_boxes_host++;
+   original(Reads, VariantIndices);
+}
+
+void markDuplicates(std::vector<SPLIT_READ> &Reads, const std::vector<unsigned> &VariantIndices)
+{
+   std::map<const std::vector<unsigned> *, PreparedBox>::iterator it = g_prepared.find(&VariantIndices);
+   if (it != g_prepared.end() && it->second.members.empty() && it->second.sorted == VariantIndices) {
+      for (size_t k = 0; k < it->second.nonunique.size(); k++) Reads[it->second.nonunique[k]].UniqueRead = false;
+      g_prepared.erase(it);
+      return;
+   }
+   typedef void (*Fn)(std::vector<SPLIT_READ> &, const std::vector<unsigned> &);
+   static Fn original = (Fn)dlsym(RTLD_NEXT, "_Z14markDuplicatesRSt6vectorI10SPLIT_READSaIS0_EERKS_IjSaIjEE");
+   if (!original) { std::fprintf(stderr, "pindel_gpu_demo: the reference's markDuplicates was not found\n"); std::exit(EXIT_FAILURE); }
+   original(Reads, VariantIndices);
+}
+
 int SearchVariant::Search(BDData &bdData, ControlState &currentState, const unsigned NumBoxes, const SearchWindow &window)
 {
    std::vector<unsigned> *Vars = new std::vector<unsigned>[NumBoxes];
@@ -634,6 +727,7 @@ int SearchVariant::Search(BDData &bdData, ControlState &currentState, const unsi
    Count_Var_Plus += counts[1];
    Count_Var_Minus += counts[2];
    LOG_INFO(*logStream << "Total: " << Count_Var << "\t+" << Count_Var_Plus << "\t-" << Count_Var_Minus << std::endl);
+   prepareBoxes(currentState.Reads_SR, Vars, NumBoxes);
    outputResults(bdData, currentState, Vars, NumBoxes, window);
    delete[] Vars;
    return EXIT_SUCCESS;
@@ -660,6 +754,7 @@ int searchTandemDuplications(ControlState &currentState, unsigned NumBoxes, cons
    int counts[3] = {0, 0, 0};
    replayDriver(PG_SV_TD, currentState, NumBoxes, window, TD, counts);
    std::ofstream TDOutf(userSettings->getTDOutputFilename().c_str(), std::ios::app);
+   prepareBoxes(currentState.Reads_SR, TD, NumBoxes);
    SortAndOutputTandemDuplications(currentState, NumBoxes, window.getChromosome()->getSeq(), currentState.Reads_SR, TD, TDOutf, false);
    delete[] TD;
    return EXIT_SUCCESS;
@@ -672,6 +767,7 @@ int searchTandemDuplicationsNT(ControlState &currentState, unsigned NumBoxes, co
    int counts[3] = {0, 0, 0};
    replayDriver(PG_SV_TD_NT, currentState, NumBoxes, window, TD_NT, counts);
    std::ofstream TDOutf(userSettings->getTDOutputFilename().c_str(), std::ios::app);
+   prepareBoxes(currentState.Reads_SR, TD_NT, NumBoxes);
    SortAndOutputTandemDuplications(currentState, NumBoxes, window.getChromosome()->getSeq(), currentState.Reads_SR, TD_NT, TDOutf, true);
    TDOutf.close();
    delete[] TD_NT;
@@ -812,10 +908,11 @@ bool ReadInBamReads_RP_Discovery(const char *bam_path, const std::string &FragNa
 static void reportAtExit()
 {
    std::fprintf(stderr, "pindel_gpu_demo: %lu GetCloseEnd calls and %lu far-end reads served by libpindel_pg (%llu kernel launches); "
-                "%lu reads classified by the SV drivers on the device, %lu records (%llu launches), %lu of the reads without a second upload; %lu read pairs clustered on the device (%llu launches); %lu BAM bytes inflated and %lu records indexed on the device, %lu discordant pairs found there\n",
+                "%lu reads classified by the SV drivers on the device, %lu records (%llu launches), %lu of the reads without a second upload; %lu read pairs clustered on the device (%llu launches); %lu BAM bytes inflated and %lu records indexed on the device, %lu discordant pairs found there; %lu boxes ordered on the device (%llu launches), %lu by the reference\n",
                 g_close_calls, g_far_reads, g_ctx ? (unsigned long long)pg_kernel_launches(g_ctx) : 0ull, g_sv_reads, g_sv_records,
                 g_ctx ? (unsigned long long)pg_classify_launches(g_ctx) : 0ull, g_sv_resident, g_rp_rows,
-                g_ctx ? (unsigned long long)pg_rp_launches(g_ctx) : 0ull, g_bgzf_bytes, g_bam_records, g_rpd_rows);
+                g_ctx ? (unsigned long long)pg_rp_launches(g_ctx) : 0ull, g_bgzf_bytes, g_bam_records, g_rpd_rows, g_boxes_sorted,
+                g_ctx ? (unsigned long long)pg_box_sort_launches(g_ctx) : 0ull, g_boxes_host);
 }
 
 int main(int argc, char *argv[])

@@ -499,3 +499,32 @@ extern "C" int64_t pgref_rp_discovery(const char *bam_path, int chr, uint32_t st
    *out_stream = buf;
    return (int64_t)out.size();
 }
+
+/* Row N4: the reference's own bubblesortReads + markDuplicates (src/reporter.cpp:932-972) on reads built from plain arrays.
+ * key: 9 int32 per read -- BPLeft, BPRight, IndelSize, NT_size, BP, Left, Right, name id (Name = "n<id>"), UniqueRead.
+ * box_off [n_boxes + 1] into idx (read indices); idx is reordered in place per box, unique_out[r] = UniqueRead afterwards. */
+void bubblesortReads(const std::vector<SPLIT_READ> &Reads, std::vector<unsigned> &VariantIndices);
+void markDuplicates(std::vector<SPLIT_READ> &Reads, const std::vector<unsigned> &VariantIndices);
+
+extern "C" int pgref_box_sort(int n_reads, const int32_t *key, int n_boxes, const uint32_t *box_off, uint32_t *idx, uint8_t *unique_out)
+{
+   std::vector<SPLIT_READ> reads((size_t)n_reads);
+   for (int i = 0; i < n_reads; i++) {
+      const int32_t *k = key + 9 * i;
+      SPLIT_READ &r = reads[i];
+      r.FragName = "c";
+      r.BPLeft = (unsigned)k[0]; r.BPRight = (unsigned)k[1]; r.IndelSize = (unsigned)k[2]; r.NT_size = (unsigned short)k[3]; r.BP = (short)k[4];
+      r.Left = k[5]; r.Right = k[6];
+      r.Name = "n" + std::to_string(k[7]);
+      r.UniqueRead = k[8] != 0;
+   }
+   for (int b = 0; b < n_boxes; b++) {
+      std::vector<unsigned> v(idx + box_off[b], idx + box_off[b + 1]);
+      if (v.empty()) continue;       /* the reporters only call with at least NumRead2ReportCutOff reads; size 0 would underflow */
+      bubblesortReads(reads, v);
+      markDuplicates(reads, v);
+      for (size_t k = 0; k < v.size(); k++) idx[box_off[b] + k] = v[k];
+   }
+   for (int i = 0; i < n_reads; i++) unique_out[i] = reads[i].UniqueRead ? 1 : 0;
+   return 0;
+}

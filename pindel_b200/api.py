@@ -107,6 +107,11 @@ def load_library() -> C.CDLL:
         lib.pg_bam_last_ms.argtypes = [C.c_void_p]
         lib.pg_bam_last_segments.restype = None
         lib.pg_bam_last_segments.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+        lib.pg_box_sort.argtypes = [C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+        lib.pg_box_sort_launches.restype = C.c_uint64
+        lib.pg_box_sort_launches.argtypes = [C.c_void_p]
+        lib.pg_box_sort_last_kernel_ms.restype = C.c_double
+        lib.pg_box_sort_last_kernel_ms.argtypes = [C.c_void_p]
         lib.pg_rp_modify.argtypes = [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p]
         lib.pg_rp_summarize.argtypes = [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p]
         lib.pg_rp_last_classes.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
@@ -404,6 +409,26 @@ class PatternGrowth:
     @property
     def bam_launches(self) -> int:
         return int(self.lib.pg_bam_launches(self.ctx))
+
+    def box_sort(self, member_keys: np.ndarray, box_off: np.ndarray):
+        """bubblesortReads + markDuplicates for all boxes at once.  member_keys: 32-byte keys per member in box order
+        (include/pindel_pg.h pg_sort_key).  -> (order within each box, nonunique per sorted position)"""
+        keys = np.ascontiguousarray(member_keys)
+        assert keys.dtype.itemsize == 32
+        box_off = np.ascontiguousarray(box_off, dtype=np.uint32)
+        order = np.zeros(keys.size, dtype=np.uint32)
+        non = np.zeros(keys.size, dtype=np.uint8)
+        vp = lambda a: a.ctypes.data_as(C.c_void_p) if a.size else None
+        self._check(self.lib.pg_box_sort(self.ctx, box_off.size - 1, vp(box_off), vp(keys), vp(order), vp(non)), "pg_box_sort")
+        return order, non
+
+    @property
+    def box_sort_last_kernel_ms(self) -> float:
+        return float(self.lib.pg_box_sort_last_kernel_ms(self.ctx))
+
+    @property
+    def box_sort_launches(self) -> int:
+        return int(self.lib.pg_box_sort_launches(self.ctx))
 
     def rp_modify(self, rows: np.ndarray) -> np.ndarray:
         """ModifyRP after its sort (src/bddata.cpp:396-430) on the device: rows = pindel_b200.rp.RP_DT in the order the

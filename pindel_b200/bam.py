@@ -59,7 +59,7 @@ def serial_index(stream: bytes) -> np.ndarray:
 
 
 def synthetic_stream(n_records: int, seed: int, refs=(("chr1", 50_000_000), ("chr2", 30_000_000)), adversarial: bool = False,
-                     discordant: float = 0.0) -> bytes:
+                     discordant: float = 0.0, switch_ref: bool = True, unplaced: float = 0.02) -> bytes:
     """A coordinate-sorted BAM stream (inflated).  adversarial: sequence / quality / tag bytes that contain whole fake
     records (valid-looking headers with names), so that a segment boundary falling into them makes the guess lock on."""
     rng = np.random.default_rng(seed)
@@ -69,7 +69,7 @@ def synthetic_stream(n_records: int, seed: int, refs=(("chr1", 50_000_000), ("ch
     fake = record(0, 12345, b"fake_read_inside_aux", 99, 60, [(0, 100)], 100, 0, 12600, 350, rng=rng)
     for i in range(n_records):
         pos += int(rng.integers(0, 60))
-        if i == n_records // 2:
+        if switch_ref and i == n_records // 2:
             tid, pos = 1, 500
         rl = int(rng.choice([76, 100, 150, 151]))
         kind = rng.random()
@@ -94,13 +94,13 @@ def synthetic_stream(n_records: int, seed: int, refs=(("chr1", 50_000_000), ("ch
                 tlen = int(rng.integers(2000, 900_000)) * (1 if rng.random() < 0.5 else -1)
                 mpos = max(0, pos + tlen)
             elif k < 0.7:
-                mtid = 1 - tid
+                mtid = (1 - tid) if len(refs) > 1 else tid
                 mpos = int(rng.integers(0, 1_000_000))
             else:
                 flag = int(rng.choice([65, 129, 113, 177]))         # both mates on one strand
                 mpos = max(0, pos - int(rng.integers(0, 3000)))
             if rng.random() < 0.1:
                 flag |= 8                                           # mate unmapped: not a pair for the discovery
-        out.append(record(tid if cig else -1 if rng.random() < 0.02 else tid, pos, b"read_%d_%d" % (seed, i), flag, int(rng.integers(0, 61)), cig, rl,
+        out.append(record(tid if cig else -1 if rng.random() < unplaced else tid, pos, b"read_%d_%d" % (seed, i), flag, int(rng.integers(0, 61)), cig, rl,
                           mtid, mpos, tlen, aux, rng))
     return b"".join(out)

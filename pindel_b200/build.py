@@ -44,12 +44,13 @@ def build_oracle():
 
 def build_emulator():
     sys.path.insert(0, ROOT)
-    from tests.emul import bam_emul, bgzf_emul, emul, rp_emul, sv_emul
+    from tests.emul import bam_emul, bgzf_emul, boxsort_emul, emul, rp_emul, sv_emul
     emul.build()
     sv_emul.build()
     rp_emul.build()
     bgzf_emul.build()
     bam_emul.build()
+    boxsort_emul.build()
 
 
 def build_all(force=False):

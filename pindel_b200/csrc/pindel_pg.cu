@@ -24,6 +24,7 @@
 #include "pg_bgzf_host.h"
 #include "pg_bam.cuh"
 #include "pg_bam_host.h"
+#include "pg_boxsort.cuh"
 #include "pg_params.h"
 #include "../../include/pindel_pg.h"
 #include "pg_host_helpers.h"
@@ -380,6 +381,10 @@ struct pg_ctx {
    size_t bz_out_len = 0;
    uint64_t bz_launches = 0;
    float bz_last_ms = 0.f;
+   // per-box read ordering (pg_box_sort)
+   DevBuf bx_off, bx_keys, bx_order, bx_non;
+   uint64_t bx_launches = 0;
+   float bx_last_ms = 0.f;
    // read-pair clustering (pg_rp_modify / pg_rp_summarize)
    DevBuf rp_in, rp_out, rp_rows, rp_off, rp_scratch, rp_merged, rp_nid, rp_counters, rp_keys;
    uint64_t rp_launches = 0;
@@ -541,7 +546,8 @@ void pg_destroy(pg_ctx *ctx)
                        &ctx->sv_close_runs, &ctx->rp_in, &ctx->rp_out, &ctx->rp_rows, &ctx->rp_off, &ctx->rp_scratch, &ctx->rp_merged,
                        &ctx->rp_nid, &ctx->rp_counters, &ctx->rp_keys, &ctx->bz_file, &ctx->bz_blocks, &ctx->bz_out, &ctx->bz_status,
                        &ctx->bm_info, &ctx->bm_starts, &ctx->bm_counts, &ctx->bm_landing, &ctx->bm_base, &ctx->bm_recs,
-                       &ctx->bd_cls, &ctx->bd_off, &ctx->bd_sums, &ctx->bd_rows, &ctx->bd_src, &ctx->bd_counters};
+                       &ctx->bd_cls, &ctx->bd_off, &ctx->bd_sums, &ctx->bd_rows, &ctx->bd_src, &ctx->bd_counters,
+                       &ctx->bx_off, &ctx->bx_keys, &ctx->bx_order, &ctx->bx_non};
    for (DevBuf *b : svbufs) if (b->p) cudaFree(b->p);
    pipe_destroy(ctx->pipe);
    if (ctx->chroms_d) cudaFree(ctx->chroms_d);
@@ -1470,6 +1476,44 @@ int pg_bam_rp_discovery(pg_ctx *ctx, const pg_rp_query *q, pg_rp *rows, uint32_t
    CU(cudaEventElapsedTime(&ctx->bm_last_ms, ctx->sv_ev0, ctx->sv_ev1));
    return PG_OK;
 }
+
+// ---- per-box read ordering and duplicate marking (row N4) -----------------------------------------------------------
+static_assert(sizeof(pg_sort_key) == sizeof(PgSortKey) && sizeof(pg_sort_key) == 32, "sort key layout");
+
+int pg_box_sort(pg_ctx *ctx, uint32_t n_boxes, const uint32_t *box_off, const pg_sort_key *keys, uint32_t *order, uint8_t *nonunique)
+{
+   if (!ctx || (n_boxes && (!box_off || !order || !nonunique))) return fail(ctx, PG_ERR_ARG, "pg_box_sort: null argument");
+   if (n_boxes == 0) return PG_OK;
+   for (uint32_t b = 0; b < n_boxes; b++)
+      if (box_off[b + 1] < box_off[b]) return fail(ctx, PG_ERR_ARG, "pg_box_sort: box offsets must be non-decreasing");
+   const size_t total = box_off[n_boxes];
+   if (total && !keys) return fail(ctx, PG_ERR_ARG, "pg_box_sort: null keys");
+   if (total == 0) return PG_OK;
+   CU(cudaSetDevice(ctx->device));
+   cudaStream_t st = ctx->stream;
+   int rc;
+   if ((rc = ensure(ctx, ctx->bx_off, sizeof(uint32_t) * ((size_t)n_boxes + 1))) != PG_OK) return rc;
+   if ((rc = ensure(ctx, ctx->bx_keys, sizeof(PgSortKey) * total)) != PG_OK) return rc;
+   if ((rc = ensure(ctx, ctx->bx_order, sizeof(uint32_t) * total)) != PG_OK) return rc;
+   if ((rc = ensure(ctx, ctx->bx_non, total)) != PG_OK) return rc;
+   CU(cudaMemcpyAsync(ctx->bx_off.p, box_off, sizeof(uint32_t) * ((size_t)n_boxes + 1), cudaMemcpyHostToDevice, st));
+   CU(cudaMemcpyAsync(ctx->bx_keys.p, keys, sizeof(PgSortKey) * total, cudaMemcpyHostToDevice, st));
+   if (!ctx->sv_ev0) { CU(cudaEventCreate(&ctx->sv_ev0)); CU(cudaEventCreate(&ctx->sv_ev1)); }
+   CU(cudaEventRecord(ctx->sv_ev0, st));
+   pg_box_sort_kernel<<<(n_boxes + 63) / 64, 64, 0, st>>>(n_boxes, (const uint32_t *)ctx->bx_off.p, (const PgSortKey *)ctx->bx_keys.p,
+                                                         (uint32_t *)ctx->bx_order.p, (uint8_t *)ctx->bx_non.p);
+   CU(cudaGetLastError());
+   CU(cudaEventRecord(ctx->sv_ev1, st));
+   ctx->bx_launches++;
+   CU(cudaMemcpyAsync(order, ctx->bx_order.p, sizeof(uint32_t) * total, cudaMemcpyDeviceToHost, st));
+   CU(cudaMemcpyAsync(nonunique, ctx->bx_non.p, total, cudaMemcpyDeviceToHost, st));
+   CU(cudaStreamSynchronize(st));
+   CU(cudaEventElapsedTime(&ctx->bx_last_ms, ctx->sv_ev0, ctx->sv_ev1));
+   return PG_OK;
+}
+
+uint64_t pg_box_sort_launches(pg_ctx *ctx) { return ctx ? ctx->bx_launches : 0; }
+double pg_box_sort_last_kernel_ms(pg_ctx *ctx) { return ctx ? (double)ctx->bx_last_ms : 0.0; }
 
 // ---- read-pair clustering (row N2) --------------------------------------------------------------------------------
 static_assert(sizeof(pg_rp) == sizeof(PgRp) && sizeof(pg_rp) == 16, "rp layout");

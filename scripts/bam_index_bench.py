@@ -26,7 +26,7 @@ def main():
     from pindel_b200 import api, bam, bgzf
     from tests.emul import bam_emul
     # one chunk of distinct records, tiled (the index does not care that positions repeat); chunk = whole BGZF blocks
-    one = bam.synthetic_stream(60_000, 1, discordant=0.05)
+    one = bam.synthetic_stream(60_000, 1, refs=(("chr1", 2_000_000_000),), discordant=0.05, switch_ref=False, unplaced=0.0)
     first, _ = bam.first_record_offset(one)
     hdr, chunk = one[:first], one[first:]
     tiles = max(1, (a.mb << 20) // len(chunk))
@@ -52,10 +52,10 @@ def main():
            "index_records_per_s_e2e": recs.size / float(np.median(t_idx)), "index_GBps_of_stream": stream_len / float(np.median(t_idx)) / 1e9,
            "d2h_bytes": int(out.nbytes)}
     # discordant-pair discovery over the whole first reference (the tiles repeat positions, so every tile contributes)
-    rows, src, irows, isrc, scanned = pg.bam_rp_discovery(0, 0, 50_000_000, 500)
+    rows, src, irows, isrc, scanned = pg.bam_rp_discovery(0, 0, 2_000_000_000, 500)
     t_d, k_d = [], []
     for _ in range(a.reps):
-        t0 = time.perf_counter(); pg.bam_rp_discovery(0, 0, 50_000_000, 500); t_d.append(time.perf_counter() - t0)
+        t0 = time.perf_counter(); pg.bam_rp_discovery(0, 0, 2_000_000_000, 500); t_d.append(time.perf_counter() - t0)
         k_d.append(pg.bam_last_ms)
     res["discovery"] = {"records_scanned": int(scanned), "rows": int(rows.size), "inter_rows": int(irows.size), "e2e_ms": 1e3 * float(np.median(t_d)),
                         "device_ms": float(np.median(k_d)), "records_per_s_e2e": scanned / float(np.median(t_d)),

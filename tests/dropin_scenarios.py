@@ -21,6 +21,13 @@ def _run(demo, args, env):
     m = re.search(r"; (\d+) reads classified .* (\d+) of the reads without a second upload", p.stderr)
     assert m, p.stderr[-500:]
     assert int(m.group(2)) == (0 if env.get("PG_BRIDGE_NO_RESIDENT") else int(m.group(1))), m.group(0)
+    # row N4: the boxes the D / SI / TD reporters sort were ordered by pg_box_sort, one call per driver
+    m = re.search(r"(\d+) boxes ordered on the device \((\d+) launches\), (\d+) by the reference", p.stderr)
+    assert m, p.stderr[-500:]
+    if env.get("PG_BRIDGE_HOST_SORT"):
+        assert int(m.group(1)) == 0 and int(m.group(3)) > 0, m.group(0)
+    else:
+        assert int(m.group(1)) > 0 and int(m.group(3)) == 0 and int(m.group(2)) <= 8, m.group(0)
     return p
 
 

@@ -17,6 +17,7 @@
 #include "rp_emul.cpp"
 #include "bgzf_emul.cpp"
 #include "bam_emul.cpp"
+#include "boxsort_emul.cpp"
 #include "../../pindel_b200/csrc/pg_host_helpers.h"
 
 struct pg_ctx {
@@ -27,7 +28,7 @@ struct pg_ctx {
    uint32_t table[PG_TABLE];
    std::vector<pg_read_out> out;
    std::vector<pg_run> runs;
-   uint64_t launches = 0, sv_launches = 0, rp_launches = 0;
+   uint64_t launches = 0, sv_launches = 0, rp_launches = 0, bx_launches = 0;
    // copy of the last far-end-only batch ("resident")
    int res_n = -1;
    std::vector<uint8_t> res_seq, res_md;
@@ -214,6 +215,13 @@ int pg_rp_summarize(pg_ctx *ctx, int32_t n, const pg_rp *in, pg_rp_cluster *inou
    return PG_OK;
 }
 uint64_t pg_rp_launches(pg_ctx *ctx) { return ctx ? ctx->rp_launches : 0; }
+int pg_box_sort(pg_ctx *ctx, uint32_t n_boxes, const uint32_t *box_off, const pg_sort_key *keys, uint32_t *order, uint8_t *nonunique)
+{
+   boxemu_sort(n_boxes, box_off, (const PgSortKey *)keys, order, nonunique);
+   ctx->bx_launches++;
+   return PG_OK;
+}
+uint64_t pg_box_sort_launches(pg_ctx *ctx) { return ctx ? ctx->bx_launches : 0; }
 int64_t pg_bgzf_inflated_size(const uint8_t *file, size_t file_len) { return bgzfemu_size(file, file_len); }
 int pg_bgzf_inflate(pg_ctx *ctx, const uint8_t *file, size_t file_len, uint8_t *out, size_t out_cap, size_t *out_len, int32_t check_crc)
 {

@@ -32,5 +32,5 @@ def test_bam_input_scenario_with_zlib_inflate(tmp_path):
 
 def test_text_input_scenario_with_the_host_array_classification(tmp_path):
     """pg_classify (everything uploaded again) instead of pg_classify_resident: the path a host takes when the far-end
-    batch is no longer on the device."""
-    D.colo_slice(DEMO, tmp_path, dict(os.environ, PG_BRIDGE_NO_RESIDENT="1"), unbatched_too=False)
+    batch is no longer on the device; and the reference's own bubblesortReads / markDuplicates instead of pg_box_sort."""
+    D.colo_slice(DEMO, tmp_path, dict(os.environ, PG_BRIDGE_NO_RESIDENT="1", PG_BRIDGE_HOST_SORT="1"), unbatched_too=False)
