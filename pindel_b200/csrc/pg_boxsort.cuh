@@ -6,8 +6,12 @@
 // order it leaves among reads with equal keys (every split read of one event has the same BPLeft/BPRight/IndelSize/
 // NT_size, often the same BP) is neither the input order nor its reverse, and it decides which read markDuplicates keeps
 // and the order of the reads under every event in the output files.  So the device does not "sort": it replays the
-// exchange sort and the duplicate scan literally, one thread per box -- the boxes are the parallel axis (tens of
-// thousands per window), the reads of a box a short serial loop.
+// exchange sort and the duplicate scan, one warp per box (the boxes are the parallel axis: tens of thousands per window).
+// One pass of the exchange sort (fixed First) carries a value "in hand" along the box: position j takes it over and gives
+// its own value to the hand exactly when key[j] <= min(key of the hand at the start, key[First+1 .. j-1]) -- the weak
+// prefix minima -- so a pass is a rotation along the chain of those positions, found 32 positions at a time with a
+// warp prefix-minimum over 128-bit packed keys.  markDuplicates is a plain lane-parallel scan per First.
+// pgs_sort_and_mark is the literal form (the first device version ran it, one thread per box: a 481-read box cost 34 ms).
 #pragma once
 #include <stdint.h>
 
@@ -59,8 +63,94 @@ PGS_HD void pgs_sort_and_mark(const PgSortKey *keys, uint32_t n, uint32_t *order
    }
 }
 
+// the five fields smaller() compares, as one 128-bit unsigned number (BP is a short: biased)
+struct PgKey128 {
+   uint64_t hi, lo;
+};
+PGS_HD PgKey128 pgs_pack(const PgSortKey &k)
+{
+   PgKey128 p;
+   p.hi = (uint64_t)k.bp_left << 32 | k.bp_right;
+   p.lo = (uint64_t)k.indel_size << 32 | (uint64_t)k.nt_size << 16 | (uint64_t)(uint16_t)((int32_t)k.bp + 32768);
+   return p;
+}
+PGS_HD bool pgs_le(const PgKey128 &a, const PgKey128 &b) { return a.hi < b.hi || (a.hi == b.hi && a.lo <= b.lo); }
+PGS_HD bool pgs_lt(const PgKey128 &a, const PgKey128 &b) { return a.hi < b.hi || (a.hi == b.hi && a.lo < b.lo); }
+
 #ifdef __CUDACC__
-// box b: keys[box_off[b] .. box_off[b+1]); order / nonunique are the box's slices of the output arrays
+__device__ __forceinline__ PgKey128 pgs_shfl(const PgKey128 &k, int src)
+{
+   PgKey128 r;
+   r.hi = __shfl_sync(0xFFFFFFFFu, k.hi, src);
+   r.lo = __shfl_sync(0xFFFFFFFFu, k.lo, src);
+   return r;
+}
+__device__ __forceinline__ PgKey128 pgs_shfl_up(const PgKey128 &k, int d)
+{
+   PgKey128 r;
+   r.hi = __shfl_up_sync(0xFFFFFFFFu, k.hi, d);
+   r.lo = __shfl_up_sync(0xFFFFFFFFu, k.lo, d);
+   return r;
+}
+
+// one warp per box
+__global__ void __launch_bounds__(256) pg_box_sort_warp_kernel(uint32_t n_boxes, const uint32_t *__restrict__ box_off, const PgSortKey *__restrict__ keys,
+                                                               uint32_t *__restrict__ order, uint8_t *__restrict__ nonunique)
+{
+   const uint32_t b = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+   const int lane = threadIdx.x & 31;
+   if (b >= n_boxes) return;
+   const uint32_t o = box_off[b], n = box_off[b + 1] - o;
+   const PgSortKey *bk = keys + o;
+   uint32_t *ord = order + o;
+   uint8_t *non = nonunique + o;
+   for (uint32_t k = lane; k < n; k += 32) ord[k] = k;
+   __syncwarp();
+   for (uint32_t first = 0; first + 1 < n; first++) {
+      uint32_t hand = ord[first];
+      PgKey128 hand_key = pgs_pack(bk[hand]);
+      for (uint32_t c0 = first + 1; c0 < n; c0 += 32) {
+         const uint32_t j = c0 + (uint32_t)lane;
+         const bool valid = j < n;
+         const uint32_t slot = valid ? ord[j] : 0u;
+         PgKey128 k;
+         k.hi = k.lo = ~0ull;
+         if (valid) k = pgs_pack(bk[slot]);
+         PgKey128 pm = k;                                   // inclusive prefix minimum over the lanes
+         for (int d = 1; d < 32; d <<= 1) {
+            const PgKey128 t = pgs_shfl_up(pm, d);
+            if (lane >= d && pgs_lt(t, pm)) pm = t;
+         }
+         PgKey128 ex = pgs_shfl_up(pm, 1);                  // minimum of the hand and the lanes before this one
+         if (lane == 0 || pgs_lt(hand_key, ex)) ex = hand_key;
+         const bool rec = valid && pgs_le(k, ex);
+         const uint32_t R = __ballot_sync(0xFFFFFFFFu, rec);
+         if (R) {
+            const uint32_t below = R & ((1u << lane) - 1u);
+            const uint32_t from_lane = __shfl_sync(0xFFFFFFFFu, slot, below ? 31 - __clz(below) : 0);
+            if (rec) ord[j] = below ? from_lane : hand;     // takes what was in hand: the previous taker's value
+            const int last = 31 - __clz(R);
+            hand = __shfl_sync(0xFFFFFFFFu, slot, last);
+            hand_key = pgs_shfl(k, last);
+         }
+      }
+      if (lane == 0) ord[first] = hand;
+      __syncwarp();
+   }
+   for (uint32_t k = lane; k < n; k += 32) non[k] = bk[ord[k]].unique ? 0 : 1;
+   __syncwarp();
+   for (uint32_t first = 0; first + 1 < n; first++) {
+      if (non[first]) continue;
+      const PgSortKey a = bk[ord[first]];
+      for (uint32_t j = first + 1 + (uint32_t)lane; j < n; j += 32) {
+         const PgSortKey &c = bk[ord[j]];
+         if (a.left == c.left && a.right == c.right && a.name_id == c.name_id) non[j] = 1;
+      }
+      __syncwarp();
+   }
+}
+
+// box b: keys[box_off[b] .. box_off[b+1]); order / nonunique are the box's slices of the output arrays (literal form)
 __global__ void pg_box_sort_kernel(uint32_t n_boxes, const uint32_t *__restrict__ box_off, const PgSortKey *__restrict__ keys,
                                    uint32_t *__restrict__ order, uint8_t *__restrict__ nonunique)
 {

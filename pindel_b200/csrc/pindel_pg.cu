@@ -1500,8 +1500,8 @@ int pg_box_sort(pg_ctx *ctx, uint32_t n_boxes, const uint32_t *box_off, const pg
    CU(cudaMemcpyAsync(ctx->bx_keys.p, keys, sizeof(PgSortKey) * total, cudaMemcpyHostToDevice, st));
    if (!ctx->sv_ev0) { CU(cudaEventCreate(&ctx->sv_ev0)); CU(cudaEventCreate(&ctx->sv_ev1)); }
    CU(cudaEventRecord(ctx->sv_ev0, st));
-   pg_box_sort_kernel<<<(n_boxes + 63) / 64, 64, 0, st>>>(n_boxes, (const uint32_t *)ctx->bx_off.p, (const PgSortKey *)ctx->bx_keys.p,
-                                                         (uint32_t *)ctx->bx_order.p, (uint8_t *)ctx->bx_non.p);
+   pg_box_sort_warp_kernel<<<(n_boxes + 7) / 8, 256, 0, st>>>(n_boxes, (const uint32_t *)ctx->bx_off.p, (const PgSortKey *)ctx->bx_keys.p,
+                                                             (uint32_t *)ctx->bx_order.p, (uint8_t *)ctx->bx_non.p);
    CU(cudaGetLastError());
    CU(cudaEventRecord(ctx->sv_ev1, st));
    ctx->bx_launches++;

@@ -23,12 +23,13 @@ def build(force=False):
     return lib
 
 
-def sort_boxes(lib, member_keys: np.ndarray, box_off: np.ndarray):
+def sort_boxes(lib, member_keys: np.ndarray, box_off: np.ndarray, warp_formulation: bool = False):
     """member_keys: KEY_DT per member (already gathered in box order).  -> (order within each box, nonunique per sorted position)"""
     keys = np.ascontiguousarray(member_keys, dtype=B.KEY_DT)
     box_off = np.ascontiguousarray(box_off, dtype=np.uint32)
     order = np.zeros(keys.size, dtype=np.uint32)
     non = np.zeros(keys.size, dtype=np.uint8)
     vp = lambda a: a.ctypes.data_as(C.c_void_p)
-    lib.boxemu_sort(C.c_uint32(box_off.size - 1), vp(box_off), vp(keys), vp(order), vp(non))
+    fn = lib.boxemu_sort_warp_formulation if warp_formulation else lib.boxemu_sort
+    fn(C.c_uint32(box_off.size - 1), vp(box_off), vp(keys), vp(order), vp(non))
     return order, non

@@ -25,9 +25,10 @@ def test_oracle_and_device_program_match_reference_dumps(lib, name):
     reads, box_off, idx = B.make_boxes(**G.CASES[name])
     o_idx, o_unique = B.sort_boxes(reads, box_off, idx)
     assert np.array_equal(o_idx, z["sorted_idx"]) and np.array_equal(o_unique, z["unique"]), "oracle"
-    order, non = boxsort_emul.sort_boxes(lib, reads[idx], box_off)
-    p_idx, p_unique = H.apply(reads, box_off, idx, order, non)
-    assert np.array_equal(p_idx, z["sorted_idx"]) and np.array_equal(p_unique, z["unique"]), "device program"
+    for warp_formulation in (False, True):      # the literal replay, and the kernel's chunked weak-prefix-minimum form
+        order, non = boxsort_emul.sort_boxes(lib, reads[idx], box_off, warp_formulation)
+        p_idx, p_unique = H.apply(reads, box_off, idx, order, non)
+        assert np.array_equal(p_idx, z["sorted_idx"]) and np.array_equal(p_unique, z["unique"]), ("device program", warp_formulation)
     # the exchange sort is not a stable sort: a stable sort of the same keys gives another order
     stable = idx.copy()
     for b in range(len(box_off) - 1):
