@@ -65,11 +65,14 @@ PGB_HD bool pgb_plausible_chain(const uint8_t *d, uint64_t n, uint64_t c, int32_
    return true;
 }
 
-// reference bases consumed by the CIGAR: M, D, N, =, X (bam_endpos); rec points at refID
-PGB_HD int32_t pgb_ref_span(const uint8_t *rec)
+// reference bases consumed by the CIGAR: M, D, N, =, X (bam_endpos); rec points at refID, rec_len = block_size.
+// A CIGAR that would run past the record (corrupt input) is cut at the record's end.
+PGB_HD int32_t pgb_ref_span(const uint8_t *rec, uint64_t rec_len)
 {
-   const uint32_t l_name = rec[8], n_cigar = pgb_le16(rec + 12), flag = pgb_le16(rec + 14);
+   const uint32_t l_name = rec[8], flag = pgb_le16(rec + 14);
+   uint32_t n_cigar = pgb_le16(rec + 12);
    const uint8_t *cig = rec + 32 + l_name;
+   if (32ull + l_name + 4ull * n_cigar > rec_len) n_cigar = 32ull + l_name >= rec_len ? 0u : (uint32_t)((rec_len - 32ull - l_name) / 4ull);
    int32_t span = 0;
    if (!(flag & 4u)) {
       for (uint32_t k = 0; k < n_cigar; k++) {
@@ -86,7 +89,7 @@ PGB_HD void pgb_fill(const uint8_t *d, uint64_t c, PgBamRec &r)
    r.off = c;
    r.tid = (int32_t)pgb_le32(rec);
    r.pos = (int32_t)pgb_le32(rec + 4);
-   r.end = r.pos + pgb_ref_span(rec);
+   r.end = r.pos + pgb_ref_span(rec, (uint64_t)pgb_le32(d + c));
    r.flag = (uint16_t)pgb_le16(rec + 14);
    r.mapq = rec[9];
    r.pad = 0;

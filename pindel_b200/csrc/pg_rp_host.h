@@ -4,6 +4,7 @@
 #pragma once
 #include <stdint.h>
 #include <algorithm>
+#include <utility>
 #include <vector>
 #include "pg_rp.cuh"
 
@@ -30,17 +31,20 @@ static inline void pg_rp_classes(int n, const PgRp *in, uint32_t warp_max, std::
       x = find(x); y = find(y);
       if (x != y) parent[x > y ? x : y] = x > y ? y : x;
    };
+   std::vector<std::pair<uint64_t, uint32_t>> keyed(live.size());
    for (int side = 0; side < 2; side++) {
-      // sweep over (strands, interval start): a row joins the running component while its start lies before the component's end
-      std::sort(live.begin(), live.end(), [&](uint32_t x, uint32_t y) {
-         const uint32_t kx = (uint32_t)in[x].da << 8 | in[x].db, ky = (uint32_t)in[y].da << 8 | in[y].db;
-         if (kx != ky) return kx < ky;
-         const uint32_t sx = side ? iv[x].b : iv[x].a, sy = side ? iv[y].b : iv[y].a;
-         return sx != sy ? sx < sy : x < y;
-      });
+      // sweep over (strands, interval start): a row joins the running component while its start lies before the component's
+      // end.  The sort runs on packed (strands << 32 | start, row) pairs: plain integer comparisons.
+      for (size_t k = 0; k < live.size(); k++) {
+         const uint32_t x = live[k];
+         keyed[k].first = (uint64_t)((uint32_t)in[x].da << 8 | in[x].db) << 32 | (side ? iv[x].b : iv[x].a);
+         keyed[k].second = x;
+      }
+      std::sort(keyed.begin(), keyed.end());
       uint32_t run_key = 0xFFFFFFFFu, run_end = 0, run_row = 0;
-      for (uint32_t x : live) {
-         const uint32_t k = (uint32_t)in[x].da << 8 | in[x].db, s0 = side ? iv[x].b : iv[x].a, s1 = side ? iv[x].b1 : iv[x].a1;
+      for (size_t i = 0; i < keyed.size(); i++) {
+         const uint32_t x = keyed[i].second;
+         const uint32_t k = (uint32_t)(keyed[i].first >> 32), s0 = (uint32_t)keyed[i].first, s1 = side ? iv[x].b1 : iv[x].a1;
          if (k == run_key && s0 < run_end) {
             unite(x, run_row);
             if (s1 > run_end) run_end = s1;
@@ -65,8 +69,7 @@ static inline void pg_rp_classes(int n, const PgRp *in, uint32_t warp_max, std::
       rows.resize(rows.size() + count[i]);
       off.push_back((uint32_t)rows.size());
    }
-   std::sort(live.begin(), live.end());
-   for (uint32_t x : live) {
+   for (uint32_t x : live) {      // live is ascending: it was filled in row order and never reordered
       const uint32_t r = find(x);
       if (count[r] < 2) continue;
       (count[r] > warp_max ? rows_big : rows_small)[slot[r]++] = x;
