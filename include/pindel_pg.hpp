@@ -9,11 +9,20 @@
 //     void CleanUniquePoints(SortedUniquePoints&)                                             src/pindel.cpp:2904-2941
 //
 // finds the same things here, batched: Searcher::GetCloseEnd(reads) and Searcher::SearchFarEnds(reads, clusters) take the
-// whole vector.  No search logic lives in this header; without a CUDA device the Searcher constructor throws.
+// whole vector.  The stages either side of the search follow the same rule (reference name, batched argument):
+//
+//     void ModifyRP(std::vector<RP_READ>&) / void Summarize(std::vector<RP_READ>&)            src/bddata.cpp:385,470
+//     void bubblesortReads(Reads, VariantIndices) / void markDuplicates(Reads, VariantIndices) src/reporter.cpp:932,946
+//     htslib's BGZF inflate + record walk behind sam_itr_next                                  src/reader.cpp:1258-1346
+//
+// -> Searcher::ModifyRP / Summarize (whole vector), Searcher::SortBoxes (all boxes of a driver), Searcher::InflateBam /
+// IndexBam.  No search logic lives in this header; without a CUDA device the Searcher constructor throws.
 #ifndef PINDEL_PG_HPP
 #define PINDEL_PG_HPP
+#include <algorithm>
 #include <cctype>
 #include <cstring>
+#include <map>
 #include <stdexcept>
 #include <string>
 #include <vector>
@@ -84,6 +93,12 @@ struct SPLIT_READ {                      // the fields of src/pindel.h:265-383 t
    bool Used = false;
    bool MapperSplit = false;
    SortedUniquePoints UP_Close, UP_Far;
+   // what the SV drivers assign and the reporters' per-box ordering reads (src/pindel.h:349-360)
+   short BP = 0;
+   int Left = 0, Right = 0;
+   unsigned int BPLeft = 0, BPRight = 0, IndelSize = 0;
+   unsigned short NT_size = 0;
+   bool UniqueRead = true;
 
    void setUnmatchedSeq(const std::string &s)                    // src/pindel.cpp:142-169: trailing non-alphanumerics are stripped
    {
@@ -98,6 +113,26 @@ struct SPLIT_READ {                      // the fields of src/pindel.h:265-383 t
 private:
    std::string UnmatchedSeq;
 };
+
+struct RP_READ {                         // src/pindel.h:215-262: the fields the read-pair clustering reads or writes
+   RP_READ() : DA('k'), DB('k'), PosA(0), PosB(0), OriginalPosA(0), OriginalPosB(0), PosA1(0), PosB1(0), InsertSize(0), ReadLength(0),
+               NumberOfIdentical(0), Report(false), Visited(false) {}
+   std::string ReadName;
+   char DA, DB;
+   unsigned PosA, PosB, OriginalPosA, OriginalPosB, PosA1, PosB1;
+   std::vector<std::string> Tags;
+   unsigned InsertSize;
+   short ReadLength;
+   unsigned NumberOfIdentical;
+   bool Report, Visited;
+};
+
+inline bool Compare2RP(const RP_READ &first, const RP_READ &second)   // src/bddata.cpp:239-253
+{
+   if (first.OriginalPosA > second.OriginalPosA) return true;
+   if (first.OriginalPosA == second.OriginalPosA) return first.OriginalPosB > second.OriginalPosB;
+   return false;
+}
 
 struct SearchWindow { int chromosome_id; unsigned int start, end; };   // src/pindel.h:665-716, [start, end) padded coordinates
 typedef std::vector<SearchWindow> SearchWindowCluster;
@@ -162,7 +197,114 @@ public:
 
    uint64_t kernelLaunches() const { return pg_kernel_launches(ctx_); }
 
+   // ModifyRP (src/bddata.cpp:385-431): sort by original position (descending), InitializeA1B1, the interval-merging loop in
+   // serial row order, + ReadLength, Visited for pairs closer than 500 -- all rows of one chromosome pair.
+   void ModifyRP(std::vector<RP_READ> &Reads_RP)
+   {
+      if (Reads_RP.empty()) return;
+      std::sort(Reads_RP.begin(), Reads_RP.end(), Compare2RP);
+      std::vector<pg_rp> in;
+      marshal(Reads_RP, in);
+      std::vector<pg_rp_cluster> out(in.size());
+      check(pg_rp_modify(ctx_, (int32_t)in.size(), in.data(), out.data()), "pg_rp_modify");
+      for (size_t i = 0; i < Reads_RP.size(); i++) {
+         RP_READ &r = Reads_RP[i];
+         r.PosA = out[i].pos_a; r.PosA1 = out[i].pos_a1; r.PosB = out[i].pos_b; r.PosB1 = out[i].pos_b1;
+         if (out[i].visited) r.Visited = true;
+      }
+   }
+
+   // Summarize (src/bddata.cpp:470-575): identical events merged into their first row (NumberOfIdentical, Tags), Report for >= 5
+   void Summarize(std::vector<RP_READ> &Reads_RP)
+   {
+      if (Reads_RP.empty()) return;
+      std::vector<pg_rp> in;
+      marshal(Reads_RP, in);
+      std::vector<pg_rp_cluster> st(in.size());
+      for (size_t i = 0; i < Reads_RP.size(); i++) {
+         const RP_READ &r = Reads_RP[i];
+         st[i].pos_a = r.PosA; st[i].pos_a1 = r.PosA1; st[i].pos_b = r.PosB; st[i].pos_b1 = r.PosB1; st[i].n_identical = r.NumberOfIdentical;
+         st[i].merged_into = (uint32_t)i; st[i].visited = r.Visited; st[i].report = r.Report; st[i].pad = 0;
+      }
+      check(pg_rp_summarize(ctx_, (int32_t)in.size(), in.data(), st.data()), "pg_rp_summarize");
+      for (size_t i = 0; i < Reads_RP.size(); i++) {
+         RP_READ &r = Reads_RP[i];
+         r.NumberOfIdentical = st[i].n_identical; r.Visited = st[i].visited != 0; r.Report = st[i].report != 0;
+         if (st[i].merged_into != (uint32_t)i && !r.Tags.empty()) {
+            RP_READ &first = Reads_RP[st[i].merged_into];
+            first.Tags.insert(first.Tags.end(), r.Tags.begin(), r.Tags.end());
+            r.Tags.clear();
+         }
+      }
+   }
+
+   // bubblesortReads + markDuplicates (src/reporter.cpp:932-972) for every box at once: boxes[b] is reordered and
+   // Reads[..].UniqueRead cleared exactly as the two functions would do box by box.  Reads of one chromosome.
+   void SortBoxes(std::vector<SPLIT_READ> &Reads, std::vector<std::vector<unsigned> > &boxes)
+   {
+      std::vector<uint32_t> off(1, 0);
+      std::vector<pg_sort_key> keys;
+      std::map<std::string, uint32_t> ids;
+      for (size_t b = 0; b < boxes.size(); b++) {
+         for (size_t k = 0; k < boxes[b].size(); k++) {
+            const SPLIT_READ &r = Reads[boxes[b][k]];
+            pg_sort_key key;
+            std::memset(&key, 0, sizeof key);
+            key.bp_left = r.BPLeft; key.bp_right = r.BPRight; key.indel_size = r.IndelSize; key.left = r.Left; key.right = r.Right;
+            key.nt_size = r.NT_size; key.bp = r.BP; key.unique = r.UniqueRead ? 1 : 0;
+            key.name_id = ids.insert(std::make_pair(r.Name, (uint32_t)ids.size())).first->second;
+            keys.push_back(key);
+         }
+         off.push_back((uint32_t)keys.size());
+      }
+      if (keys.empty()) return;
+      std::vector<uint32_t> order(keys.size());
+      std::vector<uint8_t> non(keys.size());
+      check(pg_box_sort(ctx_, (uint32_t)boxes.size(), off.data(), keys.data(), order.data(), non.data()), "pg_box_sort");
+      for (size_t b = 0; b < boxes.size(); b++) {
+         const std::vector<unsigned> before(boxes[b]);
+         for (uint32_t k = off[b]; k < off[b + 1]; k++) {
+            boxes[b][k - off[b]] = before[order[k]];
+            if (non[k]) Reads[before[order[k]]].UniqueRead = false;
+         }
+      }
+   }
+
+   // BGZF inflate of a whole BAM file on the device; the stream stays there for IndexBam (and comes back when wanted)
+   size_t InflateBam(const std::string &file_bytes, std::string *inflated = NULL, bool check_crc = true)
+   {
+      size_t n = 0;
+      if (inflated) {
+         const int64_t total = pg_bgzf_inflated_size((const uint8_t *)file_bytes.data(), file_bytes.size());
+         if (total < 0) throw std::runtime_error("pg_bgzf_inflated_size: not a BGZF file");
+         inflated->resize((size_t)total);
+      }
+      check(pg_bgzf_inflate(ctx_, (const uint8_t *)file_bytes.data(), file_bytes.size(), inflated && !inflated->empty() ? (uint8_t *)&(*inflated)[0] : NULL,
+                            inflated ? inflated->size() : 0, &n, check_crc ? 1 : 0), "pg_bgzf_inflate");
+      return n;
+   }
+
+   // the record table (offset, refID, pos, end, flag, mapq) of the inflated stream: the walk + bam_endpos of an iterator
+   std::vector<pg_bam_rec> IndexBam(uint64_t *first_record = NULL, int32_t *n_ref = NULL)
+   {
+      uint64_t n = 0;
+      int rc = pg_bam_index(ctx_, NULL, 0, &n, first_record, n_ref);
+      if (rc != PG_OK && rc != PG_ERR_RUNS_CAP) check(rc, "pg_bam_index");
+      std::vector<pg_bam_rec> recs((size_t)n);
+      if (n) check(pg_bam_index(ctx_, recs.data(), n, &n, first_record, n_ref), "pg_bam_index");
+      return recs;
+   }
+
 private:
+   static void marshal(const std::vector<RP_READ> &v, std::vector<pg_rp> &in)
+   {
+      in.resize(v.size());
+      for (size_t i = 0; i < v.size(); i++) {
+         in[i].pos_a = v[i].PosA; in[i].pos_b = v[i].PosB; in[i].insert_size = v[i].InsertSize; in[i].read_length = v[i].ReadLength;
+         in[i].da = (uint8_t)v[i].DA; in[i].db = (uint8_t)v[i].DB;
+      }
+   }
+
    struct Batch {
       std::string blob;
       std::vector<uint32_t> off, pos, region_off;

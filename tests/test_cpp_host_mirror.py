@@ -18,12 +18,34 @@ EXE = os.path.join(ROOT, "tests", "cpp", "host_mirror_test")
 LIBDIR = os.path.join(ROOT, "pindel_b200")
 
 
-def build_exe():
-    deps = [SRC, os.path.join(ROOT, "include", "pindel_pg.hpp"), os.path.join(ROOT, "include", "pindel_pg.h")]
-    if not os.path.exists(EXE) or any(os.path.getmtime(d) > os.path.getmtime(EXE) for d in deps):
-        subprocess.check_call(["/usr/bin/g++", "-O2", "-std=c++11", "-Wall", "-Wextra", "-o", EXE, SRC, "-L" + LIBDIR, "-lpindel_pg",
+def build_exe(src=SRC, exe=EXE):
+    deps = [src, os.path.join(ROOT, "include", "pindel_pg.hpp"), os.path.join(ROOT, "include", "pindel_pg.h")]
+    if not os.path.exists(exe) or any(os.path.getmtime(d) > os.path.getmtime(exe) for d in deps):
+        subprocess.check_call(["/usr/bin/g++", "-O2", "-std=c++11", "-Wall", "-Wextra", "-o", exe, src, "-L" + LIBDIR, "-lpindel_pg",
                                "-Wl,-rpath," + LIBDIR])
-    return EXE
+    return exe
+
+
+STAGES_SRC = os.path.join(ROOT, "tests", "cpp", "host_mirror_stages_test.cpp")
+STAGES_EXE = os.path.join(ROOT, "tests", "cpp", "host_mirror_stages_test")
+
+
+def write_stages_input(path, rp_rows, reads, box_off, idx, bam_bytes):
+    with open(path, "wb") as f:
+        f.write(struct.pack("<i", rp_rows.size))
+        for r in rp_rows:
+            f.write(struct.pack("<IIIhBB", int(r["pos_a"]), int(r["pos_b"]), int(r["insert_size"]), int(r["read_length"]), int(r["da"]), int(r["db"])))
+        f.write(struct.pack("<i", reads.size))
+        for r in reads:
+            f.write(struct.pack("<IIIiiIHhB", int(r["bp_left"]), int(r["bp_right"]), int(r["indel_size"]), int(r["left"]), int(r["right"]),
+                                int(r["name_id"]), int(r["nt_size"]), int(r["bp"]), int(r["unique"])))
+        f.write(struct.pack("<i", len(box_off) - 1))
+        for b in range(len(box_off) - 1):
+            m = idx[int(box_off[b]):int(box_off[b + 1])]
+            f.write(struct.pack("<i", m.size))
+            f.write(m.astype("<u4").tobytes())
+        f.write(struct.pack("<q", len(bam_bytes)))
+        f.write(bam_bytes)
 
 
 def write_input(path, chroms, batch, chr_id):
@@ -66,3 +88,54 @@ def test_cpp_mirror_matches_oracle(tmp_path):
     got = refhook.parse_stream(np.fromfile(tmp_path / "out.bin", dtype=np.int32), batch.n)
     exp = H.oracle_results([padded], batch, threads=4)
     H.compare(exp, got, "C++ host mirror")
+
+
+def test_stage_mirrors_compile_and_fail_loudly_without_a_device(tmp_path):
+    exe = build_exe(STAGES_SRC, STAGES_EXE)
+    try:
+        import torch
+        has_gpu = torch.cuda.is_available()
+    except Exception:
+        has_gpu = False
+    if has_gpu:
+        pytest.skip("device present: covered by the gpu test")
+    from oracle import boxsortoracle as B
+    from pindel_b200 import bam, bgzf
+    reads, box_off, idx = B.make_boxes(3, 1)
+    write_stages_input(tmp_path / "in.bin", synth.make_discordant_pairs(3, 1), reads, box_off, idx, bgzf.compress(bam.synthetic_stream(20, 1)))
+    p = subprocess.run([exe, str(tmp_path / "in.bin"), str(tmp_path / "out.bin")], capture_output=True, text=True)
+    assert p.returncode == 1 and "no CUDA device" in p.stderr
+
+
+@pytest.mark.gpu
+def test_cpp_stage_mirrors_match_oracles(tmp_path):
+    """ModifyRP / Summarize, SortBoxes and InflateBam / IndexBam of the C++ mirror against the oracles of their stages."""
+    from oracle import boxsortoracle as B, rporacle
+    from pindel_b200 import bam, bgzf
+    exe = build_exe(STAGES_SRC, STAGES_EXE)
+    rows = synth.make_discordant_pairs(150, 41, span=3_000_000, background=200)
+    reads, box_off, idx = B.make_boxes(300, 42)
+    stream = bam.synthetic_stream(5000, 43)
+    write_stages_input(tmp_path / "in.bin", rows, reads, box_off, idx, bgzf.compress(stream))
+    p = subprocess.run([exe, str(tmp_path / "in.bin"), str(tmp_path / "out.bin")], capture_output=True, text=True, timeout=600)
+    assert p.returncode == 0, p.stderr
+    o = np.fromfile(tmp_path / "out.bin", dtype=np.int32)
+    t = o[:9 * rows.size].reshape(-1, 9).astype(np.int64)
+    t[:, 1:5] &= 0xFFFFFFFF
+    srt = rows[t[:, 0]]                                   # the order the mirror's std::sort(Compare2RP) left
+    assert np.all(np.diff(srt["pos_a"].astype(np.int64)) <= 0)
+    exp = rporacle.cluster(srt)
+    for col, key in ((1, "pos_a"), (2, "pos_a1"), (3, "pos_b"), (4, "pos_b1"), (5, "visited"), (6, "report"), (7, "n_identical")):
+        assert np.array_equal(t[:, col], exp[key].astype(np.int64)), key
+    n_tags = np.bincount(exp["merged_into"], minlength=rows.size)       # a row holds its own tag and those merged into it
+    assert np.array_equal(t[:, 8], np.where(exp["merged_into"] == np.arange(rows.size), n_tags, 0))
+    p0 = 9 * rows.size
+    e_idx, e_unique = B.sort_boxes(reads, box_off, idx)
+    assert np.array_equal(o[p0:p0 + idx.size].astype(np.uint32), e_idx)
+    assert np.array_equal(o[p0 + idx.size:p0 + idx.size + reads.size].astype(np.uint8), e_unique)
+    q = p0 + idx.size + reads.size
+    table = bam.serial_index(stream)
+    assert o[q] == len(stream) and o[q + 1] == 1 and o[q + 2] == table.size
+    rec = o[q + 3:].reshape(-1, 3)
+    assert np.array_equal(rec[:, 0].astype(np.int64), table["off"].astype(np.int64)) and np.array_equal(rec[:, 1], table["pos"]) and \
+        np.array_equal(rec[:, 2], table["end"])
