@@ -88,6 +88,7 @@ struct PgSvBatch {
    const uint32_t *close_off;    // [n+1] or NULL
    const PgRun *close_runs;
    const int32_t *chr_id;        // [n] chromosome of the anchor (FragName) or NULL = 0: FarFragName != FragName is derived
+   const uint32_t *perm;         // [n] or NULL: thread t classifies read perm[t] ('+' anchors first: a warp's lanes walk the same arms)
    PgSvRecord *records;
    uint32_t records_cap;
    uint32_t *counters;           // [4]: [0] records allocated, [1] overflow flag, [2] pair tests (statistics)

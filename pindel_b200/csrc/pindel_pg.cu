@@ -137,8 +137,9 @@ __global__ void pg_pack_kernel(const uint8_t *__restrict__ ascii, uint32_t n_bas
 __global__ void __launch_bounds__(128) pg_sv_kernel(PgSvBatch b, const PgSvParams *__restrict__ P, const PgParams *__restrict__ prm,
                                                     const PgChrom *__restrict__ chroms)
 {
-   const int i = blockIdx.x * blockDim.x + threadIdx.x;
-   if (i >= b.n_reads) return;
+   const int t = blockIdx.x * blockDim.x + threadIdx.x;
+   if (t >= b.n_reads) return;
+   const int i = b.perm ? (int)b.perm[t] : t;
    PgSvEnv ev;
    ev.P = P;
    ev.chrom = chroms[P->chr];
@@ -233,6 +234,22 @@ __global__ void __launch_bounds__(256) pg_sv_final_seq_kernel(int n_reads, const
       }
       d[j] = ch;
    }
+}
+
+// Thread-to-read assignment of pg_sv_kernel: reads with a '+' anchor first, then the others (stable), so that the lanes of a
+// warp run the same arm of every driver.  flags -> (scan) -> perm; the number of '+' reads is the scan's total.
+__global__ void pg_sv_strand_flag_kernel(int n, const uint8_t *__restrict__ matched_d, uint8_t *__restrict__ flags)
+{
+   const int i = blockIdx.x * blockDim.x + threadIdx.x;
+   if (i < n) flags[i] = matched_d[i] == '+';
+}
+__global__ void pg_sv_perm_kernel(int n, const uint8_t *__restrict__ flags, const uint32_t *__restrict__ offsets, const uint32_t *__restrict__ n_plus,
+                                  uint32_t *__restrict__ perm)
+{
+   const int i = blockIdx.x * blockDim.x + threadIdx.x;
+   if (i >= n) return;
+   const uint32_t before = offsets[i];      // '+' reads before i
+   perm[flags[i] ? before : *n_plus + ((uint32_t)i - before)] = (uint32_t)i;
 }
 
 // Record order.  pg_sv_kernel hands out pool slots in completion order; the host replays records per driver with reads
@@ -367,7 +384,7 @@ struct pg_ctx {
    uint64_t last_window_bases = 0, last_ups = 0;
    // SV classification (pg_classify)
    DevBuf sv_seq, sv_off, sv_md, sv_isz, sv_flags, sv_runoff, sv_nclose, sv_runs, sv_records, sv_params, sv_counters, sv_counts, sv_offsets,
-      sv_blocksums, sv_ordered;
+      sv_blocksums, sv_ordered, sv_perm;
    PgSvParams sv_params_h;          // staging copy (the async upload reads it until the stream drains)
    DevBuf sv_close_off, sv_close_runs;
    uint64_t sv_aux_launches = 0;
@@ -542,7 +559,7 @@ void pg_destroy(pg_ctx *ctx)
    for (DevBuf *b : bufs) if (b->p) cudaFree(b->p);
    DevBuf *svbufs[] = {&ctx->sv_seq, &ctx->sv_off, &ctx->sv_md, &ctx->sv_isz, &ctx->sv_flags, &ctx->sv_runoff, &ctx->sv_nclose,
                        &ctx->sv_runs, &ctx->sv_records, &ctx->sv_params, &ctx->sv_counters,
-                       &ctx->sv_counts, &ctx->sv_offsets, &ctx->sv_blocksums, &ctx->sv_ordered, &ctx->sv_close_off,
+                       &ctx->sv_counts, &ctx->sv_offsets, &ctx->sv_blocksums, &ctx->sv_ordered, &ctx->sv_perm, &ctx->sv_close_off,
                        &ctx->sv_close_runs, &ctx->rp_in, &ctx->rp_out, &ctx->rp_rows, &ctx->rp_off, &ctx->rp_scratch, &ctx->rp_merged,
                        &ctx->rp_nid, &ctx->rp_counters, &ctx->rp_keys, &ctx->bz_file, &ctx->bz_blocks, &ctx->bz_out, &ctx->bz_status,
                        &ctx->bm_info, &ctx->bm_starts, &ctx->bm_counts, &ctx->bm_landing, &ctx->bm_base, &ctx->bm_recs,
@@ -1054,9 +1071,26 @@ static int sv_classify_device(pg_ctx *ctx, PgSvBatch &b, pg_sv_results *res)
    if ((rc = ensure(ctx, ctx->sv_blocksums, sizeof(uint32_t) * ((size_t)n_blocks + 1))) != PG_OK) return rc;
    uint32_t counters[4];
    if (!ctx->sv_ev0) { CU(cudaEventCreate(&ctx->sv_ev0)); CU(cudaEventCreate(&ctx->sv_ev1)); }
+   if ((rc = ensure(ctx, ctx->sv_perm, sizeof(uint32_t) * (size_t)n)) != PG_OK) return rc;
+   const bool group_by_strand = getenv("PG_SV_NO_GROUPING") == nullptr;
    for (int attempt = 0;; attempt++) {
       if ((rc = ensure(ctx, ctx->sv_records, sizeof(PgSvRecord) * cap)) != PG_OK) return rc;
       CU(cudaEventRecord(ctx->sv_ev0, st));
+      b.perm = nullptr;
+      if (group_by_strand) {      // the scan buffers are free until the record-order pass below
+         const uint32_t m16 = ((uint32_t)n + 15u) / 16u, m_blocks = (m16 + PG_SCAN_THREADS - 1) / PG_SCAN_THREADS;
+         CU(cudaMemsetAsync(ctx->sv_counts.p, 0, (size_t)m16 * 16, st));
+         pg_sv_strand_flag_kernel<<<(n + 255) / 256, 256, 0, st>>>(n, b.matched_d, (uint8_t *)ctx->sv_counts.p);
+         pg_scan_reduce<<<m_blocks, PG_SCAN_THREADS, 0, st>>>((const uint4 *)ctx->sv_counts.p, m16, (uint32_t *)ctx->sv_blocksums.p);
+         pg_scan_blocks<<<1, 1024, 0, st>>>((uint32_t *)ctx->sv_blocksums.p, m_blocks);
+         pg_scan_apply<<<m_blocks, PG_SCAN_THREADS, 0, st>>>((const uint4 *)ctx->sv_counts.p, m16, (const uint32_t *)ctx->sv_blocksums.p,
+                                                            (uint32_t *)ctx->sv_offsets.p);
+         pg_sv_perm_kernel<<<(n + 255) / 256, 256, 0, st>>>(n, (const uint8_t *)ctx->sv_counts.p, (const uint32_t *)ctx->sv_offsets.p,
+                                                         (const uint32_t *)ctx->sv_blocksums.p + m_blocks, (uint32_t *)ctx->sv_perm.p);
+         CU(cudaGetLastError());
+         ctx->sv_aux_launches += 5;
+         b.perm = (const uint32_t *)ctx->sv_perm.p;
+      }
       CU(cudaMemsetAsync(ctx->sv_counters.p, 0, sizeof(uint32_t) * 4, st));
       CU(cudaMemsetAsync(ctx->sv_counts.p, 0, (size_t)n16 * 16, st));
       b.records = (PgSvRecord *)ctx->sv_records.p;
