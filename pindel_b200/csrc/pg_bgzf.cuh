@@ -337,7 +337,12 @@ PGZ_FN int pgz_inflate(const uint8_t *in, uint32_t in_len, uint8_t *out, uint32_
          // copy independently once the earlier stores of the other lanes are visible
          PGZ_SYNC();
          const uint8_t *src = out + op - d;
-         for (uint32_t k = lane; k < len; k += nlanes) out[op + k] = src[d >= len ? k : k % d];
+         if (d >= len) {                     // the usual case: no overlap, and most matches are shorter than a warp
+            if (lane < len) out[op + lane] = src[lane];
+            for (uint32_t k = lane + nlanes; k < len; k += nlanes) out[op + k] = src[k];
+         } else {
+            for (uint32_t k = lane; k < len; k += nlanes) out[op + k] = src[k % d];
+         }
          op += len;
       }
       if (b.overrun > 2u) rc = PGZ_ERR_INPUT;   // the bit buffer may look one or two words past the end; decoding from there is an error
