@@ -151,6 +151,24 @@ class DevArr:
         self.__cuda_array_interface__ = {"shape": (nbytes,), "typestr": "|u1", "data": (ptr, False), "version": 2}
 
 
+def algorithmic_compares(ref_np, seq_np, md_np, pos_np, isz_np, max_range_index, sample=5000):
+    """CategorizePositions inner iterations per read (src/searcher.cpp:48-63), counted by the C port of the reference's
+    algorithm (oracle/pg_oracle.c, pgo_char_compares) on the first `sample` reads with one thread."""
+    import ctypes as C
+    from oracle import pgoracle
+    from pindel_b200 import synth
+    lib = pgoracle.load()
+    lib.pgo_char_compares.restype = C.c_ulonglong
+    k = min(sample, seq_np.shape[0])
+    L = seq_np.shape[1]
+    P = pgoracle.default_params(max_range_index=max_range_index)
+    lib.pgo_char_compares(1)
+    pgoracle.search(P, [synth.pad_reference(ref_np)], seq_np[:k].reshape(-1), (np.arange(k + 1, dtype=np.uint64) * L).astype(np.uint32),
+                    md_np[:k], pos_np[:k], isz_np[:k], threads=1)
+    total = int(lib.pgo_char_compares(1))
+    return {"char_compares_per_read": total / k, "unit": "Gcompare/s", "sample_reads": int(k)}
+
+
 def cpu_baseline_reference(ref_np, seq_np, md_np, pos_np, isz_np, target_seconds, max_range_index, log):
     """Times the reference's own GetCloseEnd loop + SearchFarEnds (oracle/_ref/libpindel_ref.so) with all host
     threads on a bounded prefix of the batch.  Falls back to the C port when the reference library is absent."""
@@ -382,6 +400,17 @@ def main():
     }
 
     if rank == 0 and world == 1 and not a.no_cpu_baseline:
+        try:
+            # op-roofline of SURVEY.md section 8(d)(ii): the character comparisons the reference's algorithm executes for these
+            # reads (CategorizePositions inner iterations, counted by the oracle port on a small sample, one thread)
+            ops = algorithmic_compares(ref_np, seq_h.reshape(n, L), md_h, pos_h, isz_h, a.max_range_index)
+            ops["achieved_Gcompares_per_s"] = ops["char_compares_per_read"] * value / 1e9
+            ops["note"] = ("algorithmic character comparisons per read (what the reference's level-bucket growth executes) x reads/s; the kernel "
+                           "itself compares 32 bases per LOP3 pair on bit-planes and evaluates whole 32-base stretches per seed, so it executes "
+                           "more raw comparisons than this count -- this figure is the useful work, comparable across implementations")
+            roofline["ops"] = ops
+        except Exception as e:
+            roofline["ops"] = {"unavailable": repr(e)}
         try:
             result["cpu_baseline"] = cpu_baseline_reference(ref_np, seq_h.reshape(n, L), md_h, pos_h, isz_h, a.cpu_seconds,
                                                             a.max_range_index, log)

@@ -42,6 +42,17 @@ static inline char rc4n(char c)
 }
 
 /* Matches(), src/searcher.cpp:36-44 */
+/* Algorithmic work counter for the op-roofline of SURVEY.md section 8(d): every execution of the inner statement of
+ * CategorizePositions (src/searcher.cpp:48-63: one candidate position compared with one read character) adds one.
+ * Plain (non-atomic) counter: meaningful with threads == 1 only. */
+static unsigned long long g_char_compares = 0;
+unsigned long long pgo_char_compares(int reset)
+{
+   unsigned long long v = g_char_compares;
+   if (reset) g_char_compares = 0;
+   return v;
+}
+
 static inline int matches(char readBase, char refBase)
 {
    if (readBase != 'N') return refBase == readBase;
@@ -233,6 +244,7 @@ static int close_end_inner(const pgo_params *P, const char *ref, uint32_t ref_le
       char ch = (dir == 1) ? cur[len] : cur[L - 1 - len];
       int w = 0;
       unsigned kept_le_max = 0;
+      g_char_compares += (unsigned long long)nc;
       for (int i = 0; i < nc; i++) {
          uint32_t p = cands[i].pos + (uint32_t)dir;
          int lvl = cands[i].level;
@@ -376,6 +388,7 @@ static int far_end_at_pos(const pgo_params *P, const char *const *chr_seq, const
       char ch = seq[len];
       char ch_rc = rc4n(ch);
       size_t w = 0;
+      g_char_compares += (unsigned long long)nc;
       for (size_t i = 0; i < nc; i++) {
          const char *ref = chr_seq[regions[cands[i].region].chr];
          uint32_t p;

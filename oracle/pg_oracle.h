@@ -73,6 +73,9 @@ int64_t pgo_search_stream(const pgo_params *p, int n_chr, const char *const *chr
                           int32_t **out_stream, double *seconds);
 void pgo_free(void *p);
 
+/* CategorizePositions inner iterations executed since the last reset (op-roofline of SURVEY.md 8(d)); threads == 1 only. */
+unsigned long long pgo_char_compares(int reset);
+
 #ifdef __cplusplus
 }
 #endif
