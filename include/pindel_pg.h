@@ -329,6 +329,11 @@ typedef struct pg_rp_cluster {    /* what ModifyRP / Summarize leave in the RP_R
 
 int pg_rp_modify(pg_ctx *ctx, int32_t n, const pg_rp *in, pg_rp_cluster *out);
 int pg_rp_summarize(pg_ctx *ctx, int32_t n, const pg_rp *in, pg_rp_cluster *inout);
+/* The inter-chromosomal variants, ModifyRP_InterChr (src/bddata.cpp:439-468, rows again in the order its sort leaves) and
+ * Summarize_InterChr (src/bddata.cpp:577-624), for Reads_RP_Discovery_InterChr.  chr_a / chr_b: ChrNameA / ChrNameB as numbers
+ * (equal numbers <=> equal names; below 2^24).  A row also meets the rows of the opposite orientation (Y, X, DB, DA). */
+int pg_rp_modify_interchr(pg_ctx *ctx, int32_t n, const pg_rp *in, const int32_t *chr_a, const int32_t *chr_b, pg_rp_cluster *out);
+int pg_rp_summarize_interchr(pg_ctx *ctx, int32_t n, const pg_rp *in, const int32_t *chr_a, const int32_t *chr_b, pg_rp_cluster *inout);
 uint64_t pg_rp_launches(pg_ctx *ctx);          /* clustering-kernel launches since pg_create */
 /* how the last pg_rp_modify split its rows: classes run by one warp each, classes run by one CTA each, rows in either */
 void pg_rp_last_classes(pg_ctx *ctx, uint32_t *warp_classes, uint32_t *cta_classes, uint32_t *rows_in_classes);

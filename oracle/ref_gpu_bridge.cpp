@@ -356,6 +356,16 @@ void SearchFarEnds(const std::string &chromosomeSeq, std::vector<SPLIT_READ> &re
  * ------------------------------------------------------------------------------------------------------------------- */
 bool Compare2RP(const RP_READ &first, const RP_READ &second);   /* src/bddata.cpp:239-253 */
 namespace {
+void numberChromosomes(const std::vector<RP_READ> &v, std::vector<int32_t> &ca, std::vector<int32_t> &cb)
+{
+   std::map<std::string, int32_t> id;
+   ca.resize(v.size());
+   cb.resize(v.size());
+   for (size_t i = 0; i < v.size(); i++) {
+      ca[i] = id.insert(std::make_pair(v[i].ChrNameA, (int32_t)id.size())).first->second;
+      cb[i] = id.insert(std::make_pair(v[i].ChrNameB, (int32_t)id.size())).first->second;
+   }
+}
 void marshalRP(const std::vector<RP_READ> &v, std::vector<pg_rp> &in)
 {
    in.resize(v.size());
@@ -411,6 +421,61 @@ void Summarize(std::vector<RP_READ> &Reads_RP)
          RP_READ &first = Reads_RP[st[i].merged_into];
          first.Tags.insert(first.Tags.end(), r.Tags.begin(), r.Tags.end());
          r.Tags.clear();
+      }
+   }
+}
+
+/* the inter-chromosomal variants (src/bddata.cpp:439-468, 577-624; called at :737-738): same binding, chromosome names numbered */
+void ModifyRP_InterChr(std::vector<RP_READ> &Reads_RP)
+{
+   std::cout << "Reads_RP.size(): " << Reads_RP.size() << std::endl;
+   if (Reads_RP.size() == 0) return;
+   std::cout << "sorting read-pair" << std::endl;
+   sort(Reads_RP.begin(), Reads_RP.end(), Compare2RP);
+   std::cout << "sorting InterChr read-pair finished." << std::endl;
+   std::lock_guard<std::mutex> lock(g_mutex);
+   ensureContext();
+   std::vector<pg_rp> in;
+   marshalRP(Reads_RP, in);
+   std::vector<int32_t> ca, cb;
+   numberChromosomes(Reads_RP, ca, cb);
+   std::vector<pg_rp_cluster> out(in.size());
+   if (pg_rp_modify_interchr(g_ctx, (int32_t)in.size(), &in[0], &ca[0], &cb[0], &out[0]) != PG_OK) die("pg_rp_modify_interchr");
+   for (size_t i = 0; i < Reads_RP.size(); i++) {
+      RP_READ &r = Reads_RP[i];
+      r.PosA = out[i].pos_a; r.PosA1 = out[i].pos_a1; r.PosB = out[i].pos_b; r.PosB1 = out[i].pos_b1;
+   }
+   g_rp_rows += (unsigned long)Reads_RP.size();
+}
+
+void Summarize_InterChr(std::vector<RP_READ> &Reads_RP)
+{
+   if (Reads_RP.empty()) return;
+   std::lock_guard<std::mutex> lock(g_mutex);
+   ensureContext();
+   std::vector<pg_rp> in;
+   marshalRP(Reads_RP, in);
+   std::vector<int32_t> ca, cb;
+   numberChromosomes(Reads_RP, ca, cb);
+   std::vector<pg_rp_cluster> st(in.size());
+   for (size_t i = 0; i < Reads_RP.size(); i++) {
+      const RP_READ &r = Reads_RP[i];
+      st[i].pos_a = r.PosA; st[i].pos_a1 = r.PosA1; st[i].pos_b = r.PosB; st[i].pos_b1 = r.PosB1;
+      st[i].n_identical = r.NumberOfIdentical; st[i].merged_into = (uint32_t)i;
+      st[i].visited = r.Visited ? 1 : 0; st[i].report = r.Report ? 1 : 0; st[i].pad = 0;
+   }
+   if (pg_rp_summarize_interchr(g_ctx, (int32_t)in.size(), &in[0], &ca[0], &cb[0], &st[0]) != PG_OK) die("pg_rp_summarize_interchr");
+   for (size_t i = 0; i < Reads_RP.size(); i++) {
+      RP_READ &r = Reads_RP[i];
+      r.NumberOfIdentical = st[i].n_identical;
+      r.Visited = st[i].visited != 0;
+      r.Report = st[i].report != 0;
+      if (st[i].merged_into != (uint32_t)i) {          /* src/bddata.cpp:605-609: only when the absorbing row holds Tags */
+         RP_READ &first = Reads_RP[st[i].merged_into];
+         if (first.Tags.size()) {
+            first.Tags.insert(first.Tags.end(), r.Tags.begin(), r.Tags.end());
+            r.Tags.clear();
+         }
       }
    }
 }

@@ -528,3 +528,53 @@ extern "C" int pgref_box_sort(int n_reads, const int32_t *key, int n_boxes, cons
    for (int i = 0; i < n_reads; i++) unique_out[i] = reads[i].UniqueRead ? 1 : 0;
    return 0;
 }
+
+/* The inter-chromosomal variants exactly as BDData::UpdateBD chains them (src/bddata.cpp:736-739): ModifyRP_InterChr
+ * (its own sort included), Summarize_InterChr.  chr_a / chr_b: numbers turned into names "c<k>".  Output as pgref_rp_cluster
+ * (14 int32 per row + tags), with ChrNameA / ChrNameB numbers appended after the tags (2 int32 per row). */
+void ModifyRP_InterChr(std::vector<RP_READ> &Reads_RP);
+void Summarize_InterChr(std::vector<RP_READ> &Reads_RP);
+
+extern "C" int64_t pgref_rp_cluster_interchr(int n, const uint32_t *pos_a, const uint32_t *pos_b, const char *da, const char *db,
+                                             const int16_t *read_length, const uint32_t *insert_size, const int32_t *chr_a, const int32_t *chr_b,
+                                             int32_t **out_stream)
+{
+   std::vector<RP_READ> v((size_t)n);
+   for (int i = 0; i < n; i++) {
+      RP_READ &r = v[i];
+      r.ReadName = "r" + std::to_string(i);
+      r.ChrNameA = "c" + std::to_string(chr_a[i]);
+      r.ChrNameB = "c" + std::to_string(chr_b[i]);
+      r.DA = da[i];
+      r.DB = db[i];
+      r.PosA = r.OriginalPosA = pos_a[i];
+      r.PosB = r.OriginalPosB = pos_b[i];
+      r.ReadLength = read_length[i];
+      r.InsertSize = insert_size[i];
+      r.Experimental_InsertSize = (unsigned)i;
+      r.Tag = std::to_string(i);
+      r.Tags.push_back(r.Tag);
+   }
+   ModifyRP_InterChr(v);
+   Summarize_InterChr(v);
+   std::vector<int32_t> out;
+   for (int i = 0; i < n; i++) {
+      const RP_READ &r = v[i];
+      const int32_t row[14] = {(int32_t)r.Experimental_InsertSize, (int32_t)r.OriginalPosA, (int32_t)r.OriginalPosB, r.DA, r.DB, r.ReadLength,
+                               (int32_t)r.InsertSize, (int32_t)r.PosA, (int32_t)r.PosA1, (int32_t)r.PosB, (int32_t)r.PosB1, r.Visited ? 1 : 0,
+                               r.Report ? 1 : 0, (int32_t)r.NumberOfIdentical};
+      out.insert(out.end(), row, row + 14);
+   }
+   for (int i = 0; i < n; i++) {
+      out.push_back((int32_t)v[i].Tags.size());
+      for (size_t k = 0; k < v[i].Tags.size(); k++) out.push_back((int32_t)std::stoi(v[i].Tags[k]));
+   }
+   for (int i = 0; i < n; i++) {
+      out.push_back(std::stoi(v[i].ChrNameA.substr(1)));
+      out.push_back(std::stoi(v[i].ChrNameB.substr(1)));
+   }
+   int32_t *buf = (int32_t *)malloc(out.size() * sizeof(int32_t) + 4);
+   memcpy(buf, out.data(), out.size() * sizeof(int32_t));
+   *out_stream = buf;
+   return (int64_t)out.size();
+}

@@ -243,3 +243,34 @@ def rp_cluster(rows):
         tags.append(stream[p + 1:p + 1 + c].tolist())
         p += 1 + c
     return table, tags, (secs[0], secs[1])
+
+
+def rp_cluster_interchr(rows, chr_a, chr_b):
+    """The reference's own ModifyRP_InterChr + Summarize_InterChr (oracle/ref_hook.cpp pgref_rp_cluster_interchr).
+    -> (table [n, 14] as rp_cluster, tags, chr_a, chr_b in the order ModifyRP_InterChr's sort leaves)"""
+    lib = C.CDLL(LIB)
+    lib.pgref_rp_cluster_interchr.restype = C.c_int64
+    n = len(rows)
+    cols = [np.ascontiguousarray(rows[k]) for k in ("pos_a", "pos_b", "da", "db", "read_length", "insert_size")]
+    cols += [np.ascontiguousarray(chr_a, dtype=np.int32), np.ascontiguousarray(chr_b, dtype=np.int32)]
+    out = C.POINTER(C.c_int32)()
+    devnull = os.open(os.devnull, os.O_WRONLY)
+    saved = os.dup(1)
+    os.dup2(devnull, 1)
+    try:
+        k = lib.pgref_rp_cluster_interchr(n, *[c.ctypes.data_as(C.c_void_p) for c in cols], C.byref(out))
+    finally:
+        os.dup2(saved, 1)
+        os.close(saved)
+        os.close(devnull)
+    stream = np.ctypeslib.as_array(out, shape=(max(int(k), 1),))[:k].copy()
+    lib.pgref_free(out)
+    table = stream[:14 * n].reshape(n, 14).astype(np.int64)
+    table[:, [1, 2, 6, 7, 8, 9, 10, 13]] &= 0xFFFFFFFF
+    tags, p = [], 14 * n
+    for _ in range(n):
+        c = int(stream[p])
+        tags.append(stream[p + 1:p + 1 + c].tolist())
+        p += 1 + c
+    chrs = stream[p:p + 2 * n].reshape(n, 2)
+    return table, tags, chrs[:, 0].copy(), chrs[:, 1].copy()

@@ -165,3 +165,54 @@ void rpo_summarize(int n, const rpo_in *in, rpo_out *io)
    }
    free(good);
 }
+
+/* ---- the inter-chromosomal variants, src/bddata.cpp:439-468 (ModifyRP_InterChr after its sort) and :577-624
+ * (Summarize_InterChr).  chr_a / chr_b: ChrNameA / ChrNameB as numbers (equal numbers <=> equal names). ---- */
+
+/* UpdateFirstBasedOnSecondInterChromosome, src/bddata.cpp:362-382: no RecipicalOverlap here */
+static void update_interchr(const rpo_in *fi, rpo_out *f, int32_t fa, int32_t fb, const rpo_in *si, const rpo_out *s, int32_t sa, int32_t sb)
+{
+   if (fa == sa && fb == sb) {
+      if (fi->da == si->da && fi->db == si->db) process_pair(fi, f, s);
+   } else if (fa == sb && fb == sa) {
+      if (fi->da == si->db && fi->db == si->da) {
+         rpo_out t = *s;       /* Current_AnotherSecond: the second row seen from its other end */
+         t.pos_a = s->pos_b; t.pos_a1 = s->pos_b1; t.pos_b = s->pos_a; t.pos_b1 = s->pos_a1;
+         process_pair(fi, f, &t);
+      }
+   }
+}
+
+void rpo_modify_interchr(int n, const rpo_in *in, const int32_t *chr_a, const int32_t *chr_b, rpo_out *out)
+{
+   for (int i = 0; i < n; i++) {
+      init_a1b1(&in[i], &out[i]);
+      out[i].n_identical = 0;
+      out[i].merged_into = (uint32_t)i;
+      out[i].visited = 0;
+      out[i].report = 0;
+      out[i].pad = 0;
+   }
+   for (int first = 0; first < n - 1; first++)          /* the last row is never updated, :456 */
+      for (int second = 0; second < n; second++)
+         update_interchr(&in[first], &out[first], chr_a[first], chr_b[first], &in[second], &out[second], chr_a[second], chr_b[second]);
+}
+
+void rpo_summarize_interchr(int n, const rpo_in *in, const int32_t *chr_a, const int32_t *chr_b, rpo_out *io)
+{
+   if (n == 0) return;
+   for (int first = 0; first < n - 1; first++) {
+      if (io[first].visited) continue;
+      io[first].n_identical = 0;
+      for (int second = first + 1; second < n; second++) {
+         if (io[second].visited) continue;
+         if (chr_a[first] == chr_a[second] && chr_b[first] == chr_b[second] && io[first].pos_a == io[second].pos_a &&
+             io[first].pos_b == io[second].pos_b && in[first].da == in[second].da && in[first].db == in[second].db) {
+            io[first].n_identical++;
+            io[second].visited = 1;
+            io[second].merged_into = (uint32_t)first;
+         }
+      }
+      io[first].report = io[first].n_identical >= 5;
+   }
+}

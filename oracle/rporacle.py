@@ -42,3 +42,15 @@ def summarize(rows: np.ndarray, state: np.ndarray) -> np.ndarray:
 
 def cluster(rows: np.ndarray) -> np.ndarray:
     return summarize(rows, modify(rows))
+
+
+def cluster_interchr(rows: np.ndarray, chr_a: np.ndarray, chr_b: np.ndarray):
+    """ModifyRP_InterChr (after its sort) + Summarize_InterChr, src/bddata.cpp:439-468, 577-624.  -> (after modify, after summarize)"""
+    rows = np.ascontiguousarray(rows, dtype=RP_DT)
+    ca, cb = np.ascontiguousarray(chr_a, dtype=np.int32), np.ascontiguousarray(chr_b, dtype=np.int32)
+    out = np.zeros(rows.size, dtype=CLUSTER_DT)
+    vp = lambda a: a.ctypes.data_as(C.c_void_p)
+    lib().rpo_modify_interchr(int(rows.size), vp(rows), vp(ca), vp(cb), vp(out))
+    mod = out.copy()
+    lib().rpo_summarize_interchr(int(rows.size), vp(rows), vp(ca), vp(cb), vp(out))
+    return mod, out

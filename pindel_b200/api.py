@@ -116,6 +116,8 @@ def load_library() -> C.CDLL:
         lib.pg_rp_summarize.argtypes = [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p]
         lib.pg_rp_last_classes.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
         lib.pg_rp_last_classes.restype = None
+        lib.pg_rp_modify_interchr.argtypes = [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+        lib.pg_rp_summarize_interchr.argtypes = [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
         lib.pg_rp_launches.restype = C.c_uint64
         lib.pg_rp_launches.argtypes = [C.c_void_p]
         lib.pg_rp_last_kernel_ms.restype = C.c_double
@@ -448,6 +450,19 @@ class PatternGrowth:
         self._check(self.lib.pg_rp_summarize(self.ctx, int(rows.size), rows.ctypes.data_as(C.c_void_p), out.ctypes.data_as(C.c_void_p)),
                     "pg_rp_summarize")
         return out
+
+    def rp_cluster_interchr(self, rows: np.ndarray, chr_a, chr_b):
+        """ModifyRP_InterChr (after its sort) + Summarize_InterChr (src/bddata.cpp:439-468, 577-624) on the device.
+        -> (state after modify, state after summarize)"""
+        from . import rp
+        rows = np.ascontiguousarray(rows, dtype=rp.RP_DT)
+        ca, cb = np.ascontiguousarray(chr_a, dtype=np.int32), np.ascontiguousarray(chr_b, dtype=np.int32)
+        out = np.zeros(rows.size, dtype=rp.CLUSTER_DT)
+        vp = lambda a: a.ctypes.data_as(C.c_void_p) if a.size else None
+        self._check(self.lib.pg_rp_modify_interchr(self.ctx, int(rows.size), vp(rows), vp(ca), vp(cb), vp(out)), "pg_rp_modify_interchr")
+        mod = out.copy()
+        self._check(self.lib.pg_rp_summarize_interchr(self.ctx, int(rows.size), vp(rows), vp(ca), vp(cb), vp(out)), "pg_rp_summarize_interchr")
+        return mod, out
 
     def rp_last_classes(self):
         """(classes run by one warp, classes run by one CTA, rows in either) of the last rp_modify."""

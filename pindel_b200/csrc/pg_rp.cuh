@@ -130,6 +130,38 @@ PGRP_HD bool pg_rp_same_event(const PgRpCluster &x, const PgRp &xi, const PgRpCl
    return x.pos_a == y.pos_a && x.pos_b == y.pos_b && x.pos_a1 == y.pos_a1 && x.pos_b1 == y.pos_b1 && xi.da == yi.da && xi.db == yi.db;
 }
 
+// ---- the inter-chromosomal variants: ModifyRP_InterChr (src/bddata.cpp:439-468) and Summarize_InterChr (:577-624) -------
+// UpdateFirstBasedOnSecondInterChromosome (:362-382) has no RecipicalOverlap test, and a row (X, Y, DA, DB) also meets the
+// rows (Y, X, DB, DA), seen "from their other end".  Every row is therefore put into a canonical orientation (smaller
+// chromosome number first: its A and B sides swapped when needed); in that orientation two rows interact exactly when
+// their chromosome pair and strands are equal, the take-over tests are the same on both sides, and the recurrence, the
+// class split and the kernels are those of the intra-chromosomal case with a simpler predicate.
+PGRP_HD PgRpIv pg_rp_swap_sides(const PgRpIv &v)
+{
+   PgRpIv r;
+   r.a = v.b; r.a1 = v.b1; r.b = v.a; r.b1 = v.a1;
+   return r;
+}
+PGRP_HD bool pg_rp_applicable_inter(const PgRpIv &f, const PgRpIv &s, uint8_t da, uint8_t db)
+{
+   if (!(pg_rp_takes_a(f, s, da) || pg_rp_takes_b(f, s, db))) return false;
+   return !(s.a1 - s.a > 10000u || s.b1 - s.b > 10000u);   // ProcessSameChromosomeSameStrand's guard, src/bddata.cpp:301-305
+}
+PGRP_HD void pg_rp_finish_inter(const PgRpIv &v, PgRpCluster &o, uint32_t index)   // no + ReadLength pass, no Visited mark
+{
+   o.pos_a = v.a; o.pos_a1 = v.a1; o.pos_b = v.b; o.pos_b1 = v.b1;
+   o.visited = 0;
+   o.report = 0;
+   o.n_identical = 0;
+   o.merged_into = index;
+   o.pad = 0;
+}
+PGRP_HD bool pg_rp_same_event_inter(const PgRpCluster &x, const PgRp &xi, int32_t xa, int32_t xb, const PgRpCluster &y, const PgRp &yi, int32_t ya,
+                                    int32_t yb)
+{
+   return xa == ya && xb == yb && x.pos_a == y.pos_a && x.pos_b == y.pos_b && xi.da == yi.da && xi.db == yi.db;
+}
+
 #ifdef __CUDACC__
 #define PG_RP_THREADS 1024
 
@@ -342,6 +374,142 @@ __global__ void pg_rp_report_kernel(int n, PgRpCluster *__restrict__ st, const u
       } else if (i <= n - 2) {
          o.n_identical = n_identical[i];
          if (counters[0] == 1u || (uint32_t)i != counters[1]) o.report = o.n_identical >= 5u ? 1 : 0;   // the last good row keeps its Report
+      }
+   }
+   st[i] = o;
+}
+// ---- inter-chromosomal kernels ------------------------------------------------------------------------------------
+// every row: InitializeA1B1 only (rows that share a class with nobody, and the default for the rest)
+__global__ void pg_rp_inter_single_kernel(int n, const PgRp *__restrict__ in, PgRpCluster *__restrict__ out)
+{
+   const int i = blockIdx.x * blockDim.x + threadIdx.x;
+   if (i >= n) return;
+   PgRpCluster o;
+   pg_rp_finish_inter(pg_rp_init(in[i]), o, (uint32_t)i);
+   out[i] = o;
+}
+
+// One warp per class, canonical orientation (flip[row] = the row's sides are swapped in it).  last_row: the global index
+// that ModifyRP_InterChr's outer loop never reaches (src/bddata.cpp:456).
+__global__ void __launch_bounds__(256) pg_rp_modify_inter_warp_kernel(const PgRp *__restrict__ in, const uint8_t *__restrict__ flip,
+                                                                      const uint32_t *__restrict__ group_rows, const uint32_t *__restrict__ group_off,
+                                                                      uint32_t n_groups, uint32_t last_row, uint4 *__restrict__ scratch,
+                                                                      PgRpCluster *__restrict__ out)
+{
+   const uint32_t g = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31u;
+   if (g >= n_groups) return;
+   const uint32_t g0 = group_off[g], ng = group_off[g + 1] - g0;
+   const uint32_t *rows = group_rows + g0;
+   uint4 *w = scratch + g0;
+   const bool f0 = flip[rows[0]] != 0;
+   const uint8_t da = f0 ? in[rows[0]].db : in[rows[0]].da, db = f0 ? in[rows[0]].da : in[rows[0]].db;   // the class's strands, canonical
+   for (uint32_t k = lane; k < ng; k += 32u) {
+      PgRpIv v = pg_rp_init(in[rows[k]]);
+      if (flip[rows[k]]) v = pg_rp_swap_sides(v);
+      w[k] = make_uint4(v.a, v.a1, v.b, v.b1);
+   }
+   __syncwarp();
+   for (uint32_t first = 0; first < ng; first++) {
+      if (rows[first] == last_row) continue;
+      const uint4 q = w[first];
+      PgRpIv f = {q.x, q.y, q.z, q.w};
+      bool changed = false;
+      for (uint32_t cursor = 0; cursor < ng;) {
+         const uint32_t j = cursor + lane;
+         bool app = false;
+         if (j < ng) {
+            const uint4 t = w[j];
+            const PgRpIv s = {t.x, t.y, t.z, t.w};
+            app = pg_rp_applicable_inter(f, s, da, db);
+         }
+         const uint32_t m = __ballot_sync(0xFFFFFFFFu, app);
+         if (!m) {
+            cursor += 32u;
+            continue;
+         }
+         const uint32_t jm = cursor + (uint32_t)__ffs(m) - 1u;
+         const uint4 t = w[jm];
+         const PgRpIv s = {t.x, t.y, t.z, t.w};
+         pg_rp_apply(f, s, da, db);
+         changed = true;
+         cursor = jm + 1u;
+      }
+      if (changed) {
+         if (lane == 0) w[first] = make_uint4(f.a, f.a1, f.b, f.b1);
+         __syncwarp();
+      }
+   }
+   __syncwarp();
+   for (uint32_t k = lane; k < ng; k += 32u) {
+      const uint4 t = w[k];
+      PgRpIv v = {t.x, t.y, t.z, t.w};
+      if (flip[rows[k]]) v = pg_rp_swap_sides(v);
+      PgRpCluster o;
+      pg_rp_finish_inter(v, o, rows[k]);
+      out[rows[k]] = o;
+   }
+}
+
+// Summarize_InterChr: keys over (ChrNameA, ChrNameB, PosA, PosB, DA, DB); NumberOfIdentical counts the *other* rows
+__global__ void pg_rp_inter_key_kernel(int n, const PgRp *__restrict__ in, const int32_t *__restrict__ chr_a, const int32_t *__restrict__ chr_b,
+                                       const PgRpCluster *__restrict__ st, uint64_t *__restrict__ keys)
+{
+   const int i = blockIdx.x * blockDim.x + threadIdx.x;
+   if (i >= n) return;
+   const PgRpCluster o = st[i];
+   uint64_t h = pg_rp_mix(0x243F6A8885A308D3ull, (uint64_t)o.pos_a << 32 | o.pos_b);
+   h = pg_rp_mix(h, (uint64_t)(uint32_t)chr_a[i] << 32 | (uint32_t)chr_b[i]);
+   h = pg_rp_mix(h, (uint64_t)in[i].da << 8 | in[i].db);
+   keys[i] = o.visited ? ~(uint64_t)i : (h & 0x7FFFFFFFFFFFFFFFull);
+}
+
+__global__ void __launch_bounds__(256) pg_rp_inter_group_kernel(int n, const PgRp *__restrict__ in, const int32_t *__restrict__ chr_a,
+                                                                const int32_t *__restrict__ chr_b, const PgRpCluster *__restrict__ st,
+                                                                const uint64_t *__restrict__ keys, uint32_t *__restrict__ merged_into,
+                                                                uint32_t *__restrict__ n_identical)
+{
+   const int i = (int)((blockIdx.x * blockDim.x + threadIdx.x) >> 5), lane = threadIdx.x & 31;
+   if (i >= n) return;
+   const PgRpCluster me = st[i];
+   const PgRp mi = in[i];
+   const int32_t ma = chr_a[i], mb = chr_b[i];
+   const uint64_t mykey = keys[i];
+   uint32_t rep = (uint32_t)i;
+   if (!me.visited) {
+      for (int c0 = 0; c0 < i; c0 += 32) {
+         const int j = c0 + lane;
+         bool eq = j < i && keys[j] == mykey;
+         if (eq) {
+            const PgRpCluster o = st[j];
+            eq = !o.visited && pg_rp_same_event_inter(me, mi, ma, mb, o, in[j], chr_a[j], chr_b[j]);
+         }
+         const uint32_t m = __ballot_sync(0xFFFFFFFFu, eq);
+         if (m) {
+            rep = (uint32_t)(c0 + __ffs(m) - 1);
+            break;
+         }
+      }
+   }
+   if (lane == 0) {
+      merged_into[i] = rep;
+      if (!me.visited && rep != (uint32_t)i) atomicAdd(&n_identical[rep], 1u);   // the first row itself is not counted
+   }
+}
+
+__global__ void pg_rp_inter_report_kernel(int n, PgRpCluster *__restrict__ st, const uint32_t *__restrict__ merged_into,
+                                          const uint32_t *__restrict__ n_identical)
+{
+   const int i = blockIdx.x * blockDim.x + threadIdx.x;
+   if (i >= n) return;
+   PgRpCluster o = st[i];
+   if (!o.visited) {
+      const uint32_t rep = merged_into[i];
+      if (rep != (uint32_t)i) {
+         o.visited = 1;
+         o.merged_into = rep;
+      } else if (i <= n - 2) {                 // the outer loop stops before the last row, src/bddata.cpp:585
+         o.n_identical = n_identical[i];
+         o.report = o.n_identical >= 5u ? 1 : 0;
       }
    }
    st[i] = o;

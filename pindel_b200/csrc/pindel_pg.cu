@@ -403,7 +403,7 @@ struct pg_ctx {
    uint64_t bx_launches = 0;
    float bx_last_ms = 0.f;
    // read-pair clustering (pg_rp_modify / pg_rp_summarize)
-   DevBuf rp_in, rp_out, rp_rows, rp_off, rp_scratch, rp_merged, rp_nid, rp_counters, rp_keys;
+   DevBuf rp_in, rp_out, rp_rows, rp_off, rp_scratch, rp_merged, rp_nid, rp_counters, rp_keys, rp_flip, rp_chr;
    uint64_t rp_launches = 0;
    uint32_t rp_classes_small = 0, rp_classes_big = 0, rp_rows_in_classes = 0;   // of the last pg_rp_modify
    float rp_last_ms = 0.f;    // scan + order kernels
@@ -561,7 +561,7 @@ void pg_destroy(pg_ctx *ctx)
                        &ctx->sv_runs, &ctx->sv_records, &ctx->sv_params, &ctx->sv_counters,
                        &ctx->sv_counts, &ctx->sv_offsets, &ctx->sv_blocksums, &ctx->sv_ordered, &ctx->sv_perm, &ctx->sv_close_off,
                        &ctx->sv_close_runs, &ctx->rp_in, &ctx->rp_out, &ctx->rp_rows, &ctx->rp_off, &ctx->rp_scratch, &ctx->rp_merged,
-                       &ctx->rp_nid, &ctx->rp_counters, &ctx->rp_keys, &ctx->bz_file, &ctx->bz_blocks, &ctx->bz_out, &ctx->bz_status,
+                       &ctx->rp_nid, &ctx->rp_counters, &ctx->rp_keys, &ctx->rp_flip, &ctx->rp_chr, &ctx->bz_file, &ctx->bz_blocks, &ctx->bz_out, &ctx->bz_status,
                        &ctx->bm_info, &ctx->bm_starts, &ctx->bm_counts, &ctx->bm_landing, &ctx->bm_base, &ctx->bm_recs,
                        &ctx->bd_cls, &ctx->bd_off, &ctx->bd_sums, &ctx->bd_rows, &ctx->bd_src, &ctx->bd_counters,
                        &ctx->bx_off, &ctx->bx_keys, &ctx->bx_order, &ctx->bx_non};
@@ -1634,6 +1634,83 @@ int pg_rp_summarize(pg_ctx *ctx, int32_t n, const pg_rp *in, pg_rp_cluster *inou
                                                    (const uint64_t *)ctx->rp_keys.p, (uint32_t *)ctx->rp_merged.p, (uint32_t *)ctx->rp_nid.p, (uint32_t *)ctx->rp_counters.p);
    pg_rp_report_kernel<<<(n + 255) / 256, 256, 0, st>>>(n, (PgRpCluster *)ctx->rp_out.p, (const uint32_t *)ctx->rp_merged.p,
                                                        (const uint32_t *)ctx->rp_nid.p, (const uint32_t *)ctx->rp_counters.p);
+   CU(cudaGetLastError());
+   CU(cudaEventRecord(ctx->sv_ev1, st));
+   ctx->rp_launches += 3;
+   CU(cudaMemcpyAsync(inout, ctx->rp_out.p, sizeof(PgRpCluster) * (size_t)n, cudaMemcpyDeviceToHost, st));
+   CU(cudaStreamSynchronize(st));
+   CU(cudaEventElapsedTime(&ctx->rp_last_ms, ctx->sv_ev0, ctx->sv_ev1));
+   return PG_OK;
+}
+
+int pg_rp_modify_interchr(pg_ctx *ctx, int32_t n, const pg_rp *in, const int32_t *chr_a, const int32_t *chr_b, pg_rp_cluster *out)
+{
+   if (!ctx || n < 0 || (n > 0 && (!in || !out || !chr_a || !chr_b))) return fail(ctx, PG_ERR_ARG, "pg_rp_modify_interchr: bad arguments");
+   if (n == 0) return PG_OK;
+   CU(cudaSetDevice(ctx->device));
+   cudaStream_t st = ctx->stream;
+   std::vector<uint8_t> flip;
+   std::vector<uint32_t> rows, off;
+   pg_rp_classes_interchr(n, reinterpret_cast<const PgRp *>(in), chr_a, chr_b, flip, rows, off);
+   const uint32_t n_classes = (uint32_t)off.size() - 1;
+   int rc;
+   if ((rc = ensure(ctx, ctx->rp_in, sizeof(PgRp) * (size_t)n)) != PG_OK) return rc;
+   if ((rc = ensure(ctx, ctx->rp_out, sizeof(PgRpCluster) * (size_t)n)) != PG_OK) return rc;
+   if ((rc = ensure(ctx, ctx->rp_flip, (size_t)n)) != PG_OK) return rc;
+   if ((rc = ensure(ctx, ctx->rp_rows, sizeof(uint32_t) * (rows.size() + 1))) != PG_OK) return rc;
+   if ((rc = ensure(ctx, ctx->rp_off, sizeof(uint32_t) * ((size_t)n_classes + 1))) != PG_OK) return rc;
+   if ((rc = ensure(ctx, ctx->rp_scratch, sizeof(uint4) * (rows.size() + 1))) != PG_OK) return rc;
+   CU(cudaMemcpyAsync(ctx->rp_in.p, in, sizeof(PgRp) * (size_t)n, cudaMemcpyHostToDevice, st));
+   CU(cudaMemcpyAsync(ctx->rp_flip.p, flip.data(), (size_t)n, cudaMemcpyHostToDevice, st));
+   if (!rows.empty()) CU(cudaMemcpyAsync(ctx->rp_rows.p, rows.data(), sizeof(uint32_t) * rows.size(), cudaMemcpyHostToDevice, st));
+   CU(cudaMemcpyAsync(ctx->rp_off.p, off.data(), sizeof(uint32_t) * ((size_t)n_classes + 1), cudaMemcpyHostToDevice, st));
+   if (!ctx->sv_ev0) { CU(cudaEventCreate(&ctx->sv_ev0)); CU(cudaEventCreate(&ctx->sv_ev1)); }
+   CU(cudaEventRecord(ctx->sv_ev0, st));
+   pg_rp_inter_single_kernel<<<(n + 255) / 256, 256, 0, st>>>(n, (const PgRp *)ctx->rp_in.p, (PgRpCluster *)ctx->rp_out.p);
+   ctx->rp_launches++;
+   if (n_classes) {
+      pg_rp_modify_inter_warp_kernel<<<(n_classes + 7) / 8, 256, 0, st>>>((const PgRp *)ctx->rp_in.p, (const uint8_t *)ctx->rp_flip.p,
+                                                                         (const uint32_t *)ctx->rp_rows.p, (const uint32_t *)ctx->rp_off.p, n_classes,
+                                                                         (uint32_t)(n - 1), (uint4 *)ctx->rp_scratch.p, (PgRpCluster *)ctx->rp_out.p);
+      ctx->rp_launches++;
+   }
+   CU(cudaGetLastError());
+   CU(cudaEventRecord(ctx->sv_ev1, st));
+   ctx->rp_classes_small = n_classes;
+   ctx->rp_classes_big = 0;
+   ctx->rp_rows_in_classes = (uint32_t)rows.size();
+   CU(cudaMemcpyAsync(out, ctx->rp_out.p, sizeof(PgRpCluster) * (size_t)n, cudaMemcpyDeviceToHost, st));
+   CU(cudaStreamSynchronize(st));
+   CU(cudaEventElapsedTime(&ctx->rp_last_ms, ctx->sv_ev0, ctx->sv_ev1));
+   return PG_OK;
+}
+
+int pg_rp_summarize_interchr(pg_ctx *ctx, int32_t n, const pg_rp *in, const int32_t *chr_a, const int32_t *chr_b, pg_rp_cluster *inout)
+{
+   if (!ctx || n < 0 || (n > 0 && (!in || !inout || !chr_a || !chr_b))) return fail(ctx, PG_ERR_ARG, "pg_rp_summarize_interchr: bad arguments");
+   if (n == 0) return PG_OK;
+   CU(cudaSetDevice(ctx->device));
+   cudaStream_t st = ctx->stream;
+   int rc;
+   if ((rc = ensure(ctx, ctx->rp_in, sizeof(PgRp) * (size_t)n)) != PG_OK) return rc;
+   if ((rc = ensure(ctx, ctx->rp_out, sizeof(PgRpCluster) * (size_t)n)) != PG_OK) return rc;
+   if ((rc = ensure(ctx, ctx->rp_chr, sizeof(int32_t) * 2 * (size_t)n)) != PG_OK) return rc;
+   if ((rc = ensure(ctx, ctx->rp_merged, sizeof(uint32_t) * (size_t)n)) != PG_OK) return rc;
+   if ((rc = ensure(ctx, ctx->rp_nid, sizeof(uint32_t) * (size_t)n)) != PG_OK) return rc;
+   if ((rc = ensure(ctx, ctx->rp_keys, sizeof(uint64_t) * (size_t)n)) != PG_OK) return rc;
+   int32_t *ca = (int32_t *)ctx->rp_chr.p, *cb = ca + n;
+   CU(cudaMemcpyAsync(ctx->rp_in.p, in, sizeof(PgRp) * (size_t)n, cudaMemcpyHostToDevice, st));
+   CU(cudaMemcpyAsync(ctx->rp_out.p, inout, sizeof(PgRpCluster) * (size_t)n, cudaMemcpyHostToDevice, st));
+   CU(cudaMemcpyAsync(ca, chr_a, sizeof(int32_t) * (size_t)n, cudaMemcpyHostToDevice, st));
+   CU(cudaMemcpyAsync(cb, chr_b, sizeof(int32_t) * (size_t)n, cudaMemcpyHostToDevice, st));
+   CU(cudaMemsetAsync(ctx->rp_nid.p, 0, sizeof(uint32_t) * (size_t)n, st));
+   if (!ctx->sv_ev0) { CU(cudaEventCreate(&ctx->sv_ev0)); CU(cudaEventCreate(&ctx->sv_ev1)); }
+   CU(cudaEventRecord(ctx->sv_ev0, st));
+   pg_rp_inter_key_kernel<<<(n + 255) / 256, 256, 0, st>>>(n, (const PgRp *)ctx->rp_in.p, ca, cb, (const PgRpCluster *)ctx->rp_out.p, (uint64_t *)ctx->rp_keys.p);
+   pg_rp_inter_group_kernel<<<(n + 7) / 8, 256, 0, st>>>(n, (const PgRp *)ctx->rp_in.p, ca, cb, (const PgRpCluster *)ctx->rp_out.p,
+                                                         (const uint64_t *)ctx->rp_keys.p, (uint32_t *)ctx->rp_merged.p, (uint32_t *)ctx->rp_nid.p);
+   pg_rp_inter_report_kernel<<<(n + 255) / 256, 256, 0, st>>>(n, (PgRpCluster *)ctx->rp_out.p, (const uint32_t *)ctx->rp_merged.p,
+                                                             (const uint32_t *)ctx->rp_nid.p);
    CU(cudaGetLastError());
    CU(cudaEventRecord(ctx->sv_ev1, st));
    ctx->rp_launches += 3;

@@ -288,3 +288,33 @@ def make_bam_like_bytes(n: int, seed: int) -> bytes:
     q[noise] = rng.integers(2, 41, int(noise.sum()), dtype=np.uint8)
     rec[:, 100:200] = q + 33
     return rec.tobytes()[:n]
+
+
+def make_interchr_pairs(n_events: int, seed: int, n_chr: int = 3, max_support: int = 30, background: int = 0):
+    """Synthetic Reads_RP_Discovery_InterChr (row N2, inter-chromosomal variants): pairs whose mates lie on different
+    chromosomes, stored from the read's side (ChrNameA = the read's chromosome), so one translocation shows up in both
+    orientations -- (X, Y) rows from X's window and (Y, X) rows from Y's.  -> (rows RP_DT layout, chr_a, chr_b)"""
+    rng = np.random.default_rng(seed)
+    rows, ca, cb = [], [], []
+    for _ in range(n_events):
+        rl, isz = ((100, 250), (150, 500))[int(rng.integers(0, 2))]
+        x, y = rng.choice(n_chr, 2, replace=False)
+        px, py = int(rng.integers(10_000, 5_000_000)), int(rng.integers(10_000, 5_000_000))
+        dx, dy = (b"+-", b"-+", b"++", b"--")[int(rng.integers(0, 4))]
+        for _ in range(int(rng.integers(1, max_support + 1))):
+            ax, ay = px + int(rng.integers(-isz, isz)), py + int(rng.integers(-isz, isz))
+            for _ in range(2 if rng.random() < 0.5 else 1):          # exact copies (duplicates / re-reads)
+                if rng.random() < 0.5:
+                    rows.append((ax, ay, isz, rl, dx, dy)); ca.append(int(x)); cb.append(int(y))
+                else:
+                    rows.append((ay, ax, isz, rl, dy, dx)); ca.append(int(y)); cb.append(int(x))
+    for _ in range(background):
+        rl, isz = ((100, 250), (150, 500))[int(rng.integers(0, 2))]
+        x, y = rng.choice(n_chr, 2, replace=False)
+        d = (b"+-", b"-+", b"++", b"--")[int(rng.integers(0, 4))]
+        rows.append((int(rng.integers(10_000, 5_000_000)), int(rng.integers(10_000, 5_000_000)), isz, rl, d[0], d[1])); ca.append(int(x)); cb.append(int(y))
+    out = np.zeros(len(rows), dtype=[("pos_a", "<u4"), ("pos_b", "<u4"), ("insert_size", "<u4"), ("read_length", "<i2"), ("da", "u1"), ("db", "u1")])
+    for k, r in enumerate(rows):
+        out[k] = r
+    perm = rng.permutation(len(rows))
+    return out[perm], np.array(ca, dtype=np.int32)[perm], np.array(cb, dtype=np.int32)[perm]

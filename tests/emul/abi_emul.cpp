@@ -214,6 +214,18 @@ int pg_rp_summarize(pg_ctx *ctx, int32_t n, const pg_rp *in, pg_rp_cluster *inou
    ctx->rp_launches++;
    return PG_OK;
 }
+int pg_rp_modify_interchr(pg_ctx *ctx, int32_t n, const pg_rp *in, const int32_t *chr_a, const int32_t *chr_b, pg_rp_cluster *out)
+{
+   rpemu_modify_interchr(n, (const PgRp *)in, chr_a, chr_b, (PgRpCluster *)out);
+   ctx->rp_launches++;
+   return PG_OK;
+}
+int pg_rp_summarize_interchr(pg_ctx *ctx, int32_t n, const pg_rp *in, const int32_t *chr_a, const int32_t *chr_b, pg_rp_cluster *inout)
+{
+   rpemu_summarize_interchr(n, (const PgRp *)in, chr_a, chr_b, (PgRpCluster *)inout);
+   ctx->rp_launches++;
+   return PG_OK;
+}
 uint64_t pg_rp_launches(pg_ctx *ctx) { return ctx ? ctx->rp_launches : 0; }
 int pg_box_sort(pg_ctx *ctx, uint32_t n_boxes, const uint32_t *box_off, const pg_sort_key *keys, uint32_t *order, uint8_t *nonunique)
 {

@@ -84,4 +84,55 @@ void rpemu_summarize(int n, const PgRp *in, PgRpCluster *st)
       }
    }
 }
+
+// the inter-chromosomal variants in the kernels' formulation (pg_rp_modify_inter_warp_kernel, pg_rp_inter_*_kernel)
+void rpemu_modify_interchr(int n, const PgRp *in, const int32_t *chr_a, const int32_t *chr_b, PgRpCluster *out)
+{
+   std::vector<uint8_t> flip;
+   std::vector<uint32_t> all, off;
+   pg_rp_classes_interchr(n, in, chr_a, chr_b, flip, all, off);
+   for (int i = 0; i < n; i++) pg_rp_finish_inter(pg_rp_init(in[i]), out[i], (uint32_t)i);
+   const uint32_t last_row = (uint32_t)(n - 1);
+   for (size_t g = 0; g + 1 < off.size(); g++) {
+      const uint32_t *rows = all.data() + off[g];
+      const uint32_t ng = off[g + 1] - off[g];
+      const bool f0 = flip[rows[0]] != 0;
+      const uint8_t da = f0 ? in[rows[0]].db : in[rows[0]].da, db = f0 ? in[rows[0]].da : in[rows[0]].db;
+      std::vector<PgRpIv> w(ng);
+      for (uint32_t k = 0; k < ng; k++) { w[k] = pg_rp_init(in[rows[k]]); if (flip[rows[k]]) w[k] = pg_rp_swap_sides(w[k]); }
+      for (uint32_t first = 0; first < ng; first++) {
+         if (rows[first] == last_row) continue;
+         PgRpIv f = w[first];
+         for (uint32_t cursor = 0; cursor < ng;) {
+            uint32_t jm = ng;
+            for (uint32_t j = cursor; j < ng; j++)
+               if (pg_rp_applicable_inter(f, w[j], da, db)) { jm = j; break; }
+            if (jm == ng) break;
+            pg_rp_apply(f, w[jm], da, db);
+            cursor = jm + 1;
+         }
+         w[first] = f;
+      }
+      for (uint32_t k = 0; k < ng; k++) pg_rp_finish_inter(flip[rows[k]] ? pg_rp_swap_sides(w[k]) : w[k], out[rows[k]], rows[k]);
+   }
+}
+
+void rpemu_summarize_interchr(int n, const PgRp *in, const int32_t *chr_a, const int32_t *chr_b, PgRpCluster *st)
+{
+   std::vector<uint32_t> merged((size_t)n), nid((size_t)n, 0);
+   for (int i = 0; i < n; i++) {
+      uint32_t rep = (uint32_t)i;
+      if (!st[i].visited)
+         for (int j = 0; j < i; j++)
+            if (!st[j].visited && pg_rp_same_event_inter(st[i], in[i], chr_a[i], chr_b[i], st[j], in[j], chr_a[j], chr_b[j])) { rep = (uint32_t)j; break; }
+      merged[i] = rep;
+      if (!st[i].visited && rep != (uint32_t)i) nid[rep]++;
+   }
+   for (int i = 0; i < n; i++) {
+      PgRpCluster &o = st[i];
+      if (o.visited) continue;
+      if (merged[i] != (uint32_t)i) { o.visited = 1; o.merged_into = merged[i]; }
+      else if (i <= n - 2) { o.n_identical = nid[i]; o.report = o.n_identical >= 5u ? 1 : 0; }
+   }
+}
 }

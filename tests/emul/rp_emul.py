@@ -38,3 +38,14 @@ def class_stats(lib, rows):
     st = np.zeros(3, dtype=np.uint32)
     lib.rpemu_class_stats(int(rows.size), rows.ctypes.data_as(C.c_void_p), st.ctypes.data_as(C.c_void_p))
     return tuple(int(x) for x in st)
+
+
+def cluster_interchr(lib, rows, chr_a, chr_b):
+    rows = np.ascontiguousarray(rows, dtype=rporacle.RP_DT)
+    ca, cb = np.ascontiguousarray(chr_a, dtype=np.int32), np.ascontiguousarray(chr_b, dtype=np.int32)
+    out = np.zeros(rows.size, dtype=rporacle.CLUSTER_DT)
+    vp = lambda a: a.ctypes.data_as(C.c_void_p)
+    lib.rpemu_modify_interchr(int(rows.size), vp(rows), vp(ca), vp(cb), vp(out))
+    mod = out.copy()
+    lib.rpemu_summarize_interchr(int(rows.size), vp(rows), vp(ca), vp(cb), vp(out))
+    return mod, out

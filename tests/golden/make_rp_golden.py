@@ -25,6 +25,14 @@ CASES = {
 }
 
 
+# inter-chromosomal variants: name -> make_interchr_pairs arguments
+INTER_CASES = {
+    "inter_small": dict(n_events=60, seed=201, background=40),
+    "inter_two_chr": dict(n_events=120, seed=202, n_chr=2, max_support=50),
+    "inter_many_chr": dict(n_events=150, seed=203, n_chr=6, background=200),
+}
+
+
 def rows_from_table(table):
     from oracle import rporacle
     rows = np.zeros(table.shape[0], dtype=rporacle.RP_DT)
@@ -43,6 +51,12 @@ def main():
                             tag_counts=np.array([len(t) for t in tags], np.int32),
                             tag_values=np.array([x for t in tags for x in t], np.int32))
         print(name, len(rows), "rows,", int(table[:, 12].sum()), "reported,", int(table[:, 11].sum()), "visited, %.3f s" % sum(secs))
+    for name, kw in INTER_CASES.items():
+        rows, ca, cb = synth.make_interchr_pairs(**kw)
+        table, tags, sa, sb = refhook.rp_cluster_interchr(rows, ca, cb)
+        np.savez_compressed(os.path.join(HERE, "rp_%s.npz" % name), table=table.astype(np.int64), chr_a=sa, chr_b=sb,
+                            tag_counts=np.array([len(t) for t in tags], np.int32), tag_values=np.array([x for t in tags for x in t], np.int32))
+        print(name, len(rows), "rows,", int(table[:, 12].sum()), "reported,", int(table[:, 11].sum()), "visited")
 
 
 if __name__ == "__main__":

@@ -63,3 +63,26 @@ def test_small_and_empty_inputs(pg):
     odd = rows.copy()
     odd["da"] = ord("k")          # RP_READ's default strand (src/pindel.h:221): no interval test can pass
     assert pg.rp_modify(odd).tobytes() == rporacle.modify(odd).tobytes()
+
+
+@pytest.mark.parametrize("name", list(G.INTER_CASES))
+def test_interchr_matches_reference_dumps(pg, name):
+    z = np.load(os.path.join(os.path.dirname(__file__), "golden", "rp_%s.npz" % name))
+    t = z["table"]
+    rows = G.rows_from_table(t)
+    before = pg.rp_launches
+    _, got = pg.rp_cluster_interchr(rows, z["chr_a"], z["chr_b"])
+    assert pg.rp_launches > before
+    for col, key in ((7, "pos_a"), (8, "pos_a1"), (9, "pos_b"), (10, "pos_b1"), (11, "visited"), (12, "report"), (13, "n_identical")):
+        assert np.array_equal(got[key].astype(np.int64), t[:, col]), key
+
+
+def test_interchr_matches_oracle_stage_by_stage(pg):
+    rows, ca, cb = synth.make_interchr_pairs(400, 61, n_chr=4, max_support=60, background=300)
+    order = rp.compare2rp_order(rows)
+    rows, ca, cb = rows[order], ca[order], cb[order]
+    mod, fin = pg.rp_cluster_interchr(rows, ca, cb)
+    omod, ofin = rporacle.cluster_interchr(rows, ca, cb)
+    assert mod.tobytes() == omod.tobytes() and fin.tobytes() == ofin.tobytes()
+    one = pg.rp_cluster_interchr(rows[:1], ca[:1], cb[:1])
+    assert one[1].tobytes() == rporacle.cluster_interchr(rows[:1], ca[:1], cb[:1])[1].tobytes()

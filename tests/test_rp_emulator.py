@@ -35,3 +35,22 @@ def test_program_matches_oracle_stage_by_stage(lib, seed):
     exp_mod = rporacle.modify(rows)
     assert mod.tobytes() == exp_mod.tobytes()
     assert fin.tobytes() == rporacle.summarize(rows, exp_mod).tobytes()
+
+
+@pytest.mark.parametrize("name", list(G.INTER_CASES))
+def test_interchr_program_and_oracle_match_reference_dumps(lib, name):
+    """ModifyRP_InterChr + Summarize_InterChr: the kernels' formulation (canonical orientation, class split, first applicable
+    row) and the C restatement against the reference's own functions."""
+    z = np.load(os.path.join(os.path.dirname(__file__), "golden", "rp_%s.npz" % name))
+    t = z["table"]
+    rows = G.rows_from_table(t)
+    for what, (_, got) in (("program", rp_emul.cluster_interchr(lib, rows, z["chr_a"], z["chr_b"])),
+                           ("oracle", rporacle.cluster_interchr(rows, z["chr_a"], z["chr_b"]))):
+        for col, key in ((7, "pos_a"), (8, "pos_a1"), (9, "pos_b"), (10, "pos_b1"), (11, "visited"), (12, "report"), (13, "n_identical")):
+            assert np.array_equal(got[key].astype(np.int64), t[:, col]), (what, key)
+        tags, p = [], 0
+        for c in z["tag_counts"]:
+            tags.append(z["tag_values"][p:p + c].tolist())
+            p += c
+        holder = {x: i for i, tg in enumerate(tags) for x in tg}
+        assert all(holder[int(t[i, 0])] == int(got["merged_into"][i]) for i in range(rows.size)), (what, "tags")
