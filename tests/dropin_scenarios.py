@@ -75,3 +75,70 @@ def sim_prefix_bam(demo, tmp_path, env):
     # row N2, first half: the discordant pairs came from pg_bam_rp_discovery (7928 in this fixture, as the reference finds)
     assert int(m.group(3)) == (0 if env.get("PG_BRIDGE_ZLIB") else 7928), p.stderr[-300:]
     return p
+
+
+def interchr_live(demo, tmp_path, env):
+    """A scenario none of the committed fixtures has: translocation-like clusters of pairs between two chromosomes with
+    `-I true` (inter-chromosomal events are off by default, src/fn_parameters.cpp:163-166).  No golden files: the inputs are
+    generated here from seeds and the pure reference binary (oracle/_ref/pindel_ref, which travels with the snapshot) runs
+    beside the drop-in binary.  Exercises the inter-chromosomal list of the pair discovery and ModifyRP_InterChr /
+    Summarize_InterChr through the bridge."""
+    import struct
+    import numpy as np
+    from oracle import refhook
+    from pindel_b200 import bam, bgzf
+    ref_bin = os.path.join(ROOT, "oracle", "_ref", "pindel_ref")
+    rng = np.random.default_rng(7)
+    refs = (("chrA", 300_000), ("chrB", 250_000))
+    seqs = [rng.choice(np.frombuffer(b"ACGT", dtype=np.uint8), l) for _, l in refs]
+    fa = str(tmp_path / "g.fa")
+    refhook.write_fasta(fa, [(n, s) for (n, _), s in zip(refs, seqs)])
+    off, fai = 0, []
+    for n, l in refs:                                          # samtools faidx layout: name, length, offset, 60 bases / 61 bytes per line
+        off += len(n) + 2
+        fai.append("%s\t%d\t%d\t60\t61\n" % (n, l, off))
+        off += l + (l + 59) // 60
+    (tmp_path / "g.fa.fai").write_text("".join(fai))
+    recs, k = [], 0
+    code = {65: 1, 67: 2, 71: 4, 84: 8}
+
+    def add(tid, pos, flag, mtid, mpos, tlen):
+        rl = 100
+        c = np.array([code[int(x)] for x in seqs[tid][pos:pos + rl]], dtype=np.uint8)
+        packed = (c[0::2] << 4 | c[1::2]).astype(np.uint8).tobytes()
+        nm = b"pair_%d\0" % k
+        body = struct.pack("<iiBBHHHiiii", tid, pos, len(nm), 60, 4680, 1, flag, rl, mtid, mpos, tlen) + nm + struct.pack("<I", rl << 4) + packed + \
+            bytes([30] * rl) + b"NMC\x00"
+        recs.append((tid, pos, struct.pack("<I", len(body)) + body))
+
+    for ev in range(12):
+        pa, pb = int(rng.integers(20_000, 280_000)), int(rng.integers(20_000, 230_000))
+        sa, sb = [(0, 0), (16, 0), (0, 16), (16, 16)][ev % 4]
+        for _ in range(int(rng.integers(15, 40))):
+            xa, xb = pa + int(rng.integers(-150, 150)), pb + int(rng.integers(-150, 150))
+            for _ in range(int(rng.integers(1, 4))):          # duplicates: Summarize_InterChr wants identical rows
+                add(0, xa, 1 | 64 | sa | (32 if sb else 0), 1, xb, 0)
+                add(1, xb, 1 | 128 | sb | (32 if sa else 0), 0, xa, 0)
+                k += 1
+    for _ in range(3000):                                     # ordinary pairs around them
+        tid = int(rng.integers(0, 2))
+        p = int(rng.integers(1000, refs[tid][1] - 2000))
+        add(tid, p, 1 | 64 | 32 | 2, tid, p + 400, 500)
+        add(tid, p + 400, 1 | 128 | 16 | 2, tid, p, -500)
+        k += 1
+    recs.sort(key=lambda r: (r[0], r[1]))
+    (tmp_path / "x.bam").write_bytes(bgzf.compress(bam.header(list(refs)) + b"".join(r[2] for r in recs)))
+    (tmp_path / "x.bam.bai").write_bytes(b"BAI\x01\x00\x00\x00\x00")
+    (tmp_path / "conf.txt").write_text("%s\t500\tS1\n" % (tmp_path / "x.bam"))
+    args = ["-f", fa, "-i", str(tmp_path / "conf.txt"), "-c", "ALL", "-T", "1", "-I", "true"]
+    r = subprocess.run([ref_bin] + args + ["-o", str(tmp_path / "ref")], capture_output=True, text=True, timeout=1800)
+    assert r.returncode == 0, r.stdout[-1000:] + r.stderr[-1000:]
+    assert r.stdout.count("adding interchr") >= 10            # the scenario does produce inter-chromosomal events
+    p = subprocess.run([demo] + args + ["-o", str(tmp_path / "got")], capture_output=True, text=True, timeout=1800, env=env)
+    assert p.returncode == 0, p.stdout[-1000:] + p.stderr[-1000:]
+    m = re.search(r"(\d+) read pairs clustered on the device \((\d+) launches\)", p.stderr)
+    assert m and int(m.group(1)) > 1000 and int(m.group(2)) >= 4, p.stderr[-400:]
+    for suf in ("D", "SI", "INV", "TD", "LI", "BP", "RP", "INT_final"):
+        assert (tmp_path / ("got_" + suf)).read_bytes() == (tmp_path / ("ref_" + suf)).read_bytes(), "_%s differs from the reference binary's file" % suf
+    assert (tmp_path / "ref_RP").read_bytes().count(b"\n") >= 20
+    return p

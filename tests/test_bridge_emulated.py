@@ -34,3 +34,11 @@ def test_text_input_scenario_with_the_host_array_classification(tmp_path):
     """pg_classify (everything uploaded again) instead of pg_classify_resident: the path a host takes when the far-end
     batch is no longer on the device; and the reference's own bubblesortReads / markDuplicates instead of pg_box_sort."""
     D.colo_slice(DEMO, tmp_path, dict(os.environ, PG_BRIDGE_NO_RESIDENT="1", PG_BRIDGE_HOST_SORT="1"), unbatched_too=False)
+
+
+REF_BIN = os.path.join(ROOT, "oracle", "_ref", "pindel_ref")
+
+
+@pytest.mark.skipif(not os.path.exists(REF_BIN), reason="oracle/_ref/pindel_ref not built")
+def test_interchromosomal_scenario_against_the_reference_binary(tmp_path):
+    D.interchr_live(DEMO, tmp_path, dict(os.environ))

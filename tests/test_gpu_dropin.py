@@ -29,3 +29,10 @@ def test_reference_host_with_gpu_search_writes_identical_files(tmp_path):
 
 def test_reference_host_bam_input_with_gpu_search(tmp_path):
     D.sim_prefix_bam(DEMO, tmp_path, _env())
+
+
+@pytest.mark.skipif(not os.path.exists(os.path.join(ROOT, "oracle", "_ref", "pindel_ref")), reason="oracle/_ref/pindel_ref not built")
+def test_interchromosomal_scenario_against_the_reference_binary(tmp_path):
+    """-I true on generated inputs, the pure reference binary beside the drop-in: inter-chromosomal pair discovery and
+    ModifyRP_InterChr / Summarize_InterChr on the device."""
+    D.interchr_live(DEMO, tmp_path, _env())
