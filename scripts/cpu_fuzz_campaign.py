@@ -1,6 +1,6 @@
 """scripts/cpu_fuzz_campaign.py -- a longer randomized differential run of the device programs' host builds (tests/emul/)
 against the REFERENCE ITSELF (oracle/_ref/libpindel_ref.so) and zlib, for the stages whose reference functions need no
-initialised genome: read-pair clustering, per-box ordering, BGZF inflate.  Not part of the pytest suite (minutes of CPU);
+initialised genome: read-pair clustering (both variants), per-box ordering, BGZF inflate.  Not part of the pytest suite (minutes of CPU);
 run it after touching pg_rp.cuh / pg_rp_host.h / pg_boxsort.cuh / pg_bgzf.cuh:
     python scripts/cpu_fuzz_campaign.py [--rounds N]"""
 from __future__ import annotations
@@ -44,6 +44,13 @@ def main():
             for x in tg:
                 holder[x] = i
         assert all(holder[int(table[i, 0])] == int(got["merged_into"][i]) for i in range(srt.size)), ("rp tags", r)
+        # the inter-chromosomal variants
+        irows, ica, icb = synth.make_interchr_pairs(int(rng.integers(1, 120)), 6000 + r, n_chr=int(rng.integers(2, 7)),
+                                                    max_support=int(rng.integers(2, 70)), background=int(rng.integers(0, 200)))
+        itable, itags, isa, isb = refhook.rp_cluster_interchr(irows, ica, icb)
+        _, igot = rp_emul.cluster_interchr(rp_lib, rows_from_table(itable), isa, isb)
+        for col, key in ((7, "pos_a"), (8, "pos_a1"), (9, "pos_b"), (10, "pos_b1"), (11, "visited"), (12, "report"), (13, "n_identical")):
+            assert np.array_equal(igot[key].astype(np.int64), itable[:, col]), ("rp interchr", r, key)
         # per-box ordering
         reads, box_off, idx = B.make_boxes(int(rng.integers(1, 120)), 7000 + r, max_reads=int(rng.integers(3, 120)), heavy=int(rng.integers(0, 2)))
         r_idx, r_unique = B.reference_sort_boxes(reads, box_off, idx)
@@ -61,7 +68,7 @@ def main():
                              strategy=int(rng.choice([zlib.Z_DEFAULT_STRATEGY, zlib.Z_FIXED, zlib.Z_HUFFMAN_ONLY, zlib.Z_RLE, zlib.Z_FILTERED])))
         got, status = bgzf_emul.inflate(z_lib, comp)
         assert not status.any() and got == payload, ("bgzf", r, kind)
-        print("round %d ok: %d pairs, %d boxes, %d payload bytes" % (r, rows.size, box_off.size - 1, len(payload)), flush=True)
+        print("round %d ok: %d + %d pairs, %d boxes, %d payload bytes" % (r, rows.size, irows.size, box_off.size - 1, len(payload)), flush=True)
     print("CAMPAIGN-OK")
 
 
