@@ -578,3 +578,58 @@ extern "C" int64_t pgref_rp_cluster_interchr(int n, const uint32_t *pos_a, const
    *out_stream = buf;
    return (int64_t)out.size();
 }
+
+/* Groundwork for the rest of row N3 (the reader's split-read filter): what ReadInBamReads_SR (src/reader.cpp:483-560) hands to
+ * the ReadBuffer for one BAM file and window -- fetch_func_SR's mate pairing (:1099-1151), the predicates isGoodAnchor /
+ * isWeirdRead / isRefRead (:561-690) and build_record_SR / build_record_RefRead (:799-923) -- captured before GetCloseEnd
+ * sees it.  ReadBuffer::addRead is supplied here (this object comes first on the link line, see oracle/Makefile): same
+ * behaviour as src/read_buffer.cpp:104-111, plus the capture.
+ * out: number of candidates, per candidate 7 int32 (FNV-1a of Name, MatchedD, MatchedRelPos, MS, InsertSize, ReadLength, FNV-1a of
+ * UnmatchedSeq), number of RefSupportingReads, per read 3 int32 (Pos, MQ, ReadLength). */
+#include "read_buffer.h"
+static std::vector<SPLIT_READ> *g_capture = NULL;
+void ReadBuffer::addRead(const SPLIT_READ &newRead)
+{
+   if (g_capture) {
+      g_capture->push_back(newRead);
+      return;
+   }
+   if (m_currentsize == m_CAPACITY) flush();
+   m_rawreads.push_back(newRead);
+   m_currentsize++;
+}
+bool ReadInBamReads_SR(const char *bam_path, const std::string &FragName, const std::string *CurrentChrSeq, std::vector<SPLIT_READ> &LeftReads,
+                       std::vector<SPLIT_READ> &OneEndMappedReads, std::vector<REF_READ> &RefSupportingReads, int InsertSize, std::string Tag,
+                       const SearchWindow &window, ReadBuffer &readBuffer, bool verbose);
+extern "C" int64_t pgref_sr_candidates(const char *bam_path, int chr, uint32_t start, uint32_t end, int insert_size, int min_anchor_quality,
+                                       int32_t **out_stream)
+{
+   const Chromosome *c = g_genome.getChr((unsigned)chr);
+   if (c == NULL) return -1;
+   SearchWindow w(c, start, end);
+   std::vector<SPLIT_READ> left, one_end, captured;
+   std::vector<REF_READ> ref_reads;
+   ReadBuffer buffer(50000, left, one_end, c->getSeq());
+   g_capture = &captured;
+   const unsigned saved_quality = userSettings->minimalAnchorQuality;      /* -A: the one setting the filter reads */
+   if (min_anchor_quality >= 0) userSettings->minimalAnchorQuality = (unsigned)min_anchor_quality;
+   const bool ok = ReadInBamReads_SR(bam_path, c->getName(), &c->getSeq(), left, one_end, ref_reads, insert_size, "TAG", w, buffer, false);
+   userSettings->minimalAnchorQuality = saved_quality;
+   g_capture = NULL;
+   if (!ok) return -2;
+   std::vector<int32_t> out;
+   out.push_back((int32_t)captured.size());
+   for (size_t i = 0; i < captured.size(); i++) {
+      const SPLIT_READ &r = captured[i];
+      const int32_t row[7] = {(int32_t)fnv1a(r.Name), r.MatchedD, (int32_t)r.MatchedRelPos, r.MS, r.InsertSize, r.getReadLength(), (int32_t)fnv1a(r.getUnmatchedSeq())};
+      out.insert(out.end(), row, row + 7);
+   }
+   out.push_back((int32_t)ref_reads.size());
+   for (size_t i = 0; i < ref_reads.size(); i++) {
+      out.push_back((int32_t)ref_reads[i].Pos); out.push_back(ref_reads[i].MQ); out.push_back(ref_reads[i].ReadLength);
+   }
+   int32_t *buf = (int32_t *)malloc(out.size() * sizeof(int32_t) + 4);
+   memcpy(buf, out.data(), out.size() * sizeof(int32_t));
+   *out_stream = buf;
+   return (int64_t)out.size();
+}

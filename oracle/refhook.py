@@ -124,6 +124,32 @@ class RefHook:
         rows[:, [1, 2, 6, 8]] &= 0xFFFFFFFF
         return rows, int(stream[-1])
 
+    def sr_candidates(self, bam_path: str, chr_id: int, start: int, end: int, insert_size: int, min_anchor_quality: int = -1):
+        """What the reference's ReadInBamReads_SR hands to the ReadBuffer for one BAM file and window, before GetCloseEnd
+        -> (candidates [k, 7] int64: FNV-1a of Name, MatchedD, MatchedRelPos, MS, InsertSize, ReadLength, FNV-1a of UnmatchedSeq;
+        ref reads [m, 3]: Pos, MQ, ReadLength).  min_anchor_quality: the -A setting for this call (-1 = the process default)."""
+        self.lib.pgref_sr_candidates.restype = C.c_int64
+        out = C.POINTER(C.c_int32)()
+        devnull = os.open(os.devnull, os.O_WRONLY)
+        saved = os.dup(1)
+        os.dup2(devnull, 1)
+        try:
+            k = self.lib.pgref_sr_candidates(bam_path.encode(), chr_id, C.c_uint32(start), C.c_uint32(end), insert_size, min_anchor_quality, C.byref(out))
+        finally:
+            os.dup2(saved, 1)
+            os.close(saved)
+            os.close(devnull)
+        if k < 0:
+            raise RuntimeError("pgref_sr_candidates failed: %d" % k)
+        stream = np.ctypeslib.as_array(out, shape=(int(k),)).astype(np.int64)
+        self.lib.pgref_free(out)
+        k = int(stream[0])
+        cand = stream[1:1 + 7 * k].reshape(-1, 7).copy()
+        cand[:, [0, 2, 6]] &= 0xFFFFFFFF
+        m = int(stream[1 + 7 * k])
+        refs = stream[2 + 7 * k:2 + 7 * k + 3 * m].reshape(-1, 3).copy()
+        return cand, refs
+
     def set_window(self, chr_id: int, start: int, end: int) -> None:
         if self.lib.pgref_set_window(chr_id, C.c_uint32(start), C.c_uint32(end)) != 0:
             raise RuntimeError("pgref_set_window failed")
