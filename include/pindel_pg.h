@@ -301,6 +301,45 @@ struct pg_rp;
 int pg_bam_rp_discovery(pg_ctx *ctx, const pg_rp_query *q, struct pg_rp *rows, uint32_t *src, uint64_t cap, uint64_t *n_rows,
                         struct pg_rp *inter_rows, uint32_t *inter_src, uint64_t inter_cap, uint64_t *n_inter, uint64_t *n_scanned);
 
+/* The reader's split-read filter on the indexed stream (rest of row N3): what ReadInBamReads_SR
+ * (src/reader.cpp:483-560) hands to its ReadBuffer for one BAM file and window.  Every record the region iterator delivers goes
+ * through fetch_func_SR (src/reader.cpp:1099-1151): records are paired on their read name as they stream by, reads that
+ * isWeirdRead accepts (src/reader.cpp:659-690) become candidates behind themselves and behind a mate isGoodAnchor accepts
+ * (:561-612) -- build_record_SR (:799-900): sequence decoded, N-trimmed, reverse-complemented for reverse-strand reads, N
+ * filter, the anchor's strand and position -- and reads isRefRead accepts (:619-654) are counted as reference-supporting
+ * (build_record_RefRead, :903-923).  cands / refs come back in the order of the reference's addRead / push_back calls;
+ * candidate k's UnmatchedSeq is seqs[k * stride .. + read_length) (stride: the longest sequence, returned; seqs holds
+ * seq_cap bytes).  The host adds Name ("@" + the read's name + "/1" | "/2"), read_group (the anchor's RG tag), Tag, FragName and
+ * InsertSize itself from the records `anchor` / `read` index.  n_scanned: records delivered (g_NumReadScanned's increase).
+ * PG_ERR_RUNS_CAP: a buffer is too small (*n_cands, *n_refs, *stride hold the required sizes; pass NULL buffers to ask);
+ * PG_ERR_DATA: a candidate's sequence is not shorter than insert_size -- the reference stops the program there
+ * (src/reader.cpp:866-874); PG_ERR_STATE: no indexed stream is resident (pg_bgzf_inflate + pg_bam_index). */
+typedef struct pg_sr_query {
+   int32_t tid;                   /* bam_name2id(header, FragName) */
+   int32_t beg, end;              /* the window: sam_itr_queryi(idx, tid, window.getStart(), window.getEnd()) */
+   int32_t insert_size;           /* the BAM file's insert size (configuration file) */
+   uint32_t min_anchor_quality;   /* userSettings->minimalAnchorQuality (-A) */
+   uint32_t chr_len;              /* CurrentChrSeq->size() - 2 * g_SpacerBeforeAfter: MatchedRelPos is clamped to it */
+   int32_t nm_limit;              /* userSettings->NM */
+   uint32_t pad;
+   double max_mismatch_rate;      /* userSettings->MaximumAllowedMismatchRate (-u) */
+} pg_sr_query;
+typedef struct pg_sr_cand {
+   uint32_t anchor, read;         /* indices into pg_bam_index's table: mapped_read, unmapped_read of build_record_SR */
+   uint32_t matched_rel_pos;      /* MatchedRelPos */
+   uint32_t read_length;          /* UnmatchedSeq.size() */
+   uint8_t matched_d;             /* MatchedD '+' / '-' */
+   uint8_t ms;                    /* MS */
+   uint16_t pad;
+} pg_sr_cand;
+typedef struct pg_sr_ref {
+   uint32_t pos;                  /* REF_READ::Pos */
+   int16_t read_length;           /* REF_READ::ReadLength */
+   uint8_t mq, pad;               /* REF_READ::MQ */
+} pg_sr_ref;
+int pg_bam_sr_candidates(pg_ctx *ctx, const pg_sr_query *q, pg_sr_cand *cands, uint64_t cand_cap, uint64_t *n_cands, char *seqs, uint64_t seq_cap,
+                         uint32_t *stride, pg_sr_ref *refs, uint64_t ref_cap, uint64_t *n_refs, uint64_t *n_scanned);
+
 /* ------------------------------------------------------------------------------------------------------------------
  * Discordant-read-pair clustering: the two quadratic loops of BDData::UpdateBD
  * (src/bddata.cpp:646-659) that turn the window's discordant pairs into BreakDancer-like events for the far-end search.

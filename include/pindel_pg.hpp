@@ -15,8 +15,11 @@
 //     void bubblesortReads(Reads, VariantIndices) / void markDuplicates(Reads, VariantIndices) src/reporter.cpp:932,946
 //     htslib's BGZF inflate + record walk behind sam_itr_next                                  src/reader.cpp:1258-1346
 //
+//     bool ReadInBamReads_SR(bam_path, FragName, ..., window, readBuffer, verbose)             src/reader.cpp:483-560
+//
 // -> Searcher::ModifyRP / Summarize (whole vector), Searcher::SortBoxes (all boxes of a driver), Searcher::InflateBam /
-// IndexBam.  No search logic lives in this header; without a CUDA device the Searcher constructor throws.
+// IndexBam / ReadInBamReads_SR (one window of the resident stream).  No search logic lives in this header; without a CUDA
+// device the Searcher constructor throws.
 #ifndef PINDEL_PG_HPP
 #define PINDEL_PG_HPP
 #include <algorithm>
@@ -90,6 +93,7 @@ struct SPLIT_READ {                      // the fields of src/pindel.h:265-383 t
    char MatchedD = 0;
    unsigned int MatchedRelPos = 0;
    short InsertSize = 0;
+   short MS = 0;                         // the anchor's mapping quality (set by the reader)
    bool Used = false;
    bool MapperSplit = false;
    SortedUniquePoints UP_Close, UP_Far;
@@ -112,6 +116,12 @@ struct SPLIT_READ {                      // the fields of src/pindel.h:265-383 t
    bool goodFarEndFound() const { return UP_Far.MaxLen() + UP_Close.MaxLen() >= UnmatchedSeq.size(); } // src/pindel.cpp:480-483
 private:
    std::string UnmatchedSeq;
+};
+
+struct REF_READ {                        // src/pindel.h:199-214 without Tag / FragName (the caller knows them)
+   unsigned Pos = 0;
+   short MQ = 0;
+   short ReadLength = 0;
 };
 
 struct RP_READ {                         // src/pindel.h:215-262: the fields the read-pair clustering reads or writes
@@ -293,6 +303,46 @@ public:
       std::vector<pg_bam_rec> recs((size_t)n);
       if (n) check(pg_bam_index(ctx_, recs.data(), n, &n, first_record, n_ref), "pg_bam_index");
       return recs;
+   }
+
+   // ReadInBamReads_SR (src/reader.cpp:483-560) for one window of the stream InflateBam + IndexBam left on the device: the
+   // reads build_record_SR would hand to the ReadBuffer are appended to Reads (Name, UnmatchedSeq, MatchedD, MatchedRelPos, MS,
+   // InsertSize; chromosome_id = the caller's index of FragName), the reads build_record_RefRead keeps to RefSupportingReads.
+   // inflated / recs: the host copies InflateBam / IndexBam returned (the names are read from them).  -> records scanned.
+   uint64_t ReadInBamReads_SR(const std::string &inflated, const std::vector<pg_bam_rec> &recs, const pg_sr_query &q, int chromosome_id,
+                              std::vector<SPLIT_READ> &Reads, std::vector<REF_READ> &RefSupportingReads)
+   {
+      uint64_t n = 0, m = 0, scanned = 0;
+      uint32_t stride = 0;
+      int rc = pg_bam_sr_candidates(ctx_, &q, NULL, 0, &n, NULL, 0, &stride, NULL, 0, &m, &scanned);
+      if (rc != PG_OK && rc != PG_ERR_RUNS_CAP) check(rc, "pg_bam_sr_candidates");
+      if (rc == PG_OK) return scanned;
+      std::vector<pg_sr_cand> cands((size_t)n + 1);
+      std::vector<pg_sr_ref> refs((size_t)m + 1);
+      std::vector<char> seqs((size_t)n * stride + 1);
+      check(pg_bam_sr_candidates(ctx_, &q, cands.data(), n, &n, seqs.data(), n * stride, &stride, refs.data(), m, &m, &scanned), "pg_bam_sr_candidates");
+      for (uint64_t k = 0; k < n; k++) {
+         const pg_sr_cand &c = cands[(size_t)k];
+         const pg_bam_rec &rr = recs.at(c.read);
+         SPLIT_READ t;
+         t.Name = "@";
+         t.Name.append(inflated.c_str() + rr.off + 36);
+         if (rr.flag & 0x40) t.Name.append("/1");
+         else if (rr.flag & 0x80) t.Name.append("/2");
+         t.chromosome_id = chromosome_id;
+         t.setUnmatchedSeq(std::string(&seqs[(size_t)k * stride], c.read_length));
+         t.MatchedD = (char)c.matched_d;
+         t.MatchedRelPos = c.matched_rel_pos;
+         t.MS = c.ms;
+         t.InsertSize = (short)q.insert_size;
+         Reads.push_back(t);
+      }
+      for (uint64_t k = 0; k < m; k++) {
+         REF_READ r;
+         r.Pos = refs[(size_t)k].pos; r.MQ = refs[(size_t)k].mq; r.ReadLength = refs[(size_t)k].read_length;
+         RefSupportingReads.push_back(r);
+      }
+      return scanned;
    }
 
 private:

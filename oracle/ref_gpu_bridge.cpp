@@ -970,14 +970,138 @@ bool ReadInBamReads_RP_Discovery(const char *bam_path, const std::string &FragNa
    return true;
 }
 
+/* Rest of row N3: ReadInBamReads_SR (src/reader.cpp:483-560), bound by symbol like the discovery above.  The region iterator,
+ * the pairing of mates on their names (fetch_func_SR), the three predicates and build_record_SR / build_record_RefRead run as
+ * pg_bam_sr_candidates on the resident stream; the host adds what only it needs (Name, read_group, Tag, FragName) from the
+ * records the rows point at, keeps the reader's counters, and hands every read to the caller's ReadBuffer exactly as
+ * build_record_SR does.  Opt-in (PG_BRIDGE_SR_FILTER=1) until its first run on the hardware; otherwise, and with
+ * PG_BRIDGE_ZLIB=1, the reference's own function runs (found with dlsym(RTLD_NEXT)). */
+extern unsigned int g_NumReadInWindow, g_InWinPlus, g_InWinMinus;
+void showReadStats(const std::vector<SPLIT_READ> &Reads, const std::vector<SPLIT_READ> &OneEndMappedReads);
+static unsigned long g_sr_candidates = 0;
+typedef bool (*SrReaderFn)(const char *, const std::string &, const std::string *, std::vector<SPLIT_READ> &, std::vector<SPLIT_READ> &,
+                           std::vector<REF_READ> &, int, std::string, const SearchWindow &, ReadBuffer &, bool);
+static void auxString(const uint8_t *rec, uint32_t rec_len, const char *tag, std::string &out)      /* bam_aux_get + bam_aux2Z */
+{
+   const uint32_t l_name = rec[8], n_cigar = rec[12] | rec[13] << 8, l_seq = rec[16] | rec[17] << 8 | rec[18] << 16 | (uint32_t)rec[19] << 24;
+   const uint8_t *p = rec + 32 + l_name + 4ul * n_cigar + (l_seq + 1) / 2 + l_seq, *end = rec + rec_len;
+   while (p + 3 <= end) {
+      const uint8_t t0 = p[0], t1 = p[1], ty = p[2];
+      p += 3;
+      size_t n;
+      if (ty == 'A' || ty == 'c' || ty == 'C') n = 1;
+      else if (ty == 's' || ty == 'S') n = 2;
+      else if (ty == 'i' || ty == 'I' || ty == 'f') n = 4;
+      else if (ty == 'd') n = 8;
+      else if (ty == 'Z' || ty == 'H') { const uint8_t *e = p; while (e < end && *e) e++; if (e >= end) return; n = (size_t)(e - p) + 1; }
+      else if (ty == 'B') {
+         if (p + 5 > end) return;
+         const uint8_t sub = p[0];
+         const size_t w = (sub == 'c' || sub == 'C') ? 1 : (sub == 's' || sub == 'S') ? 2 : (sub == 'i' || sub == 'I' || sub == 'f') ? 4 : 0;
+         if (!w) return;
+         n = 5 + w * (p[1] | p[2] << 8 | p[3] << 16 | (size_t)p[4] << 24);
+      } else return;
+      if (n > (size_t)(end - p)) return;
+      if (t0 == (uint8_t)tag[0] && t1 == (uint8_t)tag[1]) {
+         if (ty == 'Z') out = (const char *)p;
+         return;
+      }
+      p += n;
+   }
+}
+bool ReadInBamReads_SR(const char *bam_path, const std::string &FragName, const std::string *CurrentChrSeq, std::vector<SPLIT_READ> &LeftReads,
+                       std::vector<SPLIT_READ> &OneEndMappedReads, std::vector<REF_READ> &RefSupportingReads, int InsertSize, std::string Tag,
+                       const SearchWindow &window, ReadBuffer &readBuffer, bool verbose)
+{
+   static const bool enabled = getenv("PG_BRIDGE_SR_FILTER") != NULL;
+   if (minihts_index_hook == NULL || !enabled) {
+      static SrReaderFn original = (SrReaderFn)dlsym(RTLD_NEXT, "_Z17ReadInBamReads_SRPKcRKNSt7__cxx1112basic_stringIcSt11char_traitsIcESaIcEEEPS7_RSt6vectorI10SPLIT_READSaISB_EESE_RSA_I8REF_READSaISF_EEiS6_RK12SearchWindowR10ReadBufferb");
+      if (!original) { std::fprintf(stderr, "pindel_gpu_demo: the reference's ReadInBamReads_SR was not found\n"); std::exit(EXIT_FAILURE); }
+      return original(bam_path, FragName, CurrentChrSeq, LeftReads, OneEndMappedReads, RefSupportingReads, InsertSize, Tag, window, readBuffer, verbose);
+   }
+   samFile *fp = sam_open(bam_path, "r");
+   if (!fp) return false;
+   hts_idx_t *idx = sam_index_load(fp, bam_path);
+   bam_hdr_t *header = sam_hdr_read(fp);
+   const int tid = bam_name2id(header, FragName.c_str());
+   std::vector<pg_sr_cand> cands;
+   std::vector<pg_sr_ref> refs;
+   std::vector<char> seqs;
+   uint32_t stride = 0;
+   {
+      std::lock_guard<std::mutex> lock(g_mutex);
+      pg_sr_query q;
+      memset(&q, 0, sizeof q);
+      q.tid = tid; q.beg = (int32_t)window.getStart(); q.end = (int32_t)window.getEnd(); q.insert_size = InsertSize;
+      q.min_anchor_quality = userSettings->minimalAnchorQuality;
+      q.chr_len = (uint32_t)(CurrentChrSeq->size() - 2 * g_SpacerBeforeAfter);
+      q.nm_limit = userSettings->NM;
+      q.max_mismatch_rate = userSettings->MaximumAllowedMismatchRate;
+      uint64_t n = 0, m = 0, scanned = 0;
+      int rc = pg_bam_sr_candidates(g_ctx, &q, NULL, 0, &n, NULL, 0, &stride, NULL, 0, &m, &scanned);
+      if (rc == PG_ERR_RUNS_CAP) {
+         cands.resize(n ? n : 1); refs.resize(m ? m : 1); seqs.resize(n * stride + 1);
+         rc = pg_bam_sr_candidates(g_ctx, &q, &cands[0], n, &n, &seqs[0], n * stride, &stride, &refs[0], m, &m, &scanned);
+      }
+      if (rc == PG_ERR_DATA) {            /* the reference prints its explanation and leaves (src/reader.cpp:866-874) */
+         *logStream << "Error: the insert size is only " << InsertSize << " while a read is at least as long" << std::endl;
+         exit(EXIT_FAILURE);
+      }
+      if (rc != PG_OK) die("pg_bam_sr_candidates");
+      cands.resize(n); refs.resize(m);
+      g_NumReadScanned += (unsigned int)scanned;
+      g_sr_candidates += (unsigned long)n;
+   }
+   const uint8_t *stream = g_lastStream->data();
+   /* the reference interleaves the two kinds of calls, but they fill separate containers: candidates go to the buffer in order ... */
+   for (size_t k = 0; k < cands.size(); k++) {
+      const pg_sr_cand &c = cands[k];
+      const pg_bam_rec &ra = g_lastTable[c.anchor], &rr = g_lastTable[c.read];
+      const uint8_t *arec = stream + ra.off + 4, *rrec = stream + rr.off + 4;
+      const uint32_t alen = stream[ra.off] | stream[ra.off + 1] << 8 | stream[ra.off + 2] << 16 | (uint32_t)stream[ra.off + 3] << 24;
+      SPLIT_READ t;
+      t.MS = c.ms;
+      t.Name = "@";
+      t.Name.append((const char *)(rrec + 32));
+      if (rr.flag & 0x40) t.Name.append("/1");
+      else if (rr.flag & 0x80) t.Name.append("/2");
+      auxString(arec, alen, "RG", t.read_group);
+      t.setUnmatchedSeq(std::string(&seqs[k * (size_t)stride], c.read_length));
+      t.MatchedRelPos = c.matched_rel_pos;
+      t.MatchedD = (char)c.matched_d;
+      t.InsertSize = InsertSize;
+      t.Tag = Tag;
+      t.FragName = header->target_name[ra.tid];
+      g_NumReadInWindow++;
+      if (t.MatchedD == Plus) g_InWinPlus++; else g_InWinMinus++;
+      readBuffer.addRead(t);
+   }
+   /* ... and the reference-supporting reads to their vector */
+   for (size_t k = 0; k < refs.size(); k++) {
+      REF_READ r;
+      r.Pos = refs[k].pos;
+      r.Tag = Tag;
+      r.MQ = refs[k].mq;
+      r.FragName = header->target_name[tid];
+      r.ReadLength = refs[k].read_length;
+      RefSupportingReads.push_back(r);
+   }
+   readBuffer.flush();
+   if (verbose) showReadStats(LeftReads, OneEndMappedReads);
+   bam_hdr_destroy(header);
+   hts_idx_destroy(idx);
+   sam_close(fp);
+   return true;
+}
+
 static void reportAtExit()
 {
    std::fprintf(stderr, "pindel_gpu_demo: %lu GetCloseEnd calls and %lu far-end reads served by libpindel_pg (%llu kernel launches); "
-                "%lu reads classified by the SV drivers on the device, %lu records (%llu launches), %lu of the reads without a second upload; %lu read pairs clustered on the device (%llu launches); %lu BAM bytes inflated and %lu records indexed on the device, %lu discordant pairs found there; %lu boxes ordered on the device (%llu launches), %lu by the reference\n",
+                "%lu reads classified by the SV drivers on the device, %lu records (%llu launches), %lu of the reads without a second upload; %lu read pairs clustered on the device (%llu launches); %lu BAM bytes inflated and %lu records indexed on the device, %lu discordant pairs found there; %lu boxes ordered on the device (%llu launches), %lu by the reference; %lu split-read candidates from the device filter\n",
                 g_close_calls, g_far_reads, g_ctx ? (unsigned long long)pg_kernel_launches(g_ctx) : 0ull, g_sv_reads, g_sv_records,
                 g_ctx ? (unsigned long long)pg_classify_launches(g_ctx) : 0ull, g_sv_resident, g_rp_rows,
                 g_ctx ? (unsigned long long)pg_rp_launches(g_ctx) : 0ull, g_bgzf_bytes, g_bam_records, g_rpd_rows, g_boxes_sorted,
-                g_ctx ? (unsigned long long)pg_box_sort_launches(g_ctx) : 0ull, g_boxes_host);
+                g_ctx ? (unsigned long long)pg_box_sort_launches(g_ctx) : 0ull, g_boxes_host, g_sr_candidates);
 }
 
 int main(int argc, char *argv[])

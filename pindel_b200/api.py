@@ -101,6 +101,8 @@ def load_library() -> C.CDLL:
         lib.pg_bam_index.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64), C.POINTER(C.c_int32)]
         lib.pg_bam_rp_discovery.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.POINTER(C.c_uint64), C.c_void_p, C.c_void_p,
                                             C.c_uint64, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]
+        lib.pg_bam_sr_candidates.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.POINTER(C.c_uint64), C.c_void_p, C.c_uint64,
+                                             C.POINTER(C.c_uint32), C.c_void_p, C.c_uint64, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]
         lib.pg_bam_launches.restype = C.c_uint64
         lib.pg_bam_launches.argtypes = [C.c_void_p]
         lib.pg_bam_last_ms.restype = C.c_double
@@ -398,6 +400,25 @@ class PatternGrowth:
             self._check(self.lib.pg_bam_rp_discovery(self.ctx, q.ctypes.data, vp(rows), vp(src), rows.size, C.byref(n), vp(irows), vp(isrc), irows.size,
                                                      C.byref(ni), C.byref(ns)), "pg_bam_rp_discovery")
         return rows, src, irows, isrc, int(ns.value)
+
+    def bam_sr_candidates(self, tid, beg, end, insert_size, chr_len, min_anchor_quality=0, nm_limit=2, max_mismatch_rate=0.02):
+        """The reader's split-read filter on the indexed stream (after bgzf_inflate + bam_index): what ReadInBamReads_SR hands
+        to its ReadBuffer.  -> (cands (bam.SR_CAND_DT), seqs [n, stride] uint8, refs (bam.SR_REF_DT), records delivered)"""
+        from . import bam
+        q = np.array([(tid, beg, end, insert_size, min_anchor_quality, chr_len, nm_limit, 0, max_mismatch_rate)], dtype=bam.SR_QUERY_DT)
+        n, m, ns, stride = C.c_uint64(0), C.c_uint64(0), C.c_uint64(0), C.c_uint32(0)
+        rc = self.lib.pg_bam_sr_candidates(self.ctx, q.ctypes.data, None, C.c_uint64(0), C.byref(n), None, C.c_uint64(0), C.byref(stride), None, C.c_uint64(0),
+                                           C.byref(m), C.byref(ns))
+        if rc not in (0, PG_ERR_RUNS_CAP):
+            self._check(rc, "pg_bam_sr_candidates")
+        cands = np.zeros(int(n.value), dtype=bam.SR_CAND_DT)
+        seqs = np.zeros((int(n.value), max(int(stride.value), 1)), dtype=np.uint8)
+        refs = np.zeros(int(m.value), dtype=bam.SR_REF_DT)
+        if rc == PG_ERR_RUNS_CAP:
+            vp = lambda a: a.ctypes.data_as(C.c_void_p) if a.size else None
+            self._check(self.lib.pg_bam_sr_candidates(self.ctx, q.ctypes.data, vp(cands), C.c_uint64(cands.size), C.byref(n), vp(seqs), C.c_uint64(seqs.size),
+                                                      C.byref(stride), vp(refs), C.c_uint64(refs.size), C.byref(m), C.byref(ns)), "pg_bam_sr_candidates")
+        return cands, seqs, refs, int(ns.value)
 
     def bam_last_segments(self):
         a, b = C.c_uint32(0), C.c_uint32(0)

@@ -7,6 +7,11 @@ import struct
 import numpy as np
 
 REC_DT = np.dtype([("off", "<u8"), ("tid", "<i4"), ("pos", "<i4"), ("end", "<i4"), ("flag", "<u2"), ("mapq", "u1"), ("pad", "u1")])
+# pg_sr_query / pg_sr_cand / pg_sr_ref (include/pindel_pg.h)
+SR_QUERY_DT = np.dtype([("tid", "<i4"), ("beg", "<i4"), ("end", "<i4"), ("insert_size", "<i4"), ("min_anchor_quality", "<u4"), ("chr_len", "<u4"),
+                        ("nm_limit", "<i4"), ("pad", "<u4"), ("max_mismatch_rate", "<f8")])
+SR_CAND_DT = np.dtype([("anchor", "<u4"), ("read", "<u4"), ("matched_rel_pos", "<u4"), ("read_length", "<u4"), ("matched_d", "u1"), ("ms", "u1"), ("pad", "<u2")])
+SR_REF_DT = np.dtype([("pos", "<u4"), ("read_length", "<i2"), ("mq", "u1"), ("pad", "u1")])
 
 
 def header(refs, text: bytes = b"@HD\tVN:1.6\tSO:coordinate\n") -> bytes:

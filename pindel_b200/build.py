@@ -44,13 +44,14 @@ def build_oracle():
 
 def build_emulator():
     sys.path.insert(0, ROOT)
-    from tests.emul import bam_emul, bgzf_emul, boxsort_emul, emul, rp_emul, sv_emul
+    from tests.emul import bam_emul, bgzf_emul, boxsort_emul, emul, rp_emul, sr_emul, sv_emul
     emul.build()
     sv_emul.build()
     rp_emul.build()
     bgzf_emul.build()
     bam_emul.build()
     boxsort_emul.build()
+    sr_emul.build()
 
 
 def build_all(force=False):

@@ -24,6 +24,7 @@
 #include "pg_bgzf_host.h"
 #include "pg_bam.cuh"
 #include "pg_bam_host.h"
+#include "pg_sr.cuh"
 #include "pg_boxsort.cuh"
 #include "pg_params.h"
 #include "../../include/pindel_pg.h"
@@ -393,6 +394,7 @@ struct pg_ctx {
    uint64_t bm_launches = 0, bm_n_recs = 0;
    bool bm_valid = false;       // bm_recs holds the table of the resident stream
    DevBuf bd_cls, bd_off, bd_sums, bd_rows, bd_src, bd_counters;
+   DevBuf sr_info, sr_keys, sr_head, sr_slot, sr_next, sr_partner, sr_emit, sr_cands, sr_seqs, sr_refs;   // pg_bam_sr_candidates
    uint32_t bm_last_segments = 0, bm_last_redone = 0;
    float bm_last_ms = 0.f;
    size_t bz_out_len = 0;
@@ -564,6 +566,8 @@ void pg_destroy(pg_ctx *ctx)
                        &ctx->rp_nid, &ctx->rp_counters, &ctx->rp_keys, &ctx->rp_flip, &ctx->rp_chr, &ctx->bz_file, &ctx->bz_blocks, &ctx->bz_out, &ctx->bz_status,
                        &ctx->bm_info, &ctx->bm_starts, &ctx->bm_counts, &ctx->bm_landing, &ctx->bm_base, &ctx->bm_recs,
                        &ctx->bd_cls, &ctx->bd_off, &ctx->bd_sums, &ctx->bd_rows, &ctx->bd_src, &ctx->bd_counters,
+                       &ctx->sr_info, &ctx->sr_keys, &ctx->sr_head, &ctx->sr_slot, &ctx->sr_next, &ctx->sr_partner, &ctx->sr_emit, &ctx->sr_cands,
+                       &ctx->sr_seqs, &ctx->sr_refs,
                        &ctx->bx_off, &ctx->bx_keys, &ctx->bx_order, &ctx->bx_non};
    for (DevBuf *b : svbufs) if (b->p) cudaFree(b->p);
    pipe_destroy(ctx->pipe);
@@ -1503,6 +1507,111 @@ int pg_bam_rp_discovery(pg_ctx *ctx, const pg_rp_query *q, pg_rp *rows, uint32_t
          CU(cudaMemcpyAsync(inter_rows, rows_d + tot_intra, sizeof(PgRpRow) * (size_t)tot_inter, cudaMemcpyDeviceToHost, st));
          CU(cudaMemcpyAsync(inter_src, src_d + tot_intra, sizeof(uint32_t) * (size_t)tot_inter, cudaMemcpyDeviceToHost, st));
       }
+   } else {
+      CU(cudaEventRecord(ctx->sv_ev1, st));
+   }
+   CU(cudaStreamSynchronize(st));
+   CU(cudaEventElapsedTime(&ctx->bm_last_ms, ctx->sv_ev0, ctx->sv_ev1));
+   return PG_OK;
+}
+
+// ---- the reader's split-read filter on the indexed stream (rest of row N3) ---------------------------------------------
+static_assert(sizeof(pg_sr_query) == sizeof(PgSrQuery) && sizeof(pg_sr_query) == 40, "sr query layout");
+static_assert(sizeof(pg_sr_cand) == sizeof(PgSrCand) && sizeof(pg_sr_cand) == 20, "sr candidate layout");
+static_assert(sizeof(pg_sr_ref) == sizeof(PgSrRef) && sizeof(pg_sr_ref) == 8, "sr reference read layout");
+
+int pg_bam_sr_candidates(pg_ctx *ctx, const pg_sr_query *q, pg_sr_cand *cands, uint64_t cand_cap, uint64_t *n_cands, char *seqs, uint64_t seq_cap,
+                         uint32_t *stride, pg_sr_ref *refs, uint64_t ref_cap, uint64_t *n_refs, uint64_t *n_scanned)
+{
+   if (!ctx || !q || !n_cands || !n_refs || !stride) return fail(ctx, PG_ERR_ARG, "pg_bam_sr_candidates: null argument");
+   if (!ctx->bm_valid || ctx->bz_out_len == 0) return fail(ctx, PG_ERR_STATE, "pg_bam_sr_candidates: no indexed stream is resident (pg_bgzf_inflate + pg_bam_index)");
+   *n_cands = *n_refs = 0;
+   *stride = 0;
+   if (n_scanned) *n_scanned = 0;
+   const uint64_t n64 = ctx->bm_n_recs;
+   if (n64 == 0) return PG_OK;
+   if (n64 > 0x3FFFFFF0ull) return fail(ctx, PG_ERR_UNSUPPORTED, "pg_bam_sr_candidates: more than 2^30 records");
+   const uint32_t n = (uint32_t)n64;
+   CU(cudaSetDevice(ctx->device));
+   cudaStream_t st = ctx->stream;
+   PgSrQuery qq;
+   memcpy(&qq, q, sizeof qq);
+   const uint32_t n16 = (n + 15u) / 16u, n_blocks = (n16 + PG_SCAN_THREADS - 1) / PG_SCAN_THREADS;
+   uint32_t table_bits = 4;
+   while ((1ull << table_bits) < 2ull * n) table_bits++;
+   const size_t slots = (size_t)1 << table_bits;
+   int rc;
+   if ((rc = ensure(ctx, ctx->bd_cls, (size_t)n16 * 16 * 2)) != PG_OK) return rc;                       // n_sr | n_ref byte counts
+   if ((rc = ensure(ctx, ctx->bd_off, sizeof(uint32_t) * (size_t)n16 * 16 * 2)) != PG_OK) return rc;
+   if ((rc = ensure(ctx, ctx->bd_sums, sizeof(uint32_t) * ((size_t)n_blocks + 1) * 2)) != PG_OK) return rc;
+   if ((rc = ensure(ctx, ctx->bd_counters, sizeof(uint32_t) * 4)) != PG_OK) return rc;
+   if ((rc = ensure(ctx, ctx->sr_info, sizeof(PgSrInfo) * (size_t)n)) != PG_OK) return rc;
+   if ((rc = ensure(ctx, ctx->sr_keys, sizeof(uint64_t) * slots)) != PG_OK) return rc;
+   if ((rc = ensure(ctx, ctx->sr_head, sizeof(uint32_t) * slots)) != PG_OK) return rc;
+   if ((rc = ensure(ctx, ctx->sr_slot, sizeof(uint32_t) * (size_t)n)) != PG_OK) return rc;
+   if ((rc = ensure(ctx, ctx->sr_next, sizeof(uint32_t) * (size_t)n)) != PG_OK) return rc;
+   if ((rc = ensure(ctx, ctx->sr_partner, sizeof(uint32_t) * (size_t)n)) != PG_OK) return rc;
+   if ((rc = ensure(ctx, ctx->sr_emit, (size_t)n)) != PG_OK) return rc;
+   uint8_t *cnt_sr = (uint8_t *)ctx->bd_cls.p, *cnt_ref = cnt_sr + (size_t)n16 * 16;
+   uint32_t *off_sr = (uint32_t *)ctx->bd_off.p, *off_ref = off_sr + (size_t)n16 * 16;
+   uint32_t *sums_sr = (uint32_t *)ctx->bd_sums.p, *sums_ref = sums_sr + n_blocks + 1;
+   uint32_t *counters_d = (uint32_t *)ctx->bd_counters.p;
+   const uint32_t init[4] = {n, 0u, 0u, 0u};
+   CU(cudaMemcpyAsync(counters_d, init, sizeof init, cudaMemcpyHostToDevice, st));
+   CU(cudaMemsetAsync(ctx->bd_cls.p, 0, (size_t)n16 * 16 * 2, st));
+   CU(cudaMemsetAsync(ctx->sr_keys.p, 0, sizeof(uint64_t) * slots, st));
+   CU(cudaMemsetAsync(ctx->sr_head.p, 0xFF, sizeof(uint32_t) * slots, st));                              // PGSR_NONE
+   const uint8_t *d = (const uint8_t *)ctx->bz_out.p;
+   const PgBamRec *recs = (const PgBamRec *)ctx->bm_recs.p;
+   PgSrInfo *info = (PgSrInfo *)ctx->sr_info.p;
+   uint32_t *slot = (uint32_t *)ctx->sr_slot.p, *next = (uint32_t *)ctx->sr_next.p, *partner = (uint32_t *)ctx->sr_partner.p;
+   uint8_t *emit = (uint8_t *)ctx->sr_emit.p;
+   if (!ctx->sv_ev0) { CU(cudaEventCreate(&ctx->sv_ev0)); CU(cudaEventCreate(&ctx->sv_ev1)); }
+   CU(cudaEventRecord(ctx->sv_ev0, st));
+   const uint32_t grid = (n + 255u) / 256u;
+   pg_bam_stop_kernel<<<grid, 256, 0, st>>>(recs, n, pgsr_iterator(qq), counters_d);
+   pg_sr_info_kernel<<<grid, 256, 0, st>>>(d, recs, n, qq, counters_d, info);
+   pg_sr_insert_kernel<<<grid, 256, 0, st>>>(info, n, (unsigned long long *)ctx->sr_keys.p, (uint32_t *)ctx->sr_head.p, (uint32_t)(slots - 1), slot, next);
+   pg_sr_pair_kernel<<<grid, 256, 0, st>>>(d, recs, n, qq, info, (const uint32_t *)ctx->sr_head.p, slot, next, partner, emit, cnt_sr, cnt_ref, counters_d);
+   for (int list = 0; list < 2; list++) {
+      const uint4 *c16 = (const uint4 *)(list ? cnt_ref : cnt_sr);
+      uint32_t *sums = list ? sums_ref : sums_sr;
+      pg_scan_reduce<<<n_blocks, PG_SCAN_THREADS, 0, st>>>(c16, n16, sums);
+      pg_scan_blocks<<<1, 1024, 0, st>>>(sums, n_blocks);
+      pg_scan_apply<<<n_blocks, PG_SCAN_THREADS, 0, st>>>(c16, n16, sums, list ? off_ref : off_sr);
+   }
+   CU(cudaGetLastError());
+   ctx->bm_launches += 10;
+   uint32_t counters[4], tot_sr = 0, tot_ref = 0;
+   CU(cudaMemcpyAsync(counters, counters_d, sizeof counters, cudaMemcpyDeviceToHost, st));
+   CU(cudaMemcpyAsync(&tot_sr, sums_sr + n_blocks, sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+   CU(cudaMemcpyAsync(&tot_ref, sums_ref + n_blocks, sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+   CU(cudaStreamSynchronize(st));
+   if (n_scanned) *n_scanned = counters[1];
+   if (counters[3] & PGSR_ERR_INSERT)
+      return fail(ctx, PG_ERR_DATA, "pg_bam_sr_candidates: the insert size is not larger than a candidate read (the reference stops here, src/reader.cpp:866)");
+   const uint32_t str = counters[2] ? counters[2] : 1u;
+   *n_cands = tot_sr;
+   *n_refs = tot_ref;
+   *stride = str;
+   const uint64_t seq_bytes = (uint64_t)tot_sr * str;
+   if (tot_sr > cand_cap || tot_ref > ref_cap || seq_bytes > seq_cap || (tot_sr && (!cands || !seqs)) || (tot_ref && !refs))
+      return fail(ctx, PG_ERR_RUNS_CAP, "pg_bam_sr_candidates: buffers too small (n_cands / n_refs / stride hold the required sizes)");
+   if (tot_sr || tot_ref) {
+      if ((rc = ensure(ctx, ctx->sr_cands, sizeof(PgSrCand) * ((size_t)tot_sr + 1))) != PG_OK) return rc;
+      if ((rc = ensure(ctx, ctx->sr_seqs, (size_t)seq_bytes + 16)) != PG_OK) return rc;
+      if ((rc = ensure(ctx, ctx->sr_refs, sizeof(PgSrRef) * ((size_t)tot_ref + 1))) != PG_OK) return rc;
+      CU(cudaMemsetAsync(ctx->sr_seqs.p, 0, (size_t)seq_bytes + 16, st));
+      pg_sr_scatter_kernel<<<grid, 256, 0, st>>>(d, recs, n, qq, info, partner, emit, off_sr, off_ref, (PgSrCand *)ctx->sr_cands.p, (uint8_t *)ctx->sr_seqs.p,
+                                                 str, (PgSrRef *)ctx->sr_refs.p);
+      CU(cudaGetLastError());
+      ctx->bm_launches++;
+      CU(cudaEventRecord(ctx->sv_ev1, st));
+      if (tot_sr) {
+         CU(cudaMemcpyAsync(cands, ctx->sr_cands.p, sizeof(PgSrCand) * (size_t)tot_sr, cudaMemcpyDeviceToHost, st));
+         CU(cudaMemcpyAsync(seqs, ctx->sr_seqs.p, (size_t)seq_bytes, cudaMemcpyDeviceToHost, st));
+      }
+      if (tot_ref) CU(cudaMemcpyAsync(refs, ctx->sr_refs.p, sizeof(PgSrRef) * (size_t)tot_ref, cudaMemcpyDeviceToHost, st));
    } else {
       CU(cudaEventRecord(ctx->sv_ev1, st));
    }

@@ -18,6 +18,7 @@
 #include "bgzf_emul.cpp"
 #include "bam_emul.cpp"
 #include "boxsort_emul.cpp"
+#include "sr_emul.cpp"
 #include "../../pindel_b200/csrc/pg_host_helpers.h"
 
 struct pg_ctx {
@@ -276,6 +277,25 @@ int pg_bam_rp_discovery(pg_ctx *ctx, const pg_rp_query *q, pg_rp *rows, uint32_t
    if (counts[0] > cap || counts[1] > inter_cap) return fail(ctx, PG_ERR_RUNS_CAP, "row buffers too small");
    if (counts[0]) { memcpy(rows, a.data(), sizeof(pg_rp) * counts[0]); memcpy(src, sa.data(), 4 * counts[0]); }
    if (counts[1]) { memcpy(inter_rows, b.data(), sizeof(pg_rp) * counts[1]); memcpy(inter_src, sb.data(), 4 * counts[1]); }
+   return PG_OK;
+}
+int pg_bam_sr_candidates(pg_ctx *ctx, const pg_sr_query *q, pg_sr_cand *cands, uint64_t cand_cap, uint64_t *n_cands, char *seqs, uint64_t seq_cap,
+                         uint32_t *stride, pg_sr_ref *refs, uint64_t ref_cap, uint64_t *n_refs, uint64_t *n_scanned)
+{
+   if (ctx->stream.empty()) return fail(ctx, PG_ERR_STATE, "no indexed stream");
+   uint64_t counts[5] = {0, 0, 0, 0, 0};
+   const uint32_t n = (uint32_t)ctx->bam_table.size();
+   if (sremu_candidates(ctx->stream.data(), ctx->bam_table.data(), n, (const PgSrQuery *)q, 17u, 0, 0, NULL, NULL, NULL, counts) != 0)
+      return fail(ctx, PG_ERR_DATA, "name table");
+   if (n_scanned) *n_scanned = counts[3];
+   if (counts[4]) return fail(ctx, PG_ERR_DATA, "the insert size is not larger than a candidate read");
+   const uint32_t str = counts[2] ? (uint32_t)counts[2] : 1u;
+   *n_cands = counts[0]; *n_refs = counts[1]; *stride = str;
+   if (counts[0] > cand_cap || counts[1] > ref_cap || counts[0] * str > seq_cap || (counts[0] && (!cands || !seqs)) || (counts[1] && !refs))
+      return fail(ctx, PG_ERR_RUNS_CAP, "buffers too small");
+   std::vector<uint8_t> tmp((size_t)counts[0] * (counts[2] ? counts[2] : 1) + 1, 0);
+   sremu_candidates(ctx->stream.data(), ctx->bam_table.data(), n, (const PgSrQuery *)q, 17u, 0, 0, (PgSrCand *)cands, tmp.data(), (PgSrRef *)refs, counts);
+   for (uint64_t k = 0; k < counts[0]; k++) memcpy(seqs + k * str, tmp.data() + k * counts[2], counts[2]);
    return PG_OK;
 }
 uint64_t pg_classify_launches(pg_ctx *ctx) { return ctx ? ctx->sv_launches : 0; }

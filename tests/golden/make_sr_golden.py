@@ -67,6 +67,11 @@ def paired_stream(n_pairs: int, seed: int, refs=SYNTH_REFS) -> bytes:
                 s[p] = ord("N")
         elif k < 0.43:
             s[:] = b"N" * rl
+        elif k < 0.5:          # IUPAC codes and '=' at the ends and inside: NUL after a reverse complement, stripped when trailing
+            a, b = int(rng.integers(0, 4)), int(rng.integers(0, 4))
+            s[:a] = rng.choice(np.frombuffer(b"=MRSVWYHKDB", dtype=np.uint8), a).tobytes()
+            s[rl - b:] = rng.choice(np.frombuffer(b"=MRSVWYHKDB", dtype=np.uint8), b).tobytes()
+            s[rl // 2] = ord("R")
         return bytes(s)
 
     def cigar(rl):

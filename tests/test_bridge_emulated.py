@@ -30,6 +30,12 @@ def test_bam_input_scenario_with_zlib_inflate(tmp_path):
     D.sim_prefix_bam(DEMO, tmp_path, dict(os.environ, PG_BRIDGE_ZLIB="1"))
 
 
+def test_bam_input_scenario_with_the_device_split_read_filter(tmp_path):
+    """ReadInBamReads_SR bound to pg_bam_sr_candidates (PG_BRIDGE_SR_FILTER=1): the reader's per-record loop is replaced by the
+    device filter and the host only adds names, read groups and tags -- same files"""
+    D.sim_prefix_bam(DEMO, tmp_path, dict(os.environ, PG_BRIDGE_SR_FILTER="1"))
+
+
 def test_text_input_scenario_with_the_host_array_classification(tmp_path):
     """pg_classify (everything uploaded again) instead of pg_classify_resident: the path a host takes when the far-end
     batch is no longer on the device; and the reference's own bubblesortReads / markDuplicates instead of pg_box_sort."""

@@ -1,0 +1,89 @@
+"""GPU parity of the reader's split-read filter (rest of row N3): pg_bgzf_inflate + pg_bam_index +
+pg_bam_sr_candidates through the C ABI against the reference's own dumps (tests/golden/sr_*.npz) and the oracle, and the
+whole-program drop-in with ReadInBamReads_SR bound to it.
+
+The file sorts last on purpose: this stage was finished after the round's GPU minutes were spent, so it is CPU-verified only
+(tests/test_sr_emulator.py runs the same __host__ __device__ functions, tests/test_bridge_emulated.py the same bridge code) and its
+first run on the hardware is the round-end run of this file.  A failure here concerns this stage alone."""
+import os
+
+import numpy as np
+import pytest
+
+from oracle import sroracle
+from pindel_b200 import api, bam, bgzf
+from tests import dropin_scenarios as D
+from tests.golden import make_sr_golden as G
+from tests.test_sr_emulator import case_stream, named_stream, rows_of_product
+
+pytestmark = [pytest.mark.gpu, pytest.mark.timeout(600)]
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+GOLD = os.path.join(ROOT, "tests", "golden")
+DEMO = os.path.join(ROOT, "oracle", "_ref", "pindel_gpu_demo")
+
+
+@pytest.fixture(scope="module")
+def pg():
+    p = api.PatternGrowth()
+    yield p
+    p.close()
+
+
+@pytest.mark.parametrize("case", list(G.QUERIES))
+def test_matches_reference_dumps(pg, case):
+    z = np.load(os.path.join(GOLD, "sr_%s.npz" % case))
+    stream = case_stream(case)
+    data = open(os.path.join(GOLD, "sim_prefix.bam"), "rb").read() if case == "sim_prefix" else bgzf.compress(stream)
+    pg.bgzf_inflate(data, to_host=False)
+    recs, _, _ = pg.bam_index()
+    for k, (tid, beg, end, isz, min_q) in enumerate(G.QUERIES[case]):
+        cands, seqs, refs, _ = pg.bam_sr_candidates(tid, beg, end, isz, int(z["chr_len"][tid]), min_anchor_quality=min_q)
+        c, r = rows_of_product(stream, recs, cands, seqs, refs, isz)
+        assert np.array_equal(c, z["cand_%d" % k]), ("candidates", case, k)
+        assert np.array_equal(r, z["refs_%d" % k]), ("reference-supporting reads", case, k)
+
+
+def test_matches_oracle_on_a_larger_stream(pg):
+    stream = G.paired_stream(30_000, 77)
+    table = bam.serial_index(stream)
+    pg.bgzf_inflate(bgzf.compress(stream), to_host=False)
+    recs, _, _ = pg.bam_index()
+    for tid, beg, end, isz, min_q in ((0, 0, 400_000, 500, 0), (1, 50_000, 250_000, 300, 30), (0, 399_000, 400_000, 500, 0)):
+        exp_c, exp_r = sroracle.candidates(stream, table, tid, beg, end, isz, G.SYNTH_REFS[tid][1], min_anchor_quality=min_q)
+        cands, seqs, refs, scanned = pg.bam_sr_candidates(tid, beg, end, isz, G.SYNTH_REFS[tid][1], min_anchor_quality=min_q)
+        c, r = rows_of_product(stream, recs, cands, seqs, refs, isz)
+        assert np.array_equal(c, exp_c) and np.array_equal(r, exp_r), (tid, beg, end, isz, min_q)
+        assert scanned >= cands.size // 3
+
+
+def test_repeated_names_pair_by_rank(pg):
+    for names in ([b"same"] * 7, [b"a", b"ab", b"a", b"abc", b"ab", b"abc", b"a"], [b"r%d" % (i % 5) for i in range(23)]):
+        stream = named_stream(names)
+        pg.bgzf_inflate(bgzf.compress(stream), to_host=False)
+        recs, _, _ = pg.bam_index()
+        exp_c, exp_r = sroracle.candidates(stream, bam.serial_index(stream), 0, 0, 100_000, 500, 100_000)
+        cands, seqs, refs, scanned = pg.bam_sr_candidates(0, 0, 100_000, 500, 100_000)
+        c, r = rows_of_product(stream, recs, cands, seqs, refs, 500)
+        assert scanned == len(names) and np.array_equal(c, exp_c) and np.array_equal(r, exp_r), names
+
+
+def test_errors(pg):
+    fresh = api.PatternGrowth()
+    with pytest.raises(api.PgError):
+        fresh.bam_sr_candidates(0, 0, 1000, 500, 100_000)              # nothing resident
+    stream = named_stream([b"x", b"y", b"x"])
+    fresh.bgzf_inflate(bgzf.compress(stream), to_host=False)
+    with pytest.raises(api.PgError):
+        fresh.bam_sr_candidates(0, 0, 1000, 500, 100_000)              # inflated but not indexed
+    fresh.bam_index()
+    with pytest.raises(api.PgError):
+        fresh.bam_sr_candidates(0, 0, 100_000, 60, 100_000)            # the reference stops the program here
+    cands, _, _, _ = fresh.bam_sr_candidates(0, 0, 100_000, 61, 100_000)
+    assert cands.size > 0
+    fresh.close()
+
+
+@pytest.mark.skipif(not os.path.exists(DEMO), reason="oracle/_ref/pindel_gpu_demo not built (needs /root/reference at build time)")
+def test_reference_host_bam_input_with_the_device_filter(tmp_path):
+    env = dict(os.environ, PG_BRIDGE_SR_FILTER="1", LD_LIBRARY_PATH=os.path.join(ROOT, "pindel_b200") + ":" + os.environ.get("LD_LIBRARY_PATH", ""))
+    D.sim_prefix_bam(DEMO, tmp_path, env)
