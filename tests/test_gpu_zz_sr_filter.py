@@ -22,6 +22,16 @@ GOLD = os.path.join(ROOT, "tests", "golden")
 DEMO = os.path.join(ROOT, "oracle", "_ref", "pindel_gpu_demo")
 
 
+def _diff(got, exp):
+    """a message that says where two row tables part (this file's first hardware run is unattended)"""
+    if got.shape != exp.shape:
+        k = min(got.shape[0], exp.shape[0])
+        bad = np.nonzero((got[:k] != exp[:k]).any(axis=1))[0]
+        return "shape %s vs %s; first differing row %s" % (got.shape, exp.shape, (int(bad[0]), got[bad[0]].tolist(), exp[bad[0]].tolist()) if bad.size else "none in the common prefix")
+    bad = np.nonzero((got != exp).any(axis=1))[0]
+    return "%d of %d rows differ; first: row %d %s vs %s" % (bad.size, got.shape[0], int(bad[0]), got[bad[0]].tolist(), exp[bad[0]].tolist()) if bad.size else "equal"
+
+
 @pytest.fixture(scope="module")
 def pg():
     p = api.PatternGrowth()
@@ -39,8 +49,8 @@ def test_matches_reference_dumps(pg, case):
     for k, (tid, beg, end, isz, min_q) in enumerate(G.QUERIES[case]):
         cands, seqs, refs, _ = pg.bam_sr_candidates(tid, beg, end, isz, int(z["chr_len"][tid]), min_anchor_quality=min_q)
         c, r = rows_of_product(stream, recs, cands, seqs, refs, isz)
-        assert np.array_equal(c, z["cand_%d" % k]), ("candidates", case, k)
-        assert np.array_equal(r, z["refs_%d" % k]), ("reference-supporting reads", case, k)
+        assert np.array_equal(c, z["cand_%d" % k]), ("candidates", case, k, _diff(c, z["cand_%d" % k]))
+        assert np.array_equal(r, z["refs_%d" % k]), ("reference-supporting reads", case, k, _diff(r, z["refs_%d" % k]))
 
 
 def test_matches_oracle_on_a_larger_stream(pg):
@@ -52,7 +62,8 @@ def test_matches_oracle_on_a_larger_stream(pg):
         exp_c, exp_r = sroracle.candidates(stream, table, tid, beg, end, isz, G.SYNTH_REFS[tid][1], min_anchor_quality=min_q)
         cands, seqs, refs, scanned = pg.bam_sr_candidates(tid, beg, end, isz, G.SYNTH_REFS[tid][1], min_anchor_quality=min_q)
         c, r = rows_of_product(stream, recs, cands, seqs, refs, isz)
-        assert np.array_equal(c, exp_c) and np.array_equal(r, exp_r), (tid, beg, end, isz, min_q)
+        assert np.array_equal(c, exp_c), ("candidates", tid, beg, end, isz, min_q, _diff(c, exp_c))
+        assert np.array_equal(r, exp_r), ("reference-supporting reads", tid, beg, end, isz, min_q, _diff(r, exp_r))
         assert scanned >= cands.size // 3
 
 
@@ -64,7 +75,8 @@ def test_repeated_names_pair_by_rank(pg):
         exp_c, exp_r = sroracle.candidates(stream, bam.serial_index(stream), 0, 0, 100_000, 500, 100_000)
         cands, seqs, refs, scanned = pg.bam_sr_candidates(0, 0, 100_000, 500, 100_000)
         c, r = rows_of_product(stream, recs, cands, seqs, refs, 500)
-        assert scanned == len(names) and np.array_equal(c, exp_c) and np.array_equal(r, exp_r), names
+        assert scanned == len(names), (scanned, names)
+        assert np.array_equal(c, exp_c) and np.array_equal(r, exp_r), (names, _diff(c, exp_c), _diff(r, exp_r))
 
 
 def test_errors(pg):
