@@ -313,7 +313,8 @@ int pg_bam_rp_discovery(pg_ctx *ctx, const pg_rp_query *q, struct pg_rp *rows, u
  * InsertSize itself from the records `anchor` / `read` index.  n_scanned: records delivered (g_NumReadScanned's increase).
  * PG_ERR_RUNS_CAP: a buffer is too small (*n_cands, *n_refs, *stride hold the required sizes; pass NULL buffers to ask);
  * PG_ERR_DATA: a candidate's sequence is not shorter than insert_size -- the reference stops the program there
- * (src/reader.cpp:866-874); PG_ERR_STATE: no indexed stream is resident (pg_bgzf_inflate + pg_bam_index). */
+ * (src/reader.cpp:866-874) -- or a record of the window is malformed (its name, CIGAR and sequence do not fit its block_size:
+ * htslib's bam_read1 fails on it); PG_ERR_STATE: no indexed stream is resident (pg_bgzf_inflate + pg_bam_index). */
 typedef struct pg_sr_query {
    int32_t tid;                   /* bam_name2id(header, FragName) */
    int32_t beg, end;              /* the window: sam_itr_queryi(idx, tid, window.getStart(), window.getEnd()) */

@@ -56,6 +56,7 @@ struct PgSrInfo {
 #define PGSR_REFREAD 8u           // isRefRead
 #define PGSR_SEQ_OK 16u           // passes build_record_SR's N filter and minimum length as the read
 #define PGSR_QUAL_OK 32u          // passes build_record_SR's / build_record_RefRead's quality test
+#define PGSR_MALFORMED 64u        // the variable-length fields do not fit the record's block_size (htslib's bam_read1 fails there)
 
 #define PGSR_E_SELF 1u            // waiting record: build_record_SR(b1, b1)
 #define PGSR_E0 2u                // completing record b1 with waiting b2: build_record_SR(b2, b2)
@@ -64,6 +65,7 @@ struct PgSrInfo {
 #define PGSR_E2 16u               //    build_record_SR(b2, b1)
 #define PGSR_R1 32u               //    build_record_RefRead(b2, b1)
 #define PGSR_ERR_INSERT 64u       // a call would stop the reference: InsertSize <= length (src/reader.cpp:866-874)
+#define PGSR_ERR_MALFORMED 128u   // a delivered record is malformed: nothing is returned for the window
 #define PGSR_NONE 0xFFFFFFFFu
 
 // bam_aux_get(b, "NM") + bam_aux2i: walk the tag list; *found = the tag exists.  A malformed list ends the walk.
@@ -145,9 +147,14 @@ PGB_HD void pgsr_analyse(const uint8_t *d, const PgBamRec &r, const PgSrQuery &q
    const uint32_t l_name = rec[8], n_cigar = pgb_le16(rec + 12), flag = r.flag, l_qseq = pgb_le32(rec + 16);
    const uint8_t *cig = rec + 32 + l_name, *seq = cig + 4ull * n_cigar;
    const uint8_t *aux = seq + (l_qseq + 1u) / 2u + l_qseq, *end = rec + rec_len;
-   info.key = pgsr_name_key(rec);
    info.lead = info.length = 0;
    for (int k = 0; k < 7; k++) info.pad[k] = 0;
+   if (l_name == 0 || 32ull + l_name + 4ull * n_cigar + (l_qseq + 1ull) / 2ull + l_qseq > rec_len) {      // never look inside such a record
+      info.key = 1;
+      info.bits = (uint8_t)(PGSR_DELIVERED | PGSR_MALFORMED);
+      return;
+   }
+   info.key = pgsr_name_key(rec);
    uint32_t bits = PGSR_DELIVERED;
    const bool mapped = !(flag & 4u);
    bool has_nm = false;
@@ -195,6 +202,7 @@ PGB_HD uint32_t pgsr_emit_mask(const PgSrInfo &self, const PgSrInfo *partner, co
 {
    uint32_t m = 0;
    const uint32_t b1 = self.bits;
+   if (b1 & PGSR_MALFORMED) return PGSR_ERR_MALFORMED;
    #define PGSR_BUILD(anchor_bits, read) \
       (((anchor_bits) & PGSR_QUAL_OK) && ((read).bits & PGSR_SEQ_OK) ? ((q.insert_size <= (int32_t)(read).length) ? PGSR_ERR_INSERT : 1u) : 0u)
    if (!partner) {
@@ -337,7 +345,7 @@ __global__ void pg_sr_insert_kernel(const PgSrInfo *__restrict__ info, uint32_t 
                                     uint32_t table_mask, uint32_t *__restrict__ slot, uint32_t *__restrict__ next)
 {
    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-   if (i >= n_recs || !(info[i].bits & PGSR_DELIVERED)) return;
+   if (i >= n_recs || (info[i].bits & (PGSR_DELIVERED | PGSR_MALFORMED)) != PGSR_DELIVERED) return;
    const unsigned long long key = info[i].key;
    uint32_t s = (uint32_t)(key >> 20) & table_mask;
    for (;;) {
@@ -359,9 +367,9 @@ __global__ void pg_sr_pair_kernel(const uint8_t *__restrict__ d, const PgBamRec 
    if (i >= n_recs) return;
    uint32_t mask = 0, p = PGSR_NONE;
    if (info[i].bits & PGSR_DELIVERED) {
-      p = pgsr_partner(d, recs, next, head[slot[i]], i);
+      if (!(info[i].bits & PGSR_MALFORMED)) p = pgsr_partner(d, recs, next, head[slot[i]], i);
       mask = pgsr_emit_mask(info[i], p == PGSR_NONE ? (const PgSrInfo *)0 : &info[p], q);
-      if (mask & PGSR_ERR_INSERT) atomicOr(&counters[3], PGSR_ERR_INSERT);
+      if (mask & (PGSR_ERR_INSERT | PGSR_ERR_MALFORMED)) atomicOr(&counters[3], mask & (PGSR_ERR_INSERT | PGSR_ERR_MALFORMED));
    }
    partner[i] = p;
    emit[i] = (uint8_t)mask;

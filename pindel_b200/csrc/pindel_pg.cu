@@ -1588,6 +1588,8 @@ int pg_bam_sr_candidates(pg_ctx *ctx, const pg_sr_query *q, pg_sr_cand *cands, u
    CU(cudaMemcpyAsync(&tot_ref, sums_ref + n_blocks, sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
    CU(cudaStreamSynchronize(st));
    if (n_scanned) *n_scanned = counters[1];
+   if (counters[3] & PGSR_ERR_MALFORMED)
+      return fail(ctx, PG_ERR_DATA, "pg_bam_sr_candidates: an alignment record of the window is malformed (its fields do not fit its block_size)");
    if (counters[3] & PGSR_ERR_INSERT)
       return fail(ctx, PG_ERR_DATA, "pg_bam_sr_candidates: the insert size is not larger than a candidate read (the reference stops here, src/reader.cpp:866)");
    const uint32_t str = counters[2] ? counters[2] : 1u;

@@ -288,6 +288,7 @@ int pg_bam_sr_candidates(pg_ctx *ctx, const pg_sr_query *q, pg_sr_cand *cands, u
    if (sremu_candidates(ctx->stream.data(), ctx->bam_table.data(), n, (const PgSrQuery *)q, 17u, 0, 0, NULL, NULL, NULL, counts) != 0)
       return fail(ctx, PG_ERR_DATA, "name table");
    if (n_scanned) *n_scanned = counts[3];
+   if (counts[4] & PGSR_ERR_MALFORMED) return fail(ctx, PG_ERR_DATA, "an alignment record of the window is malformed");
    if (counts[4]) return fail(ctx, PG_ERR_DATA, "the insert size is not larger than a candidate read");
    const uint32_t str = counts[2] ? (uint32_t)counts[2] : 1u;
    *n_cands = counts[0]; *n_refs = counts[1]; *stride = str;

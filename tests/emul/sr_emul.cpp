@@ -27,7 +27,7 @@ int sremu_candidates(const uint8_t *d, const PgBamRec *recs, uint32_t n_recs, co
       memset(&info[i], 0, sizeof(PgSrInfo));
       if (i < stop && pgb_itr_delivers(recs[i], itr)) {
          pgsr_analyse(d, recs[i], *q, info[i]);
-         if (hash_mask) { info[i].key &= hash_mask; if (!info[i].key) info[i].key = 1; }
+         if (hash_mask && !(info[i].bits & PGSR_MALFORMED)) { info[i].key &= hash_mask; if (!info[i].key) info[i].key = 1; }
          delivered++;
          if (info[i].length > stride) stride = info[i].length;
       }
@@ -48,7 +48,7 @@ int sremu_candidates(const uint8_t *d, const PgBamRec *recs, uint32_t n_recs, co
       }
    for (uint32_t k = 0; k < n_recs; k++) {              // pg_sr_insert_kernel
       const uint32_t i = order[k];
-      if (!(info[i].bits & PGSR_DELIVERED)) continue;
+      if ((info[i].bits & (PGSR_DELIVERED | PGSR_MALFORMED)) != PGSR_DELIVERED) continue;
       uint32_t s = (uint32_t)(info[i].key >> 20) & mask;
       while (keys[s] != 0 && keys[s] != info[i].key) s = (s + 1u) & mask;
       keys[s] = info[i].key;
@@ -61,9 +61,9 @@ int sremu_candidates(const uint8_t *d, const PgBamRec *recs, uint32_t n_recs, co
    uint32_t err = 0, n_sr = 0, n_ref = 0;
    for (uint32_t i = 0; i < n_recs; i++) {              // pg_sr_pair_kernel + the two scans
       if (info[i].bits & PGSR_DELIVERED) {
-         partner[i] = pgsr_partner(d, recs, next.data(), head[slot[i]], i);
+         if (!(info[i].bits & PGSR_MALFORMED)) partner[i] = pgsr_partner(d, recs, next.data(), head[slot[i]], i);
          const uint32_t m = pgsr_emit_mask(info[i], partner[i] == PGSR_NONE ? (const PgSrInfo *)0 : &info[partner[i]], *q);
-         err |= m & PGSR_ERR_INSERT;
+         err |= m & (PGSR_ERR_INSERT | PGSR_ERR_MALFORMED);
          emit[i] = (uint8_t)m;
       }
       off_sr[i] = n_sr; off_ref[i] = n_ref;

@@ -114,3 +114,20 @@ def test_plain_pairs_give_reference_reads_only(libs):
     exp_c, exp_r = sroracle.candidates(stream, bam.serial_index(stream), 0, 0, 100_000, 500, 100_000)
     assert cands.size == 0 and exp_c.shape[0] == 0 and refs.size == 20 and exp_r.shape[0] == 20
     assert np.array_equal(rows_of_product(stream, recs, cands, seqs, refs, 500)[1], exp_r)
+
+
+def test_malformed_record_in_the_window_is_an_error(libs):
+    """a record whose CIGAR count points past its block_size: never looked into, reported; outside the window it is harmless"""
+    import struct
+    lib, bl = libs
+    stream = bytearray(named_stream([b"x", b"y", b"x", b"z"]))
+    recs, _ = bam_emul.index(bl, bytes(stream))
+    off = int(recs["off"][2])
+    struct.pack_into("<H", stream, off + 4 + 12, 60000)            # n_cigar_op
+    stream = bytes(stream)
+    recs, _ = bam_emul.index(bl, stream)
+    assert recs.size == 4
+    _, _, _, _, err = sr_emul.candidates(lib, stream, recs, sr_emul.query(0, 0, 100_000, 500, 100_000), 3)
+    assert err & 128
+    cands, _, _, delivered, err = sr_emul.candidates(lib, stream, recs, sr_emul.query(0, 0, 1015, 500, 100_000))       # records 0 and 1 only
+    assert err == 0 and delivered == 2 and cands.size == 2
