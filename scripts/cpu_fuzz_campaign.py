@@ -19,6 +19,7 @@ sys.path.insert(0, ROOT)
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--rounds", type=int, default=30)
+    ap.add_argument("--seed", type=int, default=2026)
     a = ap.parse_args()
     from oracle import boxsortoracle as B, refhook, rporacle
     from pindel_b200 import bgzf, synth
@@ -27,11 +28,11 @@ def main():
     from tests.golden.make_rp_golden import rows_from_table
     assert refhook.available(), "needs oracle/_ref (build in the container that has /root/reference)"
     rp_lib, box_lib, z_lib = rp_emul.build(), boxsort_emul.build(), bgzf_emul.build()
-    rng = np.random.default_rng(2026)
+    rng = np.random.default_rng(a.seed)
     for r in range(a.rounds):
         # read-pair clustering: spans from dense to sparse, 1-3 libraries, with and without duplicates
         libs = [((100, 250),), ((150, 500),), ((100, 250), (150, 500)), ((76, 200), (100, 350), (150, 600))][int(rng.integers(0, 4))]
-        rows = synth.make_discordant_pairs(int(rng.integers(1, 200)), 5000 + r, span=int(rng.choice([60_000, 400_000, 5_000_000, 60_000_000])),
+        rows = synth.make_discordant_pairs(int(rng.integers(1, 200)), 5000 + r + 1000 * (a.seed - 2026), span=int(rng.choice([60_000, 400_000, 5_000_000, 60_000_000])),
                                            background=int(rng.integers(0, 300)), max_support=int(rng.integers(2, 80)), libraries=libs,
                                            both_mates=float(rng.choice([0.0, 0.5, 0.9])))
         table, tags, _ = refhook.rp_cluster(rows)
@@ -45,14 +46,14 @@ def main():
                 holder[x] = i
         assert all(holder[int(table[i, 0])] == int(got["merged_into"][i]) for i in range(srt.size)), ("rp tags", r)
         # the inter-chromosomal variants
-        irows, ica, icb = synth.make_interchr_pairs(int(rng.integers(1, 120)), 6000 + r, n_chr=int(rng.integers(2, 7)),
+        irows, ica, icb = synth.make_interchr_pairs(int(rng.integers(1, 120)), 6000 + r + 1000 * (a.seed - 2026), n_chr=int(rng.integers(2, 7)),
                                                     max_support=int(rng.integers(2, 70)), background=int(rng.integers(0, 200)))
         itable, itags, isa, isb = refhook.rp_cluster_interchr(irows, ica, icb)
         _, igot = rp_emul.cluster_interchr(rp_lib, rows_from_table(itable), isa, isb)
         for col, key in ((7, "pos_a"), (8, "pos_a1"), (9, "pos_b"), (10, "pos_b1"), (11, "visited"), (12, "report"), (13, "n_identical")):
             assert np.array_equal(igot[key].astype(np.int64), itable[:, col]), ("rp interchr", r, key)
         # per-box ordering
-        reads, box_off, idx = B.make_boxes(int(rng.integers(1, 120)), 7000 + r, max_reads=int(rng.integers(3, 120)), heavy=int(rng.integers(0, 2)))
+        reads, box_off, idx = B.make_boxes(int(rng.integers(1, 120)), 7000 + r + 1000 * (a.seed - 2026), max_reads=int(rng.integers(3, 120)), heavy=int(rng.integers(0, 2)))
         r_idx, r_unique = B.reference_sort_boxes(reads, box_off, idx)
         for warp in (False, True):
             order, non = boxsort_emul.sort_boxes(box_lib, reads[idx], box_off, warp)
@@ -61,7 +62,7 @@ def main():
         # BGZF inflate
         kind = int(rng.integers(0, 4))
         n = int(rng.integers(0, 400_000))
-        payload = (synth.make_bam_like_bytes(n, 9000 + r) if kind == 0 else bytes(rng.integers(0, int(rng.integers(2, 257)), n, dtype=np.uint8)) if kind == 1
+        payload = (synth.make_bam_like_bytes(n, 9000 + r + 1000 * (a.seed - 2026)) if kind == 0 else bytes(rng.integers(0, int(rng.integers(2, 257)), n, dtype=np.uint8)) if kind == 1
                    else bytes(rng.choice(40, size=n, p=(lambda p: p / p.sum())(0.6 ** np.arange(40))).astype(np.uint8)) if kind == 2
                    else (b"ACGT" * 50 + bytes(rng.integers(0, 256, 30, dtype=np.uint8))) * (n // 230 + 1))
         comp = bgzf.compress(payload, level=int(rng.integers(0, 10)), block=int(rng.choice([0x4000, 0x7000])) if kind == 1 else 0xff00,

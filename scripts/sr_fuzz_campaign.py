@@ -19,6 +19,7 @@ sys.path.insert(0, ROOT)
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--rounds", type=int, default=40)
+    ap.add_argument("--first-seed", type=int, default=100)
     a = ap.parse_args()
     from oracle import refhook, sroracle
     from pindel_b200 import bam, bgzf
@@ -34,7 +35,7 @@ def main():
     h = refhook.RefHook(fa, [], workdir=tmp)
     path = os.path.join(tmp, "x.bam")
     total = 0
-    for seed in range(100, 100 + a.rounds):
+    for seed in range(a.first_seed, a.first_seed + a.rounds):
         stream = F.fuzz_stream(seed, 800)
         open(path, "wb").write(bgzf.compress(stream))
         open(path + ".bai", "wb").write(b"BAI\x01\x00\x00\x00\x00")
