@@ -280,6 +280,15 @@ typedef struct pg_bam_rec {
    uint8_t mapq, pad;
 } pg_bam_rec;
 int pg_bam_index(pg_ctx *ctx, pg_bam_rec *recs, uint64_t cap, uint64_t *n_recs, uint64_t *first_record, int32_t *n_ref);
+/* The same table for a run of whole BGZF blocks cut out of a file -- what htslib reads for one window: the blocks between the
+ * virtual offsets hts_itr_t holds for the region (iter->off[i].u / .v; coffset = voffset >> 16, uoffset = voffset & 0xffff) --
+ * after pg_bgzf_inflate of just those blocks.  No BAM header is in front, so the caller passes first_record (the uoffset of the
+ * chunk's first record inside the first block) and n_ref (bam_hdr_t::n_targets).  The last record may continue in a block that
+ * was not read: the chain stops in front of it and *tail tells where it starts (== the stream length when nothing is cut off),
+ * so the caller can read on from there.  pg_bam_rp_discovery / pg_bam_sr_candidates then work on this table as on a whole
+ * file's (record offsets are relative to the run).  PG_ERR_DATA: the chain from first_record meets a block_size that cannot
+ * be a record. */
+int pg_bam_index_run(pg_ctx *ctx, uint64_t first_record, int32_t n_ref, pg_bam_rec *recs, uint64_t cap, uint64_t *n_recs, uint64_t *tail);
 uint64_t pg_bam_launches(pg_ctx *ctx);
 double pg_bam_last_ms(pg_ctx *ctx);            /* CUDA-event duration of the last pg_bam_index (kernels + its small copies) */
 void pg_bam_last_segments(pg_ctx *ctx, uint32_t *segments, uint32_t *walked_again);

@@ -305,6 +305,19 @@ public:
       return recs;
    }
 
+   // the same for a run of BGZF blocks (one window's chunk): first_record = uoffset of the chunk's first record, n_ref =
+   // bam_hdr_t::n_targets; *tail = where a record cut off by the end of the run starts (the stream's length if none)
+   std::vector<pg_bam_rec> IndexBamRun(uint64_t first_record, int32_t n_ref, uint64_t *tail)
+   {
+      uint64_t n = 0, t = 0;
+      int rc = pg_bam_index_run(ctx_, first_record, n_ref, NULL, 0, &n, &t);
+      if (rc != PG_OK && rc != PG_ERR_RUNS_CAP) check(rc, "pg_bam_index_run");
+      std::vector<pg_bam_rec> recs((size_t)n);
+      if (n) check(pg_bam_index_run(ctx_, first_record, n_ref, recs.data(), n, &n, &t), "pg_bam_index_run");
+      if (tail) *tail = t;
+      return recs;
+   }
+
    // ReadInBamReads_SR (src/reader.cpp:483-560) for one window of the stream InflateBam + IndexBam left on the device: the
    // reads build_record_SR would hand to the ReadBuffer are appended to Reads (Name, UnmatchedSeq, MatchedD, MatchedRelPos, MS,
    // InsertSize; chromosome_id = the caller's index of FragName), the reads build_record_RefRead keeps to RefSupportingReads.

@@ -99,6 +99,7 @@ def load_library() -> C.CDLL:
         lib.pg_bgzf_last_kernel_ms.restype = C.c_double
         lib.pg_bgzf_last_kernel_ms.argtypes = [C.c_void_p]
         lib.pg_bam_index.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64), C.POINTER(C.c_int32)]
+        lib.pg_bam_index_run.argtypes = [C.c_void_p, C.c_uint64, C.c_int32, C.c_void_p, C.c_uint64, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]
         lib.pg_bam_rp_discovery.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.POINTER(C.c_uint64), C.c_void_p, C.c_void_p,
                                             C.c_uint64, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]
         lib.pg_bam_sr_candidates.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.POINTER(C.c_uint64), C.c_void_p, C.c_uint64,
@@ -382,6 +383,20 @@ class PatternGrowth:
                 return recs, int(first.value), int(nref.value)
         self._check(self.lib.pg_bam_index(self.ctx, recs.ctypes.data, recs.size, C.byref(n), C.byref(first), C.byref(nref)), "pg_bam_index")
         return recs[:n.value], int(first.value), int(nref.value)
+
+    def bam_index_run(self, first_record: int, n_ref: int):
+        """Record table of a headerless run of BGZF blocks left on the device by bgzf_inflate (a window's chunk): the first
+        record starts at first_record, the last one may be cut off.  -> (records, tail offset)"""
+        from . import bam
+        n, tail = C.c_uint64(0), C.c_uint64(0)
+        rc = self.lib.pg_bam_index_run(self.ctx, C.c_uint64(first_record), n_ref, None, C.c_uint64(0), C.byref(n), C.byref(tail))
+        if rc not in (0, PG_ERR_RUNS_CAP):
+            self._check(rc, "pg_bam_index_run")
+        recs = np.zeros(int(n.value), dtype=bam.REC_DT)
+        if recs.size:
+            self._check(self.lib.pg_bam_index_run(self.ctx, C.c_uint64(first_record), n_ref, recs.ctypes.data, C.c_uint64(recs.size), C.byref(n), C.byref(tail)),
+                        "pg_bam_index_run")
+        return recs, int(tail.value)
 
     def bam_rp_discovery(self, tid, beg, end, insert_size, min_anchor_quality=0):
         """Discordant-pair discovery on the indexed stream (after bgzf_inflate + bam_index).

@@ -112,6 +112,25 @@ PGB_HD uint64_t pgb_walk(const uint8_t *d, uint64_t n, uint64_t start, uint64_t 
    return c;
 }
 
+// The same walk over a *run* of BGZF blocks cut out of a file (the chunk of a window between two .bai virtual offsets): the
+// last record may continue in a block that is not there.  The walk stops in front of the first record that does not fit and
+// returns its offset (< limit and < n: the run's tail); PGB_NONE only for a block_size that cannot be a record.
+PGB_HD uint64_t pgb_walk_run(const uint8_t *d, uint64_t n, uint64_t start, uint64_t limit, PgBamRec *recs, uint64_t *count)
+{
+   uint64_t c = start, k = 0;
+   while (c < limit && c < n) {
+      if (c + 4 > n) break;
+      const uint64_t next = c + 4 + (uint64_t)pgb_le32(d + c);
+      if (next < c + 36) return PGB_NONE;
+      if (next > n) break;
+      if (recs) pgb_fill(d, c, recs[k]);
+      k++;
+      c = next;
+   }
+   *count = k;
+   return c;
+}
+
 // BAM header: magic, l_text, text, n_ref, (l_name, name, l_ref) per reference.  -> offset of the first record.
 PGB_HD uint64_t pgb_header(const uint8_t *d, uint64_t n, int32_t *n_ref)
 {
@@ -231,6 +250,23 @@ __global__ void pg_bam_walk_kernel(const uint8_t *__restrict__ d, uint64_t n, ui
    const uint64_t b1 = first + (uint64_t)(s + 1) * seg;
    uint64_t k = 0;
    const uint64_t land = pgb_walk(d, n, st, b1 < n ? b1 : n, recs ? recs + base[s] : (PgBamRec *)0, &k);
+   if (!recs) { counts[s] = land == PGB_NONE ? 0 : k; landing[s] = land; }
+}
+// pg_bam_walk_kernel for a run of blocks (pgb_walk_run: a truncated last record ends the chain instead of failing it)
+__global__ void pg_bam_walk_run_kernel(const uint8_t *__restrict__ d, uint64_t n, uint64_t first, uint64_t seg, uint32_t n_seg,
+                                       const uint64_t *__restrict__ starts, uint64_t *__restrict__ counts, uint64_t *__restrict__ landing,
+                                       const uint64_t *__restrict__ base, PgBamRec *__restrict__ recs)
+{
+   const uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
+   if (s >= n_seg) return;
+   const uint64_t st = starts[s];
+   if (st == PGB_NONE) {
+      if (!recs) { counts[s] = 0; landing[s] = PGB_NONE; }
+      return;
+   }
+   const uint64_t b1 = first + (uint64_t)(s + 1) * seg;
+   uint64_t k = 0;
+   const uint64_t land = pgb_walk_run(d, n, st, b1 < n ? b1 : n, recs ? recs + base[s] : (PgBamRec *)0, &k);
    if (!recs) { counts[s] = land == PGB_NONE ? 0 : k; landing[s] = land; }
 }
 // counters: [0] index of the first record past the region (initialised to n_recs), [1] records delivered

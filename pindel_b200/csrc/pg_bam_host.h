@@ -33,3 +33,32 @@ static inline long pgb_validate(uint32_t n_seg, uint64_t first, uint64_t n, uint
    *total = sum;
    return 0;
 }
+
+// The same for a run of blocks (pgb_walk_run): the chain may end in front of a record that is cut off by the end of the run.
+// A segment whose walk stopped before its own end (landing < min(segment end, n)) is where that happens: *tail = its landing
+// offset, later segments keep nothing.  *tail == n when the run ends on a record boundary.
+static inline long pgb_validate_run(uint32_t n_seg, uint64_t first, uint64_t n, uint64_t seg, const uint64_t *starts, uint64_t *counts,
+                                    const uint64_t *landing, uint64_t *forced, uint64_t *total, uint64_t *tail)
+{
+   uint64_t cur = first, sum = 0;
+   bool ended = false;
+   for (uint32_t s = 0; s < n_seg; s++) {
+      const uint64_t b1 = first + (uint64_t)(s + 1) * seg, lim = b1 < n ? b1 : n;
+      if (ended || cur >= n || cur >= b1) {
+         counts[s] = 0;
+         continue;
+      }
+      if (starts[s] != cur) {
+         *forced = cur;
+         return 1 + (long)s;
+      }
+      if (landing[s] == PGB_NONE) return -1;
+      sum += counts[s];
+      cur = landing[s];
+      if (cur < lim) ended = true;          // stopped in front of a record that does not fit
+   }
+   if (cur > n) return -1;
+   *total = sum;
+   *tail = cur;
+   return 0;
+}

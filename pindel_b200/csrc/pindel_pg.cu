@@ -1423,6 +1423,81 @@ int pg_bam_index(pg_ctx *ctx, pg_bam_rec *recs, uint64_t cap, uint64_t *n_recs, 
    return PG_OK;
 }
 
+// The record table of a run of BGZF blocks (a window's chunk between two .bai virtual offsets) instead of a whole file: no BAM
+// header in front -- the caller says where the first record starts and how many references the file has -- and the last
+// record may be cut off by the end of the run (*tail = where it starts; == the stream's length when nothing is cut off).
+int pg_bam_index_run(pg_ctx *ctx, uint64_t first_record, int32_t n_ref, pg_bam_rec *recs, uint64_t cap, uint64_t *n_recs, uint64_t *tail)
+{
+   if (!ctx || !n_recs || !tail) return fail(ctx, PG_ERR_ARG, "pg_bam_index_run: null argument");
+   if (ctx->bz_out_len == 0) return fail(ctx, PG_ERR_STATE, "pg_bam_index_run: no inflated stream is resident (call pg_bgzf_inflate)");
+   const uint64_t n = ctx->bz_out_len;
+   if (first_record > n || n_ref < 0) return fail(ctx, PG_ERR_ARG, "pg_bam_index_run: first_record beyond the stream or negative n_ref");
+   CU(cudaSetDevice(ctx->device));
+   cudaStream_t st = ctx->stream;
+   const uint8_t *d = (const uint8_t *)ctx->bz_out.p;
+   const uint64_t first = first_record, seg = PGB_SEGMENT;
+   ctx->bm_valid = false;
+   int rc;
+   if (!ctx->sv_ev0) { CU(cudaEventCreate(&ctx->sv_ev0)); CU(cudaEventCreate(&ctx->sv_ev1)); }
+   CU(cudaEventRecord(ctx->sv_ev0, st));
+   const uint32_t n_seg = first >= n ? 1u : (uint32_t)((n - first + seg - 1) / seg);
+   if ((rc = ensure(ctx, ctx->bm_starts, sizeof(uint64_t) * (size_t)n_seg)) != PG_OK) return rc;
+   if ((rc = ensure(ctx, ctx->bm_counts, sizeof(uint64_t) * (size_t)n_seg)) != PG_OK) return rc;
+   if ((rc = ensure(ctx, ctx->bm_landing, sizeof(uint64_t) * (size_t)n_seg)) != PG_OK) return rc;
+   if ((rc = ensure(ctx, ctx->bm_base, sizeof(uint64_t) * (size_t)n_seg)) != PG_OK) return rc;
+   pg_bam_start_kernel<<<(n_seg + 7) / 8, 256, 0, st>>>(d, n, first, seg, n_seg, n_ref, (uint64_t *)ctx->bm_starts.p);
+   ctx->bm_launches++;
+   std::vector<uint64_t> starts(n_seg), counts(n_seg), landing(n_seg), base(n_seg);
+   uint64_t total = 0, tail_off = n;
+   uint32_t redone = 0;
+   for (;;) {
+      pg_bam_walk_run_kernel<<<(n_seg + 127) / 128, 128, 0, st>>>(d, n, first, seg, n_seg, (const uint64_t *)ctx->bm_starts.p, (uint64_t *)ctx->bm_counts.p,
+                                                                 (uint64_t *)ctx->bm_landing.p, nullptr, nullptr);
+      CU(cudaGetLastError());
+      ctx->bm_launches++;
+      CU(cudaMemcpyAsync(starts.data(), ctx->bm_starts.p, sizeof(uint64_t) * (size_t)n_seg, cudaMemcpyDeviceToHost, st));
+      CU(cudaMemcpyAsync(counts.data(), ctx->bm_counts.p, sizeof(uint64_t) * (size_t)n_seg, cudaMemcpyDeviceToHost, st));
+      CU(cudaMemcpyAsync(landing.data(), ctx->bm_landing.p, sizeof(uint64_t) * (size_t)n_seg, cudaMemcpyDeviceToHost, st));
+      CU(cudaStreamSynchronize(st));
+      uint64_t forced = 0;
+      const long v = pgb_validate_run(n_seg, first, n, seg, starts.data(), counts.data(), landing.data(), &forced, &total, &tail_off);
+      if (v < 0) return fail(ctx, PG_ERR_DATA, "pg_bam_index_run: a block_size in the record chain cannot be a record (wrong first_record or corrupt BAM)");
+      if (v == 0) break;
+      CU(cudaMemcpyAsync((uint64_t *)ctx->bm_starts.p + (v - 1), &forced, sizeof(uint64_t), cudaMemcpyHostToDevice, st));
+      CU(cudaStreamSynchronize(st));
+      redone++;
+   }
+   ctx->bm_last_segments = n_seg;
+   ctx->bm_last_redone = redone;
+   *n_recs = total;
+   *tail = tail_off;
+   if (total > cap || (total && !recs)) {
+      CU(cudaEventRecord(ctx->sv_ev1, st));
+      return fail(ctx, PG_ERR_RUNS_CAP, "pg_bam_index_run: record buffer too small (n_recs holds the required size)");
+   }
+   if (total) {
+      uint64_t b = 0;
+      for (uint32_t s = 0; s < n_seg; s++) { base[s] = b; b += counts[s]; }
+      for (uint32_t s = 0; s < n_seg; s++) if (counts[s] == 0) starts[s] = PGB_NONE;
+      if ((rc = ensure(ctx, ctx->bm_recs, sizeof(PgBamRec) * (size_t)total)) != PG_OK) return rc;
+      CU(cudaMemcpyAsync(ctx->bm_starts.p, starts.data(), sizeof(uint64_t) * (size_t)n_seg, cudaMemcpyHostToDevice, st));
+      CU(cudaMemcpyAsync(ctx->bm_base.p, base.data(), sizeof(uint64_t) * (size_t)n_seg, cudaMemcpyHostToDevice, st));
+      pg_bam_walk_run_kernel<<<(n_seg + 127) / 128, 128, 0, st>>>(d, n, first, seg, n_seg, (const uint64_t *)ctx->bm_starts.p, nullptr, nullptr,
+                                                                 (const uint64_t *)ctx->bm_base.p, (PgBamRec *)ctx->bm_recs.p);
+      CU(cudaGetLastError());
+      ctx->bm_launches++;
+      CU(cudaEventRecord(ctx->sv_ev1, st));
+      CU(cudaMemcpyAsync(recs, ctx->bm_recs.p, sizeof(PgBamRec) * (size_t)total, cudaMemcpyDeviceToHost, st));
+   } else {
+      CU(cudaEventRecord(ctx->sv_ev1, st));
+   }
+   CU(cudaStreamSynchronize(st));
+   CU(cudaEventElapsedTime(&ctx->bm_last_ms, ctx->sv_ev0, ctx->sv_ev1));
+   ctx->bm_n_recs = total;
+   ctx->bm_valid = true;
+   return PG_OK;
+}
+
 uint64_t pg_bam_launches(pg_ctx *ctx) { return ctx ? ctx->bm_launches : 0; }
 double pg_bam_last_ms(pg_ctx *ctx) { return ctx ? (double)ctx->bm_last_ms : 0.0; }
 void pg_bam_last_segments(pg_ctx *ctx, uint32_t *segments, uint32_t *walked_again)

@@ -262,6 +262,20 @@ int pg_bam_index(pg_ctx *ctx, pg_bam_rec *recs, uint64_t cap, uint64_t *n_recs, 
    ctx->bam_table.assign((const PgBamRec *)recs, (const PgBamRec *)recs + n);
    return PG_OK;
 }
+int pg_bam_index_run(pg_ctx *ctx, uint64_t first_record, int32_t n_ref, pg_bam_rec *recs, uint64_t cap, uint64_t *n_recs, uint64_t *tail)
+{
+   if (ctx->stream.empty()) return fail(ctx, PG_ERR_STATE, "no inflated stream");
+   if (first_record > ctx->stream.size()) return fail(ctx, PG_ERR_ARG, "first_record beyond the stream");
+   uint64_t stats[4] = {0, 0, 0, 0};
+   const long n = bamemu_index_run(ctx->stream.data(), ctx->stream.size(), first_record, n_ref, 0, NULL, 0, stats);
+   if (n < 0) return fail(ctx, PG_ERR_DATA, "impossible block_size in the chain");
+   *n_recs = (uint64_t)n;
+   *tail = stats[3];
+   if ((uint64_t)n > cap || (n && !recs)) return fail(ctx, PG_ERR_RUNS_CAP, "record buffer too small");
+   bamemu_index_run(ctx->stream.data(), ctx->stream.size(), first_record, n_ref, 0, (PgBamRec *)recs, cap, stats);
+   ctx->bam_table.assign((const PgBamRec *)recs, (const PgBamRec *)recs + n);
+   return PG_OK;
+}
 int pg_bam_rp_discovery(pg_ctx *ctx, const pg_rp_query *q, pg_rp *rows, uint32_t *src, uint64_t cap, uint64_t *n_rows, pg_rp *inter_rows,
                         uint32_t *inter_src, uint64_t inter_cap, uint64_t *n_inter, uint64_t *n_scanned)
 {

@@ -58,6 +58,50 @@ long bamemu_index(const uint8_t *d, uint64_t n, uint64_t seg, PgBamRec *recs, ui
    return (long)total;
 }
 
+// pg_bam_index_run: a headerless run of blocks whose last record may be cut off.  Returns the number of records, -2 for a
+// chain that meets an impossible block_size; stats[3] = the tail offset.
+long bamemu_index_run(const uint8_t *d, uint64_t n, uint64_t first, int32_t n_ref, uint64_t seg, PgBamRec *recs, uint64_t cap, uint64_t *stats)
+{
+   if (seg == 0) seg = PGB_SEGMENT;
+   const uint32_t n_seg = first >= n ? 1u : (uint32_t)((n - first + seg - 1) / seg);
+   std::vector<uint64_t> starts(n_seg), counts(n_seg), landing(n_seg), base(n_seg);
+   for (uint32_t s = 0; s < n_seg; s++) {         // pg_bam_start_kernel
+      if (s == 0) { starts[0] = first; continue; }
+      const uint64_t b0 = first + (uint64_t)s * seg, b1 = b0 + seg < n ? b0 + seg : n;
+      starts[s] = PGB_NONE;
+      for (uint64_t c = b0; c < b1; c++)
+         if (pgb_plausible_chain(d, n, c, n_ref)) { starts[s] = c; break; }
+   }
+   uint64_t redone = 0, total = 0, tail = n;
+   for (;;) {
+      for (uint32_t s = 0; s < n_seg; s++) {      // pg_bam_walk_run_kernel, pass 0
+         if (starts[s] == PGB_NONE) { counts[s] = 0; landing[s] = PGB_NONE; continue; }
+         const uint64_t b1 = first + (uint64_t)(s + 1) * seg;
+         uint64_t k = 0;
+         landing[s] = pgb_walk_run(d, n, starts[s], b1 < n ? b1 : n, NULL, &k);
+         counts[s] = landing[s] == PGB_NONE ? 0 : k;
+      }
+      uint64_t forced = 0;
+      const long v = pgb_validate_run(n_seg, first, n, seg, starts.data(), counts.data(), landing.data(), &forced, &total, &tail);
+      if (v < 0) return -2;
+      if (v == 0) break;
+      starts[(size_t)(v - 1)] = forced;
+      redone++;
+   }
+   if (stats) { stats[0] = n_seg; stats[1] = redone; stats[2] = first; stats[3] = tail; }
+   if (!recs) return (long)total;
+   if (cap < total) return -3;
+   uint64_t b = 0;
+   for (uint32_t s = 0; s < n_seg; s++) { base[s] = b; b += counts[s]; }
+   for (uint32_t s = 0; s < n_seg; s++) {         // pass 1
+      if (counts[s] == 0) continue;
+      const uint64_t b1 = first + (uint64_t)(s + 1) * seg;
+      uint64_t k = 0;
+      pgb_walk_run(d, n, starts[s], b1 < n ? b1 : n, recs + base[s], &k);
+   }
+   return (long)total;
+}
+
 // pg_bam_rp_discovery in the kernels' formulation: the stop index, the class of every record before it, positions by
 // prefix count, scatter.  rows/src hold the intra rows then (from n_intra on) nothing; inter_* the inter-chromosomal ones.
 // counts[0] = intra rows, [1] = inter rows, [2] = records delivered.

@@ -22,6 +22,8 @@ def build(force=False):
     lib = C.CDLL(LIB)
     lib.bamemu_index.restype = C.c_long
     lib.bamemu_index.argtypes = [C.c_void_p, C.c_uint64, C.c_uint64, C.c_void_p, C.c_uint64, C.c_void_p]
+    lib.bamemu_index_run.restype = C.c_long
+    lib.bamemu_index_run.argtypes = [C.c_void_p, C.c_uint64, C.c_uint64, C.c_int32, C.c_uint64, C.c_void_p, C.c_uint64, C.c_void_p]
     assert lib.bamemu_rec_size() == REC_DT.itemsize
     return lib
 
@@ -37,6 +39,18 @@ def index(lib, stream: bytes, seg: int = 0):
     n2 = lib.bamemu_index(buf.ctypes.data, buf.size, seg, recs.ctypes.data, n, stats.ctypes.data)
     assert n2 == n
     return recs, tuple(int(x) for x in stats)
+
+
+def index_run(lib, run: bytes, first_record: int, n_ref: int, seg: int = 0):
+    """a headerless run of blocks -> (records, tail offset, segments walked again)"""
+    buf = np.frombuffer(run, dtype=np.uint8)
+    stats = np.zeros(4, dtype=np.uint64)
+    n = lib.bamemu_index_run(buf.ctypes.data, buf.size, first_record, n_ref, seg, None, 0, stats.ctypes.data)
+    if n < 0:
+        raise ValueError("bamemu_index_run: %d" % n)
+    recs = np.zeros(n, dtype=REC_DT)
+    assert lib.bamemu_index_run(buf.ctypes.data, buf.size, first_record, n_ref, seg, recs.ctypes.data, n, stats.ctypes.data) == n
+    return recs, int(stats[3]), int(stats[1])
 
 
 RP_DT = np.dtype([("pos_a", "<u4"), ("pos_b", "<u4"), ("insert_size", "<u4"), ("read_length", "<i2"), ("da", "u1"), ("db", "u1")])
