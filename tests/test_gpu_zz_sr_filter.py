@@ -39,6 +39,49 @@ def pg():
     p.close()
 
 
+def _run_setup(pg):
+    from tests.test_bam_index_emulator import run_expectation
+    stream = G.paired_stream(6000, 19, refs=G.SYNTH_REFS[:1])
+    table = bam.serial_index(stream)
+    block = 0x8000
+    n_blocks = -(-len(stream) // block)
+    lo, hi = 5 * block, (n_blocks - 4) * block
+    exp, first, tail = run_expectation(table, len(stream), lo, hi)
+    run = stream[lo:hi]
+    pg.bgzf_inflate(bgzf.compress(run, block=block), to_host=False)
+    recs, _ = pg.bam_index_run(first, 1)
+    inside = table[(table["off"] >= lo + first) & (table["off"] < lo + tail)]
+    return stream, table, run, recs, int(inside["pos"][50]), int(inside["pos"][-50])
+
+
+def test_index_of_a_run_of_blocks(pg):
+    """pg_bam_index_run (CPU-verified only so far, like the filter below): a window's chunk of BGZF blocks instead of the whole
+    file -- no header in front, the last record cut off -- gives the serial walk's records of that stretch, and the discordant-pair
+    discovery (kernels that have run on the hardware) on it gives what it gives on the whole file"""
+    from tests.test_bam_index_emulator import run_expectation, same
+    from oracle import rpdoracle
+    from tests.test_rp_discovery import rows_of_product as rpd_rows
+    stream = G.paired_stream(6000, 19, refs=G.SYNTH_REFS[:1])
+    table = bam.serial_index(stream)
+    block = 0x8000
+    n_blocks = -(-len(stream) // block)
+    rng = np.random.default_rng(3)
+    for _ in range(6):
+        b0 = int(rng.integers(1, n_blocks - 2))
+        b1 = int(rng.integers(b0 + 1, n_blocks + 1))
+        lo, hi = b0 * block, min(b1 * block, len(stream))
+        exp, first, tail = run_expectation(table, len(stream), lo, hi)
+        pg.bgzf_inflate(bgzf.compress(stream[lo:hi], block=block), to_host=False)
+        recs, got_tail = pg.bam_index_run(first, 1)
+        assert same(recs, exp) and got_tail == tail, (b0, b1, recs.size, exp.size, got_tail, tail)
+    stream, table, run, recs, beg, end = _run_setup(pg)
+    exp_rows, _, scanned = rpdoracle.discovery(stream, table, 0, beg, end, 500)
+    rows, src, irows, isrc, sc = pg.bam_rp_discovery(0, beg, end, 500)
+    assert sc == scanned and np.array_equal(rpd_rows(run, recs, rows, src, irows, isrc), exp_rows)
+    with pytest.raises(api.PgError):
+        pg.bam_index_run(len(run) + 1, 1)
+
+
 @pytest.mark.parametrize("case", list(G.QUERIES))
 def test_matches_reference_dumps(pg, case):
     z = np.load(os.path.join(GOLD, "sr_%s.npz" % case))
@@ -95,42 +138,12 @@ def test_errors(pg):
     fresh.close()
 
 
-def test_index_of_a_run_of_blocks_and_window_queries_on_it(pg):
-    """pg_bam_index_run (also CPU-verified only so far): a window's chunk of BGZF blocks instead of the whole file -- no header in
-    front, the last record cut off -- gives the serial walk's records of that stretch, and the window queries on it give what
-    they give on the whole file"""
-    from tests.test_bam_index_emulator import run_expectation, same
-    from oracle import rpdoracle
-    from tests.test_rp_discovery import rows_of_product as rpd_rows
-    stream = G.paired_stream(6000, 19, refs=G.SYNTH_REFS[:1])
-    table = bam.serial_index(stream)
-    block = 0x8000
-    n_blocks = -(-len(stream) // block)
-    rng = np.random.default_rng(3)
-    for _ in range(6):
-        b0 = int(rng.integers(1, n_blocks - 2))
-        b1 = int(rng.integers(b0 + 1, n_blocks + 1))
-        lo, hi = b0 * block, min(b1 * block, len(stream))
-        exp, first, tail = run_expectation(table, len(stream), lo, hi)
-        pg.bgzf_inflate(bgzf.compress(stream[lo:hi], block=block), to_host=False)
-        recs, got_tail = pg.bam_index_run(first, 1)
-        assert same(recs, exp) and got_tail == tail, (b0, b1, recs.size, exp.size, got_tail, tail)
-    lo, hi = 5 * block, (n_blocks - 4) * block
-    exp, first, tail = run_expectation(table, len(stream), lo, hi)
-    run = stream[lo:hi]
-    pg.bgzf_inflate(bgzf.compress(run, block=block), to_host=False)
-    recs, _ = pg.bam_index_run(first, 1)
-    inside = table[(table["off"] >= lo + first) & (table["off"] < lo + tail)]
-    beg, end = int(inside["pos"][50]), int(inside["pos"][-50])
+def test_split_read_filter_on_a_run_of_blocks(pg):
+    stream, table, run, recs, beg, end = _run_setup(pg)
     exp_c, exp_r = sroracle.candidates(stream, table, 0, beg, end, 500, G.SYNTH_REFS[0][1])
     cands, seqs, refs, _ = pg.bam_sr_candidates(0, beg, end, 500, G.SYNTH_REFS[0][1])
     c, r = rows_of_product(run, recs, cands, seqs, refs, 500)
     assert np.array_equal(c, exp_c) and np.array_equal(r, exp_r), (_diff(c, exp_c), _diff(r, exp_r))
-    exp_rows, _, scanned = rpdoracle.discovery(stream, table, 0, beg, end, 500)
-    rows, src, irows, isrc, sc = pg.bam_rp_discovery(0, beg, end, 500)
-    assert sc == scanned and np.array_equal(rpd_rows(run, recs, rows, src, irows, isrc), exp_rows)
-    with pytest.raises(api.PgError):
-        pg.bam_index_run(len(run) + 1, 1)
 
 
 @pytest.mark.skipif(not os.path.exists(DEMO), reason="oracle/_ref/pindel_gpu_demo not built (needs /root/reference at build time)")
