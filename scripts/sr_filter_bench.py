@@ -23,8 +23,9 @@ REFS = (("chr1", 400_000), ("chr2", 300_000))
 
 
 def tiled_pairs(n_pairs: int, chunk_pairs: int = 20_000, seed: int = 5):
-    """A coordinate-sorted stream of about n_pairs named pairs: one seeded chunk of chr1 records, repeated with the tile number
-    written into every read name (names stay unique, so pairs never join across tiles).  -> (stream, records)"""
+    """A stream of about n_pairs named pairs: one seeded, coordinate-sorted chunk of chr1 records, repeated with the tile number
+    written into every read name (names stay unique, so pairs never join across tiles).  Positions start over in every tile;
+    the benchmark's window is the whole reference, so the iterator's stop rule never fires.  -> (stream, records)"""
     from pindel_b200 import bam
     from tests.golden import make_sr_golden as G
     one = G.paired_stream(chunk_pairs, seed, refs=REFS[:1])
