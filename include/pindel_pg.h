@@ -156,11 +156,14 @@ uint64_t pg_kernel_launches(pg_ctx *ctx);      /* search-kernel launches since p
 uint32_t pg_last_run_count(pg_ctx *ctx);       /* runs produced by the last completed launch (valid after pg_sync/pg_download) */
 
 /* Statistics of the last completed launch (waits for it): reference positions scanned (sum of the window sizes of every
- * search executed, the W terms of the algorithmic-bytes formula in DESIGN.md) and UniquePoints produced. */
+ * search executed, the W terms of the algorithmic-bytes formula in DESIGN.md) and UniquePoints produced.  After a call
+ * that was chunked through the pipeline (pg_search & co. on >= 2 chunks) these are the totals over its chunks. */
 int pg_last_stats(pg_ctx *ctx, uint64_t *window_bases, uint64_t *unique_points);
 
 /* Device pointers of the last completed launch's results (pg_read_out[n], pg_run[n_runs]), valid until the next
- * pg_launch/pg_upload; for callers that hand the records to a collective (NCCL gather) without a host round trip. */
+ * pg_launch/pg_upload; for callers that hand the records to a collective (NCCL gather) without a host round trip.
+ * PG_ERR_STATE when nothing is resident: no pg_launch yet, or the last call went through the chunked pipeline (whose
+ * results were delivered to the caller's host buffers chunk by chunk). */
 int pg_device_results(pg_ctx *ctx, void **out_dev, void **runs_dev, uint32_t *n_runs);
 
 /* Pinned host memory for batch buffers (optional; any host pointer is accepted by the calls above). */

@@ -40,6 +40,7 @@ static inline int pg_fill_params(PgParams *p, int add_mm, int min_close, int min
    p->min_close = min_close;
    p->min_perfect = min_perfect;
    p->max_range_index = max_range_index;
+   p->filter_min_pos = PG_FILTER_MIN_POS;
    for (int i = 0; i < 512; i++) {
       uint32_t v = (i < PG_TABLE) ? max_mismatch[i] : 0u;
       if (v > 250u) return -1;

@@ -63,6 +63,13 @@ PG_DEV uint8_t pg_ldg8(const uint8_t *p) { return __ldg(p); }
 
 #include "pg_warp_types.h"
 
+// One growth step of the filter: read index `sh` compared with the reference base `sh` to the right of a plus seed and
+// `sh` to the left of a minus seed (rsh = 32 - sh is the funnel shift that brings that base under the seed's bit).
+struct alignas(16) PgFStep {
+   uint32_t lo, hi;   // the read character's two code bits, each spread over a whole word
+   uint32_t sh, rsh;
+};
+
 // ------------------------------------------------------------------------------------------------
 // Per-warp shared memory
 // ------------------------------------------------------------------------------------------------
@@ -82,6 +89,12 @@ struct PgWarpSmem {
    uint32_t A[TL + 1], B[TL + 1], P[TL + 1], META[TL + 1], H[TL + 1], ALIAS[TL + 1];
    uint32_t queue[PG_QCAP];
    uint16_t seedq[PG_CHUNK_POS];     // seeds of the current chunk: offset from the tile origin | strand << 15
+   // threshold filter of the far rings (pg_filter_tile): the read's first characters as a step table, the number of
+   // steps after which each level is tested, and the surviving seeds of the staged tile (one bit per position)
+   alignas(16) PgFStep ftab[32];
+   uint32_t fuse;                    // read indices 1..31 that have a table entry (not N / other, below L)
+   uint32_t fcnt[TL];
+   uint32_t fsp[PG_TILE_WORDS], fsm[PG_TILE_WORDS];
 };
 
 struct PgLevel {      // warp-level top-2 for level == lane
@@ -243,6 +256,119 @@ PG_DEV void pg_flush_queue(PgWarpCtx<LW, TL> &cx, const PgSearch &se, const PgCh
    cx.qn = 0;
 }
 
+// ------------------------------------------------------------------------------------------------
+// Threshold filter for the far rings.
+//
+// A seed can only change the top-2 state (A_t, B_t) of some level t if its D_t exceeds the current second-largest B_t,
+// i.e. if it has at most t mismatches among the read indices 1..B_t.  Once a few hundred positions have been scanned the
+// B_t are large (B_0 ~ log4 of the seeds seen), so in the outer rings of SearchFarEnd's schedule (src/pindel.cpp:1025-1070)
+// all but a handful of the seeds are irrelevant -- and that can be decided for 32 positions per lane at once, bit-sliced:
+// the lane owns one 32-base word of the staged tile; for read index j the mismatch word of all 32 plus seeds is the
+// reference planes funnel-shifted by j against the (uniform) read character, for the 32 minus seeds the planes shifted the
+// other way against its complement; alive_t (seeds with <= t mismatches so far) is a thermometer counter updated with one
+// LOP3 per level; after B_t steps alive_t is OR-ed into the survivors and level t is dropped (its members are survivors
+// already).  Conservative by construction -- stale thresholds, skipped read N / other characters and reference N (seen as
+// 'A') can only under-count mismatches -- and every survivor then takes the exact per-seed path, so the result is
+// unchanged; the filter only decides how many seeds take that path.
+// ------------------------------------------------------------------------------------------------
+#ifdef PG_EMULATE
+static unsigned long long pg_emul_filter_stats[3];    // host build only: seeds in, survivors out, tiles filtered
+#endif
+template <int LW, int TL>
+PG_COLD void pg_filter_prepare(PgWarpSmem<LW, TL> *ws, int arr, uint32_t inv, int L)
+{
+   const int lane = pg_lane();
+   const uint32_t qlo = ws->q[arr][0][0] ^ inv, qhi = ws->q[arr][1][0] ^ inv;
+   const uint32_t use = pg_valid_mask<LW, TL>(L, 0) & ~1u & ~(ws->q[arr][2][0] | ws->q[arr][3][0]);
+   if ((use >> lane) & 1u) {
+      PgFStep e;
+      e.lo = ((qlo >> lane) & 1u) ? ~0u : 0u;
+      e.hi = ((qhi >> lane) & 1u) ? ~0u : 0u;
+      e.sh = (uint32_t)lane; e.rsh = 32u - (uint32_t)lane;
+      ws->ftab[pg_popc(use & ((1u << lane) - 1u))] = e;
+   }
+   if (lane == 0) ws->fuse = use;
+   pg_syncwarp();
+}
+
+// Thresholds of the staged tile from the warp-level state (lane t holds level t): fcnt[t] = number of table steps that cover
+// the read indices 1..B_t, made non-increasing towards the lower levels (an earlier test only lets more seeds through).
+template <int LW, int TL>
+PG_DEV void pg_filter_thresholds(PgWarpCtx<LW, TL> &cx, int T)
+{
+   PgWarpSmem<LW, TL> *ws = cx.ws;
+   const int lane = pg_lane();
+   const uint32_t Bm = cx.lvl.B;
+   uint32_t c = (uint32_t)pg_popc(ws->fuse & (Bm >= 31u ? ~0u : ((2u << Bm) - 1u)));
+   if (lane >= T) c = 0xffffu;
+#pragma unroll
+   for (int d = 1; d < 32 && d < TL; d <<= 1) {
+      uint32_t v = pg_shfl(c, (lane + d) & 31);
+      if (lane + d < 32) c = pg_umin(c, v);
+   }
+   if (lane < TL) ws->fcnt[lane] = c;
+   pg_syncwarp();
+}
+
+// Survivors of the positions [r0, r1) (relative to the tile origin) into ws->fsp / ws->fsm, one word per tile word.
+// Returns (uniform) whether the range holds any seed at all.
+template <int LW, int TL>
+PG_COLD bool pg_filter_tile(PgWarpSmem<LW, TL> *ws, uint32_t r0, uint32_t r1, uint32_t c0lom, uint32_t c0him, int T)
+{
+   const int lane = pg_lane();
+   const uint32_t wlast = (r1 - 1u) >> 5;
+   bool any = false;
+   for (uint32_t wb = r0 >> 5; wb <= wlast; wb += 32u) {
+      const uint32_t wi = wb + (uint32_t)lane;
+      if (wi <= wlast) {
+         const uint2 Wm = ws->tile[wi - 1], W0 = ws->tile[wi], Wp = ws->tile[wi + 1];
+         const uint32_t p0 = wi << 5;
+         uint32_t inr = ~0u;
+         if (p0 < r0) inr &= ~0u << (r0 - p0);
+         if (r1 - p0 < 32u) inr &= (1u << (r1 - p0)) - 1u;
+         const uint32_t ok = ~ws->tile_n[wi] & inr;
+         const uint32_t dl = W0.x ^ c0lom, dh = W0.y ^ c0him;
+         const uint32_t plus = ~(dl | dh) & ok, minus = (dl & dh) & ok;
+         any = any || (plus | minus) != 0u;
+         uint32_t ap[TL], am[TL];
+#pragma unroll
+         for (int t = 0; t < TL; t++) { ap[t] = plus; am[t] = minus; }
+         uint32_t sp = 0, sm = 0;
+         uint32_t k = 0;
+#pragma unroll
+         for (int t0 = 0; t0 < TL; t0++) {
+            if (t0 < T) {
+               const uint32_t kend = ws->fcnt[t0];
+#pragma unroll 1
+               for (; k < kend; k++) {
+                  const PgFStep e = ws->ftab[k];
+                  const uint32_t mp = (pg_fsr(W0.x, Wp.x, e.sh) ^ e.lo) | (pg_fsr(W0.y, Wp.y, e.sh) ^ e.hi);
+                  const uint32_t mm = ~(pg_fsr(Wm.x, W0.x, e.rsh) ^ e.lo) | ~(pg_fsr(Wm.y, W0.y, e.rsh) ^ e.hi);
+#pragma unroll
+                  for (int t = TL - 1; t > t0; t--) {
+                     ap[t] = (ap[t] & ~mp) | (ap[t - 1] & mp);
+                     am[t] = (am[t] & ~mm) | (am[t - 1] & mm);
+                  }
+                  ap[t0] &= ~mp; am[t0] &= ~mm;
+               }
+               sp |= ap[t0]; sm |= am[t0];
+            }
+         }
+         ws->fsp[wi] = sp; ws->fsm[wi] = sm;
+#ifdef PG_EMULATE
+         pg_emul_filter_stats[0] += (unsigned long long)pg_popc(plus | minus);
+         pg_emul_filter_stats[1] += (unsigned long long)pg_popc(sp | sm);
+#endif
+      }
+   }
+#ifdef PG_EMULATE
+   if (lane == 0) pg_emul_filter_stats[2]++;
+#endif
+   any = pg_any(any);
+   pg_syncwarp();
+   return any;
+}
+
 // Scan window [s, e) of one chromosome (tile by tile) and fold its seeds into cx.lvl.
 //
 // Two phases per chunk of PG_CHUNK_POS positions, so that the expensive part runs on full warps:
@@ -251,8 +377,11 @@ PG_DEV void pg_flush_queue(PgWarpCtx<LW, TL> &cx, const PgSearch &se, const PgCh
 //       its seeds without looking at the read; a warp prefix sum packs them, in position order, into ws->seedq;
 //   (2) seeds are dealt 32 at a time to the lanes: funnel-shift the 32-base stretch out of the staged tile, XOR with
 //       the read's bit-planes, pull the first TL mismatch indices out of the mask, update the lane-local top-2 keys.
+//
+// `filter` (far rings only): the seed list of a tile is first reduced to the seeds that can still beat a second-largest
+// D_t of the state so far (pg_filter_tile); the survivors of the whole tile then share the passes of phase (2).
 template <int LW, int TL>
-PG_DEV void pg_scan_window(PgWarpCtx<LW, TL> &cx, const PgSearch &se, int chr_id, uint32_t s, uint32_t e, uint32_t &phase)
+PG_DEV void pg_scan_window(PgWarpCtx<LW, TL> &cx, const PgSearch &se, int chr_id, uint32_t s, uint32_t e, uint32_t &phase, bool filter)
 {
    PgWarpSmem<LW, TL> *ws = cx.ws;
    const PgChrom chrom = cx.chroms[chr_id];
@@ -275,8 +404,11 @@ PG_DEV void pg_scan_window(PgWarpCtx<LW, TL> &cx, const PgSearch &se, int chr_id
    PG_PIN(valid0);                              // keep it in a register: it is otherwise re-derived from L in every pass
    const bool far = se.far;
    const bool single_fwd = se.d > 0;
-   for (uint32_t ts = s; ts < e; ts += PG_TILE_POS) {
-      const uint32_t te = (e - ts > PG_TILE_POS) ? ts + PG_TILE_POS : e;
+   // windows of several tiles are cut at multiples of the tile size, so that all tiles but the first are whole words
+   const bool aligned_tiles = e - s > PG_TILE_POS;
+   for (uint32_t ts = s, te; ts < e; ts = te) {
+      te = aligned_tiles ? (ts & ~(uint32_t)(PG_TILE_POS - 1)) + PG_TILE_POS : e;
+      if (te > e) te = e;
       const int64_t w0 = (((int64_t)(ts >> 5)) - 1) & ~(int64_t)3;
       const int64_t w1 = (int64_t)((te - 1) >> 5) + 2;          // exclusive
       const int nw = (int)(((w1 - w0) + 3) & ~(int64_t)3);
@@ -287,6 +419,12 @@ PG_DEV void pg_scan_window(PgWarpCtx<LW, TL> &cx, const PgSearch &se, int chr_id
       for (int i = lane; i < nw; i += 32) nacc |= ws->tile_n[i];
       const bool special = read_special || pg_any(nacc != 0);
       const uint32_t origin = (uint32_t)(w0 << 5);              // absolute position of tile word 0, bit 0 (w0 >= -4)
+      bool filt = false;
+      if (TL <= 16 && filter) {
+         pg_filter_thresholds<LW, TL>(cx, se.T);
+         if (pg_filter_tile<LW, TL>(ws, ts - origin, te - origin, c0lom, c0him, se.T)) cx.any_seed = 1;
+         filt = true;
+      }
       uint32_t ka_[TL], kb_[TL];     // lane-local top-2 keys of this tile, one pair per level
 #pragma unroll
       for (int t = 0; t < TL; t++) { ka_[t] = 0; kb_[t] = 0; }
@@ -295,45 +433,60 @@ PG_DEV void pg_scan_window(PgWarpCtx<LW, TL> &cx, const PgSearch &se, int chr_id
       const uint32_t tlen = te - (ts & ~31u);
       const uint32_t gran = tlen <= 256u ? 8u : (tlen <= 512u ? 16u : 32u);
       const uint32_t gmask = gran == 32u ? ~0u : ((1u << gran) - 1u);
-      for (uint32_t cs = ts & ~31u; cs < te; cs += 32u * gran) {
-         // ---- (1) seed list of this chunk ----
-         uint32_t plus = 0, minus = 0;
-         const uint32_t p0 = cs + gran * (uint32_t)lane;         // first position owned by this lane
-         {
+      // the seed queue is filled chunk by chunk; without the filter every chunk is processed on its own, with it the
+      // (few) survivors of the whole tile share their passes
+      uint32_t cs = ts & ~31u;
+      uint32_t nq = 0;                                           // seeds waiting in ws->seedq (uniform)
+      for (;;) {
+         // ---- (1) seed list ----
+         while (cs < te) {
+            uint32_t plus = 0, minus = 0;
+            const uint32_t p0 = cs + gran * (uint32_t)lane;      // first position owned by this lane
             if (p0 < te) {
                int wi = (int)((int64_t)(p0 >> 5) - w0);
                uint32_t sub = p0 & 31u;
-               uint2 W = ws->tile[wi];
-               uint32_t notn = ~ws->tile_n[wi] >> sub;
-               uint32_t inr = gmask;                              // owned positions inside [ts, te)
-               if (p0 < ts) inr &= (ts - p0 >= 32u) ? 0u : (~0u << (ts - p0));
-               if (te - p0 < gran) inr &= (1u << (te - p0)) - 1u;
-               uint32_t dl = (W.x ^ c0lom) >> sub, dh = (W.y ^ c0him) >> sub;   // 0 bits where the base equals read[0]
-               plus = ~(dl | dh) & notn & inr;
-               if (far) minus = (dl & dh) & notn & inr;          // both planes differ: the complement of read[0]
-               else if (!single_fwd) { minus = plus; plus = 0; } // close end growing left: every seed is a "minus" seed
+               if (filt) {
+                  plus = (ws->fsp[wi] >> sub) & gmask;
+                  minus = (ws->fsm[wi] >> sub) & gmask;
+               } else {
+                  uint2 W = ws->tile[wi];
+                  uint32_t notn = ~ws->tile_n[wi] >> sub;
+                  uint32_t inr = gmask;                           // owned positions inside [ts, te)
+                  if (p0 < ts) inr &= (ts - p0 >= 32u) ? 0u : (~0u << (ts - p0));
+                  if (te - p0 < gran) inr &= (1u << (te - p0)) - 1u;
+                  uint32_t dl = (W.x ^ c0lom) >> sub, dh = (W.y ^ c0him) >> sub;   // 0 bits where the base equals read[0]
+                  plus = ~(dl | dh) & notn & inr;
+                  if (far) minus = (dl & dh) & notn & inr;       // both planes differ: the complement of read[0]
+                  else if (!single_fwd) { minus = plus; plus = 0; } // close end growing left: every seed is a "minus" seed
+               }
             }
-         }
-         uint32_t cnt = (uint32_t)(pg_popc(plus) + pg_popc(minus));
-         uint32_t incl = cnt;                                     // inclusive prefix sum over the lanes
+            uint32_t cnt = (uint32_t)(pg_popc(plus) + pg_popc(minus));
+            uint32_t incl = cnt;                                  // inclusive prefix sum over the lanes
 #pragma unroll
-         for (int d = 1; d < 32; d <<= 1) {
-            uint32_t v = pg_shfl_up(incl, d);
-            if (lane >= d) incl += v;
-         }
-         const uint32_t nseeds = pg_shfl(incl, 31);
-         if (nseeds == 0) continue;
-         cx.any_seed = 1;
-         {
-            uint32_t o = incl - cnt;
-            uint32_t both = plus | minus;
-            uint32_t rel = p0 - origin;
-            while (both) {
-               uint32_t bit = (uint32_t)pg_ffs(both) - 1u;
-               both &= both - 1u;
-               ws->seedq[o++] = (uint16_t)((rel + bit) | (((minus >> bit) & 1u) << 15));
+            for (int d = 1; d < 32; d <<= 1) {
+               uint32_t v = pg_shfl_up(incl, d);
+               if (lane >= d) incl += v;
             }
+            const uint32_t nseeds = pg_shfl(incl, 31);
+            if (nq + nseeds > PG_CHUNK_POS) break;                // no room: process the queue first, then this chunk again
+            if (nseeds) {
+               cx.any_seed = 1;
+               uint32_t o = nq + incl - cnt;
+               uint32_t both = plus | minus;
+               uint32_t rel = p0 - origin;
+               while (both) {
+                  uint32_t bit = (uint32_t)pg_ffs(both) - 1u;
+                  both &= both - 1u;
+                  ws->seedq[o++] = (uint16_t)((rel + bit) | (((minus >> bit) & 1u) << 15));
+               }
+               nq += nseeds;
+            }
+            cs += 32u * gran;
+            if (!filt && nq) break;
          }
+         if (nq == 0) break;                                      // cs >= te and nothing queued
+         const uint32_t nseeds = nq;
+         nq = 0;
          pg_syncwarp();
          // ---- (2) 32 seeds per pass ----
          for (uint32_t q0 = 0; q0 < nseeds; q0 += 32) {
@@ -682,6 +835,7 @@ PG_DEV void pg_process_read(PgWarpCtx<LW, TL> &cx, const PgBatch &bt, int ri, Pg
    int k = 1;                  // SearchFarEnd: rangeIndex 1..MaxRangeIndex+1
    uint32_t span = 64;         // START_SEARCH_SPAN
    bool have_prev_window = false;
+   bool filter_ready = false;  // ws->ftab describes this read
    uint32_t prev_ws = 0, prev_we = 0;
    if (bt.mode & 1) {
       st = ST_CLOSE;
@@ -758,7 +912,14 @@ PG_DEV void pg_process_read(PgWarpCtx<LW, TL> &cx, const PgBatch &bt, int ri, Pg
                s = (uint32_t)ss; e = (uint32_t)ee;
             }
             if (e > s) {
-               pg_scan_window<LW, TL>(cx, se, rg.chr, s, e, phase);
+               // the outer rings of the far schedule go through the threshold filter (the state of the inner windows
+               // supplies the thresholds); its step table is built once per read, here, from the final sequence
+               const bool use_filter = TL <= 16 && se.far && keep_state && e - s >= prm->filter_min_pos;
+               if (use_filter && !filter_ready) {
+                  pg_filter_prepare<LW, TL>(ws, se.chp.arr, se.chp.inv, L);
+                  filter_ready = true;
+               }
+               pg_scan_window<LW, TL>(cx, se, rg.chr, s, e, phase, use_filter);
                if (st != ST_FAR_WINDOW) window_bases += (unsigned long long)(e - s);
             }
          }

@@ -18,6 +18,9 @@ struct uint2 { uint32_t x, y; };
 #define PG_QCAP 64          // deferred ("slow") seed queue per warp
 #define PG_IDX_BITS 20
 #define PG_IDX_MASK 0xFFFFFu
+#ifndef PG_FILTER_MIN_POS
+#define PG_FILTER_MIN_POS 512u   // far rings at least this long go through the threshold filter (pg_filter_tile)
+#endif
 #define PG_FAR_BP_START 10  // src/farend_searcher.cpp:89
 #define PG_TABLE 500        // g_maxMismatch size, src/pindel.cpp:801
 
@@ -39,6 +42,7 @@ struct PgParams {
    int32_t min_close;       // -H  g_MinClose
    int32_t min_perfect;     // -m  Min_Perfect_Match_Around_BP
    int32_t max_range_index; // -x  MaxRangeIndex
+   uint32_t filter_min_pos; // far rings at least this long go through the threshold filter (PG_FILTER_MIN_POS; tuning knob, results do not depend on it)
    uint8_t g[512];          // g_maxMismatch[len] (src/pindel.cpp:794-819), host-computed in double
    uint16_t thr[512];       // thr[L] = least n with (float)n >= (float)(L * -u), src/searcher.cpp:366,383
 };

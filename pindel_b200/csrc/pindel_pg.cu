@@ -380,6 +380,7 @@ struct pg_ctx {
    uint32_t *counters_h = nullptr;     // pinned
    int last_mode = 0;
    bool launched = false;
+   bool stats_valid = false;      // last_window_bases / last_ups / last_runs describe a completed call (resident or pipelined)
    uint64_t launches = 0;
    uint32_t last_runs = 0;
    uint64_t last_window_bases = 0, last_ups = 0;
@@ -534,6 +535,7 @@ pg_ctx *pg_create(const pg_settings *s)
       delete ctx;
       return nullptr;
    }
+   if (const char *e = getenv("PG_FILTER_MIN_POS")) ctx->prm_h.filter_min_pos = (uint32_t)strtoul(e, nullptr, 10);   // tuning only
    bool ok = cudaSetDevice(ctx->device) == cudaSuccess &&
              cudaDeviceGetAttribute(&ctx->n_sm, cudaDevAttrMultiProcessorCount, ctx->device) == cudaSuccess &&
              cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking) == cudaSuccess &&
@@ -649,6 +651,7 @@ int pg_upload(pg_ctx *ctx, const pg_reads *in)
    CU(cudaSetDevice(ctx->device));
    const int n = in->n;
    ctx->launched = false;
+   ctx->stats_valid = false;
    ctx->n = n;
    ctx->have_anchor = in->matched_d && in->matched_rel_pos && in->insert_size;
    ctx->have_chr = in->chr_id != nullptr;
@@ -758,6 +761,7 @@ static int finish_launch(pg_ctx *ctx)
          ctx->last_runs = ctx->counters_h[1];
          memcpy(&ctx->last_window_bases, ctx->counters_h + 4, 8);
          memcpy(&ctx->last_ups, ctx->counters_h + 6, 8);
+         ctx->stats_valid = true;
          return PG_OK;
       }
       uint32_t need = ctx->counters_h[1];
@@ -908,8 +912,23 @@ static int run_pipelined(pg_ctx *ctx, PipeState *&ps, const pg_reads *in, pg_res
             return fail(ctx, PG_ERR_ARG, "region chromosome out of range");
    int rc = pipe_init(ctx, ps);
    if (rc != PG_OK) return rc;
+   // A slot is only ever drained by the call that launched it: whatever way this function is left (an allocation that
+   // fails, a failed drain, a pool that keeps overflowing), the three streams are drained and both slots are idle again,
+   // so the next call never sees a stale chunk with another caller's c0 / c1 / result buffers.
+   struct PipeIdle {
+      PipeState *ps;
+      void settle() const
+      {
+         if (!ps->slot[0].busy && !ps->slot[1].busy) return;
+         cudaStreamSynchronize(ps->s_in); cudaStreamSynchronize(ps->s_k); cudaStreamSynchronize(ps->s_out);
+         ps->slot[0].busy = ps->slot[1].busy = false;
+      }
+      ~PipeIdle() { settle(); }
+   } idle{ps};
+   idle.settle();
    CU(cudaStreamSynchronize(ctx->stream));         // everything queued by the caller on its stream comes first
    ctx->launched = false;                           // no resident batch after a pipelined call
+   ctx->stats_valid = false;
    ctx->n = 0;
    const int nchunks = (n + ctx->pipe_chunk - 1) / ctx->pipe_chunk;
    uint64_t total_runs = 0, wb = 0, ups = 0;
@@ -994,6 +1013,7 @@ static int run_pipelined(pg_ctx *ctx, PipeState *&ps, const pg_reads *in, pg_res
    ctx->last_runs = (uint32_t)total_runs;
    ctx->last_window_bases = wb;
    ctx->last_ups = ups;
+   ctx->stats_valid = true;
    res->n_runs = (uint32_t)total_runs;
    if (cap_exceeded) return fail(ctx, PG_ERR_RUNS_CAP, "run buffer too small (results->n_runs holds the required size; repeat the call)");
    return PG_OK;
@@ -1026,8 +1046,10 @@ int pg_last_stats(pg_ctx *ctx, uint64_t *window_bases, uint64_t *unique_points)
 {
    if (!ctx) return PG_ERR_ARG;
    CU(cudaSetDevice(ctx->device));
-   int rc = finish_launch(ctx);
-   if (rc != PG_OK) return rc;
+   if (ctx->launched || !ctx->stats_valid) {      // after a pipelined call nothing is resident, but its totals are kept
+      int rc = finish_launch(ctx);
+      if (rc != PG_OK) return rc;
+   }
    if (window_bases) *window_bases = ctx->last_window_bases;
    if (unique_points) *unique_points = ctx->last_ups;
    return PG_OK;
@@ -1037,6 +1059,8 @@ int pg_device_results(pg_ctx *ctx, void **out_dev, void **runs_dev, uint32_t *n_
 {
    if (!ctx) return PG_ERR_ARG;
    CU(cudaSetDevice(ctx->device));
+   if (!ctx->launched)
+      return fail(ctx, PG_ERR_STATE, "pg_device_results: nothing is resident (no launch, or the last call was chunked through the pipeline)");
    int rc = finish_launch(ctx);
    if (rc != PG_OK) return rc;
    if (out_dev) *out_dev = ctx->out.p;

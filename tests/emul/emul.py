@@ -59,3 +59,10 @@ def search(lib, params, chr_seqs, seq_blob, seq_off, matched_d, rel_pos, insert_
                           C.byref(used))
     assert rc == 0, "run pool overflow"
     return out, pool[:used.value]
+
+
+def filter_stats(lib):
+    """(seeds that entered the far rings' threshold filter, survivors, tiles filtered) since the last call."""
+    a = (C.c_ulonglong * 3)()
+    lib.pgemu_filter_stats(a)
+    return int(a[0]), int(a[1]), int(a[2])

@@ -215,6 +215,12 @@ int pgemu_search(int n_chr, const char *const *chr_seq, const uint32_t *chr_len,
    return (int)counters[2];
 }
 
+// seeds that entered the far rings' filter, seeds that survived it, tiles filtered -- since the last call
+void pgemu_filter_stats(unsigned long long *out)
+{
+   for (int i = 0; i < 3; i++) { out[i] = pg_emul_filter_stats[i]; pg_emul_filter_stats[i] = 0; }
+}
+
 int pgemu_sizes(int which)
 {
    switch (which) {

@@ -95,6 +95,7 @@ def test_pipelined_large_batch_path_equals_single_launch(ref2m, monkeypatch):
     pg1.set_reference([padded])
     a = R.per_read(*pg1.search(**kw), kw["seq_blob"], kw["seq_off"])
     launches_single = pg1.kernel_launches
+    stats_single = pg1.last_stats()
     pg1.close()
     monkeypatch.setenv("PG_PIPE_CHUNK", "1000")
     pg2 = api.PatternGrowth()
@@ -107,5 +108,8 @@ def test_pipelined_large_batch_path_equals_single_launch(ref2m, monkeypatch):
     small = np.empty(10, dtype=R.RUN_DT)
     out2, runs2 = pg2.search(runs=small, **kw)
     H.compare(a, R.per_read(out2, runs2, kw["seq_blob"], kw["seq_off"]), "pipelined after RUNS_CAP retry")
-    wb, ups = pg2.last_stats() if False else (0, 0)
+    # the totals of a chunked call are kept although nothing stays resident; the resident-results query says so
+    assert pg2.last_stats() == stats_single
+    with pytest.raises(api.PgError):
+        pg2.device_results()
     pg2.close()
