@@ -151,20 +151,32 @@ int pg_launch(pg_ctx *ctx, int32_t mode);
 int pg_download(pg_ctx *ctx, pg_results *res);
 int pg_sync(pg_ctx *ctx);
 
+/* pg_upload + pg_launch in one call that leaves batch and results on the device (read them with pg_device_results /
+ * pg_download, classify them with pg_classify_resident).  Large batches are uploaded in chunks while the kernel already
+ * runs on the chunks that have arrived; the call returns once everything is queued.  The host buffers of `in` must stay
+ * valid (and, to overlap at all, pinned: pg_host_alloc) until the results have been waited for. */
+int pg_search_resident(pg_ctx *ctx, const pg_reads *in, int32_t mode);
+
+/* Size limits of one call: seq_off / region_off / run offsets are 32-bit, so one batch holds less than 4 GiB of sequence
+ * (28.6 M reads of 150 bp) and produces less than 2^32 runs; larger inputs are split by the caller (the reference itself
+ * works window by window, src/pindel.cpp:1778-1985).  pg_upload / pg_search return PG_ERR_ARG when seq_off wraps. */
+
 /* Bookkeeping the benchmarks report. */
 uint64_t pg_kernel_launches(pg_ctx *ctx);      /* search-kernel launches since pg_create */
 uint32_t pg_last_run_count(pg_ctx *ctx);       /* runs produced by the last completed launch (valid after pg_sync/pg_download) */
 
 /* Statistics of the last completed launch (waits for it): reference positions scanned (sum of the window sizes of every
- * search executed, the W terms of the algorithmic-bytes formula in DESIGN.md) and UniquePoints produced.  After a call
- * that was chunked through the pipeline (pg_search & co. on >= 2 chunks) these are the totals over its chunks. */
+ * search executed, the W terms of the algorithmic-bytes formula in DESIGN.md) and UniquePoints produced. */
 int pg_last_stats(pg_ctx *ctx, uint64_t *window_bases, uint64_t *unique_points);
 
-/* Device pointers of the last completed launch's results (pg_read_out[n], pg_run[n_runs]), valid until the next
- * pg_launch/pg_upload; for callers that hand the records to a collective (NCCL gather) without a host round trip.
- * PG_ERR_STATE when nothing is resident: no pg_launch yet, or the last call went through the chunked pipeline (whose
- * results were delivered to the caller's host buffers chunk by chunk). */
+/* Device pointers of the last launch's results (pg_read_out[n], pg_run[n_runs]; waits for that launch only), for
+ * callers that hand the records to a collective (NCCL gather) without a host round trip.  Results rotate through three
+ * slots: the pointers of launch k stay valid until launch k+3 is queued, so the records of launch k can travel while the
+ * launches k+1 and k+2 run -- pg_device_results_previous returns launch k's after launch k+1 was queued (waits for launch
+ * k only); the caller orders launch k+3 behind whatever still reads launch k's records.  PG_ERR_STATE when there is no
+ * such launch. */
 int pg_device_results(pg_ctx *ctx, void **out_dev, void **runs_dev, uint32_t *n_runs);
+int pg_device_results_previous(pg_ctx *ctx, void **out_dev, void **runs_dev, uint32_t *n_runs, int32_t *n_reads);
 
 /* Pinned host memory for batch buffers (optional; any host pointer is accepted by the calls above). */
 void *pg_host_alloc(size_t bytes);

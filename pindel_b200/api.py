@@ -132,6 +132,10 @@ def load_library() -> C.CDLL:
         lib.pg_compress_ups.restype = C.c_uint32
         lib.pg_compress_ups.argtypes = [C.c_void_p, C.c_uint32, C.c_void_p]
         lib.pg_device_results.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+        lib.pg_device_results_previous.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+        lib.pg_device_results_previous.restype = C.c_int
+        lib.pg_search_resident.argtypes = [C.c_void_p, C.c_void_p, C.c_int32]
+        lib.pg_search_resident.restype = C.c_int
         _lib = lib
     return _lib
 
@@ -290,6 +294,22 @@ class PatternGrowth:
         o, r, k = C.c_void_p(0), C.c_void_p(0), C.c_uint32(0)
         self._check(self.lib.pg_device_results(self.ctx, C.byref(o), C.byref(r), C.byref(k)), "pg_device_results")
         return int(o.value or 0), int(r.value or 0), int(k.value)
+
+    def device_results_previous(self):
+        """(out device pointer, runs device pointer, n_runs, n_reads) of the launch before the last one; waits for that
+        launch only, so the latest launch keeps running while these records are handed on."""
+        o, r, k, n = C.c_void_p(0), C.c_void_p(0), C.c_uint32(0), C.c_int32(0)
+        self._check(self.lib.pg_device_results_previous(self.ctx, C.byref(o), C.byref(r), C.byref(k), C.byref(n)),
+                    "pg_device_results_previous")
+        return int(o.value or 0), int(r.value or 0), int(k.value), int(n.value)
+
+    def search_resident(self, mode: int = 3, **batch):
+        """pg_upload + pg_launch with the upload chunked behind the kernel; batch and results stay on the device.  The
+        arrays are kept alive by this object until the next batch call."""
+        r, keep = self._reads(**batch)
+        self._keep = keep
+        self._n = r.n
+        self._check(self.lib.pg_search_resident(self.ctx, C.byref(r), mode), "pg_search_resident")
 
     def classify(self, batch: dict, win: dict, records=None) -> np.ndarray:
         """The seven SV drivers of SearchSVs (src/pindel.cpp:1140-1164) on one window: batch = the arrays of pg_sv_reads

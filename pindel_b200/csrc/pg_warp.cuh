@@ -37,7 +37,7 @@
 #define PG_DEV __device__ __forceinline__
 #define PG_PIN(x) asm volatile("" : "+r"(x))
 #define PG_COLD __device__ __noinline__   // rarely executed helpers: one out-of-line copy keeps the kernel's code small
-PG_DEV int pg_lane() { return (int)(threadIdx.x & 31); }
+PG_DEV int pg_lane() { return (int)threadIdx.x; }      // one warp per CTA
 PG_DEV uint32_t pg_ballot(bool p) { return __ballot_sync(0xffffffffu, p); }
 PG_DEV bool pg_any(bool p) { return __any_sync(0xffffffffu, p); }
 PG_DEV uint32_t pg_shfl(uint32_t v, int src) { return __shfl_sync(0xffffffffu, v, src); }
@@ -86,7 +86,7 @@ struct PgWarpSmem {
    uint32_t S[TL][LW];
    uint32_t mw[LW];
    // per-level results of the current job
-   uint32_t A[TL + 1], B[TL + 1], P[TL + 1], META[TL + 1], H[TL + 1], ALIAS[TL + 1];
+   uint32_t A[TL + 1], B[TL + 1], P[TL + 1], META[TL + 1], H[TL + 1], ALIAS[TL + 1], AM[TL + 1];
    uint32_t queue[PG_QCAP];
    uint16_t seedq[PG_CHUNK_POS];     // seeds of the current chunk: offset from the tile origin | strand << 15
    // threshold filter of the far rings (pg_filter_tile): the read's first characters as a step table, the number of
@@ -576,27 +576,32 @@ PG_DEV PgResult pg_walk_emit(PgWarpCtx<LW, TL> &cx, const PgSearch &se, PgRun *d
    int lane = pg_lane();
    PgResult res;
    res.n_runs = 0; res.n_ups = 0; res.max_len = 0; res.last_abs_loc = 0; res.seeds = cx.any_seed ? 1u : 0u;
-   if (lane <= TL) { ws->A[lane] = 0; ws->B[lane] = 0; }
-   pg_syncwarp();
-   if (lane < se.T) {
-      ws->A[lane] = cx.lvl.A; ws->B[lane] = cx.lvl.B; ws->P[lane] = cx.lvl.pos; ws->META[lane] = cx.lvl.meta;
+   // levels >= T read as "no candidate" (A = B = 0)
+   const bool mine = lane < se.T;
+   if (lane <= TL) {
+      ws->A[lane] = mine ? cx.lvl.A : 0u; ws->B[lane] = mine ? cx.lvl.B : 0u;
+      ws->AM[lane] = lane <= se.MAX ? cx.lvl.A : 0xffffffffu;      // A_t of the levels that count towards m
+      ws->P[lane] = cx.lvl.pos; ws->META[lane] = cx.lvl.meta;
    }
-   pg_syncwarp();
-   // full-length masks of the seeds that can own a UniquePoint (one per level <= MAX)
-#pragma unroll 1
-   for (int t = 0; t <= se.MAX; t++) {
-      uint32_t At = ws->A[t];
-      bool need = At >= (uint32_t)(se.bp_start + t);
-      bool alias = need && t > 0 && ws->A[t - 1] >= (uint32_t)(se.bp_start + t - 1) && ws->P[t] == ws->P[t - 1] &&
-                   ws->META[t] == ws->META[t - 1];
-      if (!need) { if (lane == 0) ws->ALIAS[t] = (uint32_t)t; pg_syncwarp(); continue; }
-      if (alias) { if (lane == 0) { ws->ALIAS[t] = ws->ALIAS[t - 1]; ws->H[t] = ws->H[t - 1]; } pg_syncwarp(); continue; }
-      uint32_t meta = ws->META[t];
-      int d = se.far ? ((meta & 1u) ? -1 : 1) : se.d;
-      PgChars ch = se.chp;
-      if (se.far && (meta & 1u)) ch.inv = ~ch.inv;
-      uint32_t h = pg_full_masks<LW, TL>(ws, cx.chroms + (meta >> 1), ch.arr, ch.inv, ws->P[t], d, se.L, t);
-      if (lane == 0) { ws->ALIAS[t] = (uint32_t)t; ws->H[t] = h; }
+   // Full-length masks of the seeds that can own a UniquePoint: one per level <= MAX whose best seed is long enough
+   // (need), shared between consecutive levels owned by the same seed (alias).  Lane t decides for level t.
+   {
+      const uint32_t pA = pg_shfl_up(cx.lvl.A, 1), pP = pg_shfl_up(cx.lvl.pos, 1), pM = pg_shfl_up(cx.lvl.meta, 1);
+      const bool need = lane <= se.MAX && cx.lvl.A >= (uint32_t)(se.bp_start + lane);
+      const bool alias = need && lane > 0 && pA >= (uint32_t)(se.bp_start + lane - 1) && pP == cx.lvl.pos && pM == cx.lvl.meta;
+      uint32_t todo = pg_ballot(need && !alias);
+      // the level whose masks level t uses: the nearest computed level at or below t
+      if (lane <= TL) ws->ALIAS[lane] = need ? (uint32_t)(31 - pg_clz(todo & ((2u << lane) - 1u))) : (uint32_t)lane;
+      pg_syncwarp();
+      while (todo) {
+         const int t = pg_ffs(todo) - 1;
+         todo &= todo - 1u;
+         const uint32_t meta = ws->META[t];
+         const int d = se.far ? ((meta & 1u) ? -1 : 1) : se.d;
+         const uint32_t inv = (se.far && (meta & 1u)) ? ~se.chp.inv : se.chp.inv;
+         const uint32_t h = pg_full_masks<LW, TL>(ws, cx.chroms + (meta >> 1), se.chp.arr, inv, ws->P[t], d, se.L, t);
+         if (lane == 0) ws->H[t] = h;
+      }
       pg_syncwarp();
    }
    const int L = se.L, MAX = se.MAX, ADD = prm->add_mm, MP = prm->min_perfect;
@@ -608,12 +613,14 @@ PG_DEV PgResult pg_walk_emit(PgWarpCtx<LW, TL> &cx, const PgSearch &se, PgRun *d
    // A_t is non-decreasing in t: no length beyond A_MAX can pass the in-range test (m would be MAX+1 > g[len])
    int len_hi = (int)ws->A[MAX];
    if (len_hi > L - 1) len_hi = L - 1;
+#pragma unroll 1
    for (int r0 = se.bp_start; r0 <= len_hi && !dead; r0 += 32) {
       int len = r0 + lane;
       bool inrange = len <= L - 1;
       int m = 0;
-#pragma unroll 1
-      for (int t = 0; t <= MAX; t++) m += (ws->A[t] < (uint32_t)len) ? 1 : 0;
+#pragma unroll
+      for (int t = 0; t < TL; t++) m += (ws->AM[t] < (uint32_t)len) ? 1 : 0;
+      PG_PIN(m);               // one register, computed once (the compiler otherwise re-derives it at every use)
       bool abort_here = inrange && ((uint32_t)m > (uint32_t)prm->g[len]);       // searcher.cpp:167-169, pindel.cpp:2836-2838
       uint32_t abmask = pg_ballot(abort_here);
       uint32_t live = abmask ? ((1u << (pg_ffs(abmask) - 1)) - 1u) : 0xffffffffu;
@@ -635,7 +642,7 @@ PG_DEV PgResult pg_walk_emit(PgWarpCtx<LW, TL> &cx, const PgSearch &se, PgRun *d
             int bit = len - MP + j;
             ok = !((ws->S[slot][bit >> 5] >> (bit & 31)) & 1u);
          }
-         valid = ok && ws->H[m] >= thr;                                          // searcher.cpp:383
+         valid = ok && ws->H[slot] >= thr;                                       // searcher.cpp:383
       }
       uint32_t vmask = pg_ballot(valid);
       // run boundaries: a run continues while consecutive lengths are valid with the same level
@@ -715,34 +722,45 @@ template <int LW, int TL>
 PG_COLD int pg_pack_read(PgWarpSmem<LW, TL> *ws, const uint8_t *seq, int len)
 {
    int lane = pg_lane();
-   // strip trailing non-alphanumerics
-   int L = 0;
-   for (int c0 = 0; c0 < len; c0 += 32) {
-      int i = c0 + lane;
-      uint8_t ch = (i < len) ? pg_ldg8(seq + i) : (uint8_t)0;
-      bool alnum = (ch >= '0' && ch <= '9') || (ch >= 'A' && ch <= 'Z') || (ch >= 'a' && ch <= 'z');
-      uint32_t mk = pg_ballot(alnum);
-      if (mk) L = c0 + 32 - pg_clz(mk);
-   }
-   const int nch = (L + 31) >> 5;
-   if (lane < 8 * LW) (&ws->q[0][0][0])[lane] = 0u;         // 8 * LW plane words (<= 128): zero the unused tail words
+   if (lane < 8 * LW) (&ws->q[0][0][0])[lane] = 0u;         // 8 * LW plane words (<= 128)
    if (lane + 32 < 8 * LW) (&ws->q[0][0][0])[lane + 32] = 0u;
    if (lane + 64 < 8 * LW) (&ws->q[0][0][0])[lane + 64] = 0u;
    if (lane + 96 < 8 * LW) (&ws->q[0][0][0])[lane + 96] = 0u;
    pg_syncwarp();
+   // one pass over the characters: the forward planes, and L = the length without trailing non-alphanumerics
+   int L = 0;
+   const int nraw = (len + 31) >> 5;
 #pragma unroll 1
-   for (int c = 0; c < nch; c++) {
-#pragma unroll 1
-      for (int rev = 0; rev < 2; rev++) {
-         int i = 32 * c + lane;
-         int src = rev ? (L - 1 - i) : i;
-         uint8_t ch = (i < L) ? pg_ldg8(seq + src) : (uint8_t)'A';
-         uint32_t code = (ch == 'C') ? 1u : (ch == 'G') ? 2u : (ch == 'T') ? 3u : 0u;
-         bool isn = (ch == 'N');
-         bool isx = !(ch == 'A' || ch == 'C' || ch == 'G' || ch == 'T' || ch == 'N');
-         uint32_t lo = pg_ballot((code & 1u) != 0), hi = pg_ballot((code & 2u) != 0);
-         uint32_t nn = pg_ballot(isn), xx = pg_ballot(isx);
-         if (lane == 0) { ws->q[rev][0][c] = lo; ws->q[rev][1][c] = hi; ws->q[rev][2][c] = nn; ws->q[rev][3][c] = xx; }
+   for (int c = 0; c < nraw; c++) {
+      const int i = 32 * c + lane;
+      const uint8_t ch = (i < len) ? pg_ldg8(seq + i) : (uint8_t)0;
+      const bool alnum = (ch >= '0' && ch <= '9') || (ch >= 'A' && ch <= 'Z') || (ch >= 'a' && ch <= 'z');
+      const uint32_t mk = pg_ballot(alnum);
+      if (mk) L = 32 * c + 32 - pg_clz(mk);
+      const uint32_t code = (ch == 'C') ? 1u : (ch == 'G') ? 2u : (ch == 'T') ? 3u : 0u;
+      const bool isn = (ch == 'N');
+      const bool isx = !(ch == 'A' || ch == 'C' || ch == 'G' || ch == 'T' || ch == 'N');
+      const uint32_t lo = pg_ballot((code & 1u) != 0), hi = pg_ballot((code & 2u) != 0);
+      const uint32_t nn = pg_ballot(isn), xx = pg_ballot(isx);
+      if (lane == 0) { ws->q[0][0][c] = lo; ws->q[0][1][c] = hi; ws->q[0][2][c] = nn; ws->q[0][3][c] = xx; }
+   }
+   pg_syncwarp();
+   // cut the planes at L, then the reversed planes from the forward ones: with G = the whole LW-word string bit-reversed
+   // (G word c = brev of forward word LW-1-c), reversed[i] = forward[L-1-i] = G[i + 32*LW - L]
+   if (lane < LW) {
+      const uint32_t vm = pg_valid_mask<LW, TL>(L, lane);
+#pragma unroll
+      for (int pl = 0; pl < 4; pl++) ws->q[0][pl][lane] &= vm;
+   }
+   pg_syncwarp();
+   if (lane < LW) {
+      const int sft = 32 * LW - L, c0 = lane + (sft >> 5);
+      const uint32_t sb = (uint32_t)(sft & 31);
+#pragma unroll
+      for (int pl = 0; pl < 4; pl++) {
+         const uint32_t g0 = c0 < LW ? pg_brev(ws->q[0][pl][LW - 1 - c0]) : 0u;
+         const uint32_t g1 = c0 + 1 < LW ? pg_brev(ws->q[0][pl][LW - 2 - c0]) : 0u;
+         ws->q[1][pl][lane] = pg_fsr(g0, g1, sb);
       }
    }
    pg_syncwarp();

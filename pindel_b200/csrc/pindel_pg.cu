@@ -37,9 +37,9 @@ static_assert(sizeof(pg_close_info) == sizeof(PgCloseInfo) && sizeof(pg_close_in
 static_assert(PG_READ_FLIPPED == PG_F_FLIPPED && PG_READ_UNSUPPORTED == PG_F_TOOLONG && PG_READ_OVERFLOW == PG_F_OVERFLOW, "flags");
 
 #define PG_PIPE_CHUNK_DEFAULT (1 << 20)   // reads per chunk of the pipelined path; PG_PIPE_CHUNK in the environment overrides it (tests)
-#define PG_BLOCK_THREADS 256
+#define PG_BLOCK_THREADS 32
 #ifndef PG_MINB
-#define PG_MINB 4          // resident CTAs per SM the register allocator is asked to make room for (TL <= 8 variants)
+#define PG_MINB 32         // resident CTAs (= warps) per SM the register allocator is asked to make room for (TL <= 8 variants)
 #endif
 #define PG_WARPS_PER_BLOCK (PG_BLOCK_THREADS / 32)
 
@@ -75,33 +75,25 @@ __device__ __forceinline__ void pg_tile_load(PgWarpSmem<LW, TL> *ws, const PgChr
    phase ^= 1u;
 }
 
+// One warp per CTA: the warp's working set is a static __shared__ object, so every access to it is an LDS / STS with a
+// link-time constant address (with several warps per CTA the per-warp base had to be re-derived from the shared window
+// all over the hot loop, a few percent of all instructions), and the parameter block is read from the constant bank the
+// kernel arguments live in.  32 resident CTAs per SM = 32 warps at 64 registers, the same occupancy as 4 x 256 threads.
 template <int LW, int TL>
-__global__ void __launch_bounds__(PG_BLOCK_THREADS, (TL <= 8) ? PG_MINB : 1) pg_search_kernel(PgBatch bt, const PgParams *__restrict__ prm_g,
-                                                                     const PgChrom *__restrict__ chroms)
+__global__ void __launch_bounds__(32, (TL <= 8) ? PG_MINB : 1) pg_search_kernel(const __grid_constant__ PgBatch bt, const __grid_constant__ PgParams prm,
+                                                                                const PgChrom *__restrict__ chroms)
 {
-   extern __shared__ __align__(128) unsigned char pg_dyn_smem[];
-   __shared__ PgParams s_prm;
-   {
-      const uint32_t *src = reinterpret_cast<const uint32_t *>(prm_g);
-      uint32_t *dst = reinterpret_cast<uint32_t *>(&s_prm);
-      for (int i = threadIdx.x; i < (int)(sizeof(PgParams) / 4); i += blockDim.x) dst[i] = src[i];
-   }
-   const int warp = threadIdx.x >> 5;
-   // the byte offset of this warp's slice is made opaque so that it lives in one register instead of being
-   // re-derived from %tid at every use (the compiler otherwise rematerialises it all over the hot loop)
-   uint32_t ws_off = (uint32_t)warp * (uint32_t)sizeof(PgWarpSmem<LW, TL>);
-   asm volatile("" : "+r"(ws_off));
-   PgWarpSmem<LW, TL> *ws = reinterpret_cast<PgWarpSmem<LW, TL> *>(pg_dyn_smem + ws_off);
+   __shared__ __align__(128) PgWarpSmem<LW, TL> ws_s;
+   PgWarpSmem<LW, TL> *ws = &ws_s;
    if (pg_lane() == 0) {
       asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(pg_smem_addr(&ws->mbar)) : "memory");
       asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
    }
-   __syncthreads();
+   __syncwarp();
    PgWarpCtx<LW, TL> cx;
-   cx.ws = ws; cx.prm = &s_prm; cx.chroms = chroms;
+   cx.ws = ws; cx.prm = &prm; cx.chroms = chroms;
    uint32_t phase = 0;
-   const uint32_t gwarp = blockIdx.x * PG_WARPS_PER_BLOCK + warp;
-   PgRun *scratch = bt.scratch + (size_t)gwarp * 3u * bt.scratch_cap;
+   PgRun *scratch = bt.scratch + (size_t)blockIdx.x * 3u * bt.scratch_cap;
    for (;;) {
       uint32_t ri = 0;
       if (pg_lane() == 0) ri = atomicAdd(bt.counters, 1u);
@@ -352,6 +344,8 @@ __global__ void __launch_bounds__(256) pg_sv_order_kernel(const PgSvRecord *__re
 // ------------------------------------------------------------------------------------------------
 // Context
 // ------------------------------------------------------------------------------------------------
+#define PG_RES_SLOTS 3
+
 struct DevBuf {
    void *p = nullptr;
    size_t cap = 0;
@@ -375,9 +369,21 @@ struct pg_ctx {
    bool have_anchor = false, have_chr = false, have_close = false, have_regions = false;
    uint32_t max_read_len = 0;
    size_t blob_bytes = 0;
-   DevBuf seq_blob, seq_off, md, pos, isz, chr, closeinfo, regions, region_off, out, pool, counters, scratch;
-   uint32_t pool_cap = 0;
-   uint32_t *counters_h = nullptr;     // pinned
+   DevBuf seq_blob, seq_off, md, pos, isz, chr, closeinfo, regions, region_off, scratch;
+   // Results rotate through three slots, so that the records of launch k can still be read (handed to a collective that only
+   // gets SM time when a persistent search kernel drains, copied out) while launches k+1 and k+2 are queued: each slot has its
+   // own header array, run pool, counters and completion event.
+   struct ResSlot {
+      DevBuf out, pool, counters;
+      uint32_t pool_cap = 0;
+      uint32_t *counters_h = nullptr;  // pinned copy of the counters, filled right behind the kernel
+      cudaEvent_t done = nullptr;      // kernel + counters copy of the slot's launch
+      int n = 0, mode = 0;
+      bool launched = false;
+      uint32_t runs = 0;
+      uint64_t window_bases = 0, ups = 0;
+   } rs[PG_RES_SLOTS];
+   int cur = 0;                        // slot of the latest launch
    int last_mode = 0;
    bool launched = false;
    bool stats_valid = false;      // last_window_bases / last_ups / last_runs describe a completed call (resident or pipelined)
@@ -448,8 +454,7 @@ template <int LW, int TL>
 static int launch_variant(pg_ctx *ctx, const PgBatch &bt_in, cudaStream_t stream, DevBuf &scratch)
 {
    PgBatch bt = bt_in;
-   size_t smem = sizeof(PgWarpSmem<LW, TL>) * PG_WARPS_PER_BLOCK;
-   CU(cudaFuncSetAttribute(pg_search_kernel<LW, TL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+   size_t smem = 0;           // the warp's working set is static shared memory
    int per_sm = 0;
    CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, pg_search_kernel<LW, TL>, PG_BLOCK_THREADS, smem));
    if (per_sm < 1) per_sm = 1;
@@ -460,7 +465,7 @@ static int launch_variant(pg_ctx *ctx, const PgBatch &bt_in, cudaStream_t stream
    int rc = ensure(ctx, scratch, sizeof(PgRun) * 3u * bt.scratch_cap * (size_t)grid * PG_WARPS_PER_BLOCK);
    if (rc != PG_OK) return rc;
    bt.scratch = (PgRun *)scratch.p;
-   pg_search_kernel<LW, TL><<<grid, PG_BLOCK_THREADS, smem, stream>>>(bt, ctx->prm_d, ctx->chroms_d);
+   pg_search_kernel<LW, TL><<<grid, PG_BLOCK_THREADS, smem, stream>>>(bt, ctx->prm_h, ctx->chroms_d);
    CU(cudaGetLastError());
    ctx->launches++;
    return PG_OK;
@@ -540,8 +545,10 @@ pg_ctx *pg_create(const pg_settings *s)
              cudaDeviceGetAttribute(&ctx->n_sm, cudaDevAttrMultiProcessorCount, ctx->device) == cudaSuccess &&
              cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking) == cudaSuccess &&
              cudaMalloc(&ctx->prm_d, sizeof(PgParams)) == cudaSuccess &&
-             cudaMemcpy(ctx->prm_d, &ctx->prm_h, sizeof(PgParams), cudaMemcpyHostToDevice) == cudaSuccess &&
-             cudaHostAlloc((void **)&ctx->counters_h, 32, cudaHostAllocDefault) == cudaSuccess;
+             cudaMemcpy(ctx->prm_d, &ctx->prm_h, sizeof(PgParams), cudaMemcpyHostToDevice) == cudaSuccess;
+   for (int i = 0; ok && i < PG_RES_SLOTS; i++)
+      ok = cudaHostAlloc((void **)&ctx->rs[i].counters_h, 32, cudaHostAllocDefault) == cudaSuccess &&
+           cudaEventCreateWithFlags(&ctx->rs[i].done, cudaEventDisableTiming) == cudaSuccess;
    if (!ok) {
       g_create_error = std::string("CUDA initialisation failed: ") + cudaGetErrorString(cudaGetLastError());
       delete ctx;
@@ -559,8 +566,10 @@ void pg_destroy(pg_ctx *ctx)
    cudaDeviceSynchronize();
    for (void *p : ctx->chrom_allocs) cudaFree(p);
    DevBuf *bufs[] = {&ctx->seq_blob, &ctx->seq_off, &ctx->md, &ctx->pos, &ctx->isz, &ctx->chr, &ctx->closeinfo,
-                     &ctx->regions, &ctx->region_off, &ctx->out, &ctx->pool, &ctx->counters, &ctx->scratch};
+                     &ctx->regions, &ctx->region_off, &ctx->scratch};
    for (DevBuf *b : bufs) if (b->p) cudaFree(b->p);
+   for (int i = 0; i < PG_RES_SLOTS; i++)
+      for (DevBuf *b : {&ctx->rs[i].out, &ctx->rs[i].pool, &ctx->rs[i].counters}) if (b->p) cudaFree(b->p);
    DevBuf *svbufs[] = {&ctx->sv_seq, &ctx->sv_off, &ctx->sv_md, &ctx->sv_isz, &ctx->sv_flags, &ctx->sv_runoff, &ctx->sv_nclose,
                        &ctx->sv_runs, &ctx->sv_records, &ctx->sv_params, &ctx->sv_counters,
                        &ctx->sv_counts, &ctx->sv_offsets, &ctx->sv_blocksums, &ctx->sv_ordered, &ctx->sv_perm, &ctx->sv_close_off,
@@ -575,7 +584,10 @@ void pg_destroy(pg_ctx *ctx)
    pipe_destroy(ctx->pipe);
    if (ctx->chroms_d) cudaFree(ctx->chroms_d);
    if (ctx->prm_d) cudaFree(ctx->prm_d);
-   if (ctx->counters_h) cudaFreeHost(ctx->counters_h);
+   for (int i = 0; i < PG_RES_SLOTS; i++) {
+      if (ctx->rs[i].counters_h) cudaFreeHost(ctx->rs[i].counters_h);
+      if (ctx->rs[i].done) cudaEventDestroy(ctx->rs[i].done);
+   }
    if (ctx->sv_ev0) { cudaEventDestroy(ctx->sv_ev0); cudaEventDestroy(ctx->sv_ev1); }
    if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
    delete ctx;
@@ -700,27 +712,24 @@ int pg_upload(pg_ctx *ctx, const pg_reads *in)
    return PG_OK;
 }
 
-int pg_launch(pg_ctx *ctx, int32_t mode)
+// The search kernel over the resident batch into result slot `slot`; the slot's counters follow the kernel to the host
+// and its event marks both, so the slot can be waited for on its own while later work is already queued on the stream.
+static int launch_into(pg_ctx *ctx, int32_t mode, int slot)
 {
-   if (!ctx || mode < 1 || mode > 3) return fail(ctx, PG_ERR_ARG, "pg_launch: mode must be 1, 2 or 3");
-   if (ctx->chroms_h.empty()) return fail(ctx, PG_ERR_STATE, "pg_launch: no reference (call pg_set_reference)");
-   if ((mode & 1) && !ctx->have_anchor) return fail(ctx, PG_ERR_ARG, "close-end search needs matched_d, matched_rel_pos and insert_size");
-   if (mode == 2 && !ctx->have_close) return fail(ctx, PG_ERR_ARG, "far-end-only search needs close_info");
-   CU(cudaSetDevice(ctx->device));
-   ctx->last_mode = mode;
-   ctx->launched = true;
-   if (ctx->n == 0) return PG_OK;
+   pg_ctx::ResSlot &r = ctx->rs[slot];
    const int n = ctx->n;
+   r.n = n; r.mode = mode; r.launched = true;
+   if (n == 0) return PG_OK;
    int rc;
-   if ((rc = ensure(ctx, ctx->out, sizeof(PgReadOut) * (size_t)n)) != PG_OK) return rc;
-   if ((rc = ensure(ctx, ctx->counters, 32)) != PG_OK) return rc;
-   if (ctx->pool_cap == 0 || ctx->pool.p == nullptr) {
+   if ((rc = ensure(ctx, r.out, sizeof(PgReadOut) * (size_t)n)) != PG_OK) return rc;
+   if ((rc = ensure(ctx, r.counters, 32)) != PG_OK) return rc;
+   if (r.pool_cap == 0 || r.pool.p == nullptr) {
       size_t want = (size_t)n * 24u + 4096u;
       if (want > 0xfffffff0u) want = 0xfffffff0u;
-      if ((rc = ensure(ctx, ctx->pool, sizeof(PgRun) * want)) != PG_OK) return rc;
-      ctx->pool_cap = (uint32_t)(ctx->pool.cap / sizeof(PgRun));
+      if ((rc = ensure(ctx, r.pool, sizeof(PgRun) * want)) != PG_OK) return rc;
+      r.pool_cap = (uint32_t)(r.pool.cap / sizeof(PgRun));
    }
-   CU(cudaMemsetAsync(ctx->counters.p, 0, 32, ctx->stream));
+   CU(cudaMemsetAsync(r.counters.p, 0, 32, ctx->stream));
    PgBatch bt;
    memset(&bt, 0, sizeof(bt));
    bt.n_reads = n;
@@ -734,11 +743,28 @@ int pg_launch(pg_ctx *ctx, int32_t mode)
    bt.close_info = (mode == 2 && ctx->have_close) ? (const PgCloseInfo *)ctx->closeinfo.p : nullptr;
    bt.regions = ctx->have_regions ? (const PgRegion *)ctx->regions.p : nullptr;
    bt.region_off = ctx->have_regions ? (const uint32_t *)ctx->region_off.p : nullptr;
-   bt.out = (PgReadOut *)ctx->out.p;
-   bt.run_pool = (PgRun *)ctx->pool.p;
-   bt.run_pool_cap = ctx->pool_cap;
-   bt.counters = (uint32_t *)ctx->counters.p;
-   return dispatch_variant(ctx, bt, ctx->max_read_len, ctx->stream, ctx->scratch);
+   bt.out = (PgReadOut *)r.out.p;
+   bt.run_pool = (PgRun *)r.pool.p;
+   bt.run_pool_cap = r.pool_cap;
+   bt.counters = (uint32_t *)r.counters.p;
+   rc = dispatch_variant(ctx, bt, ctx->max_read_len, ctx->stream, ctx->scratch);
+   if (rc != PG_OK) return rc;
+   CU(cudaMemcpyAsync(r.counters_h, r.counters.p, 32, cudaMemcpyDeviceToHost, ctx->stream));
+   CU(cudaEventRecord(r.done, ctx->stream));
+   return PG_OK;
+}
+
+int pg_launch(pg_ctx *ctx, int32_t mode)
+{
+   if (!ctx || mode < 1 || mode > 3) return fail(ctx, PG_ERR_ARG, "pg_launch: mode must be 1, 2 or 3");
+   if (ctx->chroms_h.empty()) return fail(ctx, PG_ERR_STATE, "pg_launch: no reference (call pg_set_reference)");
+   if ((mode & 1) && !ctx->have_anchor) return fail(ctx, PG_ERR_ARG, "close-end search needs matched_d, matched_rel_pos and insert_size");
+   if (mode == 2 && !ctx->have_close) return fail(ctx, PG_ERR_ARG, "far-end-only search needs close_info");
+   CU(cudaSetDevice(ctx->device));
+   ctx->last_mode = mode;
+   ctx->launched = true;
+   ctx->cur = (ctx->cur + 1) % PG_RES_SLOTS;
+   return launch_into(ctx, mode, ctx->cur);
 }
 
 int pg_sync(pg_ctx *ctx)
@@ -749,31 +775,44 @@ int pg_sync(pg_ctx *ctx)
    return PG_OK;
 }
 
-// Waits for the launch; if the run pool was too small, grows it to the exact size and runs again.
-static int finish_launch(pg_ctx *ctx)
+// Waits for the launch of a slot (its event, not the whole stream); if the run pool was too small, grows it to the exact size
+// and runs the slot again.
+static int finish_slot(pg_ctx *ctx, int slot)
 {
-   if (!ctx->launched) return fail(ctx, PG_ERR_STATE, "no launch to wait for");
-   if (ctx->n == 0) { ctx->last_runs = 0; return PG_OK; }
+   pg_ctx::ResSlot &r = ctx->rs[slot];
+   if (!r.launched) return fail(ctx, PG_ERR_STATE, "no launch to wait for");
+   if (r.n == 0) { r.runs = 0; r.window_bases = r.ups = 0; return PG_OK; }
    for (int attempt = 0; attempt < 3; attempt++) {
-      CU(cudaMemcpyAsync(ctx->counters_h, ctx->counters.p, 32, cudaMemcpyDeviceToHost, ctx->stream));
-      CU(cudaStreamSynchronize(ctx->stream));
-      if (ctx->counters_h[2] == 0) {
-         ctx->last_runs = ctx->counters_h[1];
-         memcpy(&ctx->last_window_bases, ctx->counters_h + 4, 8);
-         memcpy(&ctx->last_ups, ctx->counters_h + 6, 8);
-         ctx->stats_valid = true;
+      CU(cudaEventSynchronize(r.done));
+      if (r.counters_h[2] == 0) {
+         r.runs = r.counters_h[1];
+         memcpy(&r.window_bases, r.counters_h + 4, 8);
+         memcpy(&r.ups, r.counters_h + 6, 8);
          return PG_OK;
       }
-      uint32_t need = ctx->counters_h[1];
-      CU(cudaFree(ctx->pool.p));
-      ctx->pool.p = nullptr; ctx->pool.cap = 0; ctx->pool_cap = 0;
-      int rc = ensure(ctx, ctx->pool, sizeof(PgRun) * ((size_t)need + 1024u));
+      if (r.n != ctx->n) return fail(ctx, PG_ERR_STATE, "run pool overflow in a launch whose batch is no longer resident");
+      uint32_t need = r.counters_h[1];
+      CU(cudaStreamSynchronize(ctx->stream));
+      CU(cudaFree(r.pool.p));
+      r.pool.p = nullptr; r.pool.cap = 0; r.pool_cap = 0;
+      int rc = ensure(ctx, r.pool, sizeof(PgRun) * ((size_t)need + 1024u));
       if (rc != PG_OK) return rc;
-      ctx->pool_cap = (uint32_t)(ctx->pool.cap / sizeof(PgRun));
-      rc = pg_launch(ctx, ctx->last_mode);
+      r.pool_cap = (uint32_t)(r.pool.cap / sizeof(PgRun));
+      rc = launch_into(ctx, r.mode, slot);
       if (rc != PG_OK) return rc;
    }
    return fail(ctx, PG_ERR_CUDA, "run pool kept overflowing");
+}
+
+static int finish_launch(pg_ctx *ctx)
+{
+   if (!ctx->launched) return fail(ctx, PG_ERR_STATE, "no launch to wait for");
+   int rc = finish_slot(ctx, ctx->cur);
+   if (rc != PG_OK) return rc;
+   const pg_ctx::ResSlot &r = ctx->rs[ctx->cur];
+   ctx->last_runs = r.runs; ctx->last_window_bases = r.window_bases; ctx->last_ups = r.ups;
+   ctx->stats_valid = true;
+   return PG_OK;
 }
 
 int pg_download(pg_ctx *ctx, pg_results *res)
@@ -787,9 +826,9 @@ int pg_download(pg_ctx *ctx, pg_results *res)
    if (!res->out) return fail(ctx, PG_ERR_ARG, "pg_download: out is NULL");
    if (res->n_runs > res->runs_cap || (res->n_runs && !res->runs))
       return fail(ctx, PG_ERR_RUNS_CAP, "run buffer too small");
-   CU(cudaMemcpyAsync(res->out, ctx->out.p, sizeof(PgReadOut) * (size_t)ctx->n, cudaMemcpyDeviceToHost, ctx->stream));
+   CU(cudaMemcpyAsync(res->out, ctx->rs[ctx->cur].out.p, sizeof(PgReadOut) * (size_t)ctx->n, cudaMemcpyDeviceToHost, ctx->stream));
    if (res->n_runs)
-      CU(cudaMemcpyAsync(res->runs, ctx->pool.p, sizeof(PgRun) * (size_t)res->n_runs, cudaMemcpyDeviceToHost, ctx->stream));
+      CU(cudaMemcpyAsync(res->runs, ctx->rs[ctx->cur].pool.p, sizeof(PgRun) * (size_t)res->n_runs, cudaMemcpyDeviceToHost, ctx->stream));
    CU(cudaStreamSynchronize(ctx->stream));
    return PG_OK;
 }
@@ -798,95 +837,63 @@ int pg_download(pg_ctx *ctx, pg_results *res)
 } // extern "C"
 
 // ------------------------------------------------------------------------------------------------
-// Large batches: chunks of ctx->pipe_chunk reads flow through two device slots on three streams, so that the H2D copy
-// of chunk c+1 and the D2H copy of chunk c-1 overlap the search kernel of chunk c.
+// Large batches: the batch is uploaded in chunks of ctx->pipe_chunk reads on a copy stream while the search kernel of the
+// previous chunk runs on a second stream and (pg_search & co.) the records of the chunk before that travel to the caller's
+// host buffers on a third.  Every chunk's kernel works on its range of the ONE resident batch and allocates its runs from
+// the ONE run pool of the current result slot, so a chunk's runs are a contiguous stretch of the pool, run offsets are
+// global, and when the call returns the whole batch and its results are resident exactly as after pg_upload + pg_launch
+// (pg_device_results, pg_classify_resident work on them).
 // ------------------------------------------------------------------------------------------------
-
-struct PipeSlot {
-   DevBuf seq_blob, seq_off, md, pos, isz, chr, closeinfo, regions, region_off, out, pool, counters, scratch;
-   uint32_t pool_cap = 0;
-   uint32_t *counters_h = nullptr;
-   cudaEvent_t in_done = nullptr, k_done = nullptr, cnt_done = nullptr, out_done = nullptr;
-   int c0 = 0, c1 = 0;
-   uint32_t n_runs = 0;
-   bool busy = false;
-};
+#define PG_PIPE_MAX_CHUNKS 4096
 
 struct PipeState {
-   PipeSlot slot[2];
    cudaStream_t s_in = nullptr, s_k = nullptr, s_out = nullptr;
-   bool ready = false;
+   std::vector<cudaEvent_t> in_done, k_done;    // per chunk
+   cudaEvent_t out_done = nullptr;
+   uint32_t *counters_h = nullptr;               // pinned, 8 words per chunk
+   int counters_cap = 0;
+   bool busy = false;                            // work of a call may still be queued (only after an error return)
 };
 
 static void pipe_destroy(PipeState *ps)
 {
    if (!ps) return;
-   for (int i = 0; i < 2; i++) {
-      PipeSlot &sl = ps->slot[i];
-      DevBuf *bufs[] = {&sl.seq_blob, &sl.seq_off, &sl.md, &sl.pos, &sl.isz, &sl.chr, &sl.closeinfo, &sl.regions, &sl.region_off,
-                        &sl.out, &sl.pool, &sl.counters, &sl.scratch};
-      for (DevBuf *b : bufs) if (b->p) cudaFree(b->p);
-      if (sl.counters_h) cudaFreeHost(sl.counters_h);
-      cudaEvent_t evs[] = {sl.in_done, sl.k_done, sl.cnt_done, sl.out_done};
-      for (cudaEvent_t e : evs) if (e) cudaEventDestroy(e);
-   }
+   for (cudaEvent_t e : ps->in_done) cudaEventDestroy(e);
+   for (cudaEvent_t e : ps->k_done) cudaEventDestroy(e);
+   if (ps->out_done) cudaEventDestroy(ps->out_done);
+   if (ps->counters_h) cudaFreeHost(ps->counters_h);
    if (ps->s_in) cudaStreamDestroy(ps->s_in);
    if (ps->s_k) cudaStreamDestroy(ps->s_k);
    if (ps->s_out) cudaStreamDestroy(ps->s_out);
    delete ps;
 }
 
-static int pipe_init(pg_ctx *ctx, PipeState *&ps)
+static int pipe_init(pg_ctx *ctx, PipeState *&ps, int nchunks)
 {
-   if (ps && ps->ready) return PG_OK;
    if (!ps) ps = new PipeState();
-   CU(cudaStreamCreateWithFlags(&ps->s_in, cudaStreamNonBlocking));
-   CU(cudaStreamCreateWithFlags(&ps->s_k, cudaStreamNonBlocking));
-   CU(cudaStreamCreateWithFlags(&ps->s_out, cudaStreamNonBlocking));
-   for (int i = 0; i < 2; i++) {
-      PipeSlot &sl = ps->slot[i];
-      CU(cudaHostAlloc((void **)&sl.counters_h, 32, cudaHostAllocDefault));
-      CU(cudaEventCreateWithFlags(&sl.in_done, cudaEventDisableTiming));
-      CU(cudaEventCreateWithFlags(&sl.k_done, cudaEventDisableTiming));
-      CU(cudaEventCreateWithFlags(&sl.cnt_done, cudaEventDisableTiming));
-      CU(cudaEventCreateWithFlags(&sl.out_done, cudaEventDisableTiming));
+   if (!ps->s_in) CU(cudaStreamCreateWithFlags(&ps->s_in, cudaStreamNonBlocking));
+   if (!ps->s_k) CU(cudaStreamCreateWithFlags(&ps->s_k, cudaStreamNonBlocking));
+   if (!ps->s_out) CU(cudaStreamCreateWithFlags(&ps->s_out, cudaStreamNonBlocking));
+   if (!ps->out_done) CU(cudaEventCreateWithFlags(&ps->out_done, cudaEventDisableTiming));
+   while ((int)ps->in_done.size() < nchunks) {
+      cudaEvent_t e = nullptr;
+      CU(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+      ps->in_done.push_back(e);
    }
-   ps->ready = true;
+   while ((int)ps->k_done.size() < nchunks) {
+      cudaEvent_t e = nullptr;
+      CU(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+      ps->k_done.push_back(e);
+   }
+   if (ps->counters_cap < nchunks) {
+      if (ps->counters_h) { cudaFreeHost(ps->counters_h); ps->counters_h = nullptr; ps->counters_cap = 0; }
+      CU(cudaHostAlloc((void **)&ps->counters_h, 32 * (size_t)nchunks, cudaHostAllocDefault));
+      ps->counters_cap = nchunks;
+   }
    return PG_OK;
 }
 
-static int pipe_launch_kernel(pg_ctx *ctx, PipeState *ps, PipeSlot &sl, const pg_reads *in, int mode, uint32_t max_read_len)
-{
-   const int m = sl.c1 - sl.c0;
-   const bool have_anchor = in->matched_d && in->matched_rel_pos && in->insert_size;
-   const bool have_regions = in->regions && in->region_off;
-   CU(cudaMemsetAsync(sl.counters.p, 0, 32, ps->s_k));
-   PgBatch bt;
-   memset(&bt, 0, sizeof(bt));
-   bt.n_reads = m;
-   bt.mode = mode;
-   // offsets stay absolute (as the caller gave them); the blob / region pointers are shifted instead
-   bt.seq_blob = (const uint8_t *)sl.seq_blob.p - in->seq_off[sl.c0];
-   bt.seq_off = (const uint32_t *)sl.seq_off.p;
-   bt.matched_d = have_anchor ? (const uint8_t *)sl.md.p : nullptr;
-   bt.matched_rel_pos = have_anchor ? (const uint32_t *)sl.pos.p : nullptr;
-   bt.insert_size = have_anchor ? (const int16_t *)sl.isz.p : nullptr;
-   bt.chr_id = in->chr_id ? (const int32_t *)sl.chr.p : nullptr;
-   bt.close_info = (mode == 2 && in->close_info) ? (const PgCloseInfo *)sl.closeinfo.p : nullptr;
-   bt.regions = have_regions ? (const PgRegion *)sl.regions.p - in->region_off[sl.c0] : nullptr;
-   bt.region_off = have_regions ? (const uint32_t *)sl.region_off.p : nullptr;
-   bt.out = (PgReadOut *)sl.out.p;
-   bt.run_pool = (PgRun *)sl.pool.p;
-   bt.run_pool_cap = sl.pool_cap;
-   bt.counters = (uint32_t *)sl.counters.p;
-   int rc = dispatch_variant(ctx, bt, max_read_len, ps->s_k, sl.scratch);
-   if (rc != PG_OK) return rc;
-   CU(cudaEventRecord(sl.k_done, ps->s_k));
-   CU(cudaMemcpyAsync(sl.counters_h, sl.counters.p, 32, cudaMemcpyDeviceToHost, ps->s_k));
-   CU(cudaEventRecord(sl.cnt_done, ps->s_k));
-   return PG_OK;
-}
-
+// res == nullptr: nothing is copied back (pg_search_resident); the call then returns as soon as everything is queued.
 static int run_pipelined(pg_ctx *ctx, PipeState *&ps, const pg_reads *in, pg_results *res, int mode)
 {
    const int n = in->n;
@@ -895,7 +902,7 @@ static int run_pipelined(pg_ctx *ctx, PipeState *&ps, const pg_reads *in, pg_res
    if ((mode & 1) && !have_anchor) return fail(ctx, PG_ERR_ARG, "close-end search needs matched_d, matched_rel_pos and insert_size");
    if (mode == 2 && !in->close_info) return fail(ctx, PG_ERR_ARG, "far-end-only search needs close_info");
    if (ctx->chroms_h.empty()) return fail(ctx, PG_ERR_STATE, "no reference (call pg_set_reference)");
-   if (!res || !res->out) return fail(ctx, PG_ERR_ARG, "results buffers missing");
+   if (res && !res->out) return fail(ctx, PG_ERR_ARG, "results buffers missing");
    uint32_t maxlen = 0;
    for (int i = 0; i < n; i++) {
       if (in->seq_off[i + 1] < in->seq_off[i]) return fail(ctx, PG_ERR_ARG, "seq_off must be non-decreasing");
@@ -910,111 +917,156 @@ static int run_pipelined(pg_ctx *ctx, PipeState *&ps, const pg_reads *in, pg_res
       for (size_t i = 0, nr = in->region_off[n]; i < nr; i++)
          if (in->regions[i].chr < 0 || (size_t)in->regions[i].chr >= ctx->chroms_h.size())
             return fail(ctx, PG_ERR_ARG, "region chromosome out of range");
-   int rc = pipe_init(ctx, ps);
+   int chunk = ctx->pipe_chunk;
+   if ((n + chunk - 1) / chunk > PG_PIPE_MAX_CHUNKS) chunk = (n + PG_PIPE_MAX_CHUNKS - 1) / PG_PIPE_MAX_CHUNKS;
+   const int nchunks = (n + chunk - 1) / chunk;
+   int rc = pipe_init(ctx, ps, nchunks);
    if (rc != PG_OK) return rc;
-   // A slot is only ever drained by the call that launched it: whatever way this function is left (an allocation that
-   // fails, a failed drain, a pool that keeps overflowing), the three streams are drained and both slots are idle again,
-   // so the next call never sees a stale chunk with another caller's c0 / c1 / result buffers.
+   // Whatever way this function is left, the three streams are drained before the next call touches the buffers again.
    struct PipeIdle {
       PipeState *ps;
       void settle() const
       {
-         if (!ps->slot[0].busy && !ps->slot[1].busy) return;
+         if (!ps->busy) return;
          cudaStreamSynchronize(ps->s_in); cudaStreamSynchronize(ps->s_k); cudaStreamSynchronize(ps->s_out);
-         ps->slot[0].busy = ps->slot[1].busy = false;
+         ps->busy = false;
       }
       ~PipeIdle() { settle(); }
    } idle{ps};
    idle.settle();
    CU(cudaStreamSynchronize(ctx->stream));         // everything queued by the caller on its stream comes first
-   ctx->launched = false;                           // no resident batch after a pipelined call
+   // the batch becomes the resident batch
+   ctx->launched = false;
    ctx->stats_valid = false;
-   ctx->n = 0;
-   const int nchunks = (n + ctx->pipe_chunk - 1) / ctx->pipe_chunk;
-   uint64_t total_runs = 0, wb = 0, ups = 0;
-   bool cap_exceeded = false;
-   auto drain = [&](PipeSlot &sl) -> int {        // kernel of this slot is done: copy its results out
-      CU(cudaEventSynchronize(sl.cnt_done));
-      if (sl.counters_h[2] != 0) {                // run pool too small for this chunk: grow exactly, run the chunk again
-         uint32_t need = sl.counters_h[1];
-         CU(cudaFree(sl.pool.p));
-         sl.pool.p = nullptr; sl.pool.cap = 0;
-         int r = ensure(ctx, sl.pool, sizeof(PgRun) * ((size_t)need + 1024u));
-         if (r != PG_OK) return r;
-         sl.pool_cap = (uint32_t)(sl.pool.cap / sizeof(PgRun));
-         r = pipe_launch_kernel(ctx, ps, sl, in, mode, maxlen);
-         if (r != PG_OK) return r;
-         CU(cudaEventSynchronize(sl.cnt_done));
-         if (sl.counters_h[2] != 0) return fail(ctx, PG_ERR_CUDA, "run pool kept overflowing");
+   ctx->n = n;
+   ctx->have_anchor = have_anchor;
+   ctx->have_chr = in->chr_id != nullptr;
+   ctx->have_close = in->close_info != nullptr;
+   ctx->have_regions = have_regions;
+   ctx->max_read_len = maxlen;
+   ctx->blob_bytes = in->seq_off[n];
+   const size_t n_regions = have_regions ? in->region_off[n] : 0;
+   if ((rc = ensure(ctx, ctx->seq_blob, ctx->blob_bytes ? ctx->blob_bytes : 1)) != PG_OK) return rc;
+   if ((rc = ensure(ctx, ctx->seq_off, sizeof(uint32_t) * ((size_t)n + 1))) != PG_OK) return rc;
+   if (have_anchor) {
+      if ((rc = ensure(ctx, ctx->md, (size_t)n)) != PG_OK) return rc;
+      if ((rc = ensure(ctx, ctx->pos, sizeof(uint32_t) * (size_t)n)) != PG_OK) return rc;
+      if ((rc = ensure(ctx, ctx->isz, sizeof(int16_t) * (size_t)n)) != PG_OK) return rc;
+   }
+   if (in->chr_id && (rc = ensure(ctx, ctx->chr, sizeof(int32_t) * (size_t)n)) != PG_OK) return rc;
+   if (in->close_info && (rc = ensure(ctx, ctx->closeinfo, sizeof(pg_close_info) * (size_t)n)) != PG_OK) return rc;
+   if (have_regions) {
+      if ((rc = ensure(ctx, ctx->regions, sizeof(pg_region) * (n_regions ? n_regions : 1))) != PG_OK) return rc;
+      if ((rc = ensure(ctx, ctx->region_off, sizeof(uint32_t) * ((size_t)n + 1))) != PG_OK) return rc;
+   }
+   ctx->cur = (ctx->cur + 1) % PG_RES_SLOTS;
+   pg_ctx::ResSlot &r = ctx->rs[ctx->cur];
+   r.n = n; r.mode = mode; r.launched = false;
+   if ((rc = ensure(ctx, r.out, sizeof(PgReadOut) * (size_t)n)) != PG_OK) return rc;
+   if ((rc = ensure(ctx, r.counters, 32)) != PG_OK) return rc;
+   if (r.pool_cap == 0 || r.pool.p == nullptr) {
+      size_t want = (size_t)n * 24u + 4096u;
+      if (want > 0xfffffff0u) want = 0xfffffff0u;
+      if ((rc = ensure(ctx, r.pool, sizeof(PgRun) * want)) != PG_OK) return rc;
+      r.pool_cap = (uint32_t)(r.pool.cap / sizeof(PgRun));
+   }
+   ps->busy = true;
+   CU(cudaMemsetAsync(r.counters.p, 0, 32, ps->s_k));
+   uint32_t runs_before = 0;      // runs allocated by the chunks already drained
+   bool cap_exceeded = false, overflow = false;
+   auto drain = [&](int c) -> int {                 // chunk c's kernel: wait for it, send its records to the caller
+      CU(cudaEventSynchronize(ps->k_done[c]));
+      const uint32_t *cn = ps->counters_h + 8 * (size_t)c;
+      if (cn[2] != 0) { overflow = true; return PG_OK; }
+      const uint32_t runs_now = cn[1];
+      const int c0 = c * chunk, c1 = (c0 + chunk < n) ? c0 + chunk : n;
+      if (res && !overflow) {
+         CU(cudaStreamWaitEvent(ps->s_out, ps->k_done[c], 0));
+         CU(cudaMemcpyAsync(res->out + c0, (const PgReadOut *)r.out.p + c0, sizeof(PgReadOut) * (size_t)(c1 - c0), cudaMemcpyDeviceToHost, ps->s_out));
+         if (runs_now <= res->runs_cap && res->runs) {
+            if (runs_now > runs_before)
+               CU(cudaMemcpyAsync(res->runs + runs_before, (const PgRun *)r.pool.p + runs_before, sizeof(PgRun) * (size_t)(runs_now - runs_before),
+                                  cudaMemcpyDeviceToHost, ps->s_out));
+         } else if (runs_now) {
+            cap_exceeded = true;
+         }
       }
-      sl.n_runs = sl.counters_h[1];
-      uint64_t a, b;
-      memcpy(&a, sl.counters_h + 4, 8); memcpy(&b, sl.counters_h + 6, 8);
-      wb += a; ups += b;
-      const int m = sl.c1 - sl.c0;
-      CU(cudaStreamWaitEvent(ps->s_out, sl.k_done, 0));
-      CU(cudaMemcpyAsync(res->out + sl.c0, sl.out.p, sizeof(PgReadOut) * (size_t)m, cudaMemcpyDeviceToHost, ps->s_out));
-      if (total_runs + sl.n_runs <= res->runs_cap && res->runs) {
-         if (sl.n_runs)
-            CU(cudaMemcpyAsync(res->runs + total_runs, sl.pool.p, sizeof(PgRun) * (size_t)sl.n_runs, cudaMemcpyDeviceToHost, ps->s_out));
-      } else {
-         cap_exceeded = true;
-      }
-      CU(cudaEventRecord(sl.out_done, ps->s_out));
-      CU(cudaEventSynchronize(sl.out_done));       // (the next chunk's kernel is already running behind this wait)
-      const uint32_t base = (uint32_t)total_runs;  // run offsets of this chunk become offsets into the caller's buffer
-      if (base)
-         for (int i = sl.c0; i < sl.c1; i++) res->out[i].run_off += base;
-      total_runs += sl.n_runs;
-      sl.busy = false;
+      runs_before = runs_now;
       return PG_OK;
    };
    for (int c = 0; c < nchunks; c++) {
-      PipeSlot &sl = ps->slot[c & 1];
-      if (sl.busy) { rc = drain(sl); if (rc != PG_OK) return rc; }
-      sl.c0 = c * ctx->pipe_chunk;
-      sl.c1 = (sl.c0 + ctx->pipe_chunk < n) ? sl.c0 + ctx->pipe_chunk : n;
-      const int m = sl.c1 - sl.c0;
-#define UPS(buf, src, bytes)                                                                              \
-   if ((rc = ensure(ctx, buf, (bytes))) != PG_OK) return rc;                                              \
-   CU(cudaMemcpyAsync(buf.p, (src), (bytes), cudaMemcpyHostToDevice, ps->s_in))
-      size_t b0 = in->seq_off[sl.c0], b1 = in->seq_off[sl.c1];
-      UPS(sl.seq_blob, in->seq_blob + b0, (b1 - b0) ? (b1 - b0) : 1);
-      UPS(sl.seq_off, in->seq_off + sl.c0, sizeof(uint32_t) * ((size_t)m + 1));
+      const int c0 = c * chunk, c1 = (c0 + chunk < n) ? c0 + chunk : n, m = c1 - c0;
+#define UPS(buf, src, off, bytes) CU(cudaMemcpyAsync((char *)buf.p + (off), (const char *)(src) + (off), (bytes), cudaMemcpyHostToDevice, ps->s_in))
+      const size_t b0 = in->seq_off[c0], b1 = in->seq_off[c1];
+      if (b1 > b0) UPS(ctx->seq_blob, in->seq_blob, b0, b1 - b0);
+      UPS(ctx->seq_off, in->seq_off, sizeof(uint32_t) * (size_t)c0, sizeof(uint32_t) * ((size_t)m + 1));
       if (have_anchor) {
-         UPS(sl.md, in->matched_d + sl.c0, (size_t)m);
-         UPS(sl.pos, in->matched_rel_pos + sl.c0, sizeof(uint32_t) * (size_t)m);
-         UPS(sl.isz, in->insert_size + sl.c0, sizeof(int16_t) * (size_t)m);
+         UPS(ctx->md, in->matched_d, (size_t)c0, (size_t)m);
+         UPS(ctx->pos, in->matched_rel_pos, sizeof(uint32_t) * (size_t)c0, sizeof(uint32_t) * (size_t)m);
+         UPS(ctx->isz, in->insert_size, sizeof(int16_t) * (size_t)c0, sizeof(int16_t) * (size_t)m);
       }
-      if (in->chr_id) { UPS(sl.chr, in->chr_id + sl.c0, sizeof(int32_t) * (size_t)m); }
-      if (mode == 2 && in->close_info) { UPS(sl.closeinfo, in->close_info + sl.c0, sizeof(pg_close_info) * (size_t)m); }
+      if (in->chr_id) UPS(ctx->chr, in->chr_id, sizeof(int32_t) * (size_t)c0, sizeof(int32_t) * (size_t)m);
+      if (in->close_info) UPS(ctx->closeinfo, in->close_info, sizeof(pg_close_info) * (size_t)c0, sizeof(pg_close_info) * (size_t)m);
       if (have_regions) {
-         size_t r0 = in->region_off[sl.c0], r1 = in->region_off[sl.c1];
-         UPS(sl.regions, in->regions + r0, sizeof(pg_region) * ((r1 - r0) ? (r1 - r0) : 1));
-         UPS(sl.region_off, in->region_off + sl.c0, sizeof(uint32_t) * ((size_t)m + 1));
+         const size_t r0 = in->region_off[c0], r1 = in->region_off[c1];
+         if (r1 > r0) UPS(ctx->regions, in->regions, sizeof(pg_region) * r0, sizeof(pg_region) * (r1 - r0));
+         UPS(ctx->region_off, in->region_off, sizeof(uint32_t) * (size_t)c0, sizeof(uint32_t) * ((size_t)m + 1));
       }
 #undef UPS
-      CU(cudaEventRecord(sl.in_done, ps->s_in));
-      if ((rc = ensure(ctx, sl.out, sizeof(PgReadOut) * (size_t)m)) != PG_OK) return rc;
-      if ((rc = ensure(ctx, sl.counters, 32)) != PG_OK) return rc;
-      if (sl.pool_cap == 0) {
-         if ((rc = ensure(ctx, sl.pool, sizeof(PgRun) * ((size_t)ctx->pipe_chunk * 12u + 4096u))) != PG_OK) return rc;
-         sl.pool_cap = (uint32_t)(sl.pool.cap / sizeof(PgRun));
-      }
-      CU(cudaStreamWaitEvent(ps->s_k, sl.in_done, 0));
-      rc = pipe_launch_kernel(ctx, ps, sl, in, mode, maxlen);
+      CU(cudaEventRecord(ps->in_done[c], ps->s_in));
+      CU(cudaStreamWaitEvent(ps->s_k, ps->in_done[c], 0));
+      CU(cudaMemsetAsync(r.counters.p, 0, 4, ps->s_k));       // the chunk's own read counter; the run allocator and the statistics run on
+      PgBatch bt;
+      memset(&bt, 0, sizeof(bt));
+      bt.n_reads = m;
+      bt.mode = mode;
+      bt.seq_blob = (const uint8_t *)ctx->seq_blob.p;           // offsets are absolute: every chunk sees the whole blob / region list
+      bt.seq_off = (const uint32_t *)ctx->seq_off.p + c0;
+      bt.matched_d = have_anchor ? (const uint8_t *)ctx->md.p + c0 : nullptr;
+      bt.matched_rel_pos = have_anchor ? (const uint32_t *)ctx->pos.p + c0 : nullptr;
+      bt.insert_size = have_anchor ? (const int16_t *)ctx->isz.p + c0 : nullptr;
+      bt.chr_id = in->chr_id ? (const int32_t *)ctx->chr.p + c0 : nullptr;
+      bt.close_info = (mode == 2 && in->close_info) ? (const PgCloseInfo *)ctx->closeinfo.p + c0 : nullptr;
+      bt.regions = have_regions ? (const PgRegion *)ctx->regions.p : nullptr;
+      bt.region_off = have_regions ? (const uint32_t *)ctx->region_off.p + c0 : nullptr;
+      bt.out = (PgReadOut *)r.out.p + c0;
+      bt.run_pool = (PgRun *)r.pool.p;
+      bt.run_pool_cap = r.pool_cap;
+      bt.counters = (uint32_t *)r.counters.p;
+      rc = dispatch_variant(ctx, bt, maxlen, ps->s_k, ctx->scratch);
       if (rc != PG_OK) return rc;
-      sl.busy = true;
+      CU(cudaMemcpyAsync(ps->counters_h + 8 * (size_t)c, r.counters.p, 32, cudaMemcpyDeviceToHost, ps->s_k));
+      CU(cudaEventRecord(ps->k_done[c], ps->s_k));
+      if (res && c >= 1) { rc = drain(c - 1); if (rc != PG_OK) return rc; }
    }
-   for (int k = 0; k < 2; k++) {                  // drain in chunk order
-      PipeSlot &sl = ps->slot[(nchunks + k) & 1];
-      if (sl.busy) { rc = drain(sl); if (rc != PG_OK) return rc; }
+   // the slot's own completion record: final counters + event, and the caller's stream waits for it
+   CU(cudaMemcpyAsync(r.counters_h, r.counters.p, 32, cudaMemcpyDeviceToHost, ps->s_k));
+   CU(cudaEventRecord(r.done, ps->s_k));
+   CU(cudaStreamWaitEvent(ctx->stream, r.done, 0));
+   r.launched = true;
+   ctx->launched = true;
+   ctx->last_mode = mode;
+   if (!res) return PG_OK;          // resident only: nothing to wait for here (ps->busy stays set; the next call settles)
+   rc = drain(nchunks - 1);
+   if (rc != PG_OK) return rc;
+   CU(cudaEventRecord(ps->out_done, ps->s_out));
+   CU(cudaEventSynchronize(ps->out_done));
+   if (overflow) {
+      // the run pool was too small for some chunk: finish_slot grows it to the exact size and repeats the launch over the
+      // (now resident) batch, then everything is copied in one piece
+      rc = finish_launch(ctx);
+      if (rc != PG_OK) return rc;
+      res->n_runs = ctx->last_runs;
+      if (res->n_runs > res->runs_cap || (res->n_runs && !res->runs))
+         return fail(ctx, PG_ERR_RUNS_CAP, "run buffer too small (results->n_runs holds the required size; repeat the call)");
+      CU(cudaMemcpyAsync(res->out, r.out.p, sizeof(PgReadOut) * (size_t)n, cudaMemcpyDeviceToHost, ctx->stream));
+      if (res->n_runs) CU(cudaMemcpyAsync(res->runs, r.pool.p, sizeof(PgRun) * (size_t)res->n_runs, cudaMemcpyDeviceToHost, ctx->stream));
+      CU(cudaStreamSynchronize(ctx->stream));
+      return PG_OK;
    }
-   ctx->last_runs = (uint32_t)total_runs;
-   ctx->last_window_bases = wb;
-   ctx->last_ups = ups;
-   ctx->stats_valid = true;
-   res->n_runs = (uint32_t)total_runs;
+   rc = finish_launch(ctx);        // totals of the call (the event is long reached)
+   if (rc != PG_OK) return rc;
+   res->n_runs = ctx->last_runs;
    if (cap_exceeded) return fail(ctx, PG_ERR_RUNS_CAP, "run buffer too small (results->n_runs holds the required size; repeat the call)");
    return PG_OK;
 }
@@ -1025,7 +1077,6 @@ static int run_all(pg_ctx *ctx, const pg_reads *in, pg_results *res, int mode)
 {
    if (ctx && in && in->n >= 2 * ctx->pipe_chunk && in->seq_blob && in->seq_off) {
       CU(cudaSetDevice(ctx->device));
-      ctx->launched = false;      // the chunks went through the pipeline's own slots: nothing stays resident
       return run_pipelined(ctx, ctx->pipe, in, res, mode);
    }
    int rc = pg_upload(ctx, in);
@@ -1039,6 +1090,18 @@ int pg_close_end(pg_ctx *ctx, const pg_reads *in, pg_results *res) { return run_
 int pg_far_end(pg_ctx *ctx, const pg_reads *in, pg_results *res) { return run_all(ctx, in, res, 2); }
 int pg_search(pg_ctx *ctx, const pg_reads *in, pg_results *res) { return run_all(ctx, in, res, 3); }
 
+int pg_search_resident(pg_ctx *ctx, const pg_reads *in, int32_t mode)
+{
+   if (!ctx || !in || in->n < 0 || mode < 1 || mode > 3) return fail(ctx, PG_ERR_ARG, "pg_search_resident: bad arguments");
+   if (in->n >= 2 * ctx->pipe_chunk && in->seq_blob && in->seq_off) {
+      CU(cudaSetDevice(ctx->device));
+      return run_pipelined(ctx, ctx->pipe, in, nullptr, mode);
+   }
+   int rc = pg_upload(ctx, in);
+   if (rc != PG_OK) return rc;
+   return pg_launch(ctx, mode);
+}
+
 uint64_t pg_kernel_launches(pg_ctx *ctx) { return ctx ? ctx->launches : 0; }
 uint32_t pg_last_run_count(pg_ctx *ctx) { return ctx ? ctx->last_runs : 0; }
 
@@ -1046,10 +1109,8 @@ int pg_last_stats(pg_ctx *ctx, uint64_t *window_bases, uint64_t *unique_points)
 {
    if (!ctx) return PG_ERR_ARG;
    CU(cudaSetDevice(ctx->device));
-   if (ctx->launched || !ctx->stats_valid) {      // after a pipelined call nothing is resident, but its totals are kept
-      int rc = finish_launch(ctx);
-      if (rc != PG_OK) return rc;
-   }
+   int rc = finish_launch(ctx);
+   if (rc != PG_OK) return rc;
    if (window_bases) *window_bases = ctx->last_window_bases;
    if (unique_points) *unique_points = ctx->last_ups;
    return PG_OK;
@@ -1059,13 +1120,26 @@ int pg_device_results(pg_ctx *ctx, void **out_dev, void **runs_dev, uint32_t *n_
 {
    if (!ctx) return PG_ERR_ARG;
    CU(cudaSetDevice(ctx->device));
-   if (!ctx->launched)
-      return fail(ctx, PG_ERR_STATE, "pg_device_results: nothing is resident (no launch, or the last call was chunked through the pipeline)");
    int rc = finish_launch(ctx);
    if (rc != PG_OK) return rc;
-   if (out_dev) *out_dev = ctx->out.p;
-   if (runs_dev) *runs_dev = ctx->pool.p;
+   if (out_dev) *out_dev = ctx->rs[ctx->cur].out.p;
+   if (runs_dev) *runs_dev = ctx->rs[ctx->cur].pool.p;
    if (n_runs) *n_runs = ctx->last_runs;
+   return PG_OK;
+}
+
+int pg_device_results_previous(pg_ctx *ctx, void **out_dev, void **runs_dev, uint32_t *n_runs, int32_t *n_reads)
+{
+   if (!ctx) return PG_ERR_ARG;
+   CU(cudaSetDevice(ctx->device));
+   const int slot = (ctx->cur + PG_RES_SLOTS - 1) % PG_RES_SLOTS;
+   if (!ctx->rs[slot].launched) return fail(ctx, PG_ERR_STATE, "pg_device_results_previous: only one launch so far");
+   int rc = finish_slot(ctx, slot);
+   if (rc != PG_OK) return rc;
+   if (out_dev) *out_dev = ctx->rs[slot].out.p;
+   if (runs_dev) *runs_dev = ctx->rs[slot].pool.p;
+   if (n_runs) *n_runs = ctx->rs[slot].runs;
+   if (n_reads) *n_reads = ctx->rs[slot].n;
    return PG_OK;
 }
 
@@ -1264,8 +1338,8 @@ int pg_classify_resident(pg_ctx *ctx, const pg_sv_window *win, const uint8_t *rf
    b.matched_d = (const uint8_t *)ctx->md.p;
    b.insert_size = (const int16_t *)ctx->isz.p;
    b.chr_id = ctx->have_chr ? (const int32_t *)ctx->chr.p : nullptr;
-   b.res_out = (const PgReadOut *)ctx->out.p;
-   b.res_pool = (const PgRun *)ctx->pool.p;
+   b.res_out = (const PgReadOut *)ctx->rs[ctx->cur].out.p;
+   b.res_pool = (const PgRun *)ctx->rs[ctx->cur].pool.p;
    if (rflags) {
       if ((rc = ensure(ctx, ctx->sv_flags, (size_t)n)) != PG_OK) return rc;
       CU(cudaMemcpyAsync(ctx->sv_flags.p, rflags, (size_t)n, cudaMemcpyHostToDevice, st));
@@ -1286,7 +1360,7 @@ int pg_classify_resident(pg_ctx *ctx, const pg_sv_window *win, const uint8_t *rf
       // close + far launch: the flips happened on the device; materialise the final sequences next to the originals
       if ((rc = ensure(ctx, ctx->sv_seq, ctx->blob_bytes + 4)) != PG_OK) return rc;
       pg_sv_final_seq_kernel<<<(n + 7) / 8, 256, 0, st>>>(n, (const uint8_t *)ctx->seq_blob.p, (const uint32_t *)ctx->seq_off.p,
-                                                        (const PgReadOut *)ctx->out.p, (uint8_t *)ctx->sv_seq.p);
+                                                        (const PgReadOut *)ctx->rs[ctx->cur].out.p, (uint8_t *)ctx->sv_seq.p);
       CU(cudaGetLastError());
       ctx->sv_aux_launches++;
       b.seq_blob = (const uint8_t *)ctx->sv_seq.p;

@@ -72,3 +72,76 @@ def merge_gathered(parts, owners: np.ndarray):
         runs_all.append(ru)
         base += ru.size
     return out, (np.concatenate(runs_all) if runs_all else np.zeros(0, dtype=R.RUN_DT))
+
+
+class DevArr:
+    """A raw device pointer as a __cuda_array_interface__ object (for torch.as_tensor)."""
+
+    def __init__(self, ptr, nbytes):
+        self.__cuda_array_interface__ = {"shape": (nbytes,), "typestr": "|u1", "data": (ptr, False), "version": 2}
+
+
+class RecordGatherer:
+    """The single collective of the path on the GPUs: every rank's breakpoint records (per-read headers + runs, straight from
+    the library's result slot: pg_device_results / pg_device_results_previous) to rank 0 over NCCL, on its own stream so that
+    it travels while the next launch runs.  Exact sizes (one small all_gather of the two byte counts), no padding, no staging
+    copy; rank 0 keeps one receive buffer per rank and, when asked, copies everything on to pinned host memory."""
+
+    def __init__(self, dev, rank, world):
+        import torch
+        self.dev, self.rank, self.world = dev, rank, world
+        self.stream = torch.cuda.Stream(device=dev)
+        self.bufs = [None] * world
+        self.host = None
+        self.last = None            # rank 0: [(out bytes tensor, runs bytes tensor)] per rank, of the last gather
+
+    def _buf(self, r, nbytes):
+        import torch
+        if self.bufs[r] is None or self.bufs[r].numel() < nbytes:
+            self.bufs[r] = torch.empty(int(nbytes * 1.1) + 4096, dtype=torch.uint8, device=self.dev)
+        return self.bufs[r]
+
+    def gather(self, out_ptr, runs_ptr, n_out_bytes, n_run_bytes, after_event=None, to_host=False):
+        """Queues the gather on the gatherer's stream (after `after_event`, if given) -> total bytes that reach rank 0."""
+        import torch
+        import torch.distributed as dist
+        with torch.cuda.stream(self.stream):
+            if after_event is not None:
+                self.stream.wait_event(after_event)
+            out_d = torch.as_tensor(DevArr(out_ptr, max(1, n_out_bytes)), device=self.dev)[:n_out_bytes]
+            runs_d = torch.as_tensor(DevArr(runs_ptr, max(1, n_run_bytes)), device=self.dev)[:n_run_bytes]
+            sz = torch.tensor([n_out_bytes, n_run_bytes], dtype=torch.int64, device=self.dev)
+            sizes = torch.empty(2 * self.world, dtype=torch.int64, device=self.dev)
+            dist.all_gather_into_tensor(sizes, sz)
+            sizes = sizes.cpu().numpy().reshape(self.world, 2)
+            ops, parts = [], []
+            if self.rank == 0:
+                parts.append((out_d, runs_d))
+                for r in range(1, self.world):
+                    b = self._buf(r, int(sizes[r].sum()))
+                    o, ru = b[:int(sizes[r, 0])], b[int(sizes[r, 0]):int(sizes[r].sum())]
+                    if o.numel():
+                        ops.append(dist.P2POp(dist.irecv, o, r))
+                    if ru.numel():
+                        ops.append(dist.P2POp(dist.irecv, ru, r))
+                    parts.append((o, ru))
+            else:
+                if out_d.numel():
+                    ops.append(dist.P2POp(dist.isend, out_d, 0))
+                if runs_d.numel():
+                    ops.append(dist.P2POp(dist.isend, runs_d, 0))
+            if ops:
+                for req in dist.batch_isend_irecv(ops):
+                    req.wait()
+            if self.rank == 0:
+                self.last = parts
+                if to_host:
+                    tot = int(sizes.sum())
+                    if self.host is None or self.host.numel() < tot:
+                        self.host = torch.empty(int(tot * 1.1) + 4096, dtype=torch.uint8).pin_memory()
+                    p = 0
+                    for o, ru in parts:
+                        for t in (o, ru):
+                            self.host[p:p + t.numel()].copy_(t, non_blocking=True)
+                            p += t.numel()
+            return int(sizes.sum())

@@ -108,8 +108,14 @@ def test_pipelined_large_batch_path_equals_single_launch(ref2m, monkeypatch):
     small = np.empty(10, dtype=R.RUN_DT)
     out2, runs2 = pg2.search(runs=small, **kw)
     H.compare(a, R.per_read(out2, runs2, kw["seq_blob"], kw["seq_off"]), "pipelined after RUNS_CAP retry")
-    # the totals of a chunked call are kept although nothing stays resident; the resident-results query says so
+    # a chunked call leaves batch and results resident exactly like upload + launch: same totals, same records
     assert pg2.last_stats() == stats_single
-    with pytest.raises(api.PgError):
-        pg2.device_results()
+    assert pg2.device_results()[2] == runs2.size
+    out3, runs3 = pg2.download()
+    H.compare(a, R.per_read(out3, runs3, kw["seq_blob"], kw["seq_off"]), "download after a chunked call")
+    # the same through the call that copies nothing back, and the result slots alternate
+    pg2.search_resident(**kw)
+    out4, runs4 = pg2.download()
+    H.compare(a, R.per_read(out4, runs4, kw["seq_blob"], kw["seq_off"]), "search_resident + download")
+    assert pg2.device_results_previous()[2] == runs2.size
     pg2.close()
