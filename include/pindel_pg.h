@@ -364,6 +364,17 @@ typedef struct pg_sr_ref {
 } pg_sr_ref;
 int pg_bam_sr_candidates(pg_ctx *ctx, const pg_sr_query *q, pg_sr_cand *cands, uint64_t cand_cap, uint64_t *n_cands, char *seqs, uint64_t seq_cap,
                          uint32_t *stride, pg_sr_ref *refs, uint64_t ref_cap, uint64_t *n_refs, uint64_t *n_scanned);
+/* The same candidates, searched where they lie: the candidate rows become the resident batch of the search kernel on the
+ * device (sequences at their stride, anchors from the rows, InsertSize = q->insert_size, chromosome chr_id of
+ * pg_set_reference) and GetCloseEnd runs on them at once -- what ReadBuffer::addRead + flush (src/read_buffer.cpp:36-105)
+ * do with the reads build_record_SR hands over, without the sequences travelling to the host and back.  Returns what
+ * pg_bam_sr_candidates returns plus results->out[n_cands] / runs as pg_close_end does for the same reads in the same order
+ * (UP_Close before CleanUniquePoints, PG_READ_NFLIPS).  The filter and the search run once per inflated stream, query and
+ * chr_id: the size-asking call (NULL buffers, PG_ERR_RUNS_CAP with all sizes incl. results->n_runs) and the call that
+ * fetches the rows share them, and a pg_bam_sr_candidates call with the same query costs only its copies.  The batch stays
+ * resident (pg_classify_resident, pg_device_results). */
+int pg_bam_sr_close_end(pg_ctx *ctx, const pg_sr_query *q, int32_t chr_id, pg_sr_cand *cands, uint64_t cand_cap, uint64_t *n_cands, char *seqs,
+                        uint64_t seq_cap, uint32_t *stride, pg_sr_ref *refs, uint64_t ref_cap, uint64_t *n_refs, uint64_t *n_scanned, pg_results *res);
 
 /* ------------------------------------------------------------------------------------------------------------------
  * Discordant-read-pair clustering: the two quadratic loops of BDData::UpdateBD

@@ -62,6 +62,7 @@ namespace {
 pg_ctx *g_ctx = NULL;
 std::mutex g_mutex;
 unsigned long g_close_calls = 0, g_far_reads = 0, g_sv_reads = 0, g_sv_records = 0, g_sv_resident = 0, g_rp_rows = 0;
+bool g_flushPresearched = false;               /* the reads in the ReadBuffer already went through GetCloseEnd on the device */
 const SPLIT_READ *g_farResidentBase = NULL;   /* Reads_SR of the last SearchFarEnds call, still resident on the device */
 size_t g_farResidentN = 0;
 
@@ -263,7 +264,7 @@ void GetCloseEnd(const std::string &CurrentChrSeq, SPLIT_READ &read)
  * order the reference produces with one thread). */
 void ReadBuffer::flush()
 {
-   {
+   if (!g_flushPresearched) {          /* reads from the device's split-read filter arrive with their close ends (pg_bam_sr_close_end) */
       std::lock_guard<std::mutex> lock(g_mutex);
       ensureContext();
       std::vector<int> idx;                  /* reads that take part (MapperSplit == false, read_buffer.cpp:46) */
@@ -974,11 +975,14 @@ bool ReadInBamReads_RP_Discovery(const char *bam_path, const std::string &FragNa
  * the pairing of mates on their names (fetch_func_SR), the three predicates and build_record_SR / build_record_RefRead run as
  * pg_bam_sr_candidates on the resident stream; the host adds what only it needs (Name, read_group, Tag, FragName) from the
  * records the rows point at, keeps the reader's counters, and hands every read to the caller's ReadBuffer exactly as
- * build_record_SR does.  Opt-in (PG_BRIDGE_SR_FILTER=1) until its first run on the hardware; otherwise, and with
- * PG_BRIDGE_ZLIB=1, the reference's own function runs (found with dlsym(RTLD_NEXT)). */
+ * build_record_SR does.  By default the candidates are also searched where the filter left them (pg_bam_sr_close_end:
+ * GetCloseEnd on the device without the sequences travelling to the host and back), so the reads reach the ReadBuffer with
+ * their close ends and its flush only post-processes them; PG_BRIDGE_SR_UNCHAINED=1 keeps the two steps apart (filter, then
+ * the buffer's batched search).  With PG_BRIDGE_HOST_SR=1 or PG_BRIDGE_ZLIB=1 the reference's own function runs (found with
+ * dlsym(RTLD_NEXT)). */
 extern unsigned int g_NumReadInWindow, g_InWinPlus, g_InWinMinus;
 void showReadStats(const std::vector<SPLIT_READ> &Reads, const std::vector<SPLIT_READ> &OneEndMappedReads);
-static unsigned long g_sr_candidates = 0;
+static unsigned long g_sr_candidates = 0, g_sr_searched = 0;
 typedef bool (*SrReaderFn)(const char *, const std::string &, const std::string *, std::vector<SPLIT_READ> &, std::vector<SPLIT_READ> &,
                            std::vector<REF_READ> &, int, std::string, const SearchWindow &, ReadBuffer &, bool);
 static void auxString(const uint8_t *rec, uint32_t rec_len, const char *tag, std::string &out)      /* bam_aux_get + bam_aux2Z */
@@ -1013,8 +1017,8 @@ bool ReadInBamReads_SR(const char *bam_path, const std::string &FragName, const 
                        std::vector<SPLIT_READ> &OneEndMappedReads, std::vector<REF_READ> &RefSupportingReads, int InsertSize, std::string Tag,
                        const SearchWindow &window, ReadBuffer &readBuffer, bool verbose)
 {
-   static const bool enabled = getenv("PG_BRIDGE_SR_FILTER") != NULL;
-   if (minihts_index_hook == NULL || !enabled) {
+   static const bool host_reader = getenv("PG_BRIDGE_HOST_SR") != NULL;
+   if (minihts_index_hook == NULL || host_reader) {
       static SrReaderFn original = (SrReaderFn)dlsym(RTLD_NEXT, "_Z17ReadInBamReads_SRPKcRKNSt7__cxx1112basic_stringIcSt11char_traitsIcESaIcEEEPS7_RSt6vectorI10SPLIT_READSaISB_EESE_RSA_I8REF_READSaISF_EEiS6_RK12SearchWindowR10ReadBufferb");
       if (!original) { std::fprintf(stderr, "pindel_gpu_demo: the reference's ReadInBamReads_SR was not found\n"); std::exit(EXIT_FAILURE); }
       return original(bam_path, FragName, CurrentChrSeq, LeftReads, OneEndMappedReads, RefSupportingReads, InsertSize, Tag, window, readBuffer, verbose);
@@ -1027,9 +1031,13 @@ bool ReadInBamReads_SR(const char *bam_path, const std::string &FragName, const 
    std::vector<pg_sr_cand> cands;
    std::vector<pg_sr_ref> refs;
    std::vector<char> seqs;
+   std::vector<pg_read_out> sr_out;        /* GetCloseEnd of the candidates, searched on the device where the filter left them */
+   std::vector<pg_run> sr_runs;
+   bool searched = false;
    uint32_t stride = 0;
    {
       std::lock_guard<std::mutex> lock(g_mutex);
+      ensureContext();
       pg_sr_query q;
       memset(&q, 0, sizeof q);
       q.tid = tid; q.beg = (int32_t)window.getStart(); q.end = (int32_t)window.getEnd(); q.insert_size = InsertSize;
@@ -1038,19 +1046,36 @@ bool ReadInBamReads_SR(const char *bam_path, const std::string &FragName, const 
       q.nm_limit = userSettings->NM;
       q.max_mismatch_rate = userSettings->MaximumAllowedMismatchRate;
       uint64_t n = 0, m = 0, scanned = 0;
-      int rc = pg_bam_sr_candidates(g_ctx, &q, NULL, 0, &n, NULL, 0, &stride, NULL, 0, &m, &scanned);
-      if (rc == PG_ERR_RUNS_CAP) {
-         cands.resize(n ? n : 1); refs.resize(m ? m : 1); seqs.resize(n * stride + 1);
-         rc = pg_bam_sr_candidates(g_ctx, &q, &cands[0], n, &n, &seqs[0], n * stride, &stride, &refs[0], m, &m, &scanned);
+      int rc = PG_ERR_UNSUPPORTED;
+      if (getenv("PG_BRIDGE_SR_UNCHAINED") == NULL) {
+         /* filter + GetCloseEnd in one call: the size-asking call runs the kernels, the second one only copies */
+         pg_results res;
+         memset(&res, 0, sizeof res);
+         rc = pg_bam_sr_close_end(g_ctx, &q, g_genome.getChrID(FragName), NULL, 0, &n, NULL, 0, &stride, NULL, 0, &m, &scanned, &res);
+         if (rc == PG_ERR_RUNS_CAP) {
+            cands.resize(n ? n : 1); refs.resize(m ? m : 1); seqs.resize(n * stride + 1);
+            sr_out.resize(n ? n : 1); sr_runs.resize(res.n_runs ? res.n_runs : 1);
+            res.out = &sr_out[0]; res.runs = &sr_runs[0]; res.runs_cap = (uint32_t)sr_runs.size();
+            rc = pg_bam_sr_close_end(g_ctx, &q, g_genome.getChrID(FragName), &cands[0], n, &n, &seqs[0], n * stride, &stride, &refs[0], m, &m, &scanned, &res);
+         }
+         searched = rc == PG_OK;
+      }
+      if (rc == PG_ERR_UNSUPPORTED) {     /* candidates the search kernel does not take (>= 500 bases): filter alone, the buffer searches */
+         rc = pg_bam_sr_candidates(g_ctx, &q, NULL, 0, &n, NULL, 0, &stride, NULL, 0, &m, &scanned);
+         if (rc == PG_ERR_RUNS_CAP) {
+            cands.resize(n ? n : 1); refs.resize(m ? m : 1); seqs.resize(n * stride + 1);
+            rc = pg_bam_sr_candidates(g_ctx, &q, &cands[0], n, &n, &seqs[0], n * stride, &stride, &refs[0], m, &m, &scanned);
+         }
       }
       if (rc == PG_ERR_DATA) {            /* the reference prints its explanation and leaves (src/reader.cpp:866-874) */
          *logStream << "Error: the insert size is only " << InsertSize << " while a read is at least as long" << std::endl;
          exit(EXIT_FAILURE);
       }
-      if (rc != PG_OK) die("pg_bam_sr_candidates");
+      if (rc != PG_OK) die("pg_bam_sr_close_end / pg_bam_sr_candidates");
       cands.resize(n); refs.resize(m);
       g_NumReadScanned += (unsigned int)scanned;
       g_sr_candidates += (unsigned long)n;
+      if (searched) g_sr_searched += (unsigned long)n;
    }
    const uint8_t *stream = g_lastStream->data();
    /* the reference interleaves the two kinds of calls, but they fill separate containers: candidates go to the buffer in order ... */
@@ -1074,8 +1099,19 @@ bool ReadInBamReads_SR(const char *bam_path, const std::string &FragName, const 
       t.FragName = header->target_name[ra.tid];
       g_NumReadInWindow++;
       if (t.MatchedD == Plus) g_InWinPlus++; else g_InWinMinus++;
+      if (searched) {                     /* what GetCloseEnd leaves in the read (closeEndBatch above) */
+         if (t.InsertSize > g_maxInsertSize) g_maxInsertSize = t.InsertSize;
+         if (sr_out[k].flags & PG_READ_UNSUPPORTED) die("read not supported by the library");
+         for (unsigned f = 0; f < PG_READ_NFLIPS(sr_out[k].flags); f++) t.setUnmatchedSeq(ReverseComplement(t.getUnmatchedSeq()));
+         t.UP_Close.clear();
+         appendRuns(t.UP_Close, &sr_runs[sr_out[k].run_off], sr_out[k].n_close_runs);
+         if (!t.UP_Close.empty()) t.Used = false;
+         g_close_calls++;
+      }
+      g_flushPresearched = searched;      /* the buffer may flush inside addRead */
       readBuffer.addRead(t);
    }
+   g_flushPresearched = searched;
    /* ... and the reference-supporting reads to their vector */
    for (size_t k = 0; k < refs.size(); k++) {
       REF_READ r;
@@ -1087,6 +1123,7 @@ bool ReadInBamReads_SR(const char *bam_path, const std::string &FragName, const 
       RefSupportingReads.push_back(r);
    }
    readBuffer.flush();
+   g_flushPresearched = false;
    if (verbose) showReadStats(LeftReads, OneEndMappedReads);
    bam_hdr_destroy(header);
    hts_idx_destroy(idx);
@@ -1097,11 +1134,11 @@ bool ReadInBamReads_SR(const char *bam_path, const std::string &FragName, const 
 static void reportAtExit()
 {
    std::fprintf(stderr, "pindel_gpu_demo: %lu GetCloseEnd calls and %lu far-end reads served by libpindel_pg (%llu kernel launches); "
-                "%lu reads classified by the SV drivers on the device, %lu records (%llu launches), %lu of the reads without a second upload; %lu read pairs clustered on the device (%llu launches); %lu BAM bytes inflated and %lu records indexed on the device, %lu discordant pairs found there; %lu boxes ordered on the device (%llu launches), %lu by the reference; %lu split-read candidates from the device filter\n",
+                "%lu reads classified by the SV drivers on the device, %lu records (%llu launches), %lu of the reads without a second upload; %lu read pairs clustered on the device (%llu launches); %lu BAM bytes inflated and %lu records indexed on the device, %lu discordant pairs found there; %lu boxes ordered on the device (%llu launches), %lu by the reference; %lu split-read candidates from the device filter, %lu of them searched where the filter left them\n",
                 g_close_calls, g_far_reads, g_ctx ? (unsigned long long)pg_kernel_launches(g_ctx) : 0ull, g_sv_reads, g_sv_records,
                 g_ctx ? (unsigned long long)pg_classify_launches(g_ctx) : 0ull, g_sv_resident, g_rp_rows,
                 g_ctx ? (unsigned long long)pg_rp_launches(g_ctx) : 0ull, g_bgzf_bytes, g_bam_records, g_rpd_rows, g_boxes_sorted,
-                g_ctx ? (unsigned long long)pg_box_sort_launches(g_ctx) : 0ull, g_boxes_host, g_sr_candidates);
+                g_ctx ? (unsigned long long)pg_box_sort_launches(g_ctx) : 0ull, g_boxes_host, g_sr_candidates, g_sr_searched);
 }
 
 int main(int argc, char *argv[])

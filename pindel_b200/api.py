@@ -104,6 +104,9 @@ def load_library() -> C.CDLL:
                                             C.c_uint64, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]
         lib.pg_bam_sr_candidates.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.POINTER(C.c_uint64), C.c_void_p, C.c_uint64,
                                              C.POINTER(C.c_uint32), C.c_void_p, C.c_uint64, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]
+        lib.pg_bam_sr_close_end.argtypes = [C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_uint64, C.POINTER(C.c_uint64), C.c_void_p, C.c_uint64,
+                                            C.POINTER(C.c_uint32), C.c_void_p, C.c_uint64, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64), C.c_void_p]
+        lib.pg_bam_sr_close_end.restype = C.c_int
         lib.pg_bam_launches.restype = C.c_uint64
         lib.pg_bam_launches.argtypes = [C.c_void_p]
         lib.pg_bam_last_ms.restype = C.c_double
@@ -454,6 +457,31 @@ class PatternGrowth:
             self._check(self.lib.pg_bam_sr_candidates(self.ctx, q.ctypes.data, vp(cands), C.c_uint64(cands.size), C.byref(n), vp(seqs), C.c_uint64(seqs.size),
                                                       C.byref(stride), vp(refs), C.c_uint64(refs.size), C.byref(m), C.byref(ns)), "pg_bam_sr_candidates")
         return cands, seqs, refs, int(ns.value)
+
+    def bam_sr_close_end(self, tid, beg, end, insert_size, chr_len, chr_id=0, min_anchor_quality=0, nm_limit=2, max_mismatch_rate=0.02):
+        """bam_sr_candidates with the candidates searched where they lie (GetCloseEnd on the device, no sequence upload).
+        -> (cands, seqs [n, stride], refs, records delivered, out (runs.OUT_DT), runs (runs.RUN_DT))"""
+        from . import bam
+        q = np.array([(tid, beg, end, insert_size, min_anchor_quality, chr_len, nm_limit, 0, max_mismatch_rate)], dtype=bam.SR_QUERY_DT)
+        n, m, ns, stride = C.c_uint64(0), C.c_uint64(0), C.c_uint64(0), C.c_uint32(0)
+        res = _Results(None, None, 0, 0)
+        rc = self.lib.pg_bam_sr_close_end(self.ctx, q.ctypes.data, chr_id, None, C.c_uint64(0), C.byref(n), None, C.c_uint64(0), C.byref(stride), None,
+                                          C.c_uint64(0), C.byref(m), C.byref(ns), C.byref(res))
+        if rc not in (0, PG_ERR_RUNS_CAP):
+            self._check(rc, "pg_bam_sr_close_end")
+        cands = np.zeros(int(n.value), dtype=bam.SR_CAND_DT)
+        seqs = np.zeros((int(n.value), max(int(stride.value), 1)), dtype=np.uint8)
+        refs = np.zeros(int(m.value), dtype=bam.SR_REF_DT)
+        out = np.zeros(int(n.value), dtype=R.OUT_DT)
+        runs = np.zeros(max(1, int(res.n_runs)), dtype=R.RUN_DT)
+        if rc == PG_ERR_RUNS_CAP:
+            vp = lambda a: a.ctypes.data_as(C.c_void_p) if a.size else None
+            res = _Results(out.ctypes.data, runs.ctypes.data, runs.size, 0)
+            self._check(self.lib.pg_bam_sr_close_end(self.ctx, q.ctypes.data, chr_id, vp(cands), C.c_uint64(cands.size), C.byref(n), vp(seqs),
+                                                     C.c_uint64(seqs.size), C.byref(stride), vp(refs), C.c_uint64(refs.size), C.byref(m), C.byref(ns),
+                                                     C.byref(res)), "pg_bam_sr_close_end")
+        self._n = int(n.value)
+        return cands, seqs, refs, int(ns.value), out, runs[:res.n_runs]
 
     def bam_last_segments(self):
         a, b = C.c_uint32(0), C.c_uint32(0)

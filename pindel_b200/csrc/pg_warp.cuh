@@ -311,13 +311,13 @@ PG_DEV void pg_filter_thresholds(PgWarpCtx<LW, TL> &cx, int T)
 }
 
 // Survivors of the positions [r0, r1) (relative to the tile origin) into ws->fsp / ws->fsm, one word per tile word.
-// Returns (uniform) whether the range holds any seed at all.
+// Returns (uniform) bit 0: the range holds a seed at all, bit 1: some seed survived.
 template <int LW, int TL>
-PG_COLD bool pg_filter_tile(PgWarpSmem<LW, TL> *ws, uint32_t r0, uint32_t r1, uint32_t c0lom, uint32_t c0him, int T)
+PG_COLD uint32_t pg_filter_tile(PgWarpSmem<LW, TL> *ws, uint32_t r0, uint32_t r1, uint32_t c0lom, uint32_t c0him, int T)
 {
    const int lane = pg_lane();
    const uint32_t wlast = (r1 - 1u) >> 5;
-   bool any = false;
+   bool any = false, surv = false;
    for (uint32_t wb = r0 >> 5; wb <= wlast; wb += 32u) {
       const uint32_t wi = wb + (uint32_t)lane;
       if (wi <= wlast) {
@@ -355,6 +355,7 @@ PG_COLD bool pg_filter_tile(PgWarpSmem<LW, TL> *ws, uint32_t r0, uint32_t r1, ui
             }
          }
          ws->fsp[wi] = sp; ws->fsm[wi] = sm;
+         surv = surv || (sp | sm) != 0u;
 #ifdef PG_EMULATE
          pg_emul_filter_stats[0] += (unsigned long long)pg_popc(plus | minus);
          pg_emul_filter_stats[1] += (unsigned long long)pg_popc(sp | sm);
@@ -364,9 +365,9 @@ PG_COLD bool pg_filter_tile(PgWarpSmem<LW, TL> *ws, uint32_t r0, uint32_t r1, ui
 #ifdef PG_EMULATE
    if (lane == 0) pg_emul_filter_stats[2]++;
 #endif
-   any = pg_any(any);
+   const uint32_t r = (pg_any(any) ? 1u : 0u) | (pg_any(surv) ? 2u : 0u);
    pg_syncwarp();
-   return any;
+   return r;
 }
 
 // Scan window [s, e) of one chromosome (tile by tile) and fold its seeds into cx.lvl.
@@ -406,6 +407,7 @@ PG_DEV void pg_scan_window(PgWarpCtx<LW, TL> &cx, const PgSearch &se, int chr_id
    const bool single_fwd = se.d > 0;
    // windows of several tiles are cut at multiples of the tile size, so that all tiles but the first are whole words
    const bool aligned_tiles = e - s > PG_TILE_POS;
+   bool thr_valid = false;
    for (uint32_t ts = s, te; ts < e; ts = te) {
       te = aligned_tiles ? (ts & ~(uint32_t)(PG_TILE_POS - 1)) + PG_TILE_POS : e;
       if (te > e) te = e;
@@ -413,18 +415,22 @@ PG_DEV void pg_scan_window(PgWarpCtx<LW, TL> &cx, const PgSearch &se, int chr_id
       const int64_t w1 = (int64_t)((te - 1) >> 5) + 2;          // exclusive
       const int nw = (int)(((w1 - w0) + 3) & ~(int64_t)3);
       pg_tile_load<LW, TL>(ws, chrom, w0, nw, phase);
+      const uint32_t origin = (uint32_t)(w0 << 5);              // absolute position of tile word 0, bit 0 (w0 >= -4)
+      bool filt = false;
+      if (TL <= 16 && filter) {
+         // the thresholds only move when a survivor was merged into the state
+         if (!thr_valid) { pg_filter_thresholds<LW, TL>(cx, se.T); thr_valid = true; }
+         const uint32_t fr = pg_filter_tile<LW, TL>(ws, ts - origin, te - origin, c0lom, c0him, se.T);
+         if (fr & 1u) cx.any_seed = 1;
+         if (!(fr & 2u)) continue;                               // nothing in this tile can change the state: next tile
+         filt = true;
+         thr_valid = false;
+      }
       // does the tile hold any reference N?
       uint32_t nacc = 0;
 #pragma unroll 1
       for (int i = lane; i < nw; i += 32) nacc |= ws->tile_n[i];
       const bool special = read_special || pg_any(nacc != 0);
-      const uint32_t origin = (uint32_t)(w0 << 5);              // absolute position of tile word 0, bit 0 (w0 >= -4)
-      bool filt = false;
-      if (TL <= 16 && filter) {
-         pg_filter_thresholds<LW, TL>(cx, se.T);
-         if (pg_filter_tile<LW, TL>(ws, ts - origin, te - origin, c0lom, c0him, se.T)) cx.any_seed = 1;
-         filt = true;
-      }
       uint32_t ka_[TL], kb_[TL];     // lane-local top-2 keys of this tile, one pair per level
 #pragma unroll
       for (int t = 0; t < TL; t++) { ka_[t] = 0; kb_[t] = 0; }

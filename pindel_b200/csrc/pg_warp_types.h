@@ -19,7 +19,7 @@ struct uint2 { uint32_t x, y; };
 #define PG_IDX_BITS 20
 #define PG_IDX_MASK 0xFFFFFu
 #ifndef PG_FILTER_MIN_POS
-#define PG_FILTER_MIN_POS 512u   // far rings at least this long go through the threshold filter (pg_filter_tile)
+#define PG_FILTER_MIN_POS 2048u  // far rings at least this long go through the threshold filter (pg_filter_tile): from the fourth window on (-x >= 3); measured: at 512 the filter saves instructions at -x 2 but its code no longer fits the instruction cache beside the rest
 #endif
 #define PG_FAR_BP_START 10  // src/farend_searcher.cpp:89
 #define PG_TABLE 500        // g_maxMismatch size, src/pindel.cpp:801

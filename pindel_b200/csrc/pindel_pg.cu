@@ -402,6 +402,12 @@ struct pg_ctx {
    bool bm_valid = false;       // bm_recs holds the table of the resident stream
    DevBuf bd_cls, bd_off, bd_sums, bd_rows, bd_src, bd_counters;
    DevBuf sr_info, sr_keys, sr_head, sr_slot, sr_next, sr_partner, sr_emit, sr_cands, sr_seqs, sr_refs;   // pg_bam_sr_candidates
+   // the last split-read filter run (sr_filter_device): valid for stream generation sr_cache_gen and query sr_cache_q
+   bool sr_cache_valid = false, sr_batch_ready = false;
+   uint64_t bm_generation = 0, sr_cache_gen = 0;
+   pg_sr_query sr_cache_q;
+   int sr_cache_rc = 0, sr_batch_chr = -1;
+   uint32_t sr_tot = 0, sr_tot_ref = 0, sr_stride = 1, sr_scanned = 0;
    uint32_t bm_last_segments = 0, bm_last_redone = 0;
    float bm_last_ms = 0.f;
    size_t bz_out_len = 0;
@@ -664,6 +670,7 @@ int pg_upload(pg_ctx *ctx, const pg_reads *in)
    const int n = in->n;
    ctx->launched = false;
    ctx->stats_valid = false;
+   ctx->sr_batch_ready = false;
    ctx->n = n;
    ctx->have_anchor = in->matched_d && in->matched_rel_pos && in->insert_size;
    ctx->have_chr = in->chr_id != nullptr;
@@ -936,6 +943,7 @@ static int run_pipelined(pg_ctx *ctx, PipeState *&ps, const pg_reads *in, pg_res
    idle.settle();
    CU(cudaStreamSynchronize(ctx->stream));         // everything queued by the caller on its stream comes first
    // the batch becomes the resident batch
+   ctx->sr_batch_ready = false;
    ctx->launched = false;
    ctx->stats_valid = false;
    ctx->n = n;
@@ -1392,7 +1400,7 @@ int pg_bgzf_inflate(pg_ctx *ctx, const uint8_t *file, size_t file_len, uint8_t *
    const size_t total = blocks.empty() ? 0 : (size_t)(blocks.back().out_off + blocks.back().isize);
    *out_len = total;
    ctx->bz_out_len = 0;
-   ctx->bm_valid = false;
+   ctx->bm_valid = false; ctx->bm_generation++;
    if (out && out_cap < total) return fail(ctx, PG_ERR_RUNS_CAP, "pg_bgzf_inflate: output buffer too small (out_len holds the required size)");
    if (blocks.empty()) return PG_OK;
    CU(cudaSetDevice(ctx->device));
@@ -1517,7 +1525,7 @@ int pg_bam_index(pg_ctx *ctx, pg_bam_rec *recs, uint64_t cap, uint64_t *n_recs, 
    CU(cudaStreamSynchronize(st));
    CU(cudaEventElapsedTime(&ctx->bm_last_ms, ctx->sv_ev0, ctx->sv_ev1));
    ctx->bm_n_recs = total;
-   ctx->bm_valid = true;
+   ctx->bm_valid = true; ctx->bm_generation++;
    return PG_OK;
 }
 
@@ -1534,7 +1542,7 @@ int pg_bam_index_run(pg_ctx *ctx, uint64_t first_record, int32_t n_ref, pg_bam_r
    cudaStream_t st = ctx->stream;
    const uint8_t *d = (const uint8_t *)ctx->bz_out.p;
    const uint64_t first = first_record, seg = PGB_SEGMENT;
-   ctx->bm_valid = false;
+   ctx->bm_valid = false; ctx->bm_generation++;
    int rc;
    if (!ctx->sv_ev0) { CU(cudaEventCreate(&ctx->sv_ev0)); CU(cudaEventCreate(&ctx->sv_ev1)); }
    CU(cudaEventRecord(ctx->sv_ev0, st));
@@ -1592,7 +1600,7 @@ int pg_bam_index_run(pg_ctx *ctx, uint64_t first_record, int32_t n_ref, pg_bam_r
    CU(cudaStreamSynchronize(st));
    CU(cudaEventElapsedTime(&ctx->bm_last_ms, ctx->sv_ev0, ctx->sv_ev1));
    ctx->bm_n_recs = total;
-   ctx->bm_valid = true;
+   ctx->bm_valid = true; ctx->bm_generation++;
    return PG_OK;
 }
 
@@ -1693,17 +1701,20 @@ static_assert(sizeof(pg_sr_query) == sizeof(PgSrQuery) && sizeof(pg_sr_query) ==
 static_assert(sizeof(pg_sr_cand) == sizeof(PgSrCand) && sizeof(pg_sr_cand) == 20, "sr candidate layout");
 static_assert(sizeof(pg_sr_ref) == sizeof(PgSrRef) && sizeof(pg_sr_ref) == 8, "sr reference read layout");
 
-int pg_bam_sr_candidates(pg_ctx *ctx, const pg_sr_query *q, pg_sr_cand *cands, uint64_t cand_cap, uint64_t *n_cands, char *seqs, uint64_t seq_cap,
-                         uint32_t *stride, pg_sr_ref *refs, uint64_t ref_cap, uint64_t *n_refs, uint64_t *n_scanned)
+// The device part of the split-read filter: the four per-record kernels, the two prefix counts and the scatter.  Leaves the
+// candidates (ctx->sr_cands), their sequences at a fixed stride (ctx->sr_seqs, NUL-filled behind every sequence) and the
+// reference-supporting reads (ctx->sr_refs) on the device and remembers the query, so that the usual size-then-rows pair of
+// calls -- and pg_bam_sr_close_end behind pg_bam_sr_candidates -- runs the kernels once per stream and query.
+static int sr_filter_device(pg_ctx *ctx, const pg_sr_query *q)
 {
-   if (!ctx || !q || !n_cands || !n_refs || !stride) return fail(ctx, PG_ERR_ARG, "pg_bam_sr_candidates: null argument");
-   if (!ctx->bm_valid || ctx->bz_out_len == 0) return fail(ctx, PG_ERR_STATE, "pg_bam_sr_candidates: no indexed stream is resident (pg_bgzf_inflate + pg_bam_index)");
-   *n_cands = *n_refs = 0;
-   *stride = 0;
-   if (n_scanned) *n_scanned = 0;
+   if (!ctx->bm_valid || ctx->bz_out_len == 0) return fail(ctx, PG_ERR_STATE, "no indexed stream is resident (pg_bgzf_inflate + pg_bam_index)");
+   if (ctx->sr_cache_valid && ctx->sr_cache_gen == ctx->bm_generation && memcmp(&ctx->sr_cache_q, q, sizeof *q) == 0) return ctx->sr_cache_rc;
+   ctx->sr_cache_valid = false;
+   ctx->sr_tot = ctx->sr_tot_ref = 0; ctx->sr_stride = 1; ctx->sr_scanned = 0;
    const uint64_t n64 = ctx->bm_n_recs;
-   if (n64 == 0) return PG_OK;
-   if (n64 > 0x3FFFFFF0ull) return fail(ctx, PG_ERR_UNSUPPORTED, "pg_bam_sr_candidates: more than 2^30 records");
+   auto remember = [&](int rc) { ctx->sr_cache_valid = true; ctx->sr_cache_gen = ctx->bm_generation; ctx->sr_cache_q = *q; ctx->sr_cache_rc = rc; ctx->sr_batch_ready = false; return rc; };
+   if (n64 == 0) return remember(PG_OK);
+   if (n64 > 0x3FFFFFF0ull) return fail(ctx, PG_ERR_UNSUPPORTED, "split-read filter: more than 2^30 records");
    const uint32_t n = (uint32_t)n64;
    CU(cudaSetDevice(ctx->device));
    cudaStream_t st = ctx->stream;
@@ -1760,18 +1771,14 @@ int pg_bam_sr_candidates(pg_ctx *ctx, const pg_sr_query *q, pg_sr_cand *cands, u
    CU(cudaMemcpyAsync(&tot_sr, sums_sr + n_blocks, sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
    CU(cudaMemcpyAsync(&tot_ref, sums_ref + n_blocks, sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
    CU(cudaStreamSynchronize(st));
-   if (n_scanned) *n_scanned = counters[1];
+   ctx->sr_scanned = counters[1];
    if (counters[3] & PGSR_ERR_MALFORMED)
-      return fail(ctx, PG_ERR_DATA, "pg_bam_sr_candidates: an alignment record of the window is malformed (its fields do not fit its block_size)");
+      return remember(fail(ctx, PG_ERR_DATA, "split-read filter: an alignment record of the window is malformed (its fields do not fit its block_size)"));
    if (counters[3] & PGSR_ERR_INSERT)
-      return fail(ctx, PG_ERR_DATA, "pg_bam_sr_candidates: the insert size is not larger than a candidate read (the reference stops here, src/reader.cpp:866)");
+      return remember(fail(ctx, PG_ERR_DATA, "split-read filter: the insert size is not larger than a candidate read (the reference stops here, src/reader.cpp:866)"));
    const uint32_t str = counters[2] ? counters[2] : 1u;
-   *n_cands = tot_sr;
-   *n_refs = tot_ref;
-   *stride = str;
+   ctx->sr_tot = tot_sr; ctx->sr_tot_ref = tot_ref; ctx->sr_stride = str;
    const uint64_t seq_bytes = (uint64_t)tot_sr * str;
-   if (tot_sr > cand_cap || tot_ref > ref_cap || seq_bytes > seq_cap || (tot_sr && (!cands || !seqs)) || (tot_ref && !refs))
-      return fail(ctx, PG_ERR_RUNS_CAP, "pg_bam_sr_candidates: buffers too small (n_cands / n_refs / stride hold the required sizes)");
    if (tot_sr || tot_ref) {
       if ((rc = ensure(ctx, ctx->sr_cands, sizeof(PgSrCand) * ((size_t)tot_sr + 1))) != PG_OK) return rc;
       if ((rc = ensure(ctx, ctx->sr_seqs, (size_t)seq_bytes + 16)) != PG_OK) return rc;
@@ -1781,17 +1788,113 @@ int pg_bam_sr_candidates(pg_ctx *ctx, const pg_sr_query *q, pg_sr_cand *cands, u
                                                  str, (PgSrRef *)ctx->sr_refs.p);
       CU(cudaGetLastError());
       ctx->bm_launches++;
-      CU(cudaEventRecord(ctx->sv_ev1, st));
-      if (tot_sr) {
-         CU(cudaMemcpyAsync(cands, ctx->sr_cands.p, sizeof(PgSrCand) * (size_t)tot_sr, cudaMemcpyDeviceToHost, st));
-         CU(cudaMemcpyAsync(seqs, ctx->sr_seqs.p, (size_t)seq_bytes, cudaMemcpyDeviceToHost, st));
-      }
-      if (tot_ref) CU(cudaMemcpyAsync(refs, ctx->sr_refs.p, sizeof(PgSrRef) * (size_t)tot_ref, cudaMemcpyDeviceToHost, st));
-   } else {
-      CU(cudaEventRecord(ctx->sv_ev1, st));
    }
+   CU(cudaEventRecord(ctx->sv_ev1, st));
    CU(cudaStreamSynchronize(st));
    CU(cudaEventElapsedTime(&ctx->bm_last_ms, ctx->sv_ev0, ctx->sv_ev1));
+   return remember(PG_OK);
+}
+
+int pg_bam_sr_candidates(pg_ctx *ctx, const pg_sr_query *q, pg_sr_cand *cands, uint64_t cand_cap, uint64_t *n_cands, char *seqs, uint64_t seq_cap,
+                         uint32_t *stride, pg_sr_ref *refs, uint64_t ref_cap, uint64_t *n_refs, uint64_t *n_scanned)
+{
+   if (!ctx || !q || !n_cands || !n_refs || !stride) return fail(ctx, PG_ERR_ARG, "pg_bam_sr_candidates: null argument");
+   *n_cands = *n_refs = 0;
+   *stride = 0;
+   if (n_scanned) *n_scanned = 0;
+   int rc = sr_filter_device(ctx, q);
+   if (n_scanned) *n_scanned = ctx->sr_scanned;
+   if (rc != PG_OK) return rc;
+   const uint32_t tot_sr = ctx->sr_tot, tot_ref = ctx->sr_tot_ref, str = ctx->sr_stride;
+   *n_cands = tot_sr; *n_refs = tot_ref; *stride = str;
+   const uint64_t seq_bytes = (uint64_t)tot_sr * str;
+   if (tot_sr > cand_cap || tot_ref > ref_cap || seq_bytes > seq_cap || (tot_sr && (!cands || !seqs)) || (tot_ref && !refs))
+      return fail(ctx, PG_ERR_RUNS_CAP, "pg_bam_sr_candidates: buffers too small (n_cands / n_refs / stride hold the required sizes)");
+   cudaStream_t st = ctx->stream;
+   if (tot_sr) {
+      CU(cudaMemcpyAsync(cands, ctx->sr_cands.p, sizeof(PgSrCand) * (size_t)tot_sr, cudaMemcpyDeviceToHost, st));
+      CU(cudaMemcpyAsync(seqs, ctx->sr_seqs.p, (size_t)seq_bytes, cudaMemcpyDeviceToHost, st));
+   }
+   if (tot_ref) CU(cudaMemcpyAsync(refs, ctx->sr_refs.p, sizeof(PgSrRef) * (size_t)tot_ref, cudaMemcpyDeviceToHost, st));
+   CU(cudaStreamSynchronize(st));
+   return PG_OK;
+}
+
+// The candidates become the resident batch of the search kernel where they lie: warp-free, one thread per candidate for the
+// anchor arrays; the sequences are used at their stride (the kernel strips the NUL fill as setUnmatchedSeq strips trailing
+// non-alphanumerics), one device-to-device copy into the batch's blob.
+__global__ void pg_sr_batch_kernel(uint32_t n, const PgSrCand *__restrict__ cands, uint32_t stride, int16_t insert_size, int32_t chr_id,
+                                   uint32_t *__restrict__ seq_off, uint8_t *__restrict__ md, uint32_t *__restrict__ pos, int16_t *__restrict__ isz,
+                                   int32_t *__restrict__ chr)
+{
+   const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+   if (i > n) return;
+   seq_off[i] = i * stride;
+   if (i == n) return;
+   const PgSrCand c = cands[i];
+   md[i] = c.matched_d;
+   pos[i] = c.matched_rel_pos;
+   isz[i] = insert_size;
+   chr[i] = chr_id;
+}
+
+int pg_bam_sr_close_end(pg_ctx *ctx, const pg_sr_query *q, int32_t chr_id, pg_sr_cand *cands, uint64_t cand_cap, uint64_t *n_cands, char *seqs,
+                        uint64_t seq_cap, uint32_t *stride, pg_sr_ref *refs, uint64_t ref_cap, uint64_t *n_refs, uint64_t *n_scanned, pg_results *res)
+{
+   if (!ctx || !q || !n_cands || !n_refs || !stride || !res) return fail(ctx, PG_ERR_ARG, "pg_bam_sr_close_end: null argument");
+   if (chr_id < 0 || (size_t)chr_id >= ctx->chroms_h.size()) return fail(ctx, PG_ERR_ARG, "pg_bam_sr_close_end: chr_id out of range (pg_set_reference first)");
+   *n_cands = *n_refs = 0;
+   *stride = 0;
+   res->n_runs = 0;
+   if (n_scanned) *n_scanned = 0;
+   int rc = sr_filter_device(ctx, q);
+   if (n_scanned) *n_scanned = ctx->sr_scanned;
+   if (rc != PG_OK) return rc;
+   const uint32_t n = ctx->sr_tot, tot_ref = ctx->sr_tot_ref, str = ctx->sr_stride;
+   *n_cands = n; *n_refs = tot_ref; *stride = str;
+   const uint64_t seq_bytes = (uint64_t)n * str;
+   if (seq_bytes >= 0xFFFFFFF0ull) return fail(ctx, PG_ERR_UNSUPPORTED, "pg_bam_sr_close_end: more than 4 GiB of candidate sequence in one window");
+   if (str >= PG_TABLE) return fail(ctx, PG_ERR_UNSUPPORTED, "pg_bam_sr_close_end: candidate longer than 499 bases");
+   cudaStream_t st = ctx->stream;
+   if (n && !(ctx->sr_batch_ready && ctx->sr_batch_chr == chr_id)) {
+      ctx->launched = false;
+      ctx->stats_valid = false;
+      ctx->n = (int)n;
+      ctx->have_anchor = true; ctx->have_chr = true; ctx->have_close = false; ctx->have_regions = false;
+      ctx->max_read_len = str;
+      ctx->blob_bytes = (size_t)seq_bytes;
+      if ((rc = ensure(ctx, ctx->seq_blob, (size_t)seq_bytes + 16)) != PG_OK) return rc;
+      if ((rc = ensure(ctx, ctx->seq_off, sizeof(uint32_t) * ((size_t)n + 1))) != PG_OK) return rc;
+      if ((rc = ensure(ctx, ctx->md, (size_t)n)) != PG_OK) return rc;
+      if ((rc = ensure(ctx, ctx->pos, sizeof(uint32_t) * (size_t)n)) != PG_OK) return rc;
+      if ((rc = ensure(ctx, ctx->isz, sizeof(int16_t) * (size_t)n)) != PG_OK) return rc;
+      if ((rc = ensure(ctx, ctx->chr, sizeof(int32_t) * (size_t)n)) != PG_OK) return rc;
+      CU(cudaMemcpyAsync(ctx->seq_blob.p, ctx->sr_seqs.p, (size_t)seq_bytes, cudaMemcpyDeviceToDevice, st));
+      pg_sr_batch_kernel<<<(n + 256u) / 256u, 256, 0, st>>>(n, (const PgSrCand *)ctx->sr_cands.p, str, (int16_t)q->insert_size, chr_id, (uint32_t *)ctx->seq_off.p,
+                                                           (uint8_t *)ctx->md.p, (uint32_t *)ctx->pos.p, (int16_t *)ctx->isz.p, (int32_t *)ctx->chr.p);
+      CU(cudaGetLastError());
+      ctx->bm_launches++;
+      rc = pg_launch(ctx, 1);
+      if (rc != PG_OK) return rc;
+      ctx->sr_batch_ready = true;
+      ctx->sr_batch_chr = chr_id;
+   }
+   if (n) {
+      rc = finish_launch(ctx);
+      if (rc != PG_OK) return rc;
+      res->n_runs = ctx->last_runs;
+   }
+   if (n > cand_cap || tot_ref > ref_cap || seq_bytes > seq_cap || (n && (!cands || !seqs || !res->out)) || (tot_ref && !refs) ||
+       res->n_runs > res->runs_cap || (res->n_runs && !res->runs))
+      return fail(ctx, PG_ERR_RUNS_CAP, "pg_bam_sr_close_end: buffers too small (n_cands / n_refs / stride / results->n_runs hold the required sizes)");
+   if (n) {
+      CU(cudaMemcpyAsync(cands, ctx->sr_cands.p, sizeof(PgSrCand) * (size_t)n, cudaMemcpyDeviceToHost, st));
+      CU(cudaMemcpyAsync(seqs, ctx->sr_seqs.p, (size_t)seq_bytes, cudaMemcpyDeviceToHost, st));
+      CU(cudaMemcpyAsync(res->out, ctx->rs[ctx->cur].out.p, sizeof(PgReadOut) * (size_t)n, cudaMemcpyDeviceToHost, st));
+      if (res->n_runs) CU(cudaMemcpyAsync(res->runs, ctx->rs[ctx->cur].pool.p, sizeof(PgRun) * (size_t)res->n_runs, cudaMemcpyDeviceToHost, st));
+   }
+   if (tot_ref) CU(cudaMemcpyAsync(refs, ctx->sr_refs.p, sizeof(PgSrRef) * (size_t)tot_ref, cudaMemcpyDeviceToHost, st));
+   CU(cudaStreamSynchronize(st));
    return PG_OK;
 }
 

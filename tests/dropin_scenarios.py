@@ -74,9 +74,12 @@ def sim_prefix_bam(demo, tmp_path, env):
     assert (int(m.group(2)) == 0) == bool(env.get("PG_BRIDGE_ZLIB")), p.stderr[-300:]
     # row N2, first half: the discordant pairs came from pg_bam_rp_discovery (7928 in this fixture, as the reference finds)
     assert int(m.group(3)) == (0 if env.get("PG_BRIDGE_ZLIB") else 7928), p.stderr[-300:]
-    # rest of row N3 (opt-in): the split-read candidates came from pg_bam_sr_candidates instead of the reader's per-record loop
-    m = re.search(r"(\d+) split-read candidates from the device filter", p.stderr)
-    assert m and (int(m.group(1)) > 0) == bool(env.get("PG_BRIDGE_SR_FILTER") and not env.get("PG_BRIDGE_ZLIB")), p.stderr[-300:]
+    # rest of row N3: the split-read candidates came from the device filter instead of the reader's per-record loop, and were
+    # searched where the filter left them (no upload of their sequences) unless the scenario keeps the two steps apart
+    m = re.search(r"(\d+) split-read candidates from the device filter, (\d+) of them searched where the filter left them", p.stderr)
+    on = not (env.get("PG_BRIDGE_HOST_SR") or env.get("PG_BRIDGE_ZLIB"))
+    assert m and (int(m.group(1)) > 0) == on, p.stderr[-300:]
+    assert int(m.group(2)) == (0 if (env.get("PG_BRIDGE_SR_UNCHAINED") or not on) else int(m.group(1))), p.stderr[-300:]
     return p
 
 

@@ -313,6 +313,57 @@ int pg_bam_sr_candidates(pg_ctx *ctx, const pg_sr_query *q, pg_sr_cand *cands, u
    for (uint64_t k = 0; k < counts[0]; k++) memcpy(seqs + k * str, tmp.data() + k * counts[2], counts[2]);
    return PG_OK;
 }
+int pg_bam_sr_close_end(pg_ctx *ctx, const pg_sr_query *q, int32_t chr_id, pg_sr_cand *cands, uint64_t cand_cap, uint64_t *n_cands, char *seqs,
+                        uint64_t seq_cap, uint32_t *stride, pg_sr_ref *refs, uint64_t ref_cap, uint64_t *n_refs, uint64_t *n_scanned, pg_results *res)
+{
+   /* the filter, then GetCloseEnd on its rows in their own layout: sequences at the stride, NUL-filled */
+   std::vector<pg_sr_cand> c;
+   std::vector<pg_sr_ref> rf;
+   std::vector<char> sq;
+   uint64_t n = 0, m = 0;
+   uint32_t str = 0;
+   int rc = pg_bam_sr_candidates(ctx, q, NULL, 0, &n, NULL, 0, &str, NULL, 0, &m, n_scanned);
+   if (rc != PG_OK && rc != PG_ERR_RUNS_CAP) return rc;
+   c.resize(n + 1); rf.resize(m + 1); sq.assign(n * str + 1, 0);
+   if (rc == PG_ERR_RUNS_CAP) {
+      rc = pg_bam_sr_candidates(ctx, q, c.data(), n, &n, sq.data(), n * str, &str, rf.data(), m, &m, n_scanned);
+      if (rc != PG_OK) return rc;
+   }
+   *n_cands = n; *n_refs = m; *stride = str;
+   std::vector<uint32_t> off(n + 1), pos(n);
+   std::vector<char> md(n);
+   std::vector<int16_t> isz(n, (int16_t)q->insert_size);
+   std::vector<int32_t> chr(n, chr_id);
+   for (uint64_t k = 0; k <= n; k++) off[k] = (uint32_t)(k * str);
+   for (uint64_t k = 0; k < n; k++) { md[k] = (char)c[k].matched_d; pos[k] = c[k].matched_rel_pos; }
+   std::vector<pg_read_out> out(n + 1);
+   std::vector<pg_run> runs;
+   uint32_t n_runs = 0;
+   if (n) {
+      pg_reads in;
+      memset(&in, 0, sizeof in);
+      in.n = (int32_t)n; in.seq_blob = sq.data(); in.seq_off = off.data(); in.matched_d = md.data(); in.matched_rel_pos = pos.data();
+      in.insert_size = isz.data(); in.chr_id = chr.data();
+      runs.resize(n * 16 + 1024);
+      pg_results r;
+      r.out = out.data(); r.runs = runs.data(); r.runs_cap = (uint32_t)runs.size(); r.n_runs = 0;
+      rc = pg_close_end(ctx, &in, &r);
+      if (rc == PG_ERR_RUNS_CAP) { runs.resize(r.n_runs); r.runs = runs.data(); r.runs_cap = r.n_runs; rc = pg_close_end(ctx, &in, &r); }
+      if (rc != PG_OK) return rc;
+      n_runs = r.n_runs;
+   }
+   res->n_runs = n_runs;
+   if (n > cand_cap || m > ref_cap || n * str > seq_cap || (n && (!cands || !seqs || !res->out)) || (m && !refs) || n_runs > res->runs_cap ||
+       (n_runs && !res->runs))
+      return fail(ctx, PG_ERR_RUNS_CAP, "buffers too small");
+   if (n) {
+      memcpy(cands, c.data(), sizeof(pg_sr_cand) * n); memcpy(seqs, sq.data(), n * str);
+      memcpy(res->out, out.data(), sizeof(pg_read_out) * n);
+      if (n_runs) memcpy(res->runs, runs.data(), sizeof(pg_run) * n_runs);
+   }
+   if (m) memcpy(refs, rf.data(), sizeof(pg_sr_ref) * m);
+   return PG_OK;
+}
 uint64_t pg_classify_launches(pg_ctx *ctx) { return ctx ? ctx->sv_launches : 0; }
 double pg_classify_last_kernel_ms(pg_ctx *) { return 0.0; }
 uint32_t pg_expand_runs(const pg_run *runs, uint32_t n_runs, pg_up *out) { return pgh_expand_runs(runs, n_runs, out); }

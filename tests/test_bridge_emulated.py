@@ -30,10 +30,15 @@ def test_bam_input_scenario_with_zlib_inflate(tmp_path):
     D.sim_prefix_bam(DEMO, tmp_path, dict(os.environ, PG_BRIDGE_ZLIB="1"))
 
 
-def test_bam_input_scenario_with_the_device_split_read_filter(tmp_path):
-    """ReadInBamReads_SR bound to pg_bam_sr_candidates (PG_BRIDGE_SR_FILTER=1): the reader's per-record loop is replaced by the
-    device filter and the host only adds names, read groups and tags -- same files"""
-    D.sim_prefix_bam(DEMO, tmp_path, dict(os.environ, PG_BRIDGE_SR_FILTER="1"))
+def test_bam_input_scenario_with_the_split_read_filter_and_search_apart(tmp_path):
+    """The default (test_bam_input_scenario) binds ReadInBamReads_SR to pg_bam_sr_close_end: filter and GetCloseEnd in one
+    call.  PG_BRIDGE_SR_UNCHAINED=1 keeps them apart (pg_bam_sr_candidates, then the ReadBuffer's batched search) -- same files."""
+    D.sim_prefix_bam(DEMO, tmp_path, dict(os.environ, PG_BRIDGE_SR_UNCHAINED="1"))
+
+
+def test_bam_input_scenario_with_the_reference_reader(tmp_path):
+    """PG_BRIDGE_HOST_SR=1: the reference's own ReadInBamReads_SR (per-record loop on the host) -- same files"""
+    D.sim_prefix_bam(DEMO, tmp_path, dict(os.environ, PG_BRIDGE_HOST_SR="1"))
 
 
 def test_text_input_scenario_with_the_host_array_classification(tmp_path):

@@ -41,10 +41,12 @@ def repetitive_reference(n, seed):
     return ref
 
 
-def run_both(lib, padded, batch, **settings):
+def run_both(lib, padded, batch, filter_min_pos=None, **settings):
     names = dict(seq_error_rate="seq_error_rate", sensitivity="sensitivity", max_mismatch_rate="max_mismatch_rate",
                  additional_mismatch="add_mm", min_close="min_close", min_perfect_match="min_perfect", max_range_index="max_range_index")
     prm = emul.make_params(lib, **{names[k]: v for k, v in settings.items()})
+    if filter_min_pos is not None:
+        prm.view(np.uint32)[4] = filter_min_pos      # PgParams::filter_min_pos: rings from this length on are filtered
     blob, off = batch.blob()
     emul.filter_stats(lib)
     out, pool = emul.search(lib, prm, [padded], blob, off, batch.matched_d, batch.matched_rel_pos, batch.insert_size)
@@ -91,3 +93,13 @@ def test_filter_on_a_short_chromosome(lib):
     batch = synth.make_reads(ref, 40, 100, seed=32, max_del=2000, insert_size=300)
     exp, got = run_both(lib, padded, batch, max_range_index=5, additional_mismatch=2)
     H.compare(exp, got, "filter rings, short chromosome")
+
+
+def test_filter_on_short_rings(lib):
+    """The library filters rings of 2048 positions and more (the fourth window on); with the knob turned down the second and
+    third windows of Pindel's default -x 2 go through it as well -- thresholds from 128 positions, most seeds survive."""
+    ref = repetitive_reference(300_000, 41)
+    padded = synth.pad_reference(ref)
+    batch = synth.make_reads(ref, 80, 100, seed=42, max_del=900, n_rate=0.003)
+    exp, got = run_both(lib, padded, batch, filter_min_pos=64, max_range_index=2)
+    H.compare(exp, got, "filter on the short rings of -x 2")

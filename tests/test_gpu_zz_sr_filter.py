@@ -148,5 +148,41 @@ def test_split_read_filter_on_a_run_of_blocks(pg):
 
 @pytest.mark.skipif(not os.path.exists(DEMO), reason="oracle/_ref/pindel_gpu_demo not built (needs /root/reference at build time)")
 def test_reference_host_bam_input_with_the_device_filter(tmp_path):
-    env = dict(os.environ, PG_BRIDGE_SR_FILTER="1", LD_LIBRARY_PATH=os.path.join(ROOT, "pindel_b200") + ":" + os.environ.get("LD_LIBRARY_PATH", ""))
+    env = dict(os.environ, PG_BRIDGE_SR_UNCHAINED="1", LD_LIBRARY_PATH=os.path.join(ROOT, "pindel_b200") + ":" + os.environ.get("LD_LIBRARY_PATH", ""))
     D.sim_prefix_bam(DEMO, tmp_path, env)
+
+
+def test_candidates_searched_where_the_filter_left_them(pg):
+    """pg_bam_sr_close_end: the filter's rows become the search kernel's batch on the device.  Same rows as pg_bam_sr_candidates,
+    and the close ends equal pg_close_end on the same reads uploaded from the host (and therefore the oracle's)."""
+    from pindel_b200 import runs as R, synth
+    from tests import helpers as H
+    stream = G.paired_stream(30_000, 78)
+    pg.bgzf_inflate(bgzf.compress(stream), to_host=False)
+    recs, _, _ = pg.bam_index()
+    refs_np = [synth.make_reference(ln, 900 + i) for i, (_, ln) in enumerate(G.SYNTH_REFS)]
+    padded = [synth.pad_reference(r) for r in refs_np]
+    pg.set_reference(padded)
+    for tid, beg, end, isz in ((0, 0, 400_000, 500), (1, 50_000, 250_000, 300)):
+        c0, s0, r0, n0 = pg.bam_sr_candidates(tid, beg, end, isz, G.SYNTH_REFS[tid][1])
+        launches = pg.kernel_launches
+        cands, seqs, refs, scanned, out, runs = pg.bam_sr_close_end(tid, beg, end, isz, G.SYNTH_REFS[tid][1], chr_id=tid)
+        assert pg.kernel_launches == launches + 1           # one search launch for the size-asking call and the fetch together
+        assert np.array_equal(cands, c0) and np.array_equal(seqs, s0) and np.array_equal(refs, r0) and scanned == n0
+        assert cands.size > 100
+        # the same reads through the host-array entry point
+        blob = b"".join(bytes(seqs[k, :cands["read_length"][k]]) for k in range(cands.size))
+        off = np.zeros(cands.size + 1, dtype=np.uint32)
+        off[1:] = np.cumsum(cands["read_length"])
+        kw = dict(seq_blob=np.frombuffer(blob, dtype=np.uint8), seq_off=off, matched_d=cands["matched_d"], matched_rel_pos=cands["matched_rel_pos"],
+                  insert_size=np.full(cands.size, isz, np.int16), chr_id=np.full(cands.size, tid, np.int32))
+        out2, runs2 = pg.get_close_end(**kw)
+        a = R.per_read(out, runs, kw["seq_blob"], off)
+        b = R.per_read(out2, runs2, kw["seq_blob"], off)
+        H.compare(b, a, "filter + search on the device vs pg_close_end from host arrays")
+        from oracle import pgoracle, refhook
+        st, _ = pgoracle.search(pgoracle.default_params(), padded, kw["seq_blob"], off, kw["matched_d"], kw["matched_rel_pos"], kw["insert_size"],
+                                chr_id=kw["chr_id"], far=False, threads=8)
+        exp = refhook.parse_stream(st, cands.size)
+        for e, g in zip(exp, a):
+            assert e["flip"] == g["flip"] and e["L"] == g["L"] and np.array_equal(e["close_raw"], g["close_raw"])
