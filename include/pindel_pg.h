@@ -161,6 +161,25 @@ int pg_search_resident(pg_ctx *ctx, const pg_reads *in, int32_t mode);
  * (28.6 M reads of 150 bp) and produces less than 2^32 runs; larger inputs are split by the caller (the reference itself
  * works window by window, src/pindel.cpp:1778-1985).  pg_upload / pg_search return PG_ERR_ARG when seq_off wraps. */
 
+/* Several GPUs behind one handle ("device id(s) ... multi-GPU fan-out is internal"): a group owns one context per device,
+ * the packed reference is replicated, and every batch call deals the reads to the devices in contiguous ranges -- one host
+ * thread per device uploads its range behind its kernel, the per-device run counts become offsets, and every device copies
+ * its records straight to their place in the caller's buffers.  Reads are independent units (each call mutates only its own
+ * SPLIT_READ, src/pindel.cpp:1118-1121), so the results are exactly those of one device, in the caller's order.  This is the
+ * form a single-process host (the reference's main()) uses; one process per GPU with an NCCL gather of the records is the other
+ * (pindel_b200/shard.py, bench.py).  devices == NULL: 0 .. n_devices-1.  Errors as above, text from pg_group_last_error;
+ * pg_group_context(g, k) gives the k-th device's context for the single-device calls (classification, BAM stages). */
+typedef struct pg_group pg_group;
+pg_group *pg_group_create(const pg_settings *s, int32_t n_devices, const int32_t *devices);   /* NULL: see pg_create_error() */
+void pg_group_destroy(pg_group *g);
+const char *pg_group_last_error(pg_group *g);
+int32_t pg_group_size(pg_group *g);
+pg_ctx *pg_group_context(pg_group *g, int32_t k);
+int pg_group_set_reference(pg_group *g, int32_t n_chr, const char *const *seq, const uint32_t *len);
+int pg_group_close_end(pg_group *g, const pg_reads *in, pg_results *res);
+int pg_group_far_end(pg_group *g, const pg_reads *in, pg_results *res);
+int pg_group_search(pg_group *g, const pg_reads *in, pg_results *res);
+
 /* Bookkeeping the benchmarks report. */
 uint64_t pg_kernel_launches(pg_ctx *ctx);      /* search-kernel launches since pg_create */
 uint32_t pg_last_run_count(pg_ctx *ctx);       /* runs produced by the last completed launch (valid after pg_sync/pg_download) */

@@ -45,7 +45,9 @@
 #include <cstdio>
 #include <dlfcn.h>
 #include <algorithm>
+#include <chrono>
 #include <cstdlib>
+#include <cstring>
 #include <map>
 #include <mutex>
 #include <string>
@@ -60,7 +62,21 @@ extern short g_MinClose;
 
 namespace {
 pg_ctx *g_ctx = NULL;
+pg_group *g_group = NULL;      /* PG_BRIDGE_DEVICES > 1 */
 std::mutex g_mutex;
+/* where the drop-in's wall time goes (printed at exit): per binding the host-side marshalling, the library call (copies +
+ * kernels) and the host-side application of the results */
+struct Acc { double s; unsigned long n; };
+Acc t_close_marshal = {0, 0}, t_close_lib = {0, 0}, t_close_apply = {0, 0}, t_far_marshal = {0, 0}, t_far_lib = {0, 0}, t_far_apply = {0, 0},
+    t_sv_lib = {0, 0}, t_sv_total = {0, 0}, t_box_lib = {0, 0}, t_rp_lib = {0, 0}, t_inflate_lib = {0, 0}, t_index_lib = {0, 0}, t_rpd_lib = {0, 0},
+    t_sr_lib = {0, 0}, t_sr_host = {0, 0}, t_setup = {0, 0};
+struct Tick {
+   Acc &a;
+   std::chrono::steady_clock::time_point t0;
+   explicit Tick(Acc &acc) : a(acc), t0(std::chrono::steady_clock::now()) {}
+   ~Tick() { a.s += std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count(); a.n++; }
+};
+const std::chrono::steady_clock::time_point g_t_start = std::chrono::steady_clock::now();
 unsigned long g_close_calls = 0, g_far_reads = 0, g_sv_reads = 0, g_sv_records = 0, g_sv_resident = 0, g_rp_rows = 0;
 bool g_flushPresearched = false;               /* the reads in the ReadBuffer already went through GetCloseEnd on the device */
 const SPLIT_READ *g_farResidentBase = NULL;   /* Reads_SR of the last SearchFarEnds call, still resident on the device */
@@ -75,6 +91,7 @@ void die(const char *what)
 void ensureContext()
 {
    if (g_ctx) return;
+   Tick tk(t_setup);
    pg_settings s;
    pg_default_settings(&s);
    s.seq_error_rate = userSettings->Seq_Error_Rate;
@@ -84,7 +101,21 @@ void ensureContext()
    s.min_close = g_MinClose;
    s.min_perfect_match = userSettings->Min_Perfect_Match_Around_BP;
    s.max_range_index = userSettings->MaxRangeIndex;
-   g_ctx = pg_create(&s);
+   /* PG_BRIDGE_DEVICES=N: the two batched seams fan out over N GPUs inside the library (pg_group); everything else -- and the
+    * classification, which then takes the host arrays -- runs on the group's first device */
+   std::vector<int32_t> devs;        /* "N" = devices 0 .. N-1, or a comma list of ordinals ("0,0,0": three contexts on one GPU) */
+   if (const char *e = getenv("PG_BRIDGE_DEVICES")) {
+      if (strchr(e, ',')) { for (const char *p = e; *p; ) { devs.push_back(atoi(p)); p = strchr(p, ','); if (!p) break; p++; } }
+      else for (int k = 0; k < atoi(e); k++) devs.push_back(k);
+   }
+   const int n_dev = (int)devs.size();
+   if (n_dev > 1) {
+      g_group = pg_group_create(&s, n_dev, &devs[0]);
+      if (!g_group) die("pg_group_create");
+      g_ctx = pg_group_context(g_group, 0);
+   } else {
+      g_ctx = pg_create(&s);
+   }
    if (!g_ctx) die("pg_create");
    std::vector<const char *> seqs;
    std::vector<uint32_t> lens;
@@ -92,7 +123,9 @@ void ensureContext()
       seqs.push_back(g_genome.getChr(i)->getSeq().c_str());
       lens.push_back(g_genome.getChr(i)->getCompSize());
    }
-   if (pg_set_reference(g_ctx, (int)seqs.size(), &seqs[0], &lens[0]) != PG_OK) die("pg_set_reference");
+   if (g_group) {
+      if (pg_group_set_reference(g_group, (int)seqs.size(), &seqs[0], &lens[0]) != PG_OK) { std::fprintf(stderr, "pindel_gpu_demo: %s\n", pg_group_last_error(g_group)); std::exit(EXIT_FAILURE); }
+   } else if (pg_set_reference(g_ctx, (int)seqs.size(), &seqs[0], &lens[0]) != PG_OK) die("pg_set_reference");
    /* the library derives g_maxMismatch itself; it must agree with the host's table */
    std::vector<uint32_t> tab(500);
    pg_max_mismatch_table(g_ctx, &tab[0]);
@@ -119,6 +152,7 @@ static void closeEndBatch(std::vector<SPLIT_READ> &reads, const std::vector<int>
 {
    const int m = (int)idx.size();
    if (m == 0) return;
+   Tick *tk = new Tick(t_close_marshal);
    std::string blob;
    std::vector<uint32_t> off(m + 1, 0), pos(m);
    std::vector<char> md(m);
@@ -139,13 +173,16 @@ static void closeEndBatch(std::vector<SPLIT_READ> &reads, const std::vector<int>
    std::vector<pg_run> runs((size_t)m * 16 + 1024);
    pg_results res;
    res.out = &out[0]; res.runs = &runs[0]; res.runs_cap = (uint32_t)runs.size(); res.n_runs = 0;
-   int rc = pg_close_end(g_ctx, &in, &res);
+   delete tk; tk = new Tick(t_close_lib);
+   int rc = g_group ? pg_group_close_end(g_group, &in, &res) : pg_close_end(g_ctx, &in, &res);
    if (rc == PG_ERR_RUNS_CAP) {
       runs.resize(res.n_runs);
       res.runs = &runs[0]; res.runs_cap = (uint32_t)runs.size();
-      rc = pg_close_end(g_ctx, &in, &res);
+      rc = g_group ? pg_group_close_end(g_group, &in, &res) : pg_close_end(g_ctx, &in, &res);
    }
-   if (rc != PG_OK) die("pg_close_end (batch)");
+   if (rc != PG_OK) { if (g_group) std::fprintf(stderr, "pindel_gpu_demo: %s\n", pg_group_last_error(g_group)); die("pg_close_end (batch)"); }
+   delete tk;
+   Tick tk2(t_close_apply);
    for (int k = 0; k < m; k++) {
       SPLIT_READ &read = reads[idx[k]];
       if (out[k].flags & PG_READ_UNSUPPORTED) die("read not supported by the library");
@@ -289,6 +326,7 @@ void SearchFarEnds(const std::string &chromosomeSeq, std::vector<SPLIT_READ> &re
    std::lock_guard<std::mutex> lock(g_mutex);
    ensureContext();
    const int n = (int)reads.size();
+   Tick *tk = new Tick(t_far_marshal);
    std::string blob;
    std::vector<uint32_t> off(n + 1, 0), region_off(n + 1, 0);
    std::vector<int32_t> chr(n);
@@ -331,13 +369,16 @@ void SearchFarEnds(const std::string &chromosomeSeq, std::vector<SPLIT_READ> &re
    std::vector<pg_run> runs((size_t)n * 16 + 1024);
    pg_results res;
    res.out = &out[0]; res.runs = &runs[0]; res.runs_cap = (uint32_t)runs.size(); res.n_runs = 0;
-   int rc = pg_far_end(g_ctx, &in, &res);
+   delete tk; tk = new Tick(t_far_lib);
+   int rc = g_group ? pg_group_far_end(g_group, &in, &res) : pg_far_end(g_ctx, &in, &res);
    if (rc == PG_ERR_RUNS_CAP) {
       runs.resize(res.n_runs);
       res.runs = &runs[0]; res.runs_cap = (uint32_t)runs.size();
-      rc = pg_download(g_ctx, &res);
+      rc = g_group ? pg_group_far_end(g_group, &in, &res) : pg_download(g_ctx, &res);
    }
-   if (rc != PG_OK) die("pg_far_end");
+   if (rc != PG_OK) { if (g_group) std::fprintf(stderr, "pindel_gpu_demo: %s\n", pg_group_last_error(g_group)); die("pg_far_end"); }
+   delete tk;
+   Tick tk2(t_far_apply);
    for (int i = 0; i < n; i++) {
       if (ci[i].max_len == 0) continue;
       reads[i].UP_Far.clear();
@@ -345,7 +386,7 @@ void SearchFarEnds(const std::string &chromosomeSeq, std::vector<SPLIT_READ> &re
       g_far_reads++;
    }
    /* the batch stays on the device: the first SV driver of this window classifies it there (pg_classify_resident) */
-   g_farResidentBase = (n && !staleFarEnd) ? &reads[0] : NULL;
+   g_farResidentBase = (n && !staleFarEnd && !g_group) ? &reads[0] : NULL;      /* a group's batch is spread over its devices */
    g_farResidentN = (size_t)n;
    *logStream << "Far end searching completed for this window." << std::endl;   /* src/pindel.cpp:1137 */
 }
@@ -389,7 +430,7 @@ void ModifyRP(std::vector<RP_READ> &Reads_RP)
    std::vector<pg_rp> in;
    marshalRP(Reads_RP, in);
    std::vector<pg_rp_cluster> out(in.size());
-   if (pg_rp_modify(g_ctx, (int32_t)in.size(), &in[0], &out[0]) != PG_OK) die("pg_rp_modify");
+   { Tick tk(t_rp_lib); if (pg_rp_modify(g_ctx, (int32_t)in.size(), &in[0], &out[0]) != PG_OK) die("pg_rp_modify"); }
    for (size_t i = 0; i < Reads_RP.size(); i++) {
       RP_READ &r = Reads_RP[i];
       r.PosA = out[i].pos_a; r.PosA1 = out[i].pos_a1; r.PosB = out[i].pos_b; r.PosB1 = out[i].pos_b1;
@@ -412,7 +453,7 @@ void Summarize(std::vector<RP_READ> &Reads_RP)
       st[i].n_identical = r.NumberOfIdentical; st[i].merged_into = (uint32_t)i;
       st[i].visited = r.Visited ? 1 : 0; st[i].report = r.Report ? 1 : 0; st[i].pad = 0;
    }
-   if (pg_rp_summarize(g_ctx, (int32_t)in.size(), &in[0], &st[0]) != PG_OK) die("pg_rp_summarize");
+   { Tick tk(t_rp_lib); if (pg_rp_summarize(g_ctx, (int32_t)in.size(), &in[0], &st[0]) != PG_OK) die("pg_rp_summarize"); }
    for (size_t i = 0; i < Reads_RP.size(); i++) {
       RP_READ &r = Reads_RP[i];
       r.NumberOfIdentical = st[i].n_identical;
@@ -519,6 +560,7 @@ void classifyWindow(ControlState &cs, unsigned NumBoxes, const SearchWindow &win
 {
    std::lock_guard<std::mutex> lock(g_mutex);
    ensureContext();
+   Tick tk_all(t_sv_total);
    std::vector<SPLIT_READ> &reads = cs.Reads_SR;
    const int n = (int)reads.size();
    pg_sv_window w;
@@ -563,7 +605,7 @@ void classifyWindow(ControlState &cs, unsigned NumBoxes, const SearchWindow &win
          used[i] = (uint8_t)(flags[i] & PG_SVR_USED);
       }
       for (int attempt = 0; attempt < 2; attempt++) {
-         rc = pg_classify_resident(g_ctx, &w, &used[0], &closeOff[0], closeRuns.empty() ? NULL : &closeRuns[0], &res);
+         { Tick tk(t_sv_lib); rc = pg_classify_resident(g_ctx, &w, &used[0], &closeOff[0], closeRuns.empty() ? NULL : &closeRuns[0], &res); }
          if (rc != PG_ERR_RUNS_CAP) break;
          g_sv.records.resize(res.n_records);
          res.records = &g_sv.records[0];
@@ -608,7 +650,7 @@ void classifyWindow(ControlState &cs, unsigned NumBoxes, const SearchWindow &win
       in.n_close_runs = n ? &nClose[0] : NULL;
       in.runs = runs.empty() ? NULL : &runs[0];
       for (int attempt = 0; attempt < 2; attempt++) {
-         rc = pg_classify(g_ctx, &in, &w, &res);
+         { Tick tk(t_sv_lib); rc = pg_classify(g_ctx, &in, &w, &res); }
          if (rc != PG_ERR_RUNS_CAP) break;
          g_sv.records.resize(res.n_records);
          res.records = &g_sv.records[0];
@@ -737,7 +779,7 @@ void prepareBoxes(const std::vector<SPLIT_READ> &Reads, std::vector<unsigned> Va
    if (boxes.empty()) return;
    std::vector<uint32_t> order(keys.size());
    std::vector<uint8_t> non(keys.size());
-   if (pg_box_sort(g_ctx, (uint32_t)boxes.size(), &boxOff[0], &keys[0], &order[0], &non[0]) != PG_OK) die("pg_box_sort");
+   { Tick tk(t_box_lib); if (pg_box_sort(g_ctx, (uint32_t)boxes.size(), &boxOff[0], &keys[0], &order[0], &non[0]) != PG_OK) die("pg_box_sort"); }
    for (size_t i = 0; i < boxes.size(); i++) {
       const std::vector<unsigned> &v = Vars[boxes[i]];
       PreparedBox &p = g_prepared[&v];
@@ -878,7 +920,7 @@ static int deviceInflate(const uint8_t *file, size_t len, std::vector<uint8_t> &
    if (total < 0) { std::fprintf(stderr, "pindel_gpu_demo: not a BGZF file\n"); return 1; }
    out.resize((size_t)total);
    size_t got = 0;
-   if (pg_bgzf_inflate(g_ctx, file, len, out.empty() ? NULL : &out[0], out.size(), &got, 1) != PG_OK) die("pg_bgzf_inflate");
+   { Tick tk(t_inflate_lib); if (pg_bgzf_inflate(g_ctx, file, len, out.empty() ? NULL : &out[0], out.size(), &got, 1) != PG_OK) die("pg_bgzf_inflate"); }
    g_bgzf_bytes += (unsigned long)got;
    g_lastStream = &out;          /* the reader's copy of the stream: valid until its sam_close */
    g_lastTable.clear();
@@ -892,6 +934,7 @@ static unsigned long g_bam_records = 0;
 static int deviceIndex(size_t first_record, std::vector<uint8_t> &rows24)
 {
    std::lock_guard<std::mutex> lock(g_mutex);
+   Tick tk(t_index_lib);
    uint64_t n = 0, first = 0;
    int32_t nref = 0;
    int rc = pg_bam_index(g_ctx, NULL, 0, &n, &first, &nref);
@@ -931,6 +974,7 @@ bool ReadInBamReads_RP_Discovery(const char *bam_path, const std::string &FragNa
       q.tid = tid; q.beg = (int32_t)currentWindow.getStart(); q.end = (int32_t)currentWindow.getEnd(); q.insert_size = InsertSize;
       q.min_anchor_quality = userSettings->minimalAnchorQuality;
       uint64_t n = 0, ni = 0, scanned = 0;
+      Tick tk(t_rpd_lib);
       int rc = pg_bam_rp_discovery(g_ctx, &q, NULL, NULL, 0, &n, NULL, NULL, 0, &ni, &scanned);
       std::vector<pg_rp> rows(n ? n : 1), irows(ni ? ni : 1);
       std::vector<uint32_t> src(n ? n : 1), isrc(ni ? ni : 1);
@@ -1047,6 +1091,7 @@ bool ReadInBamReads_SR(const char *bam_path, const std::string &FragName, const 
       q.max_mismatch_rate = userSettings->MaximumAllowedMismatchRate;
       uint64_t n = 0, m = 0, scanned = 0;
       int rc = PG_ERR_UNSUPPORTED;
+      Tick tk(t_sr_lib);
       if (getenv("PG_BRIDGE_SR_UNCHAINED") == NULL) {
          /* filter + GetCloseEnd in one call: the size-asking call runs the kernels, the second one only copies */
          pg_results res;
@@ -1077,6 +1122,7 @@ bool ReadInBamReads_SR(const char *bam_path, const std::string &FragName, const 
       g_sr_candidates += (unsigned long)n;
       if (searched) g_sr_searched += (unsigned long)n;
    }
+   Tick tk_host(t_sr_host);
    const uint8_t *stream = g_lastStream->data();
    /* the reference interleaves the two kinds of calls, but they fill separate containers: candidates go to the buffer in order ... */
    for (size_t k = 0; k < cands.size(); k++) {
@@ -1133,6 +1179,16 @@ bool ReadInBamReads_SR(const char *bam_path, const std::string &FragName, const 
 
 static void reportAtExit()
 {
+   const double wall = std::chrono::duration<double>(std::chrono::steady_clock::now() - g_t_start).count();
+   const double lib = t_close_lib.s + t_far_lib.s + t_sv_lib.s + t_box_lib.s + t_rp_lib.s + t_inflate_lib.s + t_index_lib.s + t_rpd_lib.s + t_sr_lib.s;
+   const double host = t_close_marshal.s + t_close_apply.s + t_far_marshal.s + t_far_apply.s + (t_sv_total.s - t_sv_lib.s) + t_sr_host.s;
+   std::fprintf(stderr, "pindel_gpu_demo timing: wall %.3f s; context + reference upload %.3f; library calls %.3f (close end %.3f in %lu, far end %.3f in %lu, "
+                "classification %.3f in %lu, box ordering %.3f in %lu, pair clustering %.3f in %lu, inflate %.3f in %lu, record index %.3f in %lu, pair discovery %.3f in %lu, "
+                "split-read filter + search %.3f in %lu); bridge marshalling %.3f (close end: in %.3f, out %.3f; far end: in %.3f, out %.3f; classification records and replay %.3f; "
+                "split-read rows to SPLIT_READs %.3f); the reference's own host code (parsing, window loop, reporters) %.3f\n",
+                wall, t_setup.s, lib, t_close_lib.s, t_close_lib.n, t_far_lib.s, t_far_lib.n, t_sv_lib.s, t_sv_lib.n, t_box_lib.s, t_box_lib.n, t_rp_lib.s, t_rp_lib.n,
+                t_inflate_lib.s, t_inflate_lib.n, t_index_lib.s, t_index_lib.n, t_rpd_lib.s, t_rpd_lib.n, t_sr_lib.s, t_sr_lib.n, host, t_close_marshal.s, t_close_apply.s,
+                t_far_marshal.s, t_far_apply.s, t_sv_total.s - t_sv_lib.s, t_sr_host.s, wall - t_setup.s - lib - host);
    std::fprintf(stderr, "pindel_gpu_demo: %lu GetCloseEnd calls and %lu far-end reads served by libpindel_pg (%llu kernel launches); "
                 "%lu reads classified by the SV drivers on the device, %lu records (%llu launches), %lu of the reads without a second upload; %lu read pairs clustered on the device (%llu launches); %lu BAM bytes inflated and %lu records indexed on the device, %lu discordant pairs found there; %lu boxes ordered on the device (%llu launches), %lu by the reference; %lu split-read candidates from the device filter, %lu of them searched where the filter left them\n",
                 g_close_calls, g_far_reads, g_ctx ? (unsigned long long)pg_kernel_launches(g_ctx) : 0ull, g_sv_reads, g_sv_records,

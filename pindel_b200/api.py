@@ -139,6 +139,16 @@ def load_library() -> C.CDLL:
         lib.pg_device_results_previous.restype = C.c_int
         lib.pg_search_resident.argtypes = [C.c_void_p, C.c_void_p, C.c_int32]
         lib.pg_search_resident.restype = C.c_int
+        lib.pg_group_create.restype = C.c_void_p
+        lib.pg_group_create.argtypes = [C.c_void_p, C.c_int32, C.c_void_p]
+        lib.pg_group_destroy.argtypes = [C.c_void_p]
+        lib.pg_group_destroy.restype = None
+        lib.pg_group_last_error.restype = C.c_char_p
+        lib.pg_group_last_error.argtypes = [C.c_void_p]
+        lib.pg_group_set_reference.argtypes = [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p]
+        for f in ("pg_group_close_end", "pg_group_far_end", "pg_group_search"):
+            getattr(lib, f).argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+            getattr(lib, f).restype = C.c_int
         _lib = lib
     return _lib
 
@@ -577,3 +587,67 @@ class PatternGrowth:
     @property
     def last_run_count(self) -> int:
         return int(self.lib.pg_last_run_count(self.ctx))
+
+
+class PatternGrowthGroup:
+    """Several GPUs behind one handle (pg_group): the batch calls of PatternGrowth with the reads dealt to the devices in
+    contiguous ranges inside the library; results come back in the caller's order."""
+
+    def __init__(self, devices, **settings):
+        self.lib = load_library()
+        s = Settings()
+        self.lib.pg_default_settings(C.byref(s))
+        for k, v in settings.items():
+            if not hasattr(s, k):
+                raise TypeError("unknown setting %r" % k)
+            setattr(s, k, v)
+        dev = np.ascontiguousarray(devices, dtype=np.int32)
+        self.grp = self.lib.pg_group_create(C.byref(s), int(dev.size), dev.ctypes.data_as(C.c_void_p))
+        if not self.grp:
+            raise PgError("pg_group_create: " + self.lib.pg_create_error().decode())
+        self._reads = PatternGrowth._reads.__get__(self)
+
+    def close(self):
+        if getattr(self, "grp", None):
+            self.lib.pg_group_destroy(self.grp)
+            self.grp = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, rc, what):
+        if rc != PG_OK:
+            raise PgError("%s failed (%d): %s" % (what, rc, self.lib.pg_group_last_error(self.grp).decode()))
+
+    def set_reference(self, chr_seqs):
+        arrs = [np.frombuffer(c, dtype=np.uint8) if isinstance(c, (bytes, bytearray)) else
+                np.ascontiguousarray(c, dtype=np.uint8) for c in chr_seqs]
+        ptrs = (C.c_void_p * len(arrs))(*[a.ctypes.data for a in arrs])
+        lens = np.array([a.size for a in arrs], dtype=np.uint32)
+        self._check(self.lib.pg_group_set_reference(self.grp, len(arrs), ptrs, lens.ctypes.data_as(C.c_void_p)), "pg_group_set_reference")
+
+    def _call(self, fn, what, out=None, runs=None, **batch):
+        r, keep = self._reads(**batch)
+        n = r.n
+        out = np.zeros(n, dtype=R.OUT_DT) if out is None else out
+        runs = np.empty(max(1024, 8 * n), dtype=R.RUN_DT) if runs is None else runs
+        res = _Results(out.ctypes.data, runs.ctypes.data, runs.size, 0)
+        rc = fn(self.grp, C.byref(r), C.byref(res))
+        if rc == PG_ERR_RUNS_CAP:
+            runs = np.empty(res.n_runs, dtype=R.RUN_DT)
+            res = _Results(out.ctypes.data, runs.ctypes.data, runs.size, 0)
+            rc = fn(self.grp, C.byref(r), C.byref(res))
+        self._check(rc, what)
+        return out, runs[:res.n_runs]
+
+    def get_close_end(self, **batch):
+        return self._call(self.lib.pg_group_close_end, "pg_group_close_end", **batch)
+
+    def search_far_ends(self, **batch):
+        return self._call(self.lib.pg_group_far_end, "pg_group_far_end", **batch)
+
+    def search(self, **batch):
+        return self._call(self.lib.pg_group_search, "pg_group_search", **batch)

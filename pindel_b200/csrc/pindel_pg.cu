@@ -14,6 +14,7 @@
 #include <string.h>
 #include <algorithm>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "pg_warp.cuh"
@@ -1109,6 +1110,135 @@ int pg_search_resident(pg_ctx *ctx, const pg_reads *in, int32_t mode)
    if (rc != PG_OK) return rc;
    return pg_launch(ctx, mode);
 }
+
+// ------------------------------------------------------------------------------------------------
+// Several GPUs behind one handle ("device id(s) ... multi-GPU fan-out is internal").  A group owns one
+// context per device, the reference is replicated, and a batch is dealt to the devices in contiguous ranges of reads: one
+// host thread per device uploads its range chunk by chunk behind its kernel (pg_search_resident), the run counts are
+// exchanged, and every device copies its records straight to their final place in the caller's buffers -- the only
+// "collective" of a single process is that prefix sum.  Reads are independent units, so the result is that of one device.
+// ------------------------------------------------------------------------------------------------
+struct pg_group {
+   std::vector<pg_ctx *> ctx;
+   std::string err;
+};
+
+static int group_run(pg_group *g, const pg_reads *in, pg_results *res, int mode)
+{
+   if (!g || !in || !res || in->n < 0) return PG_ERR_ARG;
+   const int nd = (int)g->ctx.size(), n = in->n;
+   res->n_runs = 0;
+   if (n == 0) return PG_OK;
+   if (!in->seq_blob || !in->seq_off || !res->out) { g->err = "pg_group: null buffers"; return PG_ERR_ARG; }
+   std::vector<int> c0(nd + 1);
+   for (int k = 0; k <= nd; k++) c0[k] = (int)((long long)n * k / nd);
+   std::vector<int> rc(nd, PG_OK);
+   std::vector<uint32_t> nruns(nd, 0);
+   std::vector<std::vector<uint32_t>> off(nd), roff(nd);
+   std::vector<pg_reads> sub(nd);
+   // phase 1: every device searches its range; batch and results stay on the device
+   auto phase1 = [&](int k) {
+      const int a = c0[k], b = c0[k + 1], m = b - a;
+      if (m == 0) return;
+      pg_reads &r = sub[k];
+      r = *in;
+      r.n = m;
+      off[k].resize((size_t)m + 1);
+      for (int i = 0; i <= m; i++) off[k][i] = in->seq_off[a + i] - in->seq_off[a];
+      r.seq_blob = in->seq_blob + in->seq_off[a];
+      r.seq_off = off[k].data();
+      if (in->matched_d) r.matched_d = in->matched_d + a;
+      if (in->matched_rel_pos) r.matched_rel_pos = in->matched_rel_pos + a;
+      if (in->insert_size) r.insert_size = in->insert_size + a;
+      if (in->chr_id) r.chr_id = in->chr_id + a;
+      if (in->close_info) r.close_info = in->close_info + a;
+      if (in->regions && in->region_off) {
+         roff[k].resize((size_t)m + 1);
+         for (int i = 0; i <= m; i++) roff[k][i] = in->region_off[a + i] - in->region_off[a];
+         r.regions = in->regions + in->region_off[a];
+         r.region_off = roff[k].data();
+      }
+      int e = pg_search_resident(g->ctx[k], &r, mode);
+      if (e == PG_OK) e = finish_launch(g->ctx[k]);
+      rc[k] = e;
+      nruns[k] = g->ctx[k]->last_runs;
+   };
+   {
+      std::vector<std::thread> th;
+      for (int k = 1; k < nd; k++) th.emplace_back(phase1, k);
+      phase1(0);
+      for (auto &t : th) t.join();
+   }
+   for (int k = 0; k < nd; k++)
+      if (rc[k] != PG_OK) { g->err = "device " + std::to_string(g->ctx[k]->device) + ": " + g->ctx[k]->err; return rc[k]; }
+   std::vector<uint64_t> base(nd + 1, 0);
+   for (int k = 0; k < nd; k++) base[k + 1] = base[k] + nruns[k];
+   if (base[nd] > 0xFFFFFFFFull) { g->err = "pg_group: more than 2^32 runs in one batch"; return PG_ERR_UNSUPPORTED; }
+   res->n_runs = (uint32_t)base[nd];
+   if (res->n_runs > res->runs_cap || (res->n_runs && !res->runs)) { g->err = "run buffer too small (results->n_runs holds the required size; repeat the call)"; return PG_ERR_RUNS_CAP; }
+   // phase 2: the records go to their final place, run offsets made global
+   auto phase2 = [&](int k) {
+      const int a = c0[k], m = c0[k + 1] - a;
+      if (m == 0) return;
+      pg_results r;
+      r.out = res->out + a; r.runs = res->runs ? res->runs + base[k] : nullptr; r.runs_cap = nruns[k]; r.n_runs = 0;
+      rc[k] = pg_download(g->ctx[k], &r);
+      if (rc[k] == PG_OK && base[k])
+         for (int i = 0; i < m; i++) res->out[a + i].run_off += (uint32_t)base[k];
+   };
+   {
+      std::vector<std::thread> th;
+      for (int k = 1; k < nd; k++) th.emplace_back(phase2, k);
+      phase2(0);
+      for (auto &t : th) t.join();
+   }
+   for (int k = 0; k < nd; k++)
+      if (rc[k] != PG_OK) { g->err = "device " + std::to_string(g->ctx[k]->device) + ": " + g->ctx[k]->err; return rc[k]; }
+   return PG_OK;
+}
+
+pg_group *pg_group_create(const pg_settings *s, int32_t n_devices, const int32_t *devices)
+{
+   g_create_error.clear();
+   if (!s || n_devices < 1 || n_devices > 64) { g_create_error = "pg_group_create: bad arguments"; return nullptr; }
+   pg_group *g = new pg_group();
+   for (int k = 0; k < n_devices; k++) {
+      pg_settings sk = *s;
+      sk.device = devices ? devices[k] : k;
+      pg_ctx *c = pg_create(&sk);
+      if (!c) { for (pg_ctx *x : g->ctx) pg_destroy(x); delete g; return nullptr; }
+      g->ctx.push_back(c);
+   }
+   return g;
+}
+
+void pg_group_destroy(pg_group *g)
+{
+   if (!g) return;
+   for (pg_ctx *c : g->ctx) pg_destroy(c);
+   delete g;
+}
+
+const char *pg_group_last_error(pg_group *g) { return g ? g->err.c_str() : "null group"; }
+int32_t pg_group_size(pg_group *g) { return g ? (int32_t)g->ctx.size() : 0; }
+pg_ctx *pg_group_context(pg_group *g, int32_t k) { return (g && k >= 0 && (size_t)k < g->ctx.size()) ? g->ctx[k] : nullptr; }
+
+int pg_group_set_reference(pg_group *g, int32_t n_chr, const char *const *seq, const uint32_t *len)
+{
+   if (!g) return PG_ERR_ARG;
+   std::vector<int> rc(g->ctx.size(), PG_OK);
+   std::vector<std::thread> th;
+   for (size_t k = 1; k < g->ctx.size(); k++) th.emplace_back([&, k] { rc[k] = pg_set_reference(g->ctx[k], n_chr, seq, len); });
+   rc[0] = pg_set_reference(g->ctx[0], n_chr, seq, len);
+   for (auto &t : th) t.join();
+   for (size_t k = 0; k < g->ctx.size(); k++)
+      if (rc[k] != PG_OK) { g->err = "device " + std::to_string(g->ctx[k]->device) + ": " + g->ctx[k]->err; return rc[k]; }
+   return PG_OK;
+}
+
+int pg_group_close_end(pg_group *g, const pg_reads *in, pg_results *res) { return group_run(g, in, res, 1); }
+int pg_group_far_end(pg_group *g, const pg_reads *in, pg_results *res) { return group_run(g, in, res, 2); }
+int pg_group_search(pg_group *g, const pg_reads *in, pg_results *res) { return group_run(g, in, res, 3); }
 
 uint64_t pg_kernel_launches(pg_ctx *ctx) { return ctx ? ctx->launches : 0; }
 uint32_t pg_last_run_count(pg_ctx *ctx) { return ctx ? ctx->last_runs : 0; }

@@ -145,6 +145,68 @@ int pg_far_end(pg_ctx *ctx, const pg_reads *in, pg_results *res) { return run(ct
 int pg_search(pg_ctx *ctx, const pg_reads *in, pg_results *res) { return run(ctx, in, res, 3); }
 uint64_t pg_kernel_launches(pg_ctx *ctx) { return ctx ? ctx->launches : 0; }
 
+/* pg_group on the emulators: the same dealing of contiguous ranges and the same merge (run offsets made global), serially */
+struct pg_group {
+   std::vector<pg_ctx *> ctx;
+   std::string err;
+};
+pg_group *pg_group_create(const pg_settings *s, int32_t n_devices, const int32_t *)
+{
+   pg_group *g = new pg_group;
+   for (int k = 0; k < n_devices; k++) g->ctx.push_back(pg_create(s));
+   return g;
+}
+void pg_group_destroy(pg_group *g) { if (g) { for (pg_ctx *c : g->ctx) pg_destroy(c); delete g; } }
+const char *pg_group_last_error(pg_group *g) { return g ? g->err.c_str() : "null group"; }
+int32_t pg_group_size(pg_group *g) { return g ? (int32_t)g->ctx.size() : 0; }
+pg_ctx *pg_group_context(pg_group *g, int32_t k) { return g->ctx[k]; }
+int pg_group_set_reference(pg_group *g, int32_t n_chr, const char *const *seq, const uint32_t *len)
+{
+   for (pg_ctx *c : g->ctx) pg_set_reference(c, n_chr, seq, len);
+   return PG_OK;
+}
+static int group_run(pg_group *g, const pg_reads *in, pg_results *res, int mode)
+{
+   const int nd = (int)g->ctx.size(), n = in->n;
+   res->n_runs = 0;
+   std::vector<std::vector<pg_run>> runs(nd);
+   std::vector<uint32_t> nruns(nd, 0);
+   for (int k = 0; k < nd; k++) {
+      const int a = (int)((long long)n * k / nd), b = (int)((long long)n * (k + 1) / nd), m = b - a;
+      if (m == 0) continue;
+      pg_reads r = *in;
+      r.n = m;
+      std::vector<uint32_t> off(m + 1), roff(m + 1);
+      for (int i = 0; i <= m; i++) off[i] = in->seq_off[a + i] - in->seq_off[a];
+      r.seq_blob = in->seq_blob + in->seq_off[a]; r.seq_off = off.data();
+      if (in->matched_d) r.matched_d = in->matched_d + a;
+      if (in->matched_rel_pos) r.matched_rel_pos = in->matched_rel_pos + a;
+      if (in->insert_size) r.insert_size = in->insert_size + a;
+      if (in->chr_id) r.chr_id = in->chr_id + a;
+      if (in->close_info) r.close_info = in->close_info + a;
+      if (in->regions && in->region_off) {
+         for (int i = 0; i <= m; i++) roff[i] = in->region_off[a + i] - in->region_off[a];
+         r.regions = in->regions + in->region_off[a]; r.region_off = roff.data();
+      }
+      runs[k].resize((size_t)m * 16 + 1024);
+      pg_results pr;
+      pr.out = res->out + a; pr.runs = runs[k].data(); pr.runs_cap = (uint32_t)runs[k].size(); pr.n_runs = 0;
+      int rc = run(g->ctx[k], &r, &pr, mode);
+      if (rc == PG_ERR_RUNS_CAP) { runs[k].resize(pr.n_runs); pr.runs = runs[k].data(); pr.runs_cap = pr.n_runs; rc = run(g->ctx[k], &r, &pr, mode); }
+      if (rc != PG_OK) { g->err = g->ctx[k]->err; return rc; }
+      nruns[k] = pr.n_runs;
+      for (int i = 0; i < m; i++) res->out[a + i].run_off += res->n_runs;
+      res->n_runs += pr.n_runs;
+   }
+   if (res->n_runs > res->runs_cap) { g->err = "run buffer too small"; return PG_ERR_RUNS_CAP; }
+   uint32_t p = 0;
+   for (int k = 0; k < nd; k++) { if (nruns[k]) memcpy(res->runs + p, runs[k].data(), sizeof(pg_run) * nruns[k]); p += nruns[k]; }
+   return PG_OK;
+}
+int pg_group_close_end(pg_group *g, const pg_reads *in, pg_results *res) { return group_run(g, in, res, 1); }
+int pg_group_far_end(pg_group *g, const pg_reads *in, pg_results *res) { return group_run(g, in, res, 2); }
+int pg_group_search(pg_group *g, const pg_reads *in, pg_results *res) { return group_run(g, in, res, 3); }
+
 int pg_classify(pg_ctx *ctx, const pg_sv_reads *in, const pg_sv_window *win, pg_sv_results *res)
 {
    res->n_records = 0;

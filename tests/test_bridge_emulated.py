@@ -41,6 +41,12 @@ def test_bam_input_scenario_with_the_reference_reader(tmp_path):
     D.sim_prefix_bam(DEMO, tmp_path, dict(os.environ, PG_BRIDGE_HOST_SR="1"))
 
 
+def test_text_input_scenario_over_a_device_group(tmp_path):
+    """PG_BRIDGE_DEVICES=3: the two batched seams go through pg_group_close_end / pg_group_far_end (reads dealt to three
+    contexts, records merged with global run offsets), the classification takes the host arrays -- same files"""
+    D.colo_slice(DEMO, tmp_path, dict(os.environ, PG_BRIDGE_DEVICES="3", PG_BRIDGE_NO_RESIDENT="1"), unbatched_too=False)
+
+
 def test_text_input_scenario_with_the_host_array_classification(tmp_path):
     """pg_classify (everything uploaded again) instead of pg_classify_resident: the path a host takes when the far-end
     batch is no longer on the device; and the reference's own bubblesortReads / markDuplicates instead of pg_box_sort."""

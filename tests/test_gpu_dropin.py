@@ -36,3 +36,16 @@ def test_interchromosomal_scenario_against_the_reference_binary(tmp_path):
     """-I true on generated inputs, the pure reference binary beside the drop-in: inter-chromosomal pair discovery and
     ModifyRP_InterChr / Summarize_InterChr on the device."""
     D.interchr_live(DEMO, tmp_path, _env())
+
+
+def test_reference_host_over_a_device_group(tmp_path):
+    """PG_BRIDGE_DEVICES: the two batched seams fan out inside the library (pg_group_close_end / pg_group_far_end).  Three
+    contexts on device 0 on a one-GPU box, the real devices when there are more -- same files."""
+    import torch
+    nd = torch.cuda.device_count()
+    D.colo_slice(DEMO, tmp_path, dict(_env(), PG_BRIDGE_DEVICES=str(nd) if nd > 1 else "0,0,0", PG_BRIDGE_NO_RESIDENT="1"), unbatched_too=False)
+
+
+def test_reference_host_bam_input_with_the_reference_reader(tmp_path):
+    """PG_BRIDGE_HOST_SR=1: the reference's own ReadInBamReads_SR instead of the device filter + search -- same files"""
+    D.sim_prefix_bam(DEMO, tmp_path, dict(_env(), PG_BRIDGE_HOST_SR="1"))

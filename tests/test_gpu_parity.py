@@ -119,3 +119,28 @@ def test_pipelined_large_batch_path_equals_single_launch(ref2m, monkeypatch):
     H.compare(a, R.per_read(out4, runs4, kw["seq_blob"], kw["seq_off"]), "search_resident + download")
     assert pg2.device_results_previous()[2] == runs2.size
     pg2.close()
+
+
+def test_device_group_equals_single_device(ref2m, monkeypatch):
+    """pg_group: the reads of a batch dealt to several contexts in contiguous ranges, records written to their final place
+    with global run offsets.  Three contexts on device 0 exercise the splitting and merging on a one-GPU box (with two or
+    more GPUs tests/test_gpu_multi.py runs real devices); chunked uploads inside (PG_PIPE_CHUNK) and a too-small run buffer."""
+    import torch
+    ref, padded = ref2m
+    batch = synth.make_reads(ref, 9001, 100, seed=43)
+    kw = H.batch_kwargs(batch)
+    pg1 = api.PatternGrowth()
+    pg1.set_reference([padded])
+    a = R.per_read(*pg1.search(**kw), kw["seq_blob"], kw["seq_off"])
+    ac = R.per_read(*pg1.get_close_end(**kw), kw["seq_blob"], kw["seq_off"])
+    pg1.close()
+    monkeypatch.setenv("PG_PIPE_CHUNK", "1000")
+    nd = torch.cuda.device_count()
+    for devices in ([0, 0, 0], list(range(nd)) if nd > 1 else [0]):
+        g = api.PatternGrowthGroup(devices)
+        g.set_reference([padded])
+        H.compare(a, R.per_read(*g.search(**kw), kw["seq_blob"], kw["seq_off"]), "group %s search" % devices)
+        H.compare(ac, R.per_read(*g.get_close_end(**kw), kw["seq_blob"], kw["seq_off"]), "group %s close end" % devices)
+        small = np.empty(10, dtype=R.RUN_DT)
+        H.compare(a, R.per_read(*g.search(runs=small, **kw), kw["seq_blob"], kw["seq_off"]), "group %s after RUNS_CAP" % devices)
+        g.close()
