@@ -63,6 +63,17 @@ PG_DEV uint8_t pg_ldg8(const uint8_t *p) { return __ldg(p); }
 
 #include "pg_warp_types.h"
 
+// Per-read state of pg_process_read that lives across searches (uniform over the warp).
+struct PgReadState {
+   unsigned long long window_bases;
+   int32_t chr_id;
+   uint32_t n_regions;
+   uint32_t close_runs, close_ups, close_max_len, close_last;   // the close end: PgResult of the search that found it
+   uint32_t best_runs, best_ups, best_max_len, far_best;        // the best far end so far and the scratch third that holds it
+   uint32_t have_prev, prev_ws, prev_we;                        // the previous far window
+   uint32_t filter_ready;
+};
+
 // One growth step of the filter: read index `sh` compared with the reference base `sh` to the right of a plus seed and
 // `sh` to the left of a minus seed (rsh = 32 - sh is the funnel shift that brings that base under the seed's bit).
 struct alignas(16) PgFStep {
@@ -95,6 +106,7 @@ struct PgWarpSmem {
    uint32_t fuse;                    // read indices 1..31 that have a table entry (not N / other, below L)
    uint32_t fcnt[TL];
    uint32_t fsp[PG_TILE_WORDS], fsm[PG_TILE_WORDS];
+   PgReadState rs;                   // what pg_process_read keeps across the searches of one read
 };
 
 struct PgLevel {      // warp-level top-2 for level == lane
@@ -422,7 +434,9 @@ PG_DEV void pg_scan_window(PgWarpCtx<LW, TL> &cx, const PgSearch &se, int chr_id
          if (!thr_valid) { pg_filter_thresholds<LW, TL>(cx, se.T); thr_valid = true; }
          const uint32_t fr = pg_filter_tile<LW, TL>(ws, ts - origin, te - origin, c0lom, c0him, se.T);
          if (fr & 1u) cx.any_seed = 1;
+#ifndef PG_NO_TILE_SKIP
          if (!(fr & 2u)) continue;                               // nothing in this tile can change the state: next tile
+#endif
          filt = true;
          thr_valid = false;
       }
@@ -817,7 +831,9 @@ PG_COLD int pg_flip_read(PgWarpSmem<LW, TL> *ws, int L)
 }
 
 // The whole per-read program: GetCloseEnd (pindel.cpp:2531-2605) then SearchFarEnd (pindel.cpp:1001-1074), written
-// as one loop over "searches" so that the scan and the replay are instantiated exactly once.
+// as one loop over "searches" so that the scan and the replay are instantiated exactly once.  What lives across searches
+// (the close end's and the best far end's summaries, the previous window, the statistics) sits in the warp's shared memory
+// (ws->rs: every lane writes and reads the same words), not in registers: the scan's hot loop needs all 64 of them.
 template <int LW, int TL>
 PG_DEV void pg_process_read(PgWarpCtx<LW, TL> &cx, const PgBatch &bt, int ri, PgRun *scratch, uint32_t &phase)
 {
@@ -825,7 +841,6 @@ PG_DEV void pg_process_read(PgWarpCtx<LW, TL> &cx, const PgBatch &bt, int ri, Pg
    const PgParams *prm = cx.prm;
    int lane = pg_lane();
    const uint32_t cap = bt.scratch_cap;
-   PgRun *closeBuf = scratch, *farBest = scratch + cap, *farNew = scratch + 2 * cap;
    uint32_t o0 = bt.seq_off[ri], o1 = bt.seq_off[ri + 1];
    int rawlen = (int)(o1 - o0);
    PgReadOut ro;
@@ -841,33 +856,30 @@ PG_DEV void pg_process_read(PgWarpCtx<LW, TL> &cx, const PgBatch &bt, int ri, Pg
       if (lane == 0) bt.out[ri] = ro;
       return;
    }
-   const int chr_id = bt.chr_id ? bt.chr_id[ri] : 0;
-   const uint8_t md = (bt.mode & 1) ? bt.matched_d[ri] : (uint8_t)0;
-   const uint32_t rp = (bt.mode & 1) ? bt.matched_rel_pos[ri] : 0u;
-   const int isz = (bt.mode & 1) ? bt.insert_size[ri] : 0;
-   const int n_regions = (bt.regions && bt.region_off) ? (int)(bt.region_off[ri + 1] - bt.region_off[ri]) : 0;
-   const PgRegion *cluster = n_regions ? bt.regions + bt.region_off[ri] : (const PgRegion *)0;
+   PgReadState &rs = ws->rs;
+   rs.chr_id = bt.chr_id ? bt.chr_id[ri] : 0;
+   rs.n_regions = (bt.regions && bt.region_off) ? (bt.region_off[ri + 1] - bt.region_off[ri]) : 0u;
+   rs.close_runs = 0; rs.close_ups = 0; rs.close_max_len = 0; rs.close_last = 0;
+   rs.best_runs = 0; rs.best_ups = 0; rs.best_max_len = 0;
+   rs.far_best = 1;            // scratch third that holds the best far end (the other of 1 / 2 receives the next one)
+   rs.window_bases = 0;        // reference positions scanned for this read (bench statistics)
+   rs.have_prev = 0; rs.prev_ws = 0; rs.prev_we = 0;
+   rs.filter_ready = 0;        // ws->ftab describes this read
    uint32_t flips = 0;
-   PgResult cres, best;
-   cres.n_runs = 0; cres.n_ups = 0; cres.max_len = 0; cres.last_abs_loc = 0; cres.seeds = 0;
-   best = cres;
    enum { ST_CLOSE = 0, ST_FAR_CLUSTER = 1, ST_FAR_WINDOW = 2, ST_DONE = 3 };
    int st = ST_DONE;
    int range_index = 0;        // GetCloseEnd: RangeIndex 0..1
    bool second_try = false;    // GetCloseEnd: the attempt after setUnmatchedSeq(ReverseComplement())
-   unsigned long long window_bases = 0;   // reference positions scanned for this read (bench statistics)
    int k = 1;                  // SearchFarEnd: rangeIndex 1..MaxRangeIndex+1
    uint32_t span = 64;         // START_SEARCH_SPAN
-   bool have_prev_window = false;
-   bool filter_ready = false;  // ws->ftab describes this read
-   uint32_t prev_ws = 0, prev_we = 0;
    if (bt.mode & 1) {
       st = ST_CLOSE;
    } else if ((bt.mode & 2) && bt.close_info) {
-      cres.n_ups = bt.close_info[ri].max_len ? 1u : 0u;
-      cres.max_len = bt.close_info[ri].max_len;
-      cres.last_abs_loc = bt.close_info[ri].last_abs_loc;
-      if (cres.n_ups && L > 0) st = n_regions ? ST_FAR_CLUSTER : ST_FAR_WINDOW;
+      const PgCloseInfo ci = bt.close_info[ri];
+      rs.close_ups = ci.max_len ? 1u : 0u;
+      rs.close_max_len = ci.max_len;
+      rs.close_last = ci.last_abs_loc;
+      if (ci.max_len && L > 0) st = rs.n_regions ? ST_FAR_CLUSTER : ST_FAR_WINDOW;
    }
    while (st != ST_DONE) {
       // ---- describe the search ----
@@ -877,13 +889,16 @@ PG_DEV void pg_process_read(PgWarpCtx<LW, TL> &cx, const PgBatch &bt, int ri, Pg
       PgRegion &one = two[0];
       const PgRegion *regs = two;
       int nreg = 1;
-      PgRun *dst = farNew;
       bool skip = false;
       bool keep_state = false;     // far windows are nested: window k only scans the two rings around window k-1
-      unsigned long long alg_bases = 0;
+      uint32_t alg_bases = 0;
+      const int chr_id = rs.chr_id;
       if (st == ST_CLOSE) {
          // GetCloseEndInner, pindel.cpp:2250-2396
-         se.far = false; se.bp_start = prm->min_close; dst = closeBuf;
+         se.far = false; se.bp_start = prm->min_close;
+         const uint8_t md = bt.matched_d[ri];
+         const uint32_t rp = bt.matched_rel_pos[ri];
+         const int isz = bt.insert_size[ri];
          int64_t start, end;
          if (md == '+') {
             // CurrentReadSeq = ReverseComplement(read): chars[j] = comp(R[L-1-j]); seeded on its first char, grows right
@@ -904,22 +919,24 @@ PG_DEV void pg_process_read(PgWarpCtx<LW, TL> &cx, const PgBatch &bt, int ri, Pg
          // SearchFarEndAtPos, farend_searcher.cpp:46-103
          se.far = true; se.bp_start = PG_FAR_BP_START; se.chp.arr = 0; se.chp.inv = 0u; se.d = 1;
          skip = (ws->q[0][2][0] & 1u) != 0;          // read[0] == 'N' -> returns at once (:54-56)
-         if (st == ST_FAR_CLUSTER) { regs = cluster; nreg = n_regions; }
+         if (st == ST_FAR_CLUSTER) { regs = bt.regions + bt.region_off[ri]; nreg = (int)rs.n_regions; }
          else {
-            uint32_t center = cres.last_abs_loc, size = cx.chroms[chr_id].len;
+            uint32_t center = rs.close_last, size = cx.chroms[chr_id].len;
             uint32_t wsx = (center > span + PG_SPACER) ? center - span : PG_SPACER;            // pindel.cpp:1033-1042
             uint32_t wex = (center + span + PG_SPACER < size) ? center + span : size - PG_SPACER;
-            alg_bases = wex > wsx ? (unsigned long long)(wex - wsx) : 0ull;
+            alg_bases = wex > wsx ? wex - wsx : 0u;
             one.chr = chr_id; one.start = wsx; one.end = wex;
-            if (have_prev_window && !skip && wsx <= prev_ws && wex >= prev_we && prev_we >= prev_ws) {
+            const uint32_t pws = rs.prev_ws, pwe = rs.prev_we, have_prev = rs.have_prev;
+            pg_syncwarp();              // every lane has read the previous window before any lane replaces it
+            if (have_prev && !skip && wsx <= pws && wex >= pwe && pwe >= pws) {
                // the reference searches the whole window again (pindel.cpp:1027-1029); the top-2 state of window k-1
                // is still exact for its positions, so only [wsx, prev_ws) and [prev_we, wex) are new
                keep_state = true;
-               two[0].chr = chr_id; two[0].start = wsx; two[0].end = prev_ws;
-               two[1].chr = chr_id; two[1].start = prev_we; two[1].end = wex;
+               two[0].chr = chr_id; two[0].start = wsx; two[0].end = pws;
+               two[1].chr = chr_id; two[1].start = pwe; two[1].end = wex;
                nreg = 2;
             }
-            have_prev_window = !skip; prev_ws = wsx; prev_we = wex;
+            rs.have_prev = skip ? 0u : 1u; rs.prev_ws = wsx; rs.prev_we = wex;
          }
       }
       // ---- run it ----
@@ -939,22 +956,29 @@ PG_DEV void pg_process_read(PgWarpCtx<LW, TL> &cx, const PgBatch &bt, int ri, Pg
                // the outer rings of the far schedule go through the threshold filter (the state of the inner windows
                // supplies the thresholds); its step table is built once per read, here, from the final sequence
                const bool use_filter = TL <= 16 && se.far && keep_state && e - s >= prm->filter_min_pos;
-               if (use_filter && !filter_ready) {
+               if (use_filter && !rs.filter_ready) {
                   pg_filter_prepare<LW, TL>(ws, se.chp.arr, se.chp.inv, L);
-                  filter_ready = true;
+                  rs.filter_ready = 1;
                }
                pg_scan_window<LW, TL>(cx, se, rg.chr, s, e, phase, use_filter);
-               if (st != ST_FAR_WINDOW) window_bases += (unsigned long long)(e - s);
+               if (st != ST_FAR_WINDOW) alg_bases += e - s;
             }
          }
-         window_bases += alg_bases;      // far windows are accounted at the size the reference scans, rings or not
+         // far windows are accounted at the size the reference scans, rings or not
+         const unsigned long long wb = rs.window_bases;
+         pg_syncwarp();
+         rs.window_bases = wb + alg_bases;
       }
+      // close runs go to the first third of the warp's scratch, a new far end to the third that does not hold the best one
+      PgRun *dst = scratch + (st == ST_CLOSE ? 0u : (3u - rs.far_best) * cap);
       PgResult res = pg_walk_emit<LW, TL>(cx, se, dst, cap);
       // ---- decide what comes next ----
+      const uint32_t best_ml = rs.best_max_len, close_ml = rs.close_max_len, far_best = rs.far_best;
+      pg_syncwarp();                    // reads of the shared state above, writes below
       if (st == ST_CLOSE) {
-         cres = res;
+         rs.close_runs = res.n_runs; rs.close_ups = res.n_ups; rs.close_max_len = res.max_len; rs.close_last = res.last_abs_loc;
          if (res.n_ups) {
-            st = ((bt.mode & 2) && L > 0) ? (n_regions ? ST_FAR_CLUSTER : ST_FAR_WINDOW) : ST_DONE;
+            st = ((bt.mode & 2) && L > 0) ? (rs.n_regions ? ST_FAR_CLUSTER : ST_FAR_WINDOW) : ST_DONE;
          } else if (!second_try) {
             L = pg_flip_read<LW, TL>(ws, L);         // Temp_One_Read.setUnmatchedSeq(ReverseComplement(..)), pindel.cpp:2545
             flips++;
@@ -964,11 +988,12 @@ PG_DEV void pg_process_read(PgWarpCtx<LW, TL> &cx, const PgBatch &bt, int ri, Pg
             if (++range_index >= 2) st = ST_DONE;    // MaxRange = 2
          }
       } else {
-         if (res.seeds && res.max_len >= best.max_len) {          // NewUPFarIsBetter, farend_searcher.cpp:30-44
-            best = res;
-            PgRun *t = farBest; farBest = farNew; farNew = t;
+         const bool better = res.seeds && res.max_len >= best_ml;     // NewUPFarIsBetter, farend_searcher.cpp:30-44
+         if (better) {
+            rs.best_runs = res.n_runs; rs.best_ups = res.n_ups; rs.best_max_len = res.max_len;
+            rs.far_best = 3u - far_best;
          }
-         bool good = best.max_len + cres.max_len >= (uint32_t)L; // goodFarEndFound, pindel.cpp:480-483
+         bool good = (better ? res.max_len : best_ml) + close_ml >= (uint32_t)L; // goodFarEndFound, pindel.cpp:480-483
          if (st == ST_FAR_CLUSTER) {
             st = good ? ST_DONE : ST_FAR_WINDOW;
          } else {
@@ -978,26 +1003,27 @@ PG_DEV void pg_process_read(PgWarpCtx<LW, TL> &cx, const PgBatch &bt, int ri, Pg
       }
    }
    // publish: one allocation in the run pool for close + far runs
-   uint32_t ncl = (bt.mode & 1) ? cres.n_runs : 0u;
-   uint32_t total = ncl + best.n_runs;
+   const uint32_t ncl = (bt.mode & 1) ? rs.close_runs : 0u, nfar = rs.best_runs;
+   const PgRun *closeBuf = scratch, *farBest = scratch + rs.far_best * cap;
+   uint32_t total = ncl + nfar;
    uint32_t off = 0;
    if (lane == 0 && total) off = pg_atomic_add(bt.counters + 1, total);
    off = pg_shfl(off, 0);
    ro.len_after = (uint16_t)L;
    ro.flags = (uint16_t)(((flips & 1u) ? PG_F_FLIPPED : 0u) | ((flips & 3u) << PG_F_NFLIPS_SHIFT));
-   if (total && (off + total > bt.run_pool_cap || ncl > cap || best.n_runs > cap)) {
+   if (total && (off + total > bt.run_pool_cap || ncl > cap || nfar > cap)) {
       ro.flags |= PG_F_OVERFLOW;
       if (lane == 0) bt.counters[2] = 1;
    } else {
-      ro.run_off = off; ro.n_close_runs = (uint16_t)ncl; ro.n_far_runs = (uint16_t)best.n_runs;
+      ro.run_off = off; ro.n_close_runs = (uint16_t)ncl; ro.n_far_runs = (uint16_t)nfar;
       pg_syncwarp();
       for (uint32_t i = (uint32_t)lane; i < total; i += 32) bt.run_pool[off + i] = (i < ncl) ? closeBuf[i] : farBest[i - ncl];
    }
    if (lane == 0) {
       bt.out[ri] = ro;
       // statistics for the roofline arithmetic: counters[4..5] = window bases, [6..7] = UniquePoints (64-bit each)
-      pg_atomic_add64((unsigned long long *)(bt.counters + 4), window_bases);
-      pg_atomic_add64((unsigned long long *)(bt.counters + 6), (unsigned long long)(((bt.mode & 1) ? cres.n_ups : 0u) + best.n_ups));
+      pg_atomic_add64((unsigned long long *)(bt.counters + 4), rs.window_bases);
+      pg_atomic_add64((unsigned long long *)(bt.counters + 6), (unsigned long long)(((bt.mode & 1) ? rs.close_ups : 0u) + rs.best_ups));
    }
    pg_syncwarp();
 }

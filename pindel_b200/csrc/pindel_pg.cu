@@ -40,7 +40,9 @@ static_assert(PG_READ_FLIPPED == PG_F_FLIPPED && PG_READ_UNSUPPORTED == PG_F_TOO
 #define PG_PIPE_CHUNK_DEFAULT (1 << 20)   // reads per chunk of the pipelined path; PG_PIPE_CHUNK in the environment overrides it (tests)
 #define PG_BLOCK_THREADS 32
 #ifndef PG_MINB
-#define PG_MINB 32         // resident CTAs (= warps) per SM the register allocator is asked to make room for (TL <= 8 variants)
+#define PG_MINB 24         // resident CTAs (= warps) per SM the register allocator is asked to make room for (TL <= 8 variants):
+                           // measured (scripts/kernel_ab.py, profiles/r2n_kernel_ab.txt) 32 warps at 64 registers 79.4 M reads/s,
+                           // 24 at 80 registers 81.5, 20 at 96 75.2, 16 at 113 65.6 on the headline workload
 #endif
 #define PG_WARPS_PER_BLOCK (PG_BLOCK_THREADS / 32)
 
@@ -79,7 +81,7 @@ __device__ __forceinline__ void pg_tile_load(PgWarpSmem<LW, TL> *ws, const PgChr
 // One warp per CTA: the warp's working set is a static __shared__ object, so every access to it is an LDS / STS with a
 // link-time constant address (with several warps per CTA the per-warp base had to be re-derived from the shared window
 // all over the hot loop, a few percent of all instructions), and the parameter block is read from the constant bank the
-// kernel arguments live in.  32 resident CTAs per SM = 32 warps at 64 registers, the same occupancy as 4 x 256 threads.
+// kernel arguments live in.  The warps of an SM are its resident CTAs (PG_MINB of them).
 template <int LW, int TL>
 __global__ void __launch_bounds__(32, (TL <= 8) ? PG_MINB : 1) pg_search_kernel(const __grid_constant__ PgBatch bt, const __grid_constant__ PgParams prm,
                                                                                 const PgChrom *__restrict__ chroms)
@@ -2078,7 +2080,11 @@ int pg_rp_modify(pg_ctx *ctx, int32_t n, const pg_rp *in, pg_rp_cluster *out)
    CU(cudaSetDevice(ctx->device));
    cudaStream_t st = ctx->stream;
    std::vector<uint32_t> rows_small, off_small, rows_big, off_big;
-   pg_rp_classes(n, reinterpret_cast<const PgRp *>(in), 1024u, rows_small, off_small, rows_big, off_big);
+   // classes of up to 1024 rows take the warp kernel, larger ones the CTA kernel; PG_RP_WARP_MAX lowers the limit so that a
+   // small input exercises the CTA kernel (compute-sanitizer racecheck slows its barrier loop by orders of magnitude)
+   uint32_t warp_max = 1024u;
+   if (const char *e = getenv("PG_RP_WARP_MAX")) { const unsigned long v = strtoul(e, nullptr, 10); if (v >= 1 && v < 1024) warp_max = (uint32_t)v; }
+   pg_rp_classes(n, reinterpret_cast<const PgRp *>(in), warp_max, rows_small, off_small, rows_big, off_big);
    const uint32_t n_small = (uint32_t)off_small.size() - 1, n_big = (uint32_t)off_big.size() - 1;
    const size_t rs = rows_small.size(), rb = rows_big.size();
    // device layout: [small class rows | big class rows], [small offsets | big offsets]
