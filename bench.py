@@ -11,7 +11,8 @@ Pindel defaults):
   value     reads/s with the batch already resident in HBM (K launches timed with CUDA events, max over ranks; with
             several GPUs every step ends with the NCCL gather of the breakpoint records on rank 0, which travels while the
             next step's kernel runs)
-  e2e       reads/s through the C ABI with host buffers: H2D of the batch + search + D2H of the records per step
+  e2e       reads/s through the C ABI with host buffers: H2D of the batch + search + D2H of the records per step (with
+            several GPUs every rank's result buffers are a shared-memory segment that rank 0 maps)
   roofline  algorithmic bytes per launch / measured launch time, against the measured HBM peak
   parity    after the timed region: a sample of the last step's records (from every rank) against the CPU restatement
   cpu_baseline  the reference's GetCloseEnd/SearchFarEnds on this box's host cores, on a bounded sample of the batch,
@@ -399,6 +400,64 @@ def algorithmic_compares(w, spec, sample=5000):
 
 
 # ---------------------------------------------------------------------------------------------------------------
+class SharedRecords:
+    """Result buffers of one rank (pg_read_out[n] + pg_run[cap]) in a /dev/shm file, page-locked for the GPU's copies; rank 0 maps
+    every rank's file, which makes the end-to-end "gather" a matter of each rank's own D2H."""
+
+    def __init__(self, rank, n, run_cap, torch):
+        from pindel_b200 import runs as R
+        self.torch, self.n, self.run_cap = torch, n, run_cap
+        self.nbytes = n * R.OUT_DT.itemsize + run_cap * R.RUN_DT.itemsize
+        # /dev/shm when it has room for every rank's segment, else a file under the temporary directory (page cache)
+        base = "/dev/shm"
+        try:
+            st = os.statvfs(base)
+            if st.f_blocks * st.f_frsize < 12 * self.nbytes:      # capacity, not free space: every rank must decide alike
+                base = tempfile.gettempdir()
+        except OSError:
+            base = tempfile.gettempdir()
+        self.tag = os.path.join(base, "pgbench_%s_" % os.environ.get("MASTER_PORT", "0"))
+        self.path = "%s%d" % (self.tag, rank)
+        self.mm = np.memmap(self.path, dtype=np.uint8, mode="w+", shape=(self.nbytes,))
+        self.mm[:] = 0                                    # touch every page before registering
+        self.registered = torch.cuda.cudart().cudaHostRegister(self.mm.ctypes.data, self.nbytes, 0)
+        self.out = self.mm[:n * R.OUT_DT.itemsize].view(R.OUT_DT)
+        self.runs = self.mm[n * R.OUT_DT.itemsize:].view(R.RUN_DT)
+
+    def check_on_rank0(self, world, gat, R):
+        """Rank 0 maps the other ranks' segments and compares the first headers with what the NCCL gather of the resident path
+        delivered (same reads, same kernel: lengths, flags and run counts must agree).  -> ranks seen"""
+        import torch.distributed as dist
+        dist.barrier()
+        if dist.get_rank() != 0:
+            return None
+        seen = 0
+        for r in range(world):
+            mm = np.memmap("%s%d" % (self.tag, r), dtype=np.uint8, mode="r")
+            k = min(1000, self.n)
+            mine = mm[:k * R.OUT_DT.itemsize].view(R.OUT_DT)
+            ref = gat.last[r][0][:k * R.OUT_DT.itemsize].cpu().numpy().view(R.OUT_DT)
+            if all(np.array_equal(mine[f], ref[f]) for f in ("n_close_runs", "n_far_runs", "len_after", "flags")):
+                seen += 1
+            del mm
+        return seen
+
+    def close(self):
+        try:
+            self.torch.cuda.cudart().cudaHostUnregister(self.mm.ctypes.data)
+        except Exception:
+            pass
+        del self.out, self.runs
+        try:
+            self.mm._mmap.close()
+        except Exception:
+            pass
+        try:
+            os.unlink(self.path)
+        except OSError:
+            pass
+
+
 def run_workload(a, spec, w, rank, local_rank, world, dev, steps, warmup, log, want_cpu):
     """Times one workload on this rank's GPU (collectively with the other ranks) -> result dict (rank 0) or None."""
     import torch
@@ -428,8 +487,16 @@ def run_workload(a, spec, w, rank, local_rank, world, dev, steps, warmup, log, w
         chr_h[:] = w["chr_id"]
         batch["chr_id"] = chr_h
         h2d_bytes += chr_h.nbytes
-    out_h = api.pinned_empty(n, R.OUT_DT)
-    runs_h = api.pinned_empty(max(1024, 8 * n), R.RUN_DT)
+    shm = None
+    if world == 1:
+        out_h = api.pinned_empty(n, R.OUT_DT)
+        runs_h = api.pinned_empty(max(1024, 8 * n), R.RUN_DT)
+    else:
+        # several GPUs, end to end: every rank's records land in a host shared-memory segment that rank 0 maps (page-locked with
+        # cudaHostRegister), so the records of all ranks are in rank 0's address space after each rank's own D2H -- N PCIe links
+        # in parallel instead of one
+        shm = SharedRecords(rank, n, 4 * n + 4096, torch)
+        out_h, runs_h = shm.out, shm.runs
     gat = shard.RecordGatherer(dev, rank, world) if world > 1 else None
 
     def barrier():
@@ -467,33 +534,20 @@ def run_workload(a, spec, w, rank, local_rank, world, dev, steps, warmup, log, w
             stream.wait_stream(gat.stream)
 
     def e2e_steps(k):
-        """The call a user makes, k times.  One GPU: host buffers in, host buffers out (pg_search; large batches are chunked
-        so the copies overlap the kernel).  Several GPUs: every rank uploads its batch from pinned host memory chunk by chunk
-        behind the kernel (pg_search_resident), the records go from the device to rank 0 in one NCCL gather and from there
-        to pinned host memory -- both while the next step is already running."""
-        if not gat:
-            res = None
-            for _ in range(k):
-                res = pg.search(out=out_h, runs=runs_h, **batch)
-            return res[0].nbytes + res[1].nbytes
-        moved = 0
-        ev_prev, gdone = None, []
-        for i in range(k):
-            if i >= 3:
-                gdone[i - 3].synchronize()          # step i reuses the result slot of step i-3 (long done: the host only checks)
-            pg.search_resident(3, **batch)
-            ev = torch.cuda.Event()
-            ev.record(stream)
-            if i > 0:
-                o, r, nr, nn = pg.device_results_previous()
-                moved = gat.gather(o, r, nn * R.OUT_DT.itemsize, nr * R.RUN_DT.itemsize, after_event=ev_prev, to_host=True)
-                g = torch.cuda.Event()
-                g.record(gat.stream)
-                gdone.append(g)
-            ev_prev = ev
-        o, r, nr = pg.device_results()
-        moved = gat.gather(o, r, n * R.OUT_DT.itemsize, nr * R.RUN_DT.itemsize, after_event=ev_prev, to_host=True)
-        stream.wait_stream(gat.stream)
+        """The call a user makes, k times: host buffers in, host buffers out (pg_search; large batches are chunked so the copies
+        overlap the kernel).  With several GPUs every rank does that for its shard over its own PCIe link, and its result
+        buffers are a shared-memory segment rank 0 maps: after the closing barrier all records are in rank 0's address space.
+        (The first version of this round gathered the records on the device -- NCCL, as the resident path does -- and copied them
+        to the host on rank 0: 3.9 GB per step through ONE PCIe link at N = 8, 334 M reads/s instead of ~600,
+        profiles/r2q_bench_n8_gather_then_d2h.json.)"""
+        res = None
+        for _ in range(k):
+            res = pg.search(out=out_h, runs=runs_h, **batch)
+        moved = res[0].nbytes + res[1].nbytes
+        if world > 1:
+            t = torch.tensor([moved], device=dev, dtype=torch.int64)
+            dist.all_reduce(t)
+            moved = int(t.item())
         return moved
 
     # ---- warm-up ----
@@ -533,6 +587,7 @@ def run_workload(a, spec, w, rank, local_rank, world, dev, steps, warmup, log, w
     torch.cuda.profiler.stop()
     e2e_ms_step = max_over_ranks(e0.elapsed_time(e1)) / steps
     e2e_value = world * n / (e2e_ms_step / 1e3)
+    e2e_seen = shm.check_on_rank0(world, gat, R) if shm else None
     launches += pg.kernel_launches - launches_e2e0
 
     # ---- roofline of the search kernel (the only kernel in the timed region) ----
@@ -556,7 +611,7 @@ def run_workload(a, spec, w, rank, local_rank, world, dev, steps, warmup, log, w
     result = {"metric": METRIC, "value": value, "unit": "reads/s", "n_gpus": world, "steps": steps, "warmup": warmup, "ms_per_step": ms_step,
               "higher_is_better": True, "scaling": spec["scaling"], "vs_baseline": None, "dtype": "u32", "data": "synthetic", "config": cfg,
               "e2e": {"value": e2e_value, "unit": "reads/s", "ms_per_step": e2e_ms_step, "h2d_bytes_per_step": int(h2d_bytes * world),
-                      "d2h_bytes_per_step": int(d2h_bytes)},
+                      "d2h_bytes_per_step": int(d2h_bytes), **({"records_visible_on_rank0": e2e_seen} if e2e_seen is not None else {})},
               "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "parity": parity}
     if rank == 0 and want_cpu:
         try:
@@ -574,6 +629,10 @@ def run_workload(a, spec, w, rank, local_rank, world, dev, steps, warmup, log, w
             result["cpu_baseline"] = {"value": None, "unit": "reads/s", "cores": os.cpu_count(), "kind": "unavailable", "sample": repr(e)}
     pg.close()
     del seq_h, off_h, md_h, pos_h, isz_h, out_h, runs_h
+    if shm:
+        if world > 1:
+            dist.barrier()
+        shm.close()
     torch.cuda.empty_cache()
     return result if rank == 0 else None
 

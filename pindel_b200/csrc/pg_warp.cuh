@@ -330,65 +330,6 @@ PG_COLD uint32_t pg_filter_tile(PgWarpSmem<LW, TL> *ws, uint32_t r0, uint32_t r1
    const int lane = pg_lane();
    const uint32_t wlast = (r1 - 1u) >> 5;
    bool any = false, surv = false;
-#ifdef PG_FILTER_W2
-   // two adjacent words per lane and trip: the step table's load and the loop control are shared by 64 positions, and a
-   // whole 2048-position tile is one trip
-   for (uint32_t wb = r0 >> 5; wb <= wlast; wb += 64u) {
-      const uint32_t wa = wb + 2u * (uint32_t)lane;
-      if (wa <= wlast) {
-         const uint2 Wm = ws->tile[wa - 1], W0 = ws->tile[wa], W1 = ws->tile[wa + 1], W2 = ws->tile[wa + 2];
-         uint32_t oka, okb;
-         {
-            const uint32_t p0 = wa << 5;
-            uint32_t inr = ~0u;
-            if (p0 < r0) inr &= ~0u << (r0 - p0);
-            if (r1 - p0 < 32u) inr &= (1u << (r1 - p0)) - 1u;
-            oka = ~ws->tile_n[wa] & inr;
-            inr = wa + 1u <= wlast ? ~0u : 0u;
-            if (r1 - p0 < 64u) inr &= (r1 - p0 <= 32u) ? 0u : ((1u << (r1 - p0 - 32u)) - 1u);
-            okb = ~ws->tile_n[wa + 1] & inr;
-         }
-         const uint32_t dla = W0.x ^ c0lom, dha = W0.y ^ c0him, dlb = W1.x ^ c0lom, dhb = W1.y ^ c0him;
-         const uint32_t plusa = ~(dla | dha) & oka, minusa = (dla & dha) & oka, plusb = ~(dlb | dhb) & okb, minusb = (dlb & dhb) & okb;
-         any = any || (plusa | minusa | plusb | minusb) != 0u;
-         uint32_t apa[TL], ama[TL], apb[TL], amb[TL];
-#pragma unroll
-         for (int t = 0; t < TL; t++) { apa[t] = plusa; ama[t] = minusa; apb[t] = plusb; amb[t] = minusb; }
-         uint32_t spa = 0, sma = 0, spb = 0, smb = 0;
-         uint32_t k = 0;
-#pragma unroll
-         for (int t0 = 0; t0 < TL; t0++) {
-            if (t0 < T) {
-               const uint32_t kend = ws->fcnt[t0];
-#pragma unroll 1
-               for (; k < kend; k++) {
-                  const PgFStep e = ws->ftab[k];
-                  const uint32_t mpa = (pg_fsr(W0.x, W1.x, e.sh) ^ e.lo) | (pg_fsr(W0.y, W1.y, e.sh) ^ e.hi);
-                  const uint32_t mma = ~(pg_fsr(Wm.x, W0.x, e.rsh) ^ e.lo) | ~(pg_fsr(Wm.y, W0.y, e.rsh) ^ e.hi);
-                  const uint32_t mpb = (pg_fsr(W1.x, W2.x, e.sh) ^ e.lo) | (pg_fsr(W1.y, W2.y, e.sh) ^ e.hi);
-                  const uint32_t mmb = ~(pg_fsr(W0.x, W1.x, e.rsh) ^ e.lo) | ~(pg_fsr(W0.y, W1.y, e.rsh) ^ e.hi);
-#pragma unroll
-                  for (int t = TL - 1; t > t0; t--) {
-                     apa[t] = (apa[t] & ~mpa) | (apa[t - 1] & mpa);
-                     ama[t] = (ama[t] & ~mma) | (ama[t - 1] & mma);
-                     apb[t] = (apb[t] & ~mpb) | (apb[t - 1] & mpb);
-                     amb[t] = (amb[t] & ~mmb) | (amb[t - 1] & mmb);
-                  }
-                  apa[t0] &= ~mpa; ama[t0] &= ~mma; apb[t0] &= ~mpb; amb[t0] &= ~mmb;
-               }
-               spa |= apa[t0]; sma |= ama[t0]; spb |= apb[t0]; smb |= amb[t0];
-            }
-         }
-         ws->fsp[wa] = spa; ws->fsm[wa] = sma;
-         if (wa + 1u <= wlast) { ws->fsp[wa + 1] = spb; ws->fsm[wa + 1] = smb; }
-         surv = surv || (spa | sma | spb | smb) != 0u;
-#ifdef PG_EMULATE
-         pg_emul_filter_stats[0] += (unsigned long long)(pg_popc(plusa | minusa) + pg_popc(plusb | minusb));
-         pg_emul_filter_stats[1] += (unsigned long long)(pg_popc(spa | sma) + pg_popc(spb | smb));
-#endif
-      }
-   }
-#else
    for (uint32_t wb = r0 >> 5; wb <= wlast; wb += 32u) {
       const uint32_t wi = wb + (uint32_t)lane;
       if (wi <= wlast) {
@@ -433,7 +374,6 @@ PG_COLD uint32_t pg_filter_tile(PgWarpSmem<LW, TL> *ws, uint32_t r0, uint32_t r1
 #endif
       }
    }
-#endif
 #ifdef PG_EMULATE
    if (lane == 0) pg_emul_filter_stats[2]++;
 #endif
