@@ -396,6 +396,35 @@ int pg_bam_sr_close_end(pg_ctx *ctx, const pg_sr_query *q, int32_t chr_id, pg_sr
                         uint64_t seq_cap, uint32_t *stride, pg_sr_ref *refs, uint64_t ref_cap, uint64_t *n_refs, uint64_t *n_scanned, pg_results *res);
 
 /* ------------------------------------------------------------------------------------------------------------------
+ * The BreakDancer mask and the cluster lookup (last part): what turns the window's events
+ * into the `regions` SearchFarEnd scans first (src/pindel.cpp:1006-1020).
+ *   pg_bd_load_region = BDData::loadRegion (src/bddata.cpp:850-946) for SearchWindow(chr, start, end): `events` is the whole
+ *                       event list in the reference's order (BDData::m_bdEvents after UpdateBD's sort, sortOnFirstBDCoordinate:
+ *                       chromosome NAME, position, then the second coordinate), positions as the reference holds them (padded;
+ *                       pos <= pos2 per coordinate -- swapped here if not, as the constructor does), chromosome indices of
+ *                       pg_set_reference, chr_name_rank[c] = rank of chromosome c's name in std::string order (the cluster
+ *                       builder sorts by name).  No per-position mask is built: the region is two arrays the lookup searches.
+ *   far-end searches    pg_far_end / pg_launch(2) on a batch WITHOUT regions take every read's cluster from the loaded region on
+ *                       the device (getCorrespondingSearchWindowCluster, src/bddata.cpp:949-967, at close_info.last_abs_loc)
+ *                       until pg_bd_unload; batches that bring their own regions are unaffected.
+ *   pg_bd_clusters    = the lookup alone, host arrays in and out (region_off [n+1], regions as in pg_reads): for hosts that
+ *                       keep the clusters, and for the tests.
+ * A close end at the last swept position or beyond reads mask entries the reference never wrote (its mask has one entry more
+ * than its sweep fills, and the range check admits one more): defined here as "no cluster".  PG_ERR_UNSUPPORTED: a cluster of
+ * more than 255 windows. */
+typedef struct pg_bd_event {
+   int32_t chr_a;
+   uint32_t pos_a, pos2_a;        /* BreakDancerEvent::first  (.position, .position2) */
+   int32_t chr_b;
+   uint32_t pos_b, pos2_b;        /* BreakDancerEvent::second */
+} pg_bd_event;
+int pg_bd_load_region(pg_ctx *ctx, const pg_bd_event *events, uint32_t n_events, const int32_t *chr_name_rank, int32_t chr, uint32_t start, uint32_t end);
+int pg_bd_unload(pg_ctx *ctx);
+int pg_bd_clusters(pg_ctx *ctx, uint32_t n, const uint32_t *close_last_abs_loc, uint32_t *region_off, pg_region *regions, uint64_t cap, uint64_t *n_regions);
+uint64_t pg_bd_launches(pg_ctx *ctx);
+uint64_t pg_bd_lookups(pg_ctx *ctx);          /* reads whose cluster was looked up on the device since pg_create */
+
+/* ------------------------------------------------------------------------------------------------------------------
  * Discordant-read-pair clustering: the two quadratic loops of BDData::UpdateBD
  * (src/bddata.cpp:646-659) that turn the window's discordant pairs into BreakDancer-like events for the far-end search.
  *   pg_rp_modify    = ModifyRP (src/bddata.cpp:385-431) after its std::sort: the caller sorts (Compare2RP,

@@ -25,7 +25,12 @@
  * (outputResults / SortOutput*) exactly as before.  PG_BRIDGE_CPU_SV=1 is not offered: there is no CPU path behind the ABI.
  */
 #include "pindel.h"
+#include "control_state.h"
+/* BDData::loadRegion is supplied below (row N2): a member function, so this TU -- test infrastructure -- sees the members it
+ * works on (the event list UpdateBD filled, the window, the mask) as public.  A maintainer would simply edit the member. */
+#define private public
 #include "bddata.h"
+#undef private
 #include "read_buffer.h"
 #include "reader.h"
 #include "pindel_read_reader.h"
@@ -69,7 +74,7 @@ std::mutex g_mutex;
 struct Acc { double s; unsigned long n; };
 Acc t_close_marshal = {0, 0}, t_close_lib = {0, 0}, t_close_apply = {0, 0}, t_far_marshal = {0, 0}, t_far_lib = {0, 0}, t_far_apply = {0, 0},
     t_sv_lib = {0, 0}, t_sv_total = {0, 0}, t_box_lib = {0, 0}, t_rp_lib = {0, 0}, t_inflate_lib = {0, 0}, t_index_lib = {0, 0}, t_rpd_lib = {0, 0},
-    t_sr_lib = {0, 0}, t_sr_host = {0, 0}, t_setup = {0, 0};
+    t_sr_lib = {0, 0}, t_sr_host = {0, 0}, t_setup = {0, 0}, t_bd_lib = {0, 0};
 struct Tick {
    Acc &a;
    std::chrono::steady_clock::time_point t0;
@@ -78,6 +83,8 @@ struct Tick {
 };
 const std::chrono::steady_clock::time_point g_t_start = std::chrono::steady_clock::now();
 unsigned long g_close_calls = 0, g_far_reads = 0, g_sv_reads = 0, g_sv_records = 0, g_sv_resident = 0, g_rp_rows = 0;
+bool g_bdOnDevice = false;                     /* the current window's BreakDancer region is loaded in the library (pg_bd_load_region) */
+unsigned long g_bd_regions = 0, g_bd_events = 0;
 bool g_flushPresearched = false;               /* the reads in the ReadBuffer already went through GetCloseEnd on the device */
 const SPLIT_READ *g_farResidentBase = NULL;   /* Reads_SR of the last SearchFarEnds call, still resident on the device */
 size_t g_farResidentN = 0;
@@ -348,6 +355,7 @@ void SearchFarEnds(const std::string &chromosomeSeq, std::vector<SPLIT_READ> &re
       else {
          ci[i].max_len = (uint16_t)r.UP_Close.MaxLen();
          ci[i].last_abs_loc = r.getLastAbsLocCloseEnd();
+         if (g_bdOnDevice) continue;       /* the library looks every read's cluster up in the region loadRegion gave it */
          const SearchWindowCluster &cl = g_bdData.getCorrespondingSearchWindowCluster(r);      /* src/pindel.cpp:1006 */
          for (unsigned k = 0; k < cl.size(); k++) {
             pg_region g;
@@ -357,7 +365,7 @@ void SearchFarEnds(const std::string &chromosomeSeq, std::vector<SPLIT_READ> &re
             regions.push_back(g);
          }
       }
-      region_off[i + 1] = (uint32_t)regions.size();
+      if (!g_bdOnDevice) region_off[i + 1] = (uint32_t)regions.size();
    }
    (void)currentChromosome;
    pg_reads in;
@@ -389,6 +397,83 @@ void SearchFarEnds(const std::string &chromosomeSeq, std::vector<SPLIT_READ> &re
    g_farResidentBase = (n && !staleFarEnd && !g_group) ? &reads[0] : NULL;      /* a group's batch is spread over its devices */
    g_farResidentN = (size_t)n;
    *logStream << "Far end searching completed for this window." << std::endl;   /* src/pindel.cpp:1137 */
+}
+
+/* ---------------------------------------------------------------------------------------------------------------------
+ * Row N2, last part: BDData::loadRegion (src/bddata.cpp:852-946), called once per window (src/pindel.cpp:1853).  The reference
+ * sweeps every position of the padded window to fill a position -> cluster mask that getCorrespondingSearchWindowCluster
+ * (:949-967) then reads once per split read inside SearchFarEnd (src/pindel.cpp:1006).  Here the window's events go to the
+ * library (pg_bd_load_region) and pg_far_end derives every read's cluster on the device; SearchFarEnds above then sends no
+ * clusters.  The host keeps what the other readers of the state expect: the padded window and the empty cluster 0.  The
+ * reference's own function runs instead (dlsym(RTLD_NEXT)) with PG_BRIDGE_HOST_BD=1, when -Q/-b ask for isBreakDancerEvent
+ * (which reads the mask itself, src/bddata.cpp:981-995), or when an event names a chromosome that is not loaded (the
+ * reference's error path, src/control_state.cpp:62-70).
+ * ------------------------------------------------------------------------------------------------------------------- */
+extern bool doOutputBreakdancerEvents();       /* src/pindel.cpp:521 */
+void BDData::loadRegion(const SearchWindow &searchWindow)
+{
+   typedef void (*Fn)(BDData *, const SearchWindow &);
+   static Fn original = (Fn)dlsym(RTLD_NEXT, "_ZN6BDData10loadRegionERK12SearchWindow");
+   static const bool hostBD = getenv("PG_BRIDGE_HOST_BD") != NULL;
+   std::lock_guard<std::mutex> lock(g_mutex);
+   g_bdOnDevice = false;
+   bool device = !hostBD && !doOutputBreakdancerEvents() && this == &g_bdData;
+   std::vector<pg_bd_event> ev;
+   std::vector<int32_t> rank;
+   int32_t chrId = -1;
+   if (device) {
+      /* chromosome index by name; rank of every loaded chromosome's name in string order (the comparators compare names) */
+      std::map<std::string, int32_t> idOf;
+      std::vector<std::string> names;
+      for (unsigned c = 0; g_genome.getChr(c) != NULL; c++) { idOf[g_genome.getChr(c)->getName()] = (int32_t)c; names.push_back(g_genome.getChr(c)->getName()); }
+      rank.resize(names.size());
+      { int32_t k = 0; for (std::map<std::string, int32_t>::const_iterator it = idOf.begin(); it != idOf.end(); ++it) rank[it->second] = k++; }
+      const std::string &chrName = searchWindow.getChromosome()->getName();
+      chrId = idOf.count(chrName) ? idOf[chrName] : -1;
+      if (chrId < 0 || idOf.size() != names.size()) device = false;
+      /* only the window chromosome's events can fall between the two bounds of the sorted list (:879-885); they keep their order */
+      for (size_t i = 0; device && i < m_bdEvents.size(); i++) {
+         const BreakDancerEvent &e = m_bdEvents[i];
+         if (e.first.getChromosomeName() != chrName) continue;
+         std::map<std::string, int32_t>::const_iterator b = idOf.find(e.second.getChromosomeName());
+         if (b == idOf.end()) { device = false; break; }
+         pg_bd_event x;
+         x.chr_a = chrId; x.pos_a = e.first.position; x.pos2_a = e.first.position2;
+         x.chr_b = b->second; x.pos_b = e.second.position; x.pos2_b = e.second.position2;
+         ev.push_back(x);
+      }
+   }
+   if (device) {
+      ensureContext();
+      Tick tk(t_bd_lib);
+      const int nctx = g_group ? pg_group_size(g_group) : 1;
+      for (int k = 0; k < nctx && device; k++) {
+         pg_ctx *c = g_group ? pg_group_context(g_group, k) : g_ctx;
+         if (pg_bd_load_region(c, ev.empty() ? NULL : &ev[0], (uint32_t)ev.size(), &rank[0], chrId, searchWindow.getStart(), searchWindow.getEnd()) != PG_OK) {
+            std::fprintf(stderr, "pindel_gpu_demo: pg_bd_load_region: %s -- the reference's loadRegion runs\n", pg_last_error(c));
+            device = false;
+         }
+      }
+   }
+   if (!device) {
+      if (g_ctx) {
+         const int nctx = g_group ? pg_group_size(g_group) : 1;
+         for (int k = 0; k < nctx; k++) pg_bd_unload(g_group ? pg_group_context(g_group, k) : g_ctx);
+      }
+      original(this, searchWindow);
+      return;
+   }
+   /* host state as the reference leaves it, minus the mask (:856-872, :895-899) */
+   m_currentWindow = searchWindow;
+   m_currentWindow.setStart(m_currentWindow.getStart() >= 3000 ? m_currentWindow.getStart() - 3000 : 0);
+   m_currentWindow.setEnd(m_currentWindow.getEnd() + 3000);
+   delete[] m_breakDancerMask;
+   m_breakDancerMask = NULL;
+   m_regionsToScanCollection.clear();
+   m_regionsToScanCollection.push_back(SearchWindowCluster());
+   g_bdOnDevice = true;
+   g_bd_regions++;
+   g_bd_events += ev.size();
 }
 
 /* ---------------------------------------------------------------------------------------------------------------------
@@ -1180,21 +1265,21 @@ bool ReadInBamReads_SR(const char *bam_path, const std::string &FragName, const 
 static void reportAtExit()
 {
    const double wall = std::chrono::duration<double>(std::chrono::steady_clock::now() - g_t_start).count();
-   const double lib = t_close_lib.s + t_far_lib.s + t_sv_lib.s + t_box_lib.s + t_rp_lib.s + t_inflate_lib.s + t_index_lib.s + t_rpd_lib.s + t_sr_lib.s;
+   const double lib = t_close_lib.s + t_far_lib.s + t_sv_lib.s + t_box_lib.s + t_rp_lib.s + t_inflate_lib.s + t_index_lib.s + t_rpd_lib.s + t_sr_lib.s + t_bd_lib.s;
    const double host = t_close_marshal.s + t_close_apply.s + t_far_marshal.s + t_far_apply.s + (t_sv_total.s - t_sv_lib.s) + t_sr_host.s;
    std::fprintf(stderr, "pindel_gpu_demo timing: wall %.3f s; context + reference upload %.3f; library calls %.3f (close end %.3f in %lu, far end %.3f in %lu, "
                 "classification %.3f in %lu, box ordering %.3f in %lu, pair clustering %.3f in %lu, inflate %.3f in %lu, record index %.3f in %lu, pair discovery %.3f in %lu, "
-                "split-read filter + search %.3f in %lu); bridge marshalling %.3f (close end: in %.3f, out %.3f; far end: in %.3f, out %.3f; classification records and replay %.3f; "
+                "split-read filter + search %.3f in %lu, BreakDancer regions %.3f in %lu); bridge marshalling %.3f (close end: in %.3f, out %.3f; far end: in %.3f, out %.3f; classification records and replay %.3f; "
                 "split-read rows to SPLIT_READs %.3f); the reference's own host code (parsing, window loop, reporters) %.3f\n",
                 wall, t_setup.s, lib, t_close_lib.s, t_close_lib.n, t_far_lib.s, t_far_lib.n, t_sv_lib.s, t_sv_lib.n, t_box_lib.s, t_box_lib.n, t_rp_lib.s, t_rp_lib.n,
-                t_inflate_lib.s, t_inflate_lib.n, t_index_lib.s, t_index_lib.n, t_rpd_lib.s, t_rpd_lib.n, t_sr_lib.s, t_sr_lib.n, host, t_close_marshal.s, t_close_apply.s,
+                t_inflate_lib.s, t_inflate_lib.n, t_index_lib.s, t_index_lib.n, t_rpd_lib.s, t_rpd_lib.n, t_sr_lib.s, t_sr_lib.n, t_bd_lib.s, t_bd_lib.n, host, t_close_marshal.s, t_close_apply.s,
                 t_far_marshal.s, t_far_apply.s, t_sv_total.s - t_sv_lib.s, t_sr_host.s, wall - t_setup.s - lib - host);
    std::fprintf(stderr, "pindel_gpu_demo: %lu GetCloseEnd calls and %lu far-end reads served by libpindel_pg (%llu kernel launches); "
-                "%lu reads classified by the SV drivers on the device, %lu records (%llu launches), %lu of the reads without a second upload; %lu read pairs clustered on the device (%llu launches); %lu BAM bytes inflated and %lu records indexed on the device, %lu discordant pairs found there; %lu boxes ordered on the device (%llu launches), %lu by the reference; %lu split-read candidates from the device filter, %lu of them searched where the filter left them\n",
+                "%lu reads classified by the SV drivers on the device, %lu records (%llu launches), %lu of the reads without a second upload; %lu read pairs clustered on the device (%llu launches); %lu BAM bytes inflated and %lu records indexed on the device, %lu discordant pairs found there; %lu boxes ordered on the device (%llu launches), %lu by the reference; %lu split-read candidates from the device filter, %lu of them searched where the filter left them; %lu BreakDancer regions (%lu events) loaded into the library, %llu cluster lookups there\n",
                 g_close_calls, g_far_reads, g_ctx ? (unsigned long long)pg_kernel_launches(g_ctx) : 0ull, g_sv_reads, g_sv_records,
                 g_ctx ? (unsigned long long)pg_classify_launches(g_ctx) : 0ull, g_sv_resident, g_rp_rows,
                 g_ctx ? (unsigned long long)pg_rp_launches(g_ctx) : 0ull, g_bgzf_bytes, g_bam_records, g_rpd_rows, g_boxes_sorted,
-                g_ctx ? (unsigned long long)pg_box_sort_launches(g_ctx) : 0ull, g_boxes_host, g_sr_candidates, g_sr_searched);
+                g_ctx ? (unsigned long long)pg_box_sort_launches(g_ctx) : 0ull, g_boxes_host, g_sr_candidates, g_sr_searched, g_bd_regions, g_bd_events, g_ctx ? (unsigned long long)pg_bd_lookups(g_ctx) : 0ull);
 }
 
 int main(int argc, char *argv[])

@@ -139,6 +139,13 @@ def load_library() -> C.CDLL:
         lib.pg_device_results_previous.restype = C.c_int
         lib.pg_search_resident.argtypes = [C.c_void_p, C.c_void_p, C.c_int32]
         lib.pg_search_resident.restype = C.c_int
+        lib.pg_bd_load_region.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p, C.c_int32, C.c_uint32, C.c_uint32]
+        lib.pg_bd_unload.argtypes = [C.c_void_p]
+        lib.pg_bd_clusters.argtypes = [C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.POINTER(C.c_uint64)]
+        lib.pg_bd_launches.restype = C.c_uint64
+        lib.pg_bd_launches.argtypes = [C.c_void_p]
+        lib.pg_bd_lookups.restype = C.c_uint64
+        lib.pg_bd_lookups.argtypes = [C.c_void_p]
         lib.pg_group_create.restype = C.c_void_p
         lib.pg_group_create.argtypes = [C.c_void_p, C.c_int32, C.c_void_p]
         lib.pg_group_destroy.argtypes = [C.c_void_p]
@@ -492,6 +499,36 @@ class PatternGrowth:
                                                      C.byref(res)), "pg_bam_sr_close_end")
         self._n = int(n.value)
         return cands, seqs, refs, int(ns.value), out, runs[:res.n_runs]
+
+    # ---- BreakDancer mask (row N2, last part) ----------------------------------------------------
+    def bd_load_region(self, events, chr_name_rank, chr_id, start, end):
+        """BDData::loadRegion for SearchWindow(chr_id, start, end): events [n, 6] int (chr_a, pos_a, pos2_a, chr_b, pos_b, pos2_b)
+        in the reference's order; chr_name_rank[c] = rank of chromosome c's name in string order."""
+        ev = np.ascontiguousarray(np.array(events, dtype=np.int64).reshape(-1, 6).astype(np.uint32).view(np.int32))
+        rk = np.ascontiguousarray(chr_name_rank, dtype=np.int32)
+        self._check(self.lib.pg_bd_load_region(self.ctx, ev.ctypes.data_as(C.c_void_p), ev.shape[0], rk.ctypes.data_as(C.c_void_p), chr_id,
+                                               C.c_uint32(start), C.c_uint32(end)), "pg_bd_load_region")
+
+    def bd_unload(self):
+        self._check(self.lib.pg_bd_unload(self.ctx), "pg_bd_unload")
+
+    def bd_clusters(self, positions):
+        """getCorrespondingSearchWindowCluster for every close-end position -> (region_off [n+1], regions (runs.REGION_DT))"""
+        q = np.ascontiguousarray(positions, dtype=np.uint32)
+        off = np.zeros(q.size + 1, dtype=np.uint32)
+        n = C.c_uint64(0)
+        rc = self.lib.pg_bd_clusters(self.ctx, q.size, q.ctypes.data_as(C.c_void_p), off.ctypes.data_as(C.c_void_p), None, C.c_uint64(0), C.byref(n))
+        if rc not in (0, PG_ERR_RUNS_CAP):
+            self._check(rc, "pg_bd_clusters")
+        reg = np.zeros(int(n.value), dtype=R.REGION_DT)
+        if rc == PG_ERR_RUNS_CAP:
+            self._check(self.lib.pg_bd_clusters(self.ctx, q.size, q.ctypes.data_as(C.c_void_p), off.ctypes.data_as(C.c_void_p),
+                                                reg.ctypes.data_as(C.c_void_p), C.c_uint64(reg.size), C.byref(n)), "pg_bd_clusters")
+        return off, reg
+
+    @property
+    def bd_lookups(self) -> int:
+        return int(self.lib.pg_bd_lookups(self.ctx))
 
     def bam_last_segments(self):
         a, b = C.c_uint32(0), C.c_uint32(0)

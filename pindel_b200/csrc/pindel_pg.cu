@@ -27,6 +27,8 @@
 #include "pg_bam_host.h"
 #include "pg_sr.cuh"
 #include "pg_boxsort.cuh"
+#include "pg_bd.cuh"
+#include "pg_bd_host.h"
 #include "pg_params.h"
 #include "../../include/pindel_pg.h"
 #include "pg_host_helpers.h"
@@ -416,6 +418,11 @@ struct pg_ctx {
    size_t bz_out_len = 0;
    uint64_t bz_launches = 0;
    float bz_last_ms = 0.f;
+   // BreakDancer mask of the current window (pg_bd_load_region) and the clusters derived from it for the resident batch
+   DevBuf bk_start, bk_drop, bk_sel, bk_counts, bk_offsets, bk_sums, bk_regions, bk_region_off, bk_pos, bk_over;
+   PgBdRegionView bk_view;
+   bool bk_loaded = false;
+   uint64_t bk_launches = 0, bk_lookups = 0;
    // per-box read ordering (pg_box_sort)
    DevBuf bx_off, bx_keys, bx_order, bx_non;
    uint64_t bx_launches = 0;
@@ -588,7 +595,9 @@ void pg_destroy(pg_ctx *ctx)
                        &ctx->bd_cls, &ctx->bd_off, &ctx->bd_sums, &ctx->bd_rows, &ctx->bd_src, &ctx->bd_counters,
                        &ctx->sr_info, &ctx->sr_keys, &ctx->sr_head, &ctx->sr_slot, &ctx->sr_next, &ctx->sr_partner, &ctx->sr_emit, &ctx->sr_cands,
                        &ctx->sr_seqs, &ctx->sr_refs,
-                       &ctx->bx_off, &ctx->bx_keys, &ctx->bx_order, &ctx->bx_non};
+                       &ctx->bx_off, &ctx->bx_keys, &ctx->bx_order, &ctx->bx_non,
+                       &ctx->bk_start, &ctx->bk_drop, &ctx->bk_sel, &ctx->bk_counts, &ctx->bk_offsets, &ctx->bk_sums, &ctx->bk_regions, &ctx->bk_region_off,
+                       &ctx->bk_pos, &ctx->bk_over};
    for (DevBuf *b : svbufs) if (b->p) cudaFree(b->p);
    pipe_destroy(ctx->pipe);
    if (ctx->chroms_d) cudaFree(ctx->chroms_d);
@@ -722,6 +731,42 @@ int pg_upload(pg_ctx *ctx, const pg_reads *in)
    return PG_OK;
 }
 
+// The clusters of n reads from the loaded BreakDancer region, on the device: count pass, scan, fill pass.  Close-end positions
+// from ci (the resident batch's close_info) or from pos.  Leaves regions / region_off in ctx->bk_regions / bk_region_off and the
+// total in *total_h (after a stream synchronisation when total_h is given).
+static int bd_lookup_device(pg_ctx *ctx, uint32_t n, const PgCloseInfo *ci, const uint32_t *pos, uint32_t *total_h)
+{
+   cudaStream_t st = ctx->stream;
+   const uint32_t n16 = (n + 15u) / 16u, n_blocks = (n16 + PG_SCAN_THREADS - 1) / PG_SCAN_THREADS;
+   int rc;
+   if ((rc = ensure(ctx, ctx->bk_counts, (size_t)n16 * 16)) != PG_OK) return rc;
+   if ((rc = ensure(ctx, ctx->bk_offsets, sizeof(uint32_t) * (size_t)n16 * 16)) != PG_OK) return rc;
+   if ((rc = ensure(ctx, ctx->bk_sums, sizeof(uint32_t) * ((size_t)n_blocks + 1))) != PG_OK) return rc;
+   if ((rc = ensure(ctx, ctx->bk_region_off, sizeof(uint32_t) * ((size_t)n + 1))) != PG_OK) return rc;
+   if ((rc = ensure(ctx, ctx->bk_over, sizeof(uint32_t))) != PG_OK) return rc;
+   CU(cudaMemsetAsync(ctx->bk_counts.p, 0, (size_t)n16 * 16, st));
+   CU(cudaMemsetAsync(ctx->bk_over.p, 0, sizeof(uint32_t), st));
+   const uint32_t grid = (n + 255u) / 256u;
+   pg_bd_count_kernel<<<grid, 256, 0, st>>>(ctx->bk_view, n, ci, pos, (uint8_t *)ctx->bk_counts.p, (uint32_t *)ctx->bk_over.p);
+   pg_scan_reduce<<<n_blocks, PG_SCAN_THREADS, 0, st>>>((const uint4 *)ctx->bk_counts.p, n16, (uint32_t *)ctx->bk_sums.p);
+   pg_scan_blocks<<<1, 1024, 0, st>>>((uint32_t *)ctx->bk_sums.p, n_blocks);
+   pg_scan_apply<<<n_blocks, PG_SCAN_THREADS, 0, st>>>((const uint4 *)ctx->bk_counts.p, n16, (const uint32_t *)ctx->bk_sums.p, (uint32_t *)ctx->bk_offsets.p);
+   CU(cudaGetLastError());
+   uint32_t tot = 0, over = 0;
+   CU(cudaMemcpyAsync(&tot, (const uint32_t *)ctx->bk_sums.p + n_blocks, sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+   CU(cudaMemcpyAsync(&over, ctx->bk_over.p, sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+   CU(cudaStreamSynchronize(st));
+   if (over) return fail(ctx, PG_ERR_UNSUPPORTED, "BreakDancer cluster of more than 255 windows for one read");
+   if ((rc = ensure(ctx, ctx->bk_regions, sizeof(PgRegion) * ((size_t)tot + 1))) != PG_OK) return rc;
+   pg_bd_fill_kernel<<<(n + 256u) / 256u, 256, 0, st>>>(ctx->bk_view, n, ci, pos, (const uint32_t *)ctx->bk_offsets.p, (const uint8_t *)ctx->bk_counts.p,
+                                                       (PgRegion *)ctx->bk_regions.p, (uint32_t *)ctx->bk_region_off.p, (const uint32_t *)ctx->bk_sums.p + n_blocks);
+   CU(cudaGetLastError());
+   ctx->bk_launches += 5;
+   ctx->bk_lookups += n;
+   if (total_h) *total_h = tot;
+   return PG_OK;
+}
+
 // The search kernel over the resident batch into result slot `slot`; the slot's counters follow the kernel to the host
 // and its event marks both, so the slot can be waited for on its own while later work is already queued on the stream.
 static int launch_into(pg_ctx *ctx, int32_t mode, int slot)
@@ -753,6 +798,12 @@ static int launch_into(pg_ctx *ctx, int32_t mode, int slot)
    bt.close_info = (mode == 2 && ctx->have_close) ? (const PgCloseInfo *)ctx->closeinfo.p : nullptr;
    bt.regions = ctx->have_regions ? (const PgRegion *)ctx->regions.p : nullptr;
    bt.region_off = ctx->have_regions ? (const uint32_t *)ctx->region_off.p : nullptr;
+   if (mode == 2 && !ctx->have_regions && ctx->bk_loaded && ctx->have_close) {
+      // SearchFarEnd's first stop (src/pindel.cpp:1006): the read's BreakDancer cluster, looked up on the device from the close ends
+      if ((rc = bd_lookup_device(ctx, (uint32_t)n, (const PgCloseInfo *)ctx->closeinfo.p, nullptr, nullptr)) != PG_OK) return rc;
+      bt.regions = (const PgRegion *)ctx->bk_regions.p;
+      bt.region_off = (const uint32_t *)ctx->bk_region_off.p;
+   }
    bt.out = (PgReadOut *)r.out.p;
    bt.run_pool = (PgRun *)r.pool.p;
    bt.run_pool_cap = r.pool_cap;
@@ -1082,11 +1133,19 @@ static int run_pipelined(pg_ctx *ctx, PipeState *&ps, const pg_reads *in, pg_res
    return PG_OK;
 }
 
+// a far-end batch without clusters of its own takes them from the loaded BreakDancer region (pg_bd_load_region)
+static inline bool bd_applies(const pg_ctx *ctx, const pg_reads *in, int mode)
+{
+   return mode == 2 && ctx->bk_loaded && in->close_info && !(in->regions && in->region_off);
+}
+
 extern "C" {
 
 static int run_all(pg_ctx *ctx, const pg_reads *in, pg_results *res, int mode)
 {
-   if (ctx && in && in->n >= 2 * ctx->pipe_chunk && in->seq_blob && in->seq_off) {
+   // (a far-end batch that takes its clusters from the loaded BreakDancer region goes through upload + launch: the lookup
+   // runs on the whole resident batch)
+   if (ctx && in && in->n >= 2 * ctx->pipe_chunk && in->seq_blob && in->seq_off && !bd_applies(ctx, in, mode)) {
       CU(cudaSetDevice(ctx->device));
       return run_pipelined(ctx, ctx->pipe, in, res, mode);
    }
@@ -1104,7 +1163,7 @@ int pg_search(pg_ctx *ctx, const pg_reads *in, pg_results *res) { return run_all
 int pg_search_resident(pg_ctx *ctx, const pg_reads *in, int32_t mode)
 {
    if (!ctx || !in || in->n < 0 || mode < 1 || mode > 3) return fail(ctx, PG_ERR_ARG, "pg_search_resident: bad arguments");
-   if (in->n >= 2 * ctx->pipe_chunk && in->seq_blob && in->seq_off) {
+   if (in->n >= 2 * ctx->pipe_chunk && in->seq_blob && in->seq_off && !bd_applies(ctx, in, mode)) {
       CU(cudaSetDevice(ctx->device));
       return run_pipelined(ctx, ctx->pipe, in, nullptr, mode);
    }
@@ -2029,6 +2088,72 @@ int pg_bam_sr_close_end(pg_ctx *ctx, const pg_sr_query *q, int32_t chr_id, pg_sr
    CU(cudaStreamSynchronize(st));
    return PG_OK;
 }
+
+// ---- BreakDancer mask and cluster lookup (row N2, last part) ----------------------------------------------------------
+static_assert(sizeof(pg_bd_event) == sizeof(PgBdEvent) && sizeof(pg_bd_event) == 24, "bd event layout");
+
+int pg_bd_load_region(pg_ctx *ctx, const pg_bd_event *events, uint32_t n_events, const int32_t *chr_name_rank, int32_t chr, uint32_t start, uint32_t end)
+{
+   if (!ctx || (n_events && !events) || !chr_name_rank) return fail(ctx, PG_ERR_ARG, "pg_bd_load_region: null argument");
+   const int32_t n_chr = (int32_t)ctx->chroms_h.size();
+   if (n_chr == 0) return fail(ctx, PG_ERR_STATE, "pg_bd_load_region: no reference (call pg_set_reference)");
+   if (chr < 0 || chr >= n_chr || end < start) return fail(ctx, PG_ERR_ARG, "pg_bd_load_region: window out of range");
+   CU(cudaSetDevice(ctx->device));
+   ctx->bk_loaded = false;
+   PgBdPrepared P;
+   if (pgbd_prepare(reinterpret_cast<const PgBdEvent *>(events), n_events, chr_name_rank, n_chr, chr, start, end, P) != 0)
+      return fail(ctx, PG_ERR_ARG, "pg_bd_load_region: events must be in the reference's order (sortOnFirstBDCoordinate) with chromosome indices of pg_set_reference");
+   const size_t m = P.start.size();
+   int rc;
+   if ((rc = ensure(ctx, ctx->bk_start, sizeof(uint32_t) * (m + 1))) != PG_OK) return rc;
+   if ((rc = ensure(ctx, ctx->bk_drop, sizeof(uint32_t) * (m + 1))) != PG_OK) return rc;
+   if ((rc = ensure(ctx, ctx->bk_sel, sizeof(PgBdSel) * (m + 1))) != PG_OK) return rc;
+   CU(cudaStreamSynchronize(ctx->stream));          // a launch may still read the previous region
+   if (m) {
+      CU(cudaMemcpy(ctx->bk_start.p, P.start.data(), sizeof(uint32_t) * m, cudaMemcpyHostToDevice));
+      CU(cudaMemcpy(ctx->bk_drop.p, P.drop.data(), sizeof(uint32_t) * m, cudaMemcpyHostToDevice));
+      CU(cudaMemcpy(ctx->bk_sel.p, P.sel.data(), sizeof(PgBdSel) * m, cudaMemcpyHostToDevice));
+   }
+   ctx->bk_view.start = (const uint32_t *)ctx->bk_start.p;
+   ctx->bk_view.drop = (const uint32_t *)ctx->bk_drop.p;
+   ctx->bk_view.sel = (const PgBdSel *)ctx->bk_sel.p;
+   ctx->bk_view.m = (uint32_t)m; ctx->bk_view.z = P.z; ctx->bk_view.ws = P.ws; ctx->bk_view.we = P.we;
+   ctx->bk_loaded = true;
+   return PG_OK;
+}
+
+int pg_bd_unload(pg_ctx *ctx)
+{
+   if (!ctx) return PG_ERR_ARG;
+   ctx->bk_loaded = false;
+   return PG_OK;
+}
+
+int pg_bd_clusters(pg_ctx *ctx, uint32_t n, const uint32_t *close_last_abs_loc, uint32_t *region_off, pg_region *regions, uint64_t cap, uint64_t *n_regions)
+{
+   if (!ctx || !n_regions || (n && (!close_last_abs_loc || !region_off))) return fail(ctx, PG_ERR_ARG, "pg_bd_clusters: null argument");
+   if (!ctx->bk_loaded) return fail(ctx, PG_ERR_STATE, "pg_bd_clusters: no region loaded (pg_bd_load_region)");
+   *n_regions = 0;
+   if (n == 0) return PG_OK;
+   CU(cudaSetDevice(ctx->device));
+   int rc;
+   if ((rc = ensure(ctx, ctx->bk_pos, sizeof(uint32_t) * (size_t)n)) != PG_OK) return rc;
+   CU(cudaMemcpyAsync(ctx->bk_pos.p, close_last_abs_loc, sizeof(uint32_t) * (size_t)n, cudaMemcpyHostToDevice, ctx->stream));
+   uint32_t tot = 0;
+   if ((rc = bd_lookup_device(ctx, n, nullptr, (const uint32_t *)ctx->bk_pos.p, &tot)) != PG_OK) return rc;
+   *n_regions = tot;
+   CU(cudaMemcpyAsync(region_off, ctx->bk_region_off.p, sizeof(uint32_t) * ((size_t)n + 1), cudaMemcpyDeviceToHost, ctx->stream));
+   if (tot > cap || (tot && !regions)) {
+      CU(cudaStreamSynchronize(ctx->stream));
+      return fail(ctx, PG_ERR_RUNS_CAP, "pg_bd_clusters: region buffer too small (n_regions holds the required size)");
+   }
+   if (tot) CU(cudaMemcpyAsync(regions, ctx->bk_regions.p, sizeof(PgRegion) * (size_t)tot, cudaMemcpyDeviceToHost, ctx->stream));
+   CU(cudaStreamSynchronize(ctx->stream));
+   return PG_OK;
+}
+
+uint64_t pg_bd_launches(pg_ctx *ctx) { return ctx ? ctx->bk_launches : 0; }
+uint64_t pg_bd_lookups(pg_ctx *ctx) { return ctx ? ctx->bk_lookups : 0; }
 
 // ---- per-box read ordering and duplicate marking (row N4) -----------------------------------------------------------
 static_assert(sizeof(pg_sort_key) == sizeof(PgSortKey) && sizeof(pg_sort_key) == 32, "sort key layout");

@@ -80,6 +80,14 @@ def sim_prefix_bam(demo, tmp_path, env):
     on = not (env.get("PG_BRIDGE_HOST_SR") or env.get("PG_BRIDGE_ZLIB"))
     assert m and (int(m.group(1)) > 0) == on, p.stderr[-300:]
     assert int(m.group(2)) == (0 if (env.get("PG_BRIDGE_SR_UNCHAINED") or not on) else int(m.group(1))), p.stderr[-300:]
+    # rest of row N2: BDData::loadRegion handed the window's events to the library and SearchFarEnds sent no clusters --
+    # pg_far_end looked every read's cluster up on the device (PG_BRIDGE_HOST_BD=1: the reference's mask on the host)
+    m = re.search(r"(\d+) BreakDancer regions \((\d+) events\) loaded into the library, (\d+) cluster lookups there", p.stderr)
+    assert m, p.stderr[-300:]
+    if env.get("PG_BRIDGE_HOST_BD"):
+        assert int(m.group(1)) == 0 and int(m.group(3)) == 0, m.group(0)
+    else:
+        assert int(m.group(1)) > 0 and int(m.group(2)) > 0 and int(m.group(3)) > 0, m.group(0)
     return p
 
 

@@ -19,6 +19,7 @@
 #include "bam_emul.cpp"
 #include "boxsort_emul.cpp"
 #include "sr_emul.cpp"
+#include "bd_emul.cpp"
 #include "../../pindel_b200/csrc/pg_host_helpers.h"
 
 struct pg_ctx {
@@ -36,6 +37,9 @@ struct pg_ctx {
    std::vector<uint32_t> res_off;
    std::vector<int16_t> res_isz;
    std::vector<int32_t> res_chr;
+   PgBdPrepared bd;               // the loaded BreakDancer region (pg_bd_load_region)
+   bool bd_loaded = false;
+   uint64_t bd_lookups = 0;
    std::vector<uint8_t> stream;   // the last inflated stream
    std::vector<PgBamRec> bam_table;   // its record table (pg_bam_index with a buffer)
 };
@@ -95,7 +99,37 @@ int pg_set_reference(pg_ctx *ctx, int32_t n_chr, const char *const *seq, const u
    return PG_OK;
 }
 
+static int run_inner(pg_ctx *ctx, const pg_reads *in, pg_results *res, int mode);
 static int run(pg_ctx *ctx, const pg_reads *in, pg_results *res, int mode)
+{
+   /* a far-end batch without regions takes every read's cluster from the loaded BreakDancer region */
+   if (mode == 2 && ctx->bd_loaded && !(in->regions && in->region_off) && in->close_info && in->n > 0) {
+      PgBdRegionView R;
+      R.start = ctx->bd.start.data(); R.drop = ctx->bd.drop.data(); R.sel = ctx->bd.sel.data(); R.m = (uint32_t)ctx->bd.start.size();
+      R.z = ctx->bd.z; R.ws = ctx->bd.ws; R.we = ctx->bd.we;
+      std::vector<uint32_t> off((size_t)in->n + 1, 0);
+      std::vector<pg_region> reg;
+      for (int i = 0; i < in->n; i++) {
+         off[i] = (uint32_t)reg.size();
+         ctx->bd_lookups++;
+         if (in->close_info[i].max_len == 0) continue;
+         uint32_t S, E;
+         pgbd_range(R, in->close_info[i].last_abs_loc, S, E);
+         if (E > S) {
+            const uint32_t c = pgbd_cluster(R, S, E, NULL, 0);
+            reg.resize(reg.size() + c);
+            pgbd_cluster(R, S, E, reinterpret_cast<PgRegion *>(&reg[off[i]]), c);
+         }
+      }
+      off[in->n] = (uint32_t)reg.size();
+      if (reg.empty()) reg.resize(1);
+      pg_reads in2 = *in;
+      in2.regions = reg.data(); in2.region_off = off.data();
+      return run_inner(ctx, &in2, res, mode);
+   }
+   return run_inner(ctx, in, res, mode);
+}
+static int run_inner(pg_ctx *ctx, const pg_reads *in, pg_results *res, int mode)
 {
    if (ctx->chr.empty()) return fail(ctx, PG_ERR_STATE, "no reference");
    const int n = in->n;
@@ -426,6 +460,35 @@ int pg_bam_sr_close_end(pg_ctx *ctx, const pg_sr_query *q, int32_t chr_id, pg_sr
    if (m) memcpy(refs, rf.data(), sizeof(pg_sr_ref) * m);
    return PG_OK;
 }
+int pg_bd_load_region(pg_ctx *ctx, const pg_bd_event *events, uint32_t n_events, const int32_t *chr_name_rank, int32_t chr, uint32_t start, uint32_t end)
+{
+   ctx->bd_loaded = false;
+   if (pgbd_prepare(reinterpret_cast<const PgBdEvent *>(events), n_events, chr_name_rank, (int32_t)ctx->chr.size(), chr, start, end, ctx->bd) != 0)
+      return fail(ctx, PG_ERR_ARG, "events must be in the reference's order");
+   ctx->bd_loaded = true;
+   return PG_OK;
+}
+int pg_bd_unload(pg_ctx *ctx) { ctx->bd_loaded = false; return PG_OK; }
+int pg_bd_clusters(pg_ctx *ctx, uint32_t n, const uint32_t *close_last_abs_loc, uint32_t *region_off, pg_region *regions, uint64_t cap, uint64_t *n_regions)
+{
+   if (!ctx->bd_loaded) return fail(ctx, PG_ERR_STATE, "no region loaded");
+   PgBdRegionView R;
+   R.start = ctx->bd.start.data(); R.drop = ctx->bd.drop.data(); R.sel = ctx->bd.sel.data(); R.m = (uint32_t)ctx->bd.start.size();
+   R.z = ctx->bd.z; R.ws = ctx->bd.ws; R.we = ctx->bd.we;
+   uint64_t tot = 0;
+   for (uint32_t i = 0; i < n; i++) {
+      uint32_t S, E;
+      region_off[i] = (uint32_t)tot;
+      pgbd_range(R, close_last_abs_loc[i], S, E);
+      if (E > S) tot += pgbd_cluster(R, S, E, (regions && tot < cap) ? reinterpret_cast<PgRegion *>(regions + tot) : NULL, (uint32_t)(cap > tot ? cap - tot : 0));
+   }
+   if (n) region_off[n] = (uint32_t)tot;
+   *n_regions = tot;
+   ctx->bd_lookups += n;
+   return (tot > cap || (tot && !regions)) ? fail(ctx, PG_ERR_RUNS_CAP, "region buffer too small") : PG_OK;
+}
+uint64_t pg_bd_launches(pg_ctx *) { return 0; }
+uint64_t pg_bd_lookups(pg_ctx *ctx) { return ctx ? ctx->bd_lookups : 0; }
 uint64_t pg_classify_launches(pg_ctx *ctx) { return ctx ? ctx->sv_launches : 0; }
 double pg_classify_last_kernel_ms(pg_ctx *) { return 0.0; }
 uint32_t pg_expand_runs(const pg_run *runs, uint32_t n_runs, pg_up *out) { return pgh_expand_runs(runs, n_runs, out); }

@@ -41,6 +41,17 @@ def test_bam_input_scenario_with_the_reference_reader(tmp_path):
     D.sim_prefix_bam(DEMO, tmp_path, dict(os.environ, PG_BRIDGE_HOST_SR="1"))
 
 
+def test_bam_input_scenario_with_the_reference_mask(tmp_path):
+    """The default binds BDData::loadRegion to pg_bd_load_region (clusters looked up inside pg_far_end).  PG_BRIDGE_HOST_BD=1:
+    the reference's own position-by-position mask and getCorrespondingSearchWindowCluster per read -- same files"""
+    D.sim_prefix_bam(DEMO, tmp_path, dict(os.environ, PG_BRIDGE_HOST_BD="1"))
+
+
+def test_bam_input_scenario_over_a_device_group(tmp_path):
+    """PG_BRIDGE_DEVICES=0,0: the BreakDancer region is loaded into every context of the group and each looks its own reads up"""
+    D.sim_prefix_bam(DEMO, tmp_path, dict(os.environ, PG_BRIDGE_DEVICES="0,0", PG_BRIDGE_NO_RESIDENT="1"))
+
+
 def test_text_input_scenario_over_a_device_group(tmp_path):
     """PG_BRIDGE_DEVICES=3: the two batched seams go through pg_group_close_end / pg_group_far_end (reads dealt to three
     contexts, records merged with global run offsets), the classification takes the host arrays -- same files"""
