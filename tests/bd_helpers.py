@@ -40,3 +40,30 @@ def queries(rng, window, n):
     # (src/bddata.cpp:896, :904, :952): close ends at window end + 3000 and + 3001 read garbage there -- not asked
     q = q[(q != we + 3000) & (q != we + 3001)]
     return q.astype(np.uint32)
+
+
+def case(seed, dense, n_queries=600):
+    """-> (chromosome, window, events [n, 6], query positions) of one seeded case"""
+    rng = np.random.default_rng(500 + seed)
+    chr_id = int(rng.integers(0, 3))
+    ws = int(rng.choice([SPACER, SPACER + 500, SPACER + 40_000, 1000, 0]))
+    window = (ws, ws + int(rng.choice([5_000, 20_000, 60_000])))
+    ev = random_events(rng, int(rng.choice([0, 1, 3, 40, 200])) if not dense else 200, chr_id, window, dense)
+    other = random_events(rng, 20, (chr_id + 1) % 3, window)
+    ev = np.concatenate([ev, other])
+    return chr_id, window, ev, queries(rng, window, n_queries)
+
+
+def load_golden():
+    """tests/golden/bd_clusters.npz (written by tests/golden/make_bd_golden.py from the reference itself) ->
+    [(seed, chromosome, window, events, queries, clusters per query)]"""
+    import os
+    z = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "bd_clusters.npz"))
+    out = []
+    for seed in z["seeds"]:
+        chr_id, ws, we = (int(v) for v in z["win_%d" % seed])
+        cnt, reg = z["cnt_%d" % seed], z["reg_%d" % seed]
+        off = np.concatenate([[0], np.cumsum(cnt)])
+        cl = [[(int(c), int(s), int(e)) for c, s, e in reg[off[i]:off[i + 1]]] for i in range(cnt.size)]
+        out.append((int(seed), chr_id, (ws, we), z["ev_%d" % seed].astype(np.int64), z["q_%d" % seed], cl))
+    return out

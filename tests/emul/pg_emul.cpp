@@ -4,6 +4,7 @@
 // fibers and meet at every warp collective (ballot / shfl / redux / syncwarp), so the *same* warp
 // program that the CUDA kernel executes can be checked against the oracle on a machine without a
 // GPU (pytest -m "not gpu").  Never linked into libpindel_pg.so.
+#include <cstddef>
 #include <assert.h>
 #include <stdint.h>
 #include <stdio.h>
@@ -229,6 +230,8 @@ int pgemu_sizes(int which)
    case 2: return (int)sizeof(PgReadOut);
    case 3: return (int)sizeof(PgRegion);
    case 4: return (int)sizeof(PgCloseInfo);
+   case 5: return (int)offsetof(PgParams, g);
+   case 6: return (int)offsetof(PgParams, thr);
    default: return -1;
    }
 }

@@ -1,12 +1,10 @@
 """The device formulation of the BreakDancer mask (pg_bd.cuh: two binary searches per read over the window-start array and the
 prefix-maximum drop array, the cluster built per read) in its host build, against the oracle's position-by-position sweep
-(pinned to the reference by test_bd_oracle_pinning.py) and, where the reference library is built, against the reference live."""
-import os
-
+(pinned to the reference by test_bd_oracle_pinning.py) and against the committed outputs of the reference itself."""
 import numpy as np
 import pytest
 
-from oracle import bdoracle, refhook
+from oracle import bdoracle
 from tests import bd_helpers as B
 from tests.emul import bd_emul
 
@@ -16,15 +14,7 @@ def lib():
     return bd_emul.build()
 
 
-def case(seed, dense):
-    rng = np.random.default_rng(500 + seed)
-    chr_id = int(rng.integers(0, 3))
-    ws = int(rng.choice([B.SPACER, B.SPACER + 500, B.SPACER + 40_000, 1000, 0]))
-    window = (ws, ws + int(rng.choice([5_000, 20_000, 60_000])))
-    ev = B.random_events(rng, int(rng.choice([0, 1, 3, 40, 200])) if not dense else 200, chr_id, window, dense)
-    other = B.random_events(rng, 20, (chr_id + 1) % 3, window)
-    ev = np.concatenate([ev, other])
-    return chr_id, window, ev, B.queries(rng, window, 600)
+case = B.case
 
 
 @pytest.mark.parametrize("seed,dense", [(s, s % 3 == 0) for s in range(1, 25)])
@@ -50,19 +40,11 @@ def test_unnormalised_positions_and_unsorted_block(lib):
         bd_emul.clusters(lib, ev[::-1], B.NAMES, 0, 110000, 130000, [120100])
 
 
-@pytest.mark.skipif(not refhook.available(), reason="oracle/_ref/libpindel_ref.so not built")
-def test_closed_form_equals_reference_live(lib, tmp_path):
-    rng = np.random.default_rng(5)
-    fa = os.path.join(tmp_path, "g.fa")
-    refhook.write_fasta(fa, [(n, rng.choice(np.frombuffer(b"ACGT", dtype=np.uint8), l)) for n, l in zip(B.NAMES, B.LENS)])
-    hook = refhook.RefHook(fa, [], workdir=str(tmp_path))
-    for seed in range(30, 40):
-        chr_id, window, ev, q = case(seed, seed % 2 == 0)
-        exp = bdoracle.reference_clusters(hook, ev, chr_id, window[0], window[1], q)
-        ev_sorted = np.array(bdoracle.sort_on_first(bdoracle.normalise(ev), B.NAMES), dtype=np.int64).reshape(-1, 6)
-        got = bd_emul.clusters(lib, ev_sorted, B.NAMES, chr_id, window[0], window[1], q)
-        we = window[1] + 3000
-        for k, (e, g) in enumerate(zip(exp, got)):
-            if q[k] >= we:
-                continue
-            assert e == g, (seed, k, int(q[k]), e, g)
+@pytest.mark.parametrize("k", range(len(B.load_golden())))
+def test_closed_form_equals_reference_outputs(lib, k):
+    """the committed outputs of the reference's own loadRegion / getCorrespondingSearchWindowCluster (tests/golden/bd_clusters.npz)"""
+    seed, chr_id, window, ev, q, exp = B.load_golden()[k]
+    ev_sorted = np.array(bdoracle.sort_on_first(bdoracle.normalise(ev), B.NAMES), dtype=np.int64).reshape(-1, 6)
+    got = bd_emul.clusters(lib, ev_sorted, B.NAMES, chr_id, window[0], window[1], q)
+    for i, (e, g) in enumerate(zip(exp, got)):
+        assert e == g, (seed, i, int(q[i]), e, g)

@@ -53,6 +53,17 @@ def test_clusters_equal_oracle(pg3, seed):
     pg3.bd_unload()
 
 
+@pytest.mark.parametrize("k", range(len(B.load_golden())))
+def test_clusters_equal_reference_outputs(pg3, k):
+    """the committed outputs of the reference's own loadRegion / getCorrespondingSearchWindowCluster (tests/golden/bd_clusters.npz)"""
+    seed, chr_id, window, ev, q, exp = B.load_golden()[k]
+    pg3.bd_load_region(sorted_events(ev, B.NAMES), name_ranks(B.NAMES), chr_id, window[0], window[1])
+    got = as_lists(*pg3.bd_clusters(q))
+    for i, (e, g) in enumerate(zip(exp, got)):
+        assert e == g, (seed, i, int(q[i]), e, g)
+    pg3.bd_unload()
+
+
 def test_load_region_rejects_unsorted_events_and_lookup_without_region(pg3):
     ev = np.array([[0, 121000, 121000, 1, 140000, 140000], [0, 120000, 120300, 0, 150000, 150500]], dtype=np.int64)
     with pytest.raises(api.PgError):

@@ -15,8 +15,9 @@ def lib():
 
 def tables(lib, **kw):
     blob = emul.make_params(lib, **kw)
-    g = np.frombuffer(blob.tobytes()[16:16 + 512], dtype=np.uint8)
-    thr = np.frombuffer(blob.tobytes()[16 + 512:16 + 512 + 1024], dtype=np.uint16)
+    og, ot = lib.pgemu_sizes(5), lib.pgemu_sizes(6)          # offsetof(PgParams, g / thr)
+    g = np.frombuffer(blob.tobytes()[og:og + 512], dtype=np.uint8)
+    thr = np.frombuffer(blob.tobytes()[ot:ot + 1024], dtype=np.uint16)
     return g, thr
 
 
