@@ -485,17 +485,37 @@ double pg_bgzf_last_kernel_ms(pg_ctx *ctx);
  * at position k afterwards; nonunique[box_off[b] + k] = 1 when that read's UniqueRead is false afterwards.
  * keys: one per member, in box order; all reads of a call on one chromosome (smaller() compares FragName first; the caller
  * keeps boxes with mixed FragNames on the host).  name_id: equal <=> equal Name.
+ *
+ * pg_box_sort_kind: the same for every reporter.  The DI and inversion reporters carry the two loops inlined with their own
+ * rules (SortOutputDI, src/reporter.cpp:1728-1775; OutputSorter::DoSortAndOutputInversions, src/output_sorter.cpp:74-131): a
+ * STRICT exchange (equal reads are not swapped) under another comparator, and a duplicate scan on LeftMostPos / read end /
+ * anchor strand from every first read.  For those kinds `left` carries LeftMostPos, and read_length / matched_d are read.
+ * event (may be NULL): the cut of the surviving reads into events that every reporter makes next (the "event merge",
+ * src/reporter.cpp:1016-1034, 1206-1236, 1446-1487, 1790-1813, src/output_sorter.cpp:149-205): per position of the final
+ * order PG_BOX_EVENT_GOOD when that read enters GoodIndels (unique reads; every read for the inversion kinds) and
+ * PG_BOX_EVENT_START when the reporter's event key changes there (D / TD: BPLeft, BPRight; SI: BPLeft, IndelSize; DI: BPLeft,
+ * IndelSize, NT_size; INV: BPLeft + BPRight).  pg_box_sort = pg_box_sort_kind(PG_BOX_D, ..., NULL).
  * ------------------------------------------------------------------------------------------------------------------ */
 typedef struct pg_sort_key {
    uint32_t bp_left, bp_right, indel_size;   /* BPLeft, BPRight, IndelSize */
-   int32_t left, right;                      /* Left, Right */
+   int32_t left, right;                      /* Left, Right (PG_BOX_D / _SI); LeftMostPos in `left` for the other kinds */
    uint32_t name_id;
    uint16_t nt_size;                         /* NT_size */
    int16_t bp;                               /* BP */
    uint8_t unique;                           /* UniqueRead on entry */
-   uint8_t pad[3];
+   uint8_t matched_d;                        /* MatchedD ('+' / '-'); PG_BOX_DI and the inversion kinds */
+   uint16_t read_length;                     /* getReadLength(); PG_BOX_DI and the inversion kinds */
 } pg_sort_key;
+enum { PG_BOX_D = 0,        /* SortOutputD, SortAndOutputTandemDuplications */
+       PG_BOX_SI = 1,       /* SortOutputSI */
+       PG_BOX_DI = 2,       /* SortOutputDI */
+       PG_BOX_INV = 3,      /* OutputSorter::SortAndOutputInversions */
+       PG_BOX_INV_NT = 4 }; /* OutputSorter::SortAndOutputNonTemplateInversions */
+#define PG_BOX_EVENT_GOOD 1u
+#define PG_BOX_EVENT_START 2u
 int pg_box_sort(pg_ctx *ctx, uint32_t n_boxes, const uint32_t *box_off, const pg_sort_key *keys, uint32_t *order, uint8_t *nonunique);
+int pg_box_sort_kind(pg_ctx *ctx, int32_t kind, uint32_t n_boxes, const uint32_t *box_off, const pg_sort_key *keys, uint32_t *order, uint8_t *nonunique,
+                     uint8_t *event);
 uint64_t pg_box_sort_launches(pg_ctx *ctx);
 double pg_box_sort_last_kernel_ms(pg_ctx *ctx);
 

@@ -11,7 +11,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 _lib = None
 
 KEY_DT = np.dtype([("bp_left", "<u4"), ("bp_right", "<u4"), ("indel_size", "<u4"), ("left", "<i4"), ("right", "<i4"), ("name_id", "<u4"),
-                   ("nt_size", "<u2"), ("bp", "<i2"), ("unique", "u1"), ("pad", "u1", 3)])
+                   ("nt_size", "<u2"), ("bp", "<i2"), ("unique", "u1"), ("matched_d", "u1"), ("read_length", "<u2")])
 assert KEY_DT.itemsize == 32
 
 
@@ -34,6 +34,64 @@ def sort_boxes(reads: np.ndarray, box_off: np.ndarray, idx: np.ndarray):
         a, e = int(box_off[b]), int(box_off[b + 1])
         lib().bso_box(reads.ctypes.data_as(C.c_void_p), unique.ctypes.data_as(C.c_void_p), C.c_void_p(idx.ctypes.data + 4 * a), C.c_uint32(e - a))
     return idx, unique
+
+
+def sort_boxes_kind(kind: int, reads: np.ndarray, box_off: np.ndarray, idx: np.ndarray):
+    """The loops of one reporter (0 D / TD, 1 SI, 2 DI, 3 INV, 4 INV_NT) -> (idx reordered per box, UniqueRead per read,
+    event flags per position of the final order)"""
+    reads = np.ascontiguousarray(reads, dtype=KEY_DT)
+    idx = np.ascontiguousarray(idx, dtype=np.uint32).copy()
+    unique = reads["unique"].copy()
+    event = np.zeros(idx.size, dtype=np.uint8)
+    for b in range(len(box_off) - 1):
+        a, e = int(box_off[b]), int(box_off[b + 1])
+        lib().bso_box_kind(reads.ctypes.data_as(C.c_void_p), unique.ctypes.data_as(C.c_void_p), C.c_void_p(idx.ctypes.data + 4 * a), C.c_uint32(e - a),
+                           C.c_int(kind), C.c_void_p(event.ctypes.data + a))
+    return idx, unique, event
+
+
+def make_boxes_kind(kind: int, n_boxes: int, seed: int, max_reads: int = 40, heavy: int = 0):
+    """Boxes for the DI / inversion loops: events with a few breakpoint pairs per box -- for the inversion kinds several pairs
+    with the same BPLeft + BPRight and different sizes --, fragments seen twice (same LeftMostPos or same end, same anchor
+    strand), reads of different lengths, reads already marked non-unique; (box members share every key in large groups).
+    -> (reads KEY_DT, box_off, idx)"""
+    rng = np.random.default_rng(seed)
+    rows, box_off, idx = [], [0], []
+    for b in range(n_boxes):
+        n = int(rng.integers(2, max_reads + 1)) if b >= heavy else int(rng.integers(150, 400))
+        base = 100_000 + 20_000 * b
+        events = []
+        for _ in range(int(rng.integers(1, 4))):
+            bl, size = base + int(rng.integers(0, 2000)), int(rng.integers(1, 300))
+            events.append((bl, bl + size, size, int(rng.integers(0, 4))))
+            if kind >= 3 and rng.random() < 0.6:          # same centre, smaller span: one event for the inversion reporters
+                d = int(rng.integers(1, 6))
+                events.append((bl + d, bl + size - d, size - 2 * d if size > 2 * d else size, int(rng.integers(0, 4))))
+        members = []
+        for _ in range(n):
+            bl, br, size, nt = events[int(rng.integers(0, len(events)))]
+            bp = int(rng.integers(20, 26)) if rng.random() < 0.7 else int(rng.integers(5, 90))
+            rl = int(rng.choice([100, 100, 100, 101, 75]))
+            md = int(rng.choice([43, 45]))
+            lmp = bl - bp + int(rng.integers(0, 3))
+            if rng.random() < 0.2 and members:            # the same fragment again: same start (or same end), usually same strand
+                src = rows[members[int(rng.integers(0, len(members)))]]
+                lmp, rl = src[3], src[10]
+                if rng.random() < 0.3:
+                    rl2 = int(rng.choice([100, 101, 75]))
+                    lmp, rl = lmp + rl - rl2, rl2          # same end, other length
+                if rng.random() < 0.8:
+                    md = src[9]
+            row = [bl, br, size, lmp, 0, 0, nt, bp, 0 if rng.random() < 0.05 else 1, md, rl]
+            members.append(len(rows))
+            rows.append(tuple(row))
+        order = rng.permutation(len(members))
+        idx += [members[k] for k in order]
+        box_off.append(len(idx))
+    reads = np.zeros(len(rows), dtype=KEY_DT)
+    for k, r in enumerate(rows):
+        reads[k] = r
+    return reads, np.array(box_off, dtype=np.uint32), np.array(idx, dtype=np.uint32)
 
 
 def reference_sort_boxes(reads: np.ndarray, box_off: np.ndarray, idx: np.ndarray):
@@ -87,5 +145,5 @@ def make_boxes(n_boxes: int, seed: int, max_reads: int = 40, heavy: int = 0):
         box_off.append(len(idx))
     reads = np.zeros(len(rows), dtype=KEY_DT)
     for k, r in enumerate(rows):
-        reads[k] = (r[0], r[1], r[2], r[3], r[4], r[5], r[6], r[7], r[8], (0, 0, 0))
+        reads[k] = (r[0], r[1], r[2], r[3], r[4], r[5], r[6], r[7], r[8], 0, 0)
     return reads, np.array(box_off, dtype=np.uint32), np.array(idx, dtype=np.uint32)

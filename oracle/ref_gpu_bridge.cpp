@@ -909,6 +909,172 @@ void markDuplicates(std::vector<SPLIT_READ> &Reads, const std::vector<unsigned> 
    original(Reads, VariantIndices);
 }
 
+/* ---------------------------------------------------------------------------------------------------------------------
+ * Row N4, the rest: the DI and inversion reporters carry the ordering and the duplicate scan INLINED, with their own rules
+ * (SortOutputDI, src/reporter.cpp:1709-1851; OutputSorter::DoSortAndOutputInversions, src/output_sorter.cpp:62-260), so
+ * there is no function to bind: the two reporters are supplied here.  Ordering, duplicate marks and the cut of the
+ * surviving reads into events come from ONE pg_box_sort_kind call for all boxes of the driver; what follows per event --
+ * the inversion reporter's adjustment of the breakpoints to the largest member, the report / balance decisions, the text --
+ * is the reference's per-event logic and its own output functions (ReportEvent, IsInversion, OutputDI, OutputShortInversion,
+ * OutputSorter::ReportIndelEvents).  PG_BRIDGE_HOST_SORT=1: the reference's two functions run (dlsym(RTLD_NEXT)).
+ * ------------------------------------------------------------------------------------------------------------------- */
+#include "output_file_data.h"
+#include "output_sorter.h"
+extern OutputFileData deletionFileData;
+bool IsInversion(const SPLIT_READ &read, const std::string &chromosome);                                     /* src/reporter.cpp:1698 */
+bool IsGoodDeletion(std::vector<SPLIT_READ> &GoodIndels, Indel4output &OneIndelEvent, unsigned RealStart, unsigned RealEnd, ControlState &currentState);
+void OutputDI(std::vector<SPLIT_READ> &DI, const std::string &TheInput, const unsigned int &C_S, const unsigned int &C_E, const unsigned int &RealStart,
+              const unsigned int &RealEnd, std::ofstream &DeletionOutf);
+void OutputShortInversion(std::vector<SPLIT_READ> &supportingReads, const std::string &chromosome, const unsigned int &indexOfFirstRead,
+                          const unsigned int &indexOfLastRead, const unsigned int &RealStart, const unsigned int &RealEnd, std::ofstream &InversionOutF);
+namespace {
+unsigned long g_boxes_inlined = 0;      /* boxes of the DI / inversion reporters ordered on the device */
+struct OrderedBox {
+   unsigned box;
+   std::vector<unsigned> reads;         /* the box's reads in their final order */
+   std::vector<uint8_t> event;          /* PG_BOX_EVENT_* per position */
+};
+/* every box the reporter would process, through the device; the reporter's side effects on its inputs are applied here:
+ * the box's new order and the UniqueRead marks (later drivers read them) */
+void orderBoxes(int kind, std::vector<SPLIT_READ> &Reads, std::vector<unsigned> Vars[], unsigned NumBoxes, std::vector<OrderedBox> &out)
+{
+   std::lock_guard<std::mutex> lock(g_mutex);
+   ensureContext();
+   std::vector<uint32_t> boxOff(1, 0);
+   std::vector<pg_sort_key> keys;
+   for (unsigned b = 0; b < NumBoxes; b++) {
+      const std::vector<unsigned> &v = Vars[b];
+      if (v.size() < userSettings->NumRead2ReportCutOff || v.empty()) continue;
+      for (size_t k = 0; k < v.size(); k++) {
+         const SPLIT_READ &r = Reads[v[k]];
+         pg_sort_key key;
+         memset(&key, 0, sizeof key);
+         key.bp_left = r.BPLeft; key.bp_right = r.BPRight; key.indel_size = r.IndelSize; key.nt_size = r.NT_size; key.bp = r.BP;
+         key.left = (int32_t)r.LeftMostPos; key.read_length = (uint16_t)r.getReadLength(); key.matched_d = (uint8_t)r.MatchedD;
+         key.unique = r.UniqueRead ? 1 : 0;
+         keys.push_back(key);
+      }
+      OrderedBox ob;
+      ob.box = b;
+      out.push_back(ob);
+      boxOff.push_back((uint32_t)keys.size());
+   }
+   if (out.empty()) return;
+   std::vector<uint32_t> order(keys.size());
+   std::vector<uint8_t> non(keys.size()), event(keys.size());
+   { Tick tk(t_box_lib); if (pg_box_sort_kind(g_ctx, kind, (uint32_t)out.size(), &boxOff[0], &keys[0], &order[0], &non[0], &event[0]) != PG_OK) die("pg_box_sort_kind"); }
+   for (size_t i = 0; i < out.size(); i++) {
+      std::vector<unsigned> &v = Vars[out[i].box];
+      for (uint32_t k = boxOff[i]; k < boxOff[i + 1]; k++) {
+         out[i].reads.push_back(v[order[k]]);
+         out[i].event.push_back(event[k]);
+         if (non[k]) Reads[v[order[k]]].UniqueRead = false;
+      }
+      v = out[i].reads;
+      g_boxes_inlined++;
+   }
+}
+/* GoodIndels and the events' index ranges in it, from the device's flags */
+void goodReadsAndEvents(const std::vector<SPLIT_READ> &Reads, const OrderedBox &ob, std::vector<SPLIT_READ> &good, std::vector<std::pair<unsigned, unsigned> > &events)
+{
+   good.clear();
+   events.clear();
+   for (size_t k = 0; k < ob.reads.size(); k++) {
+      if (!(ob.event[k] & PG_BOX_EVENT_GOOD)) continue;
+      if (ob.event[k] & PG_BOX_EVENT_START) events.push_back(std::make_pair((unsigned)good.size(), (unsigned)good.size()));
+      else events.back().second = (unsigned)good.size();
+      good.push_back(Reads[ob.reads[k]]);
+   }
+}
+} // namespace
+
+void SortOutputDI(ControlState &currentState, const unsigned &NumBoxes, const std::string &CurrentChr, std::vector<SPLIT_READ> &Reads, std::vector<unsigned> DI[],
+                  std::ofstream &DIOutf, std::ofstream &InvOutf)
+{
+   if (getenv("PG_BRIDGE_HOST_SORT")) {
+      typedef void (*Fn)(ControlState &, const unsigned &, const std::string &, std::vector<SPLIT_READ> &, std::vector<unsigned>[], std::ofstream &, std::ofstream &);
+      static Fn original = (Fn)dlsym(RTLD_NEXT, "_Z12SortOutputDIR12ControlStateRKjRKNSt7__cxx1112basic_stringIcSt11char_traitsIcESaIcEEERSt6vectorI10SPLIT_READSaISC_EEPSB_IjSaIjEERSt14basic_ofstreamIcS6_ESL_");
+      if (!original) { std::fprintf(stderr, "pindel_gpu_demo: the reference's SortOutputDI was not found\n"); std::exit(EXIT_FAILURE); }
+      original(currentState, NumBoxes, CurrentChr, Reads, DI, DIOutf, InvOutf);
+      return;
+   }
+   LOG_INFO(*logStream << "Sorting and outputing deletions with non-template sequences ..." << std::endl);
+   std::cout << "Added: Sorting and outputing deletions with non-template sequences ..." << std::endl;      /* src/reporter.cpp:1715 */
+   std::vector<OrderedBox> boxes;
+   orderBoxes(PG_BOX_DI, Reads, DI, NumBoxes, boxes);
+   std::vector<SPLIT_READ> good;
+   std::vector<std::pair<unsigned, unsigned> > events;
+   for (size_t i = 0; i < boxes.size(); i++) {
+      goodReadsAndEvents(Reads, boxes[i], good, events);
+      for (size_t e = 0; e < events.size(); e++) {
+         const unsigned first = events[e].first, last = events[e].second;
+         if (last - first + 1 < userSettings->NumRead2ReportCutOff) continue;                                /* :1821 */
+         const SPLIT_READ &lead = good[first];
+         if (!(lead.IndelSize < userSettings->BalanceCutoff || ReportEvent(good, first, last))) continue;   /* :1824-1825 */
+         unsigned int realStart = lead.BPLeft, realEnd = lead.BPRight;
+         if (IsInversion(lead, CurrentChr)) {
+            OutputShortInversion(good, CurrentChr, first, last, realStart, realEnd, InvOutf);
+         } else {
+            Indel4output ev;             /* as the reference's walk leaves it (:1790-1812): BPRight stays the box's first */
+            ev.ChrName = lead.FragName; ev.Start = first; ev.End = last; ev.IndelSize = lead.IndelSize; ev.NT_size = lead.NT_size;
+            ev.BPLeft = lead.BPLeft; ev.BPRight = good[0].BPRight; ev.WhetherReport = true;
+            if (IsGoodDeletion(good, ev, realStart, realEnd, currentState)) {
+               OutputDI(good, CurrentChr, first, last, realStart, realEnd, DIOutf);
+               deletionFileData.increaseNonTemplateSvCounter();
+            }
+         }
+      }
+   }
+   LOG_INFO(*logStream << "deletions with non-template sequences: " << deletionFileData.getNonTemplateSvCounter() << std::endl << std::endl);
+}
+
+int OutputSorter::DoSortAndOutputInversions(ControlState &currentState, std::vector<SPLIT_READ> &Reads, std::vector<unsigned> Inv[], bool isNonTemplateInversion)
+{
+   if (getenv("PG_BRIDGE_HOST_SORT")) {
+      typedef int (*Fn)(OutputSorter *, ControlState &, std::vector<SPLIT_READ> &, std::vector<unsigned>[], bool);
+      static Fn original = (Fn)dlsym(RTLD_NEXT, "_ZN12OutputSorter25DoSortAndOutputInversionsER12ControlStateRSt6vectorI10SPLIT_READSaIS3_EEPS2_IjSaIjEEb");
+      if (!original) { std::fprintf(stderr, "pindel_gpu_demo: the reference's DoSortAndOutputInversions was not found\n"); std::exit(EXIT_FAILURE); }
+      return original(this, currentState, Reads, Inv, isNonTemplateInversion);
+   }
+   int reported = 0;
+   std::vector<OrderedBox> boxes;
+   orderBoxes(isNonTemplateInversion ? PG_BOX_INV_NT : PG_BOX_INV, Reads, Inv, NumBoxes, boxes);
+   std::vector<SPLIT_READ> good;
+   std::vector<std::pair<unsigned, unsigned> > events;
+   std::vector<Indel4output> indelEvents;
+   for (size_t i = 0; i < boxes.size(); i++) {
+      goodReadsAndEvents(Reads, boxes[i], good, events);          /* every read of the box is "good" here (src/output_sorter.cpp:134-137) */
+      indelEvents.clear();
+      bool report = true;               /* OneIndelEvent.WhetherReport: set once per box, never set back (:148) */
+      for (size_t e = 0; e < events.size(); e++) {
+         const unsigned first = events[e].first, last = events[e].second;
+         Indel4output ev;
+         ev.Start = first; ev.End = last;
+         ev.BPLeft = good[first].BPLeft; ev.BPRight = good[first].BPRight;       /* before the adjustment below */
+         /* the members take the breakpoints of the largest one (:159-189, :209-236) */
+         unsigned maxSize = 0;
+         for (unsigned k = first; k <= last; k++) if (good[k].IndelSize > maxSize) maxSize = good[k].IndelSize;
+         for (unsigned k = first; k <= last; k++) {
+            SPLIT_READ &r = good[k];
+            if (r.IndelSize / (float)maxSize < 0.95 || maxSize + 30 > r.getReadLength() + r.IndelSize) { report = false; break; }
+            const short diff = (maxSize - r.IndelSize) / 2;
+            r.IndelSize = maxSize;
+            r.BPLeft = r.BPLeft - diff;
+            r.BPRight = r.BPRight + diff;
+            if (r.MatchedD == '+') { if (r.BP > diff) r.BP = r.BP - diff; }
+            else if (r.BP + diff < r.getReadLengthMinus()) r.BP = r.BP + diff;
+         }
+         if (e + 1 < events.size()) { ev.RealStart = good[first].BPLeft; ev.RealEnd = good[first].BPRight; }   /* :190-191: after the adjustment */
+         else { ev.RealStart = ev.BPLeft; ev.RealEnd = ev.BPRight; }                                          /* :237-238: the box's last event keeps its own */
+         ev.Support = last - first + 1;
+         ev.WhetherReport = report;
+         if (report) indelEvents.push_back(ev);
+      }
+      if (!indelEvents.empty()) reported += ReportIndelEvents(currentState, indelEvents, good);
+   }
+   return reported;
+}
+
 int SearchVariant::Search(BDData &bdData, ControlState &currentState, const unsigned NumBoxes, const SearchWindow &window)
 {
    std::vector<unsigned> *Vars = new std::vector<unsigned>[NumBoxes];
@@ -1275,11 +1441,11 @@ static void reportAtExit()
                 t_inflate_lib.s, t_inflate_lib.n, t_index_lib.s, t_index_lib.n, t_rpd_lib.s, t_rpd_lib.n, t_sr_lib.s, t_sr_lib.n, t_bd_lib.s, t_bd_lib.n, host, t_close_marshal.s, t_close_apply.s,
                 t_far_marshal.s, t_far_apply.s, t_sv_total.s - t_sv_lib.s, t_sr_host.s, wall - t_setup.s - lib - host);
    std::fprintf(stderr, "pindel_gpu_demo: %lu GetCloseEnd calls and %lu far-end reads served by libpindel_pg (%llu kernel launches); "
-                "%lu reads classified by the SV drivers on the device, %lu records (%llu launches), %lu of the reads without a second upload; %lu read pairs clustered on the device (%llu launches); %lu BAM bytes inflated and %lu records indexed on the device, %lu discordant pairs found there; %lu boxes ordered on the device (%llu launches), %lu by the reference; %lu split-read candidates from the device filter, %lu of them searched where the filter left them; %lu BreakDancer regions (%lu events) loaded into the library, %llu cluster lookups there\n",
+                "%lu reads classified by the SV drivers on the device, %lu records (%llu launches), %lu of the reads without a second upload; %lu read pairs clustered on the device (%llu launches); %lu BAM bytes inflated and %lu records indexed on the device, %lu discordant pairs found there; %lu boxes ordered on the device (%llu launches), %lu by the reference, %lu boxes of the DI / inversion reporters ordered and cut into events there; %lu split-read candidates from the device filter, %lu of them searched where the filter left them; %lu BreakDancer regions (%lu events) loaded into the library, %llu cluster lookups there\n",
                 g_close_calls, g_far_reads, g_ctx ? (unsigned long long)pg_kernel_launches(g_ctx) : 0ull, g_sv_reads, g_sv_records,
                 g_ctx ? (unsigned long long)pg_classify_launches(g_ctx) : 0ull, g_sv_resident, g_rp_rows,
                 g_ctx ? (unsigned long long)pg_rp_launches(g_ctx) : 0ull, g_bgzf_bytes, g_bam_records, g_rpd_rows, g_boxes_sorted,
-                g_ctx ? (unsigned long long)pg_box_sort_launches(g_ctx) : 0ull, g_boxes_host, g_sr_candidates, g_sr_searched, g_bd_regions, g_bd_events, g_ctx ? (unsigned long long)pg_bd_lookups(g_ctx) : 0ull);
+                g_ctx ? (unsigned long long)pg_box_sort_launches(g_ctx) : 0ull, g_boxes_host, g_boxes_inlined, g_sr_candidates, g_sr_searched, g_bd_regions, g_bd_events, g_ctx ? (unsigned long long)pg_bd_lookups(g_ctx) : 0ull);
 }
 
 int main(int argc, char *argv[])

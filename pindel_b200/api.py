@@ -114,6 +114,7 @@ def load_library() -> C.CDLL:
         lib.pg_bam_last_segments.restype = None
         lib.pg_bam_last_segments.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
         lib.pg_box_sort.argtypes = [C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+        lib.pg_box_sort_kind.argtypes = [C.c_void_p, C.c_int32, C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
         lib.pg_box_sort_launches.restype = C.c_uint64
         lib.pg_box_sort_launches.argtypes = [C.c_void_p]
         lib.pg_box_sort_last_kernel_ms.restype = C.c_double
@@ -554,6 +555,19 @@ class PatternGrowth:
         vp = lambda a: a.ctypes.data_as(C.c_void_p) if a.size else None
         self._check(self.lib.pg_box_sort(self.ctx, box_off.size - 1, vp(box_off), vp(keys), vp(order), vp(non)), "pg_box_sort")
         return order, non
+
+    def box_sort_kind(self, kind: int, member_keys: np.ndarray, box_off: np.ndarray):
+        """The ordering, duplicate marks and event cut of one reporter (include/pindel_pg.h PG_BOX_*) for all boxes at once.
+        -> (order within each box, nonunique per sorted position, event flags per sorted position)"""
+        keys = np.ascontiguousarray(member_keys)
+        assert keys.dtype.itemsize == 32
+        box_off = np.ascontiguousarray(box_off, dtype=np.uint32)
+        order = np.zeros(keys.size, dtype=np.uint32)
+        non = np.zeros(keys.size, dtype=np.uint8)
+        ev = np.zeros(keys.size, dtype=np.uint8)
+        vp = lambda a: a.ctypes.data_as(C.c_void_p) if a.size else None
+        self._check(self.lib.pg_box_sort_kind(self.ctx, kind, box_off.size - 1, vp(box_off), vp(keys), vp(order), vp(non), vp(ev)), "pg_box_sort_kind")
+        return order, non, ev
 
     @property
     def box_sort_last_kernel_ms(self) -> float:

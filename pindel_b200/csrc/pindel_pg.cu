@@ -424,7 +424,7 @@ struct pg_ctx {
    bool bk_loaded = false;
    uint64_t bk_launches = 0, bk_lookups = 0;
    // per-box read ordering (pg_box_sort)
-   DevBuf bx_off, bx_keys, bx_order, bx_non;
+   DevBuf bx_off, bx_keys, bx_order, bx_non, bx_event;
    uint64_t bx_launches = 0;
    float bx_last_ms = 0.f;
    // read-pair clustering (pg_rp_modify / pg_rp_summarize)
@@ -597,7 +597,7 @@ void pg_destroy(pg_ctx *ctx)
                        &ctx->sr_seqs, &ctx->sr_refs,
                        &ctx->bx_off, &ctx->bx_keys, &ctx->bx_order, &ctx->bx_non,
                        &ctx->bk_start, &ctx->bk_drop, &ctx->bk_sel, &ctx->bk_counts, &ctx->bk_offsets, &ctx->bk_sums, &ctx->bk_regions, &ctx->bk_region_off,
-                       &ctx->bk_pos, &ctx->bk_over};
+                       &ctx->bk_pos, &ctx->bk_over, &ctx->bx_event};
    for (DevBuf *b : svbufs) if (b->p) cudaFree(b->p);
    pipe_destroy(ctx->pipe);
    if (ctx->chroms_d) cudaFree(ctx->chroms_d);
@@ -2157,10 +2157,20 @@ uint64_t pg_bd_lookups(pg_ctx *ctx) { return ctx ? ctx->bk_lookups : 0; }
 
 // ---- per-box read ordering and duplicate marking (row N4) -----------------------------------------------------------
 static_assert(sizeof(pg_sort_key) == sizeof(PgSortKey) && sizeof(pg_sort_key) == 32, "sort key layout");
+static_assert(offsetof(pg_sort_key, matched_d) == offsetof(PgSortKey, matched_d) && offsetof(pg_sort_key, read_length) == offsetof(PgSortKey, read_length), "sort key layout");
+static_assert((int)PG_BOX_D == (int)PGS_D && (int)PG_BOX_SI == (int)PGS_SI && (int)PG_BOX_DI == (int)PGS_DI && (int)PG_BOX_INV == (int)PGS_INV &&
+              (int)PG_BOX_INV_NT == (int)PGS_INV_NT, "box kinds");
+static_assert(PG_BOX_EVENT_GOOD == PGS_EV_GOOD && PG_BOX_EVENT_START == PGS_EV_START, "event flags");
 
 int pg_box_sort(pg_ctx *ctx, uint32_t n_boxes, const uint32_t *box_off, const pg_sort_key *keys, uint32_t *order, uint8_t *nonunique)
 {
+   return pg_box_sort_kind(ctx, PG_BOX_D, n_boxes, box_off, keys, order, nonunique, nullptr);
+}
+
+int pg_box_sort_kind(pg_ctx *ctx, int32_t kind, uint32_t n_boxes, const uint32_t *box_off, const pg_sort_key *keys, uint32_t *order, uint8_t *nonunique, uint8_t *event)
+{
    if (!ctx || (n_boxes && (!box_off || !order || !nonunique))) return fail(ctx, PG_ERR_ARG, "pg_box_sort: null argument");
+   if (kind < PG_BOX_D || kind > PG_BOX_INV_NT) return fail(ctx, PG_ERR_ARG, "pg_box_sort: unknown kind");
    if (n_boxes == 0) return PG_OK;
    for (uint32_t b = 0; b < n_boxes; b++)
       if (box_off[b + 1] < box_off[b]) return fail(ctx, PG_ERR_ARG, "pg_box_sort: box offsets must be non-decreasing");
@@ -2174,17 +2184,20 @@ int pg_box_sort(pg_ctx *ctx, uint32_t n_boxes, const uint32_t *box_off, const pg
    if ((rc = ensure(ctx, ctx->bx_keys, sizeof(PgSortKey) * total)) != PG_OK) return rc;
    if ((rc = ensure(ctx, ctx->bx_order, sizeof(uint32_t) * total)) != PG_OK) return rc;
    if ((rc = ensure(ctx, ctx->bx_non, total)) != PG_OK) return rc;
+   if (event && (rc = ensure(ctx, ctx->bx_event, total)) != PG_OK) return rc;
    CU(cudaMemcpyAsync(ctx->bx_off.p, box_off, sizeof(uint32_t) * ((size_t)n_boxes + 1), cudaMemcpyHostToDevice, st));
    CU(cudaMemcpyAsync(ctx->bx_keys.p, keys, sizeof(PgSortKey) * total, cudaMemcpyHostToDevice, st));
    if (!ctx->sv_ev0) { CU(cudaEventCreate(&ctx->sv_ev0)); CU(cudaEventCreate(&ctx->sv_ev1)); }
    CU(cudaEventRecord(ctx->sv_ev0, st));
    pg_box_sort_warp_kernel<<<(n_boxes + 7) / 8, 256, 0, st>>>(n_boxes, (const uint32_t *)ctx->bx_off.p, (const PgSortKey *)ctx->bx_keys.p,
-                                                             (uint32_t *)ctx->bx_order.p, (uint8_t *)ctx->bx_non.p);
+                                                             (uint32_t *)ctx->bx_order.p, (uint8_t *)ctx->bx_non.p, (int)kind,
+                                                             event ? (uint8_t *)ctx->bx_event.p : nullptr);
    CU(cudaGetLastError());
    CU(cudaEventRecord(ctx->sv_ev1, st));
    ctx->bx_launches++;
    CU(cudaMemcpyAsync(order, ctx->bx_order.p, sizeof(uint32_t) * total, cudaMemcpyDeviceToHost, st));
    CU(cudaMemcpyAsync(nonunique, ctx->bx_non.p, total, cudaMemcpyDeviceToHost, st));
+   if (event) CU(cudaMemcpyAsync(event, ctx->bx_event.p, total, cudaMemcpyDeviceToHost, st));
    CU(cudaStreamSynchronize(st));
    CU(cudaEventElapsedTime(&ctx->bx_last_ms, ctx->sv_ev0, ctx->sv_ev1));
    return PG_OK;

@@ -28,6 +28,9 @@ def _run(demo, args, env):
         assert int(m.group(1)) == 0 and int(m.group(3)) > 0, m.group(0)
     else:
         assert int(m.group(1)) > 0 and int(m.group(3)) == 0 and int(m.group(2)) <= 8, m.group(0)
+    # ... and the boxes of the DI / inversion reporters (inlined loops: the reporters themselves are bound) by pg_box_sort_kind
+    m = re.search(r"(\d+) boxes of the DI / inversion reporters ordered and cut into events there", p.stderr)
+    assert m and (int(m.group(1)) == 0) == bool(env.get("PG_BRIDGE_HOST_SORT")), p.stderr[-500:]
     return p
 
 
@@ -88,6 +91,33 @@ def sim_prefix_bam(demo, tmp_path, env):
         assert int(m.group(1)) == 0 and int(m.group(3)) == 0, m.group(0)
     else:
         assert int(m.group(1)) > 0 and int(m.group(2)) > 0 and int(m.group(3)) > 0, m.group(0)
+    return p
+
+
+def dense_events_live(demo, tmp_path, env):
+    """Input dense in deletions with non-template bases and inversions (tests/dense_events.py): the reporters whose ordering,
+    duplicate scan and event cut are inlined loops (SortOutputDI, OutputSorter::DoSortAndOutputInversions).  No golden files:
+    the pure reference binary (oracle/_ref/pindel_ref) runs beside the drop-in binary on the same seeded input."""
+    from oracle import refhook
+    from tests import dense_events
+    ref_bin = os.path.join(ROOT, "oracle", "_ref", "pindel_ref")
+    ref, text, n = dense_events.make()
+    fa = str(tmp_path / "dense.fa")
+    refhook.write_fasta(fa, [("dense", ref)])
+    (tmp_path / "dense.fa.fai").write_text("dense\t%d\t7\t60\t61\n" % ref.size)
+    (tmp_path / "reads.txt").write_text(text)
+    args = ["-f", fa, "-p", str(tmp_path / "reads.txt"), "-k", "-s", "-l", "-T", "1"]
+    r = subprocess.run([ref_bin] + args + ["-o", str(tmp_path / "ref")], capture_output=True, text=True, timeout=1800)
+    assert r.returncode == 0, r.stdout[-1000:] + r.stderr[-1000:]
+    p = _run(demo, args + ["-o", str(tmp_path / "dropin")], env)
+    for suf in ("D", "SI", "INV", "TD", "LI", "BP", "CloseEndMapped"):
+        a, b = (tmp_path / ("ref_" + suf)).read_bytes(), (tmp_path / ("dropin_" + suf)).read_bytes()
+        assert a == b, "%s differs from the reference binary's file (%d vs %d bytes)" % (suf, len(b), len(a))
+    d, inv = (tmp_path / "ref_D").read_text(), (tmp_path / "ref_INV").read_text()
+    n_di = len(re.findall(r"\tNT [1-9]", d))
+    assert n_di >= 20 and inv.count("####") >= 30, (n_di, inv.count("####"))
+    m = re.search(r"(\d+) boxes of the DI / inversion reporters", p.stderr)
+    assert env.get("PG_BRIDGE_HOST_SORT") or int(m.group(1)) >= 60, m.group(0)
     return p
 
 

@@ -330,6 +330,13 @@ int pg_box_sort(pg_ctx *ctx, uint32_t n_boxes, const uint32_t *box_off, const pg
    ctx->bx_launches++;
    return PG_OK;
 }
+int pg_box_sort_kind(pg_ctx *ctx, int32_t kind, uint32_t n_boxes, const uint32_t *box_off, const pg_sort_key *keys, uint32_t *order, uint8_t *nonunique, uint8_t *event)
+{
+   /* the kernel's formulation (chunked prefix minima, ballots written out), not the literal loops */
+   boxemu_sort_warp_formulation_kind(kind, n_boxes, box_off, (const PgSortKey *)keys, order, nonunique, event);
+   ctx->bx_launches++;
+   return PG_OK;
+}
 uint64_t pg_box_sort_launches(pg_ctx *ctx) { return ctx ? ctx->bx_launches : 0; }
 int64_t pg_bgzf_inflated_size(const uint8_t *file, size_t file_len) { return bgzfemu_size(file, file_len); }
 int pg_bgzf_inflate(pg_ctx *ctx, const uint8_t *file, size_t file_len, uint8_t *out, size_t out_cap, size_t *out_len, int32_t check_crc)

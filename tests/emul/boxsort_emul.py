@@ -33,3 +33,16 @@ def sort_boxes(lib, member_keys: np.ndarray, box_off: np.ndarray, warp_formulati
     fn = lib.boxemu_sort_warp_formulation if warp_formulation else lib.boxemu_sort
     fn(C.c_uint32(box_off.size - 1), vp(box_off), vp(keys), vp(order), vp(non))
     return order, non
+
+
+def sort_boxes_kind(lib, kind: int, member_keys: np.ndarray, box_off: np.ndarray, warp_formulation: bool = False):
+    """-> (order within each box, nonunique per sorted position, event flags per sorted position)"""
+    keys = np.ascontiguousarray(member_keys, dtype=B.KEY_DT)
+    box_off = np.ascontiguousarray(box_off, dtype=np.uint32)
+    order = np.zeros(keys.size, dtype=np.uint32)
+    non = np.zeros(keys.size, dtype=np.uint8)
+    ev = np.zeros(keys.size, dtype=np.uint8)
+    vp = lambda a: a.ctypes.data_as(C.c_void_p)
+    fn = lib.boxemu_sort_warp_formulation_kind if warp_formulation else lib.boxemu_sort_kind
+    fn(C.c_int(kind), C.c_uint32(box_off.size - 1), vp(box_off), vp(keys), vp(order), vp(non), vp(ev))
+    return order, non, ev

@@ -68,5 +68,16 @@ REF_BIN = os.path.join(ROOT, "oracle", "_ref", "pindel_ref")
 
 
 @pytest.mark.skipif(not os.path.exists(REF_BIN), reason="oracle/_ref/pindel_ref not built")
+def test_dense_di_and_inversion_events_against_the_reference_binary(tmp_path):
+    """row N4, the rest: SortOutputDI and OutputSorter::DoSortAndOutputInversions supplied by the bridge around pg_box_sort_kind"""
+    D.dense_events_live(DEMO, tmp_path, dict(os.environ))
+
+
+@pytest.mark.skipif(not os.path.exists(REF_BIN), reason="oracle/_ref/pindel_ref not built")
+def test_dense_di_and_inversion_events_with_the_reference_reporters(tmp_path):
+    D.dense_events_live(DEMO, tmp_path, dict(os.environ, PG_BRIDGE_HOST_SORT="1", PG_BRIDGE_NO_RESIDENT="1"))
+
+
+@pytest.mark.skipif(not os.path.exists(REF_BIN), reason="oracle/_ref/pindel_ref not built")
 def test_interchromosomal_scenario_against_the_reference_binary(tmp_path):
     D.interchr_live(DEMO, tmp_path, dict(os.environ))

@@ -49,3 +49,26 @@ def test_empty_and_single_read_boxes(pg):
     assert np.array_equal(p_idx, o_idx) and np.array_equal(p_unique, o_unique)
     o, n = pg.box_sort(reads[:0], np.array([0], dtype=np.uint32))
     assert o.size == 0 and n.size == 0
+
+
+@pytest.mark.parametrize("kind", [0, 1, 2, 3, 4])
+def test_every_reporters_loops_match_oracle(pg, kind):
+    """pg_box_sort_kind: ordering, duplicate marks and event cut of the D/TD, SI, DI, INV and INV_NT reporters on a few thousand
+    boxes (three of them with hundreds of reads) against oracle/boxsort_oracle.c's restatement of the reference's loops"""
+    if kind <= 1:
+        reads, box_off, idx = B.make_boxes(3000, 40 + kind, max_reads=40, heavy=3)
+    else:
+        reads, box_off, idx = B.make_boxes_kind(kind, 3000, 40 + kind, max_reads=40, heavy=3)
+    order, non, ev = pg.box_sort_kind(kind, reads[idx], box_off)
+    p_idx, p_unique = H.apply(reads, box_off, idx, order, non)
+    o_idx, o_unique, o_event = B.sort_boxes_kind(kind, reads, box_off, idx)
+    assert np.array_equal(p_idx, o_idx), "order"
+    assert np.array_equal(p_unique, o_unique), "duplicate marks"
+    assert np.array_equal(ev, o_event), "event cut"
+    assert (o_event & 2).sum() > 3000 and (o_unique == 0).sum() > 1000
+
+
+def test_unknown_kind_is_an_error(pg):
+    reads, box_off, idx = B.make_boxes(3, 1)
+    with pytest.raises(api.PgError):
+        pg.box_sort_kind(7, reads[idx], box_off)

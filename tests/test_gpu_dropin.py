@@ -38,6 +38,13 @@ def test_interchromosomal_scenario_against_the_reference_binary(tmp_path):
     D.interchr_live(DEMO, tmp_path, _env())
 
 
+@pytest.mark.skipif(not os.path.exists(os.path.join(ROOT, "oracle", "_ref", "pindel_ref")), reason="oracle/_ref/pindel_ref not built")
+def test_dense_di_and_inversion_events_against_the_reference_binary(tmp_path):
+    """Row N4, the rest: the DI and inversion reporters (inlined ordering / duplicate scan / event cut) supplied around
+    pg_box_sort_kind, on an input dense in those events, the pure reference binary beside the drop-in."""
+    D.dense_events_live(DEMO, tmp_path, _env())
+
+
 def test_reference_host_over_a_device_group(tmp_path):
     """PG_BRIDGE_DEVICES: the two batched seams fan out inside the library (pg_group_close_end / pg_group_far_end).  Three
     contexts on device 0 on a one-GPU box, the real devices when there are more -- same files."""
