@@ -39,7 +39,7 @@ static_assert(sizeof(pg_region) == sizeof(PgRegion) && sizeof(pg_region) == 12, 
 static_assert(sizeof(pg_close_info) == sizeof(PgCloseInfo) && sizeof(pg_close_info) == 8, "close_info layout");
 static_assert(PG_READ_FLIPPED == PG_F_FLIPPED && PG_READ_UNSUPPORTED == PG_F_TOOLONG && PG_READ_OVERFLOW == PG_F_OVERFLOW, "flags");
 
-#define PG_PIPE_CHUNK_DEFAULT (1 << 20)   // reads per chunk of the pipelined path; PG_PIPE_CHUNK in the environment overrides it (tests)
+#define PG_PIPE_CHUNK_DEFAULT (1 << 19)   // reads per chunk of the pipelined path; PG_PIPE_CHUNK in the environment overrides it (tests)
 #define PG_BLOCK_THREADS 32
 #ifndef PG_MINB
 #define PG_MINB 24         // resident CTAs (= warps) per SM the register allocator is asked to make room for (TL <= 8 variants):
@@ -964,20 +964,8 @@ static int run_pipelined(pg_ctx *ctx, PipeState *&ps, const pg_reads *in, pg_res
    if (mode == 2 && !in->close_info) return fail(ctx, PG_ERR_ARG, "far-end-only search needs close_info");
    if (ctx->chroms_h.empty()) return fail(ctx, PG_ERR_STATE, "no reference (call pg_set_reference)");
    if (res && !res->out) return fail(ctx, PG_ERR_ARG, "results buffers missing");
+   // (the per-read checks of pg_upload run chunk by chunk below, behind the copies and kernels of the chunks before)
    uint32_t maxlen = 0;
-   for (int i = 0; i < n; i++) {
-      if (in->seq_off[i + 1] < in->seq_off[i]) return fail(ctx, PG_ERR_ARG, "seq_off must be non-decreasing");
-      uint32_t l = in->seq_off[i + 1] - in->seq_off[i];
-      if (l > maxlen) maxlen = l;
-      if (in->chr_id && (in->chr_id[i] < 0 || (size_t)in->chr_id[i] >= ctx->chroms_h.size()))
-         return fail(ctx, PG_ERR_ARG, "chr_id out of range");
-   }
-   if (maxlen >= PG_TABLE)
-      return fail(ctx, PG_ERR_UNSUPPORTED, "read longer than 499 bases (the reference's g_maxMismatch table has 500 entries)");
-   if (have_regions)
-      for (size_t i = 0, nr = in->region_off[n]; i < nr; i++)
-         if (in->regions[i].chr < 0 || (size_t)in->regions[i].chr >= ctx->chroms_h.size())
-            return fail(ctx, PG_ERR_ARG, "region chromosome out of range");
    int chunk = ctx->pipe_chunk;
    if ((n + chunk - 1) / chunk > PG_PIPE_MAX_CHUNKS) chunk = (n + PG_PIPE_MAX_CHUNKS - 1) / PG_PIPE_MAX_CHUNKS;
    const int nchunks = (n + chunk - 1) / chunk;
@@ -1058,6 +1046,23 @@ static int run_pipelined(pg_ctx *ctx, PipeState *&ps, const pg_reads *in, pg_res
    };
    for (int c = 0; c < nchunks; c++) {
       const int c0 = c * chunk, c1 = (c0 + chunk < n) ? c0 + chunk : n, m = c1 - c0;
+      uint32_t chunk_maxlen = 0;
+      for (int i = c0; i < c1; i++) {
+         if (in->seq_off[i + 1] < in->seq_off[i]) return fail(ctx, PG_ERR_ARG, "seq_off must be non-decreasing");
+         const uint32_t l = in->seq_off[i + 1] - in->seq_off[i];
+         if (l > chunk_maxlen) chunk_maxlen = l;
+         if (in->chr_id && (in->chr_id[i] < 0 || (size_t)in->chr_id[i] >= ctx->chroms_h.size()))
+            return fail(ctx, PG_ERR_ARG, "chr_id out of range");
+      }
+      if (chunk_maxlen >= PG_TABLE)
+         return fail(ctx, PG_ERR_UNSUPPORTED, "read longer than 499 bases (the reference's g_maxMismatch table has 500 entries)");
+      if (have_regions) {
+         if (in->region_off[c1] < in->region_off[c0]) return fail(ctx, PG_ERR_ARG, "region_off must be non-decreasing");
+         for (size_t i = in->region_off[c0], nr = in->region_off[c1]; i < nr; i++)
+            if (in->regions[i].chr < 0 || (size_t)in->regions[i].chr >= ctx->chroms_h.size())
+               return fail(ctx, PG_ERR_ARG, "region chromosome out of range");
+      }
+      if (chunk_maxlen > maxlen) { maxlen = chunk_maxlen; ctx->max_read_len = maxlen; }
 #define UPS(buf, src, off, bytes) CU(cudaMemcpyAsync((char *)buf.p + (off), (const char *)(src) + (off), (bytes), cudaMemcpyHostToDevice, ps->s_in))
       const size_t b0 = in->seq_off[c0], b1 = in->seq_off[c1];
       if (b1 > b0) UPS(ctx->seq_blob, in->seq_blob, b0, b1 - b0);
@@ -1095,7 +1100,7 @@ static int run_pipelined(pg_ctx *ctx, PipeState *&ps, const pg_reads *in, pg_res
       bt.run_pool = (PgRun *)r.pool.p;
       bt.run_pool_cap = r.pool_cap;
       bt.counters = (uint32_t *)r.counters.p;
-      rc = dispatch_variant(ctx, bt, maxlen, ps->s_k, ctx->scratch);
+      rc = dispatch_variant(ctx, bt, chunk_maxlen, ps->s_k, ctx->scratch);
       if (rc != PG_OK) return rc;
       CU(cudaMemcpyAsync(ps->counters_h + 8 * (size_t)c, r.counters.p, 32, cudaMemcpyDeviceToHost, ps->s_k));
       CU(cudaEventRecord(ps->k_done[c], ps->s_k));

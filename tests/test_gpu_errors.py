@@ -66,3 +66,37 @@ def test_too_many_levels_is_unsupported(small):
     with pytest.raises(api.PgError, match="32 mismatch levels"):
         pg.search(**H.batch_kwargs(batch))
     pg.close()
+
+
+def test_bad_read_in_a_later_chunk_of_a_chunked_call(small, monkeypatch):
+    """The chunked path checks every chunk's reads right before their upload (behind the work of the chunks before): an
+    out-of-range chromosome in the last chunk is reported after earlier chunks were launched, and the context serves the next
+    call."""
+    ref, padded, batch = small
+    monkeypatch.setenv("PG_PIPE_CHUNK", "256")
+    big = synth.make_reads(ref, 2000, 100, seed=83)
+    kw = H.batch_kwargs(big)
+    pg = api.PatternGrowth()
+    pg.set_reference([padded])
+    good = R.per_read(*pg.search(**kw), kw["seq_blob"], kw["seq_off"])
+    chr_id = np.zeros(big.n, dtype=np.int32)
+    chr_id[1900] = 5
+    with pytest.raises(api.PgError, match="chr_id out of range"):
+        pg.search(chr_id=chr_id, **kw)
+    again = R.per_read(*pg.search(**kw), kw["seq_blob"], kw["seq_off"])
+    H.compare(good, again, "after a failed chunked call")
+    # mixed read lengths: every chunk picks its kernel variant from its own longest read
+    long_batch = synth.make_reads(ref, 600, 300, seed=84)
+    blob = np.concatenate([kw["seq_blob"], long_batch.seq.reshape(-1)])
+    off = np.concatenate([kw["seq_off"], kw["seq_off"][-1] + np.arange(1, long_batch.n + 1, dtype=np.uint32) * 300]).astype(np.uint32)
+    mixed = dict(seq_blob=blob, seq_off=off, matched_d=np.concatenate([big.matched_d, long_batch.matched_d]),
+                 matched_rel_pos=np.concatenate([big.matched_rel_pos, long_batch.matched_rel_pos]),
+                 insert_size=np.concatenate([big.insert_size, long_batch.insert_size]))
+    a = R.per_read(*pg.search(**mixed), blob, off)
+    pg.close()
+    monkeypatch.setenv("PG_PIPE_CHUNK", "1000000")
+    pg1 = api.PatternGrowth()
+    pg1.set_reference([padded])
+    b = R.per_read(*pg1.search(**mixed), blob, off)
+    pg1.close()
+    H.compare(b, a, "chunk-wise kernel variants vs one launch")
