@@ -437,6 +437,7 @@ struct pg_ctx {
    float sv_last_ms = 0.f;
    struct PipeState *pipe = nullptr;    // streams, events and the two chunk slots of the pipelined path (lazy)
    int pipe_chunk = PG_PIPE_CHUNK_DEFAULT;
+   bool pipe_chunk_forced = false;      // PG_PIPE_CHUNK given: exactly that chunk size, chunked from two chunks on (tests)
 };
 
 struct PipeState;
@@ -571,7 +572,7 @@ pg_ctx *pg_create(const pg_settings *s)
       return nullptr;
    }
    ctx->stream = ctx->own_stream;
-   if (const char *e = getenv("PG_PIPE_CHUNK")) { int v = atoi(e); if (v >= 256) ctx->pipe_chunk = v; }
+   if (const char *e = getenv("PG_PIPE_CHUNK")) { int v = atoi(e); if (v >= 256) { ctx->pipe_chunk = v; ctx->pipe_chunk_forced = true; } }
    return ctx;
 }
 
@@ -967,6 +968,8 @@ static int run_pipelined(pg_ctx *ctx, PipeState *&ps, const pg_reads *in, pg_res
    // (the per-read checks of pg_upload run chunk by chunk below, behind the copies and kernels of the chunks before)
    uint32_t maxlen = 0;
    int chunk = ctx->pipe_chunk;
+   // batches below four full chunks are cut in four, so that their copies hide behind their own kernels too
+   if (!ctx->pipe_chunk_forced && n < 4 * chunk) chunk = ((n + 3) / 4 + 1023) & ~1023;
    if ((n + chunk - 1) / chunk > PG_PIPE_MAX_CHUNKS) chunk = (n + PG_PIPE_MAX_CHUNKS - 1) / PG_PIPE_MAX_CHUNKS;
    const int nchunks = (n + chunk - 1) / chunk;
    int rc = pipe_init(ctx, ps, nchunks);
@@ -1138,6 +1141,13 @@ static int run_pipelined(pg_ctx *ctx, PipeState *&ps, const pg_reads *in, pg_res
    return PG_OK;
 }
 
+// batches from this size on take the chunked path (copies of chunk k +- 1 under the kernel of chunk k)
+#define PG_PIPE_MIN_READS (1 << 18)
+static inline bool pipe_applies(const pg_ctx *ctx, int n)
+{
+   return ctx->pipe_chunk_forced ? n >= 2 * ctx->pipe_chunk : n >= PG_PIPE_MIN_READS;
+}
+
 // a far-end batch without clusters of its own takes them from the loaded BreakDancer region (pg_bd_load_region)
 static inline bool bd_applies(const pg_ctx *ctx, const pg_reads *in, int mode)
 {
@@ -1150,7 +1160,7 @@ static int run_all(pg_ctx *ctx, const pg_reads *in, pg_results *res, int mode)
 {
    // (a far-end batch that takes its clusters from the loaded BreakDancer region goes through upload + launch: the lookup
    // runs on the whole resident batch)
-   if (ctx && in && in->n >= 2 * ctx->pipe_chunk && in->seq_blob && in->seq_off && !bd_applies(ctx, in, mode)) {
+   if (ctx && in && pipe_applies(ctx, in->n) && in->seq_blob && in->seq_off && !bd_applies(ctx, in, mode)) {
       CU(cudaSetDevice(ctx->device));
       return run_pipelined(ctx, ctx->pipe, in, res, mode);
    }
@@ -1168,7 +1178,7 @@ int pg_search(pg_ctx *ctx, const pg_reads *in, pg_results *res) { return run_all
 int pg_search_resident(pg_ctx *ctx, const pg_reads *in, int32_t mode)
 {
    if (!ctx || !in || in->n < 0 || mode < 1 || mode > 3) return fail(ctx, PG_ERR_ARG, "pg_search_resident: bad arguments");
-   if (in->n >= 2 * ctx->pipe_chunk && in->seq_blob && in->seq_off && !bd_applies(ctx, in, mode)) {
+   if (pipe_applies(ctx, in->n) && in->seq_blob && in->seq_off && !bd_applies(ctx, in, mode)) {
       CU(cudaSetDevice(ctx->device));
       return run_pipelined(ctx, ctx->pipe, in, nullptr, mode);
    }
