@@ -17,7 +17,10 @@
 //
 //     bool ReadInBamReads_SR(bam_path, FragName, ..., window, readBuffer, verbose)             src/reader.cpp:483-560
 //
-// -> Searcher::ModifyRP / Summarize (whole vector), Searcher::SortBoxes (all boxes of a driver), Searcher::InflateBam /
+//     void BDData::loadRegion(const SearchWindow&) / getCorrespondingSearchWindowCluster(read)  src/bddata.cpp:852,949
+//
+// -> Searcher::loadRegion (then SearchFarEnds(reads) needs no clusters), Searcher::ModifyRP / Summarize (whole vector),
+// Searcher::SortBoxes (all boxes of a driver; with a kind: any reporter's loops and its event cut), Searcher::InflateBam /
 // IndexBam / ReadInBamReads_SR (one window of the resident stream).  No search logic lives in this header; without a CUDA
 // device the Searcher constructor throws.
 #ifndef PINDEL_PG_HPP
@@ -103,6 +106,7 @@ struct SPLIT_READ {                      // the fields of src/pindel.h:265-383 t
    unsigned int BPLeft = 0, BPRight = 0, IndelSize = 0;
    unsigned short NT_size = 0;
    bool UniqueRead = true;
+   unsigned int LeftMostPos = 0;          // read by the DI / inversion reporters' duplicate scans (src/reporter.cpp:1764-1772)
 
    void setUnmatchedSeq(const std::string &s)                    // src/pindel.cpp:142-169: trailing non-alphanumerics are stripped
    {
@@ -146,6 +150,8 @@ inline bool Compare2RP(const RP_READ &first, const RP_READ &second)   // src/bdd
 
 struct SearchWindow { int chromosome_id; unsigned int start, end; };   // src/pindel.h:665-716, [start, end) padded coordinates
 typedef std::vector<SearchWindow> SearchWindowCluster;
+struct BreakDancerCoordinate { int chromosome_id; unsigned int position, position2; };   // src/control_state.h:40-68
+struct BreakDancerEvent { BreakDancerCoordinate first, second; };                        // src/control_state.h:70-78
 
 class Searcher {
 public:
@@ -206,6 +212,44 @@ public:
    }
 
    uint64_t kernelLaunches() const { return pg_kernel_launches(ctx_); }
+
+   // BDData::loadRegion (src/bddata.cpp:852-946): events = m_bdEvents as UpdateBD leaves it (sorted with sortOnFirstBDCoordinate:
+   // chromosome NAME, position, then the second coordinate); chromosome_names[c] = name of chromosome c of the reference list.
+   // From here on SearchFarEnds(reads) without clusters takes every read's cluster from this region on the device
+   // (getCorrespondingSearchWindowCluster, :949-967) until unloadRegion().
+   void loadRegion(const std::vector<BreakDancerEvent> &events, const std::vector<std::string> &chromosome_names, const SearchWindow &window)
+   {
+      std::vector<pg_bd_event> ev(events.size());
+      for (size_t i = 0; i < events.size(); i++) {
+         ev[i].chr_a = events[i].first.chromosome_id; ev[i].pos_a = events[i].first.position; ev[i].pos2_a = events[i].first.position2;
+         ev[i].chr_b = events[i].second.chromosome_id; ev[i].pos_b = events[i].second.position; ev[i].pos2_b = events[i].second.position2;
+      }
+      std::vector<size_t> by_name(chromosome_names.size());
+      for (size_t c = 0; c < by_name.size(); c++) by_name[c] = c;
+      std::sort(by_name.begin(), by_name.end(), [&](size_t a, size_t b) { return chromosome_names[a] < chromosome_names[b]; });
+      std::vector<int32_t> rank(chromosome_names.size());
+      for (size_t k = 0; k < by_name.size(); k++) rank[by_name[k]] = (int32_t)k;
+      check(pg_bd_load_region(ctx_, ev.empty() ? NULL : ev.data(), (uint32_t)ev.size(), rank.data(), window.chromosome_id, window.start, window.end),
+            "pg_bd_load_region");
+   }
+   void unloadRegion() { check(pg_bd_unload(ctx_), "pg_bd_unload"); }
+   // getCorrespondingSearchWindowCluster for a list of close-end positions (hosts that keep the clusters; tests)
+   std::vector<SearchWindowCluster> getCorrespondingSearchWindowClusters(const std::vector<unsigned int> &lastAbsLocCloseEnd)
+   {
+      std::vector<uint32_t> off(lastAbsLocCloseEnd.size() + 1, 0);
+      std::vector<pg_region> reg;
+      uint64_t n = 0;
+      int rc = pg_bd_clusters(ctx_, (uint32_t)lastAbsLocCloseEnd.size(), lastAbsLocCloseEnd.data(), off.data(), NULL, 0, &n);
+      if (rc == PG_ERR_RUNS_CAP) {
+         reg.resize((size_t)n);
+         rc = pg_bd_clusters(ctx_, (uint32_t)lastAbsLocCloseEnd.size(), lastAbsLocCloseEnd.data(), off.data(), reg.data(), reg.size(), &n);
+      }
+      check(rc, "pg_bd_clusters");
+      std::vector<SearchWindowCluster> out(lastAbsLocCloseEnd.size());
+      for (size_t i = 0; i < out.size(); i++)
+         for (uint32_t k = off[i]; k < off[i + 1]; k++) { SearchWindow w = {reg[k].chr, reg[k].start, reg[k].end}; out[i].push_back(w); }
+      return out;
+   }
 
    // ModifyRP (src/bddata.cpp:385-431): sort by original position (descending), InitializeA1B1, the interval-merging loop in
    // serial row order, + ReadLength, Visited for pairs closer than 500 -- all rows of one chromosome pair.
@@ -276,6 +320,46 @@ public:
          for (uint32_t k = off[b]; k < off[b + 1]; k++) {
             boxes[b][k - off[b]] = before[order[k]];
             if (non[k]) Reads[before[order[k]]].UniqueRead = false;
+         }
+      }
+   }
+
+   // The ordering loop, duplicate scan and event walk of ANY reporter (kind = PG_BOX_D / _SI / _DI / _INV / _INV_NT; the DI and
+   // inversion reporters carry them inlined, src/reporter.cpp:1728-1813, src/output_sorter.cpp:74-205): boxes[b] reordered,
+   // UniqueRead cleared, and events[b][k] = PG_BOX_EVENT_GOOD | PG_BOX_EVENT_START flags of the k-th read of box b afterwards.
+   void SortBoxes(int kind, std::vector<SPLIT_READ> &Reads, std::vector<std::vector<unsigned> > &boxes, std::vector<std::vector<uint8_t> > &events)
+   {
+      std::vector<uint32_t> off(1, 0);
+      std::vector<pg_sort_key> keys;
+      std::map<std::string, uint32_t> ids;
+      for (size_t b = 0; b < boxes.size(); b++) {
+         for (size_t k = 0; k < boxes[b].size(); k++) {
+            const SPLIT_READ &r = Reads[boxes[b][k]];
+            pg_sort_key key;
+            std::memset(&key, 0, sizeof key);
+            key.bp_left = r.BPLeft; key.bp_right = r.BPRight; key.indel_size = r.IndelSize; key.nt_size = r.NT_size; key.bp = r.BP;
+            key.unique = r.UniqueRead ? 1 : 0;
+            if (kind == PG_BOX_D || kind == PG_BOX_SI) {
+               key.left = r.Left; key.right = r.Right;
+               key.name_id = ids.insert(std::make_pair(r.Name, (uint32_t)ids.size())).first->second;
+            } else {
+               key.left = (int32_t)r.LeftMostPos; key.read_length = (uint16_t)r.getReadLength(); key.matched_d = (uint8_t)r.MatchedD;
+            }
+            keys.push_back(key);
+         }
+         off.push_back((uint32_t)keys.size());
+      }
+      events.assign(boxes.size(), std::vector<uint8_t>());
+      if (keys.empty()) return;
+      std::vector<uint32_t> order(keys.size());
+      std::vector<uint8_t> non(keys.size()), ev(keys.size());
+      check(pg_box_sort_kind(ctx_, kind, (uint32_t)boxes.size(), off.data(), keys.data(), order.data(), non.data(), ev.data()), "pg_box_sort_kind");
+      for (size_t b = 0; b < boxes.size(); b++) {
+         const std::vector<unsigned> before(boxes[b]);
+         for (uint32_t k = off[b]; k < off[b + 1]; k++) {
+            boxes[b][k - off[b]] = before[order[k]];
+            if (non[k]) Reads[before[order[k]]].UniqueRead = false;
+            events[b].push_back(ev[k]);
          }
       }
    }

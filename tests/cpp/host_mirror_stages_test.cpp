@@ -6,7 +6,10 @@
 //          int32 n_reads, {uint32 BPLeft, BPRight, IndelSize, int32 Left, Right, uint32 name, uint16 NT_size, int16 BP, uint8 unique}*,
 //          int32 n_boxes, {int32 size, uint32 read*}*, int64 bam_bytes, bytes
 // out.bin: int32 stream: per RP row (in ModifyRP's order) [input index, PosA, PosA1, PosB, PosB1, Visited, Report, NumberOfIdentical, n Tags];
-//          per box its reordered read indices; per read UniqueRead; int64 inflated size, int64 n records, per record off(lo32), pos, end
+//          per box its reordered read indices; per read UniqueRead; int64 inflated size, int64 n records, per record off(lo32), pos, end;
+//          then the inversion reporter's loops on the same boxes (SortBoxes(PG_BOX_INV_NT, ..), reads as they came in, with
+//          LeftMostPos = Left, anchor strand and read length derived from the name number): per box the reordered indices,
+//          per read UniqueRead, per box position the event flags
 #include <cstdint>
 #include <cstdio>
 #include <fstream>
@@ -42,6 +45,10 @@ int main(int argc, char **argv)
       r.BPLeft = rd<uint32_t>(f); r.BPRight = rd<uint32_t>(f); r.IndelSize = rd<uint32_t>(f); r.Left = rd<int32_t>(f); r.Right = rd<int32_t>(f);
       r.Name = "n" + std::to_string(rd<uint32_t>(f));
       r.NT_size = rd<uint16_t>(f); r.BP = rd<int16_t>(f); r.UniqueRead = rd<uint8_t>(f) != 0;
+      const unsigned name = (unsigned)std::stoul(r.Name.substr(1));
+      r.LeftMostPos = (unsigned)r.Left;
+      r.MatchedD = (name & 1u) ? '+' : '-';
+      r.setUnmatchedSeq(std::string(name % 3u == 0 ? 101 : 100, 'A'));
    }
    const int32_t n_boxes = rd<int32_t>(f);
    std::vector<std::vector<unsigned> > boxes((size_t)n_boxes);
@@ -53,11 +60,16 @@ int main(int argc, char **argv)
    const int64_t bam_bytes = rd<int64_t>(f);
    std::string bam((size_t)bam_bytes, '\0');
    f.read(&bam[0], bam_bytes);
+   std::vector<SPLIT_READ> reads_inv(reads);
+   std::vector<std::vector<unsigned> > boxes_inv;
    try {
       Searcher s;                                    // throws without a CUDA device (no CPU path)
       s.ModifyRP(rp);                                // src/bddata.cpp:657
       s.Summarize(rp);                               // src/bddata.cpp:659
+      boxes_inv = boxes;
       s.SortBoxes(reads, boxes);                     // src/reporter.cpp:1425-1427, all boxes at once
+      std::vector<std::vector<uint8_t> > events;
+      s.SortBoxes(PG_BOX_INV_NT, reads_inv, boxes_inv, events);      // src/output_sorter.cpp:74-205
       std::string inflated;
       const size_t total = s.InflateBam(bam, &inflated);
       const std::vector<pg_bam_rec> recs = s.IndexBam();
@@ -72,6 +84,9 @@ int main(int argc, char **argv)
       for (int i = 0; i < n_reads; i++) o.push_back(reads[i].UniqueRead);
       o.push_back((int32_t)total); o.push_back((int32_t)(inflated.size() == total)); o.push_back((int32_t)recs.size());
       for (size_t i = 0; i < recs.size(); i++) { o.push_back((int32_t)recs[i].off); o.push_back(recs[i].pos); o.push_back(recs[i].end); }
+      for (int b = 0; b < n_boxes; b++) o.insert(o.end(), boxes_inv[b].begin(), boxes_inv[b].end());
+      for (int i = 0; i < n_reads; i++) o.push_back(reads_inv[i].UniqueRead);
+      for (int b = 0; b < n_boxes; b++) o.insert(o.end(), events[b].begin(), events[b].end());
       std::ofstream out(argv[2], std::ios::binary);
       out.write((const char *)o.data(), (std::streamsize)(o.size() * sizeof(int32_t)));
    } catch (const std::exception &e) {

@@ -136,6 +136,16 @@ def test_cpp_stage_mirrors_match_oracles(tmp_path):
     q = p0 + idx.size + reads.size
     table = bam.serial_index(stream)
     assert o[q] == len(stream) and o[q + 1] == 1 and o[q + 2] == table.size
-    rec = o[q + 3:].reshape(-1, 3)
+    rec = o[q + 3:q + 3 + 3 * table.size].reshape(-1, 3)
     assert np.array_equal(rec[:, 0].astype(np.int64), table["off"].astype(np.int64)) and np.array_equal(rec[:, 1], table["pos"]) and \
         np.array_equal(rec[:, 2], table["end"])
+    # the inversion reporter's loops through SortBoxes(PG_BOX_INV_NT, ...): same boxes, keys as the C++ side derives them
+    k = reads.copy()
+    k["left"] = reads["left"]
+    k["matched_d"] = np.where(reads["name_id"] & 1, ord("+"), ord("-"))
+    k["read_length"] = np.where(reads["name_id"] % 3 == 0, 101, 100)
+    i_idx, i_unique, i_event = B.sort_boxes_kind(4, k, box_off, idx)
+    z = q + 3 + 3 * table.size
+    assert np.array_equal(o[z:z + idx.size].astype(np.uint32), i_idx)
+    assert np.array_equal(o[z + idx.size:z + idx.size + reads.size].astype(np.uint8), i_unique)
+    assert np.array_equal(o[z + idx.size + reads.size:z + 2 * idx.size + reads.size].astype(np.uint8), i_event)
