@@ -49,6 +49,7 @@ PG_DEV void pg_syncwarp() { __syncwarp(); }
 PG_DEV int pg_popc(uint32_t v) { return __popc(v); }
 PG_DEV int pg_ffs(uint32_t v) { return __ffs((int)v); }
 PG_DEV int pg_clz(uint32_t v) { return __clz((int)v); }
+PG_DEV uint32_t pg_bfind(uint32_t v) { uint32_t r; asm("bfind.u32 %0, %1;" : "=r"(r) : "r"(v)); return r; }   // index of the highest set bit (v != 0)
 PG_DEV uint32_t pg_brev(uint32_t v) { return __brev(v); }
 PG_DEV uint32_t pg_fsr(uint32_t lo, uint32_t hi, uint32_t s) { return __funnelshift_r(lo, hi, s); }
 PG_DEV uint32_t pg_fsrc(uint32_t lo, uint32_t hi, uint32_t s) { return __funnelshift_rc(lo, hi, s); }
@@ -495,8 +496,14 @@ PG_DEV void pg_scan_window(PgWarpCtx<LW, TL> &cx, const PgSearch &se, int chr_id
                uint32_t both = plus | minus;
                uint32_t rel = p0 - origin;
                while (both) {
+#ifdef PG_LSB_SEEDS
+                  const uint32_t below = both - 1u;
+                  const uint32_t bit = pg_bfind(both & ~below);
+                  both &= below;
+#else
                   uint32_t bit = (uint32_t)pg_ffs(both) - 1u;
                   both &= both - 1u;
+#endif
                   ws->seedq[o++] = (uint16_t)((rel + bit) | (((minus >> bit) & 1u) << 15));
                }
                nq += nseeds;
@@ -535,6 +542,18 @@ PG_DEV void pg_scan_window(PgWarpCtx<LW, TL> &cx, const PgSearch &se, int chr_id
             bool hot = have && pg_popc(m0) >= TL;
             bool slow = have && !hot;
             if (hot) {
+#ifdef PG_LSB_WALK
+               // the mismatch indices upwards = the set bits from the lowest: the walk itself is two ALU operations per level
+               // (clear the lowest set bit), the bit's index comes off that chain
+               uint32_t mm = m0;
+#pragma unroll
+               for (int t = 0; t < TL; t++) {
+                  const uint32_t next = mm & (mm - 1u);
+                  const uint32_t D = pg_bfind(mm ^ next);
+                  mm = next;
+                  pg_key_update(ka_[t], kb_[t], D * (1u << PG_IDX_BITS) + off);
+               }
+#else
                uint32_t mrev = pg_brev(m0);          // mismatch at read index j <-> bit 31-j: clz walks the indices upwards
 #pragma unroll
                for (int t = 0; t < TL; t++) {
@@ -542,6 +561,7 @@ PG_DEV void pg_scan_window(PgWarpCtx<LW, TL> &cx, const PgSearch &se, int chr_id
                   mrev &= ~(0x80000000u >> D);
                   pg_key_update(ka_[t], kb_[t], D * (1u << PG_IDX_BITS) + off);
                }
+#endif
             }
             uint32_t slowmask = pg_ballot(slow);
             if (slowmask) {

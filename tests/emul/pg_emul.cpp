@@ -102,6 +102,7 @@ PG_DEV void pg_syncwarp() { emu_collective(OP_SYNC, 0, 0); }
 PG_DEV int pg_popc(uint32_t v) { return __builtin_popcount(v); }
 PG_DEV int pg_ffs(uint32_t v) { return __builtin_ffs((int)v); }
 PG_DEV int pg_clz(uint32_t v) { return v ? __builtin_clz(v) : 32; }
+PG_DEV uint32_t pg_bfind(uint32_t v) { return v ? 31u - (uint32_t)__builtin_clz(v) : 0xffffffffu; }
 PG_DEV uint32_t pg_brev(uint32_t v)
 {
    v = ((v >> 1) & 0x55555555u) | ((v & 0x55555555u) << 1);
