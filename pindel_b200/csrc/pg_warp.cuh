@@ -496,14 +496,8 @@ PG_DEV void pg_scan_window(PgWarpCtx<LW, TL> &cx, const PgSearch &se, int chr_id
                uint32_t both = plus | minus;
                uint32_t rel = p0 - origin;
                while (both) {
-#ifdef PG_LSB_SEEDS
-                  const uint32_t below = both - 1u;
-                  const uint32_t bit = pg_bfind(both & ~below);
-                  both &= below;
-#else
                   uint32_t bit = (uint32_t)pg_ffs(both) - 1u;
                   both &= both - 1u;
-#endif
                   ws->seedq[o++] = (uint16_t)((rel + bit) | (((minus >> bit) & 1u) << 15));
                }
                nq += nseeds;
@@ -542,9 +536,9 @@ PG_DEV void pg_scan_window(PgWarpCtx<LW, TL> &cx, const PgSearch &se, int chr_id
             bool hot = have && pg_popc(m0) >= TL;
             bool slow = have && !hot;
             if (hot) {
-#ifdef PG_LSB_WALK
-               // the mismatch indices upwards = the set bits from the lowest: the walk itself is two ALU operations per level
-               // (clear the lowest set bit), the bit's index comes off that chain
+               // the mismatch indices upwards = the set bits from the lowest.  The walk itself is two ALU operations per level
+               // (clear the lowest set bit); the bit's index (bfind, the slow pipe) hangs off that chain instead of being part
+               // of it -- walking a bit-reversed word with clz put FLO + shift + and-not between consecutive levels
                uint32_t mm = m0;
 #pragma unroll
                for (int t = 0; t < TL; t++) {
@@ -553,15 +547,6 @@ PG_DEV void pg_scan_window(PgWarpCtx<LW, TL> &cx, const PgSearch &se, int chr_id
                   mm = next;
                   pg_key_update(ka_[t], kb_[t], D * (1u << PG_IDX_BITS) + off);
                }
-#else
-               uint32_t mrev = pg_brev(m0);          // mismatch at read index j <-> bit 31-j: clz walks the indices upwards
-#pragma unroll
-               for (int t = 0; t < TL; t++) {
-                  uint32_t D = (uint32_t)pg_clz(mrev);
-                  mrev &= ~(0x80000000u >> D);
-                  pg_key_update(ka_[t], kb_[t], D * (1u << PG_IDX_BITS) + off);
-               }
-#endif
             }
             uint32_t slowmask = pg_ballot(slow);
             if (slowmask) {

@@ -53,6 +53,6 @@ np.save(os.path.join(SHM, "pos.npy"), pos.cpu().numpy().astype(np.uint32))
 np.save(os.path.join(SHM, "isz.npy"), isz.cpu().numpy())
 del rt, seq
 torch.cuda.empty_cache()
-for rep in range(2):
+for rep in range(int(os.environ.get("AB_REPS", "2"))):
     for lib in sys.argv[1:]:
         subprocess.run([sys.executable, os.path.abspath(__file__), "--worker"], env=dict(os.environ, PG_LIB=os.path.abspath(lib)))
