@@ -510,11 +510,6 @@ PG_DEV void pg_scan_window(PgWarpCtx<LW, TL> &cx, const PgSearch &se, int chr_id
          nq = 0;
          pg_syncwarp();
          // ---- (2) 32 seeds per pass ----
-#if defined(PG_PASS_UNROLL) && PG_PASS_UNROLL == 2
-#pragma unroll 2
-#elif defined(PG_PASS_UNROLL) && PG_PASS_UNROLL == 1
-#pragma unroll 1
-#endif
          for (uint32_t q0 = 0; q0 < nseeds; q0 += 32) {
             uint32_t qi = q0 + (uint32_t)lane;
             bool have = qi < nseeds;
