@@ -818,99 +818,26 @@ void replayDriver(int d, ControlState &cs, unsigned NumBoxes, const SearchWindow
 } // namespace
 
 /* ---------------------------------------------------------------------------------------------------------------------
- * Row N4: bubblesortReads + markDuplicates (src/reporter.cpp:932-972) are called per box from inside the reporters, which
- * stay the reference's; both are free functions, bound by symbol.  The drivers above own the boxes before the reporter
- * runs, so every box the reporter is going to sort is sorted in ONE pg_box_sort call right after the driver's records have
- * been replayed; the two functions then only hand the stored result over (checked against the box's content), and run the
- * reference's own code (dlsym(RTLD_NEXT)) for any box that was not prepared.  PG_BRIDGE_HOST_SORT=1 prepares nothing.
+ * Row N4: every reporter orders the reads of a box with an exchange sort, marks duplicates and cuts the surviving reads into
+ * events before it decides and prints (src/reporter.cpp:932-972 as functions for D / SI / TD, inlined in the other two).  All
+ * five reporters are supplied below around ONE pg_box_sort_kind call each; bubblesortReads is bound only to count the boxes the
+ * reference's own loops still order (PG_BRIDGE_HOST_SORT=1, or a box that mixes chromosomes).
  * ------------------------------------------------------------------------------------------------------------------- */
 namespace {
-struct PreparedBox {
-   std::vector<unsigned> members, sorted, nonunique;   /* content at preparation time; order afterwards; reads that lose UniqueRead */
-};
-std::map<const std::vector<unsigned> *, PreparedBox> g_prepared;
 unsigned long g_boxes_sorted = 0, g_boxes_host = 0;
-
-void prepareBoxes(const std::vector<SPLIT_READ> &Reads, std::vector<unsigned> Vars[], unsigned NumBoxes)
-{
-   g_prepared.clear();
-   if (getenv("PG_BRIDGE_HOST_SORT")) return;
-   std::lock_guard<std::mutex> lock(g_mutex);
-   ensureContext();
-   std::vector<uint32_t> boxOff(1, 0);
-   std::vector<unsigned> boxes;
-   std::vector<pg_sort_key> keys;
-   std::map<std::string, uint32_t> nameId;
-   for (unsigned b = 0; b < NumBoxes; b++) {
-      const std::vector<unsigned> &v = Vars[b];
-      if (v.size() < userSettings->NumRead2ReportCutOff || v.empty()) continue;
-      bool oneChromosome = true;
-      for (size_t k = 1; k < v.size(); k++) if (Reads[v[k]].FragName != Reads[v[0]].FragName) { oneChromosome = false; break; }
-      if (!oneChromosome) continue;      /* smaller() would go through CompareFragName: left to the reference */
-      for (size_t k = 0; k < v.size(); k++) {
-         const SPLIT_READ &r = Reads[v[k]];
-         pg_sort_key key;
-         memset(&key, 0, sizeof key);
-         key.bp_left = r.BPLeft; key.bp_right = r.BPRight; key.indel_size = r.IndelSize; key.left = r.Left; key.right = r.Right;
-         key.nt_size = r.NT_size; key.bp = r.BP; key.unique = r.UniqueRead ? 1 : 0;
-         std::map<std::string, uint32_t>::iterator it = nameId.find(r.Name);
-         if (it == nameId.end()) it = nameId.insert(std::make_pair(r.Name, (uint32_t)nameId.size())).first;
-         key.name_id = it->second;
-         keys.push_back(key);
-      }
-      boxes.push_back(b);
-      boxOff.push_back((uint32_t)keys.size());
-   }
-   if (boxes.empty()) return;
-   std::vector<uint32_t> order(keys.size());
-   std::vector<uint8_t> non(keys.size());
-   { Tick tk(t_box_lib); if (pg_box_sort(g_ctx, (uint32_t)boxes.size(), &boxOff[0], &keys[0], &order[0], &non[0]) != PG_OK) die("pg_box_sort"); }
-   for (size_t i = 0; i < boxes.size(); i++) {
-      const std::vector<unsigned> &v = Vars[boxes[i]];
-      PreparedBox &p = g_prepared[&v];
-      p.members = v;
-      for (uint32_t k = boxOff[i]; k < boxOff[i + 1]; k++) {
-         const unsigned read = v[order[k]];
-         p.sorted.push_back(read);
-         if (non[k]) p.nonunique.push_back(read);
-      }
-   }
-}
 } // namespace
 
 void bubblesortReads(const std::vector<SPLIT_READ> &Reads, std::vector<unsigned> &VariantIndices)
 {
-   std::map<const std::vector<unsigned> *, PreparedBox>::iterator it = g_prepared.find(&VariantIndices);
-   if (it != g_prepared.end() && it->second.members == VariantIndices) {
-      VariantIndices.assign(it->second.sorted.begin(), it->second.sorted.end());
-      it->second.members.clear();          /* handed over: markDuplicates recognises the box by its sorted content */
-      g_boxes_sorted++;
-      return;
-   }
    typedef void (*Fn)(const std::vector<SPLIT_READ> &, std::vector<unsigned> &);
    static Fn original = (Fn)dlsym(RTLD_NEXT, "_Z15bubblesortReadsRKSt6vectorI10SPLIT_READSaIS0_EERS_IjSaIjEE");
    if (!original) { std::fprintf(stderr, "pindel_gpu_demo: the reference's bubblesortReads was not found\n"); std::exit(EXIT_FAILURE); }
-   if (it != g_prepared.end()) g_prepared.erase(it);
    g_boxes_host++;
    original(Reads, VariantIndices);
 }
 
-void markDuplicates(std::vector<SPLIT_READ> &Reads, const std::vector<unsigned> &VariantIndices)
-{
-   std::map<const std::vector<unsigned> *, PreparedBox>::iterator it = g_prepared.find(&VariantIndices);
-   if (it != g_prepared.end() && it->second.members.empty() && it->second.sorted == VariantIndices) {
-      for (size_t k = 0; k < it->second.nonunique.size(); k++) Reads[it->second.nonunique[k]].UniqueRead = false;
-      g_prepared.erase(it);
-      return;
-   }
-   typedef void (*Fn)(std::vector<SPLIT_READ> &, const std::vector<unsigned> &);
-   static Fn original = (Fn)dlsym(RTLD_NEXT, "_Z14markDuplicatesRSt6vectorI10SPLIT_READSaIS0_EERKS_IjSaIjEE");
-   if (!original) { std::fprintf(stderr, "pindel_gpu_demo: the reference's markDuplicates was not found\n"); std::exit(EXIT_FAILURE); }
-   original(Reads, VariantIndices);
-}
-
 /* ---------------------------------------------------------------------------------------------------------------------
- * Row N4, the rest: the DI and inversion reporters carry the ordering and the duplicate scan INLINED, with their own rules
+ * The DI and inversion reporters carry the ordering and the duplicate scan INLINED, with their own rules
  * (SortOutputDI, src/reporter.cpp:1709-1851; OutputSorter::DoSortAndOutputInversions, src/output_sorter.cpp:62-260), so
  * there is no function to bind: the two reporters are supplied here.  Ordering, duplicate marks and the cut of the
  * surviving reads into events come from ONE pg_box_sort_kind call for all boxes of the driver; what follows per event --
@@ -935,23 +862,34 @@ struct OrderedBox {
    std::vector<uint8_t> event;          /* PG_BOX_EVENT_* per position */
 };
 /* every box the reporter would process, through the device; the reporter's side effects on its inputs are applied here:
- * the box's new order and the UniqueRead marks (later drivers read them) */
-void orderBoxes(int kind, std::vector<SPLIT_READ> &Reads, std::vector<unsigned> Vars[], unsigned NumBoxes, std::vector<OrderedBox> &out)
+ * the box's new order and the UniqueRead marks (later drivers read them).  false (nothing touched): a box mixes chromosomes
+ * (smaller() and the D reporter's event test compare FragName / FarFragName first) -- the reference's own function runs. */
+bool orderBoxes(int kind, std::vector<SPLIT_READ> &Reads, std::vector<unsigned> Vars[], unsigned NumBoxes, std::vector<OrderedBox> &out)
 {
    std::lock_guard<std::mutex> lock(g_mutex);
    ensureContext();
    std::vector<uint32_t> boxOff(1, 0);
    std::vector<pg_sort_key> keys;
+   std::map<std::string, uint32_t> nameId;
+   const bool byName = kind == PG_BOX_D || kind == PG_BOX_SI;      /* bubblesortReads + markDuplicates */
    for (unsigned b = 0; b < NumBoxes; b++) {
       const std::vector<unsigned> &v = Vars[b];
       if (v.size() < userSettings->NumRead2ReportCutOff || v.empty()) continue;
       for (size_t k = 0; k < v.size(); k++) {
          const SPLIT_READ &r = Reads[v[k]];
+         if (byName && (r.FragName != Reads[v[0]].FragName || r.FarFragName != r.FragName)) { out.clear(); return false; }
          pg_sort_key key;
          memset(&key, 0, sizeof key);
          key.bp_left = r.BPLeft; key.bp_right = r.BPRight; key.indel_size = r.IndelSize; key.nt_size = r.NT_size; key.bp = r.BP;
-         key.left = (int32_t)r.LeftMostPos; key.read_length = (uint16_t)r.getReadLength(); key.matched_d = (uint8_t)r.MatchedD;
          key.unique = r.UniqueRead ? 1 : 0;
+         if (byName) {
+            key.left = r.Left; key.right = r.Right;
+            std::map<std::string, uint32_t>::iterator it = nameId.find(r.Name);
+            if (it == nameId.end()) it = nameId.insert(std::make_pair(r.Name, (uint32_t)nameId.size())).first;
+            key.name_id = it->second;
+         } else {
+            key.left = (int32_t)r.LeftMostPos; key.read_length = (uint16_t)r.getReadLength(); key.matched_d = (uint8_t)r.MatchedD;
+         }
          keys.push_back(key);
       }
       OrderedBox ob;
@@ -959,7 +897,7 @@ void orderBoxes(int kind, std::vector<SPLIT_READ> &Reads, std::vector<unsigned> 
       out.push_back(ob);
       boxOff.push_back((uint32_t)keys.size());
    }
-   if (out.empty()) return;
+   if (out.empty()) return true;
    std::vector<uint32_t> order(keys.size());
    std::vector<uint8_t> non(keys.size()), event(keys.size());
    { Tick tk(t_box_lib); if (pg_box_sort_kind(g_ctx, kind, (uint32_t)out.size(), &boxOff[0], &keys[0], &order[0], &non[0], &event[0]) != PG_OK) die("pg_box_sort_kind"); }
@@ -971,8 +909,9 @@ void orderBoxes(int kind, std::vector<SPLIT_READ> &Reads, std::vector<unsigned> 
          if (non[k]) Reads[v[order[k]]].UniqueRead = false;
       }
       v = out[i].reads;
-      g_boxes_inlined++;
+      if (byName) g_boxes_sorted++; else g_boxes_inlined++;
    }
+   return true;
 }
 /* GoodIndels and the events' index ranges in it, from the device's flags */
 void goodReadsAndEvents(const std::vector<SPLIT_READ> &Reads, const OrderedBox &ob, std::vector<SPLIT_READ> &good, std::vector<std::pair<unsigned, unsigned> > &events)
@@ -987,6 +926,115 @@ void goodReadsAndEvents(const std::vector<SPLIT_READ> &Reads, const OrderedBox &
    }
 }
 } // namespace
+
+/* The D, SI and TD reporters (src/reporter.cpp:1395-1570, 975-1100, 1157-1290) call bubblesortReads / markDuplicates per box and
+ * then walk the unique reads to cut them into events.  Supplied here the same way as the two reporters below: one
+ * pg_box_sort_kind call for all boxes gives order, marks and the event cut; per event the reference's own functions decide and
+ * print.  (The two bound functions above stay for any other caller.) */
+bool IsGoodTD(std::vector<SPLIT_READ> &GoodIndels, Indel4output &OneIndelEvent, unsigned RealStart, unsigned RealEnd, ControlState &currentState);
+namespace {
+/* OneIndelEvent as the D / TD walks leave it for the event [first, last] of GoodIndels (src/reporter.cpp:1446-1497, 1206-1246) */
+Indel4output breakpointEvent(const std::vector<SPLIT_READ> &good, unsigned first, unsigned last, const std::string &CurrentChr)
+{
+   Indel4output ev;
+   ev.ChrName = good[first].FragName;
+   ev.Start = first; ev.End = last; ev.Support = last - first + 1;
+   ev.BPLeft = good[first].BPLeft; ev.BPRight = good[first].BPRight;
+   ev.RealStart = ev.BPLeft; ev.RealEnd = ev.BPRight;
+   ev.WhetherReport = true;
+   GetRealStart4Deletion(CurrentChr, ev.RealStart, ev.RealEnd);
+   return ev;
+}
+} // namespace
+
+void SortOutputD(ControlState &currentState, const unsigned &NumBoxes, const std::string &CurrentChr, std::vector<SPLIT_READ> &Reads, std::vector<unsigned> Deletions[],
+                 std::ofstream &DeletionOutf)
+{
+   std::vector<OrderedBox> boxes;
+   if (getenv("PG_BRIDGE_HOST_SORT") || !orderBoxes(PG_BOX_D, Reads, Deletions, NumBoxes, boxes)) {
+      typedef void (*Fn)(ControlState &, const unsigned &, const std::string &, std::vector<SPLIT_READ> &, std::vector<unsigned>[], std::ofstream &);
+      static Fn original = (Fn)dlsym(RTLD_NEXT, "_Z11SortOutputDR12ControlStateRKjRKNSt7__cxx1112basic_stringIcSt11char_traitsIcESaIcEEERSt6vectorI10SPLIT_READSaISC_EEPSB_IjSaIjEERSt14basic_ofstreamIcS6_E");
+      if (!original) { std::fprintf(stderr, "pindel_gpu_demo: the reference's SortOutputD was not found\n"); std::exit(EXIT_FAILURE); }
+      original(currentState, NumBoxes, CurrentChr, Reads, Deletions, DeletionOutf);
+      return;
+   }
+   LOG_INFO(*logStream << "Sorting and outputing deletions ..." << std::endl);
+   std::vector<SPLIT_READ> good;
+   std::vector<std::pair<unsigned, unsigned> > events;
+   for (size_t i = 0; i < boxes.size(); i++) {
+      goodReadsAndEvents(Reads, boxes[i], good, events);
+      for (size_t e = 0; e < events.size(); e++) {
+         Indel4output ev = breakpointEvent(good, events[e].first, events[e].second, CurrentChr);
+         if (ev.Support < userSettings->NumRead2ReportCutOff || !IsGoodDeletion(good, ev, ev.RealStart, ev.RealEnd, currentState)) continue;   /* :1539 */
+         if (good[ev.Start].IndelSize < userSettings->BalanceCutoff || ReportEvent(good, ev.Start, ev.End)) {                                  /* :1543-1559 */
+            OutputDeletions(good, CurrentChr, ev.Start, ev.End, ev.RealStart, ev.RealEnd, DeletionOutf);
+            deletionFileData.increaseTemplateSvCounter();
+         }
+      }
+   }
+   LOG_INFO(*logStream << "Deletions: " << deletionFileData.getTemplateSvCounter() << std::endl << std::endl);
+}
+
+void SortOutputSI(ControlState &currentState, const unsigned &NumBoxes, const std::string &CurrentChr, std::vector<SPLIT_READ> &Reads, std::vector<unsigned> SIs[],
+                  std::ofstream &SIsOutf)
+{
+   std::vector<OrderedBox> boxes;
+   if (getenv("PG_BRIDGE_HOST_SORT") || !orderBoxes(PG_BOX_SI, Reads, SIs, NumBoxes, boxes)) {
+      typedef void (*Fn)(ControlState &, const unsigned &, const std::string &, std::vector<SPLIT_READ> &, std::vector<unsigned>[], std::ofstream &);
+      static Fn original = (Fn)dlsym(RTLD_NEXT, "_Z12SortOutputSIR12ControlStateRKjRKNSt7__cxx1112basic_stringIcSt11char_traitsIcESaIcEEERSt6vectorI10SPLIT_READSaISC_EEPSB_IjSaIjEERSt14basic_ofstreamIcS6_E");
+      if (!original) { std::fprintf(stderr, "pindel_gpu_demo: the reference's SortOutputSI was not found\n"); std::exit(EXIT_FAILURE); }
+      original(currentState, NumBoxes, CurrentChr, Reads, SIs, SIsOutf);
+      return;
+   }
+   LOG_INFO(*logStream << "Sorting and outputing short insertions ..." << std::endl);
+   std::vector<SPLIT_READ> good;
+   std::vector<std::pair<unsigned, unsigned> > events;
+   for (size_t i = 0; i < boxes.size(); i++) {
+      goodReadsAndEvents(Reads, boxes[i], good, events);
+      for (size_t e = 0; e < events.size(); e++) {
+         Indel4output ev;
+         ev.initialize(events[e].first, good[events[e].first]);       /* src/pindel.h:418-432 */
+         ev.End = events[e].second;
+         ev.complete();
+         GetRealStart4Insertion(CurrentChr, ev.IndelStr, ev.RealStart, ev.RealEnd);
+         if (ev.WhetherReport && ev.Support >= userSettings->NumRead2ReportCutOff && ev.RealStart < ev.RealEnd)                               /* :1074 */
+            OutputSIs(good, CurrentChr, ev.Start, ev.End, ev.RealStart, ev.RealEnd, SIsOutf);
+      }
+   }
+   LOG_INFO(*logStream << "Short insertions: " << NumberOfSIsInstances << std::endl << std::endl);
+}
+
+void SortAndOutputTandemDuplications(ControlState &currentState, const unsigned &NumBoxes, const std::string &CurrentChr, std::vector<SPLIT_READ> &AllReads,
+                                     std::vector<unsigned> TDs[], std::ofstream &TDOutf, const bool nonTemplate)
+{
+   std::vector<OrderedBox> boxes;
+   if (getenv("PG_BRIDGE_HOST_SORT") || !orderBoxes(PG_BOX_D, AllReads, TDs, NumBoxes, boxes)) {
+      typedef void (*Fn)(ControlState &, const unsigned &, const std::string &, std::vector<SPLIT_READ> &, std::vector<unsigned>[], std::ofstream &, const bool);
+      static Fn original = (Fn)dlsym(RTLD_NEXT, "_Z31SortAndOutputTandemDuplicationsR12ControlStateRKjRKNSt7__cxx1112basic_stringIcSt11char_traitsIcESaIcEEERSt6vectorI10SPLIT_READSaISC_EEPSB_IjSaIjEERSt14basic_ofstreamIcS6_Eb");
+      if (!original) { std::fprintf(stderr, "pindel_gpu_demo: the reference's SortAndOutputTandemDuplications was not found\n"); std::exit(EXIT_FAILURE); }
+      original(currentState, NumBoxes, CurrentChr, AllReads, TDs, TDOutf, nonTemplate);
+      return;
+   }
+   if (nonTemplate) { LOG_INFO(*logStream << "Sorting and outputing tandem duplications with non-template sequence ..." << std::endl); }
+   else { LOG_INFO(*logStream << "Sorting and outputing tandem duplications ..." << std::endl); }
+   int countTandemDuplications = 0;
+   std::vector<SPLIT_READ> good;
+   std::vector<std::pair<unsigned, unsigned> > events;
+   for (size_t i = 0; i < boxes.size(); i++) {
+      goodReadsAndEvents(AllReads, boxes[i], good, events);
+      for (size_t e = 0; e < events.size(); e++) {
+         Indel4output ev = breakpointEvent(good, events[e].first, events[e].second, CurrentChr);
+         if (ev.Support < userSettings->NumRead2ReportCutOff || !IsGoodTD(good, ev, ev.RealStart, ev.RealEnd, currentState)) continue;        /* :1262 */
+         if (good[ev.Start].IndelSize < userSettings->BalanceCutoff || ReportEvent(good, ev.Start, ev.End)) {                                  /* :1263-1271 */
+            OutputTDs(good, CurrentChr, ev.Start, ev.End, ev.RealStart, ev.RealEnd, TDOutf);
+            NumberOfTDInstances++;
+            countTandemDuplications++;
+         }
+      }
+   }
+   if (nonTemplate) { LOG_INFO(*logStream << "Tandem duplications with non-template sequence (TD_NT): " << countTandemDuplications << std::endl << std::endl); }
+   else { LOG_INFO(*logStream << "Tandem duplications: " << NumberOfTDInstances << std::endl << std::endl); }
+}
 
 void SortOutputDI(ControlState &currentState, const unsigned &NumBoxes, const std::string &CurrentChr, std::vector<SPLIT_READ> &Reads, std::vector<unsigned> DI[],
                   std::ofstream &DIOutf, std::ofstream &InvOutf)
@@ -1086,7 +1134,6 @@ int SearchVariant::Search(BDData &bdData, ControlState &currentState, const unsi
    Count_Var_Plus += counts[1];
    Count_Var_Minus += counts[2];
    LOG_INFO(*logStream << "Total: " << Count_Var << "\t+" << Count_Var_Plus << "\t-" << Count_Var_Minus << std::endl);
-   prepareBoxes(currentState.Reads_SR, Vars, NumBoxes);
    outputResults(bdData, currentState, Vars, NumBoxes, window);
    delete[] Vars;
    return EXIT_SUCCESS;
@@ -1113,7 +1160,6 @@ int searchTandemDuplications(ControlState &currentState, unsigned NumBoxes, cons
    int counts[3] = {0, 0, 0};
    replayDriver(PG_SV_TD, currentState, NumBoxes, window, TD, counts);
    std::ofstream TDOutf(userSettings->getTDOutputFilename().c_str(), std::ios::app);
-   prepareBoxes(currentState.Reads_SR, TD, NumBoxes);
    SortAndOutputTandemDuplications(currentState, NumBoxes, window.getChromosome()->getSeq(), currentState.Reads_SR, TD, TDOutf, false);
    delete[] TD;
    return EXIT_SUCCESS;
@@ -1126,7 +1172,6 @@ int searchTandemDuplicationsNT(ControlState &currentState, unsigned NumBoxes, co
    int counts[3] = {0, 0, 0};
    replayDriver(PG_SV_TD_NT, currentState, NumBoxes, window, TD_NT, counts);
    std::ofstream TDOutf(userSettings->getTDOutputFilename().c_str(), std::ios::app);
-   prepareBoxes(currentState.Reads_SR, TD_NT, NumBoxes);
    SortAndOutputTandemDuplications(currentState, NumBoxes, window.getChromosome()->getSeq(), currentState.Reads_SR, TD_NT, TDOutf, true);
    TDOutf.close();
    delete[] TD_NT;
