@@ -1,5 +1,6 @@
 """Seeded Pindel-text input that is dense in the events whose reporters order their boxes with inlined loops: deletions with
-non-template bases (SortOutputDI) and inversions with and without non-template bases (OutputSorter), many reads per event
+non-template bases (SortOutputDI) and inversions with and without non-template bases (OutputSorter), plus plain deletions,
+short insertions and tandem duplications for the other three reporters, many reads per event
 from both anchor strands, a handful of breakpoint offsets (ties in every key, the same fragment seen several times), events
 a few bases apart (several events per box).  Test input only: both programs must write the same files from it."""
 import numpy as np
@@ -20,6 +21,10 @@ def _model(ref, kind, a, k, sz, nt, L):
     rest = L - k - len(nt)
     if kind in ("D", "DI"):
         second = ref[a + sz:a + sz + rest]
+    elif kind == "SI":                      # short insertion: the non-template bases, then straight on
+        second = ref[a:a + rest]
+    elif kind == "TD":                      # tandem duplication: the unit's end followed by its start
+        second = ref[a - sz:a - sz + rest]
     else:                                   # inversion: the far side read backwards, complemented
         second = COMP[ref[a + sz - rest:a + sz][::-1]]
     return np.concatenate([first, nt, second])
@@ -33,12 +38,13 @@ def make(seed=11, G=400_000, L=100, insert=500):
     events = []
     pos = 20_000
     while pos < G - 30_000:
-        kind = str(rng.choice(["DI", "DI", "INV", "INV", "INV_NT", "D"]))
-        sz = int(rng.integers(5, 300)) if kind in ("D", "DI") else int(rng.integers(120, 1500))
-        nt = ACGT[rng.integers(0, 4, int(rng.integers(1, 9)))] if kind in ("DI", "INV_NT") else ACGT[:0]
+        kind = str(rng.choice(["DI", "DI", "INV", "INV", "INV_NT", "D", "SI", "TD"]))
+        sz = int(rng.integers(5, 300)) if kind in ("D", "DI") else (0 if kind == "SI" else int(rng.integers(120, 1500)))
+        nt = ACGT[rng.integers(0, 4, int(rng.integers(1, 9)))] if kind in ("DI", "INV_NT", "SI") else ACGT[:0]
         events.append((kind, pos, sz, nt))
         if rng.random() < 0.4:              # a second event a few bases on: same box, other breakpoints
-            events.append((kind, pos + int(rng.integers(2, 30)), sz + int(rng.integers(-3, 4)), nt if rng.random() < 0.5 else ACGT[rng.integers(0, 4, len(nt))]))
+            events.append((kind, pos + int(rng.integers(2, 30)), max(0, sz + int(rng.integers(-3, 4))) if kind != "SI" else 0,
+                           nt if rng.random() < 0.5 else ACGT[rng.integers(0, 4, len(nt))]))
         pos += int(rng.integers(3000, 6000))
     lines, n = [], 0
     for kind, a, sz, nt in events:
@@ -50,7 +56,7 @@ def make(seed=11, G=400_000, L=100, insert=500):
                 t = _model(ref, kind, a, k, sz, nt, L)
                 g_first = a - k
             else:                                              # the same event from the other strand
-                a2 = G - (a + sz)
+                a2 = G - a if kind == "SI" else (G - (a - sz) if kind == "TD" else G - (a + sz))
                 k = L - k - len(nt)
                 t = _model(ref_rc, kind, a2, k, sz, _rc(nt), L)
                 g_first = a2 - k

@@ -95,8 +95,9 @@ def sim_prefix_bam(demo, tmp_path, env):
 
 
 def dense_events_live(demo, tmp_path, env):
-    """Input dense in deletions with non-template bases and inversions (tests/dense_events.py): the reporters whose ordering,
-    duplicate scan and event cut are inlined loops (SortOutputDI, OutputSorter::DoSortAndOutputInversions).  No golden files:
+    """Input dense in events of every reporter (tests/dense_events.py) -- above all deletions with non-template bases and
+    inversions, whose reporters carry ordering, duplicate scan and event cut as inlined loops (SortOutputDI,
+    OutputSorter::DoSortAndOutputInversions) -- so that all five supplied reporters run on crowded boxes.  No golden files:
     the pure reference binary (oracle/_ref/pindel_ref) runs beside the drop-in binary on the same seeded input."""
     from oracle import refhook
     from tests import dense_events
@@ -113,11 +114,11 @@ def dense_events_live(demo, tmp_path, env):
     for suf in ("D", "SI", "INV", "TD", "LI", "BP", "CloseEndMapped"):
         a, b = (tmp_path / ("ref_" + suf)).read_bytes(), (tmp_path / ("dropin_" + suf)).read_bytes()
         assert a == b, "%s differs from the reference binary's file (%d vs %d bytes)" % (suf, len(b), len(a))
-    d, inv = (tmp_path / "ref_D").read_text(), (tmp_path / "ref_INV").read_text()
-    n_di = len(re.findall(r"\tNT [1-9]", d))
-    assert n_di >= 20 and inv.count("####") >= 30, (n_di, inv.count("####"))
+    n_events = {suf: sum(1 for line in (tmp_path / ("ref_" + suf)).read_text().split("\n") if line.startswith("####")) for suf in ("D", "SI", "INV", "TD")}
+    n_di = len(re.findall(r"\tNT [1-9]", (tmp_path / "ref_D").read_text()))
+    assert n_di >= 20 and n_events["INV"] >= 15 and n_events["SI"] >= 8 and n_events["TD"] >= 5 and n_events["D"] - n_di >= 8, (n_di, n_events)
     m = re.search(r"(\d+) boxes of the DI / inversion reporters", p.stderr)
-    assert env.get("PG_BRIDGE_HOST_SORT") or int(m.group(1)) >= 60, m.group(0)
+    assert env.get("PG_BRIDGE_HOST_SORT") or int(m.group(1)) >= 40, m.group(0)
     return p
 
 
