@@ -149,3 +149,54 @@ def test_cpp_stage_mirrors_match_oracles(tmp_path):
     assert np.array_equal(o[z:z + idx.size].astype(np.uint32), i_idx)
     assert np.array_equal(o[z + idx.size:z + idx.size + reads.size].astype(np.uint8), i_unique)
     assert np.array_equal(o[z + idx.size + reads.size:z + 2 * idx.size + reads.size].astype(np.uint8), i_event)
+
+
+BD_SRC = os.path.join(ROOT, "tests", "cpp", "host_mirror_bd_test.cpp")
+BD_EXE = os.path.join(ROOT, "tests", "cpp", "host_mirror_bd_test")
+EMUL_DIR = os.path.join(ROOT, "oracle", "_ref")
+
+
+def bd_mirror_case(exe, tmp_path, seed):
+    """Searcher::loadRegion + getCorrespondingSearchWindowClusters against the oracle's position sweep"""
+    from oracle import bdoracle
+    from tests import bd_helpers as BH
+    chr_id, window, ev, q = BH.case(seed, seed % 2 == 0, n_queries=500)
+    ev_sorted = np.array(bdoracle.sort_on_first(bdoracle.normalise(ev), BH.NAMES), dtype=np.int64).reshape(-1, 6)
+    with open(tmp_path / "bd_in.bin", "wb") as f:
+        f.write(struct.pack("<i", len(BH.NAMES)))
+        for name, length in zip(BH.NAMES, BH.LENS):
+            f.write(struct.pack("<i", len(name))); f.write(name.encode()); f.write(struct.pack("<I", length + 2 * BH.SPACER))
+        f.write(struct.pack("<i", ev_sorted.shape[0]))
+        for e in ev_sorted:
+            f.write(struct.pack("<iIIiII", *[int(v) for v in e]))
+        f.write(struct.pack("<iII", chr_id, window[0], window[1]))
+        f.write(struct.pack("<i", q.size)); f.write(q.astype("<u4").tobytes())
+    p = subprocess.run([exe, str(tmp_path / "bd_in.bin"), str(tmp_path / "bd_out.bin")], capture_output=True, text=True, timeout=600)
+    assert p.returncode == 0, p.stderr
+    o = np.fromfile(tmp_path / "bd_out.bin", dtype=np.int32)
+    exp = bdoracle.clusters(ev, BH.NAMES, chr_id, window[0], window[1], q)
+    pos = 0
+    for k, e in enumerate(exp):
+        c = int(o[pos]); pos += 1
+        got = [(int(o[pos + 3 * j]), int(o[pos + 3 * j + 1]) & 0xFFFFFFFF, int(o[pos + 3 * j + 2]) & 0xFFFFFFFF) for j in range(c)]
+        pos += 3 * c
+        assert got == (e or []), (seed, k, int(q[k]), e, got)
+    assert pos == o.size
+
+
+@pytest.mark.skipif(not os.path.exists(os.path.join(EMUL_DIR, "libpg_abi_emul.so")), reason="oracle/_ref/libpg_abi_emul.so not built")
+def test_bd_mirror_host_logic_on_the_emulated_abi(tmp_path):
+    """the header's own work (event marshalling, name ranks, two-call buffer protocol) checked without a GPU: the same program
+    linked against the CPU emulation of the ABI (tests/emul/abi_emul.cpp) instead of libpindel_pg.so"""
+    exe = str(tmp_path / "host_mirror_bd_test_emul")
+    subprocess.check_call(["/usr/bin/g++", "-O2", "-std=c++11", "-Wall", "-Wextra", "-o", exe, BD_SRC, "-L" + EMUL_DIR, "-lpg_abi_emul",
+                           "-Wl,-rpath," + EMUL_DIR])
+    for seed in (1, 2, 3, 6):
+        bd_mirror_case(exe, tmp_path, seed)
+
+
+@pytest.mark.gpu
+def test_bd_mirror_matches_oracle(tmp_path):
+    exe = build_exe(BD_SRC, BD_EXE)
+    for seed in (1, 2, 3, 6):
+        bd_mirror_case(exe, tmp_path, seed)
