@@ -138,7 +138,10 @@ int pg_set_reference(pg_ctx *ctx, int32_t n_chr, const char *const *seq, const u
 /* g_maxMismatch as derived from -e/-E (createProbTable, src/pindel.cpp:781-819); out has 500 entries. */
 int pg_max_mismatch_table(pg_ctx *ctx, uint32_t *out);
 
-/* The reference seam, batched (host buffers in, host buffers out; copies are inside the call). */
+/* The reference seam, batched (host buffers in, host buffers out; copies are inside the call).  Batches of 256 k reads and
+ * more are cut into chunks (at most 512 k reads) whose uploads, kernels and downloads overlap; the per-read argument checks
+ * (offsets, chromosome numbers, read lengths) then run chunk by chunk, so an invalid read late in the batch is reported after
+ * earlier chunks were searched: on any error the contents of `res` are undefined and nothing stays resident. */
 int pg_close_end(pg_ctx *ctx, const pg_reads *in, pg_results *res);   /* GetCloseEnd   for every read */
 int pg_far_end(pg_ctx *ctx, const pg_reads *in, pg_results *res);     /* SearchFarEnd  for every read with a close end */
 int pg_search(pg_ctx *ctx, const pg_reads *in, pg_results *res);      /* both, without BreakDancer clusters unless given up front */
