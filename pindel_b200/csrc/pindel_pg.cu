@@ -639,6 +639,20 @@ int pg_set_reference(pg_ctx *ctx, int32_t n_chr, const char *const *seq, const u
    if (ctx->chroms_d) { cudaFree(ctx->chroms_d); ctx->chroms_d = nullptr; }
    const size_t CHUNK = (size_t)64 << 20;        // bases per staging chunk (multiple of 32)
    uint8_t *stage = nullptr;
+   // whatever way this function is left: the staging buffer goes, and a reference that was not completed leaves no
+   // half-built chromosome list behind (the context then has no reference, as before the first call)
+   struct Cleanup {
+      pg_ctx *ctx; uint8_t *&stage; bool done;
+      ~Cleanup()
+      {
+         if (stage) cudaFree(stage);
+         if (done) return;
+         for (void *p : ctx->chrom_allocs) cudaFree(p);
+         ctx->chrom_allocs.clear();
+         ctx->chroms_h.clear();
+         if (ctx->chroms_d) { cudaFree(ctx->chroms_d); ctx->chroms_d = nullptr; }
+      }
+   } cleanup{ctx, stage, false};
    size_t maxlen = 0;
    for (int i = 0; i < n_chr; i++) if (len[i] > maxlen) maxlen = len[i];
    CU(cudaMalloc((void **)&stage, maxlen < CHUNK ? (maxlen ? maxlen : 1) : CHUNK));
@@ -669,9 +683,9 @@ int pg_set_reference(pg_ctx *ctx, int32_t n_chr, const char *const *seq, const u
       c.nwords = nwords;
       ctx->chroms_h.push_back(c);
    }
-   CU(cudaFree(stage));
    CU(cudaMalloc((void **)&ctx->chroms_d, sizeof(PgChrom) * (size_t)n_chr));
    CU(cudaMemcpy(ctx->chroms_d, ctx->chroms_h.data(), sizeof(PgChrom) * (size_t)n_chr, cudaMemcpyHostToDevice));
+   cleanup.done = true;
    return PG_OK;
 }
 
