@@ -1,0 +1,53 @@
+"""scripts/emul_search_campaign.py -- CPU-only: the search kernel's warp program (pg_warp.cuh, run by the 32-fiber lane emulator of
+tests/emul/) against the oracle port on random option sets, read lengths and references with repeats, in the way
+tests/test_gpu_fuzz.py does on the hardware.  Slow (the emulator runs a few hundred reads per second); not part of pytest.
+    python scripts/emul_search_campaign.py [--rounds N] [--reads M] [--seed S]"""
+import argparse
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--rounds", type=int, default=12)
+    ap.add_argument("--reads", type=int, default=400)
+    ap.add_argument("--seed", type=int, default=2026)
+    a = ap.parse_args()
+    from oracle import pgoracle, refhook
+    from pindel_b200 import runs as R, synth
+    from tests import helpers as H
+    from tests.emul import emul
+    lib = emul.build()
+    rng = np.random.default_rng(a.seed)
+    total = 0
+    for r in range(a.rounds):
+        st = dict(max_range_index=int(rng.integers(0, 5)), add_mm=int(rng.integers(1, 4)), min_perfect=int(rng.integers(0, 8)),
+                  min_close=int(rng.integers(4, 14)), max_mismatch_rate=float(rng.choice([0.0, 0.01, 0.02, 0.05, 0.1])),
+                  seq_error_rate=float(rng.choice([0.005, 0.01, 0.02, 0.04])), sensitivity=float(rng.choice([0.9, 0.95, 0.99])))
+        L = int(rng.choice([40, 64, 75, 100, 101, 150, 200, 250]))
+        ref = synth.make_reference(int(rng.integers(250_000, 400_000)), int(rng.integers(1, 1 << 30)),
+                                   n_runs=[(int(rng.integers(20_000, 200_000)), int(rng.integers(1, 3000)))])
+        padded = synth.pad_reference(ref)
+        batch = synth.make_reads(ref, a.reads, L, seed=int(rng.integers(1, 1 << 30)), max_del=int(rng.choice([200, 1000, 20000])))
+        blob, off = batch.blob()
+        prm = emul.make_params(lib, **st)
+        out, pool = emul.search(lib, prm, [padded], blob, off, batch.matched_d, batch.matched_rel_pos, batch.insert_size)
+        assert (out["flags"] & (R.F_TOOLONG | R.F_OVERFLOW)).sum() == 0
+        got = R.per_read(out, pool, blob, off)
+        P = pgoracle.default_params(max_range_index=st["max_range_index"], additional_mismatch=st["add_mm"], min_perfect_match=st["min_perfect"],
+                                    min_close=st["min_close"], max_mismatch_rate=st["max_mismatch_rate"], seq_error_rate=st["seq_error_rate"],
+                                    sensitivity=st["sensitivity"])
+        stream, _ = pgoracle.search(P, [padded], blob, off, batch.matched_d, batch.matched_rel_pos, batch.insert_size, threads=8)
+        H.compare(refhook.parse_stream(stream, batch.n), got, "round %d L=%d %s" % (r, L, st))
+        total += batch.n
+        print("round %d ok: L=%d %s" % (r, L, st), flush=True)
+    print("campaign clean: %d rounds, %d reads, warp program (emulated) == oracle port" % (a.rounds, total))
+
+
+if __name__ == "__main__":
+    main()
