@@ -193,10 +193,3 @@ def test_bd_mirror_host_logic_on_the_emulated_abi(tmp_path):
                            "-Wl,-rpath," + EMUL_DIR])
     for seed in (1, 2, 3, 6):
         bd_mirror_case(exe, tmp_path, seed)
-
-
-@pytest.mark.gpu
-def test_bd_mirror_matches_oracle(tmp_path):
-    exe = build_exe(BD_SRC, BD_EXE)
-    for seed in (1, 2, 3, 6):
-        bd_mirror_case(exe, tmp_path, seed)
