@@ -12,6 +12,14 @@ def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with `-m gpu`)")
 
 
+def pytest_collection_modifyitems(config, items):
+    """The whole-program scenarios (the reference host on the library, tens of seconds each) run after the kernel-level tests:
+    under `-x` a scenario that fails must not hide the parity tests that would follow it alphabetically."""
+    late = [it for it in items if "test_gpu_dropin" in it.nodeid]
+    if late:
+        items[:] = [it for it in items if "test_gpu_dropin" not in it.nodeid] + late
+
+
 @pytest.fixture(scope="session")
 def oracle_lib():
     from oracle import pgoracle
