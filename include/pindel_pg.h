@@ -473,9 +473,10 @@ double pg_rp_last_kernel_ms(pg_ctx *ctx);      /* CUDA-event duration of the las
  *   out == NULL: the inflated stream stays on the device (pg_bgzf_device_data) for a consumer that parses it there;
  *   out != NULL: it is also copied to the caller's buffer (out_cap bytes; PG_ERR_RUNS_CAP if too small).
  * *out_len = inflated size.  PG_ERR_DATA: not a BGZF file / corrupt block (text in pg_last_error).
- * Damaged files: the decoder rejects over-subscribed Huffman code sets but, unlike zlib's inflate_table, accepts incomplete
- * ones, so a corrupted dynamic block that zlib refuses can decode to garbage here; use check_crc = 1 (what htslib does on
- * every block) for the same failure behaviour as the reference on damaged input -- the CRC then rejects such a block.
+ * Damaged files: Huffman code sets are judged as zlib's inflate_table judges them -- over-subscribed sets are refused, and
+ * incomplete ones too except the empty set and a single one-bit literal/length or distance code -- so a corrupted
+ * dynamic block is refused here when zlib refuses it, with or without check_crc (tests/test_bgzf_emulator.py builds such
+ * blocks bit by bit).  check_crc = 1 is what htslib does on every block and is the setting of the drop-in.
  * ------------------------------------------------------------------------------------------------------------------ */
 int64_t pg_bgzf_inflated_size(const uint8_t *file, size_t file_len);   /* host only: -1 if the header walk fails */
 int pg_bgzf_inflate(pg_ctx *ctx, const uint8_t *file, size_t file_len, uint8_t *out, size_t out_cap, size_t *out_len, int32_t check_crc);

@@ -165,9 +165,11 @@ PGZ_HD void pgz_drop(PgzBits &b, uint32_t n) { b.buf >>= n; b.cnt -= n; }
 PGZ_HD uint32_t pgz_take(PgzBits &b, uint32_t n) { const uint32_t v = pgz_peek(b, n); pgz_drop(b, n); return v; }
 
 // Build the canonical tree of n code lengths and its fast table (bits-wide, indexed by the next input bits, LSB first).
-// Returns 0, or PGZ_ERR_HEADER for an over-subscribed set of lengths (incomplete sets are accepted, like zlib accepts a
-// single distance code; an unassigned pattern then decodes to PGZ_ERR_CODE).
-PGZ_FN int pgz_build(const uint8_t *lengths, int n, PgzTree &t, uint16_t *fast, int bits)
+// Returns 0, or PGZ_ERR_HEADER for a set of lengths zlib's table builder refuses: an over-subscribed set, and an
+// incomplete one unless it is empty or -- for the literal/length and distance codes only (code_length_code = false) --
+// a single code of length 1 (zlib's inflate_table: "left > 0 && (type == CODES || max != 1)").  In an accepted
+// incomplete set an unassigned pattern decodes to PGZ_ERR_CODE.
+PGZ_FN int pgz_build(const uint8_t *lengths, int n, PgzTree &t, uint16_t *fast, int bits, bool code_length_code = false)
 {
    for (int l = 0; l < 16; l++) t.count[l] = 0;
    for (int s = 0; s < n; s++) t.count[lengths[s]]++;
@@ -179,6 +181,11 @@ PGZ_FN int pgz_build(const uint8_t *lengths, int n, PgzTree &t, uint16_t *fast, 
       left -= t.count[l];
       if (left < 0) return PGZ_ERR_HEADER;
       if (l < 15) offs[l + 1] = (uint16_t)(offs[l] + t.count[l]);
+   }
+   if (left > 0) {
+      int longest = 15;
+      while (longest > 0 && t.count[longest] == 0) longest--;
+      if (longest != 0 && (code_length_code || longest != 1)) return PGZ_ERR_HEADER;
    }
    for (int s = 0; s < n; s++)
       if (lengths[s]) t.symbol[offs[lengths[s]]++] = (uint16_t)s;
@@ -271,8 +278,8 @@ PGZ_FN int pgz_inflate(const uint8_t *in, uint32_t in_len, uint8_t *out, uint32_
          for (int s = 256; s < 280; s++) lengths[s] = 7;
          for (int s = 280; s < 288; s++) lengths[s] = 8;
          pgz_build(lengths, 288, sc->lit, sc->fast_lit, PGZ_LIT_BITS);
-         for (int s = 0; s < 30; s++) lengths[s] = 5;
-         pgz_build(lengths, 30, sc->dist, sc->fast_dist, PGZ_DIST_BITS);
+         for (int s = 0; s < 32; s++) lengths[s] = 5;      // 30 and 31 take part in the code (3.2.6) and are refused when met
+         pgz_build(lengths, 32, sc->dist, sc->fast_dist, PGZ_DIST_BITS);
       } else {                               // dynamic codes (3.2.7)
          pgz_refill(b);
          const int nlen = (int)pgz_take(b, 5) + 257, ndist = (int)pgz_take(b, 5) + 1, ncode = (int)pgz_take(b, 4) + 4;
@@ -284,7 +291,7 @@ PGZ_FN int pgz_inflate(const uint8_t *in, uint32_t in_len, uint8_t *out, uint32_
             cl[len_order[i]] = (uint8_t)pgz_take(b, 3);
          }
          // the code-length code borrows the literal tree's storage and the distance table's 64 entries
-         if (pgz_build(cl, 19, sc->lit, sc->fast_dist, PGZ_DIST_BITS) != PGZ_OK) { rc = PGZ_ERR_HEADER; break; }
+         if (pgz_build(cl, 19, sc->lit, sc->fast_dist, PGZ_DIST_BITS, true) != PGZ_OK) { rc = PGZ_ERR_HEADER; break; }
          int idx = 0;
          while (idx < nlen + ndist) {
             pgz_refill(b);
