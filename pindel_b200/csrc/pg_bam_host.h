@@ -62,3 +62,28 @@ static inline long pgb_validate_run(uint32_t n_seg, uint64_t first, uint64_t n, 
    *tail = cur;
    return 0;
 }
+
+// The settling loop of pg_bam_index / pg_bam_index_run, shared with the CPU-side harness so that its logic is tested without
+// a device: walk_all() walks every segment from its guessed start (pass 0: counts, landing); validate(&forced) is
+// pgb_validate / pgb_validate_run over the host copies; a segment whose guess was not the chain's next record gets the
+// chain's offset as its start and walk_one(s) walks that segment alone -- the segments in front of it are settled and the
+// ones behind it keep their walks, so a stream full of fake records costs one single-segment walk per bad guess instead of
+// a walk over all segments (at most n_seg repairs: each one settles its segment for good).
+// Returns 0, -1 for a corrupt chain, or the first non-zero value a walker returned.  *redone = segments walked again.
+template <class Validate, class WalkAll, class WalkOne>
+static inline int pgb_settle(uint64_t *starts, Validate validate, WalkAll walk_all, WalkOne walk_one, uint32_t *redone)
+{
+   *redone = 0;
+   int rc = walk_all();
+   if (rc != 0) return rc;
+   for (;;) {
+      uint64_t forced = 0;
+      const long v = validate(&forced);
+      if (v < 0) return -1;
+      if (v == 0) return 0;
+      const uint32_t s = (uint32_t)(v - 1);
+      starts[s] = forced;
+      if ((rc = walk_one(s)) != 0) return rc;
+      ++*redone;
+   }
+}

@@ -285,7 +285,10 @@ PG_DEV void pg_flush_queue(PgWarpCtx<LW, TL> &cx, const PgSearch &se, const PgCh
 // unchanged; the filter only decides how many seeds take that path.
 // ------------------------------------------------------------------------------------------------
 #ifdef PG_EMULATE
-static unsigned long long pg_emul_filter_stats[3];    // host build only: seeds in, survivors out, tiles filtered
+#ifndef PG_EMUL_TLS
+#define PG_EMUL_TLS
+#endif
+static PG_EMUL_TLS unsigned long long pg_emul_filter_stats[3];    // host build only: seeds in, survivors out, tiles filtered (per emulated warp's thread)
 #endif
 template <int LW, int TL>
 PG_COLD void pg_filter_prepare(PgWarpSmem<LW, TL> *ws, int arr, uint32_t inv, int L)

@@ -1700,23 +1700,33 @@ int pg_bam_index(pg_ctx *ctx, pg_bam_rec *recs, uint64_t cap, uint64_t *n_recs, 
    std::vector<uint64_t> starts(n_seg), counts(n_seg), landing(n_seg), base(n_seg);
    uint64_t total = 0;
    uint32_t redone = 0;
-   for (;;) {
-      pg_bam_walk_kernel<<<(n_seg + 127) / 128, 128, 0, st>>>(d, n, first, seg, n_seg, (const uint64_t *)ctx->bm_starts.p, (uint64_t *)ctx->bm_counts.p,
-                                                             (uint64_t *)ctx->bm_landing.p, nullptr, nullptr);
+   uint64_t *const starts_d = (uint64_t *)ctx->bm_starts.p, *const counts_d = (uint64_t *)ctx->bm_counts.p, *const landing_d = (uint64_t *)ctx->bm_landing.p;
+   auto walk_all = [&]() -> int {
+      pg_bam_walk_kernel<<<(n_seg + 127) / 128, 128, 0, st>>>(d, n, first, seg, n_seg, starts_d, counts_d, landing_d, nullptr, nullptr);
       CU(cudaGetLastError());
       ctx->bm_launches++;
-      CU(cudaMemcpyAsync(starts.data(), ctx->bm_starts.p, sizeof(uint64_t) * (size_t)n_seg, cudaMemcpyDeviceToHost, st));
-      CU(cudaMemcpyAsync(counts.data(), ctx->bm_counts.p, sizeof(uint64_t) * (size_t)n_seg, cudaMemcpyDeviceToHost, st));
-      CU(cudaMemcpyAsync(landing.data(), ctx->bm_landing.p, sizeof(uint64_t) * (size_t)n_seg, cudaMemcpyDeviceToHost, st));
+      CU(cudaMemcpyAsync(starts.data(), starts_d, sizeof(uint64_t) * (size_t)n_seg, cudaMemcpyDeviceToHost, st));
+      CU(cudaMemcpyAsync(counts.data(), counts_d, sizeof(uint64_t) * (size_t)n_seg, cudaMemcpyDeviceToHost, st));
+      CU(cudaMemcpyAsync(landing.data(), landing_d, sizeof(uint64_t) * (size_t)n_seg, cudaMemcpyDeviceToHost, st));
       CU(cudaStreamSynchronize(st));
-      uint64_t forced = 0;
-      const long v = pgb_validate(n_seg, first, n, seg, starts.data(), counts.data(), landing.data(), &forced, &total);
-      if (v < 0) return fail(ctx, PG_ERR_DATA, "pg_bam_index: the record chain does not end at the end of the stream (truncated or corrupt BAM)");
-      if (v == 0) break;
-      // a guess locked on to bytes that only look like records: walk that segment from the chain's true offset
-      CU(cudaMemcpyAsync((uint64_t *)ctx->bm_starts.p + (v - 1), &forced, sizeof(uint64_t), cudaMemcpyHostToDevice, st));
+      return PG_OK;
+   };
+   // a guess locked on to bytes that only look like records: that segment alone is walked again from the chain's true offset
+   // (the kernel over one segment: its `first` is the segment's own begin, its arrays start at the segment's entries)
+   auto walk_one = [&](uint32_t s) -> int {
+      CU(cudaMemcpyAsync(starts_d + s, &starts[s], sizeof(uint64_t), cudaMemcpyHostToDevice, st));
+      pg_bam_walk_kernel<<<1, 32, 0, st>>>(d, n, first + (uint64_t)s * seg, seg, 1u, starts_d + s, counts_d + s, landing_d + s, nullptr, nullptr);
+      CU(cudaGetLastError());
+      ctx->bm_launches++;
+      CU(cudaMemcpyAsync(&counts[s], counts_d + s, sizeof(uint64_t), cudaMemcpyDeviceToHost, st));
+      CU(cudaMemcpyAsync(&landing[s], landing_d + s, sizeof(uint64_t), cudaMemcpyDeviceToHost, st));
       CU(cudaStreamSynchronize(st));
-      redone++;
+      return PG_OK;
+   };
+   auto validate = [&](uint64_t *forced) { return pgb_validate(n_seg, first, n, seg, starts.data(), counts.data(), landing.data(), forced, &total); };
+   if ((rc = pgb_settle(starts.data(), validate, walk_all, walk_one, &redone)) != 0) {
+      if (rc < 0) return fail(ctx, PG_ERR_DATA, "pg_bam_index: the record chain does not end at the end of the stream (truncated or corrupt BAM)");
+      return rc;
    }
    ctx->bm_last_segments = n_seg;
    ctx->bm_last_redone = redone;
@@ -1776,22 +1786,33 @@ int pg_bam_index_run(pg_ctx *ctx, uint64_t first_record, int32_t n_ref, pg_bam_r
    std::vector<uint64_t> starts(n_seg), counts(n_seg), landing(n_seg), base(n_seg);
    uint64_t total = 0, tail_off = n;
    uint32_t redone = 0;
-   for (;;) {
-      pg_bam_walk_run_kernel<<<(n_seg + 127) / 128, 128, 0, st>>>(d, n, first, seg, n_seg, (const uint64_t *)ctx->bm_starts.p, (uint64_t *)ctx->bm_counts.p,
-                                                                 (uint64_t *)ctx->bm_landing.p, nullptr, nullptr);
+   uint64_t *const starts_d = (uint64_t *)ctx->bm_starts.p, *const counts_d = (uint64_t *)ctx->bm_counts.p, *const landing_d = (uint64_t *)ctx->bm_landing.p;
+   auto walk_all = [&]() -> int {
+      pg_bam_walk_run_kernel<<<(n_seg + 127) / 128, 128, 0, st>>>(d, n, first, seg, n_seg, starts_d, counts_d, landing_d, nullptr, nullptr);
       CU(cudaGetLastError());
       ctx->bm_launches++;
-      CU(cudaMemcpyAsync(starts.data(), ctx->bm_starts.p, sizeof(uint64_t) * (size_t)n_seg, cudaMemcpyDeviceToHost, st));
-      CU(cudaMemcpyAsync(counts.data(), ctx->bm_counts.p, sizeof(uint64_t) * (size_t)n_seg, cudaMemcpyDeviceToHost, st));
-      CU(cudaMemcpyAsync(landing.data(), ctx->bm_landing.p, sizeof(uint64_t) * (size_t)n_seg, cudaMemcpyDeviceToHost, st));
+      CU(cudaMemcpyAsync(starts.data(), starts_d, sizeof(uint64_t) * (size_t)n_seg, cudaMemcpyDeviceToHost, st));
+      CU(cudaMemcpyAsync(counts.data(), counts_d, sizeof(uint64_t) * (size_t)n_seg, cudaMemcpyDeviceToHost, st));
+      CU(cudaMemcpyAsync(landing.data(), landing_d, sizeof(uint64_t) * (size_t)n_seg, cudaMemcpyDeviceToHost, st));
       CU(cudaStreamSynchronize(st));
-      uint64_t forced = 0;
-      const long v = pgb_validate_run(n_seg, first, n, seg, starts.data(), counts.data(), landing.data(), &forced, &total, &tail_off);
-      if (v < 0) return fail(ctx, PG_ERR_DATA, "pg_bam_index_run: a block_size in the record chain cannot be a record (wrong first_record or corrupt BAM)");
-      if (v == 0) break;
-      CU(cudaMemcpyAsync((uint64_t *)ctx->bm_starts.p + (v - 1), &forced, sizeof(uint64_t), cudaMemcpyHostToDevice, st));
+      return PG_OK;
+   };
+   auto walk_one = [&](uint32_t s) -> int {      // one segment again, from the chain's offset (see pg_bam_index)
+      CU(cudaMemcpyAsync(starts_d + s, &starts[s], sizeof(uint64_t), cudaMemcpyHostToDevice, st));
+      pg_bam_walk_run_kernel<<<1, 32, 0, st>>>(d, n, first + (uint64_t)s * seg, seg, 1u, starts_d + s, counts_d + s, landing_d + s, nullptr, nullptr);
+      CU(cudaGetLastError());
+      ctx->bm_launches++;
+      CU(cudaMemcpyAsync(&counts[s], counts_d + s, sizeof(uint64_t), cudaMemcpyDeviceToHost, st));
+      CU(cudaMemcpyAsync(&landing[s], landing_d + s, sizeof(uint64_t), cudaMemcpyDeviceToHost, st));
       CU(cudaStreamSynchronize(st));
-      redone++;
+      return PG_OK;
+   };
+   auto validate = [&](uint64_t *forced) {
+      return pgb_validate_run(n_seg, first, n, seg, starts.data(), counts.data(), landing.data(), forced, &total, &tail_off);
+   };
+   if ((rc = pgb_settle(starts.data(), validate, walk_all, walk_one, &redone)) != 0) {
+      if (rc < 0) return fail(ctx, PG_ERR_DATA, "pg_bam_index_run: a block_size in the record chain cannot be a record (wrong first_record or corrupt BAM)");
+      return rc;
    }
    ctx->bm_last_segments = n_seg;
    ctx->bm_last_redone = redone;

@@ -10,9 +10,12 @@
 extern "C" {
 
 int bamemu_rec_size(void) { return (int)sizeof(PgBamRec); }
+static uint64_t g_last_walks = 0;
+uint64_t bamemu_last_walks(void) { return g_last_walks; }
 
 // seg: segment size (0 = the product's).  Returns the number of records (recs may be NULL to count), -1 not BAM,
 // -2 corrupt chain.  stats[0] = segments, stats[1] = segments that had to be walked again, stats[2] = first record offset.
+// bamemu_last_walks(): segment walks of pass 0 in the last call (= segments + walked again: a repair walks one segment).
 long bamemu_index(const uint8_t *d, uint64_t n, uint64_t seg, PgBamRec *recs, uint64_t cap, uint64_t *stats)
 {
    int32_t n_ref = 0;
@@ -28,22 +31,21 @@ long bamemu_index(const uint8_t *d, uint64_t n, uint64_t seg, PgBamRec *recs, ui
       for (uint64_t c = b0; c < b1; c++)
          if (pgb_plausible_chain(d, n, c, n_ref)) { starts[s] = c; break; }
    }
-   uint64_t redone = 0, total = 0;
-   for (;;) {
-      for (uint32_t s = 0; s < n_seg; s++) {      // pg_bam_walk_kernel, pass 0
-         if (starts[s] == PGB_NONE) { counts[s] = 0; landing[s] = PGB_NONE; continue; }
-         const uint64_t b1 = first + (uint64_t)(s + 1) * seg;
-         uint64_t k = 0;
-         landing[s] = pgb_walk(d, n, starts[s], b1 < n ? b1 : n, NULL, &k);
-         counts[s] = landing[s] == PGB_NONE ? 0 : k;
-      }
-      uint64_t forced = 0;
-      const long v = pgb_validate(n_seg, first, n, seg, starts.data(), counts.data(), landing.data(), &forced, &total);
-      if (v < 0) return -2;
-      if (v == 0) break;
-      starts[(size_t)(v - 1)] = forced;
-      redone++;
-   }
+   uint64_t total = 0;
+   uint32_t redone = 0, walks = 0;
+   auto walk_one = [&](uint32_t s) {              // pg_bam_walk_kernel, pass 0, one segment
+      walks++;
+      if (starts[s] == PGB_NONE) { counts[s] = 0; landing[s] = PGB_NONE; return 0; }
+      const uint64_t b1 = first + (uint64_t)(s + 1) * seg;
+      uint64_t k = 0;
+      landing[s] = pgb_walk(d, n, starts[s], b1 < n ? b1 : n, NULL, &k);
+      counts[s] = landing[s] == PGB_NONE ? 0 : k;
+      return 0;
+   };
+   auto walk_all = [&]() { for (uint32_t s = 0; s < n_seg; s++) walk_one(s); return 0; };
+   auto validate = [&](uint64_t *forced) { return pgb_validate(n_seg, first, n, seg, starts.data(), counts.data(), landing.data(), forced, &total); };
+   if (pgb_settle(starts.data(), validate, walk_all, walk_one, &redone) != 0) return -2;
+   g_last_walks = walks;
    if (stats) { stats[0] = n_seg; stats[1] = redone; stats[2] = first; }
    if (!recs) return (long)total;
    if (cap < total) return -3;
@@ -72,22 +74,23 @@ long bamemu_index_run(const uint8_t *d, uint64_t n, uint64_t first, int32_t n_re
       for (uint64_t c = b0; c < b1; c++)
          if (pgb_plausible_chain(d, n, c, n_ref)) { starts[s] = c; break; }
    }
-   uint64_t redone = 0, total = 0, tail = n;
-   for (;;) {
-      for (uint32_t s = 0; s < n_seg; s++) {      // pg_bam_walk_run_kernel, pass 0
-         if (starts[s] == PGB_NONE) { counts[s] = 0; landing[s] = PGB_NONE; continue; }
-         const uint64_t b1 = first + (uint64_t)(s + 1) * seg;
-         uint64_t k = 0;
-         landing[s] = pgb_walk_run(d, n, starts[s], b1 < n ? b1 : n, NULL, &k);
-         counts[s] = landing[s] == PGB_NONE ? 0 : k;
-      }
-      uint64_t forced = 0;
-      const long v = pgb_validate_run(n_seg, first, n, seg, starts.data(), counts.data(), landing.data(), &forced, &total, &tail);
-      if (v < 0) return -2;
-      if (v == 0) break;
-      starts[(size_t)(v - 1)] = forced;
-      redone++;
-   }
+   uint64_t total = 0, tail = n;
+   uint32_t redone = 0, walks = 0;
+   auto walk_one = [&](uint32_t s) {              // pg_bam_walk_run_kernel, pass 0, one segment
+      walks++;
+      if (starts[s] == PGB_NONE) { counts[s] = 0; landing[s] = PGB_NONE; return 0; }
+      const uint64_t b1 = first + (uint64_t)(s + 1) * seg;
+      uint64_t k = 0;
+      landing[s] = pgb_walk_run(d, n, starts[s], b1 < n ? b1 : n, NULL, &k);
+      counts[s] = landing[s] == PGB_NONE ? 0 : k;
+      return 0;
+   };
+   auto walk_all = [&]() { for (uint32_t s = 0; s < n_seg; s++) walk_one(s); return 0; };
+   auto validate = [&](uint64_t *forced) {
+      return pgb_validate_run(n_seg, first, n, seg, starts.data(), counts.data(), landing.data(), forced, &total, &tail);
+   };
+   if (pgb_settle(starts.data(), validate, walk_all, walk_one, &redone) != 0) return -2;
+   g_last_walks = walks;
    if (stats) { stats[0] = n_seg; stats[1] = redone; stats[2] = first; stats[3] = tail; }
    if (!recs) return (long)total;
    if (cap < total) return -3;

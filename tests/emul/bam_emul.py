@@ -24,6 +24,7 @@ def build(force=False):
     lib.bamemu_index.argtypes = [C.c_void_p, C.c_uint64, C.c_uint64, C.c_void_p, C.c_uint64, C.c_void_p]
     lib.bamemu_index_run.restype = C.c_long
     lib.bamemu_index_run.argtypes = [C.c_void_p, C.c_uint64, C.c_uint64, C.c_int32, C.c_uint64, C.c_void_p, C.c_uint64, C.c_void_p]
+    lib.bamemu_last_walks.restype = C.c_uint64
     assert lib.bamemu_rec_size() == REC_DT.itemsize
     return lib
 

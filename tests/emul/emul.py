@@ -19,7 +19,7 @@ def build(force=False):
     srcs = [os.path.join(HERE, "pg_emul.cpp")] + [os.path.join(CSRC, f) for f in
                                                    ("pg_warp.cuh", "pg_warp_types.h", "pg_pack.h", "pg_params.h")]
     if force or not os.path.exists(LIB) or any(os.path.getmtime(s) > os.path.getmtime(LIB) for s in srcs):
-        subprocess.check_call(["/usr/bin/g++", "-O1", "-g", "-fPIC", "-shared", "-Wall", "-Wno-unused-function",
+        subprocess.check_call(["/usr/bin/g++", "-O2", "-g", "-fPIC", "-shared", "-pthread", "-Wall", "-Wno-unused-function", "-Wno-maybe-uninitialized",
                                "-Wno-unknown-pragmas"] + os.environ.get("PG_EMUL_CXXFLAGS", "").split() + ["-o", LIB, srcs[0]])
     return C.CDLL(LIB)
 

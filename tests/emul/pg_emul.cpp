@@ -10,10 +10,39 @@
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
-#include <ucontext.h>
+#include <atomic>
+#include <mutex>
+#include <thread>
 #include <vector>
 
+// Fibers switch either through a 12-instruction stack swap (x86-64, the default: no system call) or through ucontext
+// (-DPG_EMUL_UCONTEXT, and under AddressSanitizer, which knows swapcontext but not a hand-made switch; glibc's swapcontext
+// saves and restores the signal mask with a system call per switch, a third of the emulator's time).
+#if defined(__SANITIZE_ADDRESS__) && !defined(PG_EMUL_UCONTEXT)
+#define PG_EMUL_UCONTEXT 1
+#endif
+#if !defined(__x86_64__) && !defined(PG_EMUL_UCONTEXT)
+#define PG_EMUL_UCONTEXT 1
+#endif
+#ifdef PG_EMUL_UCONTEXT
+#include <ucontext.h>
+#else
+extern "C" void pgemu_switch(void **save_sp, void *load_sp) __attribute__((visibility("hidden")));
+asm(".text\n"
+    ".hidden pgemu_switch\n"
+    ".globl pgemu_switch\n"
+    ".type pgemu_switch,@function\n"
+    "pgemu_switch:\n"                      // callee-saved registers onto the old stack, stack pointers exchanged, popped from the new one
+    "   pushq %rbp\n   pushq %rbx\n   pushq %r12\n   pushq %r13\n   pushq %r14\n   pushq %r15\n"
+    "   movq %rsp, (%rdi)\n"
+    "   movq %rsi, %rsp\n"
+    "   popq %r15\n   popq %r14\n   popq %r13\n   popq %r12\n   popq %rbx\n   popq %rbp\n"
+    "   ret\n"
+    ".size pgemu_switch,.-pgemu_switch\n");
+#endif
+
 #define PG_EMULATE 1
+#define PG_EMUL_TLS thread_local
 #define PG_DEV static inline
 #define PG_COLD static
 #define PG_PIN(x) ((void)(x))
@@ -21,8 +50,13 @@ struct uint2 { uint32_t x, y; };
 
 enum { OP_NONE, OP_BALLOT, OP_ANY, OP_SHFL, OP_SHFL_UP, OP_MAX, OP_ADD, OP_OR, OP_SYNC };
 struct Emu {
+#ifdef PG_EMUL_UCONTEXT
    ucontext_t sched;
    ucontext_t lane_ctx[32];
+#else
+   void *sched_sp;
+   void *lane_sp[32];
+#endif
    std::vector<char> stacks[32];
    int cur;
    bool done[32];
@@ -33,20 +67,32 @@ struct Emu {
    void (*body)(void *);
    void *arg;
 };
-static Emu *E;
+// one emulated warp per OS thread (pgemu_search runs several at once): the running warp of this thread
+static thread_local Emu *E;
+
+#ifdef PG_EMUL_UCONTEXT
+static inline void emu_to_sched(Emu *e, int lane) { swapcontext(&e->lane_ctx[lane], &e->sched); }
+static inline void emu_to_lane(Emu *e, int lane) { swapcontext(&e->sched, &e->lane_ctx[lane]); }
+#else
+static inline void emu_to_sched(Emu *e, int lane) { pgemu_switch(&e->lane_sp[lane], e->sched_sp); }
+static inline void emu_to_lane(Emu *e, int lane) { pgemu_switch(&e->sched_sp, e->lane_sp[lane]); }
+#endif
 
 static uint32_t emu_collective(int op, uint32_t v, int aux)
 {
-   int me = E->cur;
-   E->op[me] = op; E->in[me] = v; E->aux[me] = aux;
-   swapcontext(&E->lane_ctx[me], &E->sched);
-   return E->out[me];
+   Emu *e = E;
+   int me = e->cur;
+   e->op[me] = op; e->in[me] = v; e->aux[me] = aux;
+   emu_to_sched(e, me);
+   return e->out[me];
 }
 static void emu_trampoline()
 {
-   E->body(E->arg);
-   E->done[E->cur] = true;
-   swapcontext(&E->lane_ctx[E->cur], &E->sched);
+   Emu *e = E;
+   e->body(e->arg);
+   e->done[e->cur] = true;
+   emu_to_sched(e, e->cur);
+   abort();                               // a finished lane is never resumed
 }
 static void emu_run_warp(void (*body)(void *), void *arg)
 {
@@ -55,11 +101,22 @@ static void emu_run_warp(void (*body)(void *), void *arg)
    emu.body = body; emu.arg = arg;
    for (int i = 0; i < 32; i++) {
       emu.stacks[i].resize(1 << 18);
+#ifdef PG_EMUL_UCONTEXT
       getcontext(&emu.lane_ctx[i]);
       emu.lane_ctx[i].uc_stack.ss_sp = emu.stacks[i].data();
       emu.lane_ctx[i].uc_stack.ss_size = emu.stacks[i].size();
       emu.lane_ctx[i].uc_link = &emu.sched;
       makecontext(&emu.lane_ctx[i], emu_trampoline, 0);
+#else
+      // the frame pgemu_switch pops: six registers, then the trampoline as the return address; above it a null return
+      // address, so that the trampoline starts with the stack alignment of a called function (rsp = 16 k + 8)
+      uintptr_t top = ((uintptr_t)emu.stacks[i].data() + emu.stacks[i].size()) & ~(uintptr_t)15;
+      void **sp = (void **)top;
+      *--sp = NULL;
+      *--sp = (void *)emu_trampoline;
+      for (int r = 0; r < 6; r++) *--sp = NULL;
+      emu.lane_sp[i] = (void *)sp;
+#endif
       emu.done[i] = false; emu.op[i] = OP_NONE;
    }
    for (;;) {
@@ -67,7 +124,7 @@ static void emu_run_warp(void (*body)(void *), void *arg)
       for (int i = 0; i < 32; i++) {
          if (emu.done[i]) { ndone++; continue; }
          emu.cur = i;
-         swapcontext(&emu.sched, &emu.lane_ctx[i]);
+         emu_to_lane(&emu, i);
          if (emu.done[i]) ndone++;
       }
       if (ndone == 32) break;
@@ -113,8 +170,8 @@ PG_DEV uint32_t pg_brev(uint32_t v)
 }
 PG_DEV uint32_t pg_fsr(uint32_t lo, uint32_t hi, uint32_t s) { uint64_t v = ((uint64_t)hi << 32) | lo; return (uint32_t)(v >> (s & 31)); }
 PG_DEV uint32_t pg_fsrc(uint32_t lo, uint32_t hi, uint32_t s) { uint64_t v = ((uint64_t)hi << 32) | lo; if (s > 32) s = 32; return (uint32_t)(v >> s); }
-PG_DEV uint32_t pg_atomic_add(uint32_t *p, uint32_t v) { uint32_t o = *p; *p = o + v; return o; }
-PG_DEV void pg_atomic_add64(unsigned long long *p, unsigned long long v) { *p += v; }
+PG_DEV uint32_t pg_atomic_add(uint32_t *p, uint32_t v) { return __atomic_fetch_add(p, v, __ATOMIC_RELAXED); }
+PG_DEV void pg_atomic_add64(unsigned long long *p, unsigned long long v) { __atomic_fetch_add(p, v, __ATOMIC_RELAXED); }
 PG_DEV uint32_t pg_umax(uint32_t a, uint32_t b) { return a > b ? a : b; }
 PG_DEV uint32_t pg_umin(uint32_t a, uint32_t b) { return a < b ? a : b; }
 PG_DEV uint32_t pg_ldg32(const uint32_t *p) { return *p; }
@@ -161,14 +218,40 @@ static void emu_warp_body(void *p)
    }
 }
 
+// seeds that entered the far rings' filter, seeds that survived it, tiles filtered: the threads' counts, summed when they end
+static unsigned long long g_filter_stats[3];
+static std::mutex g_filter_stats_mutex;
+
+static int emu_thread_count(int n_reads)
+{
+   int t = (int)std::thread::hardware_concurrency();
+   if (const char *e = getenv("PG_EMUL_THREADS")) t = atoi(e);
+   if (t > 16) t = 16;
+   if (t > n_reads / 8) t = n_reads / 8;      // a handful of reads: one warp
+   return t < 1 ? 1 : t;
+}
+
+// The batch on `threads` emulated warps at once, one OS thread each -- like the grid's warps they share nothing but the read
+// ticket, the run pool's allocation counter and the statistics (atomics), and every warp has its own shared-memory image and
+// scratch lists.  As on the device, the order of the runs in the pool then depends on the schedule; the records do not.
 template <int LW, int TL>
 static void run_variant(const PgBatch &bt, const PgParams *prm, const PgChrom *chroms)
 {
-   static PgWarpSmem<LW, TL> ws;
-   memset(&ws, 0, sizeof(ws));
-   EmuArgs<LW, TL> a;
-   a.bt = bt; a.prm = prm; a.chroms = chroms; a.ws = &ws;
-   emu_run_warp(emu_warp_body<LW, TL>, &a);
+   const int threads = emu_thread_count(bt.n_reads);
+   auto one_warp = [&]() {
+      PgWarpSmem<LW, TL> *ws = (PgWarpSmem<LW, TL> *)calloc(1, sizeof(PgWarpSmem<LW, TL>));
+      std::vector<PgRun> scratch(3 * (size_t)bt.scratch_cap);
+      EmuArgs<LW, TL> a;
+      a.bt = bt; a.bt.scratch = scratch.data(); a.prm = prm; a.chroms = chroms; a.ws = ws;
+      emu_run_warp(emu_warp_body<LW, TL>, &a);
+      free(ws);
+      std::lock_guard<std::mutex> g(g_filter_stats_mutex);
+      for (int i = 0; i < 3; i++) { g_filter_stats[i] += pg_emul_filter_stats[i]; pg_emul_filter_stats[i] = 0; }
+   };
+   if (threads == 1) { one_warp(); return; }
+   std::vector<std::thread> pool;
+   for (int t = 0; t < threads; t++) pool.emplace_back(one_warp);
+   for (std::thread &t : pool) t.join();
 }
 
 extern "C" {
@@ -191,13 +274,12 @@ int pgemu_search(int n_chr, const char *const *chr_seq, const uint32_t *chr_len,
       chroms[i].nwords = packed[i].nwords;
    }
    alignas(8) uint32_t counters[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-   std::vector<PgRun> scratch(3 * 512);
    PgBatch bt;
    bt.n_reads = n_reads; bt.mode = mode; bt.seq_blob = seq_blob; bt.seq_off = seq_off;
    bt.matched_d = matched_d; bt.matched_rel_pos = matched_rel_pos; bt.insert_size = insert_size;
    bt.chr_id = chr_id; bt.close_info = (const PgCloseInfo *)close_info; bt.regions = (const PgRegion *)regions;
    bt.region_off = region_off; bt.out = (PgReadOut *)out; bt.run_pool = (PgRun *)run_pool;
-   bt.run_pool_cap = run_pool_cap; bt.counters = counters; bt.scratch = scratch.data(); bt.scratch_cap = 512;
+   bt.run_pool_cap = run_pool_cap; bt.counters = counters; bt.scratch = NULL; bt.scratch_cap = 512;      // (scratch: one per warp, run_variant)
    const PgParams *prm = (const PgParams *)params_blob;
    // the same variant choice the library makes: levels needed = max g + ADD + 1, words = longest read / 32
    uint32_t maxlen = 0;
@@ -220,7 +302,8 @@ int pgemu_search(int n_chr, const char *const *chr_seq, const uint32_t *chr_len,
 // seeds that entered the far rings' filter, seeds that survived it, tiles filtered -- since the last call
 void pgemu_filter_stats(unsigned long long *out)
 {
-   for (int i = 0; i < 3; i++) { out[i] = pg_emul_filter_stats[i]; pg_emul_filter_stats[i] = 0; }
+   std::lock_guard<std::mutex> g(g_filter_stats_mutex);
+   for (int i = 0; i < 3; i++) { out[i] = g_filter_stats[i]; g_filter_stats[i] = 0; }
 }
 
 int pgemu_sizes(int which)

@@ -48,6 +48,7 @@ def test_fake_records_inside_tags_are_caught(lib):
         got, stats = bam_emul.index(lib, stream, seg)
         assert same(got, exp), seg
         redone += stats[1]
+        assert lib.bamemu_last_walks() == stats[0] + stats[1]      # a repair walks its segment alone (pgb_settle)
     assert redone > 0                  # some segment boundary fell into a tag and locked on to the fake records
 
 
