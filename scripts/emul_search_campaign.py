@@ -1,7 +1,7 @@
 """scripts/emul_search_campaign.py -- CPU-only: the search kernel's warp program (pg_warp.cuh, run by the 32-fiber lane emulator of
-tests/emul/) against the oracle port on random option sets, read lengths and references with repeats, in the way
-tests/test_gpu_fuzz.py does on the hardware.  Slow (the emulator runs a few hundred reads per second); not part of pytest.
-    python scripts/emul_search_campaign.py [--rounds N] [--reads M] [--seed S]"""
+tests/emul/) against the oracle port on random option sets, read lengths and references with N runs (--repetitive: with repeats and low-complexity stretches), in the way
+tests/test_gpu_fuzz.py does on the hardware.  The emulator runs about 15 k reads per second on 8 host threads; not part of pytest.
+    python scripts/emul_search_campaign.py [--rounds N] [--reads M] [--seed S] [--x LO HI] [--ref-len LO HI]"""
 import argparse
 import os
 import sys
@@ -17,6 +17,10 @@ def main():
     ap.add_argument("--rounds", type=int, default=12)
     ap.add_argument("--reads", type=int, default=400)
     ap.add_argument("--seed", type=int, default=2026)
+    ap.add_argument("--x", type=int, nargs=2, default=[0, 4], help="range of -x (max_range_index), inclusive")
+    ap.add_argument("--ref-len", type=int, nargs=2, default=[250_000, 400_000])
+    ap.add_argument("--repetitive", action="store_true", help="references with near-identical repeats, low-complexity stretches and N runs "
+                    "(tests/test_emulator_filter.py), reads with N: what stresses the far rings' filter")
     a = ap.parse_args()
     from oracle import pgoracle, refhook
     from pindel_b200 import runs as R, synth
@@ -26,14 +30,19 @@ def main():
     rng = np.random.default_rng(a.seed)
     total = 0
     for r in range(a.rounds):
-        st = dict(max_range_index=int(rng.integers(0, 5)), add_mm=int(rng.integers(1, 4)), min_perfect=int(rng.integers(0, 8)),
+        st = dict(max_range_index=int(rng.integers(a.x[0], a.x[1] + 1)), add_mm=int(rng.integers(1, 4)), min_perfect=int(rng.integers(0, 8)),
                   min_close=int(rng.integers(4, 14)), max_mismatch_rate=float(rng.choice([0.0, 0.01, 0.02, 0.05, 0.1])),
                   seq_error_rate=float(rng.choice([0.005, 0.01, 0.02, 0.04])), sensitivity=float(rng.choice([0.9, 0.95, 0.99])))
         L = int(rng.choice([40, 64, 75, 100, 101, 150, 200, 250]))
-        ref = synth.make_reference(int(rng.integers(250_000, 400_000)), int(rng.integers(1, 1 << 30)),
-                                   n_runs=[(int(rng.integers(20_000, 200_000)), int(rng.integers(1, 3000)))])
+        if a.repetitive:
+            from tests.test_emulator_filter import repetitive_reference
+            ref = repetitive_reference(int(rng.integers(a.ref_len[0], a.ref_len[1])), int(rng.integers(1, 1 << 30)))
+            batch = synth.make_reads(ref, a.reads, L, seed=int(rng.integers(1, 1 << 30)), max_del=int(rng.choice([1000, 6000, 20000])), n_rate=0.004)
+        else:
+            ref = synth.make_reference(int(rng.integers(a.ref_len[0], a.ref_len[1])), int(rng.integers(1, 1 << 30)),
+                                       n_runs=[(int(rng.integers(20_000, 200_000)), int(rng.integers(1, 3000)))])
+            batch = synth.make_reads(ref, a.reads, L, seed=int(rng.integers(1, 1 << 30)), max_del=int(rng.choice([200, 1000, 20000])))
         padded = synth.pad_reference(ref)
-        batch = synth.make_reads(ref, a.reads, L, seed=int(rng.integers(1, 1 << 30)), max_del=int(rng.choice([200, 1000, 20000])))
         blob, off = batch.blob()
         prm = emul.make_params(lib, **st)
         out, pool = emul.search(lib, prm, [padded], blob, off, batch.matched_d, batch.matched_rel_pos, batch.insert_size)

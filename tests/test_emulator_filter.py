@@ -60,7 +60,7 @@ def run_both(lib, padded, batch, filter_min_pos=None, **settings):
     return exp, got
 
 
-@pytest.mark.parametrize("x,L,n,seed", [(3, 100, 60, 11), (4, 150, 40, 12), (5, 75, 24, 13)])
+@pytest.mark.parametrize("x,L,n,seed", [(3, 100, 600, 11), (4, 150, 400, 12), (5, 75, 240, 13), (6, 100, 120, 14)])
 def test_filter_rings_on_repetitive_reference(lib, x, L, n, seed):
     ref = repetitive_reference(400_000, seed)
     padded = synth.pad_reference(ref)

@@ -30,8 +30,8 @@ def mixed_batch(refs, rng, n_per, lens):
     return np.frombuffer(b"".join(seqs), dtype=np.uint8), off, md, pos, isz, chr_id
 
 
-@pytest.mark.parametrize("seed", [1, 2, 3, 4, 5, 6])
-def test_random_settings_and_mixed_lengths(seed):
+def fuzz_case(seed, n_per=350):
+    """-> (settings, padded chromosomes, blob, off, md, pos, isz, chr_id, regions (list of triples), region_off, lens)"""
     rng = np.random.default_rng(1000 + seed)
     settings = dict(max_range_index=int(rng.integers(0, 5)), additional_mismatch=int(rng.integers(1, 4)),
                     min_perfect_match=int(rng.integers(0, 8)), min_close=int(rng.integers(4, 14)),
@@ -41,7 +41,7 @@ def test_random_settings_and_mixed_lengths(seed):
                                  n_runs=[(int(rng.integers(20_000, 200_000)), int(rng.integers(1, 3000)))]) for _ in range(int(rng.integers(1, 4)))]
     padded = [synth.pad_reference(r) for r in refs]
     lens = rng.choice([40, 51, 64, 75, 100, 101, 150, 200, 251, 300], size=3, replace=False)
-    blob, off, md, pos, isz, chr_id = mixed_batch(refs, rng, 350, lens)
+    blob, off, md, pos, isz, chr_id = mixed_batch(refs, rng, n_per, lens)
     n = len(off) - 1
     regions, roff = [], [0]
     for i in range(n):
@@ -51,19 +51,33 @@ def test_random_settings_and_mixed_lengths(seed):
                 s = int(rng.integers(synth.SPACER, padded[c].size - synth.SPACER - 2000))
                 regions.append((c, s, s + int(rng.integers(50, 1800))))
         roff.append(len(regions))
+    return settings, padded, blob, off, md, pos, isz, chr_id, regions, np.array(roff, np.uint32), lens
+
+
+def region_array(regions):
     rg = np.zeros(len(regions), dtype=R.REGION_DT)
     if regions:
         a = np.array(regions)
         rg["chr"], rg["start"], rg["end"] = a[:, 0], a[:, 1], a[:, 2]
-    roff = np.array(roff, np.uint32)
-    pg = api.PatternGrowth(**settings)
-    pg.set_reference(padded)
-    out, runs = pg.search(seq_blob=blob, seq_off=off, matched_d=md, matched_rel_pos=pos, insert_size=isz, chr_id=chr_id,
-                          regions=rg, region_off=roff)
-    assert (out["flags"] & (R.F_TOOLONG | R.F_OVERFLOW)).sum() == 0
-    got = R.per_read(out, runs, blob, off)
+    return rg
+
+
+def oracle_answers(settings, padded, blob, off, md, pos, isz, chr_id, regions, roff):
     P = pgoracle.default_params(**settings)
     stream, _ = pgoracle.search(P, padded, blob, off, md, pos, isz, chr_id=chr_id,
                                 regions=np.array(regions, dtype=np.uint32).reshape(-1, 3), region_off=roff, threads=8)
-    H.compare(refhook.parse_stream(stream, n), got, "fuzz seed %d %s lens %s" % (seed, settings, lens.tolist()))
+    return refhook.parse_stream(stream, len(off) - 1)
+
+
+@pytest.mark.parametrize("seed", [1, 2, 3, 4, 5, 6])
+def test_random_settings_and_mixed_lengths(seed):
+    settings, padded, blob, off, md, pos, isz, chr_id, regions, roff, lens = fuzz_case(seed)
+    pg = api.PatternGrowth(**settings)
+    pg.set_reference(padded)
+    out, runs = pg.search(seq_blob=blob, seq_off=off, matched_d=md, matched_rel_pos=pos, insert_size=isz, chr_id=chr_id,
+                          regions=region_array(regions), region_off=roff)
+    assert (out["flags"] & (R.F_TOOLONG | R.F_OVERFLOW)).sum() == 0
+    got = R.per_read(out, runs, blob, off)
+    H.compare(oracle_answers(settings, padded, blob, off, md, pos, isz, chr_id, regions, roff), got,
+              "fuzz seed %d %s lens %s" % (seed, settings, lens.tolist()))
     pg.close()
