@@ -12,6 +12,28 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 
 
+def mixed(a):
+    from pindel_b200 import runs as R
+    from tests import helpers as H
+    from tests.emul import emul
+    from tests.test_gpu_fuzz import fuzz_case, oracle_answers, region_array
+    lib = emul.build()
+    names = dict(seq_error_rate="seq_error_rate", sensitivity="sensitivity", max_mismatch_rate="max_mismatch_rate",
+                 additional_mismatch="add_mm", min_close="min_close", min_perfect_match="min_perfect", max_range_index="max_range_index")
+    total = 0
+    for r in range(a.rounds):
+        seed = a.seed + r
+        settings, padded, blob, off, md, pos, isz, chr_id, regions, roff, lens = fuzz_case(seed, n_per=a.reads)
+        prm = emul.make_params(lib, **{names[k]: v for k, v in settings.items()})
+        out, pool = emul.search(lib, prm, padded, blob, off, md, pos, isz, chr_id=chr_id, regions=region_array(regions), region_off=roff)
+        assert (out["flags"] & (R.F_TOOLONG | R.F_OVERFLOW)).sum() == 0
+        H.compare(oracle_answers(settings, padded, blob, off, md, pos, isz, chr_id, regions, roff), R.per_read(out, pool, blob, off),
+                  "mixed seed %d %s lens %s" % (seed, settings, lens.tolist()))
+        total += len(off) - 1
+        print("round %d ok: seed %d, %d chromosomes, lens %s, %d clusters, %s" % (r, seed, len(padded), lens.tolist(), len(regions), settings), flush=True)
+    print("campaign clean: %d rounds, %d reads, mixed lengths / chromosomes / clusters, warp program (emulated) == oracle port" % (a.rounds, total))
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--rounds", type=int, default=12)
@@ -21,7 +43,11 @@ def main():
     ap.add_argument("--ref-len", type=int, nargs=2, default=[250_000, 400_000])
     ap.add_argument("--repetitive", action="store_true", help="references with near-identical repeats, low-complexity stretches and N runs "
                     "(tests/test_emulator_filter.py), reads with N: what stresses the far rings' filter")
+    ap.add_argument("--mixed", action="store_true", help="the GPU fuzz sweep's cases instead (tests/test_gpu_fuzz.py: mixed read lengths "
+                    "40..300 in one batch, 1-3 chromosomes, random clusters also on other chromosomes); --reads = reads per length and chromosome")
     a = ap.parse_args()
+    if a.mixed:
+        return mixed(a)
     from oracle import pgoracle, refhook
     from pindel_b200 import runs as R, synth
     from tests import helpers as H
