@@ -16,6 +16,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 SRC = os.path.join(ROOT, "tests", "cpp", "host_mirror_test.cpp")
 EXE = os.path.join(ROOT, "tests", "cpp", "host_mirror_test")
 LIBDIR = os.path.join(ROOT, "pindel_b200")
+EMUL_DIR = os.path.join(ROOT, "oracle", "_ref")
 
 
 def build_exe(src=SRC, exe=EXE):
@@ -76,9 +77,20 @@ def test_header_compiles_with_plain_gxx_and_fails_loudly_without_a_device(tmp_pa
     assert p.returncode == 1 and "no CUDA device" in p.stderr
 
 
+def build_emul_exe(src, tmp_path, name):
+    """the same program linked against the CPU emulation of the ABI (tests/emul/abi_emul.cpp) instead of libpindel_pg.so"""
+    exe = str(tmp_path / name)
+    subprocess.check_call(["/usr/bin/g++", "-O2", "-std=c++11", "-Wall", "-Wextra", "-o", exe, src, "-L" + EMUL_DIR, "-lpg_abi_emul",
+                           "-Wl,-rpath," + EMUL_DIR])
+    return exe
+
+
 @pytest.mark.gpu
 def test_cpp_mirror_matches_oracle(tmp_path):
-    exe = build_exe()
+    mirror_case(build_exe(), tmp_path)
+
+
+def mirror_case(exe, tmp_path):
     ref = synth.make_reference(500_000, 73, n_runs=[(200_000, 800)])
     padded = synth.pad_reference(ref)
     batch = synth.make_reads(ref, 3000, 100, seed=74)
@@ -110,9 +122,12 @@ def test_stage_mirrors_compile_and_fail_loudly_without_a_device(tmp_path):
 @pytest.mark.gpu
 def test_cpp_stage_mirrors_match_oracles(tmp_path):
     """ModifyRP / Summarize, SortBoxes and InflateBam / IndexBam of the C++ mirror against the oracles of their stages."""
+    stages_case(build_exe(STAGES_SRC, STAGES_EXE), tmp_path)
+
+
+def stages_case(exe, tmp_path):
     from oracle import boxsortoracle as B, rporacle
     from pindel_b200 import bam, bgzf
-    exe = build_exe(STAGES_SRC, STAGES_EXE)
     rows = synth.make_discordant_pairs(150, 41, span=3_000_000, background=200)
     reads, box_off, idx = B.make_boxes(300, 42)
     stream = bam.synthetic_stream(5000, 43)
@@ -153,7 +168,6 @@ def test_cpp_stage_mirrors_match_oracles(tmp_path):
 
 BD_SRC = os.path.join(ROOT, "tests", "cpp", "host_mirror_bd_test.cpp")
 BD_EXE = os.path.join(ROOT, "tests", "cpp", "host_mirror_bd_test")
-EMUL_DIR = os.path.join(ROOT, "oracle", "_ref")
 
 
 def bd_mirror_case(exe, tmp_path, seed):
@@ -182,6 +196,18 @@ def bd_mirror_case(exe, tmp_path, seed):
         pos += 3 * c
         assert got == (e or []), (seed, k, int(q[k]), e, got)
     assert pos == o.size
+
+
+@pytest.mark.skipif(not os.path.exists(os.path.join(EMUL_DIR, "libpg_abi_emul.so")), reason="oracle/_ref/libpg_abi_emul.so not built")
+def test_search_mirror_host_logic_on_the_emulated_abi(tmp_path):
+    """Searcher::GetCloseEnd / SearchFarEnds on SPLIT_READ vectors (marshalling into the SoA batch, runs back into UniquePoints,
+    CleanUniquePoints, the flipped reads) without a GPU: same program, same 3000 reads, same comparison as the GPU test"""
+    mirror_case(build_emul_exe(SRC, tmp_path, "host_mirror_test_emul"), tmp_path)
+
+
+@pytest.mark.skipif(not os.path.exists(os.path.join(EMUL_DIR, "libpg_abi_emul.so")), reason="oracle/_ref/libpg_abi_emul.so not built")
+def test_stage_mirrors_host_logic_on_the_emulated_abi(tmp_path):
+    stages_case(build_emul_exe(STAGES_SRC, tmp_path, "host_mirror_stages_test_emul"), tmp_path)
 
 
 @pytest.mark.skipif(not os.path.exists(os.path.join(EMUL_DIR, "libpg_abi_emul.so")), reason="oracle/_ref/libpg_abi_emul.so not built")
