@@ -13,7 +13,7 @@ export ASAN_OPTIONS=detect_leaks=0:halt_on_error=1 UBSAN_OPTIONS=print_stacktrac
 LD_PRELOAD="$(g++ -print-file-name=libasan.so) $(g++ -print-file-name=libubsan.so)" python -m pytest -x -q -p no:cacheprovider \
    tests/test_emulator.py tests/test_sv_emulator.py tests/test_rp_emulator.py tests/test_rp_discovery.py tests/test_bgzf_emulator.py \
    tests/test_bam_index_emulator.py tests/test_boxsort.py tests/test_sr_emulator.py tests/test_sr_fuzz.py tests/test_bd_emulator.py \
-   tests/test_emulator_filter.py
+   tests/test_emulator_filter.py tests/test_emulator_fuzz.py
 rc=$?
 rm -f $E/lib*_emul.so          # the next test run rebuilds the plain libraries
 exit $rc
