@@ -103,3 +103,29 @@ def test_final_sequence_replays_flips():
     assert R.final_sequence(b"MACG", 1) == b"CGT"              # leading IUPAC -> trailing NUL -> stripped
     assert R.final_sequence(b"ACGR", 2) == b"ACG"
     assert R.final_sequence(b"AMCG", 1) == b"CG\x00T"
+
+
+def test_header_is_plain_c(tmp_path):
+    """the boundary is a C ABI: include/pindel_pg.h must compile as C99 (-pedantic), which is what a cgo / JNI / ctypes-style
+    binding on the reference's side includes; and as C++ for the reference's own translation units"""
+    import subprocess
+    src = tmp_path / "t.c"
+    src.write_text('#include "pindel_pg.h"\nint main(void) { pg_settings s; (void)s; return PG_OK; }\n')
+    for cc, std in (("/usr/bin/gcc", "-std=c99"), ("/usr/bin/g++", "-std=c++11")):
+        lang = ["-x", "c++"] if cc.endswith("g++") else []
+        subprocess.check_call([cc, std, "-pedantic", "-Wall", "-Wextra", "-Werror", "-I" + os.path.join(ROOT, "include"), "-c"] + lang +
+                              [str(src), "-o", str(tmp_path / "t.o")])
+
+
+def test_emulated_abi_exports_what_the_bridge_binds():
+    """tests/emul/abi_emul.cpp stands in for the library under the drop-in bridge: every pg_* symbol the bridge object imports
+    must be declared in the header (the bridge uses nothing outside the published ABI)"""
+    import subprocess
+    obj = os.path.join(ROOT, "oracle", "_ref", "obj", "ref_gpu_bridge.o")
+    if not os.path.exists(obj):
+        pytest.skip("oracle/_ref not built")
+    out = subprocess.run(["nm", "-u", obj], capture_output=True, text=True, check=True).stdout
+    used = sorted(set(re.findall(r"\bU (pg_[a-z0-9_]+)\b", out)))
+    assert len(used) >= 15, used
+    missing = [s for s in used if s not in declared_symbols()]
+    assert not missing, "the bridge binds symbols the header does not declare: %s" % missing
