@@ -269,6 +269,7 @@ PGZ_FN int pgz_inflate(const uint8_t *in, uint32_t in_len, uint8_t *out, uint32_
             if (lane == 0) out[op] = v;
             op++;
          }
+         if (b.overrun > 2u) { rc = PGZ_ERR_INPUT; break; }     // LEN reaches past the end of the input
          continue;
       }
       if (type == 3) { rc = PGZ_ERR_HEADER; break; }
@@ -356,6 +357,10 @@ PGZ_FN int pgz_inflate(const uint8_t *in, uint32_t in_len, uint8_t *out, uint32_
    }
    PGZ_SYNC();
    *produced = op;
+   // Every bit the decoder consumed must lie inside the input: beyond it the bit buffer delivers zeros (the look-ahead of one
+   // or two words is harmless, decoding from there is not), so a stream that stops early -- cut off, or a damaged length
+   // that carries a block over the end -- is refused exactly, as zlib refuses it for want of input.
+   if (rc == PGZ_OK && 32ull * b.next_word - b.cnt > 8ull * ((uint64_t)mis + in_len)) rc = PGZ_ERR_INPUT;
    if (rc == PGZ_OK && op != isize) rc = PGZ_ERR_SIZE;
    return rc;
 }

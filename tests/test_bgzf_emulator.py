@@ -213,3 +213,35 @@ def test_incomplete_code_sets_are_judged_like_zlib(lib):
     exp = _zlib_raw(raw)
     rc, got = bgzf_emul.inflate_raw(lib, raw, 4)
     assert exp == b"AAAA" and rc == 0 and got == exp
+
+
+def test_damaged_streams_are_judged_like_zlib_without_the_crc(lib):
+    """scripts/bgzf_corruption_campaign.py in small: bit flips, overwritten bytes, truncations and random block headers in raw
+    DEFLATE streams of every block type -- zlib inflates the damaged stream completely to ISIZE bytes <=> the inflater returns
+    PGZ_OK with the same bytes; nothing is decoded from beyond the end of the input (a stored block whose LEN reaches past a
+    cut-off stream was once filled with the zeros the bit buffer delivers there)."""
+    import sys
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "scripts"))
+    import bgzf_corruption_campaign as camp
+    rng = np.random.default_rng(77)
+    streams = []
+    for level, strategy in ((1, zlib.Z_DEFAULT_STRATEGY), (6, zlib.Z_DEFAULT_STRATEGY), (6, zlib.Z_FIXED), (6, zlib.Z_HUFFMAN_ONLY), (0, zlib.Z_DEFAULT_STRATEGY)):
+        for size in (300, 5000):
+            payload = bam_like(size, 300 + level + size)
+            c = zlib.compressobj(level, zlib.DEFLATED, -15, 9, strategy)
+            streams.append((c.compress(payload) + c.flush(), payload))
+    both_ok = both_bad = 0
+    for _ in range(6000):
+        raw, payload = streams[int(rng.integers(0, len(streams)))]
+        bad = camp.damage(rng, raw)
+        exp = camp.zlib_raw(bad, len(payload))
+        rc, got = bgzf_emul.inflate_raw(lib, bad, len(payload))
+        assert (rc == 0) == (exp is not None) and (exp is None or got == exp), (rc, exp is None)
+        both_ok += exp is not None
+        both_bad += exp is None
+    assert both_ok > 500 and both_bad > 2000
+    # the stored block cut off in the middle: LEN says 5000, 100 bytes are there
+    raw, payload = streams[-1]
+    assert raw[0] & 6 == 0 and bgzf_emul.inflate_raw(lib, raw, len(payload)) == (0, payload)
+    rc, _ = bgzf_emul.inflate_raw(lib, raw[:105], len(payload))
+    assert rc == 5 and camp.zlib_raw(raw[:105], len(payload)) is None          # PGZ_ERR_INPUT
