@@ -73,14 +73,14 @@ PGB_HD int32_t pgb_ref_span(const uint8_t *rec, uint64_t rec_len)
    uint32_t n_cigar = pgb_le16(rec + 12);
    const uint8_t *cig = rec + 32 + l_name;
    if (32ull + l_name + 4ull * n_cigar > rec_len) n_cigar = 32ull + l_name >= rec_len ? 0u : (uint32_t)((rec_len - 32ull - l_name) / 4ull);
-   int32_t span = 0;
+   uint32_t span = 0;                   // (unsigned: the lengths of a damaged CIGAR may sum past 2^31; wraps like the device's add)
    if (!(flag & 4u)) {
       for (uint32_t k = 0; k < n_cigar; k++) {
          const uint32_t c = pgb_le32(cig + 4 * k), op = c & 15u;
-         if (op == 0u || op == 2u || op == 3u || op == 7u || op == 8u) span += (int32_t)(c >> 4);
+         if (op == 0u || op == 2u || op == 3u || op == 7u || op == 8u) span += c >> 4;
       }
    }
-   return span > 0 ? span : 1;
+   return (int32_t)span > 0 ? (int32_t)span : 1;
 }
 
 PGB_HD void pgb_fill(const uint8_t *d, uint64_t c, PgBamRec &r)
@@ -89,7 +89,7 @@ PGB_HD void pgb_fill(const uint8_t *d, uint64_t c, PgBamRec &r)
    r.off = c;
    r.tid = (int32_t)pgb_le32(rec);
    r.pos = (int32_t)pgb_le32(rec + 4);
-   r.end = r.pos + pgb_ref_span(rec, (uint64_t)pgb_le32(d + c));
+   r.end = (int32_t)((uint32_t)r.pos + (uint32_t)pgb_ref_span(rec, (uint64_t)pgb_le32(d + c)));
    r.flag = (uint16_t)pgb_le16(rec + 14);
    r.mapq = rec[9];
    r.pad = 0;
