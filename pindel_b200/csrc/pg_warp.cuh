@@ -431,7 +431,7 @@ PG_DEV void pg_scan_window(PgWarpCtx<LW, TL> &cx, const PgSearch &se, int chr_id
       const int64_t w1 = (int64_t)((te - 1) >> 5) + 2;          // exclusive
       const int nw = (int)(((w1 - w0) + 3) & ~(int64_t)3);
       pg_tile_load<LW, TL>(ws, chrom, w0, nw, phase);
-      const uint32_t origin = (uint32_t)(w0 << 5);              // absolute position of tile word 0, bit 0 (w0 >= -4)
+      const uint32_t origin = (uint32_t)(w0 * 32);              // absolute position of tile word 0, bit 0 (w0 >= -4: taken modulo 2^32)
       bool filt = false;
       if (TL <= 16 && filter) {
          // the thresholds only move when a survivor was merged into the state
