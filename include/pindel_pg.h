@@ -479,7 +479,9 @@ double pg_rp_last_kernel_ms(pg_ctx *ctx);      /* CUDA-event duration of the las
  * blocks bit by bit), and nothing is decoded from beyond the end of a block's compressed bytes (a cut-off stream, or a stored
  * block whose LEN reaches past it, is "compressed data exhausted").  On 400 000 randomly damaged streams of every block type the
  * decoder and zlib agree in every case on refuse / inflate and on the bytes (scripts/bgzf_corruption_campaign.py).
- * check_crc = 1 is what htslib does on every block and is the setting of the drop-in.
+ * check_crc = 1 is what htslib does on every block and is the setting of the drop-in.  Block headers are judged as htslib's
+ * check_header judges them (magic, CM = 8, FLG & 4, a 'B','C' subfield of length 2 in the extra field; the other flag bits are not
+ * looked at), so a file refused here is one htslib refuses to read as BGZF.
  * ------------------------------------------------------------------------------------------------------------------ */
 int64_t pg_bgzf_inflated_size(const uint8_t *file, size_t file_len);   /* host only: -1 if the header walk fails */
 int pg_bgzf_inflate(pg_ctx *ctx, const uint8_t *file, size_t file_len, uint8_t *out, size_t out_cap, size_t *out_len, int32_t check_crc);
