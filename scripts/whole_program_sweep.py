@@ -40,6 +40,9 @@ def draw(seed):
     return [str(x) for x in a]
 
 
+DROPIN_THREADS = 1
+
+
 def one(seed):
     args = draw(seed)
     tmp = tempfile.mkdtemp(prefix="pgsweep_")
@@ -47,12 +50,12 @@ def one(seed):
     r = subprocess.run([REF_BIN] + args + ["-T", "1", "-o", os.path.join(tmp, "ref")], cwd=cwd, capture_output=True, text=True)
     if r.returncode != 0:
         return seed, args, "reference failed: " + (r.stdout + r.stderr)[-400:], 0
-    p = subprocess.run([DEMO_BIN] + args + ["-T", "1", "-o", os.path.join(tmp, "got")], cwd=cwd, capture_output=True, text=True,
+    p = subprocess.run([DEMO_BIN] + args + ["-T", str(DROPIN_THREADS), "-o", os.path.join(tmp, "got")], cwd=cwd, capture_output=True, text=True,
                        env=dict(os.environ, PG_EMUL_THREADS="3"))
     if p.returncode != 0:
         return seed, args, "drop-in failed: " + (p.stdout + p.stderr)[-400:], 0
     total = 0
-    for suf in ALL:
+    for suf in (ALL if DROPIN_THREADS == 1 else ("D", "SI", "INV", "TD", "LI", "BP")):     # (_RP: the host's own OpenMP loop orders its lines)
         a, b = (open(os.path.join(tmp, k + "_" + suf), "rb").read() if os.path.exists(os.path.join(tmp, k + "_" + suf)) else None for k in ("ref", "got"))
         if a != b:
             return seed, args, "_%s differs (%s vs %s bytes)" % (suf, a and len(a), b and len(b)), 0
@@ -65,7 +68,11 @@ def main():
     ap.add_argument("--rounds", type=int, default=12)
     ap.add_argument("--seed", type=int, default=1)
     ap.add_argument("--jobs", type=int, default=3)
+    ap.add_argument("--dropin-threads", type=int, default=1, help="-T of the drop-in (the reference always runs with -T 1, the only "
+                    "count at which its files are reproducible); above 1 the event files are compared, _RP is not")
     a = ap.parse_args()
+    global DROPIN_THREADS
+    DROPIN_THREADS = a.dropin_threads
     assert os.path.exists(REF_BIN) and os.path.exists(DEMO_BIN) and os.path.isdir(SMALL), "needs /root/reference and oracle/_ref"
     bad, nbytes, nonempty = [], 0, 0
     with cf.ThreadPoolExecutor(a.jobs) as ex:
