@@ -1,4 +1,4 @@
-"""tests/golden/make_demo_golden.py -- writes tests/golden/reference_whole_program_sha256.json: the SHA-256 of every output
+"""tests/golden/make_whole_program_golden.py -- writes tests/golden/reference_whole_program_sha256.json: the SHA-256 of every output
 file the PURE reference binary (oracle/_ref/pindel_ref, built from the untouched sources) writes for whole-program commands of
 the reference's own that have no usable committed golden:
 
@@ -10,7 +10,7 @@ the reference's own that have no usable committed golden:
                   not reproduce them -- SURVEY.md section 4 -- so the reference binary built here is the golden)
 
 all with one thread: the reference's files depend on its thread count (reads are filed from inside OpenMP loops) and -T 1 is
-what its own scripts pin.  Needs /root/reference; takes a few minutes.      python tests/golden/make_demo_golden.py"""
+what its own scripts pin.  Needs /root/reference; takes a few minutes.      python tests/golden/make_whole_program_golden.py"""
 import hashlib
 import json
 import os

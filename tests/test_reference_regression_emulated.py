@@ -8,7 +8,7 @@ oracle/_ref/pindel_emul_demo), at the inputs' full size:
   * demo/RUNME (BASELINE.json configs[0])   pindel -i simulated_config.txt -f simulated_reference.fa -c ALL  (three BAMs)
   * src/update_target_files.sh:10-15        the whole COLO-829 file, -c 20:0-1,500,000 -x 5 -B 100 -u 0.05 -b <BreakDancer file>
     both against the SHA-256 of the files the pure reference binary writes (tests/golden/reference_whole_program_sha256.json,
-    made by tests/golden/make_demo_golden.py; the committed test/SmallTest/TargetOutput/ is from an older Pindel);
+    made by tests/golden/make_whole_program_golden.py; the committed test/SmallTest/TargetOutput/ is from an older Pindel);
   * the simulated BAM input with an external BreakDancer file (-b), the pure reference binary beside the drop-in.
 
 Every stage of SURVEY.md section 8 runs in these: close and far ends (the warp program on the lane emulator), the SV drivers,
