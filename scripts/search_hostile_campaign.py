@@ -22,7 +22,10 @@ def main():
     ap.add_argument("--rounds", type=int, default=200)
     ap.add_argument("--reads", type=int, default=300)
     ap.add_argument("--seed", type=int, default=1)
-    a = ap.parse_args()
+    run(ap.parse_args())
+
+
+def run(a):
     from pindel_b200 import runs as R, synth
     from tests.emul import emul
     lib = emul.build(force=bool(os.environ.get("PG_EMUL_CXXFLAGS")))
@@ -92,6 +95,7 @@ def main():
             print("round %d ok" % r, flush=True)
     print("campaign clean: %d rounds, %d hostile reads (%d came back with runs, %d refused by flag); no crash%s" %
           (a.rounds, total, with_runs, flagged, ", no sanitizer report" if "asan" in os.environ.get("LD_PRELOAD", "") else ""))
+    return total, with_runs
 
 
 if __name__ == "__main__":
