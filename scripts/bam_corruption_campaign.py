@@ -48,7 +48,10 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--rounds", type=int, default=300)
     ap.add_argument("--seed", type=int, default=1)
-    a = ap.parse_args()
+    run(ap.parse_args())
+
+
+def run(a):
     from pindel_b200 import bam
     from tests import sr_fuzz_helpers as F
     from tests.emul import bam_emul, sr_emul
@@ -78,6 +81,7 @@ def main():
     print("campaign clean: %d damaged streams (%d indexed, %d refused by the index), %d pair rows and %d split-read candidates produced, "
           "%d filter calls ended with the program's own error flag; no crash%s" %
           (a.rounds, indexed, refused, rows, cands, flagged, ", no sanitizer report" if "asan" in os.environ.get("LD_PRELOAD", "") else ""))
+    return indexed, rows, cands, flagged
 
 
 if __name__ == "__main__":

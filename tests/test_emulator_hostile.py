@@ -13,3 +13,11 @@ def test_hostile_batches_terminate_and_stay_inside_their_buffers():
     import search_hostile_campaign as camp
     total, with_runs = camp.run(argparse.Namespace(rounds=12, reads=300, seed=11))
     assert total == 3600 and with_runs > 50
+
+
+def test_damaged_bam_records_end_in_error_flags_not_in_a_crash():
+    """scripts/bam_corruption_campaign.py in small: record index, pair discovery and split-read filter (host builds) on streams
+    whose records are damaged behind an intact block_size chain; under the sanitizers: scripts/sanitize_bam_corruption.sh"""
+    import bam_corruption_campaign as camp
+    indexed, rows, cands, flagged = camp.run(argparse.Namespace(rounds=25, seed=21))
+    assert indexed == 25 and rows > 1000 and cands > 1000 and flagged > 0
